@@ -1,0 +1,461 @@
+// GPU BVH build for the closest-hit / any-hit kernels: replaces rtcCommitScene
+// (reference src/librender/scene.cpp:201-212, Embree 3.12.2 SAH builder).
+//
+// Pipeline (all on the device, one stream):
+//   1. k_tri_setup   gather each triangle's three positions (+prim, geom ids), reduce centroid bounds
+//   2. k_morton      63-bit Morton code of the centroid
+//   3. radix sort    (cub::DeviceRadixSort, build-time plumbing)
+//   4. k_karras      binary radix tree over the sorted codes (Karras 2012)
+//   5. k_refit       bottom-up AABBs with one atomic flag per internal node
+//   6. k_collapse    level-synchronous top-down collapse of the binary tree into 8-wide nodes
+//                    with 8-bit quantised child boxes (80 B per node, five 128-bit loads),
+//                    children placed in octant-ordered slots (Ylitie, Karras, Laine 2017)
+#include "msk_device.cuh"
+#include "msk_bvh.h"
+
+#include <cub/cub.cuh>
+#include <cfloat>
+#include <vector>
+
+namespace msk {
+
+namespace {
+
+constexpr int kThreads = 256;
+inline unsigned blocks_for(size_t n) { return (unsigned) ((n + kThreads - 1) / kThreads); }
+
+// float <-> order-preserving uint for atomicMin/atomicMax
+__device__ __forceinline__ uint32_t f2ord(float f) {
+    uint32_t u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__host__ __device__ __forceinline__ float ord2f(uint32_t u) {
+    uint32_t v = (u & 0x80000000u) ? (u & 0x7fffffffu) : ~u;
+#ifdef __CUDA_ARCH__
+    return __uint_as_float(v);
+#else
+    float f; memcpy(&f, &v, 4); return f;
+#endif
+}
+
+struct BuildState {
+    uint32_t cmin[3], cmax[3];   // centroid bounds (ordered uints)
+    uint32_t node_count;         // wide nodes allocated
+    uint32_t tri_count;          // triangles emitted into leaf order
+    uint32_t queue_count;        // items produced for the next level
+    uint32_t overflow;
+};
+
+__global__ void k_init_state(BuildState *st) {
+    for (int a = 0; a < 3; ++a) { st->cmin[a] = 0xffffffffu; st->cmax[a] = 0u; }
+    st->node_count = 1; st->tri_count = 0; st->queue_count = 0; st->overflow = 0;
+}
+
+// one launch per mesh: gathers vertices of its triangles into build order
+__global__ void k_tri_setup(const float4 *__restrict__ verts, const uint32_t *__restrict__ indices, uint32_t vert_offset,
+                            uint32_t tri_offset, uint32_t ntris, uint32_t geom, float4 *__restrict__ gathered,
+                            BuildState *st) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    float cx = 0, cy = 0, cz = 0;
+    bool valid = i < ntris;
+    if (valid) {
+        uint32_t g = tri_offset + i;
+        uint32_t i0 = indices[3 * (size_t) g], i1 = indices[3 * (size_t) g + 1], i2 = indices[3 * (size_t) g + 2];
+        float4 a = verts[2 * (size_t) (vert_offset + i0)], b = verts[2 * (size_t) (vert_offset + i1)],
+               c = verts[2 * (size_t) (vert_offset + i2)];
+        gathered[3 * (size_t) g + 0] = make_float4(a.x, a.y, a.z, __uint_as_float(i));
+        gathered[3 * (size_t) g + 1] = make_float4(b.x, b.y, b.z, __uint_as_float(geom));
+        gathered[3 * (size_t) g + 2] = make_float4(c.x, c.y, c.z, 0.f);
+        cx = 0.5f * (fminf(a.x, fminf(b.x, c.x)) + fmaxf(a.x, fmaxf(b.x, c.x)));
+        cy = 0.5f * (fminf(a.y, fminf(b.y, c.y)) + fmaxf(a.y, fmaxf(b.y, c.y)));
+        cz = 0.5f * (fminf(a.z, fminf(b.z, c.z)) + fmaxf(a.z, fmaxf(b.z, c.z)));
+    }
+    // warp reduce, then one atomic per warp and axis
+    float mn[3] = { valid ? cx : FLT_MAX, valid ? cy : FLT_MAX, valid ? cz : FLT_MAX };
+    float mx[3] = { valid ? cx : -FLT_MAX, valid ? cy : -FLT_MAX, valid ? cz : -FLT_MAX };
+    for (int a = 0; a < 3; ++a)
+        for (int o = 16; o; o >>= 1) {
+            mn[a] = fminf(mn[a], __shfl_xor_sync(0xffffffffu, mn[a], o));
+            mx[a] = fmaxf(mx[a], __shfl_xor_sync(0xffffffffu, mx[a], o));
+        }
+    if ((threadIdx.x & 31) == 0 && mn[0] != FLT_MAX)
+        for (int a = 0; a < 3; ++a) { atomicMin(&st->cmin[a], f2ord(mn[a])); atomicMax(&st->cmax[a], f2ord(mx[a])); }
+}
+
+__device__ __forceinline__ uint64_t expand21(uint32_t v) { // spread 21 bits to every third bit
+    uint64_t x = v & 0x1fffffu;
+    x = (x | x << 32) & 0x1f00000000ffffull;
+    x = (x | x << 16) & 0x1f0000ff0000ffull;
+    x = (x | x << 8) & 0x100f00f00f00f00full;
+    x = (x | x << 4) & 0x10c30c30c30c30c3ull;
+    x = (x | x << 2) & 0x1249249249249249ull;
+    return x;
+}
+
+__global__ void k_morton(const float4 *__restrict__ gathered, uint32_t n, const BuildState *st, uint64_t *__restrict__ keys,
+                         uint32_t *__restrict__ vals) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float4 a = gathered[3 * (size_t) i], b = gathered[3 * (size_t) i + 1], c = gathered[3 * (size_t) i + 2];
+    float ctr[3] = { 0.5f * (fminf(a.x, fminf(b.x, c.x)) + fmaxf(a.x, fmaxf(b.x, c.x))),
+                     0.5f * (fminf(a.y, fminf(b.y, c.y)) + fmaxf(a.y, fmaxf(b.y, c.y))),
+                     0.5f * (fminf(a.z, fminf(b.z, c.z)) + fmaxf(a.z, fmaxf(b.z, c.z))) };
+    uint32_t q[3];
+    for (int k = 0; k < 3; ++k) {
+        float lo = ord2f(st->cmin[k]), hi = ord2f(st->cmax[k]);
+        float ext = hi - lo;
+        float t = ext > 0.f ? (ctr[k] - lo) / ext : 0.f;
+        q[k] = (uint32_t) fminf(fmaxf(t * 2097152.f, 0.f), 2097151.f);
+    }
+    keys[i] = (expand21(q[0]) << 2) | (expand21(q[1]) << 1) | expand21(q[2]);
+    vals[i] = i;
+}
+
+// ---- binary radix tree (Karras 2012).  Internal nodes 0..n-2, leaves n-1..2n-2. ----
+struct Bvh2 {
+    uint32_t *left, *right, *parent; // per internal node (parent: per node, 2n-1)
+    uint32_t *first, *last;          // per internal node: covered range of sorted leaves
+    float4 *lo, *hi;                 // per node (2n-1)
+    uint32_t *flags;                 // per internal node, refit arrival counter
+};
+
+__device__ __forceinline__ int delta(const uint64_t *keys, int n, int i, int j) {
+    if (j < 0 || j >= n) return -1;
+    uint64_t a = keys[i], b = keys[j];
+    if (a == b) return 64 + __clz((uint32_t) i ^ (uint32_t) j);
+    return __clzll((long long) (a ^ b));
+}
+
+__global__ void k_karras(const uint64_t *__restrict__ keys, int n, Bvh2 t) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n - 1) return;
+    int d     = (delta(keys, n, i, i + 1) - delta(keys, n, i, i - 1)) >= 0 ? 1 : -1;
+    int dmin  = delta(keys, n, i, i - d);
+    int lmax  = 2;
+    while (delta(keys, n, i, i + lmax * d) > dmin) lmax <<= 1;
+    int l = 0;
+    for (int s = lmax >> 1; s >= 1; s >>= 1)
+        if (delta(keys, n, i, i + (l + s) * d) > dmin) l += s;
+    int j     = i + l * d;
+    int dnode = delta(keys, n, i, j);
+    int s = 0, tt = l;
+    do {
+        tt = (tt + 1) >> 1;
+        if (delta(keys, n, i, i + (s + tt) * d) > dnode) s += tt;
+    } while (tt > 1);
+    int gamma = i + s * d + min(d, 0);
+    int lo = min(i, j), hi = max(i, j);
+    uint32_t lc = (lo == gamma) ? (uint32_t) (n - 1 + gamma) : (uint32_t) gamma;
+    uint32_t rc = (hi == gamma + 1) ? (uint32_t) (n - 1 + gamma + 1) : (uint32_t) (gamma + 1);
+    t.left[i] = lc; t.right[i] = rc;
+    t.parent[lc] = i; t.parent[rc] = i;
+    t.first[i] = lo; t.last[i] = hi;
+    if (i == 0) t.parent[0] = 0xffffffffu;
+}
+
+__global__ void k_refit(const float4 *__restrict__ gathered, const uint32_t *__restrict__ sorted, int n, Bvh2 t) {
+    int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    uint32_t tri = sorted[j];
+    float4 a = gathered[3 * (size_t) tri], b = gathered[3 * (size_t) tri + 1], c = gathered[3 * (size_t) tri + 2];
+    float4 lo = make_float4(fminf(a.x, fminf(b.x, c.x)), fminf(a.y, fminf(b.y, c.y)), fminf(a.z, fminf(b.z, c.z)), 0.f);
+    float4 hi = make_float4(fmaxf(a.x, fmaxf(b.x, c.x)), fmaxf(a.y, fmaxf(b.y, c.y)), fmaxf(a.z, fmaxf(b.z, c.z)), 0.f);
+    uint32_t node = n - 1 + j;
+    t.lo[node] = lo; t.hi[node] = hi;
+    if (n == 1) return;
+    uint32_t p = t.parent[node];
+    while (p != 0xffffffffu) {
+        __threadfence();
+        if (atomicAdd(&t.flags[p], 1u) == 0) return; // first arrival: the sibling will finish this node
+        uint32_t l = t.left[p], r = t.right[p];
+        // .cg loads: the sibling's stores were made visible by its fence + the atomic
+        float4 llo = __ldcg(&t.lo[l]), lhi = __ldcg(&t.hi[l]), rlo = __ldcg(&t.lo[r]), rhi = __ldcg(&t.hi[r]);
+        lo = make_float4(fminf(llo.x, rlo.x), fminf(llo.y, rlo.y), fminf(llo.z, rlo.z), 0.f);
+        hi = make_float4(fmaxf(lhi.x, rhi.x), fmaxf(lhi.y, rhi.y), fmaxf(lhi.z, rhi.z), 0.f);
+        t.lo[p] = lo; t.hi[p] = hi;
+        p = t.parent[p];
+    }
+}
+
+__device__ __forceinline__ float half_area(float4 lo, float4 hi) {
+    float dx = hi.x - lo.x, dy = hi.y - lo.y, dz = hi.z - lo.z;
+    return dx * dy + dy * dz + dz * dx;
+}
+
+__device__ __forceinline__ uint32_t node_count(const Bvh2 &t, int n, uint32_t node) {
+    return node >= (uint32_t) (n - 1) ? 1u : t.last[node] - t.first[node] + 1u;
+}
+__device__ __forceinline__ uint32_t node_first(const Bvh2 &t, int n, uint32_t node) {
+    return node >= (uint32_t) (n - 1) ? node - (uint32_t) (n - 1) : t.first[node];
+}
+
+// exponent byte e such that 2^(e-127) >= extent / 255
+__device__ __forceinline__ uint32_t quant_exp(float extent) {
+    float s = extent / 255.f;
+    uint32_t u = __float_as_uint(s);
+    uint32_t e = (u >> 23) & 0xffu;
+    if (u & 0x7fffffu) e += 1;
+    return min(max(e, 1u), 254u);
+}
+
+struct WorkItem { uint32_t bvh2, wide; };
+
+// One thread builds one wide node from the binary subtree rooted at item.bvh2.
+__global__ void k_collapse(const WorkItem *__restrict__ in, uint32_t nin, WorkItem *__restrict__ out, uint32_t out_cap,
+                           Bvh2 t, int n, const uint32_t *__restrict__ sorted, const float4 *__restrict__ gathered,
+                           float4 *__restrict__ nodes, uint32_t node_cap, float4 *__restrict__ tris, BuildState *st,
+                           int root_is_leaf) {
+    uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= nin) return;
+    WorkItem item = in[w];
+    uint32_t cand[8];
+    int nc = 0;
+    if (root_is_leaf) {
+        cand[nc++] = item.bvh2; // n == 1: the single triangle
+    } else {
+        cand[nc++] = t.left[item.bvh2];
+        cand[nc++] = t.right[item.bvh2];
+        // greedily open the largest-area internal candidate while slots remain
+        while (nc < 8) {
+            int best = -1;
+            float best_area = -1.f;
+            for (int i = 0; i < nc; ++i) {
+                if (cand[i] >= (uint32_t) (n - 1)) continue; // single triangle
+                float a = half_area(t.lo[cand[i]], t.hi[cand[i]]);
+                if (a > best_area) { best_area = a; best = i; }
+            }
+            if (best < 0) break;
+            uint32_t o = cand[best];
+            cand[best] = t.left[o];
+            cand[nc++] = t.right[o];
+        }
+    }
+    float4 plo = t.lo[item.bvh2], phi = t.hi[item.bvh2];
+    float pc[3] = { 0.5f * (plo.x + phi.x), 0.5f * (plo.y + phi.y), 0.5f * (plo.z + phi.z) };
+    // octant-ordered slot assignment: slot s prefers the child furthest along d_s = (s&4 ? + : -, s&2 ? + : -, s&1 ? + : -)
+    float cost[8][8];
+    float4 clo[8], chi[8];
+    for (int c = 0; c < nc; ++c) {
+        clo[c] = t.lo[cand[c]]; chi[c] = t.hi[cand[c]];
+        float dx = 0.5f * (clo[c].x + chi[c].x) - pc[0], dy = 0.5f * (clo[c].y + chi[c].y) - pc[1],
+              dz = 0.5f * (clo[c].z + chi[c].z) - pc[2];
+        for (int s = 0; s < 8; ++s)
+            cost[c][s] = ((s & 4) ? dx : -dx) + ((s & 2) ? dy : -dy) + ((s & 1) ? dz : -dz);
+    }
+    int slot_child[8];
+    for (int s = 0; s < 8; ++s) slot_child[s] = -1;
+    uint32_t child_done = 0, slot_done = 0;
+    for (int k = 0; k < nc; ++k) {
+        float best = -FLT_MAX; int bc = -1, bs = -1;
+        for (int c = 0; c < nc; ++c) {
+            if (child_done & (1u << c)) continue;
+            for (int s = 0; s < 8; ++s) {
+                if (slot_done & (1u << s)) continue;
+                if (cost[c][s] > best) { best = cost[c][s]; bc = c; bs = s; }
+            }
+        }
+        slot_child[bs] = bc; child_done |= 1u << bc; slot_done |= 1u << bs;
+    }
+    // classify, count
+    uint32_t imask = 0, ninner = 0, ntri = 0;
+    for (int s = 0; s < 8; ++s) {
+        int c = slot_child[s];
+        if (c < 0) continue;
+        uint32_t cnt = node_count(t, n, cand[c]);
+        if (cnt > (uint32_t) kMaxLeafTris) { imask |= 1u << s; ninner++; } else ntri += cnt;
+    }
+    uint32_t child_base = ninner ? atomicAdd(&st->node_count, ninner) : 0u;
+    uint32_t tri_base   = ntri ? atomicAdd(&st->tri_count, ntri) : 0u;
+    uint32_t qbase      = ninner ? atomicAdd(&st->queue_count, ninner) : 0u;
+    if (child_base + ninner > node_cap || qbase + ninner > out_cap) { st->overflow = 1; return; }
+
+    uint32_t ex = quant_exp(phi.x - plo.x), ey = quant_exp(phi.y - plo.y), ez = quant_exp(phi.z - plo.z);
+    float sx = __uint_as_float(ex << 23), sy = __uint_as_float(ey << 23), sz = __uint_as_float(ez << 23);
+    uint32_t meta[2] = { 0, 0 }, q[6][2] = {};
+    uint32_t inner_rank = 0, tri_off = 0;
+    for (int s = 0; s < 8; ++s) {
+        int c = slot_child[s];
+        if (c < 0) continue;
+        uint32_t node = cand[c];
+        uint32_t cnt  = node_count(t, n, node);
+        uint32_t m;
+        if (imask & (1u << s)) {
+            m = (1u << 5) | (24u + s);
+            out[qbase + inner_rank] = WorkItem{ node, child_base + inner_rank };
+            inner_rank++;
+        } else {
+            m = (((1u << cnt) - 1u) << 5) | tri_off;
+            uint32_t f = node_first(t, n, node);
+            for (uint32_t k = 0; k < cnt; ++k) {
+                uint32_t tri = sorted[f + k];
+                size_t dst = 3 * (size_t) (tri_base + tri_off + k);
+                tris[dst + 0] = gathered[3 * (size_t) tri + 0];
+                tris[dst + 1] = gathered[3 * (size_t) tri + 1];
+                tris[dst + 2] = gathered[3 * (size_t) tri + 2];
+            }
+            tri_off += cnt;
+        }
+        meta[s >> 2] |= m << (8 * (s & 3));
+        // conservative 8-bit quantisation against the grid origin plo with cell size 2^e
+        float lo3[3] = { clo[c].x, clo[c].y, clo[c].z }, hi3[3] = { chi[c].x, chi[c].y, chi[c].z };
+        float p3[3] = { plo.x, plo.y, plo.z }, s3[3] = { sx, sy, sz };
+        for (int a = 0; a < 3; ++a) {
+            int ql = (int) floorf((lo3[a] - p3[a]) / s3[a]);
+            int qh = (int) ceilf((hi3[a] - p3[a]) / s3[a]);
+            ql = min(max(ql, 0), 255); qh = min(max(qh, 0), 255);
+            while (ql > 0 && p3[a] + (float) ql * s3[a] > lo3[a]) --ql;
+            while (qh < 255 && p3[a] + (float) qh * s3[a] < hi3[a]) ++qh;
+            q[a][s >> 2] |= (uint32_t) ql << (8 * (s & 3));
+            q[3 + a][s >> 2] |= (uint32_t) qh << (8 * (s & 3));
+        }
+    }
+    float4 *dst = nodes + (size_t) item.wide * kNodeFloat4s;
+    dst[0] = make_float4(plo.x, plo.y, plo.z, __uint_as_float(ex | (ey << 8) | (ez << 16) | (imask << 24)));
+    dst[1] = make_float4(__uint_as_float(child_base), __uint_as_float(tri_base), __uint_as_float(meta[0]), __uint_as_float(meta[1]));
+    dst[2] = make_float4(__uint_as_float(q[0][0]), __uint_as_float(q[0][1]), __uint_as_float(q[1][0]), __uint_as_float(q[1][1]));
+    dst[3] = make_float4(__uint_as_float(q[2][0]), __uint_as_float(q[2][1]), __uint_as_float(q[3][0]), __uint_as_float(q[3][1]));
+    dst[4] = make_float4(__uint_as_float(q[4][0]), __uint_as_float(q[4][1]), __uint_as_float(q[5][0]), __uint_as_float(q[5][1]));
+}
+
+__global__ void k_empty_root(float4 *nodes) { // scene without triangles: every ray misses
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        nodes[0] = make_float4(0.f, 0.f, 0.f, __uint_as_float(1u | (1u << 8) | (1u << 16)));
+        for (int i = 1; i < kNodeFloat4s; ++i) nodes[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+}
+
+// sum of (area(child)/area(root)) over wide nodes and leaves: an SAH-style quality figure
+__global__ void k_sah(const Bvh2 t, int n, float *out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    float v = 0.f;
+    if (i < n - 1) v = half_area(t.lo[i], t.hi[i]);
+    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0 && v != 0.f) atomicAdd(out, v);
+}
+
+template <typename T> cudaError_t dalloc(T **p, size_t n) { return cudaMalloc((void **) p, std::max<size_t>(n, 1) * sizeof(T)); }
+
+} // namespace
+
+int bvh_build(cudaStream_t stream, const float4 *d_verts, const uint32_t *d_indices, const std::vector<DMeshInfo> &meshes,
+              BvhResult *out) {
+    *out = BvhResult{};
+    size_t n = 0;
+    for (auto &m : meshes) n += m.ntris;
+    if (n > 0x7ffffff0ull) return fail(MSK_ERR_UNSUPPORTED, "too many triangles (%zu)", n);
+    cudaEvent_t e0, e1;
+    MSK_CUDA_CHECK(cudaEventCreate(&e0));
+    MSK_CUDA_CHECK(cudaEventCreate(&e1));
+    MSK_CUDA_CHECK(cudaEventRecord(e0, stream));
+
+    size_t node_cap = n ? (size_t) (0.66 * (double) n) + 16 : 1;
+    MSK_CUDA_CHECK(dalloc(&out->nodes, node_cap * kNodeFloat4s));
+    MSK_CUDA_CHECK(dalloc(&out->tris, n * kTriFloat4s));
+    if (n == 0) {
+        k_empty_root<<<1, 32, 0, stream>>>(out->nodes);
+        out->nnodes = 1; out->ntris = 0; out->depth = 1;
+        MSK_CUDA_CHECK(cudaEventRecord(e1, stream));
+        MSK_CUDA_CHECK(cudaEventSynchronize(e1));
+        cudaEventElapsedTime(&out->ms_build, e0, e1);
+        cudaEventDestroy(e0); cudaEventDestroy(e1);
+        return MSK_OK;
+    }
+
+    float4 *gathered = nullptr;
+    uint64_t *keys = nullptr, *keys_sorted = nullptr;
+    uint32_t *vals = nullptr, *sorted = nullptr;
+    BuildState *st = nullptr;
+    void *cub_tmp = nullptr;
+    size_t cub_bytes = 0;
+    Bvh2 t{};
+    WorkItem *qa = nullptr, *qb = nullptr;
+    float *sah = nullptr;
+    int rc = MSK_OK;
+    auto cleanup = [&]() {
+        cudaFree(gathered); cudaFree(keys); cudaFree(keys_sorted); cudaFree(vals); cudaFree(sorted); cudaFree(st);
+        cudaFree(cub_tmp); cudaFree(t.left); cudaFree(t.right); cudaFree(t.parent); cudaFree(t.first); cudaFree(t.last);
+        cudaFree(t.lo); cudaFree(t.hi); cudaFree(t.flags); cudaFree(qa); cudaFree(qb); cudaFree(sah);
+        cudaEventDestroy(e0); cudaEventDestroy(e1);
+    };
+#define BVH_CHECK(expr)                                                          \
+    do {                                                                         \
+        cudaError_t err__ = (expr);                                              \
+        if (err__ != cudaSuccess) { rc = cuda_fail(err__, #expr, __FILE__, __LINE__); cleanup(); \
+            cudaFree(out->nodes); cudaFree(out->tris); *out = BvhResult{}; return rc; } \
+    } while (0)
+
+    BVH_CHECK(dalloc(&gathered, n * 3));
+    BVH_CHECK(dalloc(&keys, n)); BVH_CHECK(dalloc(&keys_sorted, n));
+    BVH_CHECK(dalloc(&vals, n)); BVH_CHECK(dalloc(&sorted, n));
+    BVH_CHECK(dalloc(&st, 1));
+    BVH_CHECK(dalloc(&sah, 1));
+    BVH_CHECK(cudaMemsetAsync(sah, 0, sizeof(float), stream));
+    k_init_state<<<1, 1, 0, stream>>>(st);
+    for (uint32_t g = 0; g < meshes.size(); ++g) {
+        const DMeshInfo &m = meshes[g];
+        if (!m.ntris) continue;
+        k_tri_setup<<<blocks_for(m.ntris), kThreads, 0, stream>>>(d_verts, d_indices, m.vert_offset, m.tri_offset, m.ntris, g,
+                                                                  gathered, st);
+    }
+    k_morton<<<blocks_for(n), kThreads, 0, stream>>>(gathered, (uint32_t) n, st, keys, vals);
+    BVH_CHECK(cub::DeviceRadixSort::SortPairs(nullptr, cub_bytes, keys, keys_sorted, vals, sorted, (int) n, 0, 63, stream));
+    BVH_CHECK(cudaMalloc(&cub_tmp, std::max<size_t>(cub_bytes, 16)));
+    BVH_CHECK(cub::DeviceRadixSort::SortPairs(cub_tmp, cub_bytes, keys, keys_sorted, vals, sorted, (int) n, 0, 63, stream));
+
+    size_t nint = n > 1 ? n - 1 : 1;
+    BVH_CHECK(dalloc(&t.left, nint)); BVH_CHECK(dalloc(&t.right, nint));
+    BVH_CHECK(dalloc(&t.first, nint)); BVH_CHECK(dalloc(&t.last, nint));
+    BVH_CHECK(dalloc(&t.flags, nint));
+    BVH_CHECK(dalloc(&t.parent, 2 * n));
+    BVH_CHECK(dalloc(&t.lo, 2 * n)); BVH_CHECK(dalloc(&t.hi, 2 * n));
+    BVH_CHECK(cudaMemsetAsync(t.flags, 0, nint * sizeof(uint32_t), stream));
+    if (n > 1) k_karras<<<blocks_for(n - 1), kThreads, 0, stream>>>(keys_sorted, (int) n, t);
+    k_refit<<<blocks_for(n), kThreads, 0, stream>>>(gathered, sorted, (int) n, t);
+    if (n > 1) k_sah<<<blocks_for(n - 1), kThreads, 0, stream>>>(t, (int) n, sah);
+
+    // level-synchronous collapse
+    size_t qcap = node_cap;
+    BVH_CHECK(dalloc(&qa, qcap)); BVH_CHECK(dalloc(&qb, qcap));
+    WorkItem root{ 0u, 0u };
+    BVH_CHECK(cudaMemcpyAsync(qa, &root, sizeof(root), cudaMemcpyHostToDevice, stream));
+    uint32_t nin = 1, depth = 0;
+    BuildState hst{};
+    while (nin) {
+        k_collapse<<<blocks_for(nin), 128, 0, stream>>>(qa, nin, qb, (uint32_t) qcap, t, (int) n, sorted, gathered, out->nodes,
+                                                        (uint32_t) node_cap, out->tris, st, n == 1 ? 1 : 0);
+        BVH_CHECK(cudaMemcpyAsync(&hst, st, sizeof(hst), cudaMemcpyDeviceToHost, stream));
+        BVH_CHECK(cudaStreamSynchronize(stream));
+        if (hst.overflow) { cleanup(); cudaFree(out->nodes); cudaFree(out->tris); *out = BvhResult{};
+            return fail(MSK_ERR_OOM, "BVH node pool overflow (n=%zu)", n); }
+        nin = hst.queue_count;
+        BVH_CHECK(cudaMemsetAsync(&st->queue_count, 0, sizeof(uint32_t), stream));
+        std::swap(qa, qb);
+        depth++;
+    }
+    if (hst.tri_count != n) { cleanup(); cudaFree(out->nodes); cudaFree(out->tris); *out = BvhResult{};
+        return fail(MSK_ERR_CUDA, "BVH collapse emitted %u of %zu triangles", hst.tri_count, n); }
+    float hsah = 0.f;
+    float4 rlo, rhi;
+    BVH_CHECK(cudaMemcpyAsync(&hsah, sah, sizeof(float), cudaMemcpyDeviceToHost, stream));
+    BVH_CHECK(cudaMemcpyAsync(&rlo, t.lo + (n > 1 ? 0 : 0), sizeof(float4), cudaMemcpyDeviceToHost, stream));
+    BVH_CHECK(cudaMemcpyAsync(&rhi, t.hi + (n > 1 ? 0 : 0), sizeof(float4), cudaMemcpyDeviceToHost, stream));
+    BVH_CHECK(cudaEventRecord(e1, stream));
+    BVH_CHECK(cudaEventSynchronize(e1));
+    cudaEventElapsedTime(&out->ms_build, e0, e1);
+    out->nnodes = hst.node_count; out->ntris = n; out->depth = depth;
+    float ra = (rhi.x - rlo.x) * (rhi.y - rlo.y) + (rhi.y - rlo.y) * (rhi.z - rlo.z) + (rhi.z - rlo.z) * (rhi.x - rlo.x);
+    out->sah_cost = ra > 0.f ? hsah / ra : 0.f;
+    out->lo[0] = rlo.x; out->lo[1] = rlo.y; out->lo[2] = rlo.z;
+    out->hi[0] = rhi.x; out->hi[1] = rhi.y; out->hi[2] = rhi.z;
+    cleanup();
+#undef BVH_CHECK
+    return MSK_OK;
+}
+
+void bvh_free(BvhResult *r) {
+    if (!r) return;
+    cudaFree(r->nodes); cudaFree(r->tris);
+    *r = BvhResult{};
+}
+
+} // namespace msk

@@ -1,0 +1,79 @@
+// Device-side data layout shared by the BVH builder, the traversal kernels and the
+// wavefront path tracer.  sm_100a only.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/misaki_b200.h"
+
+#define MSK_CUDA_CHECK(expr)                                                                   \
+    do {                                                                                       \
+        cudaError_t err__ = (expr);                                                            \
+        if (err__ != cudaSuccess) return msk::cuda_fail(err__, #expr, __FILE__, __LINE__);     \
+    } while (0)
+
+namespace msk {
+
+int cuda_fail(cudaError_t err, const char *expr, const char *file, int line);
+int fail(int code, const char *fmt, ...);
+
+// ---- wide BVH node: 80 bytes = five 16-byte loads (Ylitie, Karras, Laine 2017 layout) ----
+//  n0: p.x p.y p.z | ex ey ez imask          origin of the quantisation grid, exponents, internal-child mask
+//  n1: child_base | tri_base | meta[0..3] | meta[4..7]
+//  n2: qlo_x[0..7]            | qlo_y[0..7]
+//  n3: qlo_z[0..7]            | qhi_x[0..7]
+//  n4: qhi_y[0..7]            | qhi_z[0..7]
+// meta[i]: 0 = empty; internal child: 0b001sssss with sssss = 24 + slot; leaf: top 3 bits = triangle
+// count in unary (1, 3 or 7), low 5 bits = offset of its first triangle from tri_base (< 24).
+constexpr int kNodeFloat4s = 5;
+constexpr int kTriFloat4s  = 3; // v0.xyz, prim | v1.xyz, geom | v2.xyz, -
+constexpr int kMaxLeafTris = 3;
+
+struct DMeshInfo {
+    uint32_t vert_offset; // first vertex in DScene::verts (units of vertices)
+    uint32_t tri_offset;  // first triangle in DScene::indices (units of triangles)
+    uint32_t ntris;
+    int32_t  bsdf;
+    int32_t  emitter;
+    uint32_t flags;       // 1 = vertex normals, 2 = texcoords
+    float    inv_area;    // 1 / Mesh::m_surface_area (float, sequential sum as mesh.cpp:39-48)
+    uint32_t cdf_offset;  // emitter meshes: first entry of the (ntris+1)-entry area CDF in DScene::cdfs
+};
+
+struct DSpectrum {
+    int32_t  kind;
+    float    c0, c1, c2;
+    float    value;
+    uint32_t table_offset, table_size;
+    float    lambda_min, inv_interval;
+};
+
+struct DCamera {
+    float s2c[16];
+    float c2w[16];
+    float near_clip, far_clip;
+    uint32_t width, height;
+    float filter_radius;
+    float filter_scale; // MSK_FILTER_RESOLUTION / radius
+};
+
+struct DScene {
+    const float4    *nodes;
+    const float4    *tris;
+    const float4    *verts;   // 2 float4 per vertex: px py pz nx | ny nz u v
+    const uint32_t  *indices; // 3 per triangle, mesh-local vertex ids
+    const DMeshInfo *meshes;
+    const MskBsdf   *bsdfs;
+    const MskEmitter *emitters;
+    const DSpectrum *spectra;
+    const float     *tables;
+    const float     *cdfs;
+    const float     *filter_table; // 33 entries
+    const float4    *cie;          // 95 rows: xbar ybar zbar d65
+    uint32_t nemitters;
+    int32_t  environment;
+    float    env_radius;
+    uint32_t nmeshes;
+    DCamera  cam;
+};
+
+} // namespace msk

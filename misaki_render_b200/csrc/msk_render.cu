@@ -1,0 +1,597 @@
+// Wavefront path tracer: replaces the TBB tile loop of SamplingIntegrator::render
+// (reference src/librender/integrator.cpp:31-126) and PathTracer::sample
+// (src/librender/integrators/path.cpp:23-131).
+//
+// One batch = every pixel of the film x a run of consecutive samples.  Stages,
+// connected by queues in HBM (all launches on one stream, no host round trips
+// inside a bounce):
+//
+//   k_raygen      camera sample -> primary ray + path state             (dense)
+//   k_intersect   persistent-thread closest hit; classifies each hit by BSDF type and
+//                 appends its queue index to that type's segment (warp match + 1 atomic)
+//   k_shade       runs over the type-sorted index list: emission/MIS, Russian roulette,
+//                 NEE sample (-> shadow queue), BSDF sample (-> next ray queue,
+//                 warp-ballot compaction), state moves to its new compacted slot
+//   k_shadow      persistent-thread any hit; unoccluded => L[path] += contribution
+//   k_film_*      per-sample XYZ records, then a per-pixel GATHER of the filtered
+//                 splats (deterministic, no float atomics)
+//
+// Sample (pixel p = y*W+x, index s) is seeded with Sampler::seed(p*spp + s) and draws
+// in source order, so any partition of the sample range over batches or GPUs
+// produces the same per-sample radiance.
+#include "msk_render.h"
+#include "msk_shading.cuh"
+#include "msk_traverse.cuh"
+
+#include <algorithm>
+#include <cstdio>
+
+namespace msk {
+
+namespace {
+
+constexpr int kNumKeys = 1 + MSK_BSDF_TYPE_COUNT; // 0 = miss, 1 + bsdf type
+
+struct Ctrl {
+    uint32_t n_rays[2];
+    uint32_t n_shadow;
+    uint32_t cursor_isect, cursor_shadow;
+    uint32_t type_count[kNumKeys];
+    uint32_t pad_;
+    unsigned long long total_closest, total_shadow;
+};
+
+struct Pool {
+    uint32_t capacity;
+    MskRay  *rays[2];
+    float4  *hit;       // t, u, v, prim
+    uint32_t *hit_geom;
+    float4  *T[2], *WL[2], *AUX[2]; // throughput | wavelengths | eta, prev_pdf, stale_pdf, -
+    uint4   *MISC[2];               // rng lo, rng hi, path, depth | flags << 16
+    float4  *L;                     // accumulated radiance per path of the batch
+    MskRay  *sh_ray;
+    float4  *sh_contrib;
+    uint32_t *sh_path;
+    uint32_t *sorted;               // kNumKeys segments of `capacity` queue indices
+    float4  *rec;                   // X, Y, Z, pos.x
+    float   *rec_py;
+    Ctrl    *ctrl;
+};
+
+struct BatchParams {
+    uint32_t npix, width;
+    uint32_t s0, ns;       // first sample index, samples per pixel in this batch
+    uint32_t spp;          // of the whole job (seeding)
+    uint64_t base_seed;
+    int32_t  max_depth, rr_depth, hide_emitters;
+};
+
+constexpr uint32_t kFlagDelta = 1u << 16;
+
+__device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31u; }
+
+// ---------------------------------------------------------------------------------------
+__global__ void k_begin_batch(Ctrl *c, uint32_t n) {
+    c->n_rays[0] = n; c->n_rays[1] = 0; c->n_shadow = 0; c->cursor_isect = 0; c->cursor_shadow = 0;
+    for (int i = 0; i < kNumKeys; ++i) c->type_count[i] = 0;
+}
+
+// after k_shade + k_shadow of bounce b: make queue `next` current
+__global__ void k_end_bounce(Ctrl *c, int cur) {
+    c->total_closest += c->n_rays[cur];
+    c->total_shadow += c->n_shadow;
+    c->n_rays[cur] = 0; c->n_shadow = 0; c->cursor_isect = 0; c->cursor_shadow = 0;
+    for (int i = 0; i < kNumKeys; ++i) c->type_count[i] = 0;
+}
+
+// ---------------------------------------------------------------------------------------
+// render_sample: integrator.cpp:103-126 (first half), perspective.cpp:22-41
+__global__ void __launch_bounds__(256) k_raygen(const __grid_constant__ DScene sc, Pool pool, BatchParams bp) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t n = bp.npix * bp.ns;
+    if (i >= n) return;
+    uint32_t pixel = i % bp.npix, s = bp.s0 + i / bp.npix;
+    uint32_t gx = pixel % bp.width, gy = pixel / bp.width;
+    uint64_t rng = pcg_seed((uint64_t) pixel * bp.spp + s + bp.base_seed);
+    float jx = next1d(rng), jy = next1d(rng);
+    float wav = next1d(rng);
+    next1d(rng); next1d(rng); // aperture sample: consumed, unused
+    float4 wl, weight;
+    sample_wavelength(wav, wl, weight);
+    V3 o, d;
+    float mint, maxt;
+    camera_ray(sc.cam, (float) gx + jx, (float) gy + jy, o, d, mint, maxt);
+    float4 *rp = reinterpret_cast<float4 *>(pool.rays[0] + i);
+    rp[0] = make_float4(o.x, o.y, o.z, mint);
+    rp[1] = make_float4(d.x, d.y, d.z, maxt);
+    pool.T[0][i]    = f4(1.f);
+    pool.WL[0][i]   = wl;
+    pool.MISC[0][i] = make_uint4((uint32_t) rng, (uint32_t) (rng >> 32), i, 1u);
+    pool.AUX[0][i]  = make_float4(1.f, 0.f, 0.f, 0.f);
+    pool.L[i]       = f4(0.f);
+}
+
+// ---------------------------------------------------------------------------------------
+// Closest hit over the current ray queue (Scene::ray_intersect, scene.cpp:216-253) + classification.
+__global__ void __launch_bounds__(128) k_intersect(const __grid_constant__ DScene sc, Pool pool, int cur) {
+    Ctrl *c = pool.ctrl;
+    const uint32_t n = c->n_rays[cur];
+    const MskRay *rays = pool.rays[cur];
+    for (;;) {
+        uint32_t base = 0;
+        if (lane_id() == 0) base = atomicAdd(&c->cursor_isect, 32u);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (base >= n) break;
+        uint32_t q = base + lane_id();
+        bool valid = q < n;
+        uint32_t key = 0xffffffffu;
+        if (valid) {
+            const float4 *rp = reinterpret_cast<const float4 *>(rays + q);
+            float4 ro = __ldcs(rp), rd = __ldcs(rp + 1);
+            RayHit h;
+            h.t = MSK_INF; h.u = 0.f; h.v = 0.f; h.prim = 0xffffffffu; h.geom = 0xffffffffu;
+            bool found = traverse<false, false>(sc.nodes, sc.tris, ro.x, ro.y, ro.z, rd.x, rd.y, rd.z, ro.w, rd.w, h);
+            if (found && h.t == rd.w) found = false; // hit <=> tfar != maxt, scene.cpp:234
+            if (!found) { h.t = MSK_INF; h.geom = 0xffffffffu; }
+            pool.hit[q]      = make_float4(h.t, h.u, h.v, __uint_as_float(h.prim));
+            pool.hit_geom[q] = h.geom;
+            key = found ? 1u + (uint32_t) sc.bsdfs[sc.meshes[h.geom].bsdf].type : 0u;
+        }
+        // sort by material: append q to the segment of its key (one atomic per key per warp)
+        uint32_t active = __ballot_sync(0xffffffffu, valid);
+        if (valid) {
+            uint32_t peers = __match_any_sync(active, key);
+            uint32_t leader = __ffs(peers) - 1u;
+            uint32_t rank = __popc(peers & ((1u << lane_id()) - 1u));
+            uint32_t slot = 0;
+            if (lane_id() == leader) slot = atomicAdd(&c->type_count[key], (uint32_t) __popc(peers));
+            slot = __shfl_sync(peers, slot, leader);
+            pool.sorted[(size_t) key * pool.capacity + slot + rank] = q;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// One path vertex: path.cpp:33-123 re-ordered so that everything that follows the hit of the
+// ray spawned at the previous vertex (emitter MIS term :82-108, Russian roulette :116-122)
+// runs at the start of the next vertex, in the original order of random draws.
+__global__ void __launch_bounds__(128) k_shade(const __grid_constant__ DScene sc, Pool pool, BatchParams bp, int cur) {
+    Ctrl *c = pool.ctrl;
+    const int nxt = cur ^ 1;
+    uint32_t counts[kNumKeys], total = 0;
+#pragma unroll
+    for (int k = 0; k < kNumKeys; ++k) { counts[k] = c->type_count[k]; total += counts[k]; }
+    const uint32_t stride = gridDim.x * blockDim.x;
+    const uint32_t rounds = (total + stride - 1) / stride;
+    for (uint32_t it = 0; it < rounds; ++it) {
+        uint32_t idx = it * stride + blockIdx.x * blockDim.x + threadIdx.x;
+        bool valid = idx < total;
+        bool emit_ray = false, emit_shadow = false;
+        MskRay nray, sray;
+        float4 nT, nWL, nAUX, contrib;
+        uint4 nMISC;
+        uint32_t path = 0;
+        if (valid) {
+            uint32_t key = 0, j = idx;
+#pragma unroll
+            for (int k = 0; k < kNumKeys - 1; ++k)
+                if (key == (uint32_t) k && j >= counts[k]) { j -= counts[k]; key = k + 1; }
+            const uint32_t q = pool.sorted[(size_t) key * pool.capacity + j];
+            const float4 hit = pool.hit[q];
+            const float4 rd  = reinterpret_cast<const float4 *>(pool.rays[cur] + q)[1];
+            float4 T = pool.T[cur][q];
+            const float4 wl = pool.WL[cur][q];
+            const uint4 misc = pool.MISC[cur][q];
+            const float4 aux = pool.AUX[cur][q];
+            uint64_t rng = (uint64_t) misc.x | ((uint64_t) misc.y << 32);
+            path = misc.z;
+            const int depth = (int) (misc.w & 0xffffu);
+            const bool prev_delta = (misc.w & kFlagDelta) != 0;
+            float eta = aux.x;
+            const float prev_pdf = aux.y, stale_pdf = aux.z;
+            float4 L = f4(0.f);
+            bool add_L = false, alive = true;
+            const V3 rdir = v3(rd.x, rd.y, rd.z);
+
+            if (key == 0) { // miss: path.cpp:34-41 (depth 1) / :90-98,:103-108 (BSDF-sampled ray escaped)
+                if (sc.environment >= 0) {
+                    float4 le = spectrum_eval(sc, sc.emitters[sc.environment].radiance, wl);
+                    if (depth == 1) { if (!bp.hide_emitters) { L = T * le; add_L = true; } }
+                    else { L = T * le * mis_weight(prev_pdf, prev_delta ? 0.f : stale_pdf); add_L = true; }
+                }
+                alive = false;
+            } else {
+                const uint32_t geom = pool.hit_geom[q];
+                const DMeshInfo mi = sc.meshes[geom];
+                const Surface sf = make_surface(sc, mi, __float_as_uint(hit.w), hit.y, hit.z);
+                const V3 wi = to_local(sf.sh, -rdir);
+                if (mi.emitter >= 0) { // area.cpp:51-54
+                    float4 le = wi.z > 0.f ? spectrum_eval(sc, sc.emitters[mi.emitter].radiance, wl) : f4(0.f);
+                    if (depth == 1) { // path.cpp:44-47
+                        if (!bp.hide_emitters) { L = T * le; add_L = true; }
+                    } else {          // path.cpp:82-88,103-108 with ds.set_query (records.cpp:7-14)
+                        float emitter_pdf = 0.f;
+                        if (!prev_delta) {
+                            float dp = fabsf(dot(rdir, sf.sh.n));
+                            emitter_pdf = mi.inv_area * ((dp != 0.f) ? (hit.x * hit.x) / dp : 0.f);
+                            if (sc.nemitters > 1) emitter_pdf *= 1.f / (float) sc.nemitters;
+                        }
+                        L = T * le * mis_weight(prev_pdf, emitter_pdf);
+                        add_L = true;
+                    }
+                }
+                if (depth > 1 && depth >= bp.rr_depth) { // path.cpp:116-122 of the previous iteration
+                    float qq = fminf(hmax(T) * eta * eta, 0.95f);
+                    if (next1d(rng) >= qq) alive = false;
+                    else T = T / qq;
+                }
+                if (alive && bp.max_depth > 0 && depth >= bp.max_depth) alive = false; // path.cpp:48-49
+                if (alive) {
+                    const MskBsdf bsdf = sc.bsdfs[mi.bsdf];
+                    float new_stale = 0.f;
+                    const float tmin_spawn = (1.f + max_abs(sf.p)) * kRayEpsilon; // interaction.h:40-44, scene.cpp:91-93
+                    if (bsdf_is_smooth(bsdf.type)) { // path.cpp:56-67
+                        float sx = next1d(rng), sy = next1d(rng);
+                        NeeSample ns = sample_emitter_direct(sc, sf.p, wl, sx, sy);
+                        new_stale = ns.stale_pdf;
+                        if (ns.pdf != 0.f) {
+                            V3 wo = to_local(sf.sh, ns.d);
+                            float4 bval; float bpdf;
+                            bsdf_eval_pdf(sc, bsdf, wi, wo, wl, bval, bpdf);
+                            float w = mis_weight(ns.pdf, bpdf);
+                            contrib = T * ns.value * bval * w;
+                            if (!is_zero(contrib)) {
+                                emit_shadow = true;
+                                sray.o[0] = sf.p.x; sray.o[1] = sf.p.y; sray.o[2] = sf.p.z;
+                                sray.tmin = kRayEpsilon * (1.f + max_abs(sf.p));
+                                sray.d[0] = ns.d.x; sray.d[1] = ns.d.y; sray.d[2] = ns.d.z;
+                                sray.tmax = ns.dist * (1.f - kShadowEpsilon);
+                            }
+                        }
+                    }
+                    float s1 = next1d(rng), s2x = next1d(rng), s2y = next1d(rng); // path.cpp:71-72, left to right
+                    BsdfSample bs = bsdf_sample(sc, bsdf, wi, wl, s1, s2x, s2y);
+                    if (is_zero(bs.weight)) alive = false; // failed sample: nothing downstream can contribute
+                    else {
+                        V3 wo = to_world(sf.sh, bs.wo);
+                        T = T * bs.weight;
+                        eta *= bs.eta;
+                        emit_ray = true;
+                        nray.o[0] = sf.p.x; nray.o[1] = sf.p.y; nray.o[2] = sf.p.z; nray.tmin = tmin_spawn;
+                        nray.d[0] = wo.x; nray.d[1] = wo.y; nray.d[2] = wo.z; nray.tmax = MSK_INF;
+                        nT = T; nWL = wl;
+                        nMISC = make_uint4((uint32_t) rng, (uint32_t) (rng >> 32), path,
+                                           (uint32_t) (depth + 1) | ((bs.type & BF_Delta) ? kFlagDelta : 0u));
+                        nAUX = make_float4(eta, bs.pdf, new_stale, 0.f);
+                    }
+                }
+            }
+            if (add_L) { float4 acc = pool.L[path]; pool.L[path] = acc + L; }
+        }
+        // compaction: one atomic per warp and queue
+        uint32_t m_ray = __ballot_sync(0xffffffffu, emit_ray), m_sh = __ballot_sync(0xffffffffu, emit_shadow);
+        uint32_t base_ray = 0, base_sh = 0;
+        if (lane_id() == 0) {
+            if (m_ray) base_ray = atomicAdd(&c->n_rays[nxt], (uint32_t) __popc(m_ray));
+            if (m_sh) base_sh = atomicAdd(&c->n_shadow, (uint32_t) __popc(m_sh));
+        }
+        base_ray = __shfl_sync(0xffffffffu, base_ray, 0);
+        base_sh  = __shfl_sync(0xffffffffu, base_sh, 0);
+        const uint32_t below = (1u << lane_id()) - 1u;
+        if (emit_ray) {
+            uint32_t o = base_ray + __popc(m_ray & below);
+            float4 *rp = reinterpret_cast<float4 *>(pool.rays[nxt] + o);
+            rp[0] = make_float4(nray.o[0], nray.o[1], nray.o[2], nray.tmin);
+            rp[1] = make_float4(nray.d[0], nray.d[1], nray.d[2], nray.tmax);
+            pool.T[nxt][o] = nT; pool.WL[nxt][o] = nWL; pool.MISC[nxt][o] = nMISC; pool.AUX[nxt][o] = nAUX;
+        }
+        if (emit_shadow) {
+            uint32_t o = base_sh + __popc(m_sh & below);
+            float4 *rp = reinterpret_cast<float4 *>(pool.sh_ray + o);
+            rp[0] = make_float4(sray.o[0], sray.o[1], sray.o[2], sray.tmin);
+            rp[1] = make_float4(sray.d[0], sray.d[1], sray.d[2], sray.tmax);
+            pool.sh_contrib[o] = contrib;
+            pool.sh_path[o]    = path;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// NEE visibility (Scene::ray_test, scene.cpp:90-98,255-273) fused with the accumulation of
+// the NEE term (path.cpp:63-66).
+__global__ void __launch_bounds__(128) k_shadow(const __grid_constant__ DScene sc, Pool pool) {
+    Ctrl *c = pool.ctrl;
+    const uint32_t n = c->n_shadow;
+    for (;;) {
+        uint32_t base = 0;
+        if (lane_id() == 0) base = atomicAdd(&c->cursor_shadow, 32u);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (base >= n) break;
+        uint32_t q = base + lane_id();
+        if (q < n) {
+            const float4 *rp = reinterpret_cast<const float4 *>(pool.sh_ray + q);
+            float4 ro = __ldcs(rp), rd = __ldcs(rp + 1);
+            RayHit h;
+            bool occluded = traverse<true, false>(sc.nodes, sc.tris, ro.x, ro.y, ro.z, rd.x, rd.y, rd.z, ro.w, rd.w, h);
+            if (occluded && h.t == rd.w) occluded = false; // scene.cpp:272
+            if (!occluded) {
+                uint32_t path = pool.sh_path[q];
+                float4 acc = pool.L[path];
+                pool.L[path] = acc + __ldcs(pool.sh_contrib + q);
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// Film.  render_sample tail (integrator.cpp:115-125): xyz = spectrum_to_xyz(result * ray_weight).
+__global__ void __launch_bounds__(256) k_film_records(const __grid_constant__ DScene sc, Pool pool, BatchParams bp) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t n = bp.npix * bp.ns;
+    if (i >= n) return;
+    uint32_t pixel = i % bp.npix, s = bp.s0 + i / bp.npix;
+    uint32_t gx = pixel % bp.width, gy = pixel / bp.width;
+    uint64_t rng = pcg_seed((uint64_t) pixel * bp.spp + s + bp.base_seed);
+    float jx = next1d(rng), jy = next1d(rng);
+    float wav = next1d(rng);
+    float4 wl, weight;
+    sample_wavelength(wav, wl, weight);
+    float4 result = pool.L[i] * weight;
+    float X, Y, Z;
+    spectrum_to_xyz(sc, result, wl, X, Y, Z);
+    pool.rec[i]    = make_float4(X, Y, Z, (float) gx + jx);
+    pool.rec_py[i] = (float) gy + jy;
+}
+
+// ImageBlock::put (imageblock.cpp:55-114) + Film::put, as a gather: pixel (x, y) sums
+// w_x * w_y * {X,Y,Z,1,1} over the samples of the 5x5 pixel neighbourhood.  A sample outside
+// the filter support looks up table[32] == 0 and adds nothing, exactly like the reference's
+// lo/hi clipping (rfilter.h:13-16).
+constexpr int kFilmTileX = 32, kFilmTileY = 8;
+__global__ void __launch_bounds__(kFilmTileX *kFilmTileY) k_film_gather(const __grid_constant__ DScene sc, Pool pool,
+                                                                         BatchParams bp, float *__restrict__ film,
+                                                                         uint32_t height) {
+    const int x = blockIdx.x * kFilmTileX + threadIdx.x, y = blockIdx.y * kFilmTileY + threadIdx.y;
+    const int W = (int) bp.width, H = (int) height;
+    if (x >= W || y >= H) return;
+    const int r = (int) ceilf(sc.cam.filter_radius - 0.5f); // border size, rfilter.cpp:22
+    const float scale = sc.cam.filter_scale;
+    float aX = 0.f, aY = 0.f, aZ = 0.f, aW = 0.f;
+    for (uint32_t s = 0; s < bp.ns; ++s) {
+        const size_t sbase = (size_t) s * bp.npix;
+        for (int ny = max(y - r, 0); ny <= min(y + r, H - 1); ++ny)
+            for (int nx = max(x - r, 0); nx <= min(x + r, W - 1); ++nx) {
+                size_t i = sbase + (size_t) ny * W + nx;
+                float4 rec = __ldg(pool.rec + i);
+                float py = __ldg(pool.rec_py + i);
+                // pos - 0.5 is exact in float for every representable sample position
+                float dx = (float) x - (rec.w - 0.5f), dy = (float) y - (py - 0.5f);
+                float wx = __ldg(sc.filter_table + min((int) fabsf(dx * scale), 32));
+                float wy = __ldg(sc.filter_table + min((int) fabsf(dy * scale), 32));
+                // the reference only visits ceil(pos-r) .. floor(pos+r); outside, |d| > radius
+                if (fabsf(dx) > sc.cam.filter_radius || fabsf(dy) > sc.cam.filter_radius) continue;
+                float w = wx * wy;
+                aX += w * rec.x; aY += w * rec.y; aZ += w * rec.z; aW += w;
+            }
+    }
+    float *p = film + ((size_t) y * W + x) * 5;
+    p[0] += aX; p[1] += aY; p[2] += aZ; p[3] += aW; p[4] += aW;
+}
+
+// ---------------------------------------------------------------------------------------
+// Stand-alone batch queries (msk_gpu_intersect / msk_gpu_occluded)
+template <bool STATS>
+__global__ void __launch_bounds__(128) k_query_closest(const __grid_constant__ DScene sc, const MskRay *__restrict__ rays,
+                                                       MskHit *__restrict__ hits, uint32_t n, uint32_t *cursor,
+                                                       uint32_t *nnodes, uint32_t *ntris) {
+    for (;;) {
+        uint32_t base = 0;
+        if (lane_id() == 0) base = atomicAdd(cursor, 32u);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (base >= n) break;
+        uint32_t q = base + lane_id();
+        if (q < n) {
+            const float4 *rp = reinterpret_cast<const float4 *>(rays + q);
+            float4 ro = __ldcs(rp), rd = __ldcs(rp + 1);
+            RayHit h;
+            h.t = MSK_INF; h.u = 0.f; h.v = 0.f; h.prim = 0xffffffffu; h.geom = 0xffffffffu;
+            uint32_t cn = 0, ct = 0;
+            bool found = traverse<false, STATS>(sc.nodes, sc.tris, ro.x, ro.y, ro.z, rd.x, rd.y, rd.z, ro.w, rd.w, h, &cn, &ct);
+            if (found && h.t == rd.w) found = false;
+            if (STATS) { nnodes[q] = cn; ntris[q] = ct; }
+            else {
+                MskHit o;
+                o.t = found ? h.t : MSK_INF; o.u = found ? h.u : 0.f; o.v = found ? h.v : 0.f;
+                o.prim = found ? h.prim : 0xffffffffu; o.geom = found ? h.geom : 0xffffffffu;
+                hits[q] = o;
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(128) k_query_any(const __grid_constant__ DScene sc, const MskRay *__restrict__ rays,
+                                                   uint8_t *__restrict__ occ, uint32_t n, uint32_t *cursor) {
+    for (;;) {
+        uint32_t base = 0;
+        if (lane_id() == 0) base = atomicAdd(cursor, 32u);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (base >= n) break;
+        uint32_t q = base + lane_id();
+        if (q < n) {
+            const float4 *rp = reinterpret_cast<const float4 *>(rays + q);
+            float4 ro = __ldcs(rp), rd = __ldcs(rp + 1);
+            RayHit h;
+            bool found = traverse<true, false>(sc.nodes, sc.tris, ro.x, ro.y, ro.z, rd.x, rd.y, rd.z, ro.w, rd.w, h);
+            if (found && h.t == rd.w) found = false;
+            occ[q] = found ? 1 : 0;
+        }
+    }
+}
+
+template <typename T> cudaError_t dalloc(T **p, size_t n) { return cudaMalloc((void **) p, std::max<size_t>(n, 1) * sizeof(T)); }
+
+} // namespace
+
+// =========================================================================================
+struct Renderer::Impl {
+    Pool pool{};
+    uint32_t capacity = 0;
+    uint32_t *query_cursor = nullptr;
+    Ctrl *h_ctrl = nullptr; // pinned
+    cudaEvent_t ev[8]{};
+    int persistent_blocks = 0;
+};
+
+Renderer::Renderer() : impl_(new Impl) {}
+Renderer::~Renderer() { release(); delete impl_; }
+
+void Renderer::release() {
+    Pool &p = impl_->pool;
+    for (int i = 0; i < 2; ++i) { cudaFree(p.rays[i]); cudaFree(p.T[i]); cudaFree(p.WL[i]); cudaFree(p.AUX[i]); cudaFree(p.MISC[i]); }
+    cudaFree(p.hit); cudaFree(p.hit_geom); cudaFree(p.L); cudaFree(p.sh_ray); cudaFree(p.sh_contrib); cudaFree(p.sh_path);
+    cudaFree(p.sorted); cudaFree(p.rec); cudaFree(p.rec_py); cudaFree(p.ctrl);
+    p = Pool{};
+    impl_->capacity = 0;
+    cudaFree(impl_->query_cursor); impl_->query_cursor = nullptr;
+    if (impl_->h_ctrl) { cudaFreeHost(impl_->h_ctrl); impl_->h_ctrl = nullptr; }
+    for (auto &e : impl_->ev) if (e) { cudaEventDestroy(e); e = nullptr; }
+}
+
+int Renderer::init(int sm_count) {
+    impl_->persistent_blocks = sm_count * 8; // 128-thread CTAs, 8 resident per SM
+    MSK_CUDA_CHECK(dalloc(&impl_->query_cursor, 1));
+    MSK_CUDA_CHECK(cudaMallocHost((void **) &impl_->h_ctrl, sizeof(Ctrl)));
+    for (auto &e : impl_->ev) MSK_CUDA_CHECK(cudaEventCreate(&e));
+    return MSK_OK;
+}
+
+int Renderer::ensure_pool(uint32_t capacity) {
+    if (capacity <= impl_->capacity) return MSK_OK;
+    Pool &p = impl_->pool;
+    for (int i = 0; i < 2; ++i) { cudaFree(p.rays[i]); cudaFree(p.T[i]); cudaFree(p.WL[i]); cudaFree(p.AUX[i]); cudaFree(p.MISC[i]); }
+    cudaFree(p.hit); cudaFree(p.hit_geom); cudaFree(p.L); cudaFree(p.sh_ray); cudaFree(p.sh_contrib); cudaFree(p.sh_path);
+    cudaFree(p.sorted); cudaFree(p.rec); cudaFree(p.rec_py); cudaFree(p.ctrl);
+    p = Pool{};
+    impl_->capacity = 0;
+    size_t n = capacity;
+    for (int i = 0; i < 2; ++i) {
+        MSK_CUDA_CHECK(dalloc(&p.rays[i], n)); MSK_CUDA_CHECK(dalloc(&p.T[i], n)); MSK_CUDA_CHECK(dalloc(&p.WL[i], n));
+        MSK_CUDA_CHECK(dalloc(&p.AUX[i], n)); MSK_CUDA_CHECK(dalloc(&p.MISC[i], n));
+    }
+    MSK_CUDA_CHECK(dalloc(&p.hit, n)); MSK_CUDA_CHECK(dalloc(&p.hit_geom, n)); MSK_CUDA_CHECK(dalloc(&p.L, n));
+    MSK_CUDA_CHECK(dalloc(&p.sh_ray, n)); MSK_CUDA_CHECK(dalloc(&p.sh_contrib, n)); MSK_CUDA_CHECK(dalloc(&p.sh_path, n));
+    MSK_CUDA_CHECK(dalloc(&p.sorted, n * kNumKeys)); MSK_CUDA_CHECK(dalloc(&p.rec, n)); MSK_CUDA_CHECK(dalloc(&p.rec_py, n));
+    MSK_CUDA_CHECK(dalloc(&p.ctrl, 1));
+    MSK_CUDA_CHECK(cudaMemset(p.ctrl, 0, sizeof(Ctrl)));
+    p.capacity = capacity;
+    impl_->capacity = capacity;
+    return MSK_OK;
+}
+
+int Renderer::render(cudaStream_t stream, const DScene &sc, const MskRenderDesc &rd, float *d_film, MskStats *stats) {
+    const uint32_t W = sc.cam.width, H = sc.cam.height;
+    const uint64_t npix64 = (uint64_t) W * H;
+    if (!W || !H || npix64 > (1ull << 27)) return fail(MSK_ERR_UNSUPPORTED, "film size %ux%u unsupported", W, H);
+    if (rd.sample_end < rd.sample_begin || rd.sample_end > rd.spp) return fail(MSK_ERR_ARG, "bad sample range");
+    if (rd.rr_depth <= 0) return fail(MSK_ERR_ARG, "\"rr_depth\" must be set to a value greater than zero!");
+    if (rd.max_depth < 0 && rd.max_depth != -1) return fail(MSK_ERR_ARG, "\"max_depth\" must be set to -1 (infinite) or a value >= 0");
+    const uint32_t npix = (uint32_t) npix64;
+    uint32_t target = rd.paths_per_batch ? rd.paths_per_batch : (8u << 20);
+    uint32_t per_batch = std::max(1u, target / npix);
+    const uint32_t nsamples = rd.sample_end - rd.sample_begin;
+    per_batch = std::min(per_batch, std::max(nsamples, 1u));
+    int rc = ensure_pool(npix * per_batch);
+    if (rc) return rc;
+    Pool &pool = impl_->pool;
+    Impl &im = *impl_;
+
+    if (rd.clear_film) MSK_CUDA_CHECK(cudaMemsetAsync(d_film, 0, (size_t) npix * 5 * sizeof(float), stream));
+    MSK_CUDA_CHECK(cudaMemsetAsync(&pool.ctrl->total_closest, 0, 2 * sizeof(unsigned long long), stream));
+    MSK_CUDA_CHECK(cudaEventRecord(im.ev[0], stream));
+    uint64_t launches = 0;
+    uint32_t max_bounces = 0, batches = 0;
+    const int pb = im.persistent_blocks;
+    for (uint32_t s0 = rd.sample_begin; s0 < rd.sample_end; s0 += per_batch) {
+        BatchParams bp;
+        bp.npix = npix; bp.width = W; bp.s0 = s0; bp.ns = std::min(per_batch, rd.sample_end - s0);
+        bp.spp = rd.spp; bp.base_seed = rd.base_seed;
+        bp.max_depth = rd.max_depth; bp.rr_depth = rd.rr_depth; bp.hide_emitters = rd.hide_emitters;
+        const uint32_t n = npix * bp.ns;
+        k_begin_batch<<<1, 1, 0, stream>>>(pool.ctrl, n);
+        k_raygen<<<(n + 255) / 256, 256, 0, stream>>>(sc, pool, bp);
+        launches += 2;
+        int cur = 0;
+        uint32_t bounce = 0;
+        // a path reaches vertex `depth` only while depth <= max_depth, and the vertex at max_depth still
+        // needs its shade pass (emission), so a bounded job runs exactly max_depth iterations
+        const uint32_t bound = rd.max_depth > 0 ? (uint32_t) rd.max_depth : (rd.max_depth == 0 ? 0u : 0xffffffffu);
+        while (bounce < bound) {
+            k_intersect<<<pb, 128, 0, stream>>>(sc, pool, cur);
+            k_shade<<<pb, 128, 0, stream>>>(sc, pool, bp, cur);
+            k_shadow<<<pb, 128, 0, stream>>>(sc, pool);
+            k_end_bounce<<<1, 1, 0, stream>>>(pool.ctrl, cur);
+            launches += 4;
+            cur ^= 1;
+            bounce++;
+            // unbounded paths (Russian roulette only): poll the queue length once it is likely short
+            if (bound == 0xffffffffu && bounce >= 4) {
+                MSK_CUDA_CHECK(cudaMemcpyAsync(im.h_ctrl, pool.ctrl, sizeof(Ctrl), cudaMemcpyDeviceToHost, stream));
+                MSK_CUDA_CHECK(cudaStreamSynchronize(stream));
+                if (im.h_ctrl->n_rays[cur] == 0) break;
+                if (bounce > 100000) return fail(MSK_ERR_CUDA, "path queue did not drain");
+            }
+        }
+        max_bounces = std::max(max_bounces, bounce);
+        k_film_records<<<(n + 255) / 256, 256, 0, stream>>>(sc, pool, bp);
+        dim3 fg((W + kFilmTileX - 1) / kFilmTileX, (H + kFilmTileY - 1) / kFilmTileY), fb(kFilmTileX, kFilmTileY);
+        k_film_gather<<<fg, fb, 0, stream>>>(sc, pool, bp, d_film, H);
+        launches += 2;
+        batches++;
+    }
+    MSK_CUDA_CHECK(cudaEventRecord(im.ev[1], stream));
+    MSK_CUDA_CHECK(cudaGetLastError());
+    if (stats) {
+        MSK_CUDA_CHECK(cudaMemcpyAsync(im.h_ctrl, pool.ctrl, sizeof(Ctrl), cudaMemcpyDeviceToHost, stream));
+        MSK_CUDA_CHECK(cudaStreamSynchronize(stream));
+        *stats = MskStats{};
+        stats->paths = (uint64_t) npix * nsamples;
+        stats->rays_closest = im.h_ctrl->total_closest;
+        stats->rays_shadow = im.h_ctrl->total_shadow;
+        stats->kernel_launches = launches;
+        stats->bounces = max_bounces; stats->batches = batches;
+        cudaEventElapsedTime(&stats->ms_render, im.ev[0], im.ev[1]);
+    }
+    return MSK_OK;
+}
+
+int Renderer::intersect(cudaStream_t stream, const DScene &sc, const MskRay *d_rays, MskHit *d_hits, size_t n) {
+    if (n > 0xfffffff0ull) return fail(MSK_ERR_UNSUPPORTED, "too many rays in one call");
+    if (!n) return MSK_OK;
+    MSK_CUDA_CHECK(cudaMemsetAsync(impl_->query_cursor, 0, sizeof(uint32_t), stream));
+    int blocks = (int) std::min<size_t>((size_t) impl_->persistent_blocks, (n + 127) / 128);
+    k_query_closest<false><<<blocks, 128, 0, stream>>>(sc, d_rays, d_hits, (uint32_t) n, impl_->query_cursor, nullptr, nullptr);
+    MSK_CUDA_CHECK(cudaGetLastError());
+    return MSK_OK;
+}
+
+int Renderer::intersect_stats(cudaStream_t stream, const DScene &sc, const MskRay *d_rays, size_t n, uint32_t *d_nodes, uint32_t *d_tris) {
+    if (n > 0xfffffff0ull) return fail(MSK_ERR_UNSUPPORTED, "too many rays in one call");
+    if (!n) return MSK_OK;
+    MSK_CUDA_CHECK(cudaMemsetAsync(impl_->query_cursor, 0, sizeof(uint32_t), stream));
+    int blocks = (int) std::min<size_t>((size_t) impl_->persistent_blocks, (n + 127) / 128);
+    k_query_closest<true><<<blocks, 128, 0, stream>>>(sc, d_rays, nullptr, (uint32_t) n, impl_->query_cursor, d_nodes, d_tris);
+    MSK_CUDA_CHECK(cudaGetLastError());
+    return MSK_OK;
+}
+
+int Renderer::occluded(cudaStream_t stream, const DScene &sc, const MskRay *d_rays, uint8_t *d_occ, size_t n) {
+    if (n > 0xfffffff0ull) return fail(MSK_ERR_UNSUPPORTED, "too many rays in one call");
+    if (!n) return MSK_OK;
+    MSK_CUDA_CHECK(cudaMemsetAsync(impl_->query_cursor, 0, sizeof(uint32_t), stream));
+    int blocks = (int) std::min<size_t>((size_t) impl_->persistent_blocks, (n + 127) / 128);
+    k_query_any<<<blocks, 128, 0, stream>>>(sc, d_rays, d_occ, (uint32_t) n, impl_->query_cursor);
+    MSK_CUDA_CHECK(cudaGetLastError());
+    return MSK_OK;
+}
+
+} // namespace msk

@@ -1,0 +1,265 @@
+"""ctypes bindings of oracle/_build/liboracle.so (see oracle/oracle.h).  TEST INFRASTRUCTURE."""
+from __future__ import annotations
+
+import ctypes as C
+import subprocess
+from pathlib import Path
+
+import numpy as np
+
+from misaki_render_b200 import capi
+
+HERE = Path(__file__).resolve().parent
+LIB = HERE / "_build" / "liboracle.so"
+REF_LIB = HERE / "_ref" / "librgb2spec_ref.so"
+REF_COEFF = HERE / "_ref" / "srgb.coeff"
+
+
+class OrcStats(C.Structure):
+    _fields_ = [("paths", C.c_uint64), ("rays_closest", C.c_uint64), ("rays_shadow", C.c_uint64), ("seconds", C.c_double),
+                ("threads", C.c_int32), ("pad_", C.c_int32)]
+
+
+def build():
+    subprocess.run(["make", "-C", str(HERE)], check=True, capture_output=True)
+
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        if not LIB.exists():
+            build()
+        L = C.CDLL(str(LIB))
+        L.orc_last_error.restype = C.c_char_p
+        L.orc_scene_create.argtypes = [C.POINTER(capi.MskSceneDesc), C.POINTER(C.c_void_p)]
+        L.orc_scene_destroy.argtypes = [C.c_void_p]
+        L.orc_scene_destroy.restype = None
+        L.orc_intersect.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int]
+        L.orc_occluded.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]
+        L.orc_intersect_margin.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]
+        L.orc_camera_rays.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]
+        L.orc_render.argtypes = [C.c_void_p, C.POINTER(capi.MskRenderDesc), C.c_void_p, C.c_int, C.POINTER(OrcStats)]
+        L.orc_trace_samples.argtypes = [C.c_void_p, C.POINTER(capi.MskRenderDesc), C.c_void_p, C.c_void_p, C.c_size_t]
+        L.orc_develop.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
+        L.orc_develop.restype = None
+        L.orc_gaussian_filter.argtypes = [C.c_float, C.POINTER(C.c_float), C.c_void_p]
+        L.orc_gaussian_filter.restype = None
+        L.orc_pcg32_floats.argtypes = [C.c_uint64, C.c_uint64, C.c_void_p, C.c_size_t]
+        L.orc_pcg32_floats.restype = None
+        L.orc_pcg32_uints.argtypes = [C.c_uint64, C.c_uint64, C.c_void_p, C.c_size_t]
+        L.orc_pcg32_uints.restype = None
+        for name in ("orc_sample_wavelength", "orc_warp", "orc_fresnel", "orc_fresnel_conductor", "orc_srgb_model_eval",
+                     "orc_spectrum_to_xyz", "orc_ggx"):
+            getattr(L, name).restype = None
+        L.orc_sample_wavelength.argtypes = [C.c_float, C.c_void_p, C.c_void_p]
+        L.orc_warp.argtypes = [C.c_int, C.c_float, C.c_float, C.c_void_p]
+        L.orc_fresnel.argtypes = [C.c_float, C.c_float, C.c_void_p]
+        L.orc_fresnel_conductor.argtypes = [C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.orc_srgb_model_eval.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.orc_spectrum_eval.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+        L.orc_spectrum_to_xyz.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.orc_ggx.argtypes = [C.c_int, C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.orc_bsdf.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 7
+        L.orc_rgb2spec_load.argtypes = [C.c_char_p]
+        L.orc_rgb2spec_load.restype = C.c_void_p
+        L.orc_rgb2spec_free.argtypes = [C.c_void_p]
+        L.orc_rgb2spec_free.restype = None
+        L.orc_rgb2spec_fetch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.orc_rgb2spec_fetch.restype = None
+        _lib = L
+    return _lib
+
+
+def _f(a, n=None):
+    a = np.ascontiguousarray(a, dtype=np.float32)
+    assert n is None or a.size == n
+    return a
+
+
+class OracleScene:
+    def __init__(self, desc):
+        self.L = lib()
+        self.desc = desc
+        self.h = C.c_void_p()
+        if self.L.orc_scene_create(C.byref(desc.c_desc()), C.byref(self.h)) != 0:
+            raise RuntimeError(self.L.orc_last_error().decode())
+        self.width, self.height = desc.width, desc.height
+
+    def close(self):
+        if self.h:
+            self.L.orc_scene_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def intersect(self, rays, brute_force=False):
+        rays = np.ascontiguousarray(rays, dtype=capi.RAY_DTYPE)
+        hits = np.empty(rays.shape[0], dtype=capi.HIT_DTYPE)
+        assert self.L.orc_intersect(self.h, rays.ctypes.data, hits.ctypes.data, rays.shape[0], int(brute_force)) == 0
+        return hits
+
+    def occluded(self, rays):
+        rays = np.ascontiguousarray(rays, dtype=capi.RAY_DTYPE)
+        occ = np.empty(rays.shape[0], dtype=np.uint8)
+        assert self.L.orc_occluded(self.h, rays.ctypes.data, occ.ctypes.data, rays.shape[0]) == 0
+        return occ
+
+    def margin(self, rays):
+        rays = np.ascontiguousarray(rays, dtype=capi.RAY_DTYPE)
+        t2 = np.empty(rays.shape[0], dtype=np.float32)
+        mb = np.empty(rays.shape[0], dtype=np.float32)
+        assert self.L.orc_intersect_margin(self.h, rays.ctypes.data, t2.ctypes.data, mb.ctypes.data, rays.shape[0]) == 0
+        return t2, mb
+
+    def camera_rays(self, samples):
+        s = _f(samples).reshape(-1, 3)
+        rays = np.empty(s.shape[0], dtype=capi.RAY_DTYPE)
+        assert self.L.orc_camera_rays(self.h, s.ctypes.data, rays.ctypes.data, s.shape[0]) == 0
+        return rays
+
+    def render(self, rd, nthreads=0, film=None):
+        if film is None:
+            film = np.zeros((self.height, self.width, 5), dtype=np.float32)
+        st = OrcStats()
+        if self.L.orc_render(self.h, C.byref(rd), film.ctypes.data, nthreads, C.byref(st)) != 0:
+            raise RuntimeError(self.L.orc_last_error().decode())
+        return film, st
+
+    def trace_samples(self, rd, pixel_sample):
+        ps = np.ascontiguousarray(pixel_sample, dtype=np.uint32).reshape(-1, 2)
+        out = np.empty((ps.shape[0], 9), dtype=np.float32)
+        assert self.L.orc_trace_samples(self.h, C.byref(rd), ps.ctypes.data, out.ctypes.data, ps.shape[0]) == 0
+        return out
+
+    def spectrum_eval(self, sid, wl):
+        wl = _f(wl, 4)
+        out = np.empty(4, dtype=np.float32)
+        assert self.L.orc_spectrum_eval(self.h, sid, wl.ctypes.data, out.ctypes.data) == 0
+        return out
+
+    def bsdf(self, bsdf_id, wi, wl, smp, wo):
+        wi, wl, smp, wo = _f(wi, 3), _f(wl, 4), _f(smp, 3), _f(wo, 3)
+        s = np.empty(10, dtype=np.float32)
+        e = np.empty(4, dtype=np.float32)
+        p = C.c_float()
+        assert self.L.orc_bsdf(self.h, bsdf_id, wi.ctypes.data, wl.ctypes.data, smp.ctypes.data, wo.ctypes.data, s.ctypes.data,
+                               e.ctypes.data, C.addressof(p)) == 0
+        return dict(wo=s[:3].copy(), pdf=float(s[3]), eta=float(s[4]), type=int(s[5]), weight=s[6:10].copy(), eval=e, eval_pdf=p.value)
+
+
+def develop(film):
+    film = np.ascontiguousarray(film, dtype=np.float32)
+    rgba = np.empty(film.shape[:2] + (4,), dtype=np.float32)
+    lib().orc_develop(film.ctypes.data, rgba.ctypes.data, film.shape[0] * film.shape[1])
+    return rgba
+
+
+def gaussian_filter(stddev=0.5):
+    r = C.c_float()
+    t = np.empty(33, dtype=np.float32)
+    lib().orc_gaussian_filter(stddev, C.byref(r), t.ctypes.data)
+    return r.value, t
+
+
+def pcg32_floats(seed, n, base_seed=0):
+    out = np.empty(n, dtype=np.float32)
+    lib().orc_pcg32_floats(seed, base_seed, out.ctypes.data, n)
+    return out
+
+
+def pcg32_uints(initstate, initseq, n):
+    out = np.empty(n, dtype=np.uint32)
+    lib().orc_pcg32_uints(initstate, initseq, out.ctypes.data, n)
+    return out
+
+
+def sample_wavelength(u):
+    wl, w = np.empty(4, np.float32), np.empty(4, np.float32)
+    lib().orc_sample_wavelength(u, wl.ctypes.data, w.ctypes.data)
+    return wl, w
+
+
+def warp(which, u, v):
+    out = np.empty(3, np.float32)
+    lib().orc_warp(which, u, v, out.ctypes.data)
+    return out
+
+
+def fresnel(cos_theta_i, eta):
+    out = np.empty(4, np.float32)
+    lib().orc_fresnel(cos_theta_i, eta, out.ctypes.data)
+    return out
+
+
+def fresnel_conductor(cos_theta_i, eta, k):
+    eta, k = _f(eta, 4), _f(k, 4)
+    out = np.empty(4, np.float32)
+    lib().orc_fresnel_conductor(cos_theta_i, eta.ctypes.data, k.ctypes.data, out.ctypes.data)
+    return out
+
+
+def srgb_model_eval(c, wl):
+    c, wl = _f(c, 3), _f(wl, 4)
+    out = np.empty(4, np.float32)
+    lib().orc_srgb_model_eval(c.ctypes.data, wl.ctypes.data, out.ctypes.data)
+    return out
+
+
+def spectrum_to_xyz(value, wl):
+    value, wl = _f(value, 4), _f(wl, 4)
+    out = np.empty(3, np.float32)
+    lib().orc_spectrum_to_xyz(value.ctypes.data, wl.ctypes.data, out.ctypes.data)
+    return out
+
+
+def ggx(which, au, av, a, b=(0, 0, 0)):
+    a, b = _f(a, 3), _f(b, 3)
+    out = np.zeros(4, np.float32)
+    lib().orc_ggx(which, au, av, a.ctypes.data, b.ctypes.data, out.ctypes.data)
+    return out
+
+
+class Rgb2Spec:
+    """The oracle's restatement of rgb2spec_load/fetch."""
+
+    def __init__(self, path=REF_COEFF):
+        self.h = lib().orc_rgb2spec_load(str(path).encode())
+        if not self.h:
+            raise RuntimeError(lib().orc_last_error().decode())
+
+    def fetch(self, rgb):
+        rgb = _f(rgb, 3)
+        out = np.empty(3, np.float32)
+        lib().orc_rgb2spec_fetch(self.h, rgb.ctypes.data, out.ctypes.data)
+        return out
+
+
+class RefRgb2Spec:
+    """The UNMODIFIED reference ext/rgb2spec/rgb2spec.c compiled into oracle/_ref (oracle/Makefile.ref)."""
+
+    def __init__(self, path=REF_COEFF):
+        self.L = C.CDLL(str(REF_LIB))
+        self.L.rgb2spec_load.restype = C.c_void_p
+        self.L.rgb2spec_load.argtypes = [C.c_char_p]
+        self.L.rgb2spec_fetch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        self.L.rgb2spec_eval_precise.restype = C.c_float
+        self.L.rgb2spec_eval_precise.argtypes = [C.c_void_p, C.c_float]
+        self.h = self.L.rgb2spec_load(str(path).encode())
+        assert self.h
+
+    def fetch(self, rgb):
+        rgb = _f(rgb, 3).copy()
+        out = np.empty(3, np.float32)
+        self.L.rgb2spec_fetch(self.h, rgb.ctypes.data, out.ctypes.data)
+        return out
+
+    def eval_precise(self, coeff, lam):
+        coeff = _f(coeff, 3).copy()
+        return self.L.rgb2spec_eval_precise(coeff.ctypes.data, lam)
