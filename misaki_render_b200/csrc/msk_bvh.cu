@@ -421,7 +421,7 @@ int bvh_build(cudaStream_t stream, const float4 *d_verts, const uint32_t *d_indi
     uint32_t nin = 1, depth = 0;
     BuildState hst{};
     while (nin) {
-        k_collapse<<<blocks_for(nin), 128, 0, stream>>>(qa, nin, qb, (uint32_t) qcap, t, (int) n, sorted, gathered, out->nodes,
+        k_collapse<<<(nin + 127) / 128, 128, 0, stream>>>(qa, nin, qb, (uint32_t) qcap, t, (int) n, sorted, gathered, out->nodes,
                                                         (uint32_t) node_cap, out->tris, st, n == 1 ? 1 : 0);
         BVH_CHECK(cudaMemcpyAsync(&hst, st, sizeof(hst), cudaMemcpyDeviceToHost, stream));
         BVH_CHECK(cudaStreamSynchronize(stream));
