@@ -39,7 +39,7 @@
 extern "C" {
 #endif
 
-#define MSK_ABI_VERSION 1
+#define MSK_ABI_VERSION 2
 
 typedef enum {
     MSK_OK            = 0,
@@ -143,7 +143,12 @@ typedef struct {
     uint64_t base_seed;     /* Sampler "base_seed" (sampler.cpp:9) */
     uint32_t clear_film;    /* 1: zero the film first; 0: accumulate on top */
     uint32_t paths_per_batch; /* 0 = default pool size */
+    uint32_t flags;         /* MSK_RENDER_* */
+    uint32_t pad_;
 } MskRenderDesc;
+
+#define MSK_RENDER_STAGE_TIMERS 1u /* fill MskStats::ms_{raygen,intersect,shade,shadow,film} (adds event records) */
+#define MSK_RENDER_TRAVERSAL_STATS 2u /* run the instrumented traversal kernels and fill MskStats::nodes_*, tris_* */
 
 typedef struct {
     uint64_t paths;          /* camera samples completed */
@@ -155,6 +160,11 @@ typedef struct {
     float    ms_shadow, ms_shade, ms_raygen, ms_film;
     uint32_t bounces;        /* wavefront iterations executed (max over batches) */
     uint32_t batches;
+    uint32_t n_intersect_launches, n_shade_launches, n_shadow_launches; /* with MSK_RENDER_STAGE_TIMERS */
+    uint32_t pad_;
+    uint64_t shaded_vertices; /* path vertices processed by the shade stage (hits + misses) */
+    uint64_t nodes_closest, tris_closest; /* with MSK_RENDER_TRAVERSAL_STATS: wide nodes visited / triangles */
+    uint64_t nodes_shadow, tris_shadow;   /*   tested, summed over all closest-hit / any-hit queries        */
 } MskStats;
 
 typedef struct { float o[3]; float tmin; float d[3]; float tmax; } MskRay;     /* 32 B */

@@ -27,6 +27,9 @@ EXPORTED_SYMBOLS = [
 SPEC_UNIFORM, SPEC_SRGB, SPEC_SRGB_D65, SPEC_REGULAR, SPEC_SRGB_UNBOUNDED = range(5)
 BSDF_DIFFUSE, BSDF_CONDUCTOR, BSDF_ROUGHCONDUCTOR, BSDF_ROUGHDIELECTRIC, BSDF_DIELECTRIC = range(5)
 EMITTER_AREA, EMITTER_CONSTANT = range(2)
+RENDER_STAGE_TIMERS = 1
+RENDER_TRAVERSAL_STATS = 2
+ABI_VERSION = 2
 
 
 class MskError(RuntimeError):
@@ -72,13 +75,16 @@ class MskSceneDesc(C.Structure):
 class MskRenderDesc(C.Structure):
     _fields_ = [("spp", C.c_uint32), ("sample_begin", C.c_uint32), ("sample_end", C.c_uint32), ("max_depth", C.c_int32),
                 ("rr_depth", C.c_int32), ("hide_emitters", C.c_int32), ("base_seed", C.c_uint64), ("clear_film", C.c_uint32),
-                ("paths_per_batch", C.c_uint32)]
+                ("paths_per_batch", C.c_uint32), ("flags", C.c_uint32), ("pad_", C.c_uint32)]
 
 
 class MskStats(C.Structure):
     _fields_ = [("paths", C.c_uint64), ("rays_closest", C.c_uint64), ("rays_shadow", C.c_uint64), ("kernel_launches", C.c_uint64),
                 ("ms_render", C.c_float), ("ms_intersect", C.c_float), ("ms_shadow", C.c_float), ("ms_shade", C.c_float),
-                ("ms_raygen", C.c_float), ("ms_film", C.c_float), ("bounces", C.c_uint32), ("batches", C.c_uint32)]
+                ("ms_raygen", C.c_float), ("ms_film", C.c_float), ("bounces", C.c_uint32), ("batches", C.c_uint32),
+                ("n_intersect_launches", C.c_uint32), ("n_shade_launches", C.c_uint32), ("n_shadow_launches", C.c_uint32),
+                ("pad_", C.c_uint32), ("shaded_vertices", C.c_uint64), ("nodes_closest", C.c_uint64),
+                ("tris_closest", C.c_uint64), ("nodes_shadow", C.c_uint64), ("tris_shadow", C.c_uint64)]
 
 
 class MskAccelInfo(C.Structure):
@@ -132,7 +138,7 @@ def check(lib, rc):
 
 
 def render_desc(spp, max_depth=-1, rr_depth=5, hide_emitters=False, base_seed=0, sample_begin=0, sample_end=None,
-                clear_film=True, paths_per_batch=0) -> MskRenderDesc:
+                clear_film=True, paths_per_batch=0, stage_timers=False, traversal_stats=False) -> MskRenderDesc:
     rd = MskRenderDesc()
     rd.spp = spp
     rd.sample_begin = sample_begin
@@ -143,6 +149,7 @@ def render_desc(spp, max_depth=-1, rr_depth=5, hide_emitters=False, base_seed=0,
     rd.base_seed = base_seed
     rd.clear_film = int(clear_film)
     rd.paths_per_batch = paths_per_batch
+    rd.flags = (RENDER_STAGE_TIMERS if stage_timers else 0) | (RENDER_TRAVERSAL_STATS if traversal_stats else 0)
     return rd
 
 

@@ -43,6 +43,8 @@ struct MskCtx {
     int sm_count = 0;
     cudaStream_t stream = nullptr;
     Renderer renderer;
+    float *film_cache = nullptr; // device staging film of msk_gpu_render (host-buffer entry point)
+    size_t film_cache_bytes = 0;
 };
 
 struct MskScene {
@@ -118,6 +120,7 @@ void msk_gpu_shutdown(MskCtx *ctx) {
     DeviceGuard guard(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     ctx->renderer.release();
+    cudaFree(ctx->film_cache);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -402,15 +405,19 @@ int msk_gpu_render(MskScene *s, const MskRenderDesc *rd, float *film_host, MskSt
     DeviceGuard guard(s->ctx->device);
     cudaStream_t st = s->ctx->stream;
     size_t bytes = (size_t) s->d.cam.width * s->d.cam.height * 5 * sizeof(float);
-    float *d_film = nullptr;
-    MSK_CUDA_CHECK(cudaMalloc((void **) &d_film, bytes));
+    MskCtx *ctx = s->ctx;
+    if (ctx->film_cache_bytes < bytes) { // staging film kept across calls: no allocator traffic per render
+        cudaFree(ctx->film_cache); ctx->film_cache = nullptr; ctx->film_cache_bytes = 0;
+        MSK_CUDA_CHECK(cudaMalloc((void **) &ctx->film_cache, bytes));
+        ctx->film_cache_bytes = bytes;
+    }
+    float *d_film = ctx->film_cache;
     cudaError_t e = cudaSuccess;
     if (!rd->clear_film) e = cudaMemcpyAsync(d_film, film_host, bytes, cudaMemcpyHostToDevice, st);
     int rc = MSK_OK;
-    if (e == cudaSuccess) rc = s->ctx->renderer.render(st, s->d, *rd, d_film, stats);
+    if (e == cudaSuccess) rc = ctx->renderer.render(st, s->d, *rd, d_film, stats);
     if (e == cudaSuccess && !rc) e = cudaMemcpyAsync(film_host, d_film, bytes, cudaMemcpyDeviceToHost, st);
     if (e == cudaSuccess && !rc) e = cudaStreamSynchronize(st);
-    cudaFree(d_film);
     if (e != cudaSuccess) return cuda_fail(e, "msk_gpu_render", __FILE__, __LINE__);
     return rc;
 }

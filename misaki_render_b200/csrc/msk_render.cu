@@ -25,6 +25,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <vector>
 
 namespace msk {
 
@@ -39,6 +40,8 @@ struct Ctrl {
     uint32_t type_count[kNumKeys];
     uint32_t pad_;
     unsigned long long total_closest, total_shadow;
+    unsigned long long nodes_closest, tris_closest, nodes_shadow, tris_shadow; // MSK_RENDER_TRAVERSAL_STATS
+    unsigned long long shaded; // path vertices processed by k_shade
 };
 
 struct Pool {
@@ -80,6 +83,7 @@ __global__ void k_begin_batch(Ctrl *c, uint32_t n) {
 __global__ void k_end_bounce(Ctrl *c, int cur) {
     c->total_closest += c->n_rays[cur];
     c->total_shadow += c->n_shadow;
+    for (int i = 0; i < kNumKeys; ++i) c->shaded += c->type_count[i];
     c->n_rays[cur] = 0; c->n_shadow = 0; c->cursor_isect = 0; c->cursor_shadow = 0;
     for (int i = 0; i < kNumKeys; ++i) c->type_count[i] = 0;
 }
@@ -113,10 +117,17 @@ __global__ void __launch_bounds__(256) k_raygen(const __grid_constant__ DScene s
 
 // ---------------------------------------------------------------------------------------
 // Closest hit over the current ray queue (Scene::ray_intersect, scene.cpp:216-253) + classification.
+__device__ __forceinline__ void add_traversal_stats(unsigned long long *nodes, unsigned long long *tris, uint32_t cn, uint32_t ct) {
+    for (int o = 16; o; o >>= 1) { cn += __shfl_xor_sync(0xffffffffu, cn, o); ct += __shfl_xor_sync(0xffffffffu, ct, o); }
+    if (lane_id() == 0) { atomicAdd(nodes, (unsigned long long) cn); atomicAdd(tris, (unsigned long long) ct); }
+}
+
+template <bool STATS>
 __global__ void __launch_bounds__(128) k_intersect(const __grid_constant__ DScene sc, Pool pool, int cur) {
     Ctrl *c = pool.ctrl;
     const uint32_t n = c->n_rays[cur];
     const MskRay *rays = pool.rays[cur];
+    uint32_t cn_total = 0, ct_total = 0;
     for (;;) {
         uint32_t base = 0;
         if (lane_id() == 0) base = atomicAdd(&c->cursor_isect, 32u);
@@ -130,7 +141,9 @@ __global__ void __launch_bounds__(128) k_intersect(const __grid_constant__ DScen
             float4 ro = __ldcs(rp), rd = __ldcs(rp + 1);
             RayHit h;
             h.t = MSK_INF; h.u = 0.f; h.v = 0.f; h.prim = 0xffffffffu; h.geom = 0xffffffffu;
-            bool found = traverse<false, false>(sc.nodes, sc.tris, ro.x, ro.y, ro.z, rd.x, rd.y, rd.z, ro.w, rd.w, h);
+            uint32_t cn = 0, ct = 0;
+            bool found = traverse<false, STATS>(sc.nodes, sc.tris, ro.x, ro.y, ro.z, rd.x, rd.y, rd.z, ro.w, rd.w, h, &cn, &ct);
+            if (STATS) { cn_total += cn; ct_total += ct; }
             if (found && h.t == rd.w) found = false; // hit <=> tfar != maxt, scene.cpp:234
             if (!found) { h.t = MSK_INF; h.geom = 0xffffffffu; }
             pool.hit[q]      = make_float4(h.t, h.u, h.v, __uint_as_float(h.prim));
@@ -149,6 +162,7 @@ __global__ void __launch_bounds__(128) k_intersect(const __grid_constant__ DScen
             pool.sorted[(size_t) key * pool.capacity + slot + rank] = q;
         }
     }
+    if (STATS) add_traversal_stats(&c->nodes_closest, &c->tris_closest, cn_total, ct_total);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -299,9 +313,11 @@ __global__ void __launch_bounds__(128) k_shade(const __grid_constant__ DScene sc
 // ---------------------------------------------------------------------------------------
 // NEE visibility (Scene::ray_test, scene.cpp:90-98,255-273) fused with the accumulation of
 // the NEE term (path.cpp:63-66).
+template <bool STATS>
 __global__ void __launch_bounds__(128) k_shadow(const __grid_constant__ DScene sc, Pool pool) {
     Ctrl *c = pool.ctrl;
     const uint32_t n = c->n_shadow;
+    uint32_t cn_total = 0, ct_total = 0;
     for (;;) {
         uint32_t base = 0;
         if (lane_id() == 0) base = atomicAdd(&c->cursor_shadow, 32u);
@@ -312,7 +328,9 @@ __global__ void __launch_bounds__(128) k_shadow(const __grid_constant__ DScene s
             const float4 *rp = reinterpret_cast<const float4 *>(pool.sh_ray + q);
             float4 ro = __ldcs(rp), rd = __ldcs(rp + 1);
             RayHit h;
-            bool occluded = traverse<true, false>(sc.nodes, sc.tris, ro.x, ro.y, ro.z, rd.x, rd.y, rd.z, ro.w, rd.w, h);
+            uint32_t cn = 0, ct = 0;
+            bool occluded = traverse<true, STATS>(sc.nodes, sc.tris, ro.x, ro.y, ro.z, rd.x, rd.y, rd.z, ro.w, rd.w, h, &cn, &ct);
+            if (STATS) { cn_total += cn; ct_total += ct; }
             if (occluded && h.t == rd.w) occluded = false; // scene.cpp:272
             if (!occluded) {
                 uint32_t path = pool.sh_path[q];
@@ -321,6 +339,7 @@ __global__ void __launch_bounds__(128) k_shadow(const __grid_constant__ DScene s
             }
         }
     }
+    if (STATS) add_traversal_stats(&c->nodes_shadow, &c->tris_shadow, cn_total, ct_total);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -348,6 +367,7 @@ __global__ void __launch_bounds__(256) k_film_records(const __grid_constant__ DS
 // the filter support looks up table[32] == 0 and adds nothing, exactly like the reference's
 // lo/hi clipping (rfilter.h:13-16).
 constexpr int kFilmTileX = 32, kFilmTileY = 8;
+constexpr int kBlockSize = 32; // MSK_BLOCK_SIZE, imageblock.h:8
 __global__ void __launch_bounds__(kFilmTileX *kFilmTileY) k_film_gather(const __grid_constant__ DScene sc, Pool pool,
                                                                          BatchParams bp, float *__restrict__ film,
                                                                          uint32_t height) {
@@ -355,7 +375,7 @@ __global__ void __launch_bounds__(kFilmTileX *kFilmTileY) k_film_gather(const __
     const int W = (int) bp.width, H = (int) height;
     if (x >= W || y >= H) return;
     const int r = (int) ceilf(sc.cam.filter_radius - 0.5f); // border size, rfilter.cpp:22
-    const float scale = sc.cam.filter_scale;
+    const float scale = sc.cam.filter_scale, radius = sc.cam.filter_radius;
     float aX = 0.f, aY = 0.f, aZ = 0.f, aW = 0.f;
     for (uint32_t s = 0; s < bp.ns; ++s) {
         const size_t sbase = (size_t) s * bp.npix;
@@ -364,12 +384,16 @@ __global__ void __launch_bounds__(kFilmTileX *kFilmTileY) k_film_gather(const __
                 size_t i = sbase + (size_t) ny * W + nx;
                 float4 rec = __ldg(pool.rec + i);
                 float py = __ldg(pool.rec_py + i);
-                // pos - 0.5 is exact in float for every representable sample position
-                float dx = (float) x - (rec.w - 0.5f), dy = (float) y - (py - 0.5f);
-                float wx = __ldg(sc.filter_table + min((int) fabsf(dx * scale), 32));
-                float wy = __ldg(sc.filter_table + min((int) fabsf(dy * scale), 32));
-                // the reference only visits ceil(pos-r) .. floor(pos+r); outside, |d| > radius
-                if (fabsf(dx) > sc.cam.filter_radius || fabsf(dy) > sc.cam.filter_radius) continue;
+                // The sample was splatted into the 32x32 ImageBlock of its own pixel (nx, ny), in
+                // block-relative float coordinates (imageblock.cpp:86-98): reproduce that rounding,
+                // because the 33-entry weight table is a step function of |x - pos|.
+                const int bx = (nx & ~(kBlockSize - 1)) - r, by = (ny & ~(kBlockSize - 1)) - r; // m_offset - m_border_size
+                const float posx = rec.w - 0.5f - (float) bx, posy = py - 0.5f - (float) by;
+                const float xb = (float) (x - bx), yb = (float) (y - by);
+                // lo = ceil(pos - radius) <= x <= floor(pos + radius) = hi
+                if (xb < posx - radius || xb > posx + radius || yb < posy - radius || yb > posy + radius) continue;
+                float wx = __ldg(sc.filter_table + min((int) fabsf((xb - posx) * scale), 32));
+                float wy = __ldg(sc.filter_table + min((int) fabsf((yb - posy) * scale), 32));
                 float w = wx * wy;
                 aX += w * rec.x; aY += w * rec.y; aZ += w * rec.z; aW += w;
             }
@@ -439,6 +463,8 @@ struct Renderer::Impl {
     uint32_t *query_cursor = nullptr;
     Ctrl *h_ctrl = nullptr; // pinned
     cudaEvent_t ev[8]{};
+    std::vector<cudaEvent_t> timer_events; // MSK_RENDER_STAGE_TIMERS
+    std::vector<int> timer_stage;
     int persistent_blocks = 0;
 };
 
@@ -455,6 +481,8 @@ void Renderer::release() {
     cudaFree(impl_->query_cursor); impl_->query_cursor = nullptr;
     if (impl_->h_ctrl) { cudaFreeHost(impl_->h_ctrl); impl_->h_ctrl = nullptr; }
     for (auto &e : impl_->ev) if (e) { cudaEventDestroy(e); e = nullptr; }
+    for (auto &e : impl_->timer_events) cudaEventDestroy(e);
+    impl_->timer_events.clear();
 }
 
 int Renderer::init(int sm_count) {
@@ -506,11 +534,35 @@ int Renderer::render(cudaStream_t stream, const DScene &sc, const MskRenderDesc 
     Impl &im = *impl_;
 
     if (rd.clear_film) MSK_CUDA_CHECK(cudaMemsetAsync(d_film, 0, (size_t) npix * 5 * sizeof(float), stream));
-    MSK_CUDA_CHECK(cudaMemsetAsync(&pool.ctrl->total_closest, 0, 2 * sizeof(unsigned long long), stream));
+    MSK_CUDA_CHECK(cudaMemsetAsync(&pool.ctrl->total_closest, 0, 7 * sizeof(unsigned long long), stream));
+    const bool tstats = (rd.flags & MSK_RENDER_TRAVERSAL_STATS) != 0;
     MSK_CUDA_CHECK(cudaEventRecord(im.ev[0], stream));
     uint64_t launches = 0;
     uint32_t max_bounces = 0, batches = 0;
     const int pb = im.persistent_blocks;
+    // MSK_RENDER_STAGE_TIMERS: bracket every launch with a pair of events (a profiling aid used by bench.py
+    // for the per-kernel roofline; the extra event records perturb ms_render slightly, so it is off by default)
+    const bool timers = (rd.flags & MSK_RENDER_STAGE_TIMERS) != 0;
+    enum { ST_RAYGEN, ST_INTERSECT, ST_SHADE, ST_SHADOW, ST_FILM, ST_COUNT };
+    std::vector<int> &tstage = im.timer_stage;
+    tstage.clear();
+    size_t tev = 0;
+    auto stage_begin = [&](int st) -> int {
+        if (!timers) return MSK_OK;
+        if (tev + 2 > im.timer_events.size()) {
+            for (int k = 0; k < 2; ++k) { cudaEvent_t e; MSK_CUDA_CHECK(cudaEventCreate(&e)); im.timer_events.push_back(e); }
+        }
+        tstage.push_back(st);
+        MSK_CUDA_CHECK(cudaEventRecord(im.timer_events[tev], stream));
+        return MSK_OK;
+    };
+    auto stage_end = [&]() -> int {
+        if (!timers) return MSK_OK;
+        MSK_CUDA_CHECK(cudaEventRecord(im.timer_events[tev + 1], stream));
+        tev += 2;
+        return MSK_OK;
+    };
+#define MSK_STAGE(st, launch) do { int rc__ = stage_begin(st); if (rc__) return rc__; launch; launches++; rc__ = stage_end(); if (rc__) return rc__; } while (0)
     for (uint32_t s0 = rd.sample_begin; s0 < rd.sample_end; s0 += per_batch) {
         BatchParams bp;
         bp.npix = npix; bp.width = W; bp.s0 = s0; bp.ns = std::min(per_batch, rd.sample_end - s0);
@@ -518,19 +570,21 @@ int Renderer::render(cudaStream_t stream, const DScene &sc, const MskRenderDesc 
         bp.max_depth = rd.max_depth; bp.rr_depth = rd.rr_depth; bp.hide_emitters = rd.hide_emitters;
         const uint32_t n = npix * bp.ns;
         k_begin_batch<<<1, 1, 0, stream>>>(pool.ctrl, n);
-        k_raygen<<<(n + 255) / 256, 256, 0, stream>>>(sc, pool, bp);
-        launches += 2;
+        launches++;
+        MSK_STAGE(ST_RAYGEN, (k_raygen<<<(n + 255) / 256, 256, 0, stream>>>(sc, pool, bp)));
         int cur = 0;
         uint32_t bounce = 0;
         // a path reaches vertex `depth` only while depth <= max_depth, and the vertex at max_depth still
         // needs its shade pass (emission), so a bounded job runs exactly max_depth iterations
         const uint32_t bound = rd.max_depth > 0 ? (uint32_t) rd.max_depth : (rd.max_depth == 0 ? 0u : 0xffffffffu);
         while (bounce < bound) {
-            k_intersect<<<pb, 128, 0, stream>>>(sc, pool, cur);
-            k_shade<<<pb, 128, 0, stream>>>(sc, pool, bp, cur);
-            k_shadow<<<pb, 128, 0, stream>>>(sc, pool);
+            if (tstats) MSK_STAGE(ST_INTERSECT, (k_intersect<true><<<pb, 128, 0, stream>>>(sc, pool, cur)));
+            else MSK_STAGE(ST_INTERSECT, (k_intersect<false><<<pb, 128, 0, stream>>>(sc, pool, cur)));
+            MSK_STAGE(ST_SHADE, (k_shade<<<pb, 128, 0, stream>>>(sc, pool, bp, cur)));
+            if (tstats) MSK_STAGE(ST_SHADOW, (k_shadow<true><<<pb, 128, 0, stream>>>(sc, pool)));
+            else MSK_STAGE(ST_SHADOW, (k_shadow<false><<<pb, 128, 0, stream>>>(sc, pool)));
             k_end_bounce<<<1, 1, 0, stream>>>(pool.ctrl, cur);
-            launches += 4;
+            launches++;
             cur ^= 1;
             bounce++;
             // unbounded paths (Russian roulette only): poll the queue length once it is likely short
@@ -542,12 +596,12 @@ int Renderer::render(cudaStream_t stream, const DScene &sc, const MskRenderDesc 
             }
         }
         max_bounces = std::max(max_bounces, bounce);
-        k_film_records<<<(n + 255) / 256, 256, 0, stream>>>(sc, pool, bp);
+        MSK_STAGE(ST_FILM, (k_film_records<<<(n + 255) / 256, 256, 0, stream>>>(sc, pool, bp)));
         dim3 fg((W + kFilmTileX - 1) / kFilmTileX, (H + kFilmTileY - 1) / kFilmTileY), fb(kFilmTileX, kFilmTileY);
-        k_film_gather<<<fg, fb, 0, stream>>>(sc, pool, bp, d_film, H);
-        launches += 2;
+        MSK_STAGE(ST_FILM, (k_film_gather<<<fg, fb, 0, stream>>>(sc, pool, bp, d_film, H)));
         batches++;
     }
+#undef MSK_STAGE
     MSK_CUDA_CHECK(cudaEventRecord(im.ev[1], stream));
     MSK_CUDA_CHECK(cudaGetLastError());
     if (stats) {
@@ -557,9 +611,25 @@ int Renderer::render(cudaStream_t stream, const DScene &sc, const MskRenderDesc 
         stats->paths = (uint64_t) npix * nsamples;
         stats->rays_closest = im.h_ctrl->total_closest;
         stats->rays_shadow = im.h_ctrl->total_shadow;
+        stats->shaded_vertices = im.h_ctrl->shaded;
+        stats->nodes_closest = im.h_ctrl->nodes_closest; stats->tris_closest = im.h_ctrl->tris_closest;
+        stats->nodes_shadow = im.h_ctrl->nodes_shadow; stats->tris_shadow = im.h_ctrl->tris_shadow;
         stats->kernel_launches = launches;
         stats->bounces = max_bounces; stats->batches = batches;
         cudaEventElapsedTime(&stats->ms_render, im.ev[0], im.ev[1]);
+        if (timers) {
+            float acc[ST_COUNT] = {};
+            uint32_t cnt[ST_COUNT] = {};
+            for (size_t k = 0; k < tstage.size(); ++k) {
+                float ms = 0.f;
+                cudaEventElapsedTime(&ms, im.timer_events[2 * k], im.timer_events[2 * k + 1]);
+                acc[tstage[k]] += ms; cnt[tstage[k]]++;
+            }
+            stats->ms_raygen = acc[ST_RAYGEN]; stats->ms_intersect = acc[ST_INTERSECT]; stats->ms_shade = acc[ST_SHADE];
+            stats->ms_shadow = acc[ST_SHADOW]; stats->ms_film = acc[ST_FILM];
+            stats->n_intersect_launches = cnt[ST_INTERSECT]; stats->n_shade_launches = cnt[ST_SHADE];
+            stats->n_shadow_launches = cnt[ST_SHADOW];
+        }
     }
     return MSK_OK;
 }

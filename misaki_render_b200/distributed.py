@@ -1,0 +1,62 @@
+"""Multi-GPU sharding of the render job: one process per GPU, the scene and BVH
+replicated, the camera samples of every pixel partitioned by SAMPLE RANGE, and one sum-reduction of the
+XYZAW film to rank 0 (NCCL over NVLink; gloo in the CPU tests).
+
+The reference has a single shared-memory level of parallelism -- tbb::parallel_for over 32x32 tiles with a
+mutex-guarded Film::put (src/librender/integrator.cpp:54-75, films/hdrfilm.cpp:43-46).  Because sample
+(pixel p, index s) is seeded with Sampler::seed(p * spp + s) (samplers/independent.cpp:20-26), the union of
+the ranks' sample ranges reproduces the single-GPU job up to float summation order, and the film channels
+are plain sums (the division by W happens in HDRFilm::image, hdrfilm.cpp:71-76), so the only exchange step
+is that reduction.  Tile partitioning would still need a sum because the 2-pixel filter border of
+neighbouring tiles overlaps (imageblock.cpp:40-48).
+"""
+from __future__ import annotations
+
+import copy
+
+from . import capi
+
+
+def shard_samples(spp: int, rank: int, world: int) -> tuple[int, int]:
+    """Contiguous, balanced sample range [begin, end) of rank `rank`; ranges tile [0, spp) exactly.
+    Ranks beyond `spp` get an empty range."""
+    if world <= 0 or not (0 <= rank < world):
+        raise ValueError(f"bad rank {rank} / world {world}")
+    base, rem = divmod(int(spp), world)
+    begin = rank * base + min(rank, rem)
+    return begin, begin + base + (1 if rank < rem else 0)
+
+
+def shard_desc(rd: capi.MskRenderDesc, rank: int, world: int) -> capi.MskRenderDesc:
+    """The MskRenderDesc of this rank: same job (spp, seeds, depths), its own sub-range of rd's sample range."""
+    out = copy.copy(rd)
+    n = rd.sample_end - rd.sample_begin
+    b, e = shard_samples(n, rank, world)
+    out.sample_begin, out.sample_end = rd.sample_begin + b, rd.sample_begin + e
+    out.clear_film = 1
+    return out
+
+
+def reduce_film(film, dst: int = 0, group=None):
+    """Sum the per-rank XYZAW films into rank `dst` (in place).  `film` is a torch tensor (CUDA for NCCL,
+    CPU for gloo).  A no-op without an initialised process group."""
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.reduce(film, dst=dst, op=dist.ReduceOp.SUM, group=group)
+    return film
+
+
+def render_sharded(scene: capi.Scene, rd: capi.MskRenderDesc, film_dev, rank: int, world: int, group=None,
+                   host_out=None):
+    """Render this rank's share of `rd` into the CUDA tensor `film_dev` (H x W x 5 float32) on the context's
+    stream, reduce to rank 0, and (rank 0, if `host_out` -- a pinned CPU tensor -- is given) copy the final
+    film to the host.  Returns this rank's MskStats."""
+    import torch
+    ext = torch.cuda.ExternalStream(scene.ctx.stream, device=film_dev.device)
+    with torch.cuda.stream(ext):
+        stats = scene.render_dev(shard_desc(rd, rank, world), film_dev.data_ptr())
+        reduce_film(film_dev, 0, group)
+        if host_out is not None and rank == 0:
+            host_out.copy_(film_dev, non_blocking=True)
+        ext.synchronize()
+    return stats

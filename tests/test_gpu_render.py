@@ -33,7 +33,9 @@ def test_cbox_equal_seed(gpu_ctx):
     assert stats.paths == 64 * 64 * 16
     # same paths => same ray counts up to rare branch flips
     assert abs(int(stats.rays_closest) - int(ost.rays_closest)) <= 1e-3 * ost.rays_closest
-    assert abs(int(stats.rays_shadow) - int(ost.rays_shadow)) <= 2e-2 * ost.rays_shadow + 8
+    # the GPU path does not trace shadow rays whose NEE contribution is exactly zero (BSDF value 0 for a light
+    # direction below the surface): an output-equivalent skip, so its any-hit count is a subset of the oracle's
+    assert 0.7 * ost.rays_shadow <= stats.rays_shadow <= ost.rays_shadow
 
 
 def test_cbox_unbounded_depth_rr(gpu_ctx):
