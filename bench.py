@@ -320,7 +320,7 @@ def run_ours(args, rank: int, local_rank: int, world: int):
                 traffic = json.loads(tf.read_text()).get(args.workload, {}).get(top)
             except (ValueError, OSError):
                 traffic = None
-        stage_ms = {"raygen": st_t.ms_raygen, "intersect": st_t.ms_intersect, "shade": st_t.ms_shade, "shadow": st_t.ms_shadow,
+        stage_ms = {"raygen": st_t.ms_raygen, "intersect": st_t.ms_intersect, "sort": st_t.ms_sort, "shade": st_t.ms_shade, "shadow": st_t.ms_shadow,
                     "film": st_t.ms_film, "step_with_timers": st_t.ms_render}
         roofline = {
             "bound": "hbm", "kernel": top, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,

@@ -165,6 +165,8 @@ typedef struct {
     uint64_t shaded_vertices; /* path vertices processed by the shade stage (hits + misses) */
     uint64_t nodes_closest, tris_closest; /* with MSK_RENDER_TRAVERSAL_STATS: wide nodes visited / triangles */
     uint64_t nodes_shadow, tris_shadow;   /*   tested, summed over all closest-hit / any-hit queries        */
+    float    ms_sort;        /* device time of the material sort launches (with MSK_RENDER_STAGE_TIMERS) */
+    uint32_t pad2_;
 } MskStats;
 
 typedef struct { float o[3]; float tmin; float d[3]; float tmax; } MskRay;     /* 32 B */

@@ -14,7 +14,8 @@ from pathlib import Path
 import numpy as np
 
 ROOT = Path(__file__).resolve().parent
-LIB_PATH = ROOT / "lib" / "libmisaki_b200.so"
+# MSK_B200_LIB: development override used by tools/sweep_variants.sh to compare builds of the same library
+LIB_PATH = Path(os.environ["MSK_B200_LIB"]) if os.environ.get("MSK_B200_LIB") else ROOT / "lib" / "libmisaki_b200.so"
 
 EXPORTED_SYMBOLS = [
     "msk_gpu_abi_version", "msk_gpu_last_error", "msk_gpu_init", "msk_gpu_shutdown", "msk_gpu_stream",
@@ -84,7 +85,8 @@ class MskStats(C.Structure):
                 ("ms_raygen", C.c_float), ("ms_film", C.c_float), ("bounces", C.c_uint32), ("batches", C.c_uint32),
                 ("n_intersect_launches", C.c_uint32), ("n_shade_launches", C.c_uint32), ("n_shadow_launches", C.c_uint32),
                 ("pad_", C.c_uint32), ("shaded_vertices", C.c_uint64), ("nodes_closest", C.c_uint64),
-                ("tris_closest", C.c_uint64), ("nodes_shadow", C.c_uint64), ("tris_shadow", C.c_uint64)]
+                ("tris_closest", C.c_uint64), ("nodes_shadow", C.c_uint64), ("tris_shadow", C.c_uint64),
+                ("ms_sort", C.c_float), ("pad2_", C.c_uint32)]
 
 
 class MskAccelInfo(C.Structure):

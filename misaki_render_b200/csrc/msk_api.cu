@@ -299,7 +299,7 @@ int msk_gpu_scene_create(MskCtx *ctx, const MskSceneDesc *d, MskScene **out) {
     s->d.cam.filter_scale = 32.f / d->camera.filter_radius; // rfilter.cpp:21
 
     if ((rc = bvh_build(ctx->stream, d_verts, d_indices, infos, &s->bvh))) return bail(rc);
-    if (s->bvh.depth + 2 > (uint32_t) 48)
+    if (2 * s->bvh.depth + 2 > (uint32_t) 64) // node groups + postponed triangle groups, msk_traverse.cuh kStackSize
         return bail(fail(MSK_ERR_UNSUPPORTED, "BVH depth %u exceeds the traversal stack", s->bvh.depth));
     s->d.nodes = s->bvh.nodes; s->d.tris = s->bvh.tris;
     cudaError_t es = cudaStreamSynchronize(ctx->stream);

@@ -31,6 +31,9 @@ namespace msk {
 
 namespace {
 
+#ifndef MSK_TRAV_MIN_BLOCKS
+#define MSK_TRAV_MIN_BLOCKS 6 /* resident 128-thread CTAs per SM the traversal kernels are compiled for (<= 80 registers) */
+#endif
 constexpr int kNumKeys = 1 + MSK_BSDF_TYPE_COUNT; // 0 = miss, 1 + bsdf type
 
 struct Ctrl {
@@ -55,9 +58,9 @@ struct Pool {
     MskRay  *sh_ray;
     float4  *sh_contrib;
     uint32_t *sh_path;
-    uint32_t *sorted;               // kNumKeys segments of `capacity` queue indices
     float4  *rec;                   // X, Y, Z, pos.x
     float   *rec_py;
+    uint32_t *sorted;               // kNumKeys segments of `capacity` queue indices
     Ctrl    *ctrl;
 };
 
@@ -83,7 +86,7 @@ __global__ void k_begin_batch(Ctrl *c, uint32_t n) {
 __global__ void k_end_bounce(Ctrl *c, int cur) {
     c->total_closest += c->n_rays[cur];
     c->total_shadow += c->n_shadow;
-    for (int i = 0; i < kNumKeys; ++i) c->shaded += c->type_count[i];
+    c->shaded += c->n_rays[cur];
     c->n_rays[cur] = 0; c->n_shadow = 0; c->cursor_isect = 0; c->cursor_shadow = 0;
     for (int i = 0; i < kNumKeys; ++i) c->type_count[i] = 0;
 }
@@ -122,53 +125,109 @@ __device__ __forceinline__ void add_traversal_stats(unsigned long long *nodes, u
     if (lane_id() == 0) { atomicAdd(nodes, (unsigned long long) cn); atomicAdd(tris, (unsigned long long) ct); }
 }
 
+// IO adaptor of trace_queue: reads the current ray queue, writes the hit record.
+#ifndef MSK_SORT_IN_COMMIT
+#define MSK_SORT_IN_COMMIT 0
+#endif
 template <bool STATS>
-__global__ void __launch_bounds__(128) k_intersect(const __grid_constant__ DScene sc, Pool pool, int cur) {
-    Ctrl *c = pool.ctrl;
-    const uint32_t n = c->n_rays[cur];
-    const MskRay *rays = pool.rays[cur];
+struct IntersectIO {
+    const Pool &pool;
+    const MskRay *rays;
+    const DScene *scp = nullptr;
     uint32_t cn_total = 0, ct_total = 0;
-    for (;;) {
-        uint32_t base = 0;
-        if (lane_id() == 0) base = atomicAdd(&c->cursor_isect, 32u);
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (base >= n) break;
-        uint32_t q = base + lane_id();
-        bool valid = q < n;
-        uint32_t key = 0xffffffffu;
-        if (valid) {
-            const float4 *rp = reinterpret_cast<const float4 *>(rays + q);
-            float4 ro = __ldcs(rp), rd = __ldcs(rp + 1);
-            RayHit h;
-            h.t = MSK_INF; h.u = 0.f; h.v = 0.f; h.prim = 0xffffffffu; h.geom = 0xffffffffu;
-            uint32_t cn = 0, ct = 0;
-            bool found = traverse<false, STATS>(sc.nodes, sc.tris, ro.x, ro.y, ro.z, rd.x, rd.y, rd.z, ro.w, rd.w, h, &cn, &ct);
-            if (STATS) { cn_total += cn; ct_total += ct; }
-            if (found && h.t == rd.w) found = false; // hit <=> tfar != maxt, scene.cpp:234
-            if (!found) { h.t = MSK_INF; h.geom = 0xffffffffu; }
-            pool.hit[q]      = make_float4(h.t, h.u, h.v, __uint_as_float(h.prim));
-            pool.hit_geom[q] = h.geom;
-            key = found ? 1u + (uint32_t) sc.bsdfs[sc.meshes[h.geom].bsdf].type : 0u;
-        }
-        // sort by material: append q to the segment of its key (one atomic per key per warp)
-        uint32_t active = __ballot_sync(0xffffffffu, valid);
-        if (valid) {
-            uint32_t peers = __match_any_sync(active, key);
-            uint32_t leader = __ffs(peers) - 1u;
-            uint32_t rank = __popc(peers & ((1u << lane_id()) - 1u));
-            uint32_t slot = 0;
-            if (lane_id() == leader) slot = atomicAdd(&c->type_count[key], (uint32_t) __popc(peers));
-            slot = __shfl_sync(peers, slot, leader);
-            pool.sorted[(size_t) key * pool.capacity + slot + rank] = q;
-        }
+    __device__ __forceinline__ void load(uint32_t q, float4 &ro, float4 &rd) const {
+        const float4 *rp = reinterpret_cast<const float4 *>(rays + q);
+        ro = __ldcs(rp); rd = __ldcs(rp + 1);
     }
-    if (STATS) add_traversal_stats(&c->nodes_closest, &c->tris_closest, cn_total, ct_total);
+    __device__ __forceinline__ void commit(bool have, uint32_t q, const Traversal &s) {
+#if MSK_SORT_IN_COMMIT
+        const uint32_t done = __ballot_sync(0xffffffffu, have);
+#endif
+        if (!have) return;
+        const bool found = s.is_hit(); // hit <=> tfar != maxt, scene.cpp:234
+        pool.hit[q]      = make_float4(found ? s.hit.t : MSK_INF, s.hit.u, s.hit.v, __uint_as_float(s.hit.prim));
+        pool.hit_geom[q] = found ? s.hit.geom : 0xffffffffu;
+        if (STATS) { cn_total += s.cnt_nodes; ct_total += s.cnt_tris; }
+#if MSK_SORT_IN_COMMIT
+        const DScene &sc = *scp;
+        const uint32_t key = found ? 1u + (uint32_t) sc.bsdfs[sc.meshes[s.hit.geom].bsdf].type : 0u;
+        const uint32_t peers = __match_any_sync(done, key);
+        const uint32_t leader = __ffs(peers) - 1u;
+        const uint32_t rank = __popc(peers & ((1u << lane_id()) - 1u));
+        uint32_t slot = 0;
+        if (lane_id() == leader) slot = atomicAdd(&pool.ctrl->type_count[key], (uint32_t) __popc(peers));
+        slot = __shfl_sync(peers, slot, leader);
+        pool.sorted[(size_t) key * pool.capacity + slot + rank] = q;
+#endif
+    }
+};
+
+template <bool STATS>
+__global__ void __launch_bounds__(128, MSK_TRAV_MIN_BLOCKS) k_intersect(const __grid_constant__ DScene sc, Pool pool, int cur, int coherent) {
+    Ctrl *c = pool.ctrl;
+    IntersectIO<STATS> io{ pool, pool.rays[cur], &sc };
+    trace_queue<false, STATS>(sc.nodes, sc.tris, c->n_rays[cur], &c->cursor_isect, io, coherent != 0);
+    if (STATS) add_traversal_stats(&c->nodes_closest, &c->tris_closest, io.cn_total, io.ct_total);
 }
 
 // ---------------------------------------------------------------------------------------
 // One path vertex: path.cpp:33-123 re-ordered so that everything that follows the hit of the
 // ray spawned at the previous vertex (emitter MIS term :82-108, Russian roulette :116-122)
 // runs at the start of the next vertex, in the original order of random draws.
+// Material sort (north_star: "sorted by material to curb divergence"): a counting sort of the queue indices by
+// key (0 = miss, 1 + BSDF type).  Each block ranks a tile of kSortTile entries in shared memory and reserves
+// its share of every key's segment with ONE global atomic per key, so the pass costs a hit_geom read and an
+// index write per ray.  Besides making k_shade's warps uniform in material it groups the NEXT bounce's rays by
+// the surface they leave (measured: the static traversal of C2 is 1.3x slower on an unsorted queue).
+constexpr int kSortThreads = 256, kSortItems = 8, kSortTile = kSortThreads * kSortItems;
+__global__ void __launch_bounds__(kSortThreads) k_sort(const __grid_constant__ DScene sc, Pool pool, int cur) {
+    Ctrl *c = pool.ctrl;
+    const uint32_t total = c->n_rays[cur];
+    __shared__ uint32_t s_cnt[kNumKeys], s_base[kNumKeys];
+    const uint32_t ntiles = (total + kSortTile - 1) / kSortTile;
+    for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const uint32_t tbase = tile * kSortTile, tn = min((uint32_t) kSortTile, total - tbase);
+        if (threadIdx.x < kNumKeys) s_cnt[threadIdx.x] = 0;
+        __syncthreads();
+        uint32_t keyrank[kSortItems]; // key << 16 | rank within (tile, key)
+#pragma unroll
+        for (int i = 0; i < kSortItems; ++i) {
+            const uint32_t e = i * kSortThreads + threadIdx.x;
+            const bool in = e < tn;
+            uint32_t key = 0;
+            if (in) {
+                const uint32_t geom = __ldcs(pool.hit_geom + tbase + e);
+                if (geom != 0xffffffffu) key = 1u + (uint32_t) sc.bsdfs[sc.meshes[geom].bsdf].type;
+            }
+            const uint32_t active = __ballot_sync(0xffffffffu, in);
+            keyrank[i] = 0;
+            if (in) {
+                const uint32_t peers = __match_any_sync(active, key);
+                const uint32_t leader = __ffs(peers) - 1u;
+                uint32_t base = 0;
+                if (lane_id() == leader) base = atomicAdd(&s_cnt[key], (uint32_t) __popc(peers));
+                base = __shfl_sync(peers, base, leader);
+                keyrank[i] = (key << 16) | (base + __popc(peers & ((1u << lane_id()) - 1u)));
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x < kNumKeys) {
+            const uint32_t cnt = s_cnt[threadIdx.x];
+            s_base[threadIdx.x] = cnt ? atomicAdd(&c->type_count[threadIdx.x], cnt) : 0u;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < kSortItems; ++i) {
+            const uint32_t e = i * kSortThreads + threadIdx.x;
+            if (e < tn) {
+                const uint32_t key = keyrank[i] >> 16;
+                pool.sorted[(size_t) key * pool.capacity + s_base[key] + (keyrank[i] & 0xffffu)] = tbase + e;
+            }
+        }
+        __syncthreads();
+    }
+}
+
 __global__ void __launch_bounds__(128) k_shade(const __grid_constant__ DScene sc, Pool pool, BatchParams bp, int cur) {
     Ctrl *c = pool.ctrl;
     const int nxt = cur ^ 1;
@@ -314,32 +373,30 @@ __global__ void __launch_bounds__(128) k_shade(const __grid_constant__ DScene sc
 // NEE visibility (Scene::ray_test, scene.cpp:90-98,255-273) fused with the accumulation of
 // the NEE term (path.cpp:63-66).
 template <bool STATS>
-__global__ void __launch_bounds__(128) k_shadow(const __grid_constant__ DScene sc, Pool pool) {
-    Ctrl *c = pool.ctrl;
-    const uint32_t n = c->n_shadow;
+struct ShadowIO {
+    const Pool &pool;
     uint32_t cn_total = 0, ct_total = 0;
-    for (;;) {
-        uint32_t base = 0;
-        if (lane_id() == 0) base = atomicAdd(&c->cursor_shadow, 32u);
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (base >= n) break;
-        uint32_t q = base + lane_id();
-        if (q < n) {
-            const float4 *rp = reinterpret_cast<const float4 *>(pool.sh_ray + q);
-            float4 ro = __ldcs(rp), rd = __ldcs(rp + 1);
-            RayHit h;
-            uint32_t cn = 0, ct = 0;
-            bool occluded = traverse<true, STATS>(sc.nodes, sc.tris, ro.x, ro.y, ro.z, rd.x, rd.y, rd.z, ro.w, rd.w, h, &cn, &ct);
-            if (STATS) { cn_total += cn; ct_total += ct; }
-            if (occluded && h.t == rd.w) occluded = false; // scene.cpp:272
-            if (!occluded) {
-                uint32_t path = pool.sh_path[q];
-                float4 acc = pool.L[path];
-                pool.L[path] = acc + __ldcs(pool.sh_contrib + q);
-            }
+    __device__ __forceinline__ void load(uint32_t q, float4 &ro, float4 &rd) const {
+        const float4 *rp = reinterpret_cast<const float4 *>(pool.sh_ray + q);
+        ro = __ldcs(rp); rd = __ldcs(rp + 1);
+    }
+    __device__ __forceinline__ void commit(bool have, uint32_t q, const Traversal &s) {
+        if (!have) return;
+        if (STATS) { cn_total += s.cnt_nodes; ct_total += s.cnt_tris; }
+        if (!s.is_hit()) { // unoccluded (scene.cpp:272): one shadow ray per path and bounce, so no atomics
+            const uint32_t path = pool.sh_path[q];
+            const float4 acc = pool.L[path];
+            pool.L[path] = acc + __ldcs(pool.sh_contrib + q);
         }
     }
-    if (STATS) add_traversal_stats(&c->nodes_shadow, &c->tris_shadow, cn_total, ct_total);
+};
+
+template <bool STATS>
+__global__ void __launch_bounds__(128, MSK_TRAV_MIN_BLOCKS) k_shadow(const __grid_constant__ DScene sc, Pool pool, int coherent) {
+    Ctrl *c = pool.ctrl;
+    ShadowIO<STATS> io{ pool };
+    trace_queue<true, STATS>(sc.nodes, sc.tris, c->n_shadow, &c->cursor_shadow, io, coherent != 0);
+    if (STATS) add_traversal_stats(&c->nodes_shadow, &c->tris_shadow, io.cn_total, io.ct_total);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -405,51 +462,51 @@ __global__ void __launch_bounds__(kFilmTileX *kFilmTileY) k_film_gather(const __
 // ---------------------------------------------------------------------------------------
 // Stand-alone batch queries (msk_gpu_intersect / msk_gpu_occluded)
 template <bool STATS>
-__global__ void __launch_bounds__(128) k_query_closest(const __grid_constant__ DScene sc, const MskRay *__restrict__ rays,
+struct QueryClosestIO {
+    const MskRay *rays;
+    MskHit *hits;
+    uint32_t *nnodes, *ntris;
+    __device__ __forceinline__ void load(uint32_t q, float4 &ro, float4 &rd) const {
+        const float4 *rp = reinterpret_cast<const float4 *>(rays + q);
+        ro = __ldcs(rp); rd = __ldcs(rp + 1);
+    }
+    __device__ __forceinline__ void commit(bool have, uint32_t q, const Traversal &s) {
+        if (!have) return;
+        if (STATS) { nnodes[q] = s.cnt_nodes; ntris[q] = s.cnt_tris; }
+        else {
+            MskHit o;
+            const bool found = s.is_hit();
+            o.t = found ? s.hit.t : MSK_INF; o.u = found ? s.hit.u : 0.f; o.v = found ? s.hit.v : 0.f;
+            o.prim = found ? s.hit.prim : 0xffffffffu; o.geom = found ? s.hit.geom : 0xffffffffu;
+            hits[q] = o;
+        }
+    }
+};
+
+template <bool STATS>
+__global__ void __launch_bounds__(128, MSK_TRAV_MIN_BLOCKS) k_query_closest(const __grid_constant__ DScene sc, const MskRay *__restrict__ rays,
                                                        MskHit *__restrict__ hits, uint32_t n, uint32_t *cursor,
                                                        uint32_t *nnodes, uint32_t *ntris) {
-    for (;;) {
-        uint32_t base = 0;
-        if (lane_id() == 0) base = atomicAdd(cursor, 32u);
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (base >= n) break;
-        uint32_t q = base + lane_id();
-        if (q < n) {
-            const float4 *rp = reinterpret_cast<const float4 *>(rays + q);
-            float4 ro = __ldcs(rp), rd = __ldcs(rp + 1);
-            RayHit h;
-            h.t = MSK_INF; h.u = 0.f; h.v = 0.f; h.prim = 0xffffffffu; h.geom = 0xffffffffu;
-            uint32_t cn = 0, ct = 0;
-            bool found = traverse<false, STATS>(sc.nodes, sc.tris, ro.x, ro.y, ro.z, rd.x, rd.y, rd.z, ro.w, rd.w, h, &cn, &ct);
-            if (found && h.t == rd.w) found = false;
-            if (STATS) { nnodes[q] = cn; ntris[q] = ct; }
-            else {
-                MskHit o;
-                o.t = found ? h.t : MSK_INF; o.u = found ? h.u : 0.f; o.v = found ? h.v : 0.f;
-                o.prim = found ? h.prim : 0xffffffffu; o.geom = found ? h.geom : 0xffffffffu;
-                hits[q] = o;
-            }
-        }
-    }
+    QueryClosestIO<STATS> io{ rays, hits, nnodes, ntris };
+    trace_queue<false, STATS>(sc.nodes, sc.tris, n, cursor, io, false);
 }
 
-__global__ void __launch_bounds__(128) k_query_any(const __grid_constant__ DScene sc, const MskRay *__restrict__ rays,
-                                                   uint8_t *__restrict__ occ, uint32_t n, uint32_t *cursor) {
-    for (;;) {
-        uint32_t base = 0;
-        if (lane_id() == 0) base = atomicAdd(cursor, 32u);
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (base >= n) break;
-        uint32_t q = base + lane_id();
-        if (q < n) {
-            const float4 *rp = reinterpret_cast<const float4 *>(rays + q);
-            float4 ro = __ldcs(rp), rd = __ldcs(rp + 1);
-            RayHit h;
-            bool found = traverse<true, false>(sc.nodes, sc.tris, ro.x, ro.y, ro.z, rd.x, rd.y, rd.z, ro.w, rd.w, h);
-            if (found && h.t == rd.w) found = false;
-            occ[q] = found ? 1 : 0;
-        }
+struct QueryAnyIO {
+    const MskRay *rays;
+    uint8_t *occ;
+    __device__ __forceinline__ void load(uint32_t q, float4 &ro, float4 &rd) const {
+        const float4 *rp = reinterpret_cast<const float4 *>(rays + q);
+        ro = __ldcs(rp); rd = __ldcs(rp + 1);
     }
+    __device__ __forceinline__ void commit(bool have, uint32_t q, const Traversal &s) {
+        if (have) occ[q] = s.is_hit() ? 1 : 0;
+    }
+};
+
+__global__ void __launch_bounds__(128, MSK_TRAV_MIN_BLOCKS) k_query_any(const __grid_constant__ DScene sc, const MskRay *__restrict__ rays,
+                                                   uint8_t *__restrict__ occ, uint32_t n, uint32_t *cursor) {
+    QueryAnyIO io{ rays, occ };
+    trace_queue<true, false>(sc.nodes, sc.tris, n, cursor, io, false);
 }
 
 template <typename T> cudaError_t dalloc(T **p, size_t n) { return cudaMalloc((void **) p, std::max<size_t>(n, 1) * sizeof(T)); }
@@ -465,7 +522,7 @@ struct Renderer::Impl {
     cudaEvent_t ev[8]{};
     std::vector<cudaEvent_t> timer_events; // MSK_RENDER_STAGE_TIMERS
     std::vector<int> timer_stage;
-    int persistent_blocks = 0;
+    int persistent_blocks = 0, sm_count = 0;
 };
 
 Renderer::Renderer() : impl_(new Impl) {}
@@ -486,6 +543,7 @@ void Renderer::release() {
 }
 
 int Renderer::init(int sm_count) {
+    impl_->sm_count = sm_count;
     impl_->persistent_blocks = sm_count * 8; // 128-thread CTAs, 8 resident per SM
     MSK_CUDA_CHECK(dalloc(&impl_->query_cursor, 1));
     MSK_CUDA_CHECK(cudaMallocHost((void **) &impl_->h_ctrl, sizeof(Ctrl)));
@@ -543,7 +601,7 @@ int Renderer::render(cudaStream_t stream, const DScene &sc, const MskRenderDesc 
     // MSK_RENDER_STAGE_TIMERS: bracket every launch with a pair of events (a profiling aid used by bench.py
     // for the per-kernel roofline; the extra event records perturb ms_render slightly, so it is off by default)
     const bool timers = (rd.flags & MSK_RENDER_STAGE_TIMERS) != 0;
-    enum { ST_RAYGEN, ST_INTERSECT, ST_SHADE, ST_SHADOW, ST_FILM, ST_COUNT };
+    enum { ST_RAYGEN, ST_INTERSECT, ST_SORT, ST_SHADE, ST_SHADOW, ST_FILM, ST_COUNT };
     std::vector<int> &tstage = im.timer_stage;
     tstage.clear();
     size_t tev = 0;
@@ -578,11 +636,12 @@ int Renderer::render(cudaStream_t stream, const DScene &sc, const MskRenderDesc 
         // needs its shade pass (emission), so a bounded job runs exactly max_depth iterations
         const uint32_t bound = rd.max_depth > 0 ? (uint32_t) rd.max_depth : (rd.max_depth == 0 ? 0u : 0xffffffffu);
         while (bounce < bound) {
-            if (tstats) MSK_STAGE(ST_INTERSECT, (k_intersect<true><<<pb, 128, 0, stream>>>(sc, pool, cur)));
-            else MSK_STAGE(ST_INTERSECT, (k_intersect<false><<<pb, 128, 0, stream>>>(sc, pool, cur)));
+            if (tstats) MSK_STAGE(ST_INTERSECT, (k_intersect<true><<<pb, 128, 0, stream>>>(sc, pool, cur, bounce == 0)));
+            else MSK_STAGE(ST_INTERSECT, (k_intersect<false><<<pb, 128, 0, stream>>>(sc, pool, cur, bounce == 0)));
+            if (!MSK_SORT_IN_COMMIT) MSK_STAGE(ST_SORT, (k_sort<<<im.sm_count * 4, kSortThreads, 0, stream>>>(sc, pool, cur)));
             MSK_STAGE(ST_SHADE, (k_shade<<<pb, 128, 0, stream>>>(sc, pool, bp, cur)));
-            if (tstats) MSK_STAGE(ST_SHADOW, (k_shadow<true><<<pb, 128, 0, stream>>>(sc, pool)));
-            else MSK_STAGE(ST_SHADOW, (k_shadow<false><<<pb, 128, 0, stream>>>(sc, pool)));
+            if (tstats) MSK_STAGE(ST_SHADOW, (k_shadow<true><<<pb, 128, 0, stream>>>(sc, pool, 0)));
+            else MSK_STAGE(ST_SHADOW, (k_shadow<false><<<pb, 128, 0, stream>>>(sc, pool, 0)));
             k_end_bounce<<<1, 1, 0, stream>>>(pool.ctrl, cur);
             launches++;
             cur ^= 1;
@@ -626,7 +685,7 @@ int Renderer::render(cudaStream_t stream, const DScene &sc, const MskRenderDesc 
                 acc[tstage[k]] += ms; cnt[tstage[k]]++;
             }
             stats->ms_raygen = acc[ST_RAYGEN]; stats->ms_intersect = acc[ST_INTERSECT]; stats->ms_shade = acc[ST_SHADE];
-            stats->ms_shadow = acc[ST_SHADOW]; stats->ms_film = acc[ST_FILM];
+            stats->ms_shadow = acc[ST_SHADOW]; stats->ms_film = acc[ST_FILM]; stats->ms_sort = acc[ST_SORT];
             stats->n_intersect_launches = cnt[ST_INTERSECT]; stats->n_shade_launches = cnt[ST_SHADE];
             stats->n_shadow_launches = cnt[ST_SHADOW];
         }

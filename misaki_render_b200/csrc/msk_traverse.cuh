@@ -13,7 +13,14 @@
 
 namespace msk {
 
-constexpr int kStackSize = 48;
+constexpr int kStackSize = 64; // node groups + postponed triangle groups: at most 2 per level of the wide tree
+
+#ifndef MSK_FETCH_THRESHOLD
+#define MSK_FETCH_THRESHOLD 20
+#endif
+#ifndef MSK_TRI_THRESHOLD
+#define MSK_TRI_THRESHOLD 12
+#endif
 
 struct RayHit {
     float t, u, v;
@@ -87,95 +94,311 @@ __device__ __forceinline__ float nz(float d) { // keep reciprocal directions fin
 
 __device__ __forceinline__ uint32_t extract_byte(uint32_t x, int i) { return (x >> (8 * i)) & 0xffu; }
 
-// ANY: stop at the first accepted hit.  STATS: count visited nodes / tested triangles.
+// Byte j of q as the float 32768 + b, built with ONE byte-permute on the ALU pipe: the byte lands in bits
+// 8..15 of 0x47000000 (= 2^15, whose ulp is 2^-8... i.e. mantissa bit 8 has weight 1).  An int->float
+// convert (I2F) would go through the quarter-rate XU pipe, which ncu showed 87 % busy in the first version of
+// this kernel (profiles/r01a_ncu_k_intersect.txt); 48 of them per node visit made XU the bound.
+template <int J> __device__ __forceinline__ float qfloat(uint32_t q) {
+    return __uint_as_float(__byte_perm(q, 0x47000000u, 0x7504u | (J << 4)));
+}
+
+// Per-lane traversal state.  A lane owns one ray at a time; the warp refills idle lanes from the queue
+// (dynamic fetch, Aila & Laine 2009) instead of waiting for its slowest ray.
+struct Traversal {
+    float ox, oy, oz, dx, dy, dz, tmin, tmax;
+    float tfar0;   // the ray's own maxt
+    float idx, idy, idz;
+    uint32_t octinv;
+    WoopRay wr;
+    uint2 ngroup, tgroup;
+    int sp;
+    RayHit hit;
+    bool found;
+    uint32_t cnt_nodes, cnt_tris;
+
+    __device__ __forceinline__ void begin(float4 ro, float4 rd) {
+        ox = ro.x; oy = ro.y; oz = ro.z; tmin = ro.w;
+        dx = rd.x; dy = rd.y; dz = rd.z; tmax = rd.w; tfar0 = rd.w;
+        idx = 1.f / nz(dx); idy = 1.f / nz(dy); idz = 1.f / nz(dz);
+        // signs of the clamped direction (-0 counts as negative)
+        const uint32_t oct = (idx < 0.f ? 4u : 0u) | (idy < 0.f ? 2u : 0u) | (idz < 0.f ? 1u : 0u);
+        octinv = 7u - oct;
+        wr = woop_setup(dx, dy, dz);
+        ngroup = make_uint2(0u, 0x80000000u); // root: "child slot 7 of a virtual parent at base 0"
+        tgroup = make_uint2(0u, 0u);
+        sp = 0;
+        found = false;
+        hit.t = __int_as_float(0x7f800000); hit.u = 0.f; hit.v = 0.f; hit.prim = 0xffffffffu; hit.geom = 0xffffffffu;
+        cnt_nodes = 0; cnt_tris = 0;
+    }
+    // Scene::ray_intersect / ray_test report a hit iff Embree moved tfar (scene.cpp:234,272): a hit at
+    // exactly t == maxt reads as a miss
+    __device__ __forceinline__ bool is_hit() const { return found && hit.t != tfar0; }
+};
+
+constexpr int kFetchThreshold = MSK_FETCH_THRESHOLD; // while-while mode: leave the loop to refill when fewer lanes are busy
+constexpr int kTriThreshold   = MSK_TRI_THRESHOLD;   // run a triangle phase once this many lanes have triangles pending
+
+// Visit the next pending inner node of s.ngroup: pushes what remains of the group, tests the node's 8
+// quantised child boxes, leaves the children hit in s.ngroup and the triangles hit in s.tgroup.
+template <bool STATS>
+__device__ __forceinline__ void node_step(const float4 *__restrict__ nodes, Traversal &s, uint2 *stack) {
+    const bool negx = s.idx < 0.f, negy = s.idy < 0.f, negz = s.idz < 0.f;
+    const uint32_t octinv4 = s.octinv * 0x01010101u;
+    const uint32_t hits  = s.ngroup.y;
+    const uint32_t imask = s.ngroup.y & 0xffu;
+    const uint32_t bit   = 31u - __clz(hits);
+    s.ngroup.y &= ~(1u << bit);
+    if (s.ngroup.y > 0x00ffffffu) stack[s.sp++] = s.ngroup;
+    const uint32_t slot = (bit - 24u) ^ s.octinv;
+    const uint32_t rel  = __popc(imask & ~(0xffffffffu << slot));
+    const uint32_t node = s.ngroup.x + rel;
+    const float4 *np = nodes + (size_t) node * kNodeFloat4s;
+    const float4 n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3), n4 = __ldg(np + 4);
+    if (STATS) s.cnt_nodes++;
+    const uint32_t e = __float_as_uint(n0.w);
+    const float adx = __uint_as_float((e & 0xffu) << 23) * s.idx, ady = __uint_as_float(((e >> 8) & 0xffu) << 23) * s.idy,
+                adz = __uint_as_float(((e >> 16) & 0xffu) << 23) * s.idz;
+    // plane j at parameter t = (32768 + q_j) * ad + (ao - 32768 * ad).  The product carries a rounding
+    // error of up to 2^-9 cell, so the near planes move 2^-8 cell towards the ray origin and the far
+    // planes 2^-8 cell away from it: the decoded boxes are supersets of the stored ones.
+    const float aox = fmaf(-32768.f, adx, (n0.x - s.ox) * s.idx), aoy = fmaf(-32768.f, ady, (n0.y - s.oy) * s.idy),
+                aoz = fmaf(-32768.f, adz, (n0.z - s.oz) * s.idz);
+    const float ex = fabsf(adx) * 0.00390625f, ey = fabsf(ady) * 0.00390625f, ez = fabsf(adz) * 0.00390625f;
+    const float nox = aox - ex, fox = aox + ex, noy = aoy - ey, foy = aoy + ey, noz = aoz - ez, foz = aoz + ez;
+    s.ngroup.x = __float_as_uint(n1.x);
+    s.tgroup.x = __float_as_uint(n1.y);
+    uint32_t hitmask = 0;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const uint32_t meta4 = __float_as_uint(h ? n1.w : n1.z);
+        const uint32_t is_inner4   = (meta4 & (meta4 << 1)) & 0x10101010u;
+        const uint32_t inner_mask4 = (is_inner4 >> 4) * 0xffu;
+        const uint32_t bit_index4  = (meta4 ^ (octinv4 & inner_mask4)) & 0x1f1f1f1fu;
+        const uint32_t child_bits4 = (meta4 >> 5) & 0x07070707u;
+        const uint32_t qlox = __float_as_uint(h ? n2.y : n2.x), qloy = __float_as_uint(h ? n2.w : n2.z),
+                       qloz = __float_as_uint(h ? n3.y : n3.x), qhix = __float_as_uint(h ? n3.w : n3.z),
+                       qhiy = __float_as_uint(h ? n4.y : n4.x), qhiz = __float_as_uint(h ? n4.w : n4.z);
+        // near / far planes by ray direction sign
+        const uint32_t nx = negx ? qhix : qlox, fx = negx ? qlox : qhix;
+        const uint32_t ny = negy ? qhiy : qloy, fy = negy ? qloy : qhiy;
+        const uint32_t nzq = negz ? qhiz : qloz, fz = negz ? qloz : qhiz;
+#define MSK_CHILD(J)                                                                                              \
+    {                                                                                                             \
+        const float t0x = fmaf(qfloat<J>(nx), adx, nox), t1x = fmaf(qfloat<J>(fx), adx, fox);                     \
+        const float t0y = fmaf(qfloat<J>(ny), ady, noy), t1y = fmaf(qfloat<J>(fy), ady, foy);                     \
+        const float t0z = fmaf(qfloat<J>(nzq), adz, noz), t1z = fmaf(qfloat<J>(fz), adz, foz);                    \
+        const float tn = fmaxf(fmaxf(t0x, t0y), fmaxf(t0z, s.tmin));                                              \
+        const float tf = fminf(fminf(t1x, t1y), fminf(t1z, s.tmax));                                              \
+        if (tn <= tf) hitmask |= extract_byte(child_bits4, J) << extract_byte(bit_index4, J);                     \
+    }
+        MSK_CHILD(0) MSK_CHILD(1) MSK_CHILD(2) MSK_CHILD(3)
+#undef MSK_CHILD
+    }
+    s.ngroup.y = (hitmask & 0xff000000u) | (e >> 24);
+    s.tgroup.y = hitmask & 0x00ffffffu;
+}
+
+// Test the highest pending triangle of s.tgroup.  Returns true when it is hit (tmax shrinks).
+template <bool STATS>
+__device__ __forceinline__ bool tri_step(const float4 *__restrict__ tris, Traversal &s) {
+    const uint32_t k = 31u - __clz(s.tgroup.y);
+    s.tgroup.y &= ~(1u << k);
+    const float4 *tp = tris + (size_t) (s.tgroup.x + k) * kTriFloat4s;
+    const float4 v0 = __ldg(tp), v1 = __ldg(tp + 1), v2 = __ldg(tp + 2);
+    if (STATS) s.cnt_tris++;
+    float t, u, v;
+    if (woop_intersect(s.wr, s.ox, s.oy, s.oz, v0, v1, v2, s.tmin, s.tmax, t, u, v)) {
+        s.tmax = t;
+        s.hit.t = t; s.hit.u = u; s.hit.v = v;
+        s.hit.prim = __float_as_uint(v0.w); s.hit.geom = __float_as_uint(v1.w);
+        s.found = true;
+        return true;
+    }
+    return false;
+}
+
+// One ray to completion, classic while-while order (used where rays are not queued).
 template <bool ANY, bool STATS>
 __device__ __forceinline__ bool traverse(const float4 *__restrict__ nodes, const float4 *__restrict__ tris, float ox, float oy,
                                          float oz, float dx, float dy, float dz, float tmin, float tmax, RayHit &hit,
                                          uint32_t *nnodes = nullptr, uint32_t *ntris = nullptr) {
     uint2 stack[kStackSize];
-    int sp = 0;
-    const float idx = 1.f / nz(dx), idy = 1.f / nz(dy), idz = 1.f / nz(dz);
-    const bool negx = idx < 0.f, negy = idy < 0.f, negz = idz < 0.f; // signs of the clamped direction (-0 counts as negative)
-    const uint32_t oct    = (negx ? 4u : 0u) | (negy ? 2u : 0u) | (negz ? 1u : 0u);
-    const uint32_t octinv = 7u - oct;
-    const uint32_t octinv4 = octinv * 0x01010101u;
-    const WoopRay wr = woop_setup(dx, dy, dz);
-    bool found = false;
-    uint32_t cnt_nodes = 0, cnt_tris = 0;
-
-    uint2 ngroup = make_uint2(0u, 0x80000000u); // root: "child slot 7 of a virtual parent at base 0"
-    uint2 tgroup = make_uint2(0u, 0u);
+    Traversal s;
+    s.begin(make_float4(ox, oy, oz, tmin), make_float4(dx, dy, dz, tmax));
     for (;;) {
-        // invariant: ngroup.y > 0x00ffffff here (only such groups are pushed, and the loop
-        // pops or exits as soon as the current group has no pending internal hits)
-        {
-            const uint32_t hits  = ngroup.y;
-            const uint32_t imask = ngroup.y & 0xffu;
-            const uint32_t bit   = 31u - __clz(hits);
-            ngroup.y &= ~(1u << bit);
-            if (ngroup.y > 0x00ffffffu) stack[sp++] = ngroup;
-            const uint32_t slot = (bit - 24u) ^ octinv;
-            const uint32_t rel  = __popc(imask & ~(0xffffffffu << slot));
-            const uint32_t node = ngroup.x + rel;
-            const float4 *np = nodes + (size_t) node * kNodeFloat4s;
-            const float4 n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3), n4 = __ldg(np + 4);
-            if (STATS) cnt_nodes++;
-            const uint32_t e = __float_as_uint(n0.w);
-            const float adx = __uint_as_float((e & 0xffu) << 23) * idx, ady = __uint_as_float(((e >> 8) & 0xffu) << 23) * idy,
-                        adz = __uint_as_float(((e >> 16) & 0xffu) << 23) * idz;
-            const float aox = (n0.x - ox) * idx, aoy = (n0.y - oy) * idy, aoz = (n0.z - oz) * idz;
-            ngroup.x = __float_as_uint(n1.x);
-            tgroup.x = __float_as_uint(n1.y);
-            uint32_t hitmask = 0;
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const uint32_t meta4 = __float_as_uint(h ? n1.w : n1.z);
-                const uint32_t is_inner4   = (meta4 & (meta4 << 1)) & 0x10101010u;
-                const uint32_t inner_mask4 = (is_inner4 >> 4) * 0xffu;
-                const uint32_t bit_index4  = (meta4 ^ (octinv4 & inner_mask4)) & 0x1f1f1f1fu;
-                const uint32_t child_bits4 = (meta4 >> 5) & 0x07070707u;
-                const uint32_t qlox = __float_as_uint(h ? n2.y : n2.x), qloy = __float_as_uint(h ? n2.w : n2.z),
-                               qloz = __float_as_uint(h ? n3.y : n3.x), qhix = __float_as_uint(h ? n3.w : n3.z),
-                               qhiy = __float_as_uint(h ? n4.y : n4.x), qhiz = __float_as_uint(h ? n4.w : n4.z);
-                // near / far planes by ray direction sign
-                const uint32_t nx = negx ? qhix : qlox, fx = negx ? qlox : qhix;
-                const uint32_t ny = negy ? qhiy : qloy, fy = negy ? qloy : qhiy;
-                const uint32_t nzq = negz ? qhiz : qloz, fz = negz ? qloz : qhiz;
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const float t0x = fmaf((float) extract_byte(nx, j), adx, aox), t1x = fmaf((float) extract_byte(fx, j), adx, aox);
-                    const float t0y = fmaf((float) extract_byte(ny, j), ady, aoy), t1y = fmaf((float) extract_byte(fy, j), ady, aoy);
-                    const float t0z = fmaf((float) extract_byte(nzq, j), adz, aoz), t1z = fmaf((float) extract_byte(fz, j), adz, aoz);
-                    const float tn = fmaxf(fmaxf(t0x, t0y), fmaxf(t0z, tmin));
-                    const float tf = fminf(fminf(t1x, t1y), fminf(t1z, tmax));
-                    if (tn <= tf) hitmask |= extract_byte(child_bits4, j) << extract_byte(bit_index4, j);
-                }
-            }
-            ngroup.y = (hitmask & 0xff000000u) | (e >> 24);
-            tgroup.y = hitmask & 0x00ffffffu;
+        if (s.ngroup.y > 0x00ffffffu) node_step<STATS>(nodes, s, stack);
+        else { s.tgroup = s.ngroup; s.ngroup = make_uint2(0u, 0u); }
+        bool stop = false;
+        while (s.tgroup.y) {
+            if (tri_step<STATS>(tris, s) && ANY) { stop = true; break; }
         }
-        while (tgroup.y) {
-            const uint32_t k = 31u - __clz(tgroup.y);
-            tgroup.y &= ~(1u << k);
-            const float4 *tp = tris + (size_t) (tgroup.x + k) * kTriFloat4s;
-            const float4 v0 = __ldg(tp), v1 = __ldg(tp + 1), v2 = __ldg(tp + 2);
-            if (STATS) cnt_tris++;
-            float t, u, v;
-            if (woop_intersect(wr, ox, oy, oz, v0, v1, v2, tmin, tmax, t, u, v)) {
-                tmax = t;
-                hit.t = t; hit.u = u; hit.v = v;
-                hit.prim = __float_as_uint(v0.w); hit.geom = __float_as_uint(v1.w);
-                found = true;
-                if (ANY) { tgroup.y = 0; ngroup.y = 0; sp = 0; break; }
-            }
-        }
-        if (ngroup.y <= 0x00ffffffu) {
-            if (sp == 0) break;
-            ngroup = stack[--sp];
+        if (stop) break;
+        if (s.ngroup.y <= 0x00ffffffu) {
+            if (s.sp == 0) break;
+            s.ngroup = stack[--s.sp];
         }
     }
-    if (STATS) { *nnodes = cnt_nodes; *ntris = cnt_tris; }
-    return found;
+    if (s.is_hit()) hit = s.hit;
+    if (STATS) { *nnodes = s.cnt_nodes; *ntris = s.cnt_tris; }
+    return s.is_hit();
+}
+
+// Persistent-warp driver: every lane pulls rays from the queue [0, n) until it is empty.
+//   io.load(q, ro, rd)                 fetch ray q
+//   io.commit(have, q, s)              called by ALL 32 lanes converged; lanes with `have` deliver the result
+//                                      of their finished ray q (s.is_hit(), s.hit, s.cnt_*)
+//
+// The warp advances in LOCKSTEP phases, each entered by a vote, so that the two expensive code blocks run
+// with as many lanes as possible (ncu on the first while-while version: 8 of 32 lanes active in the node
+// test, 3 of 32 in the triangle test -- profiles/r01a_ncu_k_intersect.txt):
+//   refill    idle lanes take the next ray (indices come from a per-warp chunk reserved with one atomic; the
+//             ray itself was prefetched into registers while the previous ray was in flight)
+//   node      every lane with a pending inner node visits one (8 child boxes)
+//   triangle  runs only when >= kTriThreshold lanes hold pending triangles or a lane has nothing else to do;
+//             every lane with pending triangles tests one.  Triangles found meanwhile wait on the stack.
+//   pop       lanes out of work pop the stack or finish
+constexpr uint32_t kChunk = 128; // ray indices reserved per atomic
+
+#ifndef MSK_TRAVERSAL_MODE
+#define MSK_TRAVERSAL_MODE 2 /* 0 static, 1 lockstep, 2 hybrid */
+#endif
+
+// Static assignment: the warp takes 32 consecutive rays and every lane runs its ray to completion.
+template <bool ANY, bool STATS, typename IO>
+__device__ __forceinline__ void trace_queue_static(const float4 *__restrict__ nodes, const float4 *__restrict__ tris, uint32_t n,
+                                                   uint32_t *cursor, IO &io, uint2 *stack) {
+    Traversal s;
+    const uint32_t lane = threadIdx.x & 31u;
+    for (;;) {
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(cursor, 32u);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (base >= n) break;
+        const uint32_t q = base + lane;
+        const bool valid = q < n;
+        if (valid) {
+            float4 ro, rd;
+            io.load(q, ro, rd);
+            s.begin(ro, rd);
+            for (;;) {
+                if (s.ngroup.y > 0x00ffffffu) node_step<STATS>(nodes, s, stack);
+                else { s.tgroup = s.ngroup; s.ngroup = make_uint2(0u, 0u); }
+                bool stop = false;
+                while (s.tgroup.y) {
+                    if (tri_step<STATS>(tris, s) && ANY) { stop = true; break; }
+                }
+                if (stop) break;
+                if (s.ngroup.y <= 0x00ffffffu) {
+                    if (s.sp == 0) break;
+                    s.ngroup = stack[--s.sp];
+                }
+            }
+        }
+        __syncwarp();
+        io.commit(valid, q, s);
+    }
+}
+
+template <bool ANY, bool STATS, typename IO>
+__device__ __forceinline__ void trace_queue(const float4 *__restrict__ nodes, const float4 *__restrict__ tris, uint32_t n,
+                                            uint32_t *cursor, IO &io, bool coherent) {
+    // Coherent queues (camera rays: neighbouring lanes follow the same nodes, so a static warp of 32 runs
+    // converged and its node fetches coalesce) and queues too small to fill the machine (latency-bound: more,
+    // shorter warps win) use the static assignment; incoherent bulk queues use the lockstep phases.
+#if MSK_TRAVERSAL_MODE == 0
+    const bool use_static = true;
+#elif MSK_TRAVERSAL_MODE == 1
+    const bool use_static = false;
+#else
+    const bool use_static = coherent || n < gridDim.x * (blockDim.x / 32u) * 64u;
+#endif
+    uint2 stack[kStackSize];
+    if (use_static) {
+        trace_queue_static<ANY, STATS>(nodes, tris, n, cursor, io, stack);
+        return;
+    }
+    Traversal s;
+    s.ngroup = make_uint2(0u, 0u); s.tgroup = make_uint2(0u, 0u); s.sp = 0;
+    const uint32_t lane = threadIdx.x & 31u, below = (1u << lane) - 1u;
+    bool busy = false, have = false;
+    uint32_t q = 0;
+    // prefetched next ray of this lane
+    float4 nro = make_float4(0, 0, 0, 0), nrd = make_float4(0, 0, 0, 0);
+    uint32_t nq = 0xffffffffu;             // 0xffffffff: none
+    uint32_t chunk_next = 0, chunk_end = 0; // warp-uniform
+    bool more = true;                       // warp-uniform: the global queue may still hold rays
+
+    // take indices for the lanes in `want` (warp-uniform mask) from the warp's chunk; returns this lane's index
+    auto take = [&](uint32_t want) -> uint32_t {
+        uint32_t need = (uint32_t) __popc(want);
+        if (chunk_end - chunk_next < need && more) { // reserve a new chunk (the rest of the old one is handed out first)
+            // simplification: hand out what is left, then continue from the new chunk
+            uint32_t base = 0;
+            if (lane == 0) base = atomicAdd(cursor, kChunk);
+            base = __shfl_sync(0xffffffffu, base, 0);
+            const uint32_t left = chunk_end - chunk_next;
+            const uint32_t rank = (uint32_t) __popc(want & below);
+            uint32_t idx;
+            if (rank < left) idx = chunk_next + rank;
+            else idx = base + (rank - left);
+            if (base >= n) more = false;
+            chunk_next = base + (need - min(need, left));
+            chunk_end  = min(base + kChunk, n);
+            if (chunk_next > chunk_end) chunk_next = chunk_end;
+            if (!(want & (1u << lane))) return 0xffffffffu;
+            return idx < n ? idx : 0xffffffffu;
+        }
+        const uint32_t rank = (uint32_t) __popc(want & below);
+        const uint32_t idx = chunk_next + rank;
+        const uint32_t avail = chunk_end - chunk_next;
+        chunk_next += min(need, avail);
+        if (!(want & (1u << lane))) return 0xffffffffu;
+        return rank < avail ? idx : 0xffffffffu;
+    };
+
+    { // prime: every lane prefetches its first ray
+        nq = take(0xffffffffu);
+        if (nq != 0xffffffffu) io.load(nq, nro, nrd);
+    }
+    for (;;) {
+        // ---- refill
+        const uint32_t idle = __ballot_sync(0xffffffffu, !busy);
+        if (idle) {
+            io.commit(have, q, s);
+            have = false;
+            const bool start = !busy && nq != 0xffffffffu;
+            if (start) { q = nq; s.begin(nro, nrd); busy = true; nq = 0xffffffffu; }
+            const uint32_t want = __ballot_sync(0xffffffffu, start);
+            if (want && (more || chunk_next < chunk_end)) {
+                const uint32_t idx = take(want);
+                if (idx != 0xffffffffu) { nq = idx; io.load(nq, nro, nrd); }
+            }
+            if (__ballot_sync(0xffffffffu, busy) == 0u) break;
+        }
+        // ---- node phase
+        if (busy && s.ngroup.y > 0x00ffffffu) {
+            if (s.tgroup.y) stack[s.sp++] = s.tgroup; // postponed triangles wait on the stack
+            node_step<STATS>(nodes, s, stack);
+        }
+        // ---- triangle phase
+        const bool has_t = busy && s.tgroup.y != 0u;
+        const uint32_t mt = __ballot_sync(0xffffffffu, has_t);
+        if (mt) {
+            const bool starved = has_t && s.ngroup.y <= 0x00ffffffu;
+            if (__popc(mt) >= kTriThreshold || __any_sync(0xffffffffu, starved)) {
+                if (has_t && tri_step<STATS>(tris, s) && ANY) { busy = false; have = true; }
+            }
+        }
+        // ---- pop
+        if (busy && s.ngroup.y <= 0x00ffffffu) {
+            if (s.sp > 0) {
+                const uint2 g = stack[s.sp - 1];
+                if (g.y > 0x00ffffffu) { s.ngroup = g; --s.sp; }
+                else if (s.tgroup.y == 0u) { s.tgroup = g; --s.sp; }
+            } else if (s.tgroup.y == 0u) { busy = false; have = true; }
+        }
+    }
 }
 
 } // namespace msk
