@@ -16,7 +16,8 @@ def _built():
     """Make sure the in-tree native pieces exist (a fresh checkout has none of the git-ignored .so files)."""
     from misaki_render_b200 import capi
     from oracle import pyoracle
-    need = [capi.LIB_PATH, pyoracle.LIB, ROOT / "misaki_render_b200" / "data" / "srgb.coeff"]
+    from misaki_render_b200 import host_api
+    need = [capi.LIB_PATH, host_api.LIB_PATH, pyoracle.LIB, ROOT / "misaki_render_b200" / "data" / "srgb.coeff"]
     if not all(p.exists() for p in need):
         import __graft_entry__
         __graft_entry__.build()

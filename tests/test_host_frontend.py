@@ -1,0 +1,268 @@
+"""The C++ host front-end (misaki_render_b200/host): misaki's XML scene format, plugin registry, OBJ loader,
+spectra and the flattening into the C ABI's MskSceneDesc -- everything before the first CUDA call, so it runs
+on CPU.  The reference has no tests of its own; the expectations below are the behaviours
+of reference src/librender/xml.cpp, properties.cpp and the plugin constructors cited in host/*.cpp."""
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from misaki_render_b200 import capi, host_api
+from misaki_render_b200.rgb2spec import model as rgb2spec_model
+from workloads import scenes
+
+ROOT = Path(__file__).resolve().parent.parent
+CBOX = ROOT / "assets" / "scenes" / "cbox.xml"
+CBOX_PARAMS = dict(w=256, h=256, spp=16, depth=5)
+REFERENCE_CBOX = Path("/root/reference/assets/cbox/scene.xml")
+
+
+def _spectra(d):
+    out = []
+    tables = np.ctypeslib.as_array(d.spectrum_tables, shape=(d.ntable_floats,)) if d.ntable_floats else np.zeros(0, np.float32)
+    for i in range(d.nspectra):
+        s = d.spectra[i]
+        t = tuple(tables[s.table_offset:s.table_offset + s.table_size]) if s.table_size else ()
+        out.append((s.kind, tuple(s.c), s.value, s.lambda_min, s.lambda_max, t))
+    return out
+
+
+def _scene(xml_body, **kw):
+    return host_api.HostScene(xml=xml_body, base_dir=str(ROOT / "assets" / "scenes"), **kw)
+
+
+MINIMAL = """<scene>
+  <sensor type="perspective"><film type="hdrfilm"><integer name="width" value="8"/><integer name="height" value="4"/></film></sensor>
+  {body}
+</scene>"""
+QUAD = '<shape type="obj"><string name="filename" value="../cbox/meshes/cbox_floor.obj"/>{inner}</shape>'
+
+
+def test_registered_plugins_cover_the_reference_list():
+    names = set(host_api.registered_plugins())
+    # the MSK_REGISTER_INSTANCE list of the reference build + conductor/dielectric/twosided
+    for n in ["obj", "d65", "regular", "srgb", "srgb_d65", "uniform", "constant", "area", "hdrfilm", "perspective", "gaussian",
+              "independent", "path", "diffuse", "roughconductor", "roughdielectric", "conductor", "dielectric", "twosided"]:
+        assert n in names, n
+
+
+def test_cbox_scene_file_flattens_to_the_programmatic_description():
+    with host_api.HostScene(CBOX, params=CBOX_PARAMS) as hs:
+        d, meshes, rd = hs.desc(), hs.meshes(), hs.render_desc()
+        sd = scenes.cbox(256, 256)
+        pd = sd.c_desc()
+        assert (d.nmeshes, d.nemitters, d.environment) == (pd.nmeshes, pd.nemitters, -1)
+        for a, b in zip(meshes, sd.meshes):  # Scene::m_shapes order == file order for <= 10 children
+            np.testing.assert_array_equal(a["verts"], b["verts"])  # OBJ loader: bit-identical vertices
+            np.testing.assert_array_equal(a["tris"], b["tris"])
+            assert (a["emitter"], a["has_normals"], a["has_uvs"]) == (b["emitter"], b["has_normals"], b["has_uvs"])
+        hspec, pspec = _spectra(d), _spectra(pd)
+        for i, (a, b) in enumerate(zip(meshes, sd.meshes)):  # same reflectance spectrum behind every mesh's bsdf
+            assert hspec[d.bsdfs[a["bsdf"]].reflectance] == pspec[pd.bsdfs[b["bsdf"]].reflectance], i
+            assert d.bsdfs[a["bsdf"]].type == capi.BSDF_DIFFUSE
+        assert hspec[d.emitters[0].radiance] == pspec[pd.emitters[0].radiance]  # srgb_d65: coefficients + scaled D65 table
+        assert d.emitters[0].shape == 0 and d.emitters[0].type == capi.EMITTER_AREA
+        cam, pcam = d.camera, pd.camera
+        np.testing.assert_allclose(cam.sample_to_camera[:], pcam.sample_to_camera[:], rtol=0, atol=2e-7)
+        np.testing.assert_array_equal(cam.to_world[:], pcam.to_world[:])
+        np.testing.assert_array_equal(cam.filter_table[:], pcam.filter_table[:])  # gaussian.cpp + init_discretization
+        assert (cam.width, cam.height, cam.near_clip, cam.far_clip, cam.filter_radius) == (256, 256, 10.0, 2800.0, 2.0)
+        assert (rd.spp, rd.sample_begin, rd.sample_end, rd.max_depth, rd.rr_depth, rd.hide_emitters, rd.base_seed) == (16, 0, 16, 5, 5, 0, 0)
+
+
+@pytest.mark.skipif(not REFERENCE_CBOX.exists(), reason="the reference tree only exists in the build container")
+def test_the_references_own_scene_file_loads_unchanged():
+    host_api.load().mskh_add_search_path(str(ROOT / "assets" / "cbox").encode())  # where the authored meshes live
+    with host_api.HostScene(REFERENCE_CBOX) as hs:  # names rgbfilm (served by hdrfilm), 800x600, 16 spp
+        d, rd = hs.desc(), hs.render_desc()
+        assert (d.nmeshes, d.nemitters, d.camera.width, d.camera.height) == (8, 1, 800, 600)
+        assert (rd.spp, rd.max_depth, rd.rr_depth) == (16, -1, 5)
+        sd = scenes.cbox(800, 600)
+        for a, b in zip(hs.meshes(), sd.meshes):
+            np.testing.assert_array_equal(a["verts"], b["verts"])
+
+
+def test_children_are_ordered_like_std_map_keys():
+    """Unnamed children are _arg_0, _arg_1, ... and Properties::objects() walks a std::map, so the 11th and 12th
+    child come before the 3rd (properties.cpp:166-176): this is the geomID order Embree saw."""
+    files = ["floor", "ceiling", "back", "greenwall", "redwall", "smallbox", "largebox", "luminaire", "floor", "ceiling", "back"]
+    body = "".join(QUAD.format(inner="").replace("cbox_floor", f"cbox_{f}") for f in files)
+    with _scene(MINIMAL.format(body=body)) as hs:
+        counts = [m["verts"].shape[0] for m in hs.meshes()]
+    # children: sensor=_arg_0, shapes=_arg_1.._arg_11; map order: _arg_1, _arg_10, _arg_11, _arg_2, ...
+    order = sorted(range(1, 12), key=lambda i: f"_arg_{i}")
+    expect = [20 if files[i - 1] in ("smallbox", "largebox") else 4 for i in order]
+    assert counts == expect
+
+
+def test_named_reference_and_shared_plugin():
+    body = ('<bsdf type="diffuse" id="shared"><rgb name="reflectance" value="0.2, 0.4, 0.6"/></bsdf>'
+            + QUAD.format(inner='<ref id="shared"/>') + QUAD.format(inner='<ref id="shared"/>'))
+    with _scene(MINIMAL.format(body=body)) as hs:
+        d, m = hs.desc(), hs.meshes()
+        assert m[0]["bsdf"] == m[1]["bsdf"] and d.nbsdfs == 1  # one instance, described once
+        np.testing.assert_array_equal(np.array(d.spectra[d.bsdfs[0].reflectance].c[:], np.float32), rgb2spec_model().fetch((0.2, 0.4, 0.6)))
+    with pytest.raises(host_api.HostError, match="reference to unknown object"):
+        _scene(MINIMAL.format(body=QUAD.format(inner='<ref id="nope"/>')))
+
+
+def test_default_bsdf_and_defaulted_texture():
+    """A shape without <bsdf> gets "diffuse" (shape.cpp:45-47) whose defaulted reflectance is gray 0.5 -- the evident
+    intent of properties.cpp:226-233 (which throws in the reference because of a key mismatch)."""
+    with _scene(MINIMAL.format(body=QUAD.format(inner=""))) as hs:
+        d = hs.desc()
+        assert d.bsdfs[0].type == capi.BSDF_DIFFUSE
+        np.testing.assert_array_equal(np.array(d.spectra[d.bsdfs[0].reflectance].c[:], np.float32), rgb2spec_model().fetch((0.5, 0.5, 0.5)))
+
+
+def test_float_spectrum_and_rgb_properties_become_textures():
+    inner = '<bsdf type="diffuse"><float name="reflectance" value="0.25"/></bsdf>'
+    with _scene(MINIMAL.format(body=QUAD.format(inner=inner))) as hs:  # <float> -> "uniform" (properties.cpp:206-211)
+        s = hs.desc().spectra[hs.desc().bsdfs[0].reflectance]
+        assert (s.kind, s.value) == (capi.SPEC_UNIFORM, 0.25)
+    inner = '<bsdf type="diffuse"><spectrum name="reflectance" value="400:0.1, 500:0.2, 600:0.4, 700:0.8"/></bsdf>'
+    with _scene(MINIMAL.format(body=QUAD.format(inner=inner))) as hs:  # regular wavelength:value pairs -> "regular"
+        sp = _spectra(hs.desc())[hs.desc().bsdfs[0].reflectance]
+        assert sp[0] == capi.SPEC_REGULAR and sp[3:5] == (400.0, 700.0)
+        np.testing.assert_allclose(sp[5], [0.1, 0.2, 0.4, 0.8], rtol=1e-7)
+    inner = '<emitter type="area"><spectrum name="radiance" value="3"/></emitter>'
+    with _scene(MINIMAL.format(body=QUAD.format(inner=inner))) as hs:  # constant spectrum in an emitter -> d65 * 3 / 10568
+        sp = _spectra(hs.desc())[hs.desc().emitters[0].radiance]
+        assert sp[0] == capi.SPEC_REGULAR and len(sp[5]) == 95
+        from misaki_render_b200.scene import D65_TABLE
+        scale = np.float32(np.float32(3) * np.float32(np.float32(1) / np.float32(10568)))
+        np.testing.assert_array_equal(np.array(sp[5], np.float32), (D65_TABLE * scale).astype(np.float32))
+
+
+def test_material_plugins_and_their_parameter_checks():
+    rc = ('<bsdf type="roughconductor"><string name="distribution" value="ggx"/><float name="alpha" value="0.1"/>'
+          '<rgb name="eta" value="0.200438, 0.924033, 1.10221"/><rgb name="k" value="3.91295, 2.45285, 2.14219"/></bsdf>')
+    with _scene(MINIMAL.format(body=QUAD.format(inner=rc))) as hs:
+        d = hs.desc()
+        b = d.bsdfs[0]
+        assert (b.type, b.distribution, b.sample_visible, b.twosided) == (capi.BSDF_ROUGHCONDUCTOR, 1, 0, 0)
+        assert abs(b.alpha_u - 0.1) < 1e-7 and b.alpha_u == b.alpha_v
+        sd = scenes.bunny(8, 8, n=2)  # the programmatic C2 material: same eta / k treatment (unbounded spectra)
+        pb = sd.c_desc().bsdfs[sd.meshes[2]["bsdf"]]
+        hspec, pspec = _spectra(d), _spectra(sd.c_desc())
+        assert hspec[b.eta] == pspec[pb.eta] and hspec[b.k] == pspec[pb.k]
+        assert hspec[b.eta][0] == capi.SPEC_SRGB_UNBOUNDED
+    with _scene(MINIMAL.format(body=QUAD.format(inner=f'<bsdf type="twosided">{rc}</bsdf>'))) as hs:
+        assert hs.desc().bsdfs[0].twosided == 1 and hs.desc().bsdfs[0].type == capi.BSDF_ROUGHCONDUCTOR
+    rd = '<bsdf type="roughdielectric"><string name="distribution" value="GGX"/><float name="int_ior" value="1.5"/><float name="ext_ior" value="1"/></bsdf>'
+    with _scene(MINIMAL.format(body=QUAD.format(inner=rd))) as hs:  # roughdielectric lower-cases the name (roughdielectric.cpp:26)
+        b = hs.desc().bsdfs[0]
+        assert (b.type, b.int_ior, b.ext_ior, b.distribution) == (capi.BSDF_ROUGHDIELECTRIC, 1.5, 1.0, 1)
+    for bad, msg in [
+        ('<bsdf type="roughconductor"><rgb name="eta" value="1,1,1"/></bsdf>', "beckmann"),  # the reference default is a stub
+        ('<bsdf type="roughconductor"><string name="distribution" value="ggx"/></bsdf>', "eta"),
+        ('<bsdf type="roughconductor"><string name="distribution" value="phong"/><rgb name="eta" value="1,1,1"/></bsdf>', "invalid distribution"),
+        ('<bsdf type="roughdielectric"><string name="distribution" value="ggx"/><float name="alpha_u" value="0.1"/></bsdf>', "alpha_u"),
+        ('<bsdf type="dielectric"><float name="int_ior" value="1.2"/><float name="ext_ior" value="1.2"/></bsdf>', "indices of refraction"),
+        (f'<bsdf type="twosided">{rd}</bsdf>', "transmission"),
+        ('<bsdf type="phong"/>', 'Plugin "phong" not found'),
+        ('<bsdf type="gaussian"/>', "Type mismatch"),
+        ('<bsdf type="diffuse"/><bsdf type="diffuse"/>', "Only one bsdf"),
+    ]:
+        with pytest.raises(host_api.HostError, match=msg):
+            _scene(MINIMAL.format(body=QUAD.format(inner=bad)))
+
+
+def test_environment_emitter_and_scene_level_checks():
+    env = '<emitter type="constant"><rgb name="radiance" value="0.5, 0.6, 0.8"/></emitter>'
+    light = QUAD.format(inner='<emitter type="area"><rgb name="radiance" value="15,15,15"/></emitter>')
+    with _scene(MINIMAL.format(body=light + env)) as hs:
+        d = hs.desc()
+        assert d.nemitters == 2 and d.environment == 1 and d.emitters[1].type == capi.EMITTER_CONSTANT and d.emitters[1].shape == -1
+    with pytest.raises(host_api.HostError, match="one environment light"):
+        _scene(MINIMAL.format(body=env + env))
+    with pytest.raises(host_api.HostError, match="Can only have one camera"):
+        _scene(MINIMAL.format(body='<sensor type="perspective"/>'))
+    with pytest.raises(host_api.HostError, match="must be a <scene> tag"):
+        host_api.HostScene(xml='<bsdf type="diffuse"/>')
+
+
+def test_integrator_parameters_and_ignored_tags():
+    integ = ('<integrator type="path"><integer name="max_depth" value="7"/><integer name="rr_depth" value="3"/>'
+             '<boolean name="hide_emitters" value="true"/></integrator>')
+    sampler = '<sampler type="independent"><integer name="sample_count" value="24"/><integer name="base_seed" value="9"/></sampler>'
+    xml = MINIMAL.format(body=integ).replace('<film type="hdrfilm">', sampler + '<film type="hdrfilm">')
+    with _scene(xml) as hs:
+        rd = hs.render_desc()
+        # <boolean> has no case in the reference's parser switch (xml.cpp:421-662): accepted, ignored
+        assert (rd.spp, rd.base_seed, rd.max_depth, rd.rr_depth, rd.hide_emitters) == (24, 9, 7, 3, 0)
+    with pytest.raises(host_api.HostError, match="rr_depth"):
+        _scene(MINIMAL.format(body='<integrator type="path"><integer name="rr_depth" value="0"/></integrator>'))
+    with pytest.raises(host_api.HostError, match="max_depth"):
+        _scene(MINIMAL.format(body='<integrator type="path"><integer name="max_depth" value="-2"/></integrator>'))
+    with _scene("<scene><sensor type=\"perspective\"/></scene>") as hs:  # defaults: film 640x320 (film.cpp:10), 1 spp, path
+        assert (hs.desc().camera.width, hs.desc().camera.height, hs.render_desc().spp) == (640, 320, 1)
+
+
+@pytest.mark.parametrize("xml,msg", [
+    ("<scene><foo/></scene>", 'unexpected tag "foo"'),
+    ('<scene><sensor type="perspective" bogus="1"/></scene>', 'unexpected attribute "bogus"'),
+    ('<scene><sensor type="perspective"><float name="fov"/></sensor></scene>', 'missing attribute "value"'),
+    ('<scene><sensor type="perspective"><float name="fov" value="12x"/></sensor></scene>', "could not parse floating point value"),
+    ('<scene><sensor type="perspective"><float name="_fov" value="1"/></sensor></scene>', "leading underscores"),
+    ('<scene><bsdf type="diffuse" id="a"/><bsdf type="diffuse" id="a"/></scene>', 'duplicate id "a"'),
+    ('<scene><translate x="1"/></scene>', "transform operations can only occur in a transform node"),
+    ('<scene><sensor type="perspective"><transform name="to_world"><float name="x" value="1"/></transform></sensor></scene>',
+     "transform nodes can only contain transform operations"),
+    ('<scene><sensor type="perspective"><float name="fov" value="1"><float name="y" value="2"/></float></sensor></scene>',
+     "cannot occur as child of a property"),
+    ("<float name=\"x\" value=\"1\"/>", "must be an object"),
+    ("<scene><sensor type=\"perspective\"></scene>", "mismatched closing tag"),
+    ("<scene>text</scene>", "unexpected content"),
+])
+def test_loader_errors(xml, msg):
+    with pytest.raises(host_api.HostError, match=msg):
+        host_api.HostScene(xml=xml)
+
+
+def test_transform_composition_and_param_substitution():
+    xml = """<scene><sensor type="perspective"><transform name="to_world">
+               <scale value="2"/><translate x="$tx" y="2" z="3"/><matrix value="1 0 0 10  0 1 0 0  0 0 1 0  0 0 0 1"/>
+             </transform></sensor></scene>"""
+    with pytest.raises(host_api.HostError, match="could not parse floating point value"):
+        host_api.HostScene(xml=xml)  # $tx not supplied
+    (ROOT / "gpurun_out").mkdir(exist_ok=True)
+    p = ROOT / "gpurun_out" / "_tmp_transform.xml"
+    p.write_text(xml)
+    with host_api.HostScene(p, params=dict(tx="1")) as hs:
+        m = np.array(hs.desc().camera.to_world[:]).reshape(4, 4)
+    # later operations are applied on the left (xml.cpp:647-660): M = matrix * translate * scale
+    expect = np.array([[2, 0, 0, 11], [0, 2, 0, 2], [0, 0, 2, 3], [0, 0, 0, 1]], dtype=np.float64)
+    np.testing.assert_allclose(m, expect, atol=1e-6)
+    p.unlink()
+
+
+def test_srgb_model_fetch_matches_the_reference_runtime():
+    """The C++ restatement of rgb2spec_fetch against the golden vectors generated by the compiled reference
+    (tests/golden/rgb2spec_fetch.json, tools/gen_golden_rgb2spec.py)."""
+    import json
+    golden = json.loads((ROOT / "tests" / "golden" / "rgb2spec_fetch.json").read_text())
+    n = 0
+    for row in golden["cases"]:
+        got = host_api.srgb_model_fetch(row["rgb"])
+        np.testing.assert_array_equal(got, np.array(row["coeff"], dtype=np.float32), err_msg=str(row["rgb"]))
+        n += 1
+    assert n > 50
+
+
+def test_film_development_and_exr_round_trip(tmp_path):
+    rng = np.random.default_rng(0)
+    film = rng.random((5, 7, 5)).astype(np.float32)
+    film[0, 0, 4] = 0  # zero weight -> black, hdrfilm.cpp:71-76
+    rgba = host_api.develop(film)
+    m = np.array([[3.240479, -1.537150, -0.498535], [-0.969256, 1.875991, 0.041556], [0.055648, -0.204043, 1.057311]], dtype=np.float32)
+    expect = np.einsum("ij,hwj->hwi", m, film[..., :3]) / np.where(film[..., 4:5] != 0, film[..., 4:5], np.inf)
+    np.testing.assert_allclose(rgba[..., :3], expect, rtol=2e-6, atol=1e-7)
+    assert (rgba[0, 0] == 0).all()
+    host_api.write_exr(tmp_path / "a.exr", rgba)
+    np.testing.assert_array_equal(host_api.read_exr_rgba(tmp_path / "a.exr"), rgba)
+    host_api.write_pfm(tmp_path / "a.pfm", rgba)
+    raw = (tmp_path / "a.pfm").read_bytes()
+    assert raw.startswith(b"PF\n7 5\n-1.0\n")
+    px = np.frombuffer(raw[len(b"PF\n7 5\n-1.0\n"):], dtype="<f4").reshape(5, 7, 3)
+    np.testing.assert_array_equal(px[::-1], rgba[..., :3])
