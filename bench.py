@@ -185,6 +185,217 @@ def run_reference(args, rank: int):
     print(json.dumps(line), flush=True)
 
 
+
+# --------------------------------------------------------------------------------------------- C5 intersection sweep
+def c5_inputs(res: int, rank: int):
+    """BASELINE configs[4]: the 9 998 244-triangle displaced sphere and its two ray sets."""
+    from workloads import scenes
+    sd = scenes.sphere10m()
+    prim = scenes.primary_rays(sd, res)
+    return sd, prim
+
+
+def c5_oracle_sample(sd, sets, budget_s: float):
+    """CPU arm of C5: the oracle's SAH BVH2 + Moeller-Trumbore (all host threads) on a strided sample of each ray
+    set, closest hit and any hit.  Returns (Mrays/s, info)."""
+    from oracle import pyoracle
+    osc = pyoracle.OracleScene(sd)  # builds the BVH
+    probe = {k: v[:: max(1, len(v) // 20000)] for k, v in sets.items()}
+    t0 = time.perf_counter()
+    for v in probe.values():
+        osc.intersect(v)
+    per_ray = (time.perf_counter() - t0) / sum(len(v) for v in probe.values())
+    n_each = int(max(20000, min(min(len(v) for v in sets.values()), budget_s / (4 * per_ray))))
+    rays_done, secs, detail = 0, 0.0, {}
+    for k, v in sets.items():
+        smp = np.ascontiguousarray(v[:: max(1, len(v) // n_each)][:n_each])
+        t0 = time.perf_counter(); osc.intersect(smp); t1 = time.perf_counter(); osc.occluded(smp); t2 = time.perf_counter()
+        detail[k] = {"closest_mrays_s": len(smp) / (t1 - t0) / 1e6, "any_mrays_s": len(smp) / (t2 - t1) / 1e6, "rays": len(smp)}
+        rays_done += 2 * len(smp); secs += t2 - t0
+    osc.close()
+    return rays_done / secs / 1e6, dict(detail=detail, seconds=secs, rays=rays_done, threads=os.cpu_count())
+
+
+def run_c5_reference(args, rank: int):
+    if rank != 0:
+        return
+    sd, prim = c5_inputs(args.c5_res, 0)
+    from oracle import pyoracle
+    osc = pyoracle.OracleScene(sd)
+    ph = osc.intersect(np.ascontiguousarray(prim[:: max(1, len(prim) // 400000)]))
+    from workloads import scenes
+    m = sd.meshes[0]
+    sub = np.ascontiguousarray(prim[:: max(1, len(prim) // 400000)])
+    sec = scenes.secondary_rays((m["verts"], m["tris"]), sub, ph, seed=0)
+    osc.close()
+    v, inf = c5_oracle_sample(sd, {"primary": sub, "secondary": sec}, args.ref_budget / (args.steps + args.warmup) * 1.0)
+    sample = f"strided sample of {inf['rays'] // 4} rays of each set (primary from the {args.c5_res}^2 grid, secondary from their hits), closest + any hit"
+    line = {"impl": "reference", "metric": "Mrays/s", "value": v, "unit": "Mrays/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": inf["seconds"] * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": C5_NAME, "sample_per_step": sample}, "detail": inf["detail"],
+            "cpu_baseline": {"value": v, "unit": "Mrays/s", "cores": inf["threads"], "kind": "port", "sample": sample, "cpu": cpu_model(),
+                             "note": "oracle SAH BVH2 + Moeller-Trumbore, std::thread; NOT Embree"},
+            "e2e": {"value": v, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+C5_NAME = "C5 10M-triangle displaced sphere (9998244 tris, one geomID): 4096^2 primary + incoherent cosine-hemisphere secondary rays, closest hit + any hit"
+
+
+def run_c5(args, rank: int, local_rank: int, world: int):
+    """Intersection sweep: one STEP = closest-hit and any-hit queries over both ray sets (4 launches).  Rays and
+    results are resident in HBM for `value`; `e2e` goes through msk_gpu_intersect / msk_gpu_occluded with pinned
+    host buffers.  N > 1: every rank traces the full ray sets against its own BVH replica (weak scaling, no
+    collective -- the queries are independent)."""
+    import torch
+    import torch.distributed as dist
+    from misaki_render_b200 import capi
+    from workloads import scenes
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- this backend has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    sd, prim = c5_inputs(args.c5_res, rank)
+    ctx = capi.Context(local_rank)
+    t0 = time.time()
+    scene = capi.Scene(ctx, sd)
+    t_scene = time.time() - t0
+    info = scene.accel_info()
+    ext = torch.cuda.ExternalStream(ctx.stream, device=dev)
+
+    def to_dev(a):
+        return torch.from_numpy(a.view(np.uint8).reshape(-1)).to(dev)
+
+    d_prim = to_dev(prim)
+    n_prim = len(prim)
+    d_hits = torch.empty(n_prim * 20, dtype=torch.uint8, device=dev)
+    d_occ = torch.empty(n_prim, dtype=torch.uint8, device=dev)
+    with torch.cuda.stream(ext):
+        scene.intersect_dev(d_prim.data_ptr(), d_hits.data_ptr(), n_prim)
+    torch.cuda.synchronize()
+    hits = d_hits.cpu().numpy().view(capi.HIT_DTYPE)
+    m = sd.meshes[0]
+    sec = scenes.secondary_rays((m["verts"], m["tris"]), prim, hits, seed=0)
+    n_sec = len(sec)
+    d_sec = to_dev(sec)
+    sets = [("primary", d_prim, n_prim), ("secondary", d_sec, n_sec)]
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(5)] for _ in range(args.steps)]
+
+    def step(ev):
+        with torch.cuda.stream(ext):
+            k = 0
+            for _, d_r, n in sets:
+                if ev: ev[k].record(ext)
+                scene.intersect_dev(d_r.data_ptr(), d_hits.data_ptr(), n); k += 1
+                if ev: ev[k].record(ext)
+                scene.occluded_dev(d_r.data_ptr(), d_occ.data_ptr(), n); k += 1
+            if ev: ev[k].record(ext)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step(None)
+    sampler = ClockSampler(physical_gpu_index(local_rank)) if rank == 0 else None
+    barrier()
+    tm0 = time.time()
+    for i in range(args.steps):
+        step(evs[i])
+    barrier()
+    tm1 = time.time()
+    ms_total = sum(e[0].elapsed_time(e[4]) for e in evs)
+    if world > 1:
+        t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+    clocks = sampler.stop(tm0, tm1) if sampler else None
+    ms_step = ms_total / args.steps
+    rays_step = 2 * (n_prim + n_sec) * world
+    value = rays_step / (ms_step * 1e-3) / 1e6
+    names = ["primary_closest", "primary_any", "secondary_closest", "secondary_any"]
+    counts = [n_prim, n_prim, n_sec, n_sec]
+    launch_ms = {nm: float(np.mean([e[i].elapsed_time(e[i + 1]) for e in evs])) for i, nm in enumerate(names)}
+    launch_mrays = {nm: counts[i] / (launch_ms[nm] * 1e-3) / 1e6 for i, nm in enumerate(names)}
+
+    # ---- end to end through the host-buffer entry points (H2D of the rays, D2H of the results inside)
+    pin_r = torch.from_numpy(sec.view(np.uint8).reshape(-1)).pin_memory()
+    pin_h = torch.empty(n_sec * 20, dtype=torch.uint8).pin_memory()
+    pin_o = torch.empty(n_sec, dtype=torch.uint8).pin_memory()
+    r_np, h_np, o_np = pin_r.numpy().view(capi.RAY_DTYPE), pin_h.numpy().view(capi.HIT_DTYPE), pin_o.numpy()
+    lib = capi.load()
+
+    def e2e_step():
+        capi.check(lib, lib.msk_gpu_intersect(scene.handle, r_np.ctypes.data, h_np.ctypes.data, n_sec))
+        capi.check(lib, lib.msk_gpu_occluded(scene.handle, r_np.ctypes.data, o_np.ctypes.data, n_sec))
+
+    e2e_step()
+    barrier()
+    w0 = time.perf_counter()
+    e2e_n = max(1, min(args.steps, 5))
+    for _ in range(e2e_n):
+        e2e_step()
+    barrier()
+    e2e_s = time.perf_counter() - w0
+    e2e = {"value": 2 * n_sec * world * e2e_n / e2e_s / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": 2 * n_sec * 32, "d2h_bytes_per_step": n_sec * 21,
+           "ms_per_step": e2e_s / e2e_n * 1e3, "timer": "host wall clock",
+           "note": f"secondary set only: msk_gpu_intersect + msk_gpu_occluded with pinned host rays/results; one-off scene upload + BVH build = {t_scene * 1e3:.0f} ms "
+                   f"(BVH build {info.ms_build:.1f} ms on device)"}
+
+    roofline = cpu = None
+    if rank == 0:
+        # traversal terms of the bytes model, counted by the instrumented kernel on a strided 1 Mi-ray sample of each set
+        per = {}
+        for nm, arr in (("primary", prim), ("secondary", sec)):
+            smp = np.ascontiguousarray(arr[:: max(1, len(arr) // (1 << 20))])
+            nn, nt = scene.intersect_stats(smp)
+            per[nm] = {"nodes": float(nn.mean()), "tris": float(nt.mean())}
+        top = max(("primary_closest", "secondary_closest"), key=lambda k: launch_ms[k])
+        which = top.split("_")[0]
+        n_top = n_prim if which == "primary" else n_sec
+        bytes_ray = BYTES_RAY_IN + BYTES_HIT_OUT + per[which]["nodes"] * BYTES_NODE + per[which]["tris"] * BYTES_TRI
+        peaks_file = ROOT / "MEASURED_PEAKS.json"
+        if peaks_file.exists():
+            peak, peak_src = float(json.loads(peaks_file.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        else:
+            peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+        achieved = n_top * bytes_ray / (launch_ms[top] * 1e-3) / 1e9
+        traffic = None
+        tf = ROOT / "profiles" / "roofline_traffic.json"
+        if tf.exists():
+            try:
+                traffic = json.loads(tf.read_text()).get("c5", {}).get(top)
+            except (ValueError, OSError):
+                traffic = None
+        roofline = {"bound": "hbm", "kernel": f"k_query_closest ({which} rays)", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                    "traffic": traffic, "peak_source": peak_src, "launches_per_step": 1, "avg_launch_ms": launch_ms[top],
+                    "algorithmic_bytes_per_launch": n_top * bytes_ray, "per_ray": per,
+                    "bytes_model": "SURVEY 8(d): 32 B ray + 20 B hit + visited wide nodes x 80 B + tested triangles x 48 B per closest-hit ray "
+                                   "(counted on a strided 1 Mi-ray sample); BVH + triangles = "
+                                   f"{(info.node_bytes + info.tri_bytes) / 1e6:.0f} MB > 126 MB L2",
+                    "launch_ms": launch_ms, "launch_mrays_per_s": launch_mrays}
+        if world == 1 and not args.no_cpu:
+            v, inf = c5_oracle_sample(sd, {"primary": prim, "secondary": sec}, args.cpu_budget)
+            cpu = {"value": v, "unit": "Mrays/s", "cores": inf["threads"], "kind": "port", "cpu": cpu_model(), "detail": inf["detail"],
+                   "sample": f"strided sample of {inf['rays'] // 4} rays of each set, closest + any hit ({inf['seconds']:.1f} s)",
+                   "note": "oracle SAH BVH2 + Moeller-Trumbore over all host threads; NOT Embree"}
+        line = {"metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": C5_NAME, "rays_primary": n_prim, "rays_secondary": n_sec, "tris": int(info.ntris), "wide_nodes": int(info.nnodes),
+                           "bvh_bytes": int(info.node_bytes + info.tri_bytes), "bvh_build_ms": info.ms_build, "sah_cost": info.sah_cost,
+                           "l2": "ray sets (0.5 GB each) and the BVH (0.6 GB) exceed the 126 MB L2; no flush needed",
+                           "partition": "replicated BVH, every rank traces the full ray sets (independent queries, no collective)"},
+                "e2e": e2e, "gpu_launches": 4 * args.steps, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "wall_s_timed_region": tm1 - tm0}
+        print(json.dumps(line), flush=True)
+    scene.close()
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
 # --------------------------------------------------------------------------------------------- our arm
 def run_ours(args, rank: int, local_rank: int, world: int):
     import torch
@@ -368,7 +579,8 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="c2", choices=["c1", "c2", "c3", "c4"])
+    ap.add_argument("--workload", default="c2", choices=["c1", "c2", "c3", "c4", "c5"])
+    ap.add_argument("--c5-res", type=int, default=4096, help="C5: primary rays are a res x res pinhole grid")
     ap.add_argument("--spp", type=int, default=0, help="override samples per pixel per GPU (development only)")
     ap.add_argument("--cpu-budget", type=float, default=15.0, help="seconds of CPU work for cpu_baseline")
     ap.add_argument("--ref-budget", type=float, default=150.0, help="seconds for the whole --impl reference run")
@@ -380,14 +592,14 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if args.impl == "reference":
-        run_reference(args, rank)
+        (run_c5_reference if args.workload == "c5" else run_reference)(args, rank)
         return
     if world == 1 and args.gpus > 1:
         # bare `python bench.py --gpus N`: re-launch under torchrun, one rank per GPU
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
                "--master-addr", "127.0.0.1", "--master-port", os.environ.get("MASTER_PORT", "29531"), str(Path(__file__).resolve())] + sys.argv[1:]
         raise SystemExit(subprocess.call(cmd))
-    run_ours(args, rank, local_rank, world)
+    (run_c5 if args.workload == "c5" else run_ours)(args, rank, local_rank, world)
 
 
 if __name__ == "__main__":

@@ -973,6 +973,24 @@ std::vector<BlockDesc> spiral_blocks(int W, int H, int bs) {
 // ==========================================================================================
 struct OrcScene { OScene sc; };
 
+// Batch queries are independent per ray: chunks of 256 rays handed out to all host threads.
+template <typename F> static void parallel_rays(size_t n, F &&body) {
+    const unsigned nthreads = (unsigned) std::min<size_t>(std::max(1u, std::thread::hardware_concurrency()), (n + 255) / 256);
+    if (nthreads <= 1) { for (size_t i = 0; i < n; ++i) body(i); return; }
+    std::atomic<size_t> next{ 0 };
+    auto worker = [&]() {
+        for (;;) {
+            const size_t b = next.fetch_add(256);
+            if (b >= n) break;
+            for (size_t i = b, e = std::min(n, b + 256); i < e; ++i) body(i);
+        }
+    };
+    std::vector<std::thread> pool;
+    for (unsigned t = 1; t < nthreads; ++t) pool.emplace_back(worker);
+    worker();
+    for (auto &t : pool) t.join();
+}
+
 extern "C" {
 
 const char *orc_last_error(void) { return g_error.c_str(); }
@@ -1034,30 +1052,29 @@ void orc_scene_destroy(OrcScene *s) { delete s; }
 
 int orc_intersect(OrcScene *s, const MskRay *rays, MskHit *hits, size_t n, int brute_force) {
     if (!s) return fail("null scene");
-    RayCounters rc;
-    for (size_t i = 0; i < n; ++i) {
+    parallel_rays(n, [&](size_t i) {
         Ray r{ V3(rays[i].o[0], rays[i].o[1], rays[i].o[2]), V3(rays[i].d[0], rays[i].d[1], rays[i].d[2]), rays[i].tmin, rays[i].tmax, Spec() };
         RawHit h = brute_force ? intersect_brute(s->sc, r) : intersect_bvh(s->sc, r, false);
         if (h.t == r.maxt) h = RawHit();
         hits[i] = { h.t, h.u, h.v, h.prim, h.geom };
-    }
+    });
     return 0;
 }
 
 int orc_occluded(OrcScene *s, const MskRay *rays, uint8_t *occ, size_t n) {
     if (!s) return fail("null scene");
-    RayCounters rc;
-    for (size_t i = 0; i < n; ++i) {
+    parallel_rays(n, [&](size_t i) {
+        RayCounters rc;
         Ray r{ V3(rays[i].o[0], rays[i].o[1], rays[i].o[2]), V3(rays[i].d[0], rays[i].d[1], rays[i].d[2]), rays[i].tmin, rays[i].tmax, Spec() };
         occ[i] = ray_test(s->sc, r, rc) ? 1 : 0;
-    }
+    });
     return 0;
 }
 
 // "second closest" distance, used by the tests to define non-degenerate rays (hard part iv)
 int orc_intersect_margin(OrcScene *s, const MskRay *rays, float *second_t, float *min_bary, size_t n) {
     if (!s) return fail("null scene");
-    for (size_t i = 0; i < n; ++i) {
+    parallel_rays(n, [&](size_t i) {
         Ray r{ V3(rays[i].o[0], rays[i].o[1], rays[i].o[2]), V3(rays[i].d[0], rays[i].d[1], rays[i].d[2]), rays[i].tmin, rays[i].tmax, Spec() };
         float t1 = Infinity, t2 = Infinity, mb = 0.f;
         for (uint32_t g = 0; g < s->sc.meshes.size(); ++g) {
@@ -1072,7 +1089,7 @@ int orc_intersect_margin(OrcScene *s, const MskRay *rays, float *second_t, float
             }
         }
         second_t[i] = t2; min_bary[i] = mb;
-    }
+    });
     return 0;
 }
 

@@ -58,3 +58,98 @@ def test_sample_range_partition_matches_whole(gpu_ctx):
     np.testing.assert_array_equal(whole, again)  # deterministic film: gather, no float atomics
     np.testing.assert_allclose(part, whole, rtol=2e-5, atol=1e-6)
     np.testing.assert_allclose(small_batches, whole, rtol=2e-5, atol=1e-6)
+
+
+def _report(name, e, stats, ost):
+    print(f"[{name}] relMSE={e:.3e} gpu rays c/s={stats.rays_closest}/{stats.rays_shadow} oracle={ost.rays_closest}/{ost.rays_shadow} "
+          f"bounces={stats.bounces}")
+
+
+def test_roughconductor_equal_seed(gpu_ctx):
+    """C2's material (roughconductor.cpp:53-120, GGX, unbounded eta/k spectra) on a small bunny-class mesh with
+    interpolated shading normals; unbounded depth with Russian roulette (path.cpp:112-120)."""
+    sd = scenes.bunny(64, 64, n=12)
+    rd = capi.render_desc(spp=8, max_depth=-1, rr_depth=5)
+    film, rgba, ofilm, oref, stats, ost = _both(gpu_ctx, sd, rd)
+    e = relmse(rgba, oref)
+    _report("roughconductor", e, stats, ost)
+    assert np.isfinite(film).all()
+    np.testing.assert_allclose(film[..., 4], ofilm[..., 4], rtol=1e-5)
+    assert e < EQUAL_SEED_RELMSE, e
+    assert abs(int(stats.rays_closest) - int(ost.rays_closest)) <= 2e-3 * ost.rays_closest
+
+
+def test_roughdielectric_environment_equal_seed(gpu_ctx):
+    """C3's material (roughdielectric.cpp:58-190: reflection/refraction choice, eta-scaled radiance, RR with
+    eta^2) plus a quad light and the constant environment (constant.cpp:21-81), depth 16."""
+    sd = scenes.teapot(64, 64, n=12)
+    rd = capi.render_desc(spp=8, max_depth=16, rr_depth=5)
+    film, rgba, ofilm, oref, stats, ost = _both(gpu_ctx, sd, rd)
+    e = relmse(rgba, oref)
+    _report("roughdielectric+env", e, stats, ost)
+    assert np.isfinite(film).all()
+    assert e < EQUAL_SEED_RELMSE, e
+    assert abs(int(stats.rays_closest) - int(ost.rays_closest)) <= 2e-3 * ost.rays_closest
+
+
+def _material_zoo(width=64, height=64):
+    """Every BSDF type of include/misaki_b200.h in one scene, two area lights (Scene::sample_emitter_direct's
+    N > 1 branch, scene.cpp:72-80) and an environment."""
+    from misaki_render_b200.scene import SceneDescription, lookat
+    from workloads import meshes
+    sd = SceneDescription(width, height, fov=40.0, near_clip=0.1, far_clip=100.0,
+                          to_world=lookat((0.0, 2.5, -6.0), (0.0, 0.8, 0.0), (0, 1, 0)))
+    gv, gt = meshes.quad((-6, 0, -6), (-6, 0, 6), (6, 0, 6), (6, 0, -6))
+    sd.add_mesh(gv, gt, sd.bsdf_diffuse((0.6, 0.5, 0.4)))
+    for cx, half, rad in ((-2.0, 0.7, (12, 10, 8)), (2.0, 0.5, (6, 9, 14))):
+        lv, lt = meshes.quad((cx - half, 4.0, -half), (cx + half, 4.0, -half), (cx + half, 4.0, half), (cx - half, 4.0, half))
+        sd.add_mesh(lv, lt, sd.bsdf_diffuse((0.5, 0.5, 0.5)), radiance=rad)
+    gold = dict(eta=(0.143, 0.375, 1.442), k=(3.983, 2.386, 1.603))
+    mats = [
+        sd.bsdf_conductor(**gold),
+        sd.bsdf_roughconductor(alpha=(0.05, 0.3), twosided=True, **gold),
+        sd.bsdf_dielectric(int_ior=1.5, ext_ior=1.0),
+        sd.bsdf_roughdielectric(int_ior=1.33, ext_ior=1.0, alpha=0.25, specular_transmittance=(0.9, 0.95, 1.0)),
+        sd.bsdf_diffuse((0.2, 0.7, 0.3), twosided=True),
+    ]
+    for i, mat in enumerate(mats):
+        v, t = meshes.cube_sphere(6, seed=10 + i, octaves=2, amplitude=0.1, radius=0.55, center=(-3.0 + 1.5 * i, 0.7, 0.3 * (i % 2)),
+                                  normals=(i != 2), uvs=(i % 2 == 0))
+        sd.add_mesh(v, t, mat, has_normals=(i != 2), has_uvs=(i % 2 == 0))
+    # an open one-sided quad seen from behind (cos_theta(wi) <= 0 paths of diffuse.cpp:24-25)
+    bv, bt = meshes.quad((-1, 0.2, 2.5), (1, 0.2, 2.5), (1, 2.2, 2.5), (-1, 2.2, 2.5))
+    sd.add_mesh(bv, bt, sd.bsdf_diffuse((0.8, 0.8, 0.2)))
+    sd.add_constant_environment((0.3, 0.35, 0.5))
+    return sd
+
+
+@pytest.mark.parametrize("max_depth,rr_depth,hide", [(6, 5, False), (-1, 3, True)])
+def test_material_zoo_equal_seed(gpu_ctx, max_depth, rr_depth, hide):
+    sd = _material_zoo()
+    rd = capi.render_desc(spp=8, max_depth=max_depth, rr_depth=rr_depth, hide_emitters=hide)
+    film, rgba, ofilm, oref, stats, ost = _both(gpu_ctx, sd, rd)
+    e = relmse(rgba, oref)
+    _report(f"zoo depth={max_depth}", e, stats, ost)
+    assert np.isfinite(film).all()
+    np.testing.assert_allclose(film[..., 3], ofilm[..., 3], rtol=1e-5)  # alpha channel: hide_emitters / misses
+    assert e < EQUAL_SEED_RELMSE, e
+
+
+def test_base_seed_and_convergence(gpu_ctx):
+    """Measurement (ii) of SURVEY 8d in miniature: against a high-spp render, the GPU's error at N spp must
+    equal the oracle's error at N spp (both are the same estimator), and a different base_seed must give a
+    different but statistically equivalent image."""
+    sd = scenes.cbox(32, 32)
+    with capi.Scene(gpu_ctx, sd) as sc:
+        ref_film, _ = sc.render(capi.render_desc(spp=4096, max_depth=5, base_seed=12345))
+        ref = sc.develop(ref_film)
+        a_film, _ = sc.render(capi.render_desc(spp=32, max_depth=5))
+        b_film, _ = sc.render(capi.render_desc(spp=32, max_depth=5, base_seed=777))
+        a, b = sc.develop(a_film), sc.develop(b_film)
+    ofilm, _ = pyoracle.OracleScene(sd).render(capi.render_desc(spp=32, max_depth=5))
+    o = pyoracle.develop(ofilm)
+    ea, eb, eo = relmse(a, ref), relmse(b, ref), relmse(o, ref)
+    print(f"[convergence] relMSE vs 4096spp: gpu={ea:.4e} gpu(seed 777)={eb:.4e} oracle={eo:.4e}")
+    assert not np.array_equal(a_film, b_film)
+    assert abs(ea - eo) <= 0.02 * eo  # same seeds: same estimator up to float noise
+    assert 0.5 * eo < eb < 2.0 * eo   # other seeds: same variance

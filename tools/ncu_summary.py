@@ -102,8 +102,44 @@ def ops_summary(rep, top=28):
             print(f"   {op:10s} {a[3]:6d} {a[0]:12d} {100 * a[0] / max(tot_i, 1):6.2f} {a[1] / max(a[0], 1):8.2f} {100 * a[2] / max(tot_s, 1):8.2f}")
 
 
+def lines_summary(rep, top=45):
+    """Per CUDA source line (needs -lineinfo and --import-source on): warp instructions, threads per instruction and
+    stall samples, for the first launch in the report."""
+    out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "sass,cuda"], capture_output=True, text=True).stdout
+    fname, func, hdr, seen_funcs = None, None, None, []
+    agg = {}
+    for r in csv.reader(io.StringIO(out)):
+        if not r:
+            continue
+        if r[0] == "File Path":
+            fname = r[1].split("/")[-1]
+        elif r[0] == "Function Name":
+            func = r[1]
+            if func not in seen_funcs:
+                seen_funcs.append(func)
+        elif r[0] == "Line No":
+            hdr = r
+        elif hdr and r[0].isdigit() and len(r) > 10:
+            if len(seen_funcs) > 1 and func != seen_funcs[0]:
+                continue
+            ci, ct, cs = hdr.index("Instructions Executed"), hdr.index("Thread Instructions Executed"), hdr.index("# Samples")
+            try:
+                key = (fname, int(r[0]))
+                a = agg.setdefault(key, [0, 0, 0, r[1].strip()[:90]])
+                a[0] += int(r[ci]); a[1] += int(r[ct]); a[2] += int(r[cs])
+            except ValueError:
+                pass
+    ti = sum(a[0] for a in agg.values()); ts = sum(a[2] for a in agg.values())
+    print(f"-- per source line ({seen_funcs[0][:80] if seen_funcs else '?'}): {ti} warp instructions, {ts} samples")
+    print(f"   {'file:line':28s} {'%inst':>6s} {'thr/inst':>8s} {'%samples':>8s}  source")
+    for (f, ln), a in sorted(agg.items(), key=lambda kv: -kv[1][0])[:top]:
+        print(f"   {f + ':' + str(ln):28s} {100 * a[0] / max(ti, 1):6.2f} {a[1] / max(a[0], 1):8.2f} {100 * a[2] / max(ts, 1):8.2f}  {a[3]}")
+
+
 if __name__ == "__main__":
     rep = sys.argv[1]
     raw_summary(rep)
     if "--ops" in sys.argv:
         ops_summary(rep)
+    if "--lines" in sys.argv:
+        lines_summary(rep)
