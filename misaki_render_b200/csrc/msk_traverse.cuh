@@ -27,41 +27,54 @@ struct RayHit {
     uint32_t prim, geom;
 };
 
-struct WoopRay { // per-ray constants of the watertight test
-    int kx, ky, kz;
-    float sx, sy, sz;
+// Per-ray constants of the watertight test.  Woop et al. permute the axes so that the dominant direction
+// component becomes z and shear the translated vertices: Ax = A[kx] - sx A[kz], Ay = A[ky] - sy A[kz],
+// Az = sz A[kz].  Here the permutation and the shear are ONE 3x3 matrix with rows
+//   mx = e_kx - sx e_kz,   my = e_ky - sy e_kz,   mz = sz e_kz
+// applied to (v - o) with plain FMAs.  The first version selected A[kx], A[ky], A[kz] with a dynamic index
+// (nine 3-way selects per triangle); ncu attributed 15 % of the kernel's warp instructions to those selects at
+// 7 of 32 lanes active (profiles/r01c_ncu_k_intersect.txt).  Watertightness needs the sheared coordinates to be a
+// function of (ray, vertex) alone -- they are: the same matrix multiplies every vertex -- and the edge functions
+// U, V, W to be exact negatives across a shared edge, which the explicit round-to-nearest mul/sub below keep.
+struct WoopRay {
+    float mxx, mxy, mxz, myx, myy, myz, mzx, mzy, mzz;
 };
 
-__device__ __forceinline__ float pick(float x, float y, float z, int k) { return k == 0 ? x : (k == 1 ? y : z); }
+__device__ __forceinline__ float rcp_approx(float x) { // MUFU.RCP, 1 ulp; inf for +-0
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
 
 __device__ __forceinline__ WoopRay woop_setup(float dx, float dy, float dz) {
+    const float ax = fabsf(dx), ay = fabsf(dy), az = fabsf(dz);
+    const int kz = (ax > ay) ? (ax > az ? 0 : 2) : (ay > az ? 1 : 2);
+    const float dkz = kz == 0 ? dx : (kz == 1 ? dy : dz);
+    int kx = kz == 2 ? 0 : kz + 1, ky = 3 - kz - kx;
+    if (dkz < 0.f) { const int tmp = kx; kx = ky; ky = tmp; } // keep the winding
+    const float dkx = kx == 0 ? dx : (kx == 1 ? dy : dz), dky = ky == 0 ? dx : (ky == 1 ? dy : dz);
+    // d = 0 (a failed BSDF sample never gets here, but the C ABI accepts any ray): sz = inf, the matrix is NaN,
+    // every comparison fails and the ray misses, as with the reference's 0/0
+    const float sz = rcp_approx(dkz), sx = dkx * sz, sy = dky * sz;
+    const float ez0 = kz == 0 ? 1.f : 0.f, ez1 = kz == 1 ? 1.f : 0.f, ez2 = kz == 2 ? 1.f : 0.f;
     WoopRay w;
-    float ax = fabsf(dx), ay = fabsf(dy), az = fabsf(dz);
-    w.kz = (ax > ay) ? (ax > az ? 0 : 2) : (ay > az ? 1 : 2);
-    w.kx = w.kz + 1; if (w.kx == 3) w.kx = 0;
-    w.ky = w.kx + 1; if (w.ky == 3) w.ky = 0;
-    float dkz = pick(dx, dy, dz, w.kz);
-    if (dkz < 0.f) { int tmp = w.kx; w.kx = w.ky; w.ky = tmp; }
-    w.sx = pick(dx, dy, dz, w.kx) / dkz;
-    w.sy = pick(dx, dy, dz, w.ky) / dkz;
-    w.sz = 1.f / dkz;
+    w.mxx = fmaf(-sx, ez0, kx == 0 ? 1.f : 0.f); w.mxy = fmaf(-sx, ez1, kx == 1 ? 1.f : 0.f); w.mxz = fmaf(-sx, ez2, kx == 2 ? 1.f : 0.f);
+    w.myx = fmaf(-sy, ez0, ky == 0 ? 1.f : 0.f); w.myy = fmaf(-sy, ez1, ky == 1 ? 1.f : 0.f); w.myz = fmaf(-sy, ez2, ky == 2 ? 1.f : 0.f);
+    w.mzx = sz * ez0; w.mzy = sz * ez1; w.mzz = sz * ez2;
     return w;
 }
 
 // Returns true and updates (t,u,v) when tnear < t <= tfar.
 __device__ __forceinline__ bool woop_intersect(const WoopRay &w, float ox, float oy, float oz, float4 v0, float4 v1, float4 v2,
                                                float tnear, float tfar, float &t_out, float &u_out, float &v_out) {
-    float ax = v0.x - ox, ay = v0.y - oy, az = v0.z - oz;
-    float bx = v1.x - ox, by = v1.y - oy, bz = v1.z - oz;
-    float cx = v2.x - ox, cy = v2.y - oy, cz = v2.z - oz;
-    float Akx = pick(ax, ay, az, w.kx), Aky = pick(ax, ay, az, w.ky), Akz = pick(ax, ay, az, w.kz);
-    float Bkx = pick(bx, by, bz, w.kx), Bky = pick(bx, by, bz, w.ky), Bkz = pick(bx, by, bz, w.kz);
-    float Ckx = pick(cx, cy, cz, w.kx), Cky = pick(cx, cy, cz, w.ky), Ckz = pick(cx, cy, cz, w.kz);
-    // shear: explicit round-to-nearest mul/sub (never contracted to FMA) so that the edge functions of a
-    // shared edge are exact negatives of each other in the two triangles -- the watertightness property
-    float Ax = __fsub_rn(Akx, __fmul_rn(w.sx, Akz)), Ay = __fsub_rn(Aky, __fmul_rn(w.sy, Akz));
-    float Bx = __fsub_rn(Bkx, __fmul_rn(w.sx, Bkz)), By = __fsub_rn(Bky, __fmul_rn(w.sy, Bkz));
-    float Cx = __fsub_rn(Ckx, __fmul_rn(w.sx, Ckz)), Cy = __fsub_rn(Cky, __fmul_rn(w.sy, Ckz));
+    const float ax = v0.x - ox, ay = v0.y - oy, az = v0.z - oz;
+    const float bx = v1.x - ox, by = v1.y - oy, bz = v1.z - oz;
+    const float cx = v2.x - ox, cy = v2.y - oy, cz = v2.z - oz;
+    const float Ax = fmaf(w.mxx, ax, fmaf(w.mxy, ay, w.mxz * az)), Ay = fmaf(w.myx, ax, fmaf(w.myy, ay, w.myz * az));
+    const float Bx = fmaf(w.mxx, bx, fmaf(w.mxy, by, w.mxz * bz)), By = fmaf(w.myx, bx, fmaf(w.myy, by, w.myz * bz));
+    const float Cx = fmaf(w.mxx, cx, fmaf(w.mxy, cy, w.mxz * cz)), Cy = fmaf(w.myx, cx, fmaf(w.myy, cy, w.myz * cz));
+    // edge functions: explicit round-to-nearest mul/sub (never contracted to FMA) so that a shared edge gives
+    // exact negatives in the two triangles
     float U = __fsub_rn(__fmul_rn(Cx, By), __fmul_rn(Cy, Bx));
     float V = __fsub_rn(__fmul_rn(Ax, Cy), __fmul_rn(Ay, Cx));
     float W = __fsub_rn(__fmul_rn(Bx, Ay), __fmul_rn(By, Ax));
@@ -74,14 +87,14 @@ __device__ __forceinline__ bool woop_intersect(const WoopRay &w, float ox, float
         W = (float) (BxAy - ByAx);
     }
     if ((U < 0.f || V < 0.f || W < 0.f) && (U > 0.f || V > 0.f || W > 0.f)) return false;
-    float det = U + V + W;
+    const float det = U + V + W;
     if (det == 0.f) return false;
-    float Az = w.sz * Akz, Bz = w.sz * Bkz, Cz = w.sz * Ckz;
-    float T  = U * Az + V * Bz + W * Cz;
-    float sgn = det < 0.f ? -1.f : 1.f;
-    float Ts = T * sgn, absdet = fabsf(det);
+    const float Az = fmaf(w.mzx, ax, fmaf(w.mzy, ay, w.mzz * az)), Bz = fmaf(w.mzx, bx, fmaf(w.mzy, by, w.mzz * bz)),
+                Cz = fmaf(w.mzx, cx, fmaf(w.mzy, cy, w.mzz * cz));
+    const float T  = U * Az + V * Bz + W * Cz;
+    const float Ts = det < 0.f ? -T : T, absdet = fabsf(det);
     if (!(Ts > tnear * absdet) || !(Ts <= tfar * absdet)) return false;
-    float rcp = 1.f / det;
+    const float rcp = 1.f / det;
     t_out = T * rcp;
     u_out = V * rcp;
     v_out = W * rcp;
@@ -105,7 +118,7 @@ template <int J> __device__ __forceinline__ float qfloat(uint32_t q) {
 // Per-lane traversal state.  A lane owns one ray at a time; the warp refills idle lanes from the queue
 // (dynamic fetch, Aila & Laine 2009) instead of waiting for its slowest ray.
 struct Traversal {
-    float ox, oy, oz, dx, dy, dz, tmin, tmax;
+    float ox, oy, oz, tmin, tmax;
     float tfar0;   // the ray's own maxt
     float idx, idy, idz;
     uint32_t octinv;
@@ -118,12 +131,15 @@ struct Traversal {
 
     __device__ __forceinline__ void begin(float4 ro, float4 rd) {
         ox = ro.x; oy = ro.y; oz = ro.z; tmin = ro.w;
-        dx = rd.x; dy = rd.y; dz = rd.z; tmax = rd.w; tfar0 = rd.w;
-        idx = 1.f / nz(dx); idy = 1.f / nz(dy); idz = 1.f / nz(dz);
+        tmax = rd.w; tfar0 = rd.w;
+        // MUFU.RCP (1 ulp) instead of three IEEE divisions: the slab test already carries float rounding of the
+        // same size, and begin() runs with few lanes active (3.7 of 32 in the first profile), so every
+        // instruction here costs a whole issue slot
+        idx = rcp_approx(nz(rd.x)); idy = rcp_approx(nz(rd.y)); idz = rcp_approx(nz(rd.z));
         // signs of the clamped direction (-0 counts as negative)
         const uint32_t oct = (idx < 0.f ? 4u : 0u) | (idy < 0.f ? 2u : 0u) | (idz < 0.f ? 1u : 0u);
         octinv = 7u - oct;
-        wr = woop_setup(dx, dy, dz);
+        wr = woop_setup(rd.x, rd.y, rd.z);
         ngroup = make_uint2(0u, 0x80000000u); // root: "child slot 7 of a virtual parent at base 0"
         tgroup = make_uint2(0u, 0u);
         sp = 0;
