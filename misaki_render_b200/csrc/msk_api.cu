@@ -282,6 +282,8 @@ int msk_gpu_scene_create(MskCtx *ctx, const MskSceneDesc *d, MskScene **out) {
     static_assert(sizeof(msk_cie_d65_rows) == 95 * sizeof(float4), "table layout");
     if ((rc = upload(s, reinterpret_cast<const float4 *>(&msk_cie_d65_rows[0][0]), 95, &s->d.cie))) return bail(rc);
     s->d.nemitters = d->nemitters; s->d.environment = d->environment; s->d.nmeshes = d->nmeshes;
+    s->d.bsdf_type_mask = 0;
+    for (uint32_t i = 0; i < d->nmeshes; ++i) s->d.bsdf_type_mask |= 1u << d->bsdfs[d->meshes[i].bsdf].type;
     // constant.cpp:21-28 + bbox.h:109-112
     s->d.env_radius = 0.f;
     if (nverts) {

@@ -73,6 +73,7 @@ struct DScene {
     int32_t  environment;
     float    env_radius;
     uint32_t nmeshes;
+    uint32_t bsdf_type_mask; // bit t: some mesh uses a BSDF of MskBsdfType t
     DCamera  cam;
 };
 

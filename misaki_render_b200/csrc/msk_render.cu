@@ -24,7 +24,9 @@
 #include "msk_traverse.cuh"
 
 #include <algorithm>
+#include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <vector>
 
 namespace msk {
@@ -231,12 +233,26 @@ __global__ void __launch_bounds__(kSortThreads) k_sort(const __grid_constant__ D
 #ifndef MSK_SHADE_MIN_BLOCKS
 #define MSK_SHADE_MIN_BLOCKS 4 /* 128 registers (28 B of spills) instead of 152: 6.2 -> 5.4 ms on C2, the stage is latency-bound */
 #endif
-__global__ void __launch_bounds__(128, MSK_SHADE_MIN_BLOCKS) k_shade(const __grid_constant__ DScene sc, Pool pool, BatchParams bp, int cur) {
+// KEY < 0: one launch walks every key segment of the sorted index list (used for short queues, where launch
+// count matters more than code size).  KEY >= 0: the launch handles segment KEY only (0 = miss, 1 + BSDF type),
+// the BSDF switch folds to one case, and the kernel gets the register budget of that material alone -- the
+// all-materials kernel needs 152 registers and its 6197 static FFMAs thrash the instruction cache
+// (stall no_instruction = 3.8 per issue, profiles/r01c_ncu_k_shade.txt).
+#ifndef MSK_SHADE_DIFFUSE_BLOCKS
+#define MSK_SHADE_DIFFUSE_BLOCKS 4
+#endif
+constexpr int shade_min_blocks(int key) { return key < 0 ? MSK_SHADE_MIN_BLOCKS : (key == 0 ? 8 : (key == 1 ? MSK_SHADE_DIFFUSE_BLOCKS : 4)); }
+template <int KEY>
+__global__ void __launch_bounds__(128, shade_min_blocks(KEY)) k_shade(const __grid_constant__ DScene sc, Pool pool, BatchParams bp, int cur) {
     Ctrl *c = pool.ctrl;
     const int nxt = cur ^ 1;
+    constexpr int TYPE = KEY > 0 ? KEY - 1 : -1;
     uint32_t counts[kNumKeys], total = 0;
+    if (KEY >= 0) total = c->type_count[KEY];
+    else {
 #pragma unroll
-    for (int k = 0; k < kNumKeys; ++k) { counts[k] = c->type_count[k]; total += counts[k]; }
+        for (int k = 0; k < kNumKeys; ++k) { counts[k] = c->type_count[k]; total += counts[k]; }
+    }
     const uint32_t stride = gridDim.x * blockDim.x;
     const uint32_t rounds = (total + stride - 1) / stride;
     for (uint32_t it = 0; it < rounds; ++it) {
@@ -248,10 +264,12 @@ __global__ void __launch_bounds__(128, MSK_SHADE_MIN_BLOCKS) k_shade(const __gri
         uint4 nMISC;
         uint32_t path = 0;
         if (valid) {
-            uint32_t key = 0, j = idx;
+            uint32_t key = KEY >= 0 ? (uint32_t) KEY : 0u, j = idx;
+            if (KEY < 0) {
 #pragma unroll
-            for (int k = 0; k < kNumKeys - 1; ++k)
-                if (key == (uint32_t) k && j >= counts[k]) { j -= counts[k]; key = k + 1; }
+                for (int k = 0; k < kNumKeys - 1; ++k)
+                    if (key == (uint32_t) k && j >= counts[k]) { j -= counts[k]; key = k + 1; }
+            }
             const uint32_t q = pool.sorted[(size_t) key * pool.capacity + j];
             const float4 hit = pool.hit[q];
             const float4 rd  = reinterpret_cast<const float4 *>(pool.rays[cur] + q)[1];
@@ -269,14 +287,14 @@ __global__ void __launch_bounds__(128, MSK_SHADE_MIN_BLOCKS) k_shade(const __gri
             bool add_L = false, alive = true;
             const V3 rdir = v3(rd.x, rd.y, rd.z);
 
-            if (key == 0) { // miss: path.cpp:34-41 (depth 1) / :90-98,:103-108 (BSDF-sampled ray escaped)
+            if (KEY == 0 || (KEY < 0 && key == 0)) { // miss: path.cpp:34-41 (depth 1) / :90-98,:103-108 (BSDF-sampled ray escaped)
                 if (sc.environment >= 0) {
                     float4 le = spectrum_eval(sc, sc.emitters[sc.environment].radiance, wl);
                     if (depth == 1) { if (!bp.hide_emitters) { L = T * le; add_L = true; } }
                     else { L = T * le * mis_weight(prev_pdf, prev_delta ? 0.f : stale_pdf); add_L = true; }
                 }
                 alive = false;
-            } else {
+            } else if (KEY != 0) {
                 const uint32_t geom = pool.hit_geom[q];
                 const DMeshInfo mi = sc.meshes[geom];
                 const Surface sf = make_surface(sc, mi, __float_as_uint(hit.w), hit.y, hit.z);
@@ -306,14 +324,14 @@ __global__ void __launch_bounds__(128, MSK_SHADE_MIN_BLOCKS) k_shade(const __gri
                     const MskBsdf bsdf = sc.bsdfs[mi.bsdf];
                     float new_stale = 0.f;
                     const float tmin_spawn = (1.f + max_abs(sf.p)) * kRayEpsilon; // interaction.h:40-44, scene.cpp:91-93
-                    if (bsdf_is_smooth(bsdf.type)) { // path.cpp:56-67
+                    if (bsdf_is_smooth(TYPE >= 0 ? TYPE : bsdf.type)) { // path.cpp:56-67
                         float sx = next1d(rng), sy = next1d(rng);
                         NeeSample ns = sample_emitter_direct(sc, sf.p, wl, sx, sy);
                         new_stale = ns.stale_pdf;
                         if (ns.pdf != 0.f) {
                             V3 wo = to_local(sf.sh, ns.d);
                             float4 bval; float bpdf;
-                            bsdf_eval_pdf(sc, bsdf, wi, wo, wl, bval, bpdf);
+                            bsdf_eval_pdf<TYPE>(sc, bsdf, wi, wo, wl, bval, bpdf);
                             float w = mis_weight(ns.pdf, bpdf);
                             contrib = T * ns.value * bval * w;
                             if (!is_zero(contrib)) {
@@ -326,7 +344,7 @@ __global__ void __launch_bounds__(128, MSK_SHADE_MIN_BLOCKS) k_shade(const __gri
                         }
                     }
                     float s1 = next1d(rng), s2x = next1d(rng), s2y = next1d(rng); // path.cpp:71-72, left to right
-                    BsdfSample bs = bsdf_sample(sc, bsdf, wi, wl, s1, s2x, s2y);
+                    BsdfSample bs = bsdf_sample<TYPE>(sc, bsdf, wi, wl, s1, s2x, s2y);
                     if (is_zero(bs.weight)) alive = false; // failed sample: nothing downstream can contribute
                     else {
                         V3 wo = to_world(sf.sh, bs.wo);
@@ -462,6 +480,66 @@ __global__ void __launch_bounds__(kFilmTileX *kFilmTileY) k_film_gather(const __
     p[0] += aX; p[1] += aY; p[2] += aZ; p[3] += aW; p[4] += aW;
 }
 
+// The same gather with the records of the tile's neighbourhood staged in shared memory, for filters whose border
+// (ceil(radius - 0.5), rfilter.cpp:22) is at most kFilmMaxBorder pixels -- the reference's only filter, gaussian with
+// radius 2, has border 2.  The global-memory version above reads every record 25 times through L1/L2 (1.3 ms of
+// the 18 ms C2 step); here each record is read once per tile (+ halo) and the 33-entry weight table sits in shared
+// memory too.  Same neighbour order (s, ny, nx), same float arithmetic: the film is bit-identical to the
+// global-memory gather.
+constexpr int kFilmMaxBorder = 2;
+constexpr int kFilmHaloX = kFilmTileX + 2 * kFilmMaxBorder, kFilmHaloY = kFilmTileY + 2 * kFilmMaxBorder;
+__global__ void __launch_bounds__(kFilmTileX *kFilmTileY) k_film_gather_tiled(const __grid_constant__ DScene sc, Pool pool,
+                                                                               BatchParams bp, float *__restrict__ film,
+                                                                               uint32_t height) {
+    __shared__ float4 s_a[kFilmHaloY][kFilmHaloX]; // X, Y, Z, posx (block-relative, imageblock.cpp:86-98)
+    __shared__ float4 s_b[kFilmHaloY][kFilmHaloX]; // posy, (float) bx, (float) by, valid
+    __shared__ float s_tab[33];
+    const int W = (int) bp.width, H = (int) height;
+    const int x0 = blockIdx.x * kFilmTileX, y0 = blockIdx.y * kFilmTileY;
+    const int x = x0 + threadIdx.x, y = y0 + threadIdx.y;
+    const int r = (int) ceilf(sc.cam.filter_radius - 0.5f);
+    const float scale = sc.cam.filter_scale, radius = sc.cam.filter_radius;
+    const int tid = threadIdx.y * kFilmTileX + threadIdx.x;
+    if (tid < 33) s_tab[tid] = __ldg(sc.filter_table + tid);
+    const bool inside = x < W && y < H;
+    // this thread's neighbour window in halo coordinates (clipped to the film like the reference's lo/hi clamp)
+    const int hx_lo = max(x - r, 0) - (x0 - kFilmMaxBorder), hx_hi = min(x + r, W - 1) - (x0 - kFilmMaxBorder);
+    const int hy_lo = max(y - r, 0) - (y0 - kFilmMaxBorder), hy_hi = min(y + r, H - 1) - (y0 - kFilmMaxBorder);
+    float aX = 0.f, aY = 0.f, aZ = 0.f, aW = 0.f;
+    for (uint32_t s = 0; s < bp.ns; ++s) {
+        const size_t sbase = (size_t) s * bp.npix;
+        __syncthreads();
+        for (int e = tid; e < kFilmHaloX * kFilmHaloY; e += kFilmTileX * kFilmTileY) {
+            const int hy = e / kFilmHaloX, hx = e - hy * kFilmHaloX;
+            const int nx = x0 - kFilmMaxBorder + hx, ny = y0 - kFilmMaxBorder + hy;
+            if (nx >= 0 && nx < W && ny >= 0 && ny < H) {
+                const size_t i = sbase + (size_t) ny * W + nx;
+                const float4 rec = __ldcs(pool.rec + i);
+                const float py = __ldcs(pool.rec_py + i);
+                const int bx = (nx & ~(kBlockSize - 1)) - r, by = (ny & ~(kBlockSize - 1)) - r; // m_offset - m_border_size
+                s_a[hy][hx] = make_float4(rec.x, rec.y, rec.z, rec.w - 0.5f - (float) bx);
+                s_b[hy][hx] = make_float4(py - 0.5f - (float) by, (float) bx, (float) by, 1.f);
+            }
+        }
+        __syncthreads();
+        if (!inside) continue;
+        for (int hy = hy_lo; hy <= hy_hi; ++hy)
+            for (int hx = hx_lo; hx <= hx_hi; ++hx) {
+                const float4 a = s_a[hy][hx], b = s_b[hy][hx];
+                const float posx = a.w, posy = b.x;
+                const float xb = (float) x - b.y, yb = (float) y - b.z; // exact: small integers
+                if (xb < posx - radius || xb > posx + radius || yb < posy - radius || yb > posy + radius) continue;
+                const float wx = s_tab[min((int) fabsf((xb - posx) * scale), 32)];
+                const float wy = s_tab[min((int) fabsf((yb - posy) * scale), 32)];
+                const float w = wx * wy;
+                aX += w * a.x; aY += w * a.y; aZ += w * a.z; aW += w;
+            }
+    }
+    if (!inside) return;
+    float *p = film + ((size_t) y * W + x) * 5;
+    p[0] += aX; p[1] += aY; p[2] += aZ; p[3] += aW; p[4] += aW;
+}
+
 // ---------------------------------------------------------------------------------------
 // Stand-alone batch queries (msk_gpu_intersect / msk_gpu_occluded)
 template <bool STATS>
@@ -522,7 +600,15 @@ struct Renderer::Impl {
     uint32_t capacity = 0;
     uint32_t *query_cursor = nullptr;
     Ctrl *h_ctrl = nullptr; // pinned
+    Ctrl *h_poll[2] = { nullptr, nullptr }; // pinned: queue-length polls of unbounded-depth jobs, double-buffered
+    cudaEvent_t poll_ev[2]{};
     cudaEvent_t ev[8]{};
+    // Tuning knobs (environment, read once in init(); defaults are the measured best on C2, tools/ab_knobs.sh)
+    uint32_t batch_paths = 32u << 20; // MSK_BATCH_PATHS: paths per wavefront batch (C2: 8 Mi -> 16 Mi = 804 -> 919 Mpaths/s, the per-batch tail of short bounces is paid once)
+    int spec_shade = 1;               // MSK_SPEC_SHADE: one k_shade launch per material key present in the scene
+    uint32_t spec_min = 1u << 18;     // MSK_SPEC_MIN: ... while the queue may hold at least this many vertices
+    int shadow_static_bounces = 0;    // MSK_SHADOW_STATIC_BOUNCES: bounces whose shadow queue counts as coherent
+    int async_poll = 1;               // MSK_ASYNC_POLL: poll the queue length one bounce late, without draining the stream
     std::vector<cudaEvent_t> timer_events; // MSK_RENDER_STAGE_TIMERS
     std::vector<int> timer_stage;
     int persistent_blocks = 0, sm_count = 0;
@@ -540,6 +626,8 @@ void Renderer::release() {
     impl_->capacity = 0;
     cudaFree(impl_->query_cursor); impl_->query_cursor = nullptr;
     if (impl_->h_ctrl) { cudaFreeHost(impl_->h_ctrl); impl_->h_ctrl = nullptr; }
+    for (auto &h : impl_->h_poll) if (h) { cudaFreeHost(h); h = nullptr; }
+    for (auto &e : impl_->poll_ev) if (e) { cudaEventDestroy(e); e = nullptr; }
     for (auto &e : impl_->ev) if (e) { cudaEventDestroy(e); e = nullptr; }
     for (auto &e : impl_->timer_events) cudaEventDestroy(e);
     impl_->timer_events.clear();
@@ -550,7 +638,18 @@ int Renderer::init(int sm_count) {
     impl_->persistent_blocks = sm_count * 8; // 128-thread CTAs, 8 resident per SM
     MSK_CUDA_CHECK(dalloc(&impl_->query_cursor, 1));
     MSK_CUDA_CHECK(cudaMallocHost((void **) &impl_->h_ctrl, sizeof(Ctrl)));
+    for (auto &h : impl_->h_poll) MSK_CUDA_CHECK(cudaMallocHost((void **) &h, sizeof(Ctrl)));
+    for (auto &e : impl_->poll_ev) MSK_CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     for (auto &e : impl_->ev) MSK_CUDA_CHECK(cudaEventCreate(&e));
+    auto env_u = [](const char *name, long long dflt) -> long long {
+        const char *v = getenv(name);
+        return (v && *v) ? atoll(v) : dflt;
+    };
+    impl_->batch_paths = (uint32_t) std::max<long long>(1, env_u("MSK_BATCH_PATHS", impl_->batch_paths));
+    impl_->spec_shade = (int) env_u("MSK_SPEC_SHADE", impl_->spec_shade);
+    impl_->spec_min = (uint32_t) env_u("MSK_SPEC_MIN", impl_->spec_min);
+    impl_->shadow_static_bounces = (int) env_u("MSK_SHADOW_STATIC_BOUNCES", impl_->shadow_static_bounces);
+    impl_->async_poll = (int) env_u("MSK_ASYNC_POLL", impl_->async_poll);
     return MSK_OK;
 }
 
@@ -585,7 +684,8 @@ int Renderer::render(cudaStream_t stream, const DScene &sc, const MskRenderDesc 
     if (rd.rr_depth <= 0) return fail(MSK_ERR_ARG, "\"rr_depth\" must be set to a value greater than zero!");
     if (rd.max_depth < 0 && rd.max_depth != -1) return fail(MSK_ERR_ARG, "\"max_depth\" must be set to -1 (infinite) or a value >= 0");
     const uint32_t npix = (uint32_t) npix64;
-    uint32_t target = rd.paths_per_batch ? rd.paths_per_batch : (8u << 20);
+    const uint32_t im_batch_paths = impl_->batch_paths;
+    uint32_t target = rd.paths_per_batch ? rd.paths_per_batch : im_batch_paths;
     uint32_t per_batch = std::max(1u, target / npix);
     const uint32_t nsamples = rd.sample_end - rd.sample_begin;
     per_batch = std::min(per_batch, std::max(nsamples, 1u));
@@ -638,29 +738,57 @@ int Renderer::render(cudaStream_t stream, const DScene &sc, const MskRenderDesc 
         // a path reaches vertex `depth` only while depth <= max_depth, and the vertex at max_depth still
         // needs its shade pass (emission), so a bounded job runs exactly max_depth iterations
         const uint32_t bound = rd.max_depth > 0 ? (uint32_t) rd.max_depth : (rd.max_depth == 0 ? 0u : 0xffffffffu);
+        uint32_t n_est = n;       // upper bound of the current queue length known to the host (queues only shrink)
+        bool poll_pending = false; // a poll of the previous bounce is in flight (async_poll)
         while (bounce < bound) {
             if (tstats) MSK_STAGE(ST_INTERSECT, (k_intersect<true><<<pb, 128, 0, stream>>>(sc, pool, cur, bounce == 0)));
             else MSK_STAGE(ST_INTERSECT, (k_intersect<false><<<pb, 128, 0, stream>>>(sc, pool, cur, bounce == 0)));
             if (!MSK_SORT_IN_COMMIT) MSK_STAGE(ST_SORT, (k_sort<<<im.sm_count * 4, kSortThreads, 0, stream>>>(sc, pool, cur)));
-            MSK_STAGE(ST_SHADE, (k_shade<<<pb, 128, 0, stream>>>(sc, pool, bp, cur)));
-            if (tstats) MSK_STAGE(ST_SHADOW, (k_shadow<true><<<pb, 128, 0, stream>>>(sc, pool, 0)));
-            else MSK_STAGE(ST_SHADOW, (k_shadow<false><<<pb, 128, 0, stream>>>(sc, pool, 0)));
+            if (im.spec_shade && n_est >= im.spec_min) {
+                const uint32_t keys = 1u | (sc.bsdf_type_mask << 1);
+#define MSK_SHADE_KEY(K) if (keys & (1u << K)) MSK_STAGE(ST_SHADE, (k_shade<K><<<pb, 128, 0, stream>>>(sc, pool, bp, cur)))
+                MSK_SHADE_KEY(0); MSK_SHADE_KEY(1); MSK_SHADE_KEY(2); MSK_SHADE_KEY(3); MSK_SHADE_KEY(4); MSK_SHADE_KEY(5);
+#undef MSK_SHADE_KEY
+                static_assert(kNumKeys == 6, "one specialised k_shade launch per key");
+            } else {
+                MSK_STAGE(ST_SHADE, (k_shade<-1><<<pb, 128, 0, stream>>>(sc, pool, bp, cur)));
+            }
+            const int sh_coherent = (int) bounce < im.shadow_static_bounces;
+            if (tstats) MSK_STAGE(ST_SHADOW, (k_shadow<true><<<pb, 128, 0, stream>>>(sc, pool, sh_coherent)));
+            else MSK_STAGE(ST_SHADOW, (k_shadow<false><<<pb, 128, 0, stream>>>(sc, pool, sh_coherent)));
             k_end_bounce<<<1, 1, 0, stream>>>(pool.ctrl, cur);
             launches++;
             cur ^= 1;
             bounce++;
-            // unbounded paths (Russian roulette only): poll the queue length once it is likely short
+            // unbounded paths (Russian roulette only): poll the queue length once it is likely short.  The poll of
+            // bounce b is read after bounce b+1 has been enqueued, so the stream never drains; the price is one
+            // bounce over an empty queue at the very end.
             if (bound == 0xffffffffu && bounce >= 4) {
-                MSK_CUDA_CHECK(cudaMemcpyAsync(im.h_ctrl, pool.ctrl, sizeof(Ctrl), cudaMemcpyDeviceToHost, stream));
-                MSK_CUDA_CHECK(cudaStreamSynchronize(stream));
-                if (im.h_ctrl->n_rays[cur] == 0) break;
+                const int slot = (int) (bounce & 1u);
+                MSK_CUDA_CHECK(cudaMemcpyAsync(im.h_poll[slot], pool.ctrl, sizeof(Ctrl), cudaMemcpyDeviceToHost, stream));
+                MSK_CUDA_CHECK(cudaEventRecord(im.poll_ev[slot], stream));
+                if (im.async_poll) {
+                    if (poll_pending) {
+                        MSK_CUDA_CHECK(cudaEventSynchronize(im.poll_ev[slot ^ 1]));
+                        n_est = im.h_poll[slot ^ 1]->n_rays[cur ^ 1]; // queue the bounce just enqueued ran over
+                        if (n_est == 0) break;
+                    }
+                    poll_pending = true;
+                } else {
+                    MSK_CUDA_CHECK(cudaEventSynchronize(im.poll_ev[slot]));
+                    n_est = im.h_poll[slot]->n_rays[cur];
+                    if (n_est == 0) break;
+                }
                 if (bounce > 100000) return fail(MSK_ERR_CUDA, "path queue did not drain");
             }
         }
         max_bounces = std::max(max_bounces, bounce);
         MSK_STAGE(ST_FILM, (k_film_records<<<(n + 255) / 256, 256, 0, stream>>>(sc, pool, bp)));
         dim3 fg((W + kFilmTileX - 1) / kFilmTileX, (H + kFilmTileY - 1) / kFilmTileY), fb(kFilmTileX, kFilmTileY);
-        MSK_STAGE(ST_FILM, (k_film_gather<<<fg, fb, 0, stream>>>(sc, pool, bp, d_film, H)));
+        if ((int) std::ceil(sc.cam.filter_radius - 0.5f) <= kFilmMaxBorder)
+            MSK_STAGE(ST_FILM, (k_film_gather_tiled<<<fg, fb, 0, stream>>>(sc, pool, bp, d_film, H)));
+        else
+            MSK_STAGE(ST_FILM, (k_film_gather<<<fg, fb, 0, stream>>>(sc, pool, bp, d_film, H)));
         batches++;
     }
 #undef MSK_STAGE

@@ -258,11 +258,14 @@ __device__ __forceinline__ bool bsdf_is_smooth(int type) { // has_flag(flags, Sm
 struct BsdfSample { V3 wo; float pdf, eta; uint32_t type; float4 weight; };
 
 // sample(): wi is the local incident direction; returns weight = f*cos/pdf
+// TYPE >= 0: the BSDF type is known at compile time (k_shade specialised per material key) and the switch folds
+// to one case; TYPE < 0: dispatch on b.type.
+template <int TYPE>
 __device__ __forceinline__ BsdfSample bsdf_sample_1(const DScene &sc, const MskBsdf &b, V3 wi, float4 wl, float s1, float s2x, float s2y) {
     BsdfSample bs;
     bs.wo = v3(0, 0, 0); bs.pdf = 0.f; bs.eta = 1.f; bs.type = 0; bs.weight = f4(0.f);
     const float ci = wi.z;
-    switch (b.type) {
+    switch (TYPE >= 0 ? TYPE : b.type) {
         case MSK_BSDF_DIFFUSE: { // diffuse.cpp:19-32
             if (ci <= 0.f) return bs;
             bs.wo = square_to_cosine_hemisphere(s2x, s2y);
@@ -331,10 +334,11 @@ __device__ __forceinline__ BsdfSample bsdf_sample_1(const DScene &sc, const MskB
 }
 
 // eval() and pdf() of the NEE direction in one pass (path.cpp:61-62)
+template <int TYPE>
 __device__ __forceinline__ void bsdf_eval_pdf_1(const DScene &sc, const MskBsdf &b, V3 wi, V3 wo, float4 wl, float4 &val, float &pdf) {
     val = f4(0.f); pdf = 0.f;
     const float ci = wi.z, co = wo.z;
-    switch (b.type) {
+    switch (TYPE >= 0 ? TYPE : b.type) {
         case MSK_BSDF_DIFFUSE: // diffuse.cpp:34-57
             if (ci > 0.f && co > 0.f) { val = spectrum_eval(sc, b.reflectance, wl) * kInvPi * co; pdf = kInvPi * co; }
             return;
@@ -384,25 +388,27 @@ __device__ __forceinline__ void bsdf_eval_pdf_1(const DScene &sc, const MskBsdf 
 }
 
 // twosided.cpp:38-101 (same BRDF on both sides)
+// (one call site of the inner function: flip wi, sample, flip wo back)
+template <int TYPE>
 __device__ __forceinline__ BsdfSample bsdf_sample(const DScene &sc, const MskBsdf &b, V3 wi, float4 wl, float s1, float s2x, float s2y) {
-    if (!b.twosided) return bsdf_sample_1(sc, b, wi, wl, s1, s2x, s2y);
-    if (wi.z > 0.f) return bsdf_sample_1(sc, b, wi, wl, s1, s2x, s2y);
-    if (wi.z < 0.f) {
-        wi.z = -wi.z;
-        BsdfSample bs = bsdf_sample_1(sc, b, wi, wl, s1, s2x, s2y);
-        bs.wo.z = -bs.wo.z;
+    const bool two = b.twosided != 0, flip = two && wi.z < 0.f;
+    if (two && wi.z == 0.f) {
+        BsdfSample bs;
+        bs.wo = v3(0, 0, 0); bs.pdf = 0.f; bs.eta = 1.f; bs.type = 0; bs.weight = f4(0.f);
         return bs;
     }
-    BsdfSample bs;
-    bs.wo = v3(0, 0, 0); bs.pdf = 0.f; bs.eta = 1.f; bs.type = 0; bs.weight = f4(0.f);
+    if (flip) wi.z = -wi.z;
+    BsdfSample bs = bsdf_sample_1<TYPE>(sc, b, wi, wl, s1, s2x, s2y);
+    if (flip) bs.wo.z = -bs.wo.z;
     return bs;
 }
+template <int TYPE>
 __device__ __forceinline__ void bsdf_eval_pdf(const DScene &sc, const MskBsdf &b, V3 wi, V3 wo, float4 wl, float4 &val, float &pdf) {
     if (b.twosided) {
         if (wi.z == 0.f) { val = f4(0.f); pdf = 0.f; return; }
         if (wi.z < 0.f) { wi.z = -wi.z; wo.z = -wo.z; }
     }
-    bsdf_eval_pdf_1(sc, b, wi, wo, wl, val, pdf);
+    bsdf_eval_pdf_1<TYPE>(sc, b, wi, wo, wl, val, pdf);
 }
 
 __device__ __forceinline__ float mis_weight(float pdf_a, float pdf_b) { // path.cpp:127-131

@@ -18,6 +18,9 @@ constexpr int kStackSize = 64; // node groups + postponed triangle groups: at mo
 #ifndef MSK_FETCH_THRESHOLD
 #define MSK_FETCH_THRESHOLD 20
 #endif
+#ifndef MSK_STATIC_MIN_GROUP
+#define MSK_STATIC_MIN_GROUP 4 /* 32 disables the adaptive group size of short static queues */
+#endif
 #ifndef MSK_TRI_THRESHOLD
 #define MSK_TRI_THRESHOLD 12
 #endif
@@ -286,13 +289,25 @@ __device__ __forceinline__ void trace_queue_static(const float4 *__restrict__ no
                                                    uint32_t *cursor, IO &io, uint2 *stack) {
     Traversal s;
     const uint32_t lane = threadIdx.x & 31u;
+    // A queue shorter than one ray per lane of the grid is latency-bound: the launch lasts as long as its slowest
+    // warp, and a warp of 32 divergent rays serialises their node and triangle steps (the tail bounces of C2 took
+    // a flat ~90 us each whatever their length, profiles/r01d_launches_c2.csv).  Spread such a queue over all
+    // warps instead: each warp takes `group` consecutive rays (a power of two, >= MSK_STATIC_MIN_GROUP).
+    uint32_t group = 32u;
+#if MSK_STATIC_MIN_GROUP < 32
+    {
+        const uint32_t nwarps = gridDim.x * (blockDim.x / 32u);
+        const uint32_t per = (n + nwarps - 1u) / nwarps;
+        if (per < 32u) { group = MSK_STATIC_MIN_GROUP; while (group < per) group <<= 1; }
+    }
+#endif
     for (;;) {
         uint32_t base = 0;
-        if (lane == 0) base = atomicAdd(cursor, 32u);
+        if (lane == 0) base = atomicAdd(cursor, group);
         base = __shfl_sync(0xffffffffu, base, 0);
         if (base >= n) break;
         const uint32_t q = base + lane;
-        const bool valid = q < n;
+        const bool valid = lane < group && q < n;
         if (valid) {
             float4 ro, rd;
             io.load(q, ro, rd);
