@@ -8,6 +8,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 #include <new>
@@ -300,7 +301,17 @@ int msk_gpu_scene_create(MskCtx *ctx, const MskSceneDesc *d, MskScene **out) {
     s->d.cam.filter_radius = d->camera.filter_radius;
     s->d.cam.filter_scale = 32.f / d->camera.filter_radius; // rfilter.cpp:21
 
-    if ((rc = bvh_build(ctx->stream, d_verts, d_indices, infos, &s->bvh))) return bail(rc);
+    // MSK_BVH_BUILDER=ploc selects the SAH-driven clustering builder; default LBVH, which measured better on the
+    // uniformly tessellated BASELINE meshes (C5 primary rays: 15.3 vs 18.5 wide nodes per ray; fuller 8-wide nodes
+    // after the collapse: 1.47 M vs 1.62 M), although PLOC lowers the binary SAH cost (66.7 -> 62.4).  A PLOC tree too
+    // deep for the traversal stack (degenerate input) falls back to the balanced LBVH.
+    const char *bsel = getenv("MSK_BVH_BUILDER");
+    int builder = (bsel && !strcmp(bsel, "ploc")) ? MSK_BVH_PLOC : MSK_BVH_LBVH;
+    if ((rc = bvh_build(ctx->stream, d_verts, d_indices, infos, &s->bvh, builder))) return bail(rc);
+    if (builder == MSK_BVH_PLOC && 2 * s->bvh.depth + 2 > (uint32_t) 64) {
+        bvh_free(&s->bvh);
+        if ((rc = bvh_build(ctx->stream, d_verts, d_indices, infos, &s->bvh, MSK_BVH_LBVH))) return bail(rc);
+    }
     if (2 * s->bvh.depth + 2 > (uint32_t) 64) // node groups + postponed triangle groups, msk_traverse.cuh kStackSize
         return bail(fail(MSK_ERR_UNSUPPORTED, "BVH depth %u exceeds the traversal stack", s->bvh.depth));
     s->d.nodes = s->bvh.nodes; s->d.tris = s->bvh.tris;

@@ -5,8 +5,12 @@
 //   1. k_tri_setup   gather each triangle's three positions (+prim, geom ids), reduce centroid bounds
 //   2. k_morton      63-bit Morton code of the centroid
 //   3. radix sort    (cub::DeviceRadixSort, build-time plumbing)
-//   4. k_karras      binary radix tree over the sorted codes (Karras 2012)
-//   5. k_refit       bottom-up AABBs with one atomic flag per internal node
+//   4. binary tree over the Morton-ordered triangles, one of
+//        PLOC (MSK_BVH_BUILDER=ploc)  parallel locally-ordered clustering (Meister & Bittner 2018): every cluster finds the
+//                        neighbour within +-kPlocRadius positions whose merged box has the smallest area, mutual
+//                        pairs merge, the cluster list is compacted; repeat until one cluster is left.  The tree
+//                        is SAH-driven (Embree's builder is an SAH builder too) instead of bit-prefix-driven.
+//        LBVH (default)  k_karras (Karras 2012) + k_refit
 //   6. k_collapse    level-synchronous top-down collapse of the binary tree into 8-wide nodes
 //                    with 8-bit quantised child boxes (80 B per node, five 128-bit loads),
 //                    children placed in octant-ordered slots (Ylitie, Karras, Laine 2017)
@@ -113,8 +117,8 @@ __global__ void k_morton(const float4 *__restrict__ gathered, uint32_t n, const 
 
 // ---- binary radix tree (Karras 2012).  Internal nodes 0..n-2, leaves n-1..2n-2. ----
 struct Bvh2 {
-    uint32_t *left, *right, *parent; // per internal node (parent: per node, 2n-1)
-    uint32_t *first, *last;          // per internal node: covered range of sorted leaves
+    uint32_t *left, *right, *parent; // per internal node (parent: per node, 2n-1; LBVH only)
+    uint32_t *count;                 // per internal node: triangles below it
     float4 *lo, *hi;                 // per node (2n-1)
     uint32_t *flags;                 // per internal node, refit arrival counter
 };
@@ -149,7 +153,7 @@ __global__ void k_karras(const uint64_t *__restrict__ keys, int n, Bvh2 t) {
     uint32_t rc = (hi == gamma + 1) ? (uint32_t) (n - 1 + gamma + 1) : (uint32_t) (gamma + 1);
     t.left[i] = lc; t.right[i] = rc;
     t.parent[lc] = i; t.parent[rc] = i;
-    t.first[i] = lo; t.last[i] = hi;
+    t.count[i] = (uint32_t) (hi - lo + 1);
     if (i == 0) t.parent[0] = 0xffffffffu;
 }
 
@@ -183,10 +187,91 @@ __device__ __forceinline__ float half_area(float4 lo, float4 hi) {
 }
 
 __device__ __forceinline__ uint32_t node_count(const Bvh2 &t, int n, uint32_t node) {
-    return node >= (uint32_t) (n - 1) ? 1u : t.last[node] - t.first[node] + 1u;
+    return node >= (uint32_t) (n - 1) ? 1u : t.count[node];
 }
-__device__ __forceinline__ uint32_t node_first(const Bvh2 &t, int n, uint32_t node) {
-    return node >= (uint32_t) (n - 1) ? node - (uint32_t) (n - 1) : t.first[node];
+
+// ---- PLOC (Meister & Bittner, "Parallel Locally-Ordered Clustering for Bounding Volume Hierarchy Construction",
+// 2018).  Clusters live in Morton order in compact arrays (node id + box, ping-ponged by the compaction). ----
+constexpr int kPlocRadius = 16;
+
+__global__ void k_ploc_init(const float4 *__restrict__ gathered, const uint32_t *__restrict__ sorted, int n, Bvh2 t,
+                            uint32_t *__restrict__ cid, float4 *__restrict__ clo, float4 *__restrict__ chi) {
+    int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    uint32_t tri = sorted[j];
+    float4 a = gathered[3 * (size_t) tri], b = gathered[3 * (size_t) tri + 1], c = gathered[3 * (size_t) tri + 2];
+    float4 lo = make_float4(fminf(a.x, fminf(b.x, c.x)), fminf(a.y, fminf(b.y, c.y)), fminf(a.z, fminf(b.z, c.z)), 0.f);
+    float4 hi = make_float4(fmaxf(a.x, fmaxf(b.x, c.x)), fmaxf(a.y, fmaxf(b.y, c.y)), fmaxf(a.z, fmaxf(b.z, c.z)), 0.f);
+    uint32_t node = (uint32_t) (n - 1 + j);
+    t.lo[node] = lo; t.hi[node] = hi;
+    cid[j] = node; clo[j] = lo; chi[j] = hi;
+}
+
+// nearest neighbour of every cluster within +-kPlocRadius positions: smallest merged half-area, ties to the lower
+// position (so that the globally best pair is always mutual and every round merges at least one pair)
+__global__ void __launch_bounds__(kThreads) k_ploc_nn(uint32_t c, const float4 *__restrict__ clo, const float4 *__restrict__ chi,
+                                                       uint32_t *__restrict__ nn) {
+    __shared__ float s_lo[3][kThreads + 2 * kPlocRadius], s_hi[3][kThreads + 2 * kPlocRadius];
+    const long long base = (long long) blockIdx.x * kThreads - kPlocRadius;
+    for (int e = threadIdx.x; e < kThreads + 2 * kPlocRadius; e += kThreads) {
+        long long g = base + e;
+        if (g >= 0 && g < (long long) c) {
+            float4 l = clo[g], h = chi[g];
+            s_lo[0][e] = l.x; s_lo[1][e] = l.y; s_lo[2][e] = l.z; s_hi[0][e] = h.x; s_hi[1][e] = h.y; s_hi[2][e] = h.z;
+        }
+    }
+    __syncthreads();
+    const uint32_t i = blockIdx.x * kThreads + threadIdx.x;
+    if (i >= c) return;
+    const int me = threadIdx.x + kPlocRadius;
+    const float lx = s_lo[0][me], ly = s_lo[1][me], lz = s_lo[2][me], hx = s_hi[0][me], hy = s_hi[1][me], hz = s_hi[2][me];
+    float best = FLT_MAX;
+    uint32_t bj = 0xffffffffu;
+    for (int d = -kPlocRadius; d <= kPlocRadius; ++d) {
+        if (d == 0) continue;
+        const long long g = (long long) i + d;
+        if (g < 0 || g >= (long long) c) continue;
+        const int e = me + d;
+        const float dx = fmaxf(hx, s_hi[0][e]) - fminf(lx, s_lo[0][e]), dy = fmaxf(hy, s_hi[1][e]) - fminf(ly, s_lo[1][e]),
+                    dz = fmaxf(hz, s_hi[2][e]) - fminf(lz, s_lo[2][e]);
+        const float a = dx * dy + dy * dz + dz * dx;
+        if (a < best) { best = a; bj = (uint32_t) g; } // ascending g: the first minimum is the lowest position
+    }
+    nn[i] = bj;
+}
+
+// mutual nearest neighbours merge into a new binary node at the lower position; ids descend from n-2 so that the
+// last merge (the root) is node 0
+__global__ void k_ploc_merge(uint32_t c, const uint32_t *__restrict__ nn, uint32_t *__restrict__ cid, float4 *__restrict__ clo,
+                             float4 *__restrict__ chi, uint32_t *__restrict__ flags, Bvh2 t, int n, uint32_t *counter) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= c) return;
+    const uint32_t j = nn[i];
+    uint32_t keep = 1u;
+    if (j != 0xffffffffu && nn[j] == i) {
+        if (i < j) {
+            const uint32_t node = (uint32_t) (n - 2) - atomicAdd(counter, 1u);
+            const uint32_t l = cid[i], r = cid[j];
+            const float4 llo = clo[i], lhi = chi[i], rlo = clo[j], rhi = chi[j];
+            const float4 lo = make_float4(fminf(llo.x, rlo.x), fminf(llo.y, rlo.y), fminf(llo.z, rlo.z), 0.f);
+            const float4 hi = make_float4(fmaxf(lhi.x, rhi.x), fmaxf(lhi.y, rhi.y), fmaxf(lhi.z, rhi.z), 0.f);
+            t.left[node] = l; t.right[node] = r; t.lo[node] = lo; t.hi[node] = hi;
+            t.count[node] = node_count(t, n, l) + node_count(t, n, r);
+            cid[i] = node; clo[i] = lo; chi[i] = hi;
+        } else keep = 0u;
+    }
+    flags[i] = keep;
+}
+
+__global__ void k_ploc_compact(uint32_t c, const uint32_t *__restrict__ flags, const uint32_t *__restrict__ pos,
+                               const uint32_t *__restrict__ cid, const float4 *__restrict__ clo, const float4 *__restrict__ chi,
+                               uint32_t *__restrict__ cid2, float4 *__restrict__ clo2, float4 *__restrict__ chi2,
+                               uint32_t *__restrict__ count_out) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= c) return;
+    const uint32_t f = flags[i], p = pos[i];
+    if (f) { cid2[p] = cid[i]; clo2[p] = clo[i]; chi2[p] = chi[i]; }
+    if (i == c - 1) *count_out = p + f;
 }
 
 // exponent byte e such that 2^(e-127) >= extent / 255
@@ -285,13 +370,21 @@ __global__ void k_collapse(const WorkItem *__restrict__ in, uint32_t nin, WorkIt
             inner_rank++;
         } else {
             m = (((1u << cnt) - 1u) << 5) | tri_off;
-            uint32_t f = node_first(t, n, node);
-            for (uint32_t k = 0; k < cnt; ++k) {
-                uint32_t tri = sorted[f + k];
-                size_t dst = 3 * (size_t) (tri_base + tri_off + k);
-                tris[dst + 0] = gathered[3 * (size_t) tri + 0];
-                tris[dst + 1] = gathered[3 * (size_t) tri + 1];
-                tris[dst + 2] = gathered[3 * (size_t) tri + 2];
+            // the <= kMaxLeafTris triangles of the subtree, left to right
+            uint32_t todo[kMaxLeafTris + 1];
+            int sp = 0;
+            uint32_t k = 0;
+            todo[sp++] = node;
+            while (sp) {
+                const uint32_t u = todo[--sp];
+                if (u >= (uint32_t) (n - 1)) {
+                    const uint32_t tri = sorted[u - (uint32_t) (n - 1)];
+                    const size_t dst = 3 * (size_t) (tri_base + tri_off + k);
+                    tris[dst + 0] = gathered[3 * (size_t) tri + 0];
+                    tris[dst + 1] = gathered[3 * (size_t) tri + 1];
+                    tris[dst + 2] = gathered[3 * (size_t) tri + 2];
+                    ++k;
+                } else { todo[sp++] = t.right[u]; todo[sp++] = t.left[u]; }
             }
             tri_off += cnt;
         }
@@ -338,8 +431,9 @@ template <typename T> cudaError_t dalloc(T **p, size_t n) { return cudaMalloc((v
 } // namespace
 
 int bvh_build(cudaStream_t stream, const float4 *d_verts, const uint32_t *d_indices, const std::vector<DMeshInfo> &meshes,
-              BvhResult *out) {
+              BvhResult *out, int builder) {
     *out = BvhResult{};
+    out->builder = builder;
     size_t n = 0;
     for (auto &m : meshes) n += m.ntris;
     if (n > 0x7ffffff0ull) return fail(MSK_ERR_UNSUPPORTED, "too many triangles (%zu)", n);
@@ -370,11 +464,16 @@ int bvh_build(cudaStream_t stream, const float4 *d_verts, const uint32_t *d_indi
     Bvh2 t{};
     WorkItem *qa = nullptr, *qb = nullptr;
     float *sah = nullptr;
+    uint32_t *p_cid[2] = { nullptr, nullptr }, *p_nn = nullptr, *p_flags = nullptr, *p_pos = nullptr, *p_counters = nullptr;
+    float4 *p_lo[2] = { nullptr, nullptr }, *p_hi[2] = { nullptr, nullptr };
+    void *p_tmp = nullptr;
     int rc = MSK_OK;
     auto cleanup = [&]() {
         cudaFree(gathered); cudaFree(keys); cudaFree(keys_sorted); cudaFree(vals); cudaFree(sorted); cudaFree(st);
-        cudaFree(cub_tmp); cudaFree(t.left); cudaFree(t.right); cudaFree(t.parent); cudaFree(t.first); cudaFree(t.last);
+        cudaFree(cub_tmp); cudaFree(t.left); cudaFree(t.right); cudaFree(t.parent); cudaFree(t.count);
         cudaFree(t.lo); cudaFree(t.hi); cudaFree(t.flags); cudaFree(qa); cudaFree(qb); cudaFree(sah);
+        for (int k = 0; k < 2; ++k) { cudaFree(p_cid[k]); cudaFree(p_lo[k]); cudaFree(p_hi[k]); }
+        cudaFree(p_nn); cudaFree(p_flags); cudaFree(p_pos); cudaFree(p_tmp); cudaFree(p_counters);
         cudaEventDestroy(e0); cudaEventDestroy(e1);
     };
 #define BVH_CHECK(expr)                                                          \
@@ -404,13 +503,41 @@ int bvh_build(cudaStream_t stream, const float4 *d_verts, const uint32_t *d_indi
 
     size_t nint = n > 1 ? n - 1 : 1;
     BVH_CHECK(dalloc(&t.left, nint)); BVH_CHECK(dalloc(&t.right, nint));
-    BVH_CHECK(dalloc(&t.first, nint)); BVH_CHECK(dalloc(&t.last, nint));
-    BVH_CHECK(dalloc(&t.flags, nint));
-    BVH_CHECK(dalloc(&t.parent, 2 * n));
+    BVH_CHECK(dalloc(&t.count, nint));
     BVH_CHECK(dalloc(&t.lo, 2 * n)); BVH_CHECK(dalloc(&t.hi, 2 * n));
-    BVH_CHECK(cudaMemsetAsync(t.flags, 0, nint * sizeof(uint32_t), stream));
-    if (n > 1) k_karras<<<blocks_for(n - 1), kThreads, 0, stream>>>(keys_sorted, (int) n, t);
-    k_refit<<<blocks_for(n), kThreads, 0, stream>>>(gathered, sorted, (int) n, t);
+    if (builder == MSK_BVH_PLOC) {
+        for (int k = 0; k < 2; ++k) { BVH_CHECK(dalloc(&p_cid[k], n)); BVH_CHECK(dalloc(&p_lo[k], n)); BVH_CHECK(dalloc(&p_hi[k], n)); }
+        BVH_CHECK(dalloc(&p_nn, n)); BVH_CHECK(dalloc(&p_flags, n)); BVH_CHECK(dalloc(&p_pos, n));
+        BVH_CHECK(dalloc(&p_counters, 2));
+        BVH_CHECK(cudaMemsetAsync(p_counters, 0, 2 * sizeof(uint32_t), stream));
+        size_t scan_bytes = 0;
+        BVH_CHECK(cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, p_flags, p_pos, (int) n, stream));
+        BVH_CHECK(cudaMalloc(&p_tmp, std::max<size_t>(scan_bytes, 16)));
+        k_ploc_init<<<blocks_for(n), kThreads, 0, stream>>>(gathered, sorted, (int) n, t, p_cid[0], p_lo[0], p_hi[0]);
+        uint32_t c = (uint32_t) n, rounds = 0;
+        int cur = 0;
+        while (c > 1) {
+            k_ploc_nn<<<blocks_for(c), kThreads, 0, stream>>>(c, p_lo[cur], p_hi[cur], p_nn);
+            k_ploc_merge<<<blocks_for(c), kThreads, 0, stream>>>(c, p_nn, p_cid[cur], p_lo[cur], p_hi[cur], p_flags, t, (int) n,
+                                                                 p_counters);
+            BVH_CHECK(cub::DeviceScan::ExclusiveSum(p_tmp, scan_bytes, p_flags, p_pos, (int) c, stream));
+            k_ploc_compact<<<blocks_for(c), kThreads, 0, stream>>>(c, p_flags, p_pos, p_cid[cur], p_lo[cur], p_hi[cur], p_cid[cur ^ 1],
+                                                                   p_lo[cur ^ 1], p_hi[cur ^ 1], p_counters + 1);
+            uint32_t c2 = 0;
+            BVH_CHECK(cudaMemcpyAsync(&c2, p_counters + 1, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+            BVH_CHECK(cudaStreamSynchronize(stream));
+            if (c2 == 0 || c2 >= c) { cleanup(); cudaFree(out->nodes); cudaFree(out->tris); *out = BvhResult{};
+                return fail(MSK_ERR_CUDA, "PLOC made no progress (%u -> %u clusters)", c, c2); }
+            c = c2; cur ^= 1; rounds++;
+        }
+        out->build_rounds = rounds;
+    } else {
+        BVH_CHECK(dalloc(&t.flags, nint));
+        BVH_CHECK(dalloc(&t.parent, 2 * n));
+        BVH_CHECK(cudaMemsetAsync(t.flags, 0, nint * sizeof(uint32_t), stream));
+        if (n > 1) k_karras<<<blocks_for(n - 1), kThreads, 0, stream>>>(keys_sorted, (int) n, t);
+        k_refit<<<blocks_for(n), kThreads, 0, stream>>>(gathered, sorted, (int) n, t);
+    }
     if (n > 1) k_sah<<<blocks_for(n - 1), kThreads, 0, stream>>>(t, (int) n, sah);
 
     // level-synchronous collapse

@@ -10,14 +10,17 @@ struct BvhResult {
     float4  *tris  = nullptr;  // ntris  x 3 float4 in leaf order, device
     uint64_t nnodes = 0, ntris = 0;
     uint32_t depth = 0;        // levels of the wide tree
+    int      builder = 0;      // MSK_BVH_PLOC / MSK_BVH_LBVH
+    uint32_t build_rounds = 0; // PLOC: clustering rounds
     float    ms_build = 0.f;
     float    sah_cost = 0.f;   // sum of binary-node areas / root area
     float    lo[3] = { 0, 0, 0 }, hi[3] = { 0, 0, 0 };
 };
 
 // d_verts: 2 float4 per vertex; d_indices: 3 mesh-local indices per triangle; both device.
+enum { MSK_BVH_PLOC = 0, MSK_BVH_LBVH = 1 };
 int  bvh_build(cudaStream_t stream, const float4 *d_verts, const uint32_t *d_indices, const std::vector<DMeshInfo> &meshes,
-               BvhResult *out);
+               BvhResult *out, int builder = MSK_BVH_LBVH);
 void bvh_free(BvhResult *r);
 
 } // namespace msk

@@ -608,6 +608,7 @@ struct Renderer::Impl {
     int spec_shade = 1;               // MSK_SPEC_SHADE: one k_shade launch per material key present in the scene
     uint32_t spec_min = 1u << 18;     // MSK_SPEC_MIN: ... while the queue may hold at least this many vertices
     int shadow_static_bounces = 0;    // MSK_SHADOW_STATIC_BOUNCES: bounces whose shadow queue counts as coherent
+    int debug_bounces = 0;            // MSK_DEBUG_BOUNCES: print polled queue lengths and per-launch stage times to stderr
     int async_poll = 1;               // MSK_ASYNC_POLL: poll the queue length one bounce late, without draining the stream
     std::vector<cudaEvent_t> timer_events; // MSK_RENDER_STAGE_TIMERS
     std::vector<int> timer_stage;
@@ -650,6 +651,7 @@ int Renderer::init(int sm_count) {
     impl_->spec_min = (uint32_t) env_u("MSK_SPEC_MIN", impl_->spec_min);
     impl_->shadow_static_bounces = (int) env_u("MSK_SHADOW_STATIC_BOUNCES", impl_->shadow_static_bounces);
     impl_->async_poll = (int) env_u("MSK_ASYNC_POLL", impl_->async_poll);
+    impl_->debug_bounces = (int) env_u("MSK_DEBUG_BOUNCES", 0);
     return MSK_OK;
 }
 
@@ -771,6 +773,7 @@ int Renderer::render(cudaStream_t stream, const DScene &sc, const MskRenderDesc 
                     if (poll_pending) {
                         MSK_CUDA_CHECK(cudaEventSynchronize(im.poll_ev[slot ^ 1]));
                         n_est = im.h_poll[slot ^ 1]->n_rays[cur ^ 1]; // queue the bounce just enqueued ran over
+                        if (im.debug_bounces) fprintf(stderr, "[msk] bounce %u ran over %u rays\n", bounce - 1, n_est);
                         if (n_est == 0) break;
                     }
                     poll_pending = true;
@@ -813,6 +816,7 @@ int Renderer::render(cudaStream_t stream, const DScene &sc, const MskRenderDesc 
             for (size_t k = 0; k < tstage.size(); ++k) {
                 float ms = 0.f;
                 cudaEventElapsedTime(&ms, im.timer_events[2 * k], im.timer_events[2 * k + 1]);
+                if (im.debug_bounces) fprintf(stderr, "[msk] launch %zu stage %d: %.1f us\n", k, tstage[k], ms * 1e3f);
                 acc[tstage[k]] += ms; cnt[tstage[k]]++;
             }
             stats->ms_raygen = acc[ST_RAYGEN]; stats->ms_intersect = acc[ST_INTERSECT]; stats->ms_shade = acc[ST_SHADE];

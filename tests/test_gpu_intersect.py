@@ -69,3 +69,23 @@ def test_edge_cases(gpu_ctx):
         ref = osc.intersect(rays, brute_force=True)
         assert (h["prim"] == ref["prim"]).all() and (h["geom"] == ref["geom"]).all()
         assert np.allclose(h["t"], ref["t"], rtol=1e-5)
+
+
+def test_ploc_builder_same_hits(gpu_ctx, monkeypatch):
+    """MSK_BVH_BUILDER=ploc (SAH-driven clustering instead of the Morton-prefix tree): another tree over the same
+    triangles must report the same closest hits and the same occlusion."""
+    sd = scenes.bunny(64, 64)
+    osc = pyoracle.OracleScene(sd)
+    rays = np.concatenate([_camera_rays(sd, osc, 3000, 7), random_rays(3000, (-2, 0.05, -2), (2, 2.5, 2), seed=8)])
+    with capi.Scene(gpu_ctx, sd) as sc:
+        base, base_occ, lb = sc.intersect(rays), sc.occluded(rays), sc.accel_info()
+    monkeypatch.setenv("MSK_BVH_BUILDER", "ploc")
+    with capi.Scene(gpu_ctx, sd) as sc:
+        ploc, ploc_occ, pl = sc.intersect(rays), sc.occluded(rays), sc.accel_info()
+    assert pl.ntris == lb.ntris and pl.sah_cost > 0
+    ref = osc.intersect(rays, brute_force=True)
+    t2, mb = osc.margin(rays)
+    assert compare_hits(ploc, ref, t2, mb, rays)["mismatches"] == 0
+    nondeg = mb > 1e-6
+    assert (ploc["prim"] == base["prim"])[nondeg].all()
+    assert (ploc_occ == base_occ)[nondeg | ~np.isfinite(ref["t"])].all()
