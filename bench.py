@@ -390,10 +390,15 @@ def run_c5(args, rank: int, local_rank: int, world: int):
                            "partition": "replicated BVH, every rank traces the full ray sets (independent queries, no collective)"},
                 "e2e": e2e, "gpu_launches": 4 * args.steps, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "wall_s_timed_region": tm1 - tm0}
         print(json.dumps(line), flush=True)
-    scene.close()
-    ctx.close()
+    # release every torch tensor that was used on the library's stream BEFORE that stream is destroyed: the caching
+    # allocator records an event on each stream a block was used on when the block is freed
+    d_prim = d_sec = d_hits = d_occ = sets = pin_r = pin_h = pin_o = r_np = h_np = o_np = None
+    barrier()
     if world > 1:
         dist.destroy_process_group()
+    torch.cuda.synchronize()
+    scene.close()
+    ctx.close()
 
 
 # --------------------------------------------------------------------------------------------- our arm
@@ -567,10 +572,16 @@ def run_ours(args, rank: int, local_rank: int, world: int):
             "wall_s_timed_region": tm1 - tm0,
         }
         print(json.dumps(line), flush=True)
-    scene.close()
-    ctx.close()
+    # release every torch tensor that was used on the library's stream (NCCL's record_stream included) BEFORE that
+    # stream is destroyed: the caching allocator records an event on each such stream when the block is freed
+    film = film_host = flush = fh = None
+    barrier()
     if world > 1:
         dist.destroy_process_group()
+    torch.cuda.synchronize()
+    torch.cuda.empty_cache()
+    scene.close()
+    ctx.close()
 
 
 def main():

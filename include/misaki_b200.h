@@ -20,6 +20,7 @@
  *                            PathTracer::sample          integrators/path.cpp:23-131
  *                            ImageBlock::put/Film::put   imageblock.cpp:36-114, hdrfilm.cpp:43-46
  *   msk_gpu_develop          HDRFilm::image              hdrfilm.cpp:48-90
+ *   msk_gpu_render_aov[_dev] AOVIntegrator::sample       integrators/aov.cpp:87-144 (+ the nested "path" child)
  *
  * Conventions: plain C, POD structs, no exceptions across the boundary.  Every
  * function returns 0 on success or a negative MskStatus; msk_gpu_last_error()
@@ -39,7 +40,7 @@
 extern "C" {
 #endif
 
-#define MSK_ABI_VERSION 2
+#define MSK_ABI_VERSION 3
 
 typedef enum {
     MSK_OK            = 0,
@@ -169,6 +170,23 @@ typedef struct {
     uint32_t pad2_;
 } MskStats;
 
+/* ---- AOV integrator (src/librender/integrators/aov.cpp:22-29,87-144) ---- */
+typedef enum {
+    MSK_AOV_DEPTH           = 0, /* 1 channel : si.t, 0 on a miss                (aov.cpp:97-99)   */
+    MSK_AOV_POSITION        = 1, /* 3 channels: si.p                             (aov.cpp:101-105) */
+    MSK_AOV_UV              = 2, /* 2 channels: si.uv                            (aov.cpp:107-110) */
+    MSK_AOV_GEO_NORMAL      = 3, /* 3 channels: si.n                             (aov.cpp:112-116) */
+    MSK_AOV_SH_NORMAL       = 4, /* 3 channels: si.sh_frame.n                    (aov.cpp:118-122) */
+    MSK_AOV_INTEGRATOR_RGBA = 5  /* 4 channels: nested "path" integrator, linear sRGB + 1 (aov.cpp:124-140) */
+} MskAovType;
+#define MSK_AOV_MAX_CHANNELS 32
+
+typedef struct {
+    const int32_t *types;   /* MskAovType, in the order of the "aovs" string followed by the nested integrators */
+    uint32_t       ntypes;
+    uint32_t       pad_;
+} MskAovDesc;
+
 typedef struct { float o[3]; float tmin; float d[3]; float tmax; } MskRay;     /* 32 B */
 typedef struct { float t, u, v; uint32_t prim; uint32_t geom; } MskHit;          /* 20 B, t=+inf: miss */
 
@@ -209,6 +227,14 @@ int  msk_gpu_intersect_stats(MskScene *scene, const MskRay *rays, size_t n,
 /* film layout: height x width x 5 float32, channels X,Y,Z,A,W (integrator.cpp:39-40) */
 int  msk_gpu_render(MskScene *scene, const MskRenderDesc *rd, float *film_host, MskStats *stats);
 int  msk_gpu_render_dev(MskScene *scene, const MskRenderDesc *rd, float *d_film, MskStats *stats);
+/* AOV integrator: film layout height x width x (5 + msk_gpu_aov_channels(aov)) float32 = X,Y,Z,A,W followed by
+ * the AOV channels, every channel splatted with the reconstruction filter like XYZAW (integrator.cpp:103-126).
+ * At most one MSK_AOV_INTEGRATOR_RGBA entry (the nested path tracer, configured by `rd`); without it X,Y,Z are 0
+ * (the reference returns an uninitialised Spectrum there, aov.cpp:91,142) and fields of a missed ray read 0
+ * (uninitialised in the reference, scene.cpp:247-251). */
+int  msk_gpu_aov_channels(const MskAovDesc *aov);
+int  msk_gpu_render_aov(MskScene *scene, const MskRenderDesc *rd, const MskAovDesc *aov, float *film_host, MskStats *stats);
+int  msk_gpu_render_aov_dev(MskScene *scene, const MskRenderDesc *rd, const MskAovDesc *aov, float *d_film, MskStats *stats);
 /* XYZAW film -> RGBA (linear sRGB / W, A / W), both host, n = width*height pixels */
 int  msk_gpu_develop(MskScene *scene, const float *film_host, float *rgba_host);
 

@@ -22,6 +22,7 @@ EXPORTED_SYMBOLS = [
     "msk_gpu_scene_create", "msk_gpu_scene_destroy", "msk_gpu_accel_info", "msk_gpu_intersect",
     "msk_gpu_occluded", "msk_gpu_intersect_dev", "msk_gpu_occluded_dev", "msk_gpu_intersect_stats",
     "msk_gpu_render", "msk_gpu_render_dev", "msk_gpu_develop",
+    "msk_gpu_aov_channels", "msk_gpu_render_aov", "msk_gpu_render_aov_dev",
 ]
 
 # enums
@@ -30,7 +31,10 @@ BSDF_DIFFUSE, BSDF_CONDUCTOR, BSDF_ROUGHCONDUCTOR, BSDF_ROUGHDIELECTRIC, BSDF_DI
 EMITTER_AREA, EMITTER_CONSTANT = range(2)
 RENDER_STAGE_TIMERS = 1
 RENDER_TRAVERSAL_STATS = 2
-ABI_VERSION = 2
+ABI_VERSION = 3
+AOV_DEPTH, AOV_POSITION, AOV_UV, AOV_GEO_NORMAL, AOV_SH_NORMAL, AOV_INTEGRATOR_RGBA = range(6)
+AOV_NAMES = {"depth": AOV_DEPTH, "position": AOV_POSITION, "uv": AOV_UV, "geo_normal": AOV_GEO_NORMAL, "sh_normal": AOV_SH_NORMAL,
+             "integrator": AOV_INTEGRATOR_RGBA}
 
 
 class MskError(RuntimeError):
@@ -89,6 +93,19 @@ class MskStats(C.Structure):
                 ("ms_sort", C.c_float), ("pad2_", C.c_uint32)]
 
 
+class MskAovDesc(C.Structure):
+    _fields_ = [("types", C.POINTER(C.c_int32)), ("ntypes", C.c_uint32), ("pad_", C.c_uint32)]
+
+
+def aov_desc(types) -> MskAovDesc:
+    """`types`: MskAovType values or their names ("depth", "position", "uv", "geo_normal", "sh_normal", "integrator")."""
+    ids = [AOV_NAMES[t] if isinstance(t, str) else int(t) for t in types]
+    arr = (C.c_int32 * max(len(ids), 1))(*ids)
+    d = MskAovDesc(C.cast(arr, C.POINTER(C.c_int32)), len(ids), 0)
+    d._keep = arr
+    return d
+
+
 class MskAccelInfo(C.Structure):
     _fields_ = [("ntris", C.c_uint64), ("nnodes", C.c_uint64), ("node_bytes", C.c_uint64), ("tri_bytes", C.c_uint64),
                 ("ms_build", C.c_float), ("sah_cost", C.c_float), ("max_depth", C.c_uint32), ("pad_", C.c_uint32)]
@@ -129,6 +146,9 @@ def load(path: os.PathLike | None = None) -> C.CDLL:
     lib.msk_gpu_render.argtypes = [C.c_void_p, C.POINTER(MskRenderDesc), C.c_void_p, C.POINTER(MskStats)]
     lib.msk_gpu_render_dev.argtypes = [C.c_void_p, C.POINTER(MskRenderDesc), C.c_void_p, C.POINTER(MskStats)]
     lib.msk_gpu_develop.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.msk_gpu_aov_channels.argtypes = [C.POINTER(MskAovDesc)]
+    lib.msk_gpu_render_aov.argtypes = [C.c_void_p, C.POINTER(MskRenderDesc), C.POINTER(MskAovDesc), C.c_void_p, C.POINTER(MskStats)]
+    lib.msk_gpu_render_aov_dev.argtypes = [C.c_void_p, C.POINTER(MskRenderDesc), C.POINTER(MskAovDesc), C.c_void_p, C.POINTER(MskStats)]
     if path is None:
         _lib = lib
     return lib
@@ -247,8 +267,22 @@ class Scene:
         check(self.lib, self.lib.msk_gpu_render_dev(self.handle, C.byref(rd), d_film, C.byref(stats) if want_stats else None))
         return stats
 
+    def render_aov(self, rd: MskRenderDesc, types, film: np.ndarray | None = None):
+        """The AOV integrator (reference integrators/aov.cpp).  Host film in / out, H x W x (5 + channels) float32:
+        X,Y,Z,A,W then the AOV channels in the order of `types`.  Returns (film, stats)."""
+        ad = aov_desc(types)
+        nch = self.lib.msk_gpu_aov_channels(C.byref(ad))
+        if nch < 0:
+            check(self.lib, nch)
+        if film is None:
+            film = np.zeros((self.height, self.width, 5 + nch), dtype=np.float32)
+        assert film.dtype == np.float32 and film.flags.c_contiguous and film.shape == (self.height, self.width, 5 + nch)
+        stats = MskStats()
+        check(self.lib, self.lib.msk_gpu_render_aov(self.handle, C.byref(rd), C.byref(ad), film.ctypes.data, C.byref(stats)))
+        return film, stats
+
     def develop(self, film: np.ndarray) -> np.ndarray:
-        film = np.ascontiguousarray(film, dtype=np.float32)
+        film = np.ascontiguousarray(film[..., :5], dtype=np.float32)
         rgba = np.empty((self.height, self.width, 4), dtype=np.float32)
         check(self.lib, self.lib.msk_gpu_develop(self.handle, film.ctypes.data, rgba.ctypes.data))
         return rgba

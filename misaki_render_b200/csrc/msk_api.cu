@@ -435,6 +435,44 @@ int msk_gpu_render(MskScene *s, const MskRenderDesc *rd, float *film_host, MskSt
     return rc;
 }
 
+// AOVIntegrator (integrators/aov.cpp): channel count of a description, or a negative status
+int msk_gpu_aov_channels(const MskAovDesc *aov) {
+    if (!aov) return fail(MSK_ERR_ARG, "null argument");
+    uint32_t nch = 0;
+    int rc = Renderer::aov_plan(*aov, &nch);
+    return rc ? rc : (int) nch;
+}
+
+int msk_gpu_render_aov_dev(MskScene *s, const MskRenderDesc *rd, const MskAovDesc *aov, float *d_film, MskStats *stats) {
+    if (!s || !rd || !aov || !d_film) return fail(MSK_ERR_ARG, "null argument");
+    DeviceGuard guard(s->ctx->device);
+    return s->ctx->renderer.render(s->ctx->stream, s->d, *rd, d_film, stats, aov);
+}
+
+int msk_gpu_render_aov(MskScene *s, const MskRenderDesc *rd, const MskAovDesc *aov, float *film_host, MskStats *stats) {
+    if (!s || !rd || !aov || !film_host) return fail(MSK_ERR_ARG, "null argument");
+    uint32_t nch = 0;
+    int rc = Renderer::aov_plan(*aov, &nch);
+    if (rc) return rc;
+    DeviceGuard guard(s->ctx->device);
+    cudaStream_t st = s->ctx->stream;
+    size_t bytes = (size_t) s->d.cam.width * s->d.cam.height * (5 + nch) * sizeof(float);
+    MskCtx *ctx = s->ctx;
+    if (ctx->film_cache_bytes < bytes) {
+        cudaFree(ctx->film_cache); ctx->film_cache = nullptr; ctx->film_cache_bytes = 0;
+        MSK_CUDA_CHECK(cudaMalloc((void **) &ctx->film_cache, bytes));
+        ctx->film_cache_bytes = bytes;
+    }
+    float *d_film = ctx->film_cache;
+    cudaError_t e = cudaSuccess;
+    if (!rd->clear_film) e = cudaMemcpyAsync(d_film, film_host, bytes, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) rc = ctx->renderer.render(st, s->d, *rd, d_film, stats, aov);
+    if (e == cudaSuccess && !rc) e = cudaMemcpyAsync(film_host, d_film, bytes, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess && !rc) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) return cuda_fail(e, "msk_gpu_render_aov", __FILE__, __LINE__);
+    return rc;
+}
+
 // HDRFilm::image, hdrfilm.cpp:48-90 (host side; runs once per image)
 int msk_gpu_develop(MskScene *s, const float *film, float *rgba) {
     if (!s || !film || !rgba) return fail(MSK_ERR_ARG, "null argument");

@@ -63,7 +63,15 @@ struct Pool {
     float4  *rec;                   // X, Y, Z, pos.x
     float   *rec_py;
     uint32_t *sorted;               // kNumKeys segments of `capacity` queue indices
+    float   *aov;                   // AOV integrator: channel-major per-sample values, aov[c * capacity + i]
     Ctrl    *ctrl;
+};
+
+// AOVIntegrator (aov.cpp:22-29): the requested outputs in channel order
+struct AovPlan {
+    uint32_t ntypes, nch;
+    int32_t  rgba_channel;          // first channel of the nested integrator's RGBA, or -1
+    uint8_t  types[MSK_AOV_MAX_CHANNELS];
 };
 
 struct BatchParams {
@@ -422,7 +430,7 @@ __global__ void __launch_bounds__(128, MSK_TRAV_MIN_BLOCKS) k_shadow(const __gri
 
 // ---------------------------------------------------------------------------------------
 // Film.  render_sample tail (integrator.cpp:115-125): xyz = spectrum_to_xyz(result * ray_weight).
-__global__ void __launch_bounds__(256) k_film_records(const __grid_constant__ DScene sc, Pool pool, BatchParams bp) {
+__global__ void __launch_bounds__(256) k_film_records(const __grid_constant__ DScene sc, Pool pool, BatchParams bp, int rgba_channel) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     uint32_t n = bp.npix * bp.ns;
     if (i >= n) return;
@@ -433,11 +441,48 @@ __global__ void __launch_bounds__(256) k_film_records(const __grid_constant__ DS
     float wav = next1d(rng);
     float4 wl, weight;
     sample_wavelength(wav, wl, weight);
-    float4 result = pool.L[i] * weight;
+    const float4 spec = pool.L[i];
+    float4 result = spec * weight;
     float X, Y, Z;
     spectrum_to_xyz(sc, result, wl, X, Y, Z);
     pool.rec[i]    = make_float4(X, Y, Z, (float) gx + jx);
     pool.rec_py[i] = (float) gy + jy;
+    if (rgba_channel >= 0) { // aov.cpp:124-140: xyz_to_srgb(spectrum_to_xyz(spec)) of the nested integrator, before ray_weight
+        float x, y, z;
+        spectrum_to_xyz(sc, spec, wl, x, y, z);
+        float *a = pool.aov + (size_t) rgba_channel * pool.capacity + i;
+        a[0]                         = 3.240479f * x + -1.537150f * y + -0.498535f * z;
+        a[pool.capacity]             = -0.969256f * x + 1.875991f * y + 0.041556f * z;
+        a[2 * (size_t) pool.capacity] = 0.055648f * x + -0.204043f * y + 1.057311f * z;
+        a[3 * (size_t) pool.capacity] = 1.f;
+    }
+}
+
+// AOVIntegrator::sample (aov.cpp:87-122): geometric outputs of the primary hit, read from the hit records of
+// bounce 0 (queue index == sample index there) before the next bounce overwrites them.
+__global__ void __launch_bounds__(256) k_aov_capture(const __grid_constant__ DScene sc, Pool pool, BatchParams bp, AovPlan plan) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t n = bp.npix * bp.ns;
+    if (i >= n) return;
+    const float4 hit = pool.hit[i];
+    const uint32_t geom = pool.hit_geom[i];
+    Surface sf;
+    sf.p = v3(0, 0, 0); sf.n = v3(0, 0, 0); sf.sh.n = v3(0, 0, 0); sf.uvx = 0.f; sf.uvy = 0.f;
+    const bool valid = geom != 0xffffffffu;
+    if (valid) sf = make_surface(sc, sc.meshes[geom], __float_as_uint(hit.w), hit.y, hit.z);
+    float *a = pool.aov + i;
+    const size_t cs = pool.capacity;
+    uint32_t c = 0;
+    for (uint32_t k = 0; k < plan.ntypes; ++k) {
+        switch (plan.types[k]) {
+            case MSK_AOV_DEPTH: a[c * cs] = valid ? hit.x : 0.f; c += 1; break;
+            case MSK_AOV_POSITION: a[c * cs] = sf.p.x; a[(c + 1) * cs] = sf.p.y; a[(c + 2) * cs] = sf.p.z; c += 3; break;
+            case MSK_AOV_UV: a[c * cs] = sf.uvx; a[(c + 1) * cs] = sf.uvy; c += 2; break;
+            case MSK_AOV_GEO_NORMAL: a[c * cs] = sf.n.x; a[(c + 1) * cs] = sf.n.y; a[(c + 2) * cs] = sf.n.z; c += 3; break;
+            case MSK_AOV_SH_NORMAL: a[c * cs] = sf.sh.n.x; a[(c + 1) * cs] = sf.sh.n.y; a[(c + 2) * cs] = sf.sh.n.z; c += 3; break;
+            default: c += 4; break; // MSK_AOV_INTEGRATOR_RGBA: written by k_film_records once the paths are complete
+        }
+    }
 }
 
 // ImageBlock::put (imageblock.cpp:55-114) + Film::put, as a gather: pixel (x, y) sums
@@ -448,7 +493,7 @@ constexpr int kFilmTileX = 32, kFilmTileY = 8;
 constexpr int kBlockSize = 32; // MSK_BLOCK_SIZE, imageblock.h:8
 __global__ void __launch_bounds__(kFilmTileX *kFilmTileY) k_film_gather(const __grid_constant__ DScene sc, Pool pool,
                                                                          BatchParams bp, float *__restrict__ film,
-                                                                         uint32_t height) {
+                                                                         uint32_t height, uint32_t stride) {
     const int x = blockIdx.x * kFilmTileX + threadIdx.x, y = blockIdx.y * kFilmTileY + threadIdx.y;
     const int W = (int) bp.width, H = (int) height;
     if (x >= W || y >= H) return;
@@ -476,8 +521,48 @@ __global__ void __launch_bounds__(kFilmTileX *kFilmTileY) k_film_gather(const __
                 aX += w * rec.x; aY += w * rec.y; aZ += w * rec.z; aW += w;
             }
     }
-    float *p = film + ((size_t) y * W + x) * 5;
+    float *p = film + ((size_t) y * W + x) * stride;
     p[0] += aX; p[1] += aY; p[2] += aZ; p[3] += aW; p[4] += aW;
+}
+
+// The AOV channels of the film (channels 5.. of every pixel): the same gather, same weights, over the channel-major
+// per-sample AOV values.  Not a hot path (the AOV integrator renders one bounce), so it reads through L1/L2.
+constexpr int kAovChunk = 8;
+__global__ void __launch_bounds__(kFilmTileX *kFilmTileY) k_film_gather_aov(const __grid_constant__ DScene sc, Pool pool,
+                                                                             BatchParams bp, float *__restrict__ film,
+                                                                             uint32_t height, uint32_t stride, uint32_t nch) {
+    const int x = blockIdx.x * kFilmTileX + threadIdx.x, y = blockIdx.y * kFilmTileY + threadIdx.y;
+    const int W = (int) bp.width, H = (int) height;
+    if (x >= W || y >= H) return;
+    const int r = (int) ceilf(sc.cam.filter_radius - 0.5f);
+    const float scale = sc.cam.filter_scale, radius = sc.cam.filter_radius;
+    for (uint32_t c0 = 0; c0 < nch; c0 += kAovChunk) {
+        float acc[kAovChunk];
+#pragma unroll
+        for (int k = 0; k < kAovChunk; ++k) acc[k] = 0.f;
+        for (uint32_t s = 0; s < bp.ns; ++s) {
+            const size_t sbase = (size_t) s * bp.npix;
+            for (int ny = max(y - r, 0); ny <= min(y + r, H - 1); ++ny)
+                for (int nx = max(x - r, 0); nx <= min(x + r, W - 1); ++nx) {
+                    const size_t i = sbase + (size_t) ny * W + nx;
+                    const float px = __ldg(&pool.rec[i].w), py = __ldg(pool.rec_py + i);
+                    const int bx = (nx & ~(kBlockSize - 1)) - r, by = (ny & ~(kBlockSize - 1)) - r;
+                    const float posx = px - 0.5f - (float) bx, posy = py - 0.5f - (float) by;
+                    const float xb = (float) (x - bx), yb = (float) (y - by);
+                    if (xb < posx - radius || xb > posx + radius || yb < posy - radius || yb > posy + radius) continue;
+                    const float wx = __ldg(sc.filter_table + min((int) fabsf((xb - posx) * scale), 32));
+                    const float wy = __ldg(sc.filter_table + min((int) fabsf((yb - posy) * scale), 32));
+                    const float w = wx * wy;
+#pragma unroll
+                    for (int k = 0; k < kAovChunk; ++k)
+                        if (c0 + k < nch) acc[k] += w * __ldg(pool.aov + (size_t) (c0 + k) * pool.capacity + i);
+                }
+        }
+        float *p = film + ((size_t) y * W + x) * stride + 5 + c0;
+#pragma unroll
+        for (int k = 0; k < kAovChunk; ++k)
+            if (c0 + k < nch) p[k] += acc[k];
+    }
 }
 
 // The same gather with the records of the tile's neighbourhood staged in shared memory, for filters whose border
@@ -490,7 +575,7 @@ constexpr int kFilmMaxBorder = 2;
 constexpr int kFilmHaloX = kFilmTileX + 2 * kFilmMaxBorder, kFilmHaloY = kFilmTileY + 2 * kFilmMaxBorder;
 __global__ void __launch_bounds__(kFilmTileX *kFilmTileY) k_film_gather_tiled(const __grid_constant__ DScene sc, Pool pool,
                                                                                BatchParams bp, float *__restrict__ film,
-                                                                               uint32_t height) {
+                                                                               uint32_t height, uint32_t stride) {
     __shared__ float4 s_a[kFilmHaloY][kFilmHaloX]; // X, Y, Z, posx (block-relative, imageblock.cpp:86-98)
     __shared__ float4 s_b[kFilmHaloY][kFilmHaloX]; // posy, (float) bx, (float) by, valid
     __shared__ float s_tab[33];
@@ -536,7 +621,7 @@ __global__ void __launch_bounds__(kFilmTileX *kFilmTileY) k_film_gather_tiled(co
             }
     }
     if (!inside) return;
-    float *p = film + ((size_t) y * W + x) * 5;
+    float *p = film + ((size_t) y * W + x) * stride;
     p[0] += aX; p[1] += aY; p[2] += aZ; p[3] += aW; p[4] += aW;
 }
 
@@ -613,6 +698,7 @@ struct Renderer::Impl {
     std::vector<cudaEvent_t> timer_events; // MSK_RENDER_STAGE_TIMERS
     std::vector<int> timer_stage;
     int persistent_blocks = 0, sm_count = 0;
+    size_t aov_floats = 0; // allocated size of pool.aov
 };
 
 Renderer::Renderer() : impl_(new Impl) {}
@@ -622,9 +708,9 @@ void Renderer::release() {
     Pool &p = impl_->pool;
     for (int i = 0; i < 2; ++i) { cudaFree(p.rays[i]); cudaFree(p.T[i]); cudaFree(p.WL[i]); cudaFree(p.AUX[i]); cudaFree(p.MISC[i]); }
     cudaFree(p.hit); cudaFree(p.hit_geom); cudaFree(p.L); cudaFree(p.sh_ray); cudaFree(p.sh_contrib); cudaFree(p.sh_path);
-    cudaFree(p.sorted); cudaFree(p.rec); cudaFree(p.rec_py); cudaFree(p.ctrl);
+    cudaFree(p.sorted); cudaFree(p.rec); cudaFree(p.rec_py); cudaFree(p.ctrl); cudaFree(p.aov);
     p = Pool{};
-    impl_->capacity = 0;
+    impl_->capacity = 0; impl_->aov_floats = 0;
     cudaFree(impl_->query_cursor); impl_->query_cursor = nullptr;
     if (impl_->h_ctrl) { cudaFreeHost(impl_->h_ctrl); impl_->h_ctrl = nullptr; }
     for (auto &h : impl_->h_poll) if (h) { cudaFreeHost(h); h = nullptr; }
@@ -660,9 +746,9 @@ int Renderer::ensure_pool(uint32_t capacity) {
     Pool &p = impl_->pool;
     for (int i = 0; i < 2; ++i) { cudaFree(p.rays[i]); cudaFree(p.T[i]); cudaFree(p.WL[i]); cudaFree(p.AUX[i]); cudaFree(p.MISC[i]); }
     cudaFree(p.hit); cudaFree(p.hit_geom); cudaFree(p.L); cudaFree(p.sh_ray); cudaFree(p.sh_contrib); cudaFree(p.sh_path);
-    cudaFree(p.sorted); cudaFree(p.rec); cudaFree(p.rec_py); cudaFree(p.ctrl);
+    cudaFree(p.sorted); cudaFree(p.rec); cudaFree(p.rec_py); cudaFree(p.ctrl); cudaFree(p.aov);
     p = Pool{};
-    impl_->capacity = 0;
+    impl_->capacity = 0; impl_->aov_floats = 0;
     size_t n = capacity;
     for (int i = 0; i < 2; ++i) {
         MSK_CUDA_CHECK(dalloc(&p.rays[i], n)); MSK_CUDA_CHECK(dalloc(&p.T[i], n)); MSK_CUDA_CHECK(dalloc(&p.WL[i], n));
@@ -678,7 +764,22 @@ int Renderer::ensure_pool(uint32_t capacity) {
     return MSK_OK;
 }
 
-int Renderer::render(cudaStream_t stream, const DScene &sc, const MskRenderDesc &rd, float *d_film, MskStats *stats) {
+int Renderer::aov_plan(const MskAovDesc &aov, uint32_t *nch) {
+    static const uint32_t per[6] = { 1, 3, 2, 3, 3, 4 };
+    if (aov.ntypes && !aov.types) return fail(MSK_ERR_ARG, "AOV description without types");
+    uint32_t n = 0, nested = 0;
+    for (uint32_t i = 0; i < aov.ntypes; ++i) {
+        if (aov.types[i] < 0 || aov.types[i] > MSK_AOV_INTEGRATOR_RGBA) return fail(MSK_ERR_ARG, "Invalid AOV type %d!", aov.types[i]);
+        nested += aov.types[i] == MSK_AOV_INTEGRATOR_RGBA;
+        n += per[aov.types[i]];
+    }
+    if (nested > 1) return fail(MSK_ERR_UNSUPPORTED, "at most one nested integrator per AOV integrator");
+    if (n > MSK_AOV_MAX_CHANNELS) return fail(MSK_ERR_UNSUPPORTED, "more than %d AOV channels", MSK_AOV_MAX_CHANNELS);
+    if (nch) *nch = n;
+    return MSK_OK;
+}
+
+int Renderer::render(cudaStream_t stream, const DScene &sc, const MskRenderDesc &rd, float *d_film, MskStats *stats, const MskAovDesc *aov) {
     const uint32_t W = sc.cam.width, H = sc.cam.height;
     const uint64_t npix64 = (uint64_t) W * H;
     if (!W || !H || npix64 > (1ull << 27)) return fail(MSK_ERR_UNSUPPORTED, "film size %ux%u unsupported", W, H);
@@ -695,8 +796,29 @@ int Renderer::render(cudaStream_t stream, const DScene &sc, const MskRenderDesc 
     if (rc) return rc;
     Pool &pool = impl_->pool;
     Impl &im = *impl_;
+    // AOV integrator: film stride 5 + nch; per-sample AOV values live beside the path pool
+    AovPlan plan{};
+    plan.rgba_channel = -1;
+    if (aov) {
+        if ((rc = aov_plan(*aov, &plan.nch))) return rc;
+        plan.ntypes = aov->ntypes;
+        static const uint32_t per[6] = { 1, 3, 2, 3, 3, 4 };
+        for (uint32_t i = 0, c = 0; i < aov->ntypes; ++i) {
+            plan.types[i] = (uint8_t) aov->types[i];
+            if (aov->types[i] == MSK_AOV_INTEGRATOR_RGBA) plan.rgba_channel = (int32_t) c;
+            c += per[aov->types[i]];
+        }
+        const size_t need = (size_t) impl_->capacity * std::max(plan.nch, 1u);
+        if (im.aov_floats < need) {
+            cudaFree(pool.aov); pool.aov = nullptr; im.aov_floats = 0;
+            MSK_CUDA_CHECK(dalloc(&pool.aov, need));
+            im.aov_floats = need;
+        }
+    }
+    const uint32_t stride = 5 + plan.nch;
+    const bool trace_paths = !aov || plan.rgba_channel >= 0; // an AOV integrator without a nested one traces primary rays only
 
-    if (rd.clear_film) MSK_CUDA_CHECK(cudaMemsetAsync(d_film, 0, (size_t) npix * 5 * sizeof(float), stream));
+    if (rd.clear_film) MSK_CUDA_CHECK(cudaMemsetAsync(d_film, 0, (size_t) npix * stride * sizeof(float), stream));
     MSK_CUDA_CHECK(cudaMemsetAsync(&pool.ctrl->total_closest, 0, 7 * sizeof(unsigned long long), stream));
     const bool tstats = (rd.flags & MSK_RENDER_TRAVERSAL_STATS) != 0;
     MSK_CUDA_CHECK(cudaEventRecord(im.ev[0], stream));
@@ -707,6 +829,7 @@ int Renderer::render(cudaStream_t stream, const DScene &sc, const MskRenderDesc 
     // for the per-kernel roofline; the extra event records perturb ms_render slightly, so it is off by default)
     const bool timers = (rd.flags & MSK_RENDER_STAGE_TIMERS) != 0;
     enum { ST_RAYGEN, ST_INTERSECT, ST_SORT, ST_SHADE, ST_SHADOW, ST_FILM, ST_COUNT };
+    uint64_t extra_closest = 0;
     std::vector<int> &tstage = im.timer_stage;
     tstage.clear();
     size_t tev = 0;
@@ -739,12 +862,19 @@ int Renderer::render(cudaStream_t stream, const DScene &sc, const MskRenderDesc 
         uint32_t bounce = 0;
         // a path reaches vertex `depth` only while depth <= max_depth, and the vertex at max_depth still
         // needs its shade pass (emission), so a bounded job runs exactly max_depth iterations
-        const uint32_t bound = rd.max_depth > 0 ? (uint32_t) rd.max_depth : (rd.max_depth == 0 ? 0u : 0xffffffffu);
+        const uint32_t bound = !trace_paths ? 0u : (rd.max_depth > 0 ? (uint32_t) rd.max_depth : (rd.max_depth == 0 ? 0u : 0xffffffffu));
+        if (aov && bound == 0) { // the AOV integrator's own ray_intersect (aov.cpp:90) when no path bounce runs
+            MSK_STAGE(ST_INTERSECT, (k_intersect<false><<<pb, 128, 0, stream>>>(sc, pool, 0, 1)));
+            MSK_STAGE(ST_FILM, (k_aov_capture<<<(n + 255) / 256, 256, 0, stream>>>(sc, pool, bp, plan)));
+            extra_closest += n;
+        }
         uint32_t n_est = n;       // upper bound of the current queue length known to the host (queues only shrink)
         bool poll_pending = false; // a poll of the previous bounce is in flight (async_poll)
         while (bounce < bound) {
             if (tstats) MSK_STAGE(ST_INTERSECT, (k_intersect<true><<<pb, 128, 0, stream>>>(sc, pool, cur, bounce == 0)));
             else MSK_STAGE(ST_INTERSECT, (k_intersect<false><<<pb, 128, 0, stream>>>(sc, pool, cur, bounce == 0)));
+            // the AOV integrator shares the primary hit with the nested path tracer (the reference intersects twice)
+            if (aov && bounce == 0) MSK_STAGE(ST_FILM, (k_aov_capture<<<(n + 255) / 256, 256, 0, stream>>>(sc, pool, bp, plan)));
             if (!MSK_SORT_IN_COMMIT) MSK_STAGE(ST_SORT, (k_sort<<<im.sm_count * 4, kSortThreads, 0, stream>>>(sc, pool, cur)));
             if (im.spec_shade && n_est >= im.spec_min) {
                 const uint32_t keys = 1u | (sc.bsdf_type_mask << 1);
@@ -786,12 +916,13 @@ int Renderer::render(cudaStream_t stream, const DScene &sc, const MskRenderDesc 
             }
         }
         max_bounces = std::max(max_bounces, bounce);
-        MSK_STAGE(ST_FILM, (k_film_records<<<(n + 255) / 256, 256, 0, stream>>>(sc, pool, bp)));
+        MSK_STAGE(ST_FILM, (k_film_records<<<(n + 255) / 256, 256, 0, stream>>>(sc, pool, bp, plan.rgba_channel)));
         dim3 fg((W + kFilmTileX - 1) / kFilmTileX, (H + kFilmTileY - 1) / kFilmTileY), fb(kFilmTileX, kFilmTileY);
         if ((int) std::ceil(sc.cam.filter_radius - 0.5f) <= kFilmMaxBorder)
-            MSK_STAGE(ST_FILM, (k_film_gather_tiled<<<fg, fb, 0, stream>>>(sc, pool, bp, d_film, H)));
+            MSK_STAGE(ST_FILM, (k_film_gather_tiled<<<fg, fb, 0, stream>>>(sc, pool, bp, d_film, H, stride)));
         else
-            MSK_STAGE(ST_FILM, (k_film_gather<<<fg, fb, 0, stream>>>(sc, pool, bp, d_film, H)));
+            MSK_STAGE(ST_FILM, (k_film_gather<<<fg, fb, 0, stream>>>(sc, pool, bp, d_film, H, stride)));
+        if (plan.nch) MSK_STAGE(ST_FILM, (k_film_gather_aov<<<fg, fb, 0, stream>>>(sc, pool, bp, d_film, H, stride, plan.nch)));
         batches++;
     }
 #undef MSK_STAGE
@@ -802,7 +933,7 @@ int Renderer::render(cudaStream_t stream, const DScene &sc, const MskRenderDesc 
         MSK_CUDA_CHECK(cudaStreamSynchronize(stream));
         *stats = MskStats{};
         stats->paths = (uint64_t) npix * nsamples;
-        stats->rays_closest = im.h_ctrl->total_closest;
+        stats->rays_closest = im.h_ctrl->total_closest + extra_closest;
         stats->rays_shadow = im.h_ctrl->total_shadow;
         stats->shaded_vertices = im.h_ctrl->shaded;
         stats->nodes_closest = im.h_ctrl->nodes_closest; stats->tris_closest = im.h_ctrl->tris_closest;

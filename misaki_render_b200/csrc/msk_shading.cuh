@@ -420,6 +420,7 @@ __device__ __forceinline__ float mis_weight(float pdf_a, float pdf_b) { // path.
 struct Surface {
     V3 p, n;      // position (barycentric), geometric normal
     Frame sh;     // shading frame
+    float uvx, uvy; // si.uv: interpolated texcoords, or the barycentrics when the mesh has none (mesh.cpp:65-72)
 };
 
 __device__ __forceinline__ Surface make_surface(const DScene &sc, const DMeshInfo &mi, uint32_t prim, float bu, float bv) {
@@ -437,7 +438,9 @@ __device__ __forceinline__ Surface make_surface(const DScene &sc, const DMeshInf
     coordinate_system(s.n, dp_du, dp_dv);
     float4 a1, b1v, c1;
     if (mi.flags) { a1 = __ldg(vp + 2 * (size_t) i0 + 1); b1v = __ldg(vp + 2 * (size_t) i1 + 1); c1 = __ldg(vp + 2 * (size_t) i2 + 1); }
+    s.uvx = bu; s.uvy = bv;
     if (mi.flags & 2u) {
+        s.uvx = a1.z * bb0 + b1v.z * b1 + c1.z * b2; s.uvy = a1.w * bb0 + b1v.w * b1 + c1.w * b2;
         float du0 = b1v.z - a1.z, dv0 = b1v.w - a1.w, du1 = c1.z - a1.z, dv1 = c1.w - a1.w;
         float det = du0 * dv1 - dv0 * du1, inv_det = 1.f / det;
         if (det != 0.f) dp_du = (dv1 * dp0 - dv0 * dp1) * inv_det;

@@ -54,6 +54,47 @@ struct DeviceContext { // one MskCtx per process and device, created on first us
 DeviceContext g_dev;
 } // namespace
 
+// Shared by the "path" and "aov" plugins: flatten the scene, run msk_gpu_render[_aov], hand the film-sized
+// border-less block to Film::put.  `aov_types` empty and `aov == false`: the plain path tracer.
+static void gpu_render(Scene *scene, Sensor *sensor, const MskRenderDesc &rd, int device_prop, bool aov,
+                       const std::vector<int32_t> &aov_types, const std::vector<std::string> &aov_names, MskStats &stats) {
+    Film *film = sensor->film();
+    std::vector<std::string> channels = aov_names; // integrator.cpp:36-41: X,Y,Z,A,W first
+    for (size_t i = 0; i < 5; ++i) channels.insert(channels.begin() + i, std::string(1, "XYZAW"[i]));
+    film->prepare(channels);
+    GpuSceneBuilder builder(scene);
+    int device = device_prop >= 0 ? device_prop : (getenv("MSK_DEVICE") ? atoi(getenv("MSK_DEVICE")) : 0);
+    std::lock_guard<std::mutex> lock(g_dev.mutex);
+    if (g_dev.ctx && g_dev.device != device) { msk_gpu_shutdown(g_dev.ctx); g_dev.ctx = nullptr; }
+    if (!g_dev.ctx) {
+        if (msk_gpu_init(device, &g_dev.ctx) != MSK_OK) Throw("%s", msk_gpu_last_error());
+        g_dev.device = device;
+    }
+    MskScene *gpu_scene = nullptr;
+    if (msk_gpu_scene_create(g_dev.ctx, &builder.desc(), &gpu_scene) != MSK_OK) Throw("%s", msk_gpu_last_error());
+    MskAccelInfo info{};
+    msk_gpu_accel_info(gpu_scene, &info);
+    Log(Info, "GPU scene: %llu triangles, %llu wide nodes, BVH built in %.2f ms", (unsigned long long) info.ntris,
+        (unsigned long long) info.nnodes, info.ms_build);
+    Log(Info, "Start rendering...");
+    ref<ImageBlock> block = new ImageBlock(film->width(), film->height(), (uint32_t) channels.size());
+    int rc;
+    if (aov) {
+        MskAovDesc ad{ aov_types.data(), (uint32_t) aov_types.size(), 0 };
+        int nch = msk_gpu_aov_channels(&ad);
+        if (nch < 0 || (size_t) nch + 5 != channels.size()) { msk_gpu_scene_destroy(gpu_scene); Throw("%s", nch < 0 ? msk_gpu_last_error() : "AOV channel names do not match the AOV types"); }
+        rc = msk_gpu_render_aov(gpu_scene, &rd, &ad, block->data().data(), &stats);
+    } else {
+        rc = msk_gpu_render(gpu_scene, &rd, block->data().data(), &stats);
+    }
+    msk_gpu_scene_destroy(gpu_scene);
+    if (rc != MSK_OK) Throw("%s", msk_gpu_last_error());
+    film->put(block.get()); // integrator.cpp:69 / hdrfilm.cpp:43-46
+    double rays = (double) stats.rays_closest + (double) stats.rays_shadow;
+    Log(Info, "Rendering finished. (took %.2f ms on the device: %.1f Mpaths/s, %.1f Mrays/s, %llu kernel launches)", stats.ms_render,
+        stats.paths / (stats.ms_render * 1e3), rays / (stats.ms_render * 1e3), (unsigned long long) stats.kernel_launches);
+}
+
 class GpuPathIntegrator final : public MonteCarloIntegrator {
 public:
     explicit GpuPathIntegrator(const Properties &props) : MonteCarloIntegrator(props) {
@@ -76,36 +117,13 @@ public:
     }
 
     bool render(Scene *scene, Sensor *sensor) override {
-        Film *film = sensor->film();
-        film->prepare({ "X", "Y", "Z", "A", "W" }); // integrator.cpp:36-41
-        GpuSceneBuilder builder(scene);
         MskRenderDesc rd;
         render_desc(sensor, rd);
-        int device = m_device >= 0 ? m_device : (getenv("MSK_DEVICE") ? atoi(getenv("MSK_DEVICE")) : 0);
-        std::lock_guard<std::mutex> lock(g_dev.mutex);
-        if (g_dev.ctx && g_dev.device != device) { msk_gpu_shutdown(g_dev.ctx); g_dev.ctx = nullptr; }
-        if (!g_dev.ctx) {
-            if (msk_gpu_init(device, &g_dev.ctx) != MSK_OK) Throw("%s", msk_gpu_last_error());
-            g_dev.device = device;
-        }
-        MskScene *gpu_scene = nullptr;
-        if (msk_gpu_scene_create(g_dev.ctx, &builder.desc(), &gpu_scene) != MSK_OK) Throw("%s", msk_gpu_last_error());
-        MskAccelInfo info{};
-        msk_gpu_accel_info(gpu_scene, &info);
-        Log(Info, "GPU scene: %llu triangles, %llu wide nodes, BVH built in %.2f ms", (unsigned long long) info.ntris,
-            (unsigned long long) info.nnodes, info.ms_build);
-        Log(Info, "Start rendering...");
-        ref<ImageBlock> block = new ImageBlock(film->width(), film->height(), 5);
-        int rc = msk_gpu_render(gpu_scene, &rd, block->data().data(), &m_stats);
-        msk_gpu_scene_destroy(gpu_scene);
-        if (rc != MSK_OK) Throw("%s", msk_gpu_last_error());
-        film->put(block.get()); // integrator.cpp:69 / hdrfilm.cpp:43-46
-        double rays = (double) m_stats.rays_closest + (double) m_stats.rays_shadow;
-        Log(Info, "Rendering finished. (took %.2f ms on the device: %.1f Mpaths/s, %.1f Mrays/s, %llu kernel launches)", m_stats.ms_render,
-            m_stats.paths / (m_stats.ms_render * 1e3), rays / (m_stats.ms_render * 1e3), (unsigned long long) m_stats.kernel_launches);
+        gpu_render(scene, sensor, rd, m_device, false, {}, {}, m_stats);
         return true;
     }
     const MskStats &stats() const { return m_stats; }
+    int device() const { return m_device; }
     MSK_DECLARE_CLASS()
 private:
     int m_device;
@@ -113,6 +131,64 @@ private:
     MskStats m_stats{};
 };
 MSK_IMPLEMENT_PLUGIN(GpuPathIntegrator, MonteCarloIntegrator, "path")
+
+// The "aov" integrator plugin: reference src/librender/integrators/aov.cpp (AOVIntegrator,
+// MSK_REGISTER_INSTANCE(AOVIntegrator, "aov") :156).  The constructor follows aov.cpp:30-85: the "aovs" string is a
+// list of <name>:<type> pairs (depth, position, uv, geo_normal, sh_normal), child integrators add
+// <child>.R/.G/.B/.A.  sample() (aov.cpp:87-144) runs on the device behind msk_gpu_render_aov; one nested
+// integrator, the GPU path tracer, is supported (nested integrators of other kinds do not exist in this build).
+class GpuAovIntegrator final : public MonteCarloIntegrator {
+public:
+    explicit GpuAovIntegrator(const Properties &props) : MonteCarloIntegrator(props) {
+        m_device = (int) props.int_("device", -1);
+        for (const std::string &token : string::tokenize(props.string("aovs"))) {
+            std::vector<std::string> item = string::tokenize(token, ":");
+            if (item.size() != 2 || item[0].empty() || item[1].empty()) {
+                Log(Warn, "Invalid AOV specification: require <name>:<type> pair");
+                continue; // the reference goes on to read item[1] out of range here (aov.cpp:37-41)
+            }
+            if (item[1] == "depth") { m_types.push_back(MSK_AOV_DEPTH); m_names.push_back(item[0]); }
+            else if (item[1] == "position") { m_types.push_back(MSK_AOV_POSITION); add3(item[0], "XYZ"); }
+            else if (item[1] == "uv") { m_types.push_back(MSK_AOV_UV); m_names.push_back(item[0] + ".U"); m_names.push_back(item[0] + ".V"); }
+            else if (item[1] == "geo_normal") { m_types.push_back(MSK_AOV_GEO_NORMAL); add3(item[0], "XYZ"); }
+            else if (item[1] == "sh_normal") { m_types.push_back(MSK_AOV_SH_NORMAL); add3(item[0], "XYZ"); }
+            else Throw("Invalid AOV type \"%s\"!", item[1].c_str());
+        }
+        for (auto &[name, obj] : props.objects()) {
+            auto *path = dynamic_cast<GpuPathIntegrator *>(obj.get());
+            if (!path) Throw("Child objects must be of type 'SamplingIntegrator'!");
+            if (m_nested) Throw("The GPU AOV integrator supports one nested integrator");
+            m_nested = path;
+            m_types.push_back(MSK_AOV_INTEGRATOR_RGBA);
+            for (const char *c : { ".R", ".G", ".B", ".A" }) m_names.push_back(name + c);
+        }
+        if (m_names.empty()) Log(Warn, "No AOVs were specified!");
+    }
+    bool render(Scene *scene, Sensor *sensor) override {
+        MskRenderDesc rd{};
+        if (m_nested) m_nested->render_desc(sensor, rd); // the nested tracer's depth / Russian-roulette parameters
+        else {
+            rd.spp = sensor->sampler()->sample_count(); rd.sample_end = rd.spp;
+            rd.max_depth = m_max_depth; rd.rr_depth = m_rr_depth; rd.hide_emitters = m_hide_emitters;
+            rd.base_seed = sensor->sampler()->base_seed(); rd.clear_film = 1;
+        }
+        gpu_render(scene, sensor, rd, m_device >= 0 ? m_device : (m_nested ? m_nested->device() : -1), true, m_types, m_names, m_stats);
+        return true;
+    }
+    const MskStats &stats() const { return m_stats; }
+    const std::vector<std::string> &aov_names() const { return m_names; }
+    MSK_DECLARE_CLASS()
+private:
+    void add3(const std::string &base, const char *suffix) {
+        for (int i = 0; i < 3; ++i) m_names.push_back(base + "." + suffix[i]);
+    }
+    int m_device;
+    std::vector<int32_t> m_types;
+    std::vector<std::string> m_names;
+    ref<GpuPathIntegrator> m_nested;
+    MskStats m_stats{};
+};
+MSK_IMPLEMENT_PLUGIN(GpuAovIntegrator, MonteCarloIntegrator, "aov")
 
 // used by the C API of the host library (capi.cpp)
 bool gpu_path_render_desc(const Integrator *integrator, const Sensor *sensor, MskRenderDesc *rd) {
@@ -122,10 +198,9 @@ bool gpu_path_render_desc(const Integrator *integrator, const Sensor *sensor, Ms
     return true;
 }
 bool gpu_path_stats(const Integrator *integrator, MskStats *stats) {
-    auto *p = dynamic_cast<const GpuPathIntegrator *>(integrator);
-    if (!p) return false;
-    *stats = p->stats();
-    return true;
+    if (auto *p = dynamic_cast<const GpuPathIntegrator *>(integrator)) { *stats = p->stats(); return true; }
+    if (auto *a = dynamic_cast<const GpuAovIntegrator *>(integrator)) { *stats = a->stats(); return true; }
+    return false;
 }
 
 } // namespace misaki

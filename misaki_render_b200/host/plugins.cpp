@@ -634,6 +634,8 @@ public:
             Throw("The \"pixel_format\" parameter must either be equal to \"rgb\" or \"rgba\". Found %s.", pixel_format.c_str());
     }
     void prepare(const std::vector<std::string> &channels) override { // hdrfilm.cpp:30-41
+        for (size_t i = 1; i < channels.size(); ++i)
+            if (channels[i] == channels[i - 1]) Throw("Film::prepare(): duplicate channel name \"%s\"", channels[i].c_str());
         m_channels = channels;
         m_storage.assign((size_t) m_width * m_height * channels.size(), 0.f);
     }
@@ -650,13 +652,20 @@ public:
     }
     void develop() override { // hdrfilm.cpp:92-112
         if (m_dest_file.empty()) Throw("Destination file not specified, cannot develop.");
-        if (m_channels.size() != 5) Throw("HDRFilm::develop: expected the X, Y, Z, A, W channels");
-        std::vector<float> rgba((size_t) m_width * m_height * 4);
-        develop_xyzaw(m_storage.data(), (size_t) m_width * m_height, rgba.data());
+        if (m_channels.size() < 5) Throw("HDRFilm::develop: expected the X, Y, Z, A, W channels");
+        const size_t nch = m_channels.size();
+        std::vector<std::string> names = { "R", "G", "B", "A" }; // hdrfilm.cpp:52-59: RGBA, then the AOV channels
+        names.insert(names.end(), m_channels.begin() + 5, m_channels.end());
+        std::vector<float> image((size_t) m_width * m_height * (nch - 1));
+        develop_channels(m_storage.data(), (size_t) m_width * m_height, nch, image.data());
         Log(Info, "Developing \"%s\" ..", m_dest_file.c_str());
-        if (m_pfm) write_pfm_rgb(m_dest_file, rgba.data(), m_width, m_height);
-        else write_exr_rgba(m_dest_file, rgba.data(), m_width, m_height);
+        if (!m_pfm) { write_exr_channels(m_dest_file, names, image.data(), m_width, m_height); return; }
+        std::vector<float> rgba((size_t) m_width * m_height * 4); // PFM holds RGB only
+        for (size_t i = 0; i < (size_t) m_width * m_height; ++i)
+            for (int c = 0; c < 4; ++c) rgba[i * 4 + c] = image[i * (nch - 1) + c];
+        write_pfm_rgb(m_dest_file, rgba.data(), m_width, m_height);
     }
+    const std::vector<std::string> &channels() const { return m_channels; }
     const std::vector<float> &storage() const { return m_storage; }
     const std::string &destination() const { return m_dest_file; }
     MSK_DECLARE_CLASS()

@@ -220,7 +220,10 @@ private:
 
 // HDRFilm::image: XYZAW -> RGBA (hdrfilm.cpp:48-90); image writers (OpenEXR scanline, uncompressed; PFM)
 void develop_xyzaw(const float *film, size_t npixels, float *rgba);
+void develop_channels(const float *film, size_t npixels, size_t nchannels, float *out); // with AOV channels (/ W)
 void write_exr_rgba(const std::string &filename, const float *rgba, uint32_t width, uint32_t height);
+void write_exr_channels(const std::string &filename, const std::vector<std::string> &names, const float *pixels, uint32_t width,
+                        uint32_t height);
 void write_pfm_rgb(const std::string &filename, const float *rgba, uint32_t width, uint32_t height);
 
 // rgb2spec (reference ext/rgb2spec/rgb2spec.c:12-47,77-119 through src/librender/srgb.cpp:11-30)

@@ -145,8 +145,9 @@ def srgb_model_fetch(rgb) -> np.ndarray:
     return out
 
 
-def read_exr_rgba(path):
-    """Reader for the uncompressed scanline RGBA float EXR files host/imageio.cpp writes (tests only)."""
+def read_exr_channels(path):
+    """Reader for the uncompressed scanline float EXR files host/imageio.cpp writes (tests only).
+    Returns (channel names in file order, H x W x C float32)."""
     import struct
     raw = Path(path).read_bytes()
     assert struct.unpack_from("<i", raw, 0)[0] == 20000630
@@ -157,13 +158,24 @@ def read_exr_rgba(path):
         (size,) = struct.unpack_from("<i", raw, pos); pos += 4
         attrs[name] = (typ, raw[pos:pos + size]); pos += size
     pos += 1
+    names, cl, cp = [], attrs["channels"][1], 0
+    while cl[cp] != 0:
+        e = cl.index(b"\0", cp); names.append(cl[cp:e].decode()); cp = e + 1
+        assert struct.unpack_from("<i", cl, cp)[0] == 2  # FLOAT
+        cp += 16
     x0, y0, x1, y1 = struct.unpack("<4i", attrs["dataWindow"][1])
     w, h = x1 - x0 + 1, y1 - y0 + 1
     assert attrs["compression"][1] == b"\0"
     offsets = struct.unpack_from(f"<{h}Q", raw, pos)
-    img = np.zeros((h, w, 4), np.float32)
-    for y, off in enumerate(offsets):
+    n = len(names)
+    img = np.zeros((h, w, n), np.float32)
+    for off in offsets:
         yy, nbytes = struct.unpack_from("<ii", raw, off)
-        row = np.frombuffer(raw, dtype="<f4", count=w * 4, offset=off + 8).reshape(4, w)  # A B G R
-        img[yy - y0, :, 3], img[yy - y0, :, 2], img[yy - y0, :, 1], img[yy - y0, :, 0] = row[0], row[1], row[2], row[3]
-    return img
+        assert nbytes == w * n * 4
+        img[yy - y0] = np.frombuffer(raw, dtype="<f4", count=w * n, offset=off + 8).reshape(n, w).T
+    return names, img
+
+
+def read_exr_rgba(path):
+    names, img = read_exr_channels(path)
+    return np.stack([img[..., names.index(c)] for c in "RGBA"], axis=-1)

@@ -906,11 +906,12 @@ inline float eval_discretized(const MskCamera &cam, float x) { // rfilter.h:13-1
 
 struct Block {
     int ox, oy, sx, sy, border;
-    std::vector<float> data; // (sy+2b) x (sx+2b) x 5
+    int nch = 5;
+    std::vector<float> data; // (sy+2b) x (sx+2b) x nch
 };
 
 // imageblock.cpp:55-114
-void block_put(Block &b, const MskCamera &cam, V2 pos_, const float value[5]) {
+void block_put(Block &b, const MskCamera &cam, V2 pos_, const float *value) {
     float r = cam.filter_radius;
     int w = b.sx + 2 * b.border, h = b.sy + 2 * b.border;
     float px = pos_.x - 0.5f - (b.ox - b.border), py = pos_.y - 0.5f - (b.oy - b.border);
@@ -920,10 +921,10 @@ void block_put(Block &b, const MskCamera &cam, V2 pos_, const float value[5]) {
     for (int x = lox, i = 0; x <= hix; ++x) wx[i++] = eval_discretized(cam, x - px);
     for (int y = loy, i = 0; y <= hiy; ++y) wy[i++] = eval_discretized(cam, y - py);
     for (int y = loy, yr = 0; y <= hiy; ++y, ++yr) {
-        float *dest = b.data.data() + (y * (size_t) w + lox) * 5;
+        float *dest = b.data.data() + (y * (size_t) w + lox) * b.nch;
         for (int x = lox, xr = 0; x <= hix; ++x, ++xr) {
             float weight = wx[xr] * wy[yr];
-            for (int k = 0; k < 5; ++k) *dest++ += weight * value[k];
+            for (int k = 0; k < b.nch; ++k) *dest++ += weight * value[k];
         }
     }
 }
@@ -937,7 +938,7 @@ void film_put(float *film, int W, int H, const Block &b) {
         for (int x = 0; x < w; ++x) {
             int fx = b.ox - b.border + x;
             if (fx < 0 || fx >= W) continue;
-            for (int k = 0; k < 5; ++k) film[((size_t) fy * W + fx) * 5 + k] += b.data[((size_t) y * w + x) * 5 + k];
+            for (int k = 0; k < b.nch; ++k) film[((size_t) fy * W + fx) * b.nch + k] += b.data[((size_t) y * w + x) * b.nch + k];
         }
     }
 }
@@ -1102,11 +1103,60 @@ int orc_camera_rays(OrcScene *s, const float *samples /* n x 3: px, py, waveleng
     return 0;
 }
 
-int orc_render(OrcScene *s, const MskRenderDesc *rd, float *film, int nthreads, OrcStats *stats) {
+// AOVIntegrator::sample, integrators/aov.cpp:87-144.  `types` lists the AOVs in channel order; an
+// MSK_AOV_INTEGRATOR_RGBA entry is the nested PathTracer (aov.cpp:124-140).  Deviations (oracle.h): fields of a
+// missed ray read 0 (uninitialised in the reference, scene.cpp:247-251), and without a nested integrator the
+// returned spectrum is 0 (uninitialised `result`, aov.cpp:91,142).
+static int aov_channel_count(const int32_t *types, uint32_t ntypes) {
+    static const int per[6] = { 1, 3, 2, 3, 3, 4 };
+    int n = 0;
+    for (uint32_t i = 0; i < ntypes; ++i) {
+        if (types[i] < 0 || types[i] > 5) return -1;
+        n += per[types[i]];
+    }
+    return n;
+}
+
+static Spec aov_sample(const OScene &sc, Sampler &sampler, const Ray &ray, const PathParams &pp, RayCounters &rc,
+                       const int32_t *types, uint32_t ntypes, float *aovs) {
+    SceneInteraction si = ray_intersect(sc, ray, rc); // aov.cpp:90
+    if (!si.is_valid()) { si.p = V3{ 0, 0, 0 }; si.n = V3{ 0, 0, 0 }; si.uv = V2{ 0, 0 }; si.sh_frame.n = V3{ 0, 0, 0 }; }
+    Spec result(0.f);
+    size_t ctr = 0;
+    for (uint32_t i = 0; i < ntypes; ++i) {
+        switch (types[i]) {
+            case MSK_AOV_DEPTH: *aovs++ = si.t == Infinity ? 0.f : si.t; break;
+            case MSK_AOV_POSITION: *aovs++ = si.p.x; *aovs++ = si.p.y; *aovs++ = si.p.z; break;
+            case MSK_AOV_UV: *aovs++ = si.uv.x; *aovs++ = si.uv.y; break;
+            case MSK_AOV_GEO_NORMAL: *aovs++ = si.n.x; *aovs++ = si.n.y; *aovs++ = si.n.z; break;
+            case MSK_AOV_SH_NORMAL: *aovs++ = si.sh_frame.n.x; *aovs++ = si.sh_frame.n.y; *aovs++ = si.sh_frame.n.z; break;
+            case MSK_AOV_INTEGRATOR_RGBA: {
+                Spec spec = path_sample(sc, sampler, ray, pp, rc);
+                float xyz[3];
+                spectrum_to_xyz(spec, ray.wavelengths, xyz);
+                // xyz_to_srgb, spectrum.h:138-143
+                *aovs++ = 3.240479f * xyz[0] + -1.537150f * xyz[1] + -0.498535f * xyz[2];
+                *aovs++ = -0.969256f * xyz[0] + 1.875991f * xyz[1] + 0.041556f * xyz[2];
+                *aovs++ = 0.055648f * xyz[0] + -0.204043f * xyz[1] + 1.057311f * xyz[2];
+                *aovs++ = 1.f;
+                if (ctr == 0) result = spec;
+                ctr++;
+            } break;
+        }
+    }
+    return result;
+}
+
+// SamplingIntegrator::render, integrator.cpp:31-126.  ntypes == 0 and types == nullptr: the plain PathTracer.
+static int render_impl(OrcScene *s, const MskRenderDesc *rd, const int32_t *types, uint32_t ntypes, bool aov, float *film, int nthreads,
+                       OrcStats *stats) {
     if (!s || !rd || !film) return fail("null argument");
     const OScene &sc = s->sc;
     const int W = (int) sc.cam.width, H = (int) sc.cam.height;
-    if (rd->clear_film) std::fill(film, film + (size_t) W * H * 5, 0.f);
+    int extra = aov ? aov_channel_count(types, ntypes) : 0;
+    if (extra < 0) return fail("invalid AOV type");
+    const int nch = 5 + extra;
+    if (rd->clear_film) std::fill(film, film + (size_t) W * H * nch, 0.f);
     PathParams pp{ rd->max_depth, rd->rr_depth, rd->hide_emitters != 0 };
     const int border = (int) std::ceil(sc.cam.filter_radius - .5f); // rfilter.cpp:22
     auto blocks = spiral_blocks(W, H, 32);                            // imageblock.h:8, integrator.cpp:48
@@ -1118,13 +1168,14 @@ int orc_render(OrcScene *s, const MskRenderDesc *rd, float *film, int nthreads, 
         RayCounters rc;
         Sampler sampler;
         sampler.base_seed = rd->base_seed;
+        std::vector<float> aovs((size_t) nch);
         for (;;) {
             size_t bi = next.fetch_add(1);
             if (bi >= blocks.size()) break;
             const BlockDesc &bd = blocks[bi];
             Block &b = done[bi];
-            b.ox = bd.ox; b.oy = bd.oy; b.sx = bd.sx; b.sy = bd.sy; b.border = border;
-            b.data.assign((size_t) (bd.sx + 2 * border) * (bd.sy + 2 * border) * 5, 0.f);
+            b.ox = bd.ox; b.oy = bd.oy; b.sx = bd.sx; b.sy = bd.sy; b.border = border; b.nch = nch;
+            b.data.assign((size_t) (bd.sx + 2 * border) * (bd.sy + 2 * border) * nch, 0.f);
             // render_block, integrator.cpp:82-101
             for (int y = 0; y < bd.sy; ++y)
                 for (int x = 0; x < bd.sx; ++x) {
@@ -1138,11 +1189,11 @@ int orc_render(OrcScene *s, const MskRenderDesc *rd, float *film, int nthreads, 
                         float wavelength_sample = sampler.next1d();
                         sampler.next2d(); // aperture sample: consumed, unused
                         auto [ray, ray_weight] = camera_sample_ray(sc.cam, wavelength_sample, position_sample);
-                        Spec result = path_sample(sc, sampler, ray, pp, rc) * ray_weight;
-                        float aovs[5];
-                        spectrum_to_xyz(result, ray.wavelengths, aovs);
+                        Spec result = (aov ? aov_sample(sc, sampler, ray, pp, rc, types, ntypes, aovs.data() + 5)
+                                           : path_sample(sc, sampler, ray, pp, rc)) * ray_weight;
+                        spectrum_to_xyz(result, ray.wavelengths, aovs.data());
                         aovs[3] = 1.f; aovs[4] = 1.f;
-                        block_put(b, sc.cam, position_sample, aovs);
+                        block_put(b, sc.cam, position_sample, aovs.data());
                     }
                 }
         }
@@ -1163,6 +1214,18 @@ int orc_render(OrcScene *s, const MskRenderDesc *rd, float *film, int nthreads, 
         stats->threads      = nthreads;
     }
     return 0;
+}
+
+int orc_render(OrcScene *s, const MskRenderDesc *rd, float *film, int nthreads, OrcStats *stats) {
+    return render_impl(s, rd, nullptr, 0, false, film, nthreads, stats);
+}
+
+int orc_aov_channels(const int32_t *types, uint32_t ntypes) { return aov_channel_count(types, ntypes); }
+
+// film: H x W x (5 + orc_aov_channels) floats
+int orc_render_aov(OrcScene *s, const MskRenderDesc *rd, const int32_t *types, uint32_t ntypes, float *film, int nthreads, OrcStats *stats) {
+    if (ntypes && !types) return fail("null argument");
+    return render_impl(s, rd, types, ntypes, true, film, nthreads, stats);
 }
 
 // Per-sample radiance for a list of (pixel, sample) pairs: lets the tests compare individual

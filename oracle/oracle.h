@@ -20,6 +20,8 @@ int  orc_occluded(OrcScene *s, const MskRay *rays, uint8_t *occ, size_t n);
 int  orc_intersect_margin(OrcScene *s, const MskRay *rays, float *second_t, float *min_bary, size_t n);
 int  orc_camera_rays(OrcScene *s, const float *samples, MskRay *rays, size_t n);
 int  orc_render(OrcScene *s, const MskRenderDesc *rd, float *film, int nthreads, OrcStats *stats);
+int  orc_aov_channels(const int32_t *types, uint32_t ntypes);
+int  orc_render_aov(OrcScene *s, const MskRenderDesc *rd, const int32_t *types, uint32_t ntypes, float *film, int nthreads, OrcStats *stats);
 int  orc_trace_samples(OrcScene *s, const MskRenderDesc *rd, const uint32_t *pixel_sample, float *out, size_t n);
 void orc_develop(const float *film, float *rgba, size_t npixels);
 void orc_gaussian_filter(float stddev, float *radius, float table[33]);

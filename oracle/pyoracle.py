@@ -42,6 +42,9 @@ def lib() -> C.CDLL:
         L.orc_intersect_margin.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]
         L.orc_camera_rays.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]
         L.orc_render.argtypes = [C.c_void_p, C.POINTER(capi.MskRenderDesc), C.c_void_p, C.c_int, C.POINTER(OrcStats)]
+        L.orc_aov_channels.argtypes = [C.c_void_p, C.c_uint32]
+        L.orc_render_aov.argtypes = [C.c_void_p, C.POINTER(capi.MskRenderDesc), C.c_void_p, C.c_uint32, C.c_void_p, C.c_int,
+                                     C.POINTER(OrcStats)]
         L.orc_trace_samples.argtypes = [C.c_void_p, C.POINTER(capi.MskRenderDesc), C.c_void_p, C.c_void_p, C.c_size_t]
         L.orc_develop.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
         L.orc_develop.restype = None
@@ -129,6 +132,18 @@ class OracleScene:
             film = np.zeros((self.height, self.width, 5), dtype=np.float32)
         st = OrcStats()
         if self.L.orc_render(self.h, C.byref(rd), film.ctypes.data, nthreads, C.byref(st)) != 0:
+            raise RuntimeError(self.L.orc_last_error().decode())
+        return film, st
+
+    def render_aov(self, rd, types, nthreads=0):
+        """AOVIntegrator restatement: film H x W x (5 + channels)."""
+        ids = np.asarray([capi.AOV_NAMES[t] if isinstance(t, str) else int(t) for t in types], dtype=np.int32)
+        nch = self.L.orc_aov_channels(ids.ctypes.data, len(ids))
+        if nch < 0:
+            raise RuntimeError("invalid AOV type")
+        film = np.zeros((self.height, self.width, 5 + nch), dtype=np.float32)
+        st = OrcStats()
+        if self.L.orc_render_aov(self.h, C.byref(rd), ids.ctypes.data, len(ids), film.ctypes.data, nthreads, C.byref(st)) != 0:
             raise RuntimeError(self.L.orc_last_error().decode())
         return film, st
 
