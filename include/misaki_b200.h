@@ -40,7 +40,7 @@
 extern "C" {
 #endif
 
-#define MSK_ABI_VERSION 3
+#define MSK_ABI_VERSION 4
 
 typedef enum {
     MSK_OK            = 0,
@@ -57,7 +57,8 @@ typedef enum {
     MSK_SPEC_SRGB     = 1, /* spectra/srgb.cpp:14-23         rgb2spec coeffs c[3]       */
     MSK_SPEC_SRGB_D65 = 2, /* spectra/srgb_d65.cpp:14-36     coeffs c[3] x table        */
     MSK_SPEC_REGULAR  = 3, /* spectra/regular.cpp:73-91      table (also "d65")         */
-    MSK_SPEC_SRGB_UNBOUNDED = 4 /* builder decision for conductor eta/k: value * srgb_model_eval(c) */
+    MSK_SPEC_SRGB_UNBOUNDED = 4, /* builder decision for conductor eta/k: value * srgb_model_eval(c) */
+    MSK_SPEC_CHECKERBOARD = 5 /* textures/checkerboard.cpp:11-31: selects child0 / child1 by the surface uv */
 } MskSpectrumKind;
 
 typedef struct {
@@ -68,6 +69,9 @@ typedef struct {
     uint32_t table_size;   /*   number of entries (>= 2) */
     float    lambda_min;   /*   wavelength of entry 0 */
     float    lambda_max;   /*   wavelength of the last entry */
+    int32_t  child0, child1; /* CHECKERBOARD: spectrum ids of "color0" / "color1" (both < this spectrum's own id) */
+    float    to_uv[6];     /* CHECKERBOARD: rows 0,1 x columns 0..2 of the "to_uv" 4x4 (Transform4f::extract,
+                            * transform.h:142-148): uv' = (m00 u + m01 v + m02, m10 u + m11 v + m12) */
 } MskSpectrum;
 
 /* ---- BSDFs (include/misaki/render/bsdf.h:82-126, src/librender/bsdfs/ *.cpp) ---- */

@@ -26,12 +26,12 @@ EXPORTED_SYMBOLS = [
 ]
 
 # enums
-SPEC_UNIFORM, SPEC_SRGB, SPEC_SRGB_D65, SPEC_REGULAR, SPEC_SRGB_UNBOUNDED = range(5)
+SPEC_UNIFORM, SPEC_SRGB, SPEC_SRGB_D65, SPEC_REGULAR, SPEC_SRGB_UNBOUNDED, SPEC_CHECKERBOARD = range(6)
 BSDF_DIFFUSE, BSDF_CONDUCTOR, BSDF_ROUGHCONDUCTOR, BSDF_ROUGHDIELECTRIC, BSDF_DIELECTRIC = range(5)
 EMITTER_AREA, EMITTER_CONSTANT = range(2)
 RENDER_STAGE_TIMERS = 1
 RENDER_TRAVERSAL_STATS = 2
-ABI_VERSION = 3
+ABI_VERSION = 4
 AOV_DEPTH, AOV_POSITION, AOV_UV, AOV_GEO_NORMAL, AOV_SH_NORMAL, AOV_INTEGRATOR_RGBA = range(6)
 AOV_NAMES = {"depth": AOV_DEPTH, "position": AOV_POSITION, "uv": AOV_UV, "geo_normal": AOV_GEO_NORMAL, "sh_normal": AOV_SH_NORMAL,
              "integrator": AOV_INTEGRATOR_RGBA}
@@ -45,7 +45,8 @@ class MskError(RuntimeError):
 
 class MskSpectrum(C.Structure):
     _fields_ = [("kind", C.c_int32), ("c", C.c_float * 3), ("value", C.c_float), ("table_offset", C.c_uint32),
-                ("table_size", C.c_uint32), ("lambda_min", C.c_float), ("lambda_max", C.c_float)]
+                ("table_size", C.c_uint32), ("lambda_min", C.c_float), ("lambda_max", C.c_float),
+                ("child0", C.c_int32), ("child1", C.c_int32), ("to_uv", C.c_float * 6)]
 
 
 class MskBsdf(C.Structure):

@@ -138,7 +138,9 @@ int msk_gpu_scene_create(MskCtx *ctx, const MskSceneDesc *d, MskScene **out) {
         return fail(MSK_ERR_UNSUPPORTED, "filter radius %g outside (0, 4]", d->camera.filter_radius);
     for (uint32_t i = 0; i < d->nspectra; ++i) {
         const MskSpectrum &s = d->spectra[i];
-        if (s.kind < 0 || s.kind > MSK_SPEC_SRGB_UNBOUNDED) return fail(MSK_ERR_ARG, "spectrum %u: unknown kind %d", i, s.kind);
+        if (s.kind < 0 || s.kind > MSK_SPEC_CHECKERBOARD) return fail(MSK_ERR_ARG, "spectrum %u: unknown kind %d", i, s.kind);
+        if (s.kind == MSK_SPEC_CHECKERBOARD && (s.child0 < 0 || s.child1 < 0 || (uint32_t) s.child0 >= i || (uint32_t) s.child1 >= i))
+            return fail(MSK_ERR_ARG, "spectrum %u: checkerboard children (%d, %d) must be spectra declared before it", i, s.child0, s.child1);
         if (s.kind == MSK_SPEC_REGULAR || s.kind == MSK_SPEC_SRGB_D65) {
             if (s.table_size < 2 || (uint64_t) s.table_offset + s.table_size > d->ntable_floats)
                 return fail(MSK_ERR_ARG, "spectrum %u: table out of range", i);
@@ -274,6 +276,12 @@ int msk_gpu_scene_create(MskCtx *ctx, const MskSceneDesc *d, MskScene **out) {
             // regular.cpp:38-39,58: interval size in double, its reciprocal stored in a float
             double range = double(m.lambda_max) - double(m.lambda_min), interval = range / (m.table_size - 1);
             o.inv_interval = float(1. / interval);
+        }
+        if (m.kind == MSK_SPEC_CHECKERBOARD) {
+            o.table_offset = (uint32_t) m.child0; o.table_size = (uint32_t) m.child1;
+            o.c0 = m.to_uv[0]; o.c1 = m.to_uv[1]; o.c2 = m.to_uv[2];
+            o.value = m.to_uv[3]; o.lambda_min = m.to_uv[4]; o.inv_interval = m.to_uv[5];
+            s->d.has_textures = 1;
         }
     }
     if ((rc = upload(s, spectra.data(), spectra.size(), &s->d.spectra))) return bail(rc);

@@ -39,7 +39,7 @@ struct DMeshInfo {
     uint32_t cdf_offset;  // emitter meshes: first entry of the (ntris+1)-entry area CDF in DScene::cdfs
 };
 
-struct DSpectrum {
+struct DSpectrum { // MSK_SPEC_CHECKERBOARD reuses the fields: see texture_resolve (msk_shading.cuh)
     int32_t  kind;
     float    c0, c1, c2;
     float    value;
@@ -74,6 +74,7 @@ struct DScene {
     float    env_radius;
     uint32_t nmeshes;
     uint32_t bsdf_type_mask; // bit t: some mesh uses a BSDF of MskBsdfType t
+    uint32_t has_textures;   // some spectrum is uv-dependent (MSK_SPEC_CHECKERBOARD): resolve ids per surface point
     DCamera  cam;
 };
 

@@ -297,7 +297,9 @@ __global__ void __launch_bounds__(128, shade_min_blocks(KEY)) k_shade(const __gr
 
             if (KEY == 0 || (KEY < 0 && key == 0)) { // miss: path.cpp:34-41 (depth 1) / :90-98,:103-108 (BSDF-sampled ray escaped)
                 if (sc.environment >= 0) {
-                    float4 le = spectrum_eval(sc, sc.emitters[sc.environment].radiance, wl);
+                    int radiance = sc.emitters[sc.environment].radiance; // constant.cpp:79-81; a miss carries no uv
+                    if (sc.has_textures) radiance = texture_resolve(sc, radiance, 0.f, 0.f);
+                    float4 le = spectrum_eval(sc, radiance, wl);
                     if (depth == 1) { if (!bp.hide_emitters) { L = T * le; add_L = true; } }
                     else { L = T * le * mis_weight(prev_pdf, prev_delta ? 0.f : stale_pdf); add_L = true; }
                 }
@@ -308,7 +310,9 @@ __global__ void __launch_bounds__(128, shade_min_blocks(KEY)) k_shade(const __gr
                 const Surface sf = make_surface(sc, mi, __float_as_uint(hit.w), hit.y, hit.z);
                 const V3 wi = to_local(sf.sh, -rdir);
                 if (mi.emitter >= 0) { // area.cpp:51-54
-                    float4 le = wi.z > 0.f ? spectrum_eval(sc, sc.emitters[mi.emitter].radiance, wl) : f4(0.f);
+                    int radiance = sc.emitters[mi.emitter].radiance;
+                    if (sc.has_textures) radiance = texture_resolve(sc, radiance, sf.uvx, sf.uvy);
+                    float4 le = wi.z > 0.f ? spectrum_eval(sc, radiance, wl) : f4(0.f);
                     if (depth == 1) { // path.cpp:44-47
                         if (!bp.hide_emitters) { L = T * le; add_L = true; }
                     } else {          // path.cpp:82-88,103-108 with ds.set_query (records.cpp:7-14)
@@ -329,7 +333,8 @@ __global__ void __launch_bounds__(128, shade_min_blocks(KEY)) k_shade(const __gr
                 }
                 if (alive && bp.max_depth > 0 && depth >= bp.max_depth) alive = false; // path.cpp:48-49
                 if (alive) {
-                    const MskBsdf bsdf = sc.bsdfs[mi.bsdf];
+                    MskBsdf bsdf = sc.bsdfs[mi.bsdf];
+                    if (sc.has_textures) bsdf_resolve_textures(sc, bsdf, sf.uvx, sf.uvy); // Texture::eval(si), checkerboard.cpp:25-31
                     float new_stale = 0.f;
                     const float tmin_spawn = (1.f + max_abs(sf.p)) * kRayEpsilon; // interaction.h:40-44, scene.cpp:91-93
                     if (bsdf_is_smooth(TYPE >= 0 ? TYPE : bsdf.type)) { // path.cpp:56-67

@@ -153,6 +153,28 @@ __device__ __forceinline__ float4 spectrum_eval(const DScene &sc, int id, float4
     return f4(0.f);
 }
 
+// textures/checkerboard.cpp:16-31: a uv-dependent texture only SELECTS one of its children, so it is resolved to
+// the id of a plain spectrum once per surface point (children have smaller ids: the loop terminates).
+// DSpectrum of a checkerboard: table_offset/table_size = child ids, (c0 c1 c2 | value lambda_min inv_interval) = the
+// two rows of Transform3f "to_uv"; the products are kept un-contracted like the oracle's.
+__device__ __forceinline__ int texture_resolve(const DScene &sc, int id, float u, float v) {
+    while (id >= 0) {
+        const DSpectrum &s = sc.spectra[id];
+        if (s.kind != MSK_SPEC_CHECKERBOARD) break;
+        float tu = __fadd_rn(__fadd_rn(__fmul_rn(s.c0, u), __fmul_rn(s.c1, v)), s.c2);
+        float tv = __fadd_rn(__fadd_rn(__fmul_rn(s.value, u), __fmul_rn(s.lambda_min, v)), s.inv_interval);
+        tu -= floorf(tu); tv -= floorf(tv);
+        id = ((tu > .5f) == (tv > .5f)) ? (int) s.table_offset : (int) s.table_size;
+    }
+    return id;
+}
+__device__ __forceinline__ void bsdf_resolve_textures(const DScene &sc, MskBsdf &b, float u, float v) {
+    b.reflectance = texture_resolve(sc, b.reflectance, u, v);
+    b.transmittance = texture_resolve(sc, b.transmittance, u, v);
+    b.eta = texture_resolve(sc, b.eta, u, v);
+    b.k = texture_resolve(sc, b.k, u, v);
+}
+
 // spectrum.h:83-115; the 4-wide mean adds (v0+v2)+(v1+v3) like Eigen's packet reduction
 __device__ __forceinline__ void spectrum_to_xyz(const DScene &sc, float4 value, float4 wl, float &X, float &Y, float &Z) {
     float l[4] = { wl.x, wl.y, wl.z, wl.w }, v[4] = { value.x, value.y, value.z, value.w };
@@ -509,16 +531,26 @@ __device__ __forceinline__ NeeSample sample_emitter_direct(const DScene &sc, V3 
         float dp = fabsf(dot(d, ns));
         float pdf = mi.inv_area * ((dp != 0.f) ? dist2 / dp : 0.f);
         r.d = d; r.dist = dist;
+        int radiance = em.radiance;
+        if (sc.has_textures) { // ps.uv, mesh.cpp:114-119: the warped sample, or the interpolated texcoords
+            float u = bx, v = by;
+            if (mi.flags & 2u) {
+                float4 a1 = __ldg(vp + 2 * (size_t) i0 + 1), b1 = __ldg(vp + 2 * (size_t) i1 + 1), c1v = __ldg(vp + 2 * (size_t) i2 + 1);
+                float w0 = 1.f - bx - by;
+                u = a1.z * w0 + b1.z * bx + c1v.z * by; v = a1.w * w0 + b1.w * bx + c1v.w * by;
+            }
+            radiance = texture_resolve(sc, radiance, u, v);
+        }
         // pdf_emitter_direct(ds) of this record: shape.cpp:80-86
         r.stale_pdf = mi.inv_area * ((dp != 0.f) ? (dist * dist) / dp : 0.f) * (ne > 1 ? 1.f / (float) ne : 1.f);
         if (dot(d, ns) < 0.f && pdf != 0.f) {
-            r.value = spectrum_eval(sc, em.radiance, wl) / pdf;
+            r.value = spectrum_eval(sc, radiance, wl) / pdf;
             r.pdf = pdf;
         }
     } else { // constant.cpp:55-73
         V3 d = square_to_uniform_sphere(sx, sy);
         r.d = d; r.dist = 2.f * sc.env_radius; r.pdf = kInvFourPi;
-        r.value = spectrum_eval(sc, em.radiance, wl) / r.pdf;
+        r.value = spectrum_eval(sc, sc.has_textures ? texture_resolve(sc, em.radiance, 0.f, 0.f) : em.radiance, wl) / r.pdf;
         r.stale_pdf = kInvFourPi * (ne > 1 ? 1.f / (float) ne : 1.f);
     }
     if (ne > 1) { r.pdf *= sel; r.value = r.value * (float) ne; }

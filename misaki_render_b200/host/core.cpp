@@ -205,6 +205,17 @@ static Vector3f normalized(Vector3f v) {
     float n = std::sqrt(v.x * v.x + v.y * v.y + v.z * v.z);
     return n > 0.f ? Vector3f{ v.x / n, v.y / n, v.z / n } : v;
 }
+Transform4f Transform4f::rotate(const Vector3f &axis_, float angle) { // transform.h:163-167 (Eigen::AngleAxisf: Rodrigues, radians)
+    Vector3f a = normalized(axis_);
+    float s = std::sin(angle), c = std::cos(angle), t = 1.f - c;
+    float r[16] = { t * a.x * a.x + c,       t * a.x * a.y - s * a.z, t * a.x * a.z + s * a.y, 0,
+                    t * a.x * a.y + s * a.z, t * a.y * a.y + c,       t * a.y * a.z - s * a.x, 0,
+                    t * a.x * a.z - s * a.y, t * a.y * a.z + s * a.x, t * a.z * a.z + c,       0,
+                    0, 0, 0, 1 };
+    float ri[16]; // the inverse of a rotation is its transpose
+    for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) ri[i * 4 + j] = r[j * 4 + i];
+    return Transform4f(r, ri);
+}
 static Vector3f cross(Vector3f a, Vector3f b) { return Vector3f{ a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x }; }
 Transform4f Transform4f::lookat(const Vector3f &origin, const Vector3f &target, const Vector3f &up) { // transform.h:170-179
     Vector3f dir = normalized(Vector3f{ target.x - origin.x, target.y - origin.y, target.z - origin.z });

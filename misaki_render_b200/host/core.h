@@ -153,6 +153,7 @@ struct Transform4f {
     bool has_nan() const;
     static Transform4f translate(const Vector3f &v);
     static Transform4f scale(const Vector3f &v);
+    static Transform4f rotate(const Vector3f &axis, float angle_radians);
     static Transform4f lookat(const Vector3f &origin, const Vector3f &target, const Vector3f &up);
     static Transform4f perspective(float fov, float near_, float far_);
 };

@@ -240,7 +240,30 @@ private:
     ref<Texture> m_d65;
 };
 
+class CheckerboardTexture final : public Texture { // textures/checkerboard.cpp:8-46
+public:
+    explicit CheckerboardTexture(const Properties &props) : Texture(props) {
+        m_color0 = props.texture("color0", .4f);
+        m_color1 = props.texture("color1", .2f);
+        m_to_uv = props.transform("to_uv", Transform4f());
+    }
+    int describe(GpuSceneBuilder &b) const override {
+        MskSpectrum s = blank_spectrum(MSK_SPEC_CHECKERBOARD);
+        s.child0 = m_color0->describe(b); // children first: their ids are smaller than the checkerboard's
+        s.child1 = m_color1->describe(b);
+        for (int r = 0; r < 2; ++r) // Transform4f::extract(): the top-left 3x3 (transform.h:142-148)
+            for (int c = 0; c < 3; ++c) s.to_uv[r * 3 + c] = m_to_uv.m[r * 4 + c];
+        return b.add_spectrum(s);
+    }
+    float mean() const override { return m_color0->mean() + m_color1->mean(); } // (sic) checkerboard.cpp:44
+    MSK_DECLARE_CLASS()
+private:
+    ref<Texture> m_color0, m_color1;
+    Transform4f m_to_uv;
+};
+
 MSK_IMPLEMENT_PLUGIN(UniformSpectrum, Texture, "uniform")
+MSK_IMPLEMENT_PLUGIN(CheckerboardTexture, Texture, "checkerboard")
 MSK_IMPLEMENT_PLUGIN(RegularSpectrum, Texture, "regular")
 MSK_IMPLEMENT_PLUGIN(D65Spectrum, Texture, "d65")
 MSK_IMPLEMENT_PLUGIN(SRGBReflectanceSpectrum, Texture, "srgb")
@@ -456,21 +479,28 @@ MSK_IMPLEMENT_PLUGIN(AreaLight, Emitter, "area")
 MSK_IMPLEMENT_PLUGIN(ConstantBackgroundEmitter, Emitter, "constant")
 
 // =========================================================================================== obj shape
-static int to_uint(const std::string &str) { // shapes/obj.cpp:11-17
+static int to_uint(const std::string &str) { // shapes/obj.cpp:11-17; a leading '-' (relative index) is kept signed
     char *end_ptr = nullptr;
-    unsigned int result = (unsigned int) strtoul(str.c_str(), &end_ptr, 10);
+    long result = strtol(str.c_str(), &end_ptr, 10);
     if (*end_ptr != '\0') Throw("Could not parse integer value \"%s\"", str.c_str());
     return (int) result;
 }
 struct OBJVertex { // shapes/obj.cpp:19-38
-    int p = -1, n = -1, uv = -1;
+    int p = -1, n = -1, uv = -1; // 1-based; -1 = absent (after make_absolute)
     OBJVertex() = default;
+    // OBJ relative indices: -k names the k-th most recent element at the time of the face line
+    void make_absolute(size_t np, size_t nuv, size_t nn, bool has_uv, bool has_n) {
+        if (p < 0) p = (int) np + 1 + p;
+        if (has_uv && uv < 0) uv = (int) nuv + 1 + uv;
+        if (has_n && n < 0) n = (int) nn + 1 + n;
+    }
+    bool has_uv_ = false, has_n_ = false;
     explicit OBJVertex(const std::string &s) {
         auto tokens = string::tokenize(s, "/", true);
         if (tokens.size() < 1 || tokens.size() > 3) Throw("Invalid vertex data: \"%s\"", s.c_str());
         p = to_uint(tokens[0]);
-        if (tokens.size() >= 2 && !tokens[1].empty()) uv = to_uint(tokens[1]);
-        if (tokens.size() >= 3 && !tokens[2].empty()) n = to_uint(tokens[2]);
+        if (tokens.size() >= 2 && !tokens[1].empty()) { uv = to_uint(tokens[1]); has_uv_ = true; }
+        if (tokens.size() >= 3 && !tokens[2].empty()) { n = to_uint(tokens[2]); has_n_ = true; }
     }
     bool operator==(const OBJVertex &v) const { return v.p == p && v.n == n && v.uv == uv; }
 };
@@ -520,15 +550,20 @@ public:
                 if (len > 0.f) { n.x /= len; n.y /= len; n.z /= len; }
                 normals.push_back(n);
             } else if (prefix == "f") {
-                std::string v1, v2, v3, v4;
-                line >> v1 >> v2 >> v3 >> v4;
-                OBJVertex verts[6];
-                int n_vertices = 3;
-                verts[0] = OBJVertex(v1); verts[1] = OBJVertex(v2); verts[2] = OBJVertex(v3);
-                if (!v4.empty()) { // quad -> (v1 v2 v3) (v4 v1 v3)
-                    verts[3] = OBJVertex(v4); verts[4] = verts[0]; verts[5] = verts[2];
-                    n_vertices = 6;
+                // triangle, quad -> (v1 v2 v3) (v4 v1 v3) as obj.cpp:104-118, and the same fan for n-gons:
+                // (v1 v2 v3) (v4 v1 v3) (v5 v1 v4) ...  (the reference reads at most four corners)
+                std::vector<OBJVertex> corners;
+                std::string tok;
+                while (line >> tok) {
+                    OBJVertex c(tok);
+                    c.make_absolute(vertices.size(), texcoords.size(), normals.size(), c.has_uv_, c.has_n_);
+                    c.has_uv_ = c.has_n_ = false;
+                    corners.push_back(c);
                 }
+                if (corners.size() < 3) Throw("Error while loading OBJ file \"%s\": face with fewer than 3 vertices", m_name.c_str());
+                std::vector<OBJVertex> verts = { corners[0], corners[1], corners[2] };
+                for (size_t j = 3; j < corners.size(); ++j) { verts.push_back(corners[j]); verts.push_back(corners[0]); verts.push_back(corners[j - 1]); }
+                int n_vertices = (int) verts.size();
                 for (int i = 0; i < n_vertices; ++i) {
                     auto it = vertex_map.find(verts[i]);
                     if (it == vertex_map.end()) {

@@ -6,8 +6,15 @@
 //   * children without a name attribute are called _arg_<n> and objects() later returns them in std::map
 //     order (_arg_0, _arg_1, _arg_10, _arg_2, ...), which fixes Scene::m_shapes order == geomID
 //   * <rgb> becomes an "srgb" texture, or "srgb_d65" inside an <emitter> (:269-277,555-559)
-//   * <boolean>, <rotate>, <include>, <alias>, <default> are registered tags with no case in the switch
-//     (:74-90 vs :421-662): they are accepted and IGNORED (a warning is logged here)
+// Front-end completion: <boolean>, <rotate>, <include>, <alias>, <default> are registered tags
+// with no case in the reference's switch (:74-90 vs :421-662), i.e. silently dropped there.  They are implemented
+// here with the semantics of the Mitsuba 2 loader the reference's xml.cpp descends from:
+//   <boolean name value="true|false">            -> Properties::set_bool
+//   <rotate x y z angle> | <rotate value angle>  -> Transform4f::rotate(axis, angle in DEGREES) (transform.h:163-167)
+//   <default name value>                         -> adds a $name parameter unless the caller already passed one
+//   <include filename>                           -> parses that file (relative to the including file); the children of
+//                                                   its <scene> root (or its single root object) become children here
+//   <alias id as>                                -> a second id for an already declared object
 #include "core.h"
 #include "render.h"
 
@@ -184,8 +191,10 @@ struct Instance {
 struct Context {
     std::string src;
     std::unordered_map<std::string, Instance> instances;
+    std::unordered_map<std::string, std::string> aliases; // <alias as="..."> -> id
     Transform4f transform;
     size_t id_counter = 0;
+    int include_depth = 0;
 };
 
 [[noreturn]] void node_error(const Context &ctx, const Node &n, const std::string &msg) {
@@ -292,7 +301,7 @@ ref<Object> create_texture_from_spectrum(float const_value, std::vector<float> &
     return InstanceManager::get()->create_instance(p, cls);
 }
 
-std::pair<std::string, std::string> parse_xml(Context &ctx, Node &node, Tag parent_tag, Properties &props, const ParameterList &param,
+std::pair<std::string, std::string> parse_xml(Context &ctx, Node &node, Tag parent_tag, Properties &props, ParameterList &param,
                                               size_t &arg_counter, int depth, bool within_emitter = false, bool within_spectrum = false) {
     if (node.kind != Node::Element) return { "", "" };
     if (!param.empty())
@@ -455,11 +464,78 @@ std::pair<std::string, std::string> parse_xml(Context &ctx, Node &node, Tag pare
                 check_attributes(ctx, node, { "x", "y", "z" }, false);
                 ctx.transform = Transform4f::scale(parse_vector(ctx, node, 1.f)) * ctx.transform;
                 break;
-            case Tag::Boolean: case Tag::Rotate: case Tag::Include: case Tag::Alias: case Tag::Default:
-                // registered but unhandled in the reference's switch: silently dropped there
-                Log(Warn, "\"%s\" (line %d): <%s> is accepted but ignored, as in the reference loader (xml.cpp:421-662)", ctx.src.c_str(),
-                    node.line, node.name.c_str());
+            case Tag::Boolean: {
+                check_attributes(ctx, node, { "name", "value" });
+                std::string v = string::to_lower(node.value("value"));
+                if (v == "true") props.set_bool(node.value("name"), true);
+                else if (v == "false") props.set_bool(node.value("name"), false);
+                else node_error(ctx, node, format("could not parse boolean value \"%s\" -- must be \"true\" or \"false\"", node.value("value").c_str()));
                 break;
+            }
+            case Tag::Rotate: {
+                expand_value_to_xyz(ctx, node);
+                check_attributes(ctx, node, { "angle", "x", "y", "z" }, false);
+                if (!node.attr("angle")) node_error(ctx, node, "missing attribute \"angle\" in element \"rotate\"");
+                Vector3f axis = parse_vector(ctx, node);
+                if (axis.x == 0.f && axis.y == 0.f && axis.z == 0.f) node_error(ctx, node, "rotate: the axis must not be zero");
+                float angle;
+                try { angle = stof_strict(node.value("angle")); }
+                catch (...) { node_error(ctx, node, format("could not parse floating point value \"%s\"", node.value("angle").c_str())); }
+                ctx.transform = Transform4f::rotate(axis, angle * (3.14159265358979323846f / 180.f)) * ctx.transform;
+                break;
+            }
+            case Tag::Default: {
+                check_attributes(ctx, node, { "name", "value" });
+                std::string name = node.value("name");
+                if (name.empty()) node_error(ctx, node, "<default>: name must be nonempty");
+                bool found = false;
+                for (auto &kv : param) found |= kv.first == name;
+                if (!found) param.emplace_back(name, node.value("value"));
+                break;
+            }
+            case Tag::Alias: {
+                check_attributes(ctx, node, { "id", "as" });
+                std::string id = node.value("id"), as = node.value("as");
+                if (ctx.instances.find(id) == ctx.instances.end() && ctx.aliases.find(id) == ctx.aliases.end())
+                    node_error(ctx, node, format("referenced id \"%s\" not found", id.c_str()));
+                if (ctx.instances.find(as) != ctx.instances.end() || ctx.aliases.find(as) != ctx.aliases.end())
+                    node_error(ctx, node, format("duplicate id \"%s\"", as.c_str()));
+                auto chained = ctx.aliases.find(id);
+                ctx.aliases[as] = chained != ctx.aliases.end() ? chained->second : id;
+                break;
+            }
+            case Tag::Include: {
+                check_attributes(ctx, node, { "filename" });
+                std::string filename = node.value("filename");
+                if (filename.empty() || filename[0] != '/') {
+                    size_t slash = ctx.src.find_last_of('/');
+                    if (slash != std::string::npos) filename = ctx.src.substr(0, slash + 1) + filename;
+                }
+                std::ifstream is(filename, std::ios::binary);
+                if (!is) { // not next to the including file: the FileResolver's search path (fresolver.cpp)
+                    filename = get_file_resolver()->resolve(node.value("filename"));
+                    is.open(filename, std::ios::binary);
+                }
+                if (!is) node_error(ctx, node, format("included file \"%s\" not found", filename.c_str()));
+                if (ctx.include_depth >= 15) node_error(ctx, node, "exceeded <include> recursion limit of 15");
+                std::stringstream ss;
+                ss << is.rdbuf();
+                const std::string text = ss.str(); // the Reader keeps references to both strings
+                Reader reader(text, filename);
+                Node root = reader.parse_document();
+                std::string outer_src = ctx.src;
+                ctx.src = filename;
+                ++ctx.include_depth;
+                auto attach = [&](Node &ch) {
+                    auto [arg_name, nested_id] = parse_xml(ctx, ch, parent_tag, props, param, arg_counter, depth, within_emitter, within_spectrum);
+                    if (!nested_id.empty()) props.set_named_reference(arg_name, nested_id);
+                };
+                if (root.name == "scene") for (Node &ch : root.children) attach(ch);
+                else attach(root);
+                --ctx.include_depth;
+                ctx.src = outer_src;
+                break;
+            }
             default: break;
         }
         for (Node &ch : node.children) parse_xml(ctx, ch, tag, props, param, arg_counter, depth + 1);
@@ -472,7 +548,8 @@ std::pair<std::string, std::string> parse_xml(Context &ctx, Node &node, Tag pare
 }
 
 ref<Object> instantiate_node(Context &ctx, const std::string &id) { // :676-710
-    auto it = ctx.instances.find(id);
+    auto alias = ctx.aliases.find(id);
+    auto it = ctx.instances.find(alias != ctx.aliases.end() ? alias->second : id);
     if (it == ctx.instances.end()) Throw("reference to unknown object \"%s\"!", id.c_str());
     Instance &inst = it->second;
     if (inst.object) return inst.object;

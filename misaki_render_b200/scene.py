@@ -116,6 +116,16 @@ class SceneDescription:
         self._cdesc = None
         return len(self.spectra) - 1
 
+    def spectrum_checkerboard(self, color0, color1, to_uv=None):
+        """"checkerboard" texture (textures/checkerboard.cpp:11-31) over two already declared spectra; `to_uv` is the
+        4x4 "to_uv" transform, of which Transform4f::extract keeps the top-left 3x3 (transform.h:142-148)."""
+        m = np.eye(4, dtype=f32) if to_uv is None else np.asarray(to_uv, dtype=f32).reshape(4, 4)
+        sid = self._add_spec(capi.SPEC_CHECKERBOARD)
+        s = self.spectra[sid]
+        s.child0, s.child1 = int(color0), int(color1)
+        s.to_uv[:] = [float(x) for x in m[:2, :3].reshape(-1)]
+        return sid
+
     def spectrum_uniform(self, value):
         return self._add_spec(capi.SPEC_UNIFORM, value=value)
 

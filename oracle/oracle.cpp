@@ -55,6 +55,8 @@ struct OSpectrum {
     std::vector<float> table;
     float lambda_min, lambda_max;
     float inv_interval_size; // regular.cpp:58 (double 1/interval stored to float)
+    int child0 = -1, child1 = -1; // checkerboard.cpp:12-13 "color0" / "color1"
+    float to_uv[6] = { 1, 0, 0, 0, 1, 0 }; // checkerboard.cpp:14: Transform4f::extract() = top-left 3x3, rows 0 and 1
 };
 
 // srgb.h:8-19
@@ -97,6 +99,18 @@ Spec spectrum_eval(const OSpectrum &s, const Spec &wl) {
         case MSK_SPEC_SRGB_UNBOUNDED: return srgb_model_eval(s.c, wl) * s.value;          // builder decision (F4)
     }
     return Spec(0.f);
+}
+
+// textures/checkerboard.cpp:25-33 (Texture::eval(si)): Transform3f::transform_affine_point (transform.h:41-48) of
+// si.uv, fractional parts, then color0 where both or neither exceed one half, else color1
+Spec texture_eval(const std::vector<OSpectrum> &spectra, int id, float u, float v, const Spec &wl) {
+    const OSpectrum &s = spectra[id];
+    if (s.kind != MSK_SPEC_CHECKERBOARD) return spectrum_eval(s, wl);
+    float tu = (s.to_uv[0] * u + s.to_uv[1] * v) + s.to_uv[2] * 1.f;
+    float tv = (s.to_uv[3] * u + s.to_uv[4] * v) + s.to_uv[5] * 1.f;
+    tu = tu - std::floor(tu);
+    tv = tv - std::floor(tv);
+    return texture_eval(spectra, ((tu > .5f) == (tv > .5f)) ? s.child0 : s.child1, u, v, wl);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -515,7 +529,7 @@ std::pair<DirectIllumSample, Spec> emitter_sample_direct(const OScene &sc, int e
         DirectIllumSample ds = shape_sample_direct(sc.meshes[em.shape], ref, sample);
         ds.object = e;
         if (dot(ds.d, ds.n) < 0.f && ds.pdf != 0.f)
-            return { ds, spectrum_eval(sc.spectra[em.radiance], ref.wavelengths) / ds.pdf };
+            return { ds, texture_eval(sc.spectra, em.radiance, ds.uv.x, ds.uv.y, ref.wavelengths) / ds.pdf }; // SceneInteraction si(ds)
         ds.pdf = 0;
         return { ds, Spec(0.f) };
     } else { // constant.cpp:55-73
@@ -526,7 +540,7 @@ std::pair<DirectIllumSample, Spec> emitter_sample_direct(const OScene &sc, int e
         ds.pdf = InvFourPi; ds.object = e; ds.d = d; ds.dist = dist;
         // the reference evaluates radiance with a default-constructed interaction whose
         // wavelengths are uninitialised (constant.cpp:70-72); restated with the query's wavelengths
-        return { ds, spectrum_eval(sc.spectra[em.radiance], ref.wavelengths) / ds.pdf };
+        return { ds, texture_eval(sc.spectra, em.radiance, 0.f, 0.f, ref.wavelengths) / ds.pdf };
     }
 }
 float emitter_pdf_direct(const OScene &sc, int e, const DirectIllumSample &ds) {
@@ -537,8 +551,8 @@ float emitter_pdf_direct(const OScene &sc, int e, const DirectIllumSample &ds) {
 Spec emitter_eval(const OScene &sc, int e, const SceneInteraction &si) {
     const MskEmitter &em = sc.emitters[e];
     if (em.type == MSK_EMITTER_AREA) // area.cpp:51-54
-        return Frame::cos_theta(si.wi) > 0.f ? spectrum_eval(sc.spectra[em.radiance], si.wavelengths) : Spec(0.f);
-    return spectrum_eval(sc.spectra[em.radiance], si.wavelengths); // constant.cpp:79-81
+        return Frame::cos_theta(si.wi) > 0.f ? texture_eval(sc.spectra, em.radiance, si.uv.x, si.uv.y, si.wavelengths) : Spec(0.f);
+    return texture_eval(sc.spectra, em.radiance, 0.f, 0.f, si.wavelengths); // constant.cpp:79-81 (a miss carries no uv)
 }
 
 // scene.cpp:69-103
@@ -594,7 +608,7 @@ uint32_t bsdf_flags(const MskBsdf &b) {
     return 0;
 }
 
-Spec tex(const OScene &sc, int id, const SceneInteraction &si) { return spectrum_eval(sc.spectra[id], si.wavelengths); }
+Spec tex(const OScene &sc, int id, const SceneInteraction &si) { return texture_eval(sc.spectra, id, si.uv.x, si.uv.y, si.wavelengths); }
 
 std::pair<BSDFSample, Spec> bsdf_sample_1(const OScene &sc, const MskBsdf &b, const SceneInteraction &si, float sample1, V2 sample) {
     BSDFSample bs;
@@ -1016,6 +1030,11 @@ int orc_scene_create(const MskSceneDesc *d, OrcScene **out) {
             double range = double(s.lambda_max) - double(s.lambda_min), interval = range / (s.table_size - 1);
             o.inv_interval_size = float(1. / interval);
         }
+        if (s.kind == MSK_SPEC_CHECKERBOARD) {
+            if (s.child0 < 0 || s.child1 < 0 || (uint32_t) s.child0 >= i || (uint32_t) s.child1 >= i) return fail("bad checkerboard children");
+            o.child0 = s.child0; o.child1 = s.child1;
+            for (int k = 0; k < 6; ++k) o.to_uv[k] = s.to_uv[k];
+        }
         sc.spectra.push_back(std::move(o));
     }
     sc.bbox_min = V3(Infinity, Infinity, Infinity);
@@ -1322,6 +1341,13 @@ void orc_srgb_model_eval(const float c[3], const float wl[4], float out[4]) {
     Spec w; for (int i = 0; i < 4; ++i) w[i] = wl[i];
     Spec r = srgb_model_eval(c, w);
     for (int i = 0; i < 4; ++i) out[i] = r[i];
+}
+int orc_texture_eval(OrcScene *s, int id, float u, float v, const float wl[4], float out[4]) {
+    if (!s || id < 0 || (size_t) id >= s->sc.spectra.size()) return fail("bad spectrum id");
+    Spec w; for (int i = 0; i < 4; ++i) w[i] = wl[i];
+    Spec r = texture_eval(s->sc.spectra, id, u, v, w);
+    for (int i = 0; i < 4; ++i) out[i] = r[i];
+    return 0;
 }
 int orc_spectrum_eval(OrcScene *s, int id, const float wl[4], float out[4]) {
     if (!s || id < 0 || (size_t) id >= s->sc.spectra.size()) return fail("bad spectrum id");

@@ -33,6 +33,7 @@ void orc_fresnel(float cos_theta_i, float eta, float out[4]);
 void orc_fresnel_conductor(float cos_theta_i, const float eta[4], const float k[4], float out[4]);
 void orc_srgb_model_eval(const float c[3], const float wl[4], float out[4]);
 int  orc_spectrum_eval(OrcScene *s, int id, const float wl[4], float out[4]);
+int  orc_texture_eval(OrcScene *s, int id, float u, float v, const float wl[4], float out[4]); /* Texture::eval(si) at si.uv */
 void orc_spectrum_to_xyz(const float value[4], const float wl[4], float xyz[3]);
 void orc_ggx(int which, float au, float av, const float a[3], const float b[3], float out[4]);
 int  orc_bsdf(OrcScene *s, int bsdf_id, const float wi[3], const float wl[4], const float smp[3], const float wo_in[3],

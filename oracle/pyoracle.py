@@ -63,6 +63,7 @@ def lib() -> C.CDLL:
         L.orc_fresnel_conductor.argtypes = [C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]
         L.orc_srgb_model_eval.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.orc_spectrum_eval.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+        L.orc_texture_eval.argtypes = [C.c_void_p, C.c_int, C.c_float, C.c_float, C.c_void_p, C.c_void_p]
         L.orc_spectrum_to_xyz.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.orc_ggx.argtypes = [C.c_int, C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]
         L.orc_bsdf.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 7
@@ -151,6 +152,12 @@ class OracleScene:
         ps = np.ascontiguousarray(pixel_sample, dtype=np.uint32).reshape(-1, 2)
         out = np.empty((ps.shape[0], 9), dtype=np.float32)
         assert self.L.orc_trace_samples(self.h, C.byref(rd), ps.ctypes.data, out.ctypes.data, ps.shape[0]) == 0
+        return out
+
+    def texture_eval(self, sid, u, v, wl):
+        wl = np.ascontiguousarray(wl, dtype=np.float32)
+        out = np.empty(4, np.float32)
+        assert self.L.orc_texture_eval(self.h, sid, float(u), float(v), wl.ctypes.data, out.ctypes.data) == 0
         return out
 
     def spectrum_eval(self, sid, wl):

@@ -169,3 +169,25 @@ def test_base_seed_and_convergence(gpu_ctx):
     assert not np.array_equal(a_film, b_film)
     assert abs(ea - eo) <= 0.02 * eo  # same seeds: same estimator up to float noise
     assert 0.5 * eo < eb < 2.0 * eo   # other seeds: same variance
+
+
+def test_checkerboard_textures_equal_seed(gpu_ctx):
+    """"checkerboard" (textures/checkerboard.cpp) on a diffuse reflectance (nested, with texcoords),
+    on an area light's radiance (no texcoords: si.uv = barycentrics, ps.uv = the warped sample) and on a rough
+    conductor's specular_reflectance.  The texture only selects a child spectrum, so parity is the usual equal-seed
+    bound; the untextured scene must differ visibly (the texture is actually evaluated)."""
+    sd = scenes.checkers(96, 96)
+    rd = capi.render_desc(spp=16, max_depth=6)
+    film, rgba, ofilm, oref, stats, ost = _both(gpu_ctx, sd, rd)
+    e = relmse(rgba, oref)
+    _report("checkers", e, stats, ost)
+    assert np.isfinite(film).all() and e < EQUAL_SEED_RELMSE, e
+    assert bad_pixel_fraction(rgba, oref) < 0.01
+    for s in sd.spectra:  # collapse every checkerboard onto its color0
+        if s.kind == capi.SPEC_CHECKERBOARD:
+            s.child1 = s.child0
+    sd._cdesc = None
+    with capi.Scene(gpu_ctx, sd) as sc:
+        film0, _ = sc.render(rd)
+        rgba0 = sc.develop(film0)
+    assert relmse(rgba0, oref) > 100 * EQUAL_SEED_RELMSE

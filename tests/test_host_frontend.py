@@ -134,6 +134,56 @@ def test_float_spectrum_and_rgb_properties_become_textures():
         np.testing.assert_array_equal(np.array(sp[5], np.float32), (D65_TABLE * scale).astype(np.float32))
 
 
+def test_checkerboard_texture_plugin():
+    """textures/checkerboard.cpp:11-15: color0/color1 default to 0.4 / 0.2, "to_uv" keeps the top-left 3x3 of the 4x4."""
+    inner = ('<bsdf type="diffuse"><texture type="checkerboard" name="reflectance">'
+             '<rgb name="color0" value="0.8 0.1 0.1"/>'
+             '<texture type="checkerboard" name="color1"><transform name="to_uv"><scale x="8" y="4"/></transform></texture>'
+             '<transform name="to_uv"><scale value="2"/><translate x="0.5" y="0.25" z="3"/></transform>'
+             '</texture></bsdf>')
+    with _scene(MINIMAL.format(body=QUAD.format(inner=inner))) as hs:
+        d = hs.desc()
+        top = d.spectra[d.bsdfs[0].reflectance]
+        assert top.kind == capi.SPEC_CHECKERBOARD and max(top.child0, top.child1) < d.bsdfs[0].reflectance
+        np.testing.assert_array_equal(top.to_uv[:], [2, 0, 0, 0, 2, 0])  # the translation column is dropped by extract()
+        c0, inner_tex = d.spectra[top.child0], d.spectra[top.child1]
+        np.testing.assert_array_equal(np.array(c0.c[:], np.float32), rgb2spec_model().fetch((0.8, 0.1, 0.1)))
+        assert inner_tex.kind == capi.SPEC_CHECKERBOARD
+        np.testing.assert_array_equal(inner_tex.to_uv[:], [8, 0, 0, 0, 4, 0])
+        a, b = d.spectra[inner_tex.child0], d.spectra[inner_tex.child1]  # defaults: gray 0.4 / 0.2 (defaulted texture rule)
+        np.testing.assert_array_equal(np.array(a.c[:], np.float32), rgb2spec_model().fetch((0.4, 0.4, 0.4)))
+        np.testing.assert_array_equal(np.array(b.c[:], np.float32), rgb2spec_model().fetch((0.2, 0.2, 0.2)))
+    assert "checkerboard" in host_api.registered_plugins()
+
+
+def test_obj_relative_indices_and_polygons(tmp_path):
+    """OBJ features beyond obj.cpp:104-118: negative (relative) indices and faces with more than
+    four corners, triangulated by the reference's own quad rule (v1 v2 v3) (v4 v1 v3) extended as a fan."""
+    (tmp_path / "abs.obj").write_text("v 0 0 0\nv 1 0 0\nv 1 1 0\nv 0 1 0\nvt 0 0\nvt 1 0\nvt 1 1\nvt 0 1\nvn 0 0 1\n"
+                                      "f 1/1/1 2/2/1 3/3/1 4/4/1\n")
+    (tmp_path / "rel.obj").write_text("v 0 0 0\nv 1 0 0\nv 1 1 0\nv 0 1 0\nvt 0 0\nvt 1 0\nvt 1 1\nvt 0 1\nvn 0 0 1\n"
+                                      "f -4/-4/-1 -3/-3/-1 -2/-2/-1 -1/-1/-1\n")
+    (tmp_path / "pent.obj").write_text("v 0 0 0\nv 2 0 0\nv 3 1 0\nv 1 2 0\nv -1 1 0\nf 1 2 3 4 5\nv 9 9 9\nf -1 1 2\n")
+    shape = '<shape type="obj"><string name="filename" value="%s"/></shape>'
+    with _scene(MINIMAL.format(body=shape % (tmp_path / "abs.obj"))) as a, _scene(MINIMAL.format(body=shape % (tmp_path / "rel.obj"))) as r:
+        ma, mr = a.meshes()[0], r.meshes()[0]
+        np.testing.assert_array_equal(ma["verts"], mr["verts"])
+        np.testing.assert_array_equal(ma["tris"], mr["tris"])
+        np.testing.assert_array_equal(ma["tris"], [[0, 1, 2], [3, 0, 2]])  # the reference's quad split
+        assert ma["has_normals"] and ma["has_uvs"]
+        np.testing.assert_array_equal(ma["verts"][:, 6:8], [[0, 1], [1, 1], [1, 0], [0, 0]])  # filp_tex_coords default
+    with _scene(MINIMAL.format(body=shape % (tmp_path / "pent.obj"))) as p:
+        m = p.meshes()[0]
+        np.testing.assert_array_equal(m["tris"], [[0, 1, 2], [3, 0, 2], [4, 0, 3], [5, 0, 1]])
+        np.testing.assert_array_equal(m["verts"][5, :3], [9, 9, 9])  # -1 named the vertex declared just before that face
+    (tmp_path / "bad.obj").write_text("v 0 0 0\nv 1 0 0\nf 1 2\n")
+    with pytest.raises(host_api.HostError, match="fewer than 3"):
+        _scene(MINIMAL.format(body=shape % (tmp_path / "bad.obj")))
+    (tmp_path / "oob.obj").write_text("v 0 0 0\nv 1 0 0\nv 0 1 0\nf 1 2 -7\n")
+    with pytest.raises(host_api.HostError, match="out of range"):
+        _scene(MINIMAL.format(body=shape % (tmp_path / "oob.obj")))
+
+
 def test_material_plugins_and_their_parameter_checks():
     rc = ('<bsdf type="roughconductor"><string name="distribution" value="ggx"/><float name="alpha" value="0.1"/>'
           '<rgb name="eta" value="0.200438, 0.924033, 1.10221"/><rgb name="k" value="3.91295, 2.45285, 2.14219"/></bsdf>')
@@ -182,15 +232,18 @@ def test_environment_emitter_and_scene_level_checks():
         host_api.HostScene(xml='<bsdf type="diffuse"/>')
 
 
-def test_integrator_parameters_and_ignored_tags():
+def test_integrator_parameters_and_boolean_tag():
     integ = ('<integrator type="path"><integer name="max_depth" value="7"/><integer name="rr_depth" value="3"/>'
              '<boolean name="hide_emitters" value="true"/></integrator>')
     sampler = '<sampler type="independent"><integer name="sample_count" value="24"/><integer name="base_seed" value="9"/></sampler>'
     xml = MINIMAL.format(body=integ).replace('<film type="hdrfilm">', sampler + '<film type="hdrfilm">')
     with _scene(xml) as hs:
         rd = hs.render_desc()
-        # <boolean> has no case in the reference's parser switch (xml.cpp:421-662): accepted, ignored
-        assert (rd.spp, rd.base_seed, rd.max_depth, rd.rr_depth, rd.hide_emitters) == (24, 9, 7, 3, 0)
+        # <boolean> has no case in the reference's parser switch (xml.cpp:421-662) and is dropped there; SURVEY 8f
+        # rank 3 asks for it to be handled, so hide_emitters (integrator.cpp:23) becomes settable
+        assert (rd.spp, rd.base_seed, rd.max_depth, rd.rr_depth, rd.hide_emitters) == (24, 9, 7, 3, 1)
+    with pytest.raises(host_api.HostError, match="could not parse boolean value"):
+        _scene(MINIMAL.format(body='<integrator type="path"><boolean name="hide_emitters" value="yes"/></integrator>'))
     with pytest.raises(host_api.HostError, match="rr_depth"):
         _scene(MINIMAL.format(body='<integrator type="path"><integer name="rr_depth" value="0"/></integrator>'))
     with pytest.raises(host_api.HostError, match="max_depth"):
@@ -235,6 +288,51 @@ def test_transform_composition_and_param_substitution():
     expect = np.array([[2, 0, 0, 11], [0, 2, 0, 2], [0, 0, 2, 3], [0, 0, 0, 1]], dtype=np.float64)
     np.testing.assert_allclose(m, expect, atol=1e-6)
     p.unlink()
+
+
+def test_rotate_default_include_and_alias_tags(tmp_path):
+    """the tags the reference registers (xml.cpp:74-90) but never handles (:421-662)."""
+    cam = """<scene><default name="ang" value="90"/><default name="tx" value="5"/>
+             <sensor type="perspective"><transform name="to_world">
+               <translate x="$tx"/><rotate z="1" angle="$ang"/>
+             </transform></sensor></scene>"""
+    p = tmp_path / "cam.xml"
+    p.write_text(cam)
+    with host_api.HostScene(p) as hs:  # defaults in effect: M = rotate_z(90 deg) * translate(5,0,0)
+        m = np.array(hs.desc().camera.to_world[:]).reshape(4, 4)
+    np.testing.assert_allclose(m, [[0, -1, 0, 0], [1, 0, 0, 5], [0, 0, 1, 0], [0, 0, 0, 1]], atol=1e-6)
+    with host_api.HostScene(p, params=dict(ang="180", tx="1")) as hs:  # caller-supplied parameters win over <default>
+        m = np.array(hs.desc().camera.to_world[:]).reshape(4, 4)
+    np.testing.assert_allclose(m, [[-1, 0, 0, -1], [0, -1, 0, 0], [0, 0, 1, 0], [0, 0, 0, 1]], atol=1e-6)
+    with host_api.HostScene(xml='<scene><sensor type="perspective"><transform name="to_world">'
+                                '<rotate value="1 1 1" angle="120"/></transform></sensor></scene>') as hs:
+        m = np.array(hs.desc().camera.to_world[:]).reshape(4, 4)  # 120 deg about (1,1,1) permutes the axes
+    np.testing.assert_allclose(m[:3, :3], [[0, 0, 1], [1, 0, 0], [0, 1, 0]], atol=1e-6)
+    for bad, msg in [('<rotate angle="3"/>', "axis must not be zero"), ('<rotate x="1"/>', 'missing attribute "angle"')]:
+        with pytest.raises(host_api.HostError, match=msg):
+            host_api.HostScene(xml='<scene><sensor type="perspective"><transform name="to_world">%s</transform></sensor></scene>' % bad)
+
+    # <include>: the children of the included <scene> become children of the including object, in place
+    (tmp_path / "materials.xml").write_text('<scene><bsdf type="diffuse" id="red"><rgb name="reflectance" value="$r 0.1 0.1"/></bsdf>'
+                                            '<alias id="red" as="wall"/></scene>')
+    (tmp_path / "light.xml").write_text(QUAD.format(inner='<ref id="wall"/><emitter type="area"><rgb name="radiance" value="3"/></emitter>'))
+    main = MINIMAL.format(body='<default name="r" value="0.8"/><include filename="materials.xml"/>'
+                               + QUAD.format(inner='<ref id="red"/>') + '<include filename="light.xml"/>')
+    host_api.load().mskh_add_search_path(str(ROOT / "assets" / "scenes").encode())
+    (tmp_path / "main.xml").write_text(main)
+    with host_api.HostScene(tmp_path / "main.xml") as hs:
+        d, meshes = hs.desc(), hs.meshes()
+        assert (d.nmeshes, d.nemitters) == (2, 1)
+        assert meshes[0]["bsdf"] == meshes[1]["bsdf"]  # <ref id="red"> and the alias "wall" name the same instance
+        assert meshes[1]["emitter"] == 0 and meshes[0]["emitter"] == -1
+        np.testing.assert_allclose(_spectra(d)[d.bsdfs[meshes[0]["bsdf"]].reflectance][1], host_api.srgb_model_fetch((0.8, 0.1, 0.1)), rtol=1e-6)
+    with pytest.raises(host_api.HostError, match='included file .* not found'):
+        host_api.HostScene(xml='<scene><include filename="nope.xml"/></scene>')
+    with pytest.raises(host_api.HostError, match='referenced id "zz" not found'):
+        host_api.HostScene(xml='<scene><alias id="zz" as="b"/></scene>')
+    (tmp_path / "loop.xml").write_text('<scene><include filename="loop.xml"/></scene>')
+    with pytest.raises(host_api.HostError, match="recursion limit"):
+        host_api.HostScene(tmp_path / "loop.xml")
 
 
 def test_srgb_model_fetch_matches_the_reference_runtime():

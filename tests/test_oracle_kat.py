@@ -268,3 +268,50 @@ def test_direct_light_closed_form():
     ybar = np.mean([po.spectrum_to_xyz(po.sample_wavelength(float(u))[1], po.sample_wavelength(float(u))[0])[1] for u in (np.arange(n) + 0.5) / n])
     got = film[4, 4, 1] / film[4, 4, 4]
     assert abs(got - want * ybar) < 0.03 * want * ybar, (got, want * ybar)
+
+
+def test_checkerboard_texture_selects_children_by_uv():
+    """textures/checkerboard.cpp:25-33: uv' = Transform3f(to_uv.extract()) * (u, v, 1); frac; color0 iff (u' > .5) == (v' > .5).
+    extract() keeps the top-left 3x3 of the 4x4 (transform.h:142-148): the z COLUMN is the uv offset, the translation
+    column is dropped."""
+    from misaki_render_b200.scene import SceneDescription, scale, translate
+    sd = SceneDescription(8, 8)
+    a, b, c = sd.spectrum_uniform(0.25), sd.spectrum_uniform(0.5), sd.spectrum_uniform(1.0)
+    plain = sd.spectrum_checkerboard(a, b)
+    scaled = sd.spectrum_checkerboard(a, b, to_uv=scale((4, 2, 1)))
+    moved = sd.spectrum_checkerboard(a, b, to_uv=translate((0.5, 0.0, 0.0)))  # translation is NOT applied
+    m = np.eye(4, dtype=np.float32); m[0, 2] = 0.5
+    zcol = sd.spectrum_checkerboard(a, b, to_uv=m)                              # the z column is
+    nested = sd.spectrum_checkerboard(c, scaled)
+    v, t = np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0]], np.float32), np.array([[0, 1, 2]], np.uint32)
+    sd.add_mesh(v, t, sd.bsdf_diffuse(nested))
+    osc = po.OracleScene(sd)
+    wl = np.array([400, 500, 600, 700], np.float32)
+    ev = lambda sid, u, v: float(osc.texture_eval(sid, u, v, wl)[0])
+    assert [ev(plain, *uv) for uv in [(0.25, 0.25), (0.75, 0.75), (0.75, 0.25), (0.25, 0.75)]] == [0.25, 0.25, 0.5, 0.5]
+    assert ev(plain, 1.25, -0.75) == 0.25 and ev(plain, -0.25, 0.25) == 0.5          # frac() of negative coordinates
+    assert ev(plain, 0.5, 0.5) == 0.25 and ev(plain, 0.5, 0.75) == 0.5               # strict > .5
+    assert [ev(scaled, u, 0.1) for u in (0.05, 0.2, 0.3, 0.45)] == [0.25, 0.5, 0.25, 0.5]
+    assert ev(moved, 0.25, 0.25) == ev(plain, 0.25, 0.25) and ev(zcol, 0.25, 0.25) == ev(plain, 0.75, 0.25)
+    assert ev(nested, 0.25, 0.25) == 1.0 and ev(nested, 0.8, 0.1) == ev(scaled, 0.8, 0.1) == 0.25
+    assert ev(nested, 0.1, 0.6) == ev(scaled, 0.1, 0.6) == 0.25 and ev(nested, 0.2, 0.6) == 0.5
+
+
+def test_checkerboard_radiance_seen_directly():
+    """An area light filling the view, max_depth 1: every sample returns Le = radiance->eval(si) (path.cpp:44-47,
+    area.cpp:51-54) with si.uv = the hit barycentrics for a mesh without texcoords (mesh.cpp:65).  With uniform
+    children 1 and 3 every pixel away from a cell border is one of two values in ratio 3."""
+    from misaki_render_b200.scene import SceneDescription, lookat, scale
+    from workloads import meshes
+    sd = SceneDescription(32, 32, fov=30.0, to_world=lookat((0, 0, -2), (0, 0, 0), (0, 1, 0)))
+    tex = sd.spectrum_checkerboard(sd.spectrum_uniform(1.0), sd.spectrum_uniform(3.0), to_uv=scale((2, 2, 1)))
+    lv, lt = meshes.quad((-4, -4, 0), (-4, 4, 0), (4, 4, 0), (4, -4, 0))  # normal towards -z (the camera)
+    sd.add_mesh(lv, lt, sd.bsdf_diffuse((0.5, 0.5, 0.5)), radiance=tex)
+    film, _ = po.OracleScene(sd).render(capi.render_desc(spp=16, max_depth=1))
+    flat = SceneDescription(32, 32, fov=30.0, to_world=lookat((0, 0, -2), (0, 0, 0), (0, 1, 0)))
+    flat.add_mesh(lv, lt, flat.bsdf_diffuse((0.5, 0.5, 0.5)), radiance=flat.spectrum_uniform(1.0))
+    base, _ = po.OracleScene(flat).render(capi.render_desc(spp=16, max_depth=1))  # same seeds, radiance 1 everywhere
+    r = film[..., 1] / base[..., 1]
+    ones, threes = np.abs(r - 1) < 1e-5, np.abs(r - 3) < 1e-5
+    assert (ones | threes).mean() > 0.6 and ones.sum() > 50 and threes.sum() > 50
+    assert r.min() >= 1 - 1e-5 and r.max() <= 3 + 1e-5

@@ -14,7 +14,7 @@ from pathlib import Path
 import numpy as np
 
 from misaki_render_b200 import capi
-from misaki_render_b200.scene import SceneDescription, lookat, translate
+from misaki_render_b200.scene import SceneDescription, lookat, scale, translate
 
 from . import meshes
 
@@ -75,6 +75,34 @@ def teapot(width=1024, height=1024, n=112):
     mat = sd.bsdf_roughdielectric(int_ior=1.5, ext_ior=1.0, alpha=0.1, distribution="ggx")
     sd.add_mesh(v, t, mat, has_normals=True, has_uvs=True)
     sd.add_constant_environment((0.5, 0.6, 0.8))
+    return sd
+
+
+def checkers(width=96, height=96, n=12):
+    """Textured scene for the "checkerboard" texture (textures/checkerboard.cpp): a ground quad with
+    texcoords whose reflectance is a checkerboard of a colour and a NESTED checkerboard, a quad light WITHOUT
+    texcoords whose radiance is a checkerboard (si.uv = barycentrics / the warped sample, mesh.cpp:65,114), and a
+    rough conductor with a checkerboard specular_reflectance on interpolated uvs."""
+    sd = SceneDescription(width, height, fov=40.0, near_clip=0.1, far_clip=100.0,
+                          to_world=lookat((0.0, 2.6, -5.0), (0.0, 0.7, 0.0), (0, 1, 0)))
+    half = 5.0
+    gv = np.zeros((4, 8), f32)
+    gv[:, :3] = [(-half, 0, -half), (-half, 0, half), (half, 0, half), (half, 0, -half)]
+    gv[:, 6:8] = [(0, 0), (0, 1), (1, 1), (1, 0)]
+    gt = np.array([[0, 1, 2], [0, 2, 3]], np.uint32)
+    fine = sd.spectrum_checkerboard(sd.spectrum_srgb((0.8, 0.7, 0.2)), sd.spectrum_srgb((0.1, 0.1, 0.5)), to_uv=scale((32, 32, 1)))
+    # the top-left 3x3 is kept (transform.h:142-148): the z column of the 4x4 acts as the uv offset
+    m = scale((4, 4, 1)); m[0, 2], m[1, 2] = 0.25, 0.125
+    ground = sd.spectrum_checkerboard(sd.spectrum_srgb((0.75, 0.75, 0.75)), fine, to_uv=m)
+    sd.add_mesh(gv, gt, sd.bsdf_diffuse(ground), has_uvs=True)
+    lv, lt = meshes.quad((-1.2, 4.5, -1.2), (1.2, 4.5, -1.2), (1.2, 4.5, 1.2), (-1.2, 4.5, 1.2))
+    light = sd.spectrum_checkerboard(sd.spectrum_srgb_d65((30, 24, 18)), sd.spectrum_srgb_d65((4, 8, 20)), to_uv=scale((3, 3, 1)))
+    sd.add_mesh(lv, lt, sd.bsdf_diffuse((0.5, 0.5, 0.5)), radiance=light)
+    v, t = meshes.cube_sphere(n, seed=5, octaves=2, amplitude=0.05, radius=0.8, center=(0, 0.9, 0), normals=True, uvs=True)
+    spec = sd.spectrum_checkerboard(sd.spectrum_srgb((1.0, 1.0, 1.0)), sd.spectrum_srgb((0.9, 0.3, 0.2)), to_uv=scale((6, 6, 1)))
+    mat = sd.bsdf_roughconductor(eta=(0.200438, 0.924033, 1.10221), k=(3.91295, 2.45285, 2.14219), alpha=0.15,
+                                 specular_reflectance=spec)
+    sd.add_mesh(v, t, mat, has_normals=True, has_uvs=True)
     return sd
 
 
