@@ -106,6 +106,16 @@ typedef struct {
     int32_t shape;    /* AREA: index into meshes; CONSTANT: -1 */
 } MskEmitter;
 
+/* ---- participating media (src/librender/medium.cpp, media/homogeneous.cpp, phase/isotropic.cpp) ---- */
+typedef enum { MSK_PHASE_ISOTROPIC = 0 } MskPhaseType; /* phase/isotropic.cpp: the only phase function of the reference */
+
+typedef struct {
+    int32_t sigma_a;  /* spectrum id, homogeneous.cpp:15 "sigma_a" (absorption coefficient per scene unit) */
+    int32_t sigma_s;  /* spectrum id, homogeneous.cpp:16 "sigma_s" (scattering coefficient) */
+    int32_t phase;    /* MskPhaseType */
+    float   scale;    /* homogeneous.cpp:18 "scale": read and stored by the reference, applied nowhere -- kept so */
+} MskMedium;
+
 /* ---- shapes (src/librender/mesh.cpp, shapes/obj.cpp:137-177) ---- */
 typedef struct {
     const float    *verts;   /* nverts x 8 floats [px py pz nx ny nz u v], stride 32 B, world space */
@@ -116,6 +126,8 @@ typedef struct {
     uint8_t  has_normals;    /* Mesh::has_vertex_normals   */
     uint8_t  has_uvs;        /* Mesh::has_vertex_texcoords */
     uint8_t  pad_[2];
+    int32_t  interior_medium; /* shape.cpp:28-39: index into media of the child medium named "interior", or -1 */
+    int32_t  exterior_medium; /*   ... of any other child medium, or -1 (at most 254 media per scene) */
 } MskMesh;
 
 /* ---- sensor + film (sensors/perspective.cpp:9-41, film.cpp, filters/gaussian.cpp) ---- */
@@ -136,6 +148,8 @@ typedef struct {
     const float       *spectrum_tables; uint32_t ntable_floats;
     int32_t            environment;                  /* emitter index of the environment, or -1 */
     MskCamera          camera;
+    const MskMedium   *media;    uint32_t nmedia;    /* consumed by the "volpath" integrator only */
+    int32_t            sensor_medium;                /* sensor.cpp:12-18: medium the camera sits in, or -1 */
 } MskSceneDesc;
 
 typedef struct {
@@ -149,8 +163,13 @@ typedef struct {
     uint32_t clear_film;    /* 1: zero the film first; 0: accumulate on top */
     uint32_t paths_per_batch; /* 0 = default pool size */
     uint32_t flags;         /* MSK_RENDER_* */
-    uint32_t pad_;
+    uint32_t integrator;    /* MskIntegrator: which MonteCarloIntegrator::sample the wavefront executes */
 } MskRenderDesc;
+
+typedef enum {
+    MSK_INTEGRATOR_PATH    = 0, /* integrators/path.cpp:23-131    (registered as "path")    */
+    MSK_INTEGRATOR_VOLPATH = 1  /* integrators/volpath.cpp:26-167 (registered as "volpath") */
+} MskIntegrator;
 
 #define MSK_RENDER_STAGE_TIMERS 1u /* fill MskStats::ms_{raygen,intersect,shade,shadow,film} (adds event records) */
 #define MSK_RENDER_TRAVERSAL_STATS 2u /* run the instrumented traversal kernels and fill MskStats::nodes_*, tris_* */

@@ -32,6 +32,7 @@ EMITTER_AREA, EMITTER_CONSTANT = range(2)
 RENDER_STAGE_TIMERS = 1
 RENDER_TRAVERSAL_STATS = 2
 ABI_VERSION = 4
+INTEGRATOR_PATH, INTEGRATOR_VOLPATH = range(2)
 AOV_DEPTH, AOV_POSITION, AOV_UV, AOV_GEO_NORMAL, AOV_SH_NORMAL, AOV_INTEGRATOR_RGBA = range(6)
 AOV_NAMES = {"depth": AOV_DEPTH, "position": AOV_POSITION, "uv": AOV_UV, "geo_normal": AOV_GEO_NORMAL, "sh_normal": AOV_SH_NORMAL,
              "integrator": AOV_INTEGRATOR_RGBA}
@@ -62,7 +63,11 @@ class MskEmitter(C.Structure):
 class MskMesh(C.Structure):
     _fields_ = [("verts", C.POINTER(C.c_float)), ("tris", C.POINTER(C.c_uint32)), ("nverts", C.c_uint32), ("ntris", C.c_uint32),
                 ("bsdf", C.c_int32), ("emitter", C.c_int32), ("has_normals", C.c_uint8), ("has_uvs", C.c_uint8),
-                ("pad_", C.c_uint8 * 2)]
+                ("pad_", C.c_uint8 * 2), ("interior_medium", C.c_int32), ("exterior_medium", C.c_int32)]
+
+
+class MskMedium(C.Structure):
+    _fields_ = [("sigma_a", C.c_int32), ("sigma_s", C.c_int32), ("phase", C.c_int32), ("scale", C.c_float)]
 
 
 class MskCamera(C.Structure):
@@ -75,13 +80,14 @@ class MskSceneDesc(C.Structure):
     _fields_ = [("meshes", C.POINTER(MskMesh)), ("nmeshes", C.c_uint32), ("bsdfs", C.POINTER(MskBsdf)), ("nbsdfs", C.c_uint32),
                 ("emitters", C.POINTER(MskEmitter)), ("nemitters", C.c_uint32), ("spectra", C.POINTER(MskSpectrum)),
                 ("nspectra", C.c_uint32), ("spectrum_tables", C.POINTER(C.c_float)), ("ntable_floats", C.c_uint32),
-                ("environment", C.c_int32), ("camera", MskCamera)]
+                ("environment", C.c_int32), ("camera", MskCamera), ("media", C.POINTER(MskMedium)), ("nmedia", C.c_uint32),
+                ("sensor_medium", C.c_int32)]
 
 
 class MskRenderDesc(C.Structure):
     _fields_ = [("spp", C.c_uint32), ("sample_begin", C.c_uint32), ("sample_end", C.c_uint32), ("max_depth", C.c_int32),
                 ("rr_depth", C.c_int32), ("hide_emitters", C.c_int32), ("base_seed", C.c_uint64), ("clear_film", C.c_uint32),
-                ("paths_per_batch", C.c_uint32), ("flags", C.c_uint32), ("pad_", C.c_uint32)]
+                ("paths_per_batch", C.c_uint32), ("flags", C.c_uint32), ("integrator", C.c_uint32)]
 
 
 class MskStats(C.Structure):
@@ -161,7 +167,7 @@ def check(lib, rc):
 
 
 def render_desc(spp, max_depth=-1, rr_depth=5, hide_emitters=False, base_seed=0, sample_begin=0, sample_end=None,
-                clear_film=True, paths_per_batch=0, stage_timers=False, traversal_stats=False) -> MskRenderDesc:
+                clear_film=True, paths_per_batch=0, stage_timers=False, traversal_stats=False, integrator=0) -> MskRenderDesc:
     rd = MskRenderDesc()
     rd.spp = spp
     rd.sample_begin = sample_begin
@@ -173,6 +179,7 @@ def render_desc(spp, max_depth=-1, rr_depth=5, hide_emitters=False, base_seed=0,
     rd.clear_film = int(clear_film)
     rd.paths_per_batch = paths_per_batch
     rd.flags = (RENDER_STAGE_TIMERS if stage_timers else 0) | (RENDER_TRAVERSAL_STATS if traversal_stats else 0)
+    rd.integrator = {"path": INTEGRATOR_PATH, "volpath": INTEGRATOR_VOLPATH}.get(integrator, integrator)
     return rd
 
 

@@ -166,6 +166,15 @@ int msk_gpu_scene_create(MskCtx *ctx, const MskSceneDesc *d, MskScene **out) {
         if (b.twosided && (b.type == MSK_BSDF_ROUGHDIELECTRIC || b.type == MSK_BSDF_DIELECTRIC))
             return fail(MSK_ERR_ARG, "Only materials without a transmission component can be nested!");
     }
+    if (d->nmedia > 254) return fail(MSK_ERR_UNSUPPORTED, "more than 254 media");
+    if (d->nmedia && !d->media) return fail(MSK_ERR_ARG, "media: null buffer");
+    for (uint32_t i = 0; i < d->nmedia; ++i) {
+        const MskMedium &m = d->media[i];
+        int rc;
+        if ((rc = check_spectrum(d, m.sigma_a, "medium sigma_a")) || (rc = check_spectrum(d, m.sigma_s, "medium sigma_s"))) return rc;
+        if (m.phase != MSK_PHASE_ISOTROPIC) return fail(MSK_ERR_UNSUPPORTED, "medium %u: unknown phase function %d", i, m.phase);
+    }
+    if (d->nmedia && (d->sensor_medium < -1 || d->sensor_medium >= (int32_t) d->nmedia)) return fail(MSK_ERR_ARG, "sensor medium out of range");
     int env_count = 0;
     for (uint32_t i = 0; i < d->nemitters; ++i) {
         const MskEmitter &e = d->emitters[i];
@@ -200,6 +209,11 @@ int msk_gpu_scene_create(MskCtx *ctx, const MskSceneDesc *d, MskScene **out) {
         infos[i].vert_offset = (uint32_t) nverts; infos[i].tri_offset = (uint32_t) ntris; infos[i].ntris = m.ntris;
         infos[i].bsdf = m.bsdf; infos[i].emitter = m.emitter;
         infos[i].flags = (m.has_normals ? 1u : 0u) | (m.has_uvs ? 2u : 0u);
+        if (d->nmedia) { // medium ids are only meaningful when the description carries media
+            if (m.interior_medium < -1 || m.interior_medium >= (int32_t) d->nmedia || m.exterior_medium < -1 || m.exterior_medium >= (int32_t) d->nmedia)
+                return bail(fail(MSK_ERR_ARG, "mesh %u: medium id out of range", i));
+            infos[i].flags |= (uint32_t) (m.interior_medium + 1) << 8 | (uint32_t) (m.exterior_medium + 1) << 16;
+        }
         infos[i].inv_area = 0.f; infos[i].cdf_offset = 0;
         nverts += m.nverts; ntris += m.ntris;
         if (nverts > 0xffffffffull || ntris > 0x7ffffff0ull) return bail(fail(MSK_ERR_UNSUPPORTED, "scene too large"));
@@ -285,6 +299,8 @@ int msk_gpu_scene_create(MskCtx *ctx, const MskSceneDesc *d, MskScene **out) {
         }
     }
     if ((rc = upload(s, spectra.data(), spectra.size(), &s->d.spectra))) return bail(rc);
+    if ((rc = upload(s, d->media, d->nmedia, &s->d.media))) return bail(rc);
+    s->d.sensor_medium = d->nmedia ? d->sensor_medium : -1;
     if ((rc = upload(s, d->spectrum_tables, d->ntable_floats, &s->d.tables))) return bail(rc);
     if ((rc = upload(s, cdfs.data(), cdfs.size(), &s->d.cdfs))) return bail(rc);
     if ((rc = upload(s, d->camera.filter_table, 33, &s->d.filter_table))) return bail(rc);

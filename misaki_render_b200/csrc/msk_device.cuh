@@ -34,7 +34,7 @@ struct DMeshInfo {
     uint32_t ntris;
     int32_t  bsdf;
     int32_t  emitter;
-    uint32_t flags;       // 1 = vertex normals, 2 = texcoords
+    uint32_t flags;       // 1 = vertex normals, 2 = texcoords; bits 8-15 / 16-23: interior / exterior medium + 1
     float    inv_area;    // 1 / Mesh::m_surface_area (float, sequential sum as mesh.cpp:39-48)
     uint32_t cdf_offset;  // emitter meshes: first entry of the (ntris+1)-entry area CDF in DScene::cdfs
 };
@@ -65,6 +65,7 @@ struct DScene {
     const MskBsdf   *bsdfs;
     const MskEmitter *emitters;
     const DSpectrum *spectra;
+    const MskMedium *media;   // media/homogeneous.cpp (volpath only)
     const float     *tables;
     const float     *cdfs;
     const float     *filter_table; // 33 entries
@@ -74,6 +75,7 @@ struct DScene {
     float    env_radius;
     uint32_t nmeshes;
     uint32_t bsdf_type_mask; // bit t: some mesh uses a BSDF of MskBsdfType t
+    int32_t  sensor_medium;  // medium the camera sits in, or -1 (sensor.cpp:12-18)
     uint32_t has_textures;   // some spectrum is uv-dependent (MSK_SPEC_CHECKERBOARD): resolve ids per surface point
     DCamera  cam;
 };

@@ -404,6 +404,226 @@ __global__ void __launch_bounds__(128, shade_min_blocks(KEY)) k_shade(const __gr
 }
 
 // ---------------------------------------------------------------------------------------
+// Volumetric path tracer: one iteration of VolumetricPathTracer::sample (integrators/volpath.cpp:40-165) per queue
+// entry -- free-flight sampling in the current medium (media/homogeneous.cpp:21-53), then either a medium
+// scattering event (attenuated NEE + isotropic phase sample, phase/isotropic.cpp) or the surface interaction
+// (emitter term, attenuated NEE, BSDF sample, medium transition), then Russian roulette.  The restatement decisions
+// for the stale RGB API are listed above oracle.cpp's volpath_sample and in DESIGN.md; the kernel mirrors the
+// oracle statement by statement, including the order of random draws.
+// Path state beyond the path tracer's: AUX.w carries (medium + 1) | channel << 8 | scattered << 10 | emitted << 11.
+constexpr uint32_t kVolChannelShift = 8, kVolScattered = 1u << 10, kVolEmitted = 1u << 11;
+
+__device__ __forceinline__ float spec_mean(float4 v) { return ((v.x + v.z) + (v.y + v.w)) / 4.f; } // Eigen packet reduction
+__device__ __forceinline__ float tr1(float st, float d) { return st == 0.f ? 1.f : expf(st * (-d)); }
+__device__ __forceinline__ float4 medium_tr(float4 st, float d) { // homogeneous.cpp:48,56-59
+    return make_float4(tr1(st.x, d), tr1(st.y, d), tr1(st.z, d), tr1(st.w, d));
+}
+__device__ __forceinline__ float4 medium_sigma_t(const DScene &sc, int medium, float4 wl, float4 &sigma_s) {
+    const MskMedium m = sc.media[medium];
+    const float4 sa = spectrum_eval(sc, m.sigma_a, wl);
+    sigma_s = spectrum_eval(sc, m.sigma_s, wl);
+    return sigma_s + sa; // homogeneous.cpp:17
+}
+
+__global__ void __launch_bounds__(128, 4) k_shade_vol(const __grid_constant__ DScene sc, Pool pool, BatchParams bp, int cur) {
+    Ctrl *c = pool.ctrl;
+    const int nxt = cur ^ 1;
+    uint32_t counts[kNumKeys], total = 0;
+#pragma unroll
+    for (int k = 0; k < kNumKeys; ++k) { counts[k] = c->type_count[k]; total += counts[k]; }
+    const uint32_t stride = gridDim.x * blockDim.x;
+    const uint32_t rounds = (total + stride - 1) / stride;
+    for (uint32_t it = 0; it < rounds; ++it) {
+        uint32_t idx = it * stride + blockIdx.x * blockDim.x + threadIdx.x;
+        bool valid = idx < total;
+        bool emit_ray = false, emit_shadow = false;
+        MskRay nray, sray;
+        float4 nT, nWL, nAUX, contrib;
+        uint4 nMISC;
+        uint32_t path = 0;
+        if (valid) {
+            uint32_t key = 0, j = idx;
+#pragma unroll
+            for (int k = 0; k < kNumKeys - 1; ++k)
+                if (key == (uint32_t) k && j >= counts[k]) { j -= counts[k]; key = k + 1; }
+            const uint32_t q = pool.sorted[(size_t) key * pool.capacity + j];
+            const float4 hit = pool.hit[q];
+            const float4 ro = reinterpret_cast<const float4 *>(pool.rays[cur] + q)[0];
+            const float4 rd = reinterpret_cast<const float4 *>(pool.rays[cur] + q)[1];
+            float4 T = pool.T[cur][q];
+            const float4 wl = pool.WL[cur][q];
+            const uint4 misc = pool.MISC[cur][q];
+            const float4 aux = pool.AUX[cur][q];
+            uint64_t rng = (uint64_t) misc.x | ((uint64_t) misc.y << 32);
+            path = misc.z;
+            const int depth = (int) (misc.w & 0xffffu);
+            float eta = aux.x;
+            uint32_t bits = __float_as_uint(aux.w);
+            if (depth == 1) { // volpath.cpp:35-39: initial medium = sensor->medium(), emitted_radiance = true, channel draw
+                const uint32_t channel = min((uint32_t) (next1d(rng) * 4.f), 3u);
+                bits = (uint32_t) (sc.sensor_medium + 1) | (channel << kVolChannelShift) | kVolEmitted;
+            }
+            int medium = (int) (bits & 0xffu) - 1;
+            const uint32_t channel = (bits >> kVolChannelShift) & 3u;
+            bool scattered = (bits & kVolScattered) != 0, emitted = (bits & kVolEmitted) != 0;
+            float4 L = f4(0.f);
+            bool add_L = false, alive = true;
+            const V3 rorg = v3(ro.x, ro.y, ro.z), rdir = v3(rd.x, rd.y, rd.z);
+
+            // ---- free flight: medium->sample_distance(ray::spawn(ray, 0, si.t), next1d, channel), volpath.cpp:41-43
+            bool ms_flag = false;
+            float4 sigma_t = f4(0.f), sigma_s = f4(0.f), tr = f4(1.f);
+            float ms_pdf = 1.f;
+            V3 msp = rorg;
+            if (medium >= 0) {
+                const float sample = next1d(rng);
+                sigma_t = medium_sigma_t(sc, medium, wl, sigma_s);
+                const float st_c = channel == 0 ? sigma_t.x : (channel == 1 ? sigma_t.y : (channel == 2 ? sigma_t.z : sigma_t.w));
+                float dist = -logf(1.f - sample) / st_c;
+                if (dist < hit.x) { // ray.maxt - ray.mint with mint = 0, maxt = si.t
+                    msp = rorg + rdir * dist;
+                    if (msp.x == rorg.x && msp.y == rorg.y && msp.z == rorg.z) ms_pdf = spec_mean(medium_tr(sigma_t, dist));
+                    else { ms_pdf = spec_mean(medium_tr(sigma_t, dist) * sigma_t); ms_flag = true; }
+                } else {
+                    dist = hit.x;
+                    ms_pdf = spec_mean(medium_tr(sigma_t, dist));
+                }
+                tr = medium_tr(sigma_t, dist);
+                if (hmax(tr) < 1e-20f) tr = f4(0.f);
+            }
+
+            if (ms_flag) { // ---- medium scattering event, volpath.cpp:44-74
+                T = T * (sigma_s * tr / ms_pdf);
+                const float sx = next1d(rng), sy = next1d(rng);
+                NeeSample ns = sample_emitter_direct(sc, msp, wl, sx, sy);
+                if (ns.pdf != 0.f) { // scene.cpp:136-138 + isotropic phase value 1 / 4 pi
+                    contrib = T * (ns.value * medium_tr(sigma_t, ns.dist)) * kInvFourPi;
+                    if (!is_zero(contrib)) {
+                        emit_shadow = true;
+                        sray.o[0] = msp.x; sray.o[1] = msp.y; sray.o[2] = msp.z; sray.tmin = kRayEpsilon; // scene.cpp:148
+                        sray.d[0] = ns.d.x; sray.d[1] = ns.d.y; sray.d[2] = ns.d.z;
+                        sray.tmax = ns.dist * (1.f - kShadowEpsilon);
+                    }
+                }
+                if (depth + 1 >= bp.max_depth && bp.max_depth > 0) alive = false;
+                else {
+                    const float px = next1d(rng), py = next1d(rng);
+                    const V3 wo = square_to_uniform_sphere(px, py);
+                    emit_ray = true;
+                    nray.o[0] = msp.x; nray.o[1] = msp.y; nray.o[2] = msp.z; nray.tmin = kRayEpsilon;
+                    nray.d[0] = wo.x; nray.d[1] = wo.y; nray.d[2] = wo.z; nray.tmax = MSK_INF;
+                    scattered = true;
+                }
+            } else {       // ---- surface interaction, volpath.cpp:75-155
+                if (medium >= 0) T = T * (tr / ms_pdf);
+                if (key == 0) { // escaped, :82-93
+                    if (emitted && (!bp.hide_emitters || scattered)) {
+                        float4 le = f4(0.f);
+                        if (sc.environment >= 0) {
+                            int radiance = sc.emitters[sc.environment].radiance;
+                            if (sc.has_textures) radiance = texture_resolve(sc, radiance, 0.f, 0.f);
+                            le = spectrum_eval(sc, radiance, wl);
+                        }
+                        L = T * le;
+                        if (medium >= 0) L = L * medium_tr(sigma_t, rd.w - ro.w); // eval_transmittance(ray): exp(sigma_t (mint - maxt))
+                        add_L = true;
+                    }
+                    alive = false;
+                } else {
+                    const uint32_t geom = pool.hit_geom[q];
+                    const DMeshInfo mi = sc.meshes[geom];
+                    const Surface sf = make_surface(sc, mi, __float_as_uint(hit.w), hit.y, hit.z);
+                    const V3 wi = to_local(sf.sh, -rdir);
+                    if (mi.emitter >= 0 && emitted && (!bp.hide_emitters || scattered)) { // :95-98, area.cpp:51-54
+                        int radiance = sc.emitters[mi.emitter].radiance;
+                        if (sc.has_textures) radiance = texture_resolve(sc, radiance, sf.uvx, sf.uvy);
+                        if (wi.z > 0.f) { L = T * spectrum_eval(sc, radiance, wl); add_L = true; }
+                    }
+                    MskBsdf bsdf = sc.bsdfs[mi.bsdf];
+                    if (sc.has_textures) bsdf_resolve_textures(sc, bsdf, sf.uvx, sf.uvy);
+                    if (bsdf_is_smooth(bsdf.type)) { // :104-115: attenuated NEE, added without the MIS weight
+                        const float sx = next1d(rng), sy = next1d(rng);
+                        NeeSample ns = sample_emitter_direct(sc, sf.p, wl, sx, sy);
+                        if (ns.pdf != 0.f) {
+                            const V3 wo = to_local(sf.sh, ns.d);
+                            float4 bval; float bpdf;
+                            bsdf_eval_pdf<-1>(sc, bsdf, wi, wo, wl, bval, bpdf);
+                            float4 ev = ns.value;
+                            if (medium >= 0) ev = ev * medium_tr(sigma_t, ns.dist);
+                            contrib = T * ev * bval;
+                            if (!is_zero(contrib)) {
+                                emit_shadow = true;
+                                sray.o[0] = sf.p.x; sray.o[1] = sf.p.y; sray.o[2] = sf.p.z; sray.tmin = kRayEpsilon;
+                                sray.d[0] = ns.d.x; sray.d[1] = ns.d.y; sray.d[2] = ns.d.z;
+                                sray.tmax = ns.dist * (1.f - kShadowEpsilon);
+                            }
+                        }
+                    }
+                    const float s1 = next1d(rng), s2x = next1d(rng), s2y = next1d(rng);
+                    BsdfSample bs = bsdf_sample<-1>(sc, bsdf, wi, wl, s1, s2x, s2y);
+                    if (is_zero(bs.weight)) alive = false; // :122-123
+                    else {
+                        emitted = false;
+                        bool recursive = depth + 1 < bp.max_depth || bp.max_depth < 0;
+                        if ((depth < bp.max_depth || bp.max_depth < 0) && (bs.type & BF_Delta)) { emitted = true; recursive = true; } // :129-135
+                        if (!recursive) alive = false;
+                        else {
+                            const V3 wo = to_world(sf.sh, bs.wo);
+                            T = T * bs.weight;
+                            eta *= bs.eta;
+                            const int interior = (int) ((mi.flags >> 8) & 0xffu) - 1, exterior = (int) ((mi.flags >> 16) & 0xffu) - 1;
+                            if (interior >= 0 || exterior >= 0) medium = dot(wo, sf.n) > 0.f ? exterior : interior; // interaction.cpp:10-13
+                            emit_ray = true;
+                            nray.o[0] = sf.p.x; nray.o[1] = sf.p.y; nray.o[2] = sf.p.z; nray.tmin = (1.f + max_abs(sf.p)) * kRayEpsilon;
+                            nray.d[0] = wo.x; nray.d[1] = wo.y; nray.d[2] = wo.z; nray.tmax = MSK_INF;
+                            scattered = true;
+                        }
+                    }
+                }
+            }
+            if (alive && emit_ray && depth + 1 >= bp.rr_depth) { // :158-164
+                const float qq = fminf(hmax(T) * eta * eta, 0.95f);
+                if (next1d(rng) >= qq) emit_ray = false;
+                else T = T / qq;
+            }
+            if (bp.max_depth > 0 && depth + 1 > bp.max_depth) emit_ray = false; // loop condition :40
+            if (!alive) emit_ray = false;
+            if (emit_ray) {
+                bits = (uint32_t) (medium + 1) | (channel << kVolChannelShift) | (scattered ? kVolScattered : 0u) | (emitted ? kVolEmitted : 0u);
+                nT = T; nWL = wl;
+                nMISC = make_uint4((uint32_t) rng, (uint32_t) (rng >> 32), path, (uint32_t) (depth + 1));
+                nAUX = make_float4(eta, 0.f, 0.f, __uint_as_float(bits));
+            }
+            if (add_L) { float4 acc = pool.L[path]; pool.L[path] = acc + L; }
+        }
+        uint32_t m_ray = __ballot_sync(0xffffffffu, emit_ray), m_sh = __ballot_sync(0xffffffffu, emit_shadow);
+        uint32_t base_ray = 0, base_sh = 0;
+        if (lane_id() == 0) {
+            if (m_ray) base_ray = atomicAdd(&c->n_rays[nxt], (uint32_t) __popc(m_ray));
+            if (m_sh) base_sh = atomicAdd(&c->n_shadow, (uint32_t) __popc(m_sh));
+        }
+        base_ray = __shfl_sync(0xffffffffu, base_ray, 0);
+        base_sh  = __shfl_sync(0xffffffffu, base_sh, 0);
+        const uint32_t below = (1u << lane_id()) - 1u;
+        if (emit_ray) {
+            uint32_t o = base_ray + __popc(m_ray & below);
+            float4 *rp = reinterpret_cast<float4 *>(pool.rays[nxt] + o);
+            rp[0] = make_float4(nray.o[0], nray.o[1], nray.o[2], nray.tmin);
+            rp[1] = make_float4(nray.d[0], nray.d[1], nray.d[2], nray.tmax);
+            pool.T[nxt][o] = nT; pool.WL[nxt][o] = nWL; pool.MISC[nxt][o] = nMISC; pool.AUX[nxt][o] = nAUX;
+        }
+        if (emit_shadow) {
+            uint32_t o = base_sh + __popc(m_sh & below);
+            float4 *rp = reinterpret_cast<float4 *>(pool.sh_ray + o);
+            rp[0] = make_float4(sray.o[0], sray.o[1], sray.o[2], sray.tmin);
+            rp[1] = make_float4(sray.d[0], sray.d[1], sray.d[2], sray.tmax);
+            pool.sh_contrib[o] = contrib;
+            pool.sh_path[o]    = path;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
 // NEE visibility (Scene::ray_test, scene.cpp:90-98,255-273) fused with the accumulation of
 // the NEE term (path.cpp:63-66).
 template <bool STATS>
@@ -789,6 +1009,7 @@ int Renderer::render(cudaStream_t stream, const DScene &sc, const MskRenderDesc 
     const uint64_t npix64 = (uint64_t) W * H;
     if (!W || !H || npix64 > (1ull << 27)) return fail(MSK_ERR_UNSUPPORTED, "film size %ux%u unsupported", W, H);
     if (rd.sample_end < rd.sample_begin || rd.sample_end > rd.spp) return fail(MSK_ERR_ARG, "bad sample range");
+    if (rd.integrator > MSK_INTEGRATOR_VOLPATH) return fail(MSK_ERR_ARG, "unknown integrator %u", rd.integrator);
     if (rd.rr_depth <= 0) return fail(MSK_ERR_ARG, "\"rr_depth\" must be set to a value greater than zero!");
     if (rd.max_depth < 0 && rd.max_depth != -1) return fail(MSK_ERR_ARG, "\"max_depth\" must be set to -1 (infinite) or a value >= 0");
     const uint32_t npix = (uint32_t) npix64;
@@ -881,7 +1102,9 @@ int Renderer::render(cudaStream_t stream, const DScene &sc, const MskRenderDesc 
             // the AOV integrator shares the primary hit with the nested path tracer (the reference intersects twice)
             if (aov && bounce == 0) MSK_STAGE(ST_FILM, (k_aov_capture<<<(n + 255) / 256, 256, 0, stream>>>(sc, pool, bp, plan)));
             if (!MSK_SORT_IN_COMMIT) MSK_STAGE(ST_SORT, (k_sort<<<im.sm_count * 4, kSortThreads, 0, stream>>>(sc, pool, cur)));
-            if (im.spec_shade && n_est >= im.spec_min) {
+            if (rd.integrator == MSK_INTEGRATOR_VOLPATH) {
+                MSK_STAGE(ST_SHADE, (k_shade_vol<<<pb, 128, 0, stream>>>(sc, pool, bp, cur)));
+            } else if (im.spec_shade && n_est >= im.spec_min) {
                 const uint32_t keys = 1u | (sc.bsdf_type_mask << 1);
 #define MSK_SHADE_KEY(K) if (keys & (1u << K)) MSK_STAGE(ST_SHADE, (k_shade<K><<<pb, 128, 0, stream>>>(sc, pool, bp, cur)))
                 MSK_SHADE_KEY(0); MSK_SHADE_KEY(1); MSK_SHADE_KEY(2); MSK_SHADE_KEY(3); MSK_SHADE_KEY(4); MSK_SHADE_KEY(5);

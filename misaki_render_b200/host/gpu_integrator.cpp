@@ -22,7 +22,6 @@ public:
 protected:
     explicit SamplingIntegrator(const Properties &props) : Integrator(props) { // integrator.cpp:17-29
         m_block_size = (uint32_t) props.int_("block_size", 32);
-        // <boolean> is dropped by the loader (as in the reference), so this is false unless set programmatically
         m_hide_emitters = props.bool_("hide_emitters", false);
     }
     uint32_t m_block_size;
@@ -95,7 +94,7 @@ static void gpu_render(Scene *scene, Sensor *sensor, const MskRenderDesc &rd, in
         stats.paths / (stats.ms_render * 1e3), rays / (stats.ms_render * 1e3), (unsigned long long) stats.kernel_launches);
 }
 
-class GpuPathIntegrator final : public MonteCarloIntegrator {
+class GpuPathIntegrator : public MonteCarloIntegrator {
 public:
     explicit GpuPathIntegrator(const Properties &props) : MonteCarloIntegrator(props) {
         // The reference's PathTracer shadows m_max_depth / m_rr_depth with private members (-1 / 5), so the
@@ -114,6 +113,7 @@ public:
         rd.max_depth = m_max_depth; rd.rr_depth = m_rr_depth; rd.hide_emitters = m_hide_emitters;
         rd.base_seed = sensor->sampler()->base_seed();
         rd.clear_film = 1;
+        rd.integrator = m_integrator;
     }
 
     bool render(Scene *scene, Sensor *sensor) override {
@@ -125,12 +125,24 @@ public:
     const MskStats &stats() const { return m_stats; }
     int device() const { return m_device; }
     MSK_DECLARE_CLASS()
+protected:
+    uint32_t m_integrator = MSK_INTEGRATOR_PATH;
 private:
     int m_device;
     int64_t m_sample_begin, m_sample_end;
     MskStats m_stats{};
 };
 MSK_IMPLEMENT_PLUGIN(GpuPathIntegrator, MonteCarloIntegrator, "path")
+
+// The "volpath" integrator plugin: reference src/librender/integrators/volpath.cpp (VolumetricPathTracer,
+// MSK_REGISTER_INSTANCE(VolumetricPathTracer, "volpath") :182) -- same parameters and render() contract, the
+// wavefront runs k_shade_vol (homogeneous media + isotropic phase function) instead of the path tracer's k_shade.
+class GpuVolPathIntegrator final : public GpuPathIntegrator {
+public:
+    explicit GpuVolPathIntegrator(const Properties &props) : GpuPathIntegrator(props) { m_integrator = MSK_INTEGRATOR_VOLPATH; }
+    MSK_DECLARE_CLASS()
+};
+MSK_IMPLEMENT_PLUGIN(GpuVolPathIntegrator, GpuPathIntegrator, "volpath")
 
 // The "aov" integrator plugin: reference src/librender/integrators/aov.cpp (AOVIntegrator,
 // MSK_REGISTER_INSTANCE(AOVIntegrator, "aov") :156).  The constructor follows aov.cpp:30-85: the "aovs" string is a

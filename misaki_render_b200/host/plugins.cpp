@@ -19,6 +19,8 @@ namespace misaki {
 MSK_IMPLEMENT_CLASS(Texture, Object, "texture")
 MSK_IMPLEMENT_CLASS(BSDF, Object, "bsdf")
 MSK_IMPLEMENT_CLASS(Emitter, Object, "emitter")
+MSK_IMPLEMENT_CLASS(PhaseFunction, Object, "phase")
+MSK_IMPLEMENT_CLASS(Medium, Object, "medium")
 MSK_IMPLEMENT_CLASS(Shape, Object, "shape")
 MSK_IMPLEMENT_CLASS(Mesh, Shape)
 MSK_IMPLEMENT_CLASS(ReconstructionFilter, Object, "rfilter")
@@ -45,12 +47,21 @@ Shape::Shape(const Properties &props) : m_id(props.id()) { // shape.cpp:14-48
     for (auto &[name, obj] : props.objects()) {
         auto *emitter = dynamic_cast<Emitter *>(obj.get());
         auto *bsdf = dynamic_cast<BSDF *>(obj.get());
+        auto *medium = dynamic_cast<Medium *>(obj.get());
         if (emitter) {
             if (m_emitter) Throw("Only one light can be specified by a shape.");
             m_emitter = emitter;
         } else if (bsdf) {
             if (m_bsdf) Throw("Only one bsdf can be specified by a shape.");
             m_bsdf = bsdf;
+        } else if (medium) { // shape.cpp:28-40: children named "interior" / "exterior"; other names are dropped
+            if (name == "interior") {
+                if (m_interior_medium) Throw("Only a single interior medium can be specified per shape.");
+                m_interior_medium = medium;
+            } else if (name == "exterior") {
+                if (m_exterior_medium) Throw("Only a single exterior medium can be specified per shape.");
+                m_exterior_medium = medium;
+            }
         } else {
             Throw("Tired to add unsuppored object of type \"%s\"", obj->to_string().c_str());
         }
@@ -58,6 +69,17 @@ Shape::Shape(const Properties &props) : m_id(props.id()) { // shape.cpp:14-48
     if (!m_bsdf) m_bsdf = InstanceManager::get()->create_instance<BSDF>(Properties("diffuse"));
 }
 void Shape::set_children() { if (m_emitter) m_emitter->set_shape(this); }
+
+Medium::Medium(const Properties &props) : m_id(props.id()) { // medium.cpp:13-31
+    for (auto &[name, obj] : props.objects()) {
+        auto *phase = dynamic_cast<PhaseFunction *>(obj.get());
+        if (phase) {
+            if (m_phase_function) Throw("Only a single phase function can be specified per medium");
+            m_phase_function = phase;
+        }
+    }
+    if (!m_phase_function) m_phase_function = InstanceManager::get()->create_instance<PhaseFunction>(Properties("isotropic"));
+}
 
 Mesh::Mesh(const Properties &props) : Shape(props) { m_to_world = props.transform("to_world", Transform4f()); } // mesh.cpp:11-13
 
@@ -84,7 +106,11 @@ Sensor::Sensor(const Properties &props) { // sensor.cpp:9-44
     for (auto &[name, obj] : props.objects()) {
         auto *film = dynamic_cast<Film *>(obj.get());
         auto *sampler = dynamic_cast<Sampler *>(obj.get());
-        if (film) {
+        auto *medium = dynamic_cast<Medium *>(obj.get());
+        if (medium) { // sensor.cpp:12-18
+            if (m_medium) Throw("Only a single medium can be specified per endpoint");
+            m_medium = medium;
+        } else if (film) {
             if (m_film) Throw("Camera can only have one film.");
             m_film = film;
         } else if (sampler) {
@@ -478,6 +504,42 @@ public:
 MSK_IMPLEMENT_PLUGIN(AreaLight, Emitter, "area")
 MSK_IMPLEMENT_PLUGIN(ConstantBackgroundEmitter, Emitter, "constant")
 
+// =========================================================================================== media
+class IsotropicPhaseFunction final : public PhaseFunction { // phase/isotropic.cpp:9-36
+public:
+    explicit IsotropicPhaseFunction(const Properties &props) : PhaseFunction(props) {}
+    MskPhaseType gpu_type() const override { return MSK_PHASE_ISOTROPIC; }
+    MSK_DECLARE_CLASS()
+};
+MSK_IMPLEMENT_PLUGIN(IsotropicPhaseFunction, PhaseFunction, "isotropic")
+
+// media/homogeneous.cpp:10-19.  The reference reads sigma_a / sigma_s with props.color() (an RGB triple of the stale
+// RGB pipeline, default 1); on the spectral pipeline they are textures like every other colour parameter: <rgb>
+// gives an UNBOUNDED upsampled spectrum (coefficients, not reflectances -- the conductor eta / k rule), <float> /
+// <spectrum> a uniform / tabulated one.  "scale" is read and stored but never applied, as in the reference.
+class HomogeneousMedium final : public Medium {
+public:
+    explicit HomogeneousMedium(const Properties &props) : Medium(props) {
+        m_sigma_a = props.texture("sigma_a", 1.f);
+        m_sigma_s = props.texture("sigma_s", 1.f);
+        m_scale = props.float_("scale", 1.f);
+    }
+    void describe(GpuSceneBuilder &b, MskMedium &out) const override {
+        bool saved = b.within_conductor;
+        b.within_conductor = true; // unbounded spectra
+        out.sigma_a = m_sigma_a->describe(b);
+        out.sigma_s = m_sigma_s->describe(b);
+        b.within_conductor = saved;
+        out.phase = m_phase_function->gpu_type();
+        out.scale = m_scale;
+    }
+    MSK_DECLARE_CLASS()
+private:
+    ref<Texture> m_sigma_a, m_sigma_s;
+    float m_scale;
+};
+MSK_IMPLEMENT_PLUGIN(HomogeneousMedium, Medium, "homogeneous")
+
 // =========================================================================================== obj shape
 static int to_uint(const std::string &str) { // shapes/obj.cpp:11-17; a leading '-' (relative index) is kept signed
     char *end_ptr = nullptr;
@@ -779,8 +841,11 @@ GpuSceneBuilder::GpuSceneBuilder(const Scene *scene) {
             m_emitters[m.emitter].shape = (int) m_meshes.size();
         }
         m.has_normals = mesh->has_vertex_normals(); m.has_uvs = mesh->has_vertex_texcoords();
+        m.interior_medium = medium_id(mesh->interior_medium());
+        m.exterior_medium = medium_id(mesh->exterior_medium());
         m_meshes.push_back(m);
     }
+    m_desc.sensor_medium = medium_id(scene->sensor()->medium());
     scene->sensor()->describe(m_desc.camera);
     finish();
 }
@@ -816,7 +881,17 @@ int GpuSceneBuilder::bsdf_id(const BSDF *b) {
     m_bsdf_ids[b] = id;
     return id;
 }
+int GpuSceneBuilder::medium_id(const Medium *m) {
+    if (!m) return -1;
+    auto it = m_medium_ids.find(m);
+    if (it != m_medium_ids.end()) return it->second;
+    MskMedium d{};
+    m->describe(*this, d);
+    m_media.push_back(d);
+    return m_medium_ids[m] = (int) m_media.size() - 1;
+}
 void GpuSceneBuilder::finish() {
+    m_desc.media = m_media.data(); m_desc.nmedia = (uint32_t) m_media.size();
     m_desc.meshes = m_meshes.data(); m_desc.nmeshes = (uint32_t) m_meshes.size();
     m_desc.bsdfs = m_bsdfs.data(); m_desc.nbsdfs = (uint32_t) m_bsdfs.size();
     m_desc.emitters = m_emitters.data(); m_desc.nemitters = (uint32_t) m_emitters.size();

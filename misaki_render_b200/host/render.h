@@ -55,9 +55,33 @@ protected:
     Transform4f m_world_transform;
 };
 
+// ---- PhaseFunction / Medium (reference include/misaki/render/phase.h, medium.h; src/librender/phase.cpp, medium.cpp)
+class PhaseFunction : public Object {
+public:
+    virtual MskPhaseType gpu_type() const = 0;
+    MSK_DECLARE_CLASS()
+protected:
+    explicit PhaseFunction(const Properties &props) : m_id(props.id()) {}
+    std::string m_id;
+};
+
+class Medium : public Object {
+public:
+    const PhaseFunction *phase_function() const { return m_phase_function.get(); }
+    virtual void describe(GpuSceneBuilder &b, MskMedium &out) const = 0;
+    MSK_DECLARE_CLASS()
+protected:
+    explicit Medium(const Properties &props); // medium.cpp:13-31
+    ref<PhaseFunction> m_phase_function;
+    std::string m_id;
+};
+
 // ---- Shape / Mesh (reference include/misaki/render/shape.h, mesh.h)
 class Shape : public Object {
 public:
+    bool is_medium_transition() const { return m_interior_medium || m_exterior_medium; } // shape.h:35-38
+    const Medium *interior_medium() const { return m_interior_medium.get(); }
+    const Medium *exterior_medium() const { return m_exterior_medium.get(); }
     bool is_emitter() const { return (bool) m_emitter; }
     Emitter *emitter() const { return m_emitter.get(); }
     const BSDF *bsdf() const { return m_bsdf.get(); }
@@ -67,6 +91,7 @@ protected:
     explicit Shape(const Properties &props);
     ref<BSDF> m_bsdf;
     ref<Emitter> m_emitter;
+    ref<Medium> m_interior_medium, m_exterior_medium;
     Transform4f m_world_transform;
     std::string m_id;
 };
@@ -158,6 +183,7 @@ class Sensor : public Object {
 public:
     Film *film() const { return m_film.get(); }
     Sampler *sampler() const { return m_sampler.get(); }
+    const Medium *medium() const { return m_medium.get(); } // sensor.h:45-46
     virtual void describe(MskCamera &cam) const = 0;
     MSK_DECLARE_CLASS()
 protected:
@@ -165,6 +191,7 @@ protected:
     Transform4f m_world_transform;
     ref<Film> m_film;
     ref<Sampler> m_sampler;
+    ref<Medium> m_medium;
     float m_aspect = 1.f;
 };
 
@@ -205,6 +232,7 @@ public:
     // memoised by object identity so shared (referenced) plugins are described once
     int spectrum_id(const Texture *t);
     int bsdf_id(const BSDF *b);
+    int medium_id(const Medium *m); // -1 for nullptr
     bool within_conductor = false; // conductor eta / k: unbounded spectra (builder decision)
 
 private:
@@ -214,7 +242,8 @@ private:
     std::vector<MskEmitter> m_emitters;
     std::vector<MskSpectrum> m_spectra;
     std::vector<float> m_tables;
-    std::map<const void *, int> m_spectrum_ids, m_bsdf_ids;
+    std::vector<MskMedium> m_media;
+    std::map<const void *, int> m_spectrum_ids, m_bsdf_ids, m_medium_ids;
     void finish();
 };
 

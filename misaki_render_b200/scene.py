@@ -98,6 +98,8 @@ class SceneDescription:
         self.emitters: list[capi.MskEmitter] = []
         self.meshes: list[dict] = []
         self.environment = -1
+        self.media: list[capi.MskMedium] = []
+        self.sensor_medium = -1
         self._keep = []
         self._cdesc = None
 
@@ -207,9 +209,20 @@ class SceneDescription:
                               transmittance=self._as_spectrum(specular_transmittance), ior=(int_ior, ext_ior))
 
     # ---- shapes / emitters ------------------------------------------------------------
-    def add_mesh(self, verts, tris, bsdf, radiance=None, has_normals=False, has_uvs=False):
+    def add_medium(self, sigma_a, sigma_s, scale=1.0):
+        """"homogeneous" medium (media/homogeneous.cpp:12-19) with the default isotropic phase function
+        (medium.cpp:24-29).  sigma_a / sigma_s: rgb tuples (-> unbounded spectra: coefficients are not reflectances),
+        floats (uniform) or spectrum ids."""
+        m = capi.MskMedium()
+        m.sigma_a, m.sigma_s = self._as_spectrum(sigma_a, True), self._as_spectrum(sigma_s, True)
+        m.phase, m.scale = 0, float(scale)
+        self.media.append(m)
+        self._cdesc = None
+        return len(self.media) - 1
+
+    def add_mesh(self, verts, tris, bsdf, radiance=None, has_normals=False, has_uvs=False, interior_medium=-1, exterior_medium=-1):
         """verts: (N, 8) or (N, 3) float32 world-space; tris: (M, 3) uint32.  radiance: rgb tuple or a
-        spectrum id -> attaches an area emitter (emitters/area.cpp)."""
+        spectrum id -> attaches an area emitter (emitters/area.cpp).  interior/exterior_medium: shape.cpp:28-39."""
         verts = np.asarray(verts, dtype=f32)
         if verts.shape[1] == 3:
             v8 = np.zeros((verts.shape[0], 8), dtype=f32)
@@ -224,7 +237,8 @@ class SceneDescription:
             e.type, e.radiance, e.shape = capi.EMITTER_AREA, spec, len(self.meshes)
             self.emitters.append(e)
             emitter = len(self.emitters) - 1
-        self.meshes.append(dict(verts=verts, tris=tris, bsdf=bsdf, emitter=emitter, has_normals=has_normals, has_uvs=has_uvs))
+        self.meshes.append(dict(verts=verts, tris=tris, bsdf=bsdf, emitter=emitter, has_normals=has_normals, has_uvs=has_uvs,
+                                interior_medium=int(interior_medium), exterior_medium=int(exterior_medium)))
         self._cdesc = None
         return len(self.meshes) - 1
 
@@ -267,6 +281,7 @@ class SceneDescription:
             meshes[i].nverts, meshes[i].ntris = m["verts"].shape[0], m["tris"].shape[0]
             meshes[i].bsdf, meshes[i].emitter = m["bsdf"], m["emitter"]
             meshes[i].has_normals, meshes[i].has_uvs = int(m["has_normals"]), int(m["has_uvs"])
+            meshes[i].interior_medium, meshes[i].exterior_medium = m.get("interior_medium", -1), m.get("exterior_medium", -1)
         bsdfs = (capi.MskBsdf * max(len(self.bsdfs), 1))(*self.bsdfs)
         emitters = (capi.MskEmitter * max(len(self.emitters), 1))(*self.emitters)
         spectra = (capi.MskSpectrum * max(len(self.spectra), 1))(*self.spectra)
@@ -279,6 +294,8 @@ class SceneDescription:
         d.ntable_floats = int(tables.size) if self.tables else 0
         d.environment = self.environment
         d.camera = self.camera()
-        self._keep = [meshes, bsdfs, emitters, spectra, tables]
+        media = (capi.MskMedium * max(len(self.media), 1))(*self.media)
+        d.media, d.nmedia, d.sensor_medium = media, len(self.media), int(self.sensor_medium)
+        self._keep = [meshes, bsdfs, emitters, spectra, tables, media]
         self._cdesc = d
         return d

@@ -141,6 +141,7 @@ struct OMesh {
     uint32_t nverts = 0, ntris = 0;
     int bsdf = 0, emitter = -1;
     bool has_normals = false, has_uvs = false;
+    int interior_medium = -1, exterior_medium = -1; // shape.cpp:28-39
     std::vector<float> cdf; // Distribution1D::m_cdf, distribution.h:84-93
     float surface_area = 0.f;
     V3 pos(uint32_t i) const { return { verts[i * 8], verts[i * 8 + 1], verts[i * 8 + 2] }; }
@@ -162,6 +163,8 @@ struct OScene {
     std::vector<MskEmitter> emitters;
     std::vector<OSpectrum> spectra;
     int environment = -1;
+    std::vector<MskMedium> media; // media/homogeneous.cpp
+    int sensor_medium = -1;       // sensor.cpp:12-18
     MskCamera cam;
     V3 bbox_min, bbox_max;
     float env_radius = 0.f; // constant.cpp:21-28
@@ -824,7 +827,7 @@ inline float mis_weight(float pdf_a, float pdf_b) { // :127-131
     return pdf_a > 0.f ? pdf_a / (pdf_a + pdf_b) : 0.f;
 }
 
-struct PathParams { int max_depth, rr_depth; bool hide_emitter; };
+struct PathParams { int max_depth, rr_depth; bool hide_emitter; int integrator = MSK_INTEGRATOR_PATH; };
 
 Spec path_sample(const OScene &sc, Sampler &sampler, const Ray &ray_, const PathParams &pp, RayCounters &rc) {
     Ray ray = ray_;
@@ -906,6 +909,181 @@ Spec path_sample(const OScene &sc, Sampler &sampler, const Ray &ray_, const Path
         }
     }
     return result;
+}
+
+// ------------------------------------------------------------------------------------------
+// Volumetric path tracer: integrators/volpath.cpp:26-167 with media/homogeneous.cpp, phase/isotropic.cpp and
+// Scene::sample_attenuated_emitter_direct / eval_transmittance (scene.cpp:114-184).  SURVEY 8f rank 4.
+//
+// The plugin is written against a stale API (RGB Spectrum, ray::spawn, MediumSample-based phase functions) and is
+// commented out of the reference build (src/librender/CMakeLists.txt:106-112), so it is restated on the current
+// spectral types with these decisions, shared with the GPU kernel:
+//  * sigma_a / sigma_s are spectra evaluated at the path's four wavelengths; `channel` (volpath.cpp:39,
+//    min(next1d * 3, 3 - 1) over RGB) becomes min(next1d * 4, 3) over the four wavelengths (Spectrum::Size)
+//  * `.mean()` is Eigen's packet reduction ((v0 + v2) + (v1 + v3)) / 4, like spectrum_to_xyz
+//  * ray::spawn(ray, 0, si.t) = the same ray over [0, si.t]; ray::spawn<false>(p, d) = Ray(p, d, RayEpsilon, inf)
+//  * medium NEE (volpath.cpp:50-51) passes the SURFACE interaction `si` as the reference point -- whose p is
+//    uninitialised when the ray escaped; the evident intent (a medium interaction at ms.p) is used instead
+//  * no compiled BSDF carries the Null flag (bsdfs/mask.cpp is not built), so eval_transmittance's loop
+//    (scene.cpp:152-182) reduces to: any surface within [RayEpsilon, dist (1 - ShadowEpsilon)] -> 0, else
+//    exp(-sigma_t dist) when the reference point lies in a medium
+//  * exp(sigma_t * -inf) with sigma_t == 0 is NaN in the reference (homogeneous.cpp:56-59 on an escaped ray);
+//    a channel without extinction transmits 1 here
+// Kept as written: `scale` is read and never applied (homogeneous.cpp:18); NEE is added WITHOUT the MIS weight
+// that is computed next to it (volpath.cpp:105-109) and emitter hits are added whenever `emitted_radiance` is set
+// (initially, and after a delta bounce; a medium scattering event leaves the flag untouched, :44-74); Russian
+// roulette uses depth + 1 >= rr_depth (:158).
+struct MediumSample { float t = Infinity; V3 p; Spec sigma_s, transmittance; float pdf = 0.f; };
+
+inline float spec_mean(const Spec &v) { return ((v[0] + v[2]) + (v[1] + v[3])) / 4.f; }
+// exp(sigma_t * -d), homogeneous.cpp:48,56-59 (with the zero-extinction guard above)
+inline Spec medium_tr(const Spec &sigma_t, float d) {
+    Spec r;
+    for (int i = 0; i < 4; ++i) r[i] = sigma_t[i] == 0.f ? 1.f : std::exp(sigma_t[i] * (-d));
+    return r;
+}
+inline Spec medium_sigma_t(const OScene &sc, int medium, const Spec &wl, Spec *sigma_s = nullptr) {
+    const MskMedium &m = sc.media[medium];
+    Spec sa = spectrum_eval(sc.spectra[m.sigma_a], wl), ss = spectrum_eval(sc.spectra[m.sigma_s], wl);
+    if (sigma_s) *sigma_s = ss;
+    return ss + sa; // homogeneous.cpp:17
+}
+
+// homogeneous.cpp:21-53
+std::pair<bool, MediumSample> medium_sample_distance(const OScene &sc, int medium, const Ray &ray, float sample, uint32_t channel) {
+    MediumSample ms;
+    Spec sigma_s, sigma_t = medium_sigma_t(sc, medium, ray.wavelengths, &sigma_s);
+    float sampled_distance = -std::log(1 - sample) / sigma_t[channel];
+    bool success = true;
+    if (sampled_distance < ray.maxt - ray.mint) {
+        ms.t       = sampled_distance + ray.mint;
+        ms.p       = ray.o + ray.d * ms.t;
+        if (ms.p.x == ray.o.x && ms.p.y == ray.o.y && ms.p.z == ray.o.z) {
+            ms.t    = Infinity;
+            ms.pdf  = spec_mean(medium_tr(sigma_t, sampled_distance));
+            success = false;
+        } else
+            ms.pdf = spec_mean(medium_tr(sigma_t, sampled_distance) * sigma_t);
+    } else {
+        ms.t             = Infinity;
+        sampled_distance = ray.maxt - ray.mint;
+        ms.pdf           = spec_mean(medium_tr(sigma_t, sampled_distance));
+        success          = false;
+    }
+    ms.sigma_s       = sigma_s;
+    ms.transmittance = medium_tr(sigma_t, sampled_distance);
+    if (ms.transmittance.max_coeff() < 1e-20f) ms.transmittance = Spec(0.f);
+    return { success, ms };
+}
+
+// scene.cpp:114-184 with the reductions stated above; `ref_p` is the surface point or ms.p
+std::pair<DirectIllumSample, Spec> sample_attenuated_emitter_direct(const OScene &sc, const SceneInteraction &ref, int medium, V2 sample,
+                                                                    RayCounters &rc) {
+    DirectIllumSample ds;
+    Spec spec(0.f);
+    size_t ne = sc.emitters.size();
+    if (ne == 0) return { ds, spec };
+    if (ne == 1) {
+        std::tie(ds, spec) = emitter_sample_direct(sc, 0, ref, sample);
+    } else {
+        float light_sel_pdf = 1.f / ne;
+        uint32_t index = std::min(uint32_t(sample.x * (float) ne), (uint32_t) ne - 1);
+        sample.x = (sample.x - index * light_sel_pdf) * ne;
+        std::tie(ds, spec) = emitter_sample_direct(sc, (int) index, ref, sample);
+        ds.pdf *= light_sel_pdf;
+        spec *= (float) ne;
+    }
+    if (ds.pdf != 0.f) { // eval_transmittance(ref.p, ds.p, medium), scene.cpp:141-184
+        V3 d = ds.p - ref.p;
+        float remaining = norm(d);
+        d = d / remaining;
+        Ray ray{ ref.p, d, RayEpsilon, remaining * (1 - ShadowEpsilon), ref.wavelengths };
+        if (ray_test(sc, ray, rc)) spec = Spec(0.f); // a surface without the Null flag blocks the segment (:156-158)
+        else if (medium >= 0) spec = spec * medium_tr(medium_sigma_t(sc, medium, ref.wavelengths), remaining); // :159-164
+    }
+    return { ds, spec };
+}
+
+Spec volpath_sample(const OScene &sc, Sampler &sampler, const Ray &ray_, const PathParams &pp, RayCounters &rc) {
+    Ray ray = ray_;
+    Spec throughput(1.f), result(0.f);
+    float eta  = 1.f;
+    int medium = sc.sensor_medium; // integrator.cpp:116: sample(scene, sampler, ray, sensor->medium(), ...)
+    bool ms_flag = false, scattered = false, emitted_radiance = true;
+    SceneInteraction si = ray_intersect(sc, ray, rc);
+    MediumSample ms;
+    uint32_t channel = std::min<uint32_t>((uint32_t) (sampler.next1d() * 4), 4 - 1);
+    for (int depth = 1; depth <= pp.max_depth || pp.max_depth < 0; depth++) {
+        if (medium >= 0) {
+            Ray seg{ ray.o, ray.d, 0.f, si.t, ray.wavelengths };
+            std::tie(ms_flag, ms) = medium_sample_distance(sc, medium, seg, sampler.next1d(), channel);
+        }
+        if (medium >= 0 && ms_flag) {
+            throughput *= ms.sigma_s * ms.transmittance / ms.pdf;
+            SceneInteraction mi; // medium interaction at ms.p (see the header comment)
+            mi.p = ms.p; mi.wavelengths = ray.wavelengths;
+            auto [ds, spec] = sample_attenuated_emitter_direct(sc, mi, medium, sampler.next2d(), rc);
+            if (!spec.is_zero()) result += throughput * spec * InvFourPi; // isotropic.cpp:24-27
+            if (depth + 1 >= pp.max_depth && pp.max_depth > 0) break;
+            V2 s2       = sampler.next2d();
+            V3 phase_wo = square_to_uniform_sphere(s2); // isotropic.cpp:16-22, phase_val = 1
+            ray         = Ray{ ms.p, phase_wo, RayEpsilon, Infinity, ray.wavelengths };
+            si          = ray_intersect(sc, ray, rc);
+            scattered   = true;
+        } else {
+            if (medium >= 0) throughput *= ms.transmittance / ms.pdf;
+            if (!si.is_valid()) {
+                if (emitted_radiance && (!pp.hide_emitter || scattered)) {
+                    Spec value = throughput * (sc.environment >= 0 ? emitter_eval(sc, sc.environment, si) : Spec(0.f));
+                    if (medium >= 0) value = value * medium_tr(medium_sigma_t(sc, medium, ray.wavelengths), ray.maxt - ray.mint);
+                    result += value;
+                }
+                break;
+            }
+            const OMesh &mesh = sc.meshes[si.shape];
+            if (mesh.emitter >= 0 && emitted_radiance && (!pp.hide_emitter || scattered))
+                result += throughput * emitter_eval(sc, mesh.emitter, si);
+            const MskBsdf &bsdf = sc.bsdfs[mesh.bsdf];
+            if (bsdf_flags(bsdf) & F_Smooth) {
+                auto [ds, emitter_val] = sample_attenuated_emitter_direct(sc, si, medium, sampler.next2d(), rc);
+                if (ds.pdf != 0.f) {
+                    V3 wo         = si.to_local(ds.d);
+                    Spec bsdf_val = bsdf_eval(sc, bsdf, si, wo);
+                    result += throughput * emitter_val * bsdf_val; // the MIS weight of :108 is computed and unused
+                }
+            }
+            float s1 = sampler.next1d();
+            V2 s2    = sampler.next2d();
+            auto [bs, bsdf_val] = bsdf_sample(sc, bsdf, si, s1, s2);
+            if (bsdf_val.is_zero()) break;
+            emitted_radiance = false;
+            bool recursive   = depth + 1 < pp.max_depth || pp.max_depth < 0;
+            // :129-138 with Null never set: a delta bounce re-enables directly seen emitters
+            if ((depth < pp.max_depth || pp.max_depth < 0) && (bs.sampled_type & F_Delta)) {
+                emitted_radiance = true;
+                recursive        = true;
+            }
+            if (!recursive) break;
+            V3 wo = si.to_world(bs.wo);
+            throughput *= bsdf_val;
+            eta *= bs.eta;
+            if (mesh.interior_medium >= 0 || mesh.exterior_medium >= 0) // interaction.cpp:10-13
+                medium = dot(wo, si.n) > 0 ? mesh.exterior_medium : mesh.interior_medium;
+            ray       = si.spawn_ray(wo);
+            si        = ray_intersect(sc, ray, rc);
+            scattered = true; // |= !Null
+        }
+        if (depth + 1 >= pp.rr_depth) {
+            float q = std::min(throughput.max_coeff() * eta * eta, 0.95f);
+            if (sampler.next1d() >= q) break;
+            throughput /= q;
+        }
+    }
+    return result;
+}
+
+Spec integrator_sample(const OScene &sc, Sampler &sampler, const Ray &ray, const PathParams &pp, RayCounters &rc) {
+    return pp.integrator == MSK_INTEGRATOR_VOLPATH ? volpath_sample(sc, sampler, ray, pp, rc) : path_sample(sc, sampler, ray, pp, rc);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1037,6 +1215,13 @@ int orc_scene_create(const MskSceneDesc *d, OrcScene **out) {
         }
         sc.spectra.push_back(std::move(o));
     }
+    for (uint32_t i = 0; i < d->nmedia; ++i) {
+        const MskMedium &m = d->media[i];
+        if (m.sigma_a < 0 || (uint32_t) m.sigma_a >= d->nspectra || m.sigma_s < 0 || (uint32_t) m.sigma_s >= d->nspectra) return fail("bad medium spectrum");
+        if (m.phase != MSK_PHASE_ISOTROPIC) return fail("unknown phase function");
+        sc.media.push_back(m);
+    }
+    sc.sensor_medium = d->nmedia && d->sensor_medium >= 0 && d->sensor_medium < (int) d->nmedia ? d->sensor_medium : -1;
     sc.bbox_min = V3(Infinity, Infinity, Infinity);
     sc.bbox_max = V3(-Infinity, -Infinity, -Infinity);
     for (uint32_t i = 0; i < d->nmeshes; ++i) {
@@ -1044,6 +1229,11 @@ int orc_scene_create(const MskSceneDesc *d, OrcScene **out) {
         OMesh o;
         o.nverts = m.nverts; o.ntris = m.ntris; o.bsdf = m.bsdf; o.emitter = m.emitter;
         o.has_normals = m.has_normals; o.has_uvs = m.has_uvs;
+        if (d->nmedia) { // medium ids are only meaningful when the description carries media
+            if (m.interior_medium < -1 || m.interior_medium >= (int) d->nmedia || m.exterior_medium < -1 || m.exterior_medium >= (int) d->nmedia)
+                return fail("bad medium id");
+            o.interior_medium = m.interior_medium; o.exterior_medium = m.exterior_medium;
+        }
         o.verts.assign(m.verts, m.verts + (size_t) m.nverts * 8);
         o.tris.assign(m.tris, m.tris + (size_t) m.ntris * 3);
         for (uint32_t t = 0; t < m.ntris * 3; ++t)
@@ -1150,7 +1340,7 @@ static Spec aov_sample(const OScene &sc, Sampler &sampler, const Ray &ray, const
             case MSK_AOV_GEO_NORMAL: *aovs++ = si.n.x; *aovs++ = si.n.y; *aovs++ = si.n.z; break;
             case MSK_AOV_SH_NORMAL: *aovs++ = si.sh_frame.n.x; *aovs++ = si.sh_frame.n.y; *aovs++ = si.sh_frame.n.z; break;
             case MSK_AOV_INTEGRATOR_RGBA: {
-                Spec spec = path_sample(sc, sampler, ray, pp, rc);
+                Spec spec = integrator_sample(sc, sampler, ray, pp, rc);
                 float xyz[3];
                 spectrum_to_xyz(spec, ray.wavelengths, xyz);
                 // xyz_to_srgb, spectrum.h:138-143
@@ -1176,7 +1366,7 @@ static int render_impl(OrcScene *s, const MskRenderDesc *rd, const int32_t *type
     if (extra < 0) return fail("invalid AOV type");
     const int nch = 5 + extra;
     if (rd->clear_film) std::fill(film, film + (size_t) W * H * nch, 0.f);
-    PathParams pp{ rd->max_depth, rd->rr_depth, rd->hide_emitters != 0 };
+    PathParams pp{ rd->max_depth, rd->rr_depth, rd->hide_emitters != 0, (int) rd->integrator };
     const int border = (int) std::ceil(sc.cam.filter_radius - .5f); // rfilter.cpp:22
     auto blocks = spiral_blocks(W, H, 32);                            // imageblock.h:8, integrator.cpp:48
     std::vector<Block> done(blocks.size());
@@ -1209,7 +1399,7 @@ static int render_impl(OrcScene *s, const MskRenderDesc *rd, const int32_t *type
                         sampler.next2d(); // aperture sample: consumed, unused
                         auto [ray, ray_weight] = camera_sample_ray(sc.cam, wavelength_sample, position_sample);
                         Spec result = (aov ? aov_sample(sc, sampler, ray, pp, rc, types, ntypes, aovs.data() + 5)
-                                           : path_sample(sc, sampler, ray, pp, rc)) * ray_weight;
+                                           : integrator_sample(sc, sampler, ray, pp, rc)) * ray_weight;
                         spectrum_to_xyz(result, ray.wavelengths, aovs.data());
                         aovs[3] = 1.f; aovs[4] = 1.f;
                         block_put(b, sc.cam, position_sample, aovs.data());
@@ -1254,7 +1444,7 @@ int orc_trace_samples(OrcScene *s, const MskRenderDesc *rd, const uint32_t *pixe
     if (!s) return fail("null scene");
     const OScene &sc = s->sc;
     const int W = (int) sc.cam.width;
-    PathParams pp{ rd->max_depth, rd->rr_depth, rd->hide_emitters != 0 };
+    PathParams pp{ rd->max_depth, rd->rr_depth, rd->hide_emitters != 0, (int) rd->integrator };
     RayCounters rc;
     Sampler sampler;
     sampler.base_seed = rd->base_seed;
@@ -1267,7 +1457,7 @@ int orc_trace_samples(OrcScene *s, const MskRenderDesc *rd, const uint32_t *pixe
         float wavelength_sample = sampler.next1d();
         sampler.next2d();
         auto [ray, ray_weight] = camera_sample_ray(sc.cam, wavelength_sample, position_sample);
-        Spec result = path_sample(sc, sampler, ray, pp, rc) * ray_weight;
+        Spec result = integrator_sample(sc, sampler, ray, pp, rc) * ray_weight;
         float xyz[3];
         spectrum_to_xyz(result, ray.wavelengths, xyz);
         float *o = out + i * 9;

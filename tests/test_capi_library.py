@@ -27,7 +27,7 @@ def test_struct_layouts_match_header(tmp_path):
     import subprocess
     structs = {"MskSpectrum": capi.MskSpectrum, "MskBsdf": capi.MskBsdf, "MskEmitter": capi.MskEmitter, "MskMesh": capi.MskMesh,
                "MskCamera": capi.MskCamera, "MskSceneDesc": capi.MskSceneDesc, "MskRenderDesc": capi.MskRenderDesc,
-               "MskStats": capi.MskStats, "MskAccelInfo": capi.MskAccelInfo}
+               "MskStats": capi.MskStats, "MskAccelInfo": capi.MskAccelInfo, "MskMedium": capi.MskMedium}
     lines = ['#include <stdio.h>', '#include <stddef.h>', f'#include "{ROOT / "include" / "misaki_b200.h"}"', "int main(void){"]
     for name, st in structs.items():
         lines.append(f'printf("{name} %zu\\n", sizeof({name}));')

@@ -191,3 +191,51 @@ def test_checkerboard_textures_equal_seed(gpu_ctx):
         film0, _ = sc.render(rd)
         rgba0 = sc.develop(film0)
     assert relmse(rgba0, oref) > 100 * EQUAL_SEED_RELMSE
+
+
+def _volpath_both(gpu_ctx, sd, rd):
+    film, rgba, ofilm, oref, stats, ost = _both(gpu_ctx, sd, rd)
+    assert np.isfinite(film).all()
+    np.testing.assert_allclose(film[..., 4], ofilm[..., 4], rtol=1e-5)
+    return rgba, oref, stats, ost
+
+
+def test_volpath_without_media_equal_seed(gpu_ctx):
+    """VolumetricPathTracer::sample (volpath.cpp:26-167) on the Cornell box: no medium anywhere, so this pins the
+    surface branch (emitter term on camera / delta chains, NEE without MIS, depth + 1 >= rr_depth roulette)."""
+    rgba, oref, stats, ost = _volpath_both(gpu_ctx, scenes.cbox(64, 64), capi.render_desc(spp=16, max_depth=6, rr_depth=3, integrator="volpath"))
+    e = relmse(rgba, oref)
+    _report("volpath cbox", e, stats, ost)
+    assert e < EQUAL_SEED_RELMSE, e
+    assert abs(int(stats.rays_closest) - int(ost.rays_closest)) <= 1e-3 * ost.rays_closest
+
+
+def test_volpath_fog_and_scattering_interior_equal_seed(gpu_ctx):
+    """Camera in a thin fog (sensor medium), a smooth-dielectric blob with a dense scattering interior and the fog
+    as exterior medium: free-flight sampling, medium NEE with transmittance, isotropic phase sampling, medium
+    transitions at the boundary (homogeneous.cpp, isotropic.cpp, scene.cpp:114-184, interaction.cpp:10-13).
+    Refraction + many scattering events amplify ulp differences, hence the chaotic-scene bound."""
+    sd = scenes.fog(96, 96)
+    rd = capi.render_desc(spp=16, max_depth=-1, rr_depth=5, integrator="volpath")
+    rgba, oref, stats, ost = _volpath_both(gpu_ctx, sd, rd)
+    e = relmse(rgba, oref)
+    _report("volpath fog", e, stats, ost)
+    assert e < CHAOTIC_RELMSE, e
+    assert bad_pixel_fraction(rgba, oref) < CHAOTIC_BAD_PIXELS
+    assert abs(int(stats.rays_closest) - int(ost.rays_closest)) <= 2e-2 * ost.rays_closest
+    # the medium matters: the same scene through the path tracer (media ignored) is a different image
+    with capi.Scene(gpu_ctx, sd) as sc:
+        film0, _ = sc.render(capi.render_desc(spp=16, max_depth=-1, rr_depth=5))
+        assert relmse(sc.develop(film0), oref) > 20 * CHAOTIC_RELMSE
+
+
+def test_volpath_bounded_depth_and_absorbing_fog(gpu_ctx):
+    """max_depth cut-offs inside both branches (volpath.cpp:57-58,127-128) and a purely absorbing sensor medium."""
+    sd = scenes.fog(64, 64, sensor_in_fog=False)
+    sd.sensor_medium = sd.add_medium(sigma_a=(0.05, 0.1, 0.2), sigma_s=0.0)
+    for depth in (1, 2, 4):
+        rgba, oref, stats, ost = _volpath_both(gpu_ctx, sd, capi.render_desc(spp=8, max_depth=depth, integrator="volpath"))
+        e = relmse(rgba, oref)
+        _report(f"volpath depth {depth}", e, stats, ost)
+        assert e < CHAOTIC_RELMSE, (depth, e)
+        assert stats.bounces == depth

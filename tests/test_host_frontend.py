@@ -184,6 +184,38 @@ def test_obj_relative_indices_and_polygons(tmp_path):
         _scene(MINIMAL.format(body=shape % (tmp_path / "oob.obj")))
 
 
+def test_volpath_media_and_phase_plugins():
+    """"volpath" + "homogeneous" + "isotropic" (SURVEY 8f rank 4): shape children named interior / exterior
+    (shape.cpp:28-40), the sensor's medium (sensor.cpp:12-18), a shared medium described once."""
+    body = ('<integrator type="volpath"><integer name="max_depth" value="9"/></integrator>'
+            '<medium type="homogeneous" id="fog"><rgb name="sigma_a" value="0.01"/><rgb name="sigma_s" value="0.06 0.07 0.09"/>'
+            '<phase type="isotropic"/></medium>'
+            + QUAD.format(inner='<bsdf type="dielectric"/><ref name="exterior" id="fog"/>'
+                                '<medium type="homogeneous" name="interior"><float name="sigma_s" value="3"/><float name="scale" value="7"/></medium>')
+            + QUAD.format(inner=""))
+    xml = MINIMAL.format(body=body).replace('<film type="hdrfilm">', '<ref id="fog"/><film type="hdrfilm">')
+    with _scene(xml) as hs:
+        d, rd, m = hs.desc(), hs.render_desc(), hs.meshes()
+        assert (rd.integrator, rd.max_depth) == (capi.INTEGRATOR_VOLPATH, 9)
+        assert d.nmedia == 2
+        fog = d.sensor_medium
+        mesh0 = d.meshes[0]
+        assert mesh0.exterior_medium == fog and mesh0.interior_medium == 1 - fog
+        assert (d.meshes[1].interior_medium, d.meshes[1].exterior_medium) == (-1, -1)
+        sp = _spectra(d)
+        sa, ss = sp[d.media[fog].sigma_a], sp[d.media[fog].sigma_s]
+        assert sa[0] == ss[0] == capi.SPEC_SRGB_UNBOUNDED and abs(sa[2] - 0.02) < 1e-7 and abs(ss[2] - 0.18) < 1e-7  # scale = 2 max(rgb)
+        wax = d.media[1 - fog]
+        assert sp[wax.sigma_s][0] == capi.SPEC_UNIFORM and sp[wax.sigma_s][2] == 3.0
+        # defaulted: gray 1 (homogeneous.cpp:15 default Color3(1)), described unbounded like every medium coefficient
+        assert sp[wax.sigma_a][0] == capi.SPEC_SRGB_UNBOUNDED and sp[wax.sigma_a][2] == 2.0
+        assert wax.scale == 7.0 and wax.phase == 0
+    for n in ("volpath", "homogeneous", "isotropic"):
+        assert n in host_api.registered_plugins()
+    with pytest.raises(host_api.HostError, match="Only a single medium can be specified per endpoint"):
+        _scene(MINIMAL.format(body="").replace('<film type="hdrfilm">', '<medium type="homogeneous"/><medium type="homogeneous"/><film type="hdrfilm">'))
+
+
 def test_material_plugins_and_their_parameter_checks():
     rc = ('<bsdf type="roughconductor"><string name="distribution" value="ggx"/><float name="alpha" value="0.1"/>'
           '<rgb name="eta" value="0.200438, 0.924033, 1.10221"/><rgb name="k" value="3.91295, 2.45285, 2.14219"/></bsdf>')

@@ -106,6 +106,22 @@ def checkers(width=96, height=96, n=12):
     return sd
 
 
+def fog(width=96, height=96, n=16, sensor_in_fog=True):
+    """Scene for the "volpath" integrator (integrators/volpath.cpp): the camera sits in a thin
+    homogeneous fog (sensor medium, sensor.cpp:12-18) that is also the exterior medium of a smooth-dielectric blob
+    whose interior is a dense, coloured scattering medium (shape.cpp:28-39); diffuse ground + quad light as in C2."""
+    sd = SceneDescription(width, height, fov=35.0, near_clip=0.1, far_clip=100.0,
+                          to_world=lookat((0.0, 2.2, -4.5), (0.0, 0.9, 0.0), (0, 1, 0)))
+    _ground_and_light(sd, radiance=(25, 25, 25))
+    haze = sd.add_medium(sigma_a=(0.01, 0.01, 0.01), sigma_s=(0.06, 0.07, 0.09))
+    wax = sd.add_medium(sigma_a=(0.2, 0.6, 1.2), sigma_s=(3.0, 2.5, 2.0))
+    v, t = meshes.cube_sphere(n, seed=4, octaves=2, amplitude=0.08, radius=0.85, center=(0, 1.0, 0), normals=True)
+    sd.add_mesh(v, t, sd.bsdf_dielectric(int_ior=1.33, ext_ior=1.0), has_normals=True, interior_medium=wax, exterior_medium=haze)
+    if sensor_in_fog:
+        sd.sensor_medium = haze
+    return sd
+
+
 def sphere10m(nu=3163, nv=1582, width=64, height=64):
     """C5: the intersection-sweep mesh (single geomID)."""
     sd = SceneDescription(width, height, fov=40.0, near_clip=0.01, far_clip=100.0,
