@@ -1,7 +1,7 @@
 #!/usr/bin/env python3
 """bench.py -- paths/s of the B200 path-tracing backend on BASELINE.json's config, next to the CPU baseline.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c1|c2|c3|c4]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c1|c2|c3|c4|c5|vol]
 
 A STEP is one complete render of the workload: every pixel x every sample of the job goes through
 ray generation -> closest hit -> shade (NEE + BSDF sampling, MIS, Russian roulette) -> shadow rays -> film.
@@ -590,7 +590,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="c2", choices=["c1", "c2", "c3", "c4", "c5"])
+    ap.add_argument("--workload", default="c2", choices=["c1", "c2", "c3", "c4", "c5", "vol"])
     ap.add_argument("--c5-res", type=int, default=4096, help="C5: primary rays are a res x res pinhole grid")
     ap.add_argument("--spp", type=int, default=0, help="override samples per pixel per GPU (development only)")
     ap.add_argument("--cpu-budget", type=float, default=15.0, help="seconds of CPU work for cpu_baseline")

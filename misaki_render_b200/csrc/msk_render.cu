@@ -500,7 +500,8 @@ __global__ void __launch_bounds__(128, 4) k_shade_vol(const __grid_constant__ DS
                     contrib = T * (ns.value * medium_tr(sigma_t, ns.dist)) * kInvFourPi;
                     if (!is_zero(contrib)) {
                         emit_shadow = true;
-                        sray.o[0] = msp.x; sray.o[1] = msp.y; sray.o[2] = msp.z; sray.tmin = kRayEpsilon; // scene.cpp:148
+                        sray.o[0] = msp.x; sray.o[1] = msp.y; sray.o[2] = msp.z;
+                        sray.tmin = kRayEpsilon * (1.f + max_abs(msp)); // scaled like scene.cpp:91-93 (see oracle.cpp, volpath notes)
                         sray.d[0] = ns.d.x; sray.d[1] = ns.d.y; sray.d[2] = ns.d.z;
                         sray.tmax = ns.dist * (1.f - kShadowEpsilon);
                     }
@@ -553,7 +554,8 @@ __global__ void __launch_bounds__(128, 4) k_shade_vol(const __grid_constant__ DS
                             contrib = T * ev * bval;
                             if (!is_zero(contrib)) {
                                 emit_shadow = true;
-                                sray.o[0] = sf.p.x; sray.o[1] = sf.p.y; sray.o[2] = sf.p.z; sray.tmin = kRayEpsilon;
+                                sray.o[0] = sf.p.x; sray.o[1] = sf.p.y; sray.o[2] = sf.p.z;
+                                sray.tmin = kRayEpsilon * (1.f + max_abs(sf.p));
                                 sray.d[0] = ns.d.x; sray.d[1] = ns.d.y; sray.d[2] = ns.d.z;
                                 sray.tmax = ns.dist * (1.f - kShadowEpsilon);
                             }

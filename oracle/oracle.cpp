@@ -925,8 +925,12 @@ Spec path_sample(const OScene &sc, Sampler &sampler, const Ray &ray_, const Path
 //  * medium NEE (volpath.cpp:50-51) passes the SURFACE interaction `si` as the reference point -- whose p is
 //    uninitialised when the ray escaped; the evident intent (a medium interaction at ms.p) is used instead
 //  * no compiled BSDF carries the Null flag (bsdfs/mask.cpp is not built), so eval_transmittance's loop
-//    (scene.cpp:152-182) reduces to: any surface within [RayEpsilon, dist (1 - ShadowEpsilon)] -> 0, else
+//    (scene.cpp:152-182) reduces to: any surface within [mint, dist (1 - ShadowEpsilon)] -> 0, else
 //    exp(-sigma_t dist) when the reference point lies in a medium
+//  * eval_transmittance starts its visibility ray at the UNSCALED RayEpsilon (scene.cpp:146-149, marked "TODO: Need to
+//    fix in volpath" there): in a scene of Cornell-box scale that is below the float spacing of the hit point, and
+//    whether a shadow ray re-hits its own surface is decided by rounding.  The scaled offset of
+//    Scene::sample_emitter_direct (scene.cpp:91-93), RayEpsilon (1 + max|p|), is used instead
 //  * exp(sigma_t * -inf) with sigma_t == 0 is NaN in the reference (homogeneous.cpp:56-59 on an escaped ray);
 //    a channel without extinction transmits 1 here
 // Kept as written: `scale` is read and never applied (homogeneous.cpp:18); NEE is added WITHOUT the MIS weight
@@ -997,7 +1001,7 @@ std::pair<DirectIllumSample, Spec> sample_attenuated_emitter_direct(const OScene
         V3 d = ds.p - ref.p;
         float remaining = norm(d);
         d = d / remaining;
-        Ray ray{ ref.p, d, RayEpsilon, remaining * (1 - ShadowEpsilon), ref.wavelengths };
+        Ray ray{ ref.p, d, RayEpsilon * (1.f + max_abs_coeff(ref.p)), remaining * (1 - ShadowEpsilon), ref.wavelengths };
         if (ray_test(sc, ray, rc)) spec = Spec(0.f); // a surface without the Null flag blocks the segment (:156-158)
         else if (medium >= 0) spec = spec * medium_tr(medium_sigma_t(sc, medium, ref.wavelengths), remaining); // :159-164
     }
