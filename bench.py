@@ -57,6 +57,10 @@ def workload(name: str, world: int):
                 "C3 teapot-class mesh (150532 tris) GGX rough dielectric 1024x1024 256spp depth16")
     if name == "c4":
         return scenes.cbox(1920, 1080), dict(spp=4096, max_depth=5, rr_depth=5), "C4 Cornell box 1920x1080 4096spp depth5"
+    if name == "vol":
+        return (scenes.fog(512, 512, n=64), dict(spp=64, max_depth=-1, rr_depth=5, integrator="volpath"),
+                "VOL volpath (SURVEY 8f rank 4): camera in thin fog, dielectric blob (49152 tris) with dense scattering interior, 512x512 64spp "
+                "max_depth=-1 rr_depth=5")
     raise SystemExit(f"unknown workload {name}")
 
 
