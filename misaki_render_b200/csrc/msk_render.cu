@@ -309,12 +309,12 @@ __global__ void __launch_bounds__(128, shade_min_blocks(KEY)) k_shade(const __gr
                 const DMeshInfo mi = sc.meshes[geom];
                 const Surface sf = make_surface(sc, mi, __float_as_uint(hit.w), hit.y, hit.z);
                 const V3 wi = to_local(sf.sh, -rdir);
-                if (mi.emitter >= 0) { // area.cpp:51-54
-                    int radiance = sc.emitters[mi.emitter].radiance;
-                    if (sc.has_textures) radiance = texture_resolve(sc, radiance, sf.uvx, sf.uvy);
-                    float4 le = wi.z > 0.f ? spectrum_eval(sc, radiance, wl) : f4(0.f);
+                // emitter term of the ray that arrived here: weight now, radiance after the single spectrum pass below
+                int id_le = -1;
+                float le_weight = 1.f;
+                if (mi.emitter >= 0 && wi.z > 0.f) { // area.cpp:51-54
                     if (depth == 1) { // path.cpp:44-47
-                        if (!bp.hide_emitters) { L = T * le; add_L = true; }
+                        if (!bp.hide_emitters) id_le = sc.emitters[mi.emitter].radiance;
                     } else {          // path.cpp:82-88,103-108 with ds.set_query (records.cpp:7-14)
                         float emitter_pdf = 0.f;
                         if (!prev_delta) {
@@ -322,42 +322,53 @@ __global__ void __launch_bounds__(128, shade_min_blocks(KEY)) k_shade(const __gr
                             emitter_pdf = mi.inv_area * ((dp != 0.f) ? (hit.x * hit.x) / dp : 0.f);
                             if (sc.nemitters > 1) emitter_pdf *= 1.f / (float) sc.nemitters;
                         }
-                        L = T * le * mis_weight(prev_pdf, emitter_pdf);
-                        add_L = true;
+                        le_weight = mis_weight(prev_pdf, emitter_pdf);
+                        id_le = sc.emitters[mi.emitter].radiance;
                     }
+                    if (id_le >= 0 && sc.has_textures) id_le = texture_resolve(sc, id_le, sf.uvx, sf.uvy);
                 }
+                const float4 T_in = T; // the emitter term uses the throughput before this vertex's roulette division
                 if (depth > 1 && depth >= bp.rr_depth) { // path.cpp:116-122 of the previous iteration
                     float qq = fminf(hmax(T) * eta * eta, 0.95f);
                     if (next1d(rng) >= qq) alive = false;
                     else T = T / qq;
                 }
                 if (alive && bp.max_depth > 0 && depth >= bp.max_depth) alive = false; // path.cpp:48-49
+                MskBsdf bsdf = sc.bsdfs[mi.bsdf];
+                NeeSample ns;
+                ns.pdf = 0.f; ns.radiance = -1; ns.stale_pdf = 0.f;
+                bool nee = false;
                 if (alive) {
-                    MskBsdf bsdf = sc.bsdfs[mi.bsdf];
                     if (sc.has_textures) bsdf_resolve_textures(sc, bsdf, sf.uvx, sf.uvy); // Texture::eval(si), checkerboard.cpp:25-31
-                    float new_stale = 0.f;
-                    const float tmin_spawn = (1.f + max_abs(sf.p)) * kRayEpsilon; // interaction.h:40-44, scene.cpp:91-93
                     if (bsdf_is_smooth(TYPE >= 0 ? TYPE : bsdf.type)) { // path.cpp:56-67
                         float sx = next1d(rng), sy = next1d(rng);
-                        NeeSample ns = sample_emitter_direct(sc, sf.p, wl, sx, sy);
-                        new_stale = ns.stale_pdf;
-                        if (ns.pdf != 0.f) {
-                            V3 wo = to_local(sf.sh, ns.d);
-                            float4 bval; float bpdf;
-                            bsdf_eval_pdf<TYPE>(sc, bsdf, wi, wo, wl, bval, bpdf);
-                            float w = mis_weight(ns.pdf, bpdf);
-                            contrib = T * ns.value * bval * w;
-                            if (!is_zero(contrib)) {
-                                emit_shadow = true;
-                                sray.o[0] = sf.p.x; sray.o[1] = sf.p.y; sray.o[2] = sf.p.z;
-                                sray.tmin = kRayEpsilon * (1.f + max_abs(sf.p));
-                                sray.d[0] = ns.d.x; sray.d[1] = ns.d.y; sray.d[2] = ns.d.z;
-                                sray.tmax = ns.dist * (1.f - kShadowEpsilon);
-                            }
+                        ns = sample_emitter_direct(sc, sf.p, sx, sy);
+                        nee = ns.pdf != 0.f;
+                    }
+                }
+                BsdfSpectra sp;
+                float4 le, ln;
+                eval_vertex_spectra<TYPE>(sc, bsdf, alive, id_le, nee ? ns.radiance : -1, wl, sp, le, ln);
+                if (id_le >= 0) { L = T_in * le * le_weight; add_L = true; } // le_weight == 1 at depth 1
+                if (alive) {
+                    const float new_stale = ns.stale_pdf;
+                    const float tmin_spawn = (1.f + max_abs(sf.p)) * kRayEpsilon; // interaction.h:40-44, scene.cpp:91-93
+                    if (nee) {
+                        V3 wo = to_local(sf.sh, ns.d);
+                        float4 bval; float bpdf;
+                        bsdf_eval_pdf<TYPE>(sp, bsdf, wi, wo, bval, bpdf);
+                        float w = mis_weight(ns.pdf, bpdf);
+                        contrib = T * nee_value(ns, ln) * bval * w;
+                        if (!is_zero(contrib)) {
+                            emit_shadow = true;
+                            sray.o[0] = sf.p.x; sray.o[1] = sf.p.y; sray.o[2] = sf.p.z;
+                            sray.tmin = kRayEpsilon * (1.f + max_abs(sf.p));
+                            sray.d[0] = ns.d.x; sray.d[1] = ns.d.y; sray.d[2] = ns.d.z;
+                            sray.tmax = ns.dist * (1.f - kShadowEpsilon);
                         }
                     }
                     float s1 = next1d(rng), s2x = next1d(rng), s2y = next1d(rng); // path.cpp:71-72, left to right
-                    BsdfSample bs = bsdf_sample<TYPE>(sc, bsdf, wi, wl, s1, s2x, s2y);
+                    BsdfSample bs = bsdf_sample<TYPE>(sp, bsdf, wi, s1, s2x, s2y);
                     if (is_zero(bs.weight)) alive = false; // failed sample: nothing downstream can contribute
                     else {
                         V3 wo = to_world(sf.sh, bs.wo);
@@ -425,7 +436,10 @@ __device__ __forceinline__ float4 medium_sigma_t(const DScene &sc, int medium, f
     return sigma_s + sa; // homogeneous.cpp:17
 }
 
-__global__ void __launch_bounds__(128, 4) k_shade_vol(const __grid_constant__ DScene sc, Pool pool, BatchParams bp, int cur) {
+#ifndef MSK_VOL_MIN_BLOCKS
+#define MSK_VOL_MIN_BLOCKS 4
+#endif
+__global__ void __launch_bounds__(128, MSK_VOL_MIN_BLOCKS) k_shade_vol(const __grid_constant__ DScene sc, Pool pool, BatchParams bp, int cur) {
     Ctrl *c = pool.ctrl;
     const int nxt = cur ^ 1;
     uint32_t counts[kNumKeys], total = 0;
@@ -495,9 +509,10 @@ __global__ void __launch_bounds__(128, 4) k_shade_vol(const __grid_constant__ DS
             if (ms_flag) { // ---- medium scattering event, volpath.cpp:44-74
                 T = T * (sigma_s * tr / ms_pdf);
                 const float sx = next1d(rng), sy = next1d(rng);
-                NeeSample ns = sample_emitter_direct(sc, msp, wl, sx, sy);
+                NeeSample ns = sample_emitter_direct(sc, msp, sx, sy);
                 if (ns.pdf != 0.f) { // scene.cpp:136-138 + isotropic phase value 1 / 4 pi
-                    contrib = T * (ns.value * medium_tr(sigma_t, ns.dist)) * kInvFourPi;
+                    const float4 ln = spectrum_eval(sc, ns.radiance, wl);
+                    contrib = T * (nee_value(ns, ln) * medium_tr(sigma_t, ns.dist)) * kInvFourPi;
                     if (!is_zero(contrib)) {
                         emit_shadow = true;
                         sray.o[0] = msp.x; sray.o[1] = msp.y; sray.o[2] = msp.z;
@@ -535,34 +550,41 @@ __global__ void __launch_bounds__(128, 4) k_shade_vol(const __grid_constant__ DS
                     const DMeshInfo mi = sc.meshes[geom];
                     const Surface sf = make_surface(sc, mi, __float_as_uint(hit.w), hit.y, hit.z);
                     const V3 wi = to_local(sf.sh, -rdir);
-                    if (mi.emitter >= 0 && emitted && (!bp.hide_emitters || scattered)) { // :95-98, area.cpp:51-54
-                        int radiance = sc.emitters[mi.emitter].radiance;
-                        if (sc.has_textures) radiance = texture_resolve(sc, radiance, sf.uvx, sf.uvy);
-                        if (wi.z > 0.f) { L = T * spectrum_eval(sc, radiance, wl); add_L = true; }
+                    int id_le = -1;
+                    if (mi.emitter >= 0 && emitted && (!bp.hide_emitters || scattered) && wi.z > 0.f) { // :95-98, area.cpp:51-54
+                        id_le = sc.emitters[mi.emitter].radiance;
+                        if (sc.has_textures) id_le = texture_resolve(sc, id_le, sf.uvx, sf.uvy);
                     }
                     MskBsdf bsdf = sc.bsdfs[mi.bsdf];
                     if (sc.has_textures) bsdf_resolve_textures(sc, bsdf, sf.uvx, sf.uvy);
+                    NeeSample ns;
+                    ns.pdf = 0.f; ns.radiance = -1;
                     if (bsdf_is_smooth(bsdf.type)) { // :104-115: attenuated NEE, added without the MIS weight
                         const float sx = next1d(rng), sy = next1d(rng);
-                        NeeSample ns = sample_emitter_direct(sc, sf.p, wl, sx, sy);
-                        if (ns.pdf != 0.f) {
-                            const V3 wo = to_local(sf.sh, ns.d);
-                            float4 bval; float bpdf;
-                            bsdf_eval_pdf<-1>(sc, bsdf, wi, wo, wl, bval, bpdf);
-                            float4 ev = ns.value;
-                            if (medium >= 0) ev = ev * medium_tr(sigma_t, ns.dist);
-                            contrib = T * ev * bval;
-                            if (!is_zero(contrib)) {
-                                emit_shadow = true;
-                                sray.o[0] = sf.p.x; sray.o[1] = sf.p.y; sray.o[2] = sf.p.z;
-                                sray.tmin = kRayEpsilon * (1.f + max_abs(sf.p));
-                                sray.d[0] = ns.d.x; sray.d[1] = ns.d.y; sray.d[2] = ns.d.z;
-                                sray.tmax = ns.dist * (1.f - kShadowEpsilon);
-                            }
+                        ns = sample_emitter_direct(sc, sf.p, sx, sy);
+                    }
+                    const bool nee = ns.pdf != 0.f;
+                    BsdfSpectra sp;
+                    float4 le, ln;
+                    eval_vertex_spectra<-1, true>(sc, bsdf, true, id_le, nee ? ns.radiance : -1, wl, sp, le, ln);
+                    if (id_le >= 0) { L = T * le; add_L = true; }
+                    if (nee) {
+                        const V3 wo = to_local(sf.sh, ns.d);
+                        float4 bval; float bpdf;
+                        bsdf_eval_pdf<-1>(sp, bsdf, wi, wo, bval, bpdf);
+                        float4 ev = nee_value(ns, ln);
+                        if (medium >= 0) ev = ev * medium_tr(sigma_t, ns.dist);
+                        contrib = T * ev * bval;
+                        if (!is_zero(contrib)) {
+                            emit_shadow = true;
+                            sray.o[0] = sf.p.x; sray.o[1] = sf.p.y; sray.o[2] = sf.p.z;
+                            sray.tmin = kRayEpsilon * (1.f + max_abs(sf.p));
+                            sray.d[0] = ns.d.x; sray.d[1] = ns.d.y; sray.d[2] = ns.d.z;
+                            sray.tmax = ns.dist * (1.f - kShadowEpsilon);
                         }
                     }
                     const float s1 = next1d(rng), s2x = next1d(rng), s2y = next1d(rng);
-                    BsdfSample bs = bsdf_sample<-1>(sc, bsdf, wi, wl, s1, s2x, s2y);
+                    BsdfSample bs = bsdf_sample<-1>(sp, bsdf, wi, s1, s2x, s2y);
                     if (is_zero(bs.weight)) alive = false; // :122-123
                     else {
                         emitted = false;

@@ -137,7 +137,14 @@ __device__ __forceinline__ float regular1(const DSpectrum &s, const float *__res
 __device__ __forceinline__ float4 regular_eval(const DSpectrum &s, const float *__restrict__ tables, float4 wl) {
     return make_float4(regular1(s, tables, wl.x), regular1(s, tables, wl.y), regular1(s, tables, wl.z), regular1(s, tables, wl.w));
 }
+#ifndef MSK_SPEC_NOINLINE
+#define MSK_SPEC_NOINLINE 0
+#endif
+#if MSK_SPEC_NOINLINE
+__device__ __noinline__ float4 spectrum_eval(const DScene &sc, int id, float4 wl) {
+#else
 __device__ __forceinline__ float4 spectrum_eval(const DScene &sc, int id, float4 wl) {
+#endif
     const DSpectrum s = sc.spectra[id];
     switch (s.kind) {
         case MSK_SPEC_UNIFORM: { // uniform.cpp:19-26
@@ -279,11 +286,17 @@ __device__ __forceinline__ bool bsdf_is_smooth(int type) { // has_flag(flags, Sm
 
 struct BsdfSample { V3 wo; float pdf, eta; uint32_t type; float4 weight; };
 
+// The spectra a BSDF reads (Texture::eval(si) of "reflectance"/"specular_reflectance", "specular_transmittance",
+// "eta", "k"), evaluated ONCE per path vertex by eval_vertex_spectra() below: sample() and eval() of the same vertex
+// used to re-evaluate them at ten inlined call sites, which made the rough-conductor shade kernel 8840 SASS
+// instructions (141 KB) and instruction-fetch bound (stall no_instruction = 4.5 per issue, profiles/r01f_ncu_k_shade.txt).
+struct BsdfSpectra { float4 R, Tr, eta, k; };
+
 // sample(): wi is the local incident direction; returns weight = f*cos/pdf
 // TYPE >= 0: the BSDF type is known at compile time (k_shade specialised per material key) and the switch folds
 // to one case; TYPE < 0: dispatch on b.type.
 template <int TYPE>
-__device__ __forceinline__ BsdfSample bsdf_sample_1(const DScene &sc, const MskBsdf &b, V3 wi, float4 wl, float s1, float s2x, float s2y) {
+__device__ __forceinline__ BsdfSample bsdf_sample_1(const BsdfSpectra &sp, const MskBsdf &b, V3 wi, float s1, float s2x, float s2y) {
     BsdfSample bs;
     bs.wo = v3(0, 0, 0); bs.pdf = 0.f; bs.eta = 1.f; bs.type = 0; bs.weight = f4(0.f);
     const float ci = wi.z;
@@ -293,13 +306,13 @@ __device__ __forceinline__ BsdfSample bsdf_sample_1(const DScene &sc, const MskB
             bs.wo = square_to_cosine_hemisphere(s2x, s2y);
             bs.pdf = kInvPi * bs.wo.z;
             bs.type = BF_DiffuseReflection;
-            if (bs.pdf > 0.f) bs.weight = spectrum_eval(sc, b.reflectance, wl);
+            if (bs.pdf > 0.f) bs.weight = sp.R;
             return bs;
         }
         case MSK_BSDF_CONDUCTOR: { // conductor.cpp:22-39
             if (ci <= 0.f) return bs;
             bs.wo = v3(-wi.x, -wi.y, wi.z); bs.pdf = 1.f; bs.type = BF_DeltaReflection;
-            bs.weight = spectrum_eval(sc, b.reflectance, wl) * fresnel_conductor(ci, spectrum_eval(sc, b.eta, wl), spectrum_eval(sc, b.k, wl));
+            bs.weight = sp.R * fresnel_conductor(ci, sp.eta, sp.k);
             return bs;
         }
         case MSK_BSDF_ROUGHCONDUCTOR: { // roughconductor.cpp:53-80
@@ -311,7 +324,7 @@ __device__ __forceinline__ BsdfSample bsdf_sample_1(const DScene &sc, const MskB
             if (!(bs.pdf != 0.f && bs.wo.z > 0.f)) return bs;
             float weight = b.sample_visible ? ggx_g1(g, bs.wo, m) : ggx_G(g, wi, bs.wo, m) * dot(wi, m) / (ci * m.z);
             bs.pdf /= 4.f * dot(bs.wo, m);
-            bs.weight = fresnel_conductor(dot(wi, m), spectrum_eval(sc, b.eta, wl), spectrum_eval(sc, b.k, wl)) * weight;
+            bs.weight = fresnel_conductor(dot(wi, m), sp.eta, sp.k) * weight;
             return bs;
         }
         case MSK_BSDF_ROUGHDIELECTRIC: { // roughdielectric.cpp:58-114
@@ -329,7 +342,7 @@ __device__ __forceinline__ BsdfSample bsdf_sample_1(const DScene &sc, const MskB
             float dwh_dwo;
             if (sel_r) {
                 bs.wo = reflect_m(wi, m);
-                weight = weight * spectrum_eval(sc, b.reflectance, wl);
+                weight = weight * sp.R;
                 dwh_dwo = 1.f / (4.f * dot(bs.wo, m));
             } else {
                 bs.wo = refract_m(wi, m, fr.cos_theta_t, fr.eta_ti);
@@ -348,7 +361,7 @@ __device__ __forceinline__ BsdfSample bsdf_sample_1(const DScene &sc, const MskB
             bs.type = sel_r ? BF_DeltaReflection : BF_DeltaTransmission;
             bs.wo = sel_r ? v3(-wi.x, -wi.y, wi.z) : v3(-fr.eta_ti * wi.x, -fr.eta_ti * wi.y, fr.cos_theta_t);
             bs.eta = sel_r ? 1.f : fr.eta_it;
-            bs.weight = sel_r ? spectrum_eval(sc, b.reflectance, wl) : spectrum_eval(sc, b.transmittance, wl) * fr.eta_ti * fr.eta_ti;
+            bs.weight = sel_r ? sp.R : sp.Tr * fr.eta_ti * fr.eta_ti;
             return bs;
         }
     }
@@ -357,12 +370,12 @@ __device__ __forceinline__ BsdfSample bsdf_sample_1(const DScene &sc, const MskB
 
 // eval() and pdf() of the NEE direction in one pass (path.cpp:61-62)
 template <int TYPE>
-__device__ __forceinline__ void bsdf_eval_pdf_1(const DScene &sc, const MskBsdf &b, V3 wi, V3 wo, float4 wl, float4 &val, float &pdf) {
+__device__ __forceinline__ void bsdf_eval_pdf_1(const BsdfSpectra &sp, const MskBsdf &b, V3 wi, V3 wo, float4 &val, float &pdf) {
     val = f4(0.f); pdf = 0.f;
     const float ci = wi.z, co = wo.z;
     switch (TYPE >= 0 ? TYPE : b.type) {
         case MSK_BSDF_DIFFUSE: // diffuse.cpp:34-57
-            if (ci > 0.f && co > 0.f) { val = spectrum_eval(sc, b.reflectance, wl) * kInvPi * co; pdf = kInvPi * co; }
+            if (ci > 0.f && co > 0.f) { val = sp.R * kInvPi * co; pdf = kInvPi * co; }
             return;
         case MSK_BSDF_ROUGHCONDUCTOR: { // roughconductor.cpp:82-120
             if (!(ci > 0.f && co > 0.f)) return;
@@ -372,8 +385,8 @@ __device__ __forceinline__ void bsdf_eval_pdf_1(const DScene &sc, const MskBsdf 
             if (D != 0.f) {
                 float G = ggx_G(g, wi, wo, H);
                 float result = D * G / (4.f * ci);
-                float4 F = fresnel_conductor(dot(wi, H), spectrum_eval(sc, b.eta, wl), spectrum_eval(sc, b.k, wl));
-                val = F * spectrum_eval(sc, b.reflectance, wl) * result;
+                float4 F = fresnel_conductor(dot(wi, H), sp.eta, sp.k);
+                val = F * sp.R * result;
             }
             if (dot(wi, H) > 0.f && dot(wo, H) > 0.f)
                 pdf = b.sample_visible ? ggx_eval(g, H) * ggx_g1(g, wi, H) / (4.f * ci) : ggx_pdf(g, H) / (4.f * dot(wo, H));
@@ -390,10 +403,10 @@ __device__ __forceinline__ void bsdf_eval_pdf_1(const DScene &sc, const MskBsdf 
             float D = ggx_eval(g, m);
             float F = fresnel_dielectric(dot(wi, m), m_eta).F;
             float G = ggx_G(g, wi, wo, m);
-            if (refl) val = F * D * G * spectrum_eval(sc, b.reflectance, wl) / (4.f * fabsf(ci));
+            if (refl) val = F * D * G * sp.R / (4.f * fabsf(ci));
             else {
                 float scale = sqr(inv_eta);
-                val = spectrum_eval(sc, b.transmittance, wl) *
+                val = sp.Tr *
                       fabsf((scale * (1.f - F) * D * G * eta * eta * dot(wi, m) * dot(wo, m)) / (ci * sqr(dot(wi, m) + eta * dot(wo, m))));
             }
             if (dot(wi, m) * ci <= 0.f || dot(wo, m) * co <= 0.f) return;
@@ -412,7 +425,7 @@ __device__ __forceinline__ void bsdf_eval_pdf_1(const DScene &sc, const MskBsdf 
 // twosided.cpp:38-101 (same BRDF on both sides)
 // (one call site of the inner function: flip wi, sample, flip wo back)
 template <int TYPE>
-__device__ __forceinline__ BsdfSample bsdf_sample(const DScene &sc, const MskBsdf &b, V3 wi, float4 wl, float s1, float s2x, float s2y) {
+__device__ __forceinline__ BsdfSample bsdf_sample(const BsdfSpectra &sp, const MskBsdf &b, V3 wi, float s1, float s2x, float s2y) {
     const bool two = b.twosided != 0, flip = two && wi.z < 0.f;
     if (two && wi.z == 0.f) {
         BsdfSample bs;
@@ -420,17 +433,17 @@ __device__ __forceinline__ BsdfSample bsdf_sample(const DScene &sc, const MskBsd
         return bs;
     }
     if (flip) wi.z = -wi.z;
-    BsdfSample bs = bsdf_sample_1<TYPE>(sc, b, wi, wl, s1, s2x, s2y);
+    BsdfSample bs = bsdf_sample_1<TYPE>(sp, b, wi, s1, s2x, s2y);
     if (flip) bs.wo.z = -bs.wo.z;
     return bs;
 }
 template <int TYPE>
-__device__ __forceinline__ void bsdf_eval_pdf(const DScene &sc, const MskBsdf &b, V3 wi, V3 wo, float4 wl, float4 &val, float &pdf) {
+__device__ __forceinline__ void bsdf_eval_pdf(const BsdfSpectra &sp, const MskBsdf &b, V3 wi, V3 wo, float4 &val, float &pdf) {
     if (b.twosided) {
         if (wi.z == 0.f) { val = f4(0.f); pdf = 0.f; return; }
         if (wi.z < 0.f) { wi.z = -wi.z; wo.z = -wo.z; }
     }
-    bsdf_eval_pdf_1<TYPE>(sc, b, wi, wo, wl, val, pdf);
+    bsdf_eval_pdf_1<TYPE>(sp, b, wi, wo, val, pdf);
 }
 
 __device__ __forceinline__ float mis_weight(float pdf_a, float pdf_b) { // path.cpp:127-131
@@ -483,13 +496,19 @@ __device__ __forceinline__ Surface make_surface(const DScene &sc, const DMeshInf
 struct NeeSample {
     V3 d;            // direction towards the light (world)
     float dist, pdf; // pdf == 0: no contribution
-    float4 value;    // radiance / pdf (before the visibility test)
+    int radiance;    // spectrum id of the sampled emitter's radiance at the sampled point (textures resolved), -1: none
+    float pdf0;      // value = spectrum_eval(radiance) / pdf0 [* scale]: emitter_sample_direct's division, then scene.cpp:86-87
+    float scale;     //   (number of emitters when a light was selected at random, else 1)
     float stale_pdf; // pdf_emitter_direct() of this record, consumed only by the env-miss quirk (q8)
 };
 
-__device__ __forceinline__ NeeSample sample_emitter_direct(const DScene &sc, V3 ref_p, float4 wl, float sx, float sy) { // scene.cpp:69-89
+__device__ __forceinline__ float4 nee_value(const NeeSample &ns, float4 radiance) { // radiance / pdf (before the visibility test)
+    float4 v = radiance / ns.pdf0;
+    return ns.scale != 1.f ? v * ns.scale : v;
+}
+__device__ __forceinline__ NeeSample sample_emitter_direct(const DScene &sc, V3 ref_p, float sx, float sy) { // scene.cpp:69-89
     NeeSample r;
-    r.pdf = 0.f; r.value = f4(0.f); r.stale_pdf = 0.f; r.dist = 0.f; r.d = v3(0, 0, 0);
+    r.pdf = 0.f; r.radiance = -1; r.pdf0 = 1.f; r.scale = 1.f; r.stale_pdf = 0.f; r.dist = 0.f; r.d = v3(0, 0, 0);
     uint32_t ne = sc.nemitters;
     if (!ne) return r;
     uint32_t index = 0;
@@ -544,17 +563,46 @@ __device__ __forceinline__ NeeSample sample_emitter_direct(const DScene &sc, V3 
         // pdf_emitter_direct(ds) of this record: shape.cpp:80-86
         r.stale_pdf = mi.inv_area * ((dp != 0.f) ? (dist * dist) / dp : 0.f) * (ne > 1 ? 1.f / (float) ne : 1.f);
         if (dot(d, ns) < 0.f && pdf != 0.f) {
-            r.value = spectrum_eval(sc, radiance, wl) / pdf;
+            r.radiance = radiance; r.pdf0 = pdf;
             r.pdf = pdf;
         }
     } else { // constant.cpp:55-73
         V3 d = square_to_uniform_sphere(sx, sy);
         r.d = d; r.dist = 2.f * sc.env_radius; r.pdf = kInvFourPi;
-        r.value = spectrum_eval(sc, sc.has_textures ? texture_resolve(sc, em.radiance, 0.f, 0.f) : em.radiance, wl) / r.pdf;
+        r.radiance = sc.has_textures ? texture_resolve(sc, em.radiance, 0.f, 0.f) : em.radiance; r.pdf0 = r.pdf;
         r.stale_pdf = kInvFourPi * (ne > 1 ? 1.f / (float) ne : 1.f);
     }
-    if (ne > 1) { r.pdf *= sel; r.value = r.value * (float) ne; }
+    if (ne > 1) { r.pdf *= sel; r.scale = (float) ne; }
     return r;
+}
+
+// Every spectrum one path vertex needs -- the BSDF's (by type), the radiance of the emitter that was hit (id_le) and of
+// the emitter NEE sampled (id_ln); ids < 0 are skipped.  The loop is deliberately NOT unrolled: one copy of
+// spectrum_eval's five-way switch per shade kernel.
+template <int TYPE, bool UNROLL = false>
+__device__ __forceinline__ void eval_vertex_spectra(const DScene &sc, const MskBsdf &b, bool need_bsdf, int id_le, int id_ln, float4 wl,
+                                                    BsdfSpectra &sp, float4 &le, float4 &ln) {
+    const int t = TYPE >= 0 ? TYPE : b.type;
+    const bool dielectric = t == MSK_BSDF_ROUGHDIELECTRIC || t == MSK_BSDF_DIELECTRIC, conductor = t == MSK_BSDF_CONDUCTOR || t == MSK_BSDF_ROUGHCONDUCTOR;
+    const int id_r = need_bsdf ? b.reflectance : -1, id_t = need_bsdf && dielectric ? b.transmittance : -1;
+    const int id_e = need_bsdf && conductor ? b.eta : -1, id_k = need_bsdf && conductor ? b.k : -1;
+    sp.R = sp.Tr = sp.eta = sp.k = le = ln = f4(0.f);
+    if (UNROLL) { // k_shade_vol: its many live values spill around the loop (measured: 25.0 -> 27.0 ms on the vol workload)
+        if (id_r >= 0) sp.R = spectrum_eval(sc, id_r, wl);
+        if (id_t >= 0) sp.Tr = spectrum_eval(sc, id_t, wl);
+        if (id_e >= 0) sp.eta = spectrum_eval(sc, id_e, wl);
+        if (id_k >= 0) sp.k = spectrum_eval(sc, id_k, wl);
+        if (id_le >= 0) le = spectrum_eval(sc, id_le, wl);
+        if (id_ln >= 0) ln = spectrum_eval(sc, id_ln, wl);
+        return;
+    }
+#pragma unroll 1
+    for (int i = 0; i < 6; ++i) {
+        const int id = i == 0 ? id_r : (i == 1 ? id_t : (i == 2 ? id_e : (i == 3 ? id_k : (i == 4 ? id_le : id_ln))));
+        if (id < 0) continue;
+        const float4 v = spectrum_eval(sc, id, wl);
+        if (i == 0) sp.R = v; else if (i == 1) sp.Tr = v; else if (i == 2) sp.eta = v; else if (i == 3) sp.k = v; else if (i == 4) le = v; else ln = v;
+    }
 }
 
 } // namespace msk
