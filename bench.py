@@ -434,7 +434,14 @@ def run_ours(args, rank: int, local_rank: int, world: int):
     t_scene = time.time() - t0
     info = scene.accel_info()
     ext = torch.cuda.ExternalStream(ctx.stream, device=dev)
-    film = torch.zeros((sd.height, sd.width, 5), dtype=torch.float32, device=dev)
+    # N > 1: the film lives in CUDA-IPC-exportable memory and is reduced by the library's own peer-memory kernel
+    # (csrc/msk_peer.cu); --reduce nccl selects torch.distributed's reduce instead
+    peer = None
+    if world > 1 and args.reduce == "peer":
+        peer = msk_dist.PeerFilm(ctx, (sd.height, sd.width, 5), rank, world)
+        film = peer.tensor(dev)
+    else:
+        film = torch.zeros((sd.height, sd.width, 5), dtype=torch.float32, device=dev)
     film_host = torch.zeros((sd.height, sd.width, 5), dtype=torch.float32).pin_memory()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
 
@@ -442,7 +449,10 @@ def run_ours(args, rank: int, local_rank: int, world: int):
         with torch.cuda.stream(ext):
             flush.zero_()  # evict the scene/BVH and queue tails from L2 between steps
             st = scene.render_dev(rd_rank, film.data_ptr())
-            msk_dist.reduce_film(film, 0)
+            if peer is not None:
+                peer.reduce()
+            else:
+                msk_dist.reduce_film(film, 0)
         if collect is not None:
             collect.append(st)
 
@@ -487,7 +497,7 @@ def run_ours(args, rank: int, local_rank: int, world: int):
         if world == 1:
             scene.render(rd_rank, film=fh)  # msk_gpu_render: host film in/out
         else:
-            msk_dist.render_sharded(scene, rd_job, film, rank, world, host_out=film_host)
+            msk_dist.render_sharded(scene, rd_job, film, rank, world, host_out=film_host, peer=peer)
 
     for _ in range(min(args.warmup, 2)):
         e2e_step()
@@ -570,6 +580,7 @@ def run_ours(args, rank: int, local_rank: int, world: int):
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
             "config": {"workload": wname, "spp_per_gpu": spp_rank, "job_spp": spp_rank * world, "partition": "sample ranges + 1 film reduce/step",
+                       "film_reduce": "none (1 GPU)" if world == 1 else ("msk_gpu_reduce_film: one kernel pulling peer films over NVLink (CUDA IPC)" if peer is not None else "ncclReduce"),
                        "l2": "256 MiB memset between steps (inside the timed region); path queues (~1.6 GB/batch) exceed the 126 MB L2",
                        "tris": int(info.ntris), "wide_nodes": int(info.nnodes), "bvh_build_ms": info.ms_build},
             "mrays_per_s": mrays, "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
@@ -578,8 +589,12 @@ def run_ours(args, rank: int, local_rank: int, world: int):
         print(json.dumps(line), flush=True)
     # release every torch tensor that was used on the library's stream (NCCL's record_stream included) BEFORE that
     # stream is destroyed: the caching allocator records an event on each such stream when the block is freed
+    if peer is not None:
+        peer.check()
     film = film_host = flush = fh = None
     barrier()
+    if peer is not None:
+        peer.close()
     if world > 1:
         dist.destroy_process_group()
     torch.cuda.synchronize()
@@ -600,6 +615,7 @@ def main():
     ap.add_argument("--cpu-budget", type=float, default=15.0, help="seconds of CPU work for cpu_baseline")
     ap.add_argument("--ref-budget", type=float, default=150.0, help="seconds for the whole --impl reference run")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--reduce", default="peer", choices=["peer", "nccl"], help="N > 1: film reduction by the library's NVLink peer kernel or by NCCL")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
     args.steps = max(args.steps, 1)

@@ -261,6 +261,26 @@ int  msk_gpu_render_aov_dev(MskScene *scene, const MskRenderDesc *rd, const MskA
 /* XYZAW film -> RGBA (linear sRGB / W, A / W), both host, n = width*height pixels */
 int  msk_gpu_develop(MskScene *scene, const float *film_host, float *rgba_host);
 
+/* ---- multi-GPU film reduction over NVLink peer memory (replaces Film::put under the mutex,
+ * films/hdrfilm.cpp:43-46, across GPUs).  One process per GPU.  Every rank creates a share (a cudaMalloc'ed film with
+ * a control word in front), exports its CUDA IPC handle, receives the other ranks' handles out of band (bench.py and
+ * misaki_render_b200/distributed.py use torch.distributed's object all-gather) and opens them.  The root passes the
+ * handles of ALL other ranks in rank order, the other ranks need not open anything.  msk_gpu_reduce_film is
+ * asynchronous on msk_gpu_stream(ctx): the root adds the peers' films of this epoch to its own in ONE kernel that
+ * waits for the peers on the device and pulls their films through NVLink; a non-root rank publishes its film and
+ * holds its stream until the root has read it.  `epoch`: non-zero, the same on every rank, different from the previous
+ * reduction's.  Device-side waits are bounded by MSK_PEER_TIMEOUT_S (default 30 s); msk_gpu_film_share_check
+ * synchronises and reports a time-out. */
+typedef struct { unsigned char reserved[64]; } MskIpcMemHandle;
+typedef struct MskFilmShare MskFilmShare;
+int    msk_gpu_film_share_create(MskCtx *ctx, size_t nfloats, MskFilmShare **out);
+float *msk_gpu_film_share_ptr(MskFilmShare *share); /* device pointer of the local film (render into it with *_dev) */
+int    msk_gpu_film_share_export(MskFilmShare *share, MskIpcMemHandle *out);
+int    msk_gpu_film_share_open(MskFilmShare *share, const MskIpcMemHandle *peers, uint32_t npeers);
+int    msk_gpu_reduce_film(MskFilmShare *share, int is_root, uint32_t epoch);
+int    msk_gpu_film_share_check(MskFilmShare *share);
+void   msk_gpu_film_share_destroy(MskFilmShare *share);
+
 #ifdef __cplusplus
 }
 #endif

@@ -23,6 +23,8 @@ EXPORTED_SYMBOLS = [
     "msk_gpu_occluded", "msk_gpu_intersect_dev", "msk_gpu_occluded_dev", "msk_gpu_intersect_stats",
     "msk_gpu_render", "msk_gpu_render_dev", "msk_gpu_develop",
     "msk_gpu_aov_channels", "msk_gpu_render_aov", "msk_gpu_render_aov_dev",
+    "msk_gpu_film_share_create", "msk_gpu_film_share_ptr", "msk_gpu_film_share_export", "msk_gpu_film_share_open",
+    "msk_gpu_reduce_film", "msk_gpu_film_share_check", "msk_gpu_film_share_destroy",
 ]
 
 # enums
@@ -156,6 +158,15 @@ def load(path: os.PathLike | None = None) -> C.CDLL:
     lib.msk_gpu_aov_channels.argtypes = [C.POINTER(MskAovDesc)]
     lib.msk_gpu_render_aov.argtypes = [C.c_void_p, C.POINTER(MskRenderDesc), C.POINTER(MskAovDesc), C.c_void_p, C.POINTER(MskStats)]
     lib.msk_gpu_render_aov_dev.argtypes = [C.c_void_p, C.POINTER(MskRenderDesc), C.POINTER(MskAovDesc), C.c_void_p, C.POINTER(MskStats)]
+    lib.msk_gpu_film_share_create.argtypes = [C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p)]
+    lib.msk_gpu_film_share_ptr.argtypes = [C.c_void_p]
+    lib.msk_gpu_film_share_ptr.restype = C.c_void_p
+    lib.msk_gpu_film_share_export.argtypes = [C.c_void_p, C.c_void_p]
+    lib.msk_gpu_film_share_open.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32]
+    lib.msk_gpu_reduce_film.argtypes = [C.c_void_p, C.c_int, C.c_uint32]
+    lib.msk_gpu_film_share_check.argtypes = [C.c_void_p]
+    lib.msk_gpu_film_share_destroy.argtypes = [C.c_void_p]
+    lib.msk_gpu_film_share_destroy.restype = None
     if path is None:
         _lib = lib
     return lib
@@ -294,3 +305,55 @@ class Scene:
         rgba = np.empty((self.height, self.width, 4), dtype=np.float32)
         check(self.lib, self.lib.msk_gpu_develop(self.handle, film.ctypes.data, rgba.ctypes.data))
         return rgba
+
+
+class FilmShare:
+    """A film in exportable device memory + the NVLink peer reduction (msk_gpu_film_share_*, msk_gpu_reduce_film)."""
+    IPC_HANDLE_BYTES = 64
+
+    def __init__(self, ctx: "Context", shape):
+        self.ctx, self.lib, self.shape = ctx, ctx.lib, tuple(int(x) for x in shape)
+        n = 1
+        for x in self.shape:
+            n *= x
+        self.nfloats = n = (n + 3) // 4 * 4  # the reduction moves float4s; the padding stays zero
+        self.handle = C.c_void_p()
+        check(self.lib, self.lib.msk_gpu_film_share_create(ctx.handle, n, C.byref(self.handle)))
+        self.ptr = int(self.lib.msk_gpu_film_share_ptr(self.handle))
+        self._epoch = 0
+
+    @property
+    def __cuda_array_interface__(self):  # lets torch.as_tensor(share, device="cuda") wrap the film without a copy
+        return {"shape": self.shape, "typestr": "<f4", "data": (self.ptr, False), "version": 2, "strides": None}
+
+    def export(self) -> bytes:
+        buf = C.create_string_buffer(self.IPC_HANDLE_BYTES)
+        check(self.lib, self.lib.msk_gpu_film_share_export(self.handle, buf))
+        return buf.raw
+
+    def open_peers(self, handles):
+        blob = b"".join(handles)
+        assert len(blob) == self.IPC_HANDLE_BYTES * len(handles)
+        buf = C.create_string_buffer(blob, len(blob)) if blob else None
+        check(self.lib, self.lib.msk_gpu_film_share_open(self.handle, buf, len(handles)))
+
+    def reduce(self, is_root: bool, epoch: int | None = None):
+        """Asynchronous on the context's stream; every rank calls it once per step with the same epoch."""
+        if epoch is None:
+            self._epoch = self._epoch % 0x7fffffff + 1
+            epoch = self._epoch
+        check(self.lib, self.lib.msk_gpu_reduce_film(self.handle, int(bool(is_root)), int(epoch)))
+
+    def check(self):
+        check(self.lib, self.lib.msk_gpu_film_share_check(self.handle))
+
+    def close(self):
+        if self.handle:
+            self.lib.msk_gpu_film_share_destroy(self.handle)
+            self.handle = C.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()

@@ -60,6 +60,10 @@ struct MskScene {
     }
 };
 
+// accessors for msk_peer.cu
+int msk_ctx_device(MskCtx *ctx) { return ctx->device; }
+int msk_ctx_sm_count(MskCtx *ctx) { return ctx->sm_count; }
+
 namespace {
 
 template <typename T> int upload(MskScene *s, const T *host, size_t n, const T **dev) {
