@@ -247,3 +247,50 @@ def test_volpath_bounded_depth_and_absorbing_fog(gpu_ctx):
         _report(f"volpath depth {depth}", e, stats, ost)
         assert e < CHAOTIC_RELMSE, (depth, e)
         assert stats.bounces == depth
+
+
+def test_render_edge_cases(gpu_ctx):
+    """Ragged and degenerate inputs through the whole wavefront: a film whose size is no multiple of the 32-pixel
+    reference block, of the film tile or of the warp; a mesh containing zero-area and duplicate triangles; several
+    emitters (uniform light selection, scene.cpp:76-87) with one of them below the horizon; one-path batches."""
+    from misaki_render_b200.scene import SceneDescription, lookat
+    from workloads import meshes
+    sd = SceneDescription(37, 23, fov=45.0, near_clip=0.1, far_clip=100.0, to_world=lookat((0, 1.5, -4), (0, 0.5, 0), (0, 1, 0)))
+    gv, gt = meshes.quad((-3, 0, -3), (-3, 0, 3), (3, 0, 3), (3, 0, -3))
+    gt = np.concatenate([gt, [[0, 0, 1], [1, 1, 1], gt[0]]]).astype(np.uint32)  # degenerate + duplicate triangles
+    sd.add_mesh(gv, gt, sd.bsdf_diffuse((0.6, 0.6, 0.6)))
+    for k, (x, rad) in enumerate([(-1.5, (30, 5, 5)), (1.5, (5, 5, 30))]):
+        lv, lt = meshes.quad((x - .4, 2.5, -.4), (x + .4, 2.5, -.4), (x + .4, 2.5, .4), (x - .4, 2.5, .4))
+        sd.add_mesh(lv, lt, sd.bsdf_diffuse((0.5, 0.5, 0.5)), radiance=rad)
+    lv, lt = meshes.quad((-1, -2, -1), (1, -2, -1), (1, -2, 1), (-1, -2, 1))  # a light under the floor: always occluded
+    sd.add_mesh(lv, lt, sd.bsdf_diffuse((0.5, 0.5, 0.5)), radiance=(9, 9, 9))
+    rd = capi.render_desc(spp=6, max_depth=4)
+    film, rgba, ofilm, oref, stats, ost = _both(gpu_ctx, sd, rd)
+    assert film.shape == (23, 37, 5) and np.isfinite(film).all()
+    np.testing.assert_allclose(film[..., 4], ofilm[..., 4], rtol=1e-5)
+    e = relmse(rgba, oref)
+    _report("edge cases", e, stats, ost)
+    assert e < EQUAL_SEED_RELMSE, e
+    with capi.Scene(gpu_ctx, sd) as sc:
+        tiny, st = sc.render(capi.render_desc(spp=6, max_depth=4, paths_per_batch=1))  # one sample of every pixel per batch
+        assert st.batches == 6
+        np.testing.assert_allclose(tiny, film, rtol=2e-5, atol=1e-6)
+        none, st0 = sc.render(capi.render_desc(spp=6, max_depth=4, sample_begin=3, sample_end=3))  # empty sample range
+        assert st0.paths == 0 and not none.any()
+        zero, stz = sc.render(capi.render_desc(spp=2, max_depth=0))  # max_depth 0: the loop body never runs (path.cpp:33)
+        assert stz.rays_closest == 0 and not zero[..., :3].any() and (zero[..., 4] > 0).all()
+
+
+def test_render_scene_without_geometry(gpu_ctx):
+    """No shapes at all: every camera ray escapes; with a constant environment each sample returns its radiance
+    (path.cpp:34-41, constant.cpp:79-81), without one the image is black but the filter weights are still there."""
+    from misaki_render_b200.scene import SceneDescription
+    for env in (None, (0.5, 0.6, 0.8)):
+        sd = SceneDescription(16, 16, fov=40.0)
+        if env is not None:
+            sd.add_constant_environment(env)
+        rd = capi.render_desc(spp=4, max_depth=3)
+        film, rgba, ofilm, oref, stats, ost = _both(gpu_ctx, sd, rd)
+        assert np.isfinite(film).all() and stats.rays_shadow == 0
+        np.testing.assert_allclose(film, ofilm, rtol=2e-5, atol=1e-7)
+        assert (rgba[..., :3].max() > 0) == (env is not None)
