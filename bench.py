@@ -528,12 +528,15 @@ def run_ours(args, rank: int, local_rank: int, world: int):
         st_s = scene.render_dev(rd_s, film.data_ptr())
         nodes_c, tris_c = st_s.nodes_closest / max(st_s.rays_closest, 1), st_s.tris_closest / max(st_s.rays_closest, 1)
         nodes_s, tris_s = st_s.nodes_shadow / max(st_s.rays_shadow, 1), st_s.tris_shadow / max(st_s.rays_shadow, 1)
+        # rays finished by the per-path tail kernel (k_tail, timed as its own stage) do not belong to the wavefront launches
+        wf_c = 1.0 - st_t.tail_rays_closest / max(st_t.rays_closest, 1)
+        wf_s = 1.0 - st_t.tail_rays_shadow / max(st_t.rays_shadow, 1)
         stages = {
             "k_intersect": (st_t.ms_intersect, st_t.n_intersect_launches,
-                            st_s.rays_closest * (BYTES_RAY_IN + BYTES_HIT_OUT) + st_s.nodes_closest * BYTES_NODE + st_s.tris_closest * BYTES_TRI),
-            "k_shade": (st_t.ms_shade, st_t.n_shade_launches, st_s.shaded_vertices * BYTES_SHADE_VERTEX),
+                            wf_c * (st_s.rays_closest * (BYTES_RAY_IN + BYTES_HIT_OUT) + st_s.nodes_closest * BYTES_NODE + st_s.tris_closest * BYTES_TRI)),
+            "k_shade": (st_t.ms_shade, st_t.n_shade_launches, wf_c * st_s.shaded_vertices * BYTES_SHADE_VERTEX),
             "k_shadow": (st_t.ms_shadow, st_t.n_shadow_launches,
-                         st_s.rays_shadow * (BYTES_RAY_IN + BYTES_OCC_OUT) + st_s.nodes_shadow * BYTES_NODE + st_s.tris_shadow * BYTES_TRI),
+                         wf_s * (st_s.rays_shadow * (BYTES_RAY_IN + BYTES_OCC_OUT) + st_s.nodes_shadow * BYTES_NODE + st_s.tris_shadow * BYTES_TRI)),
         }
         peaks_file = ROOT / "MEASURED_PEAKS.json"
         if peaks_file.exists():
@@ -551,7 +554,7 @@ def run_ours(args, rank: int, local_rank: int, world: int):
             except (ValueError, OSError):
                 traffic = None
         stage_ms = {"raygen": st_t.ms_raygen, "intersect": st_t.ms_intersect, "sort": st_t.ms_sort, "shade": st_t.ms_shade, "shadow": st_t.ms_shadow,
-                    "film": st_t.ms_film, "step_with_timers": st_t.ms_render}
+                    "film": st_t.ms_film, "tail": st_t.ms_tail, "step_with_timers": st_t.ms_render}
         roofline = {
             "bound": "hbm", "kernel": top, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
             "traffic": traffic, "peak_source": peak_src,
@@ -562,6 +565,8 @@ def run_ours(args, rank: int, local_rank: int, world: int):
                            "algorithmic-traffic figure, not DRAM traffic (see `traffic`).",
             "per_ray": {"nodes_closest": nodes_c, "tris_closest": tris_c, "nodes_shadow": nodes_s, "tris_shadow": tris_s},
             "stage_ms": stage_ms,
+            "tail": {"rays_closest": int(st_t.tail_rays_closest), "rays_shadow": int(st_t.tail_rays_shadow), "launches": int(st_t.n_tail_launches),
+                     "note": "k_tail: one launch runs every path still alive once the queue is short (MSK_TAIL_THRESHOLD rays) to completion"},
             "stage_gbs": {k: (v[2] / (v[0] * 1e-3) / 1e9 if v[0] > 0 else 0.0) for k, v in stages.items()},
         }
 

@@ -191,6 +191,11 @@ typedef struct {
     uint64_t nodes_shadow, tris_shadow;   /*   tested, summed over all closest-hit / any-hit queries        */
     float    ms_sort;        /* device time of the material sort launches (with MSK_RENDER_STAGE_TIMERS) */
     uint32_t pad2_;
+    /* unbounded-depth jobs finish with one per-path launch once the queue is short (k_tail); its rays are included in
+     * rays_closest / rays_shadow and listed here so that per-kernel rooflines can separate them */
+    uint64_t tail_rays_closest, tail_rays_shadow;
+    float    ms_tail;        /* with MSK_RENDER_STAGE_TIMERS */
+    uint32_t n_tail_launches;
 } MskStats;
 
 /* ---- AOV integrator (src/librender/integrators/aov.cpp:22-29,87-144) ---- */

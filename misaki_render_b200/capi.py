@@ -99,7 +99,8 @@ class MskStats(C.Structure):
                 ("n_intersect_launches", C.c_uint32), ("n_shade_launches", C.c_uint32), ("n_shadow_launches", C.c_uint32),
                 ("pad_", C.c_uint32), ("shaded_vertices", C.c_uint64), ("nodes_closest", C.c_uint64),
                 ("tris_closest", C.c_uint64), ("nodes_shadow", C.c_uint64), ("tris_shadow", C.c_uint64),
-                ("ms_sort", C.c_float), ("pad2_", C.c_uint32)]
+                ("ms_sort", C.c_float), ("pad2_", C.c_uint32), ("tail_rays_closest", C.c_uint64), ("tail_rays_shadow", C.c_uint64),
+                ("ms_tail", C.c_float), ("n_tail_launches", C.c_uint32)]
 
 
 class MskAovDesc(C.Structure):

@@ -47,6 +47,8 @@ struct Ctrl {
     unsigned long long total_closest, total_shadow;
     unsigned long long nodes_closest, tris_closest, nodes_shadow, tris_shadow; // MSK_RENDER_TRAVERSAL_STATS
     unsigned long long shaded; // path vertices processed by k_shade
+    unsigned long long tail_closest, tail_shadow; // rays traced by k_tail (also included in total_*)
+    unsigned long long tail_depth;                // deepest vertex k_tail reached
 };
 
 struct Pool {
@@ -250,6 +252,123 @@ __global__ void __launch_bounds__(kSortThreads) k_sort(const __grid_constant__ D
 #define MSK_SHADE_DIFFUSE_BLOCKS 4
 #endif
 constexpr int shade_min_blocks(int key) { return key < 0 ? MSK_SHADE_MIN_BLOCKS : (key == 0 ? 8 : (key == 1 ? MSK_SHADE_DIFFUSE_BLOCKS : 4)); }
+// One path vertex of PathTracer::sample given the hit record of the ray that arrived (shared by the wavefront stage
+// k_shade and the per-path tail kernel k_tail).  TYPE >= 0: BSDF type known at compile time.
+struct VertexOut {
+    bool emit_ray, emit_shadow, add_L;
+    MskRay nray, sray;
+    float4 nT, nAUX, contrib, L;
+    uint4 nMISC;
+};
+template <int TYPE>
+__device__ __forceinline__ void shade_vertex(const DScene &sc, const BatchParams &bp, bool miss, uint32_t geom, float4 hit, float4 rd,
+                                             float4 T, float4 wl, uint4 misc, float4 aux, VertexOut &o) {
+    bool emit_ray = false, emit_shadow = false;
+    MskRay nray, sray;
+    float4 nT, nAUX, contrib;
+    uint4 nMISC;
+    uint64_t rng = (uint64_t) misc.x | ((uint64_t) misc.y << 32);
+    const uint32_t path = misc.z;
+    const int depth = (int) (misc.w & 0xffffu);
+    const bool prev_delta = (misc.w & kFlagDelta) != 0;
+    float eta = aux.x;
+    const float prev_pdf = aux.y, stale_pdf = aux.z;
+    float4 L = f4(0.f);
+    bool add_L = false, alive = true;
+    const V3 rdir = v3(rd.x, rd.y, rd.z);
+
+    if (miss) { // miss: path.cpp:34-41 (depth 1) / :90-98,:103-108 (BSDF-sampled ray escaped)
+        if (sc.environment >= 0) {
+            int radiance = sc.emitters[sc.environment].radiance; // constant.cpp:79-81; a miss carries no uv
+            if (sc.has_textures) radiance = texture_resolve(sc, radiance, 0.f, 0.f);
+            float4 le = spectrum_eval(sc, radiance, wl);
+            if (depth == 1) { if (!bp.hide_emitters) { L = T * le; add_L = true; } }
+            else { L = T * le * mis_weight(prev_pdf, prev_delta ? 0.f : stale_pdf); add_L = true; }
+        }
+        alive = false;
+    } else {
+        const DMeshInfo mi = sc.meshes[geom];
+        const Surface sf = make_surface(sc, mi, __float_as_uint(hit.w), hit.y, hit.z);
+        const V3 wi = to_local(sf.sh, -rdir);
+        // emitter term of the ray that arrived here: weight now, radiance after the single spectrum pass below
+        int id_le = -1;
+        float le_weight = 1.f;
+        if (mi.emitter >= 0 && wi.z > 0.f) { // area.cpp:51-54
+            if (depth == 1) { // path.cpp:44-47
+                if (!bp.hide_emitters) id_le = sc.emitters[mi.emitter].radiance;
+            } else {          // path.cpp:82-88,103-108 with ds.set_query (records.cpp:7-14)
+                float emitter_pdf = 0.f;
+                if (!prev_delta) {
+                    float dp = fabsf(dot(rdir, sf.sh.n));
+                    emitter_pdf = mi.inv_area * ((dp != 0.f) ? (hit.x * hit.x) / dp : 0.f);
+                    if (sc.nemitters > 1) emitter_pdf *= 1.f / (float) sc.nemitters;
+                }
+                le_weight = mis_weight(prev_pdf, emitter_pdf);
+                id_le = sc.emitters[mi.emitter].radiance;
+            }
+            if (id_le >= 0 && sc.has_textures) id_le = texture_resolve(sc, id_le, sf.uvx, sf.uvy);
+        }
+        const float4 T_in = T; // the emitter term uses the throughput before this vertex's roulette division
+        if (depth > 1 && depth >= bp.rr_depth) { // path.cpp:116-122 of the previous iteration
+            float qq = fminf(hmax(T) * eta * eta, 0.95f);
+            if (next1d(rng) >= qq) alive = false;
+            else T = T / qq;
+        }
+        if (alive && bp.max_depth > 0 && depth >= bp.max_depth) alive = false; // path.cpp:48-49
+        MskBsdf bsdf = sc.bsdfs[mi.bsdf];
+        NeeSample ns;
+        ns.pdf = 0.f; ns.radiance = -1; ns.stale_pdf = 0.f;
+        bool nee = false;
+        if (alive) {
+            if (sc.has_textures) bsdf_resolve_textures(sc, bsdf, sf.uvx, sf.uvy); // Texture::eval(si), checkerboard.cpp:25-31
+            if (bsdf_is_smooth(TYPE >= 0 ? TYPE : bsdf.type)) { // path.cpp:56-67
+                float sx = next1d(rng), sy = next1d(rng);
+                ns = sample_emitter_direct(sc, sf.p, sx, sy);
+                nee = ns.pdf != 0.f;
+            }
+        }
+        BsdfSpectra sp;
+        float4 le, ln;
+        eval_vertex_spectra<TYPE>(sc, bsdf, alive, id_le, nee ? ns.radiance : -1, wl, sp, le, ln);
+        if (id_le >= 0) { L = T_in * le * le_weight; add_L = true; } // le_weight == 1 at depth 1
+        if (alive) {
+            const float new_stale = ns.stale_pdf;
+            const float tmin_spawn = (1.f + max_abs(sf.p)) * kRayEpsilon; // interaction.h:40-44, scene.cpp:91-93
+            if (nee) {
+                V3 wo = to_local(sf.sh, ns.d);
+                float4 bval; float bpdf;
+                bsdf_eval_pdf<TYPE>(sp, bsdf, wi, wo, bval, bpdf);
+                float w = mis_weight(ns.pdf, bpdf);
+                contrib = T * nee_value(ns, ln) * bval * w;
+                if (!is_zero(contrib)) {
+                    emit_shadow = true;
+                    sray.o[0] = sf.p.x; sray.o[1] = sf.p.y; sray.o[2] = sf.p.z;
+                    sray.tmin = kRayEpsilon * (1.f + max_abs(sf.p));
+                    sray.d[0] = ns.d.x; sray.d[1] = ns.d.y; sray.d[2] = ns.d.z;
+                    sray.tmax = ns.dist * (1.f - kShadowEpsilon);
+                }
+            }
+            float s1 = next1d(rng), s2x = next1d(rng), s2y = next1d(rng); // path.cpp:71-72, left to right
+            BsdfSample bs = bsdf_sample<TYPE>(sp, bsdf, wi, s1, s2x, s2y);
+            if (is_zero(bs.weight)) alive = false; // failed sample: nothing downstream can contribute
+            else {
+                V3 wo = to_world(sf.sh, bs.wo);
+                T = T * bs.weight;
+                eta *= bs.eta;
+                emit_ray = true;
+                nray.o[0] = sf.p.x; nray.o[1] = sf.p.y; nray.o[2] = sf.p.z; nray.tmin = tmin_spawn;
+                nray.d[0] = wo.x; nray.d[1] = wo.y; nray.d[2] = wo.z; nray.tmax = MSK_INF;
+                nT = T;
+                nMISC = make_uint4((uint32_t) rng, (uint32_t) (rng >> 32), path,
+                                   (uint32_t) (depth + 1) | ((bs.type & BF_Delta) ? kFlagDelta : 0u));
+                nAUX = make_float4(eta, bs.pdf, new_stale, 0.f);
+            }
+        }
+    }
+    o.emit_ray = emit_ray; o.emit_shadow = emit_shadow; o.add_L = add_L;
+    o.nray = nray; o.sray = sray; o.nT = nT; o.nAUX = nAUX; o.contrib = contrib; o.L = L; o.nMISC = nMISC;
+}
+
 template <int KEY>
 __global__ void __launch_bounds__(128, shade_min_blocks(KEY)) k_shade(const __grid_constant__ DScene sc, Pool pool, BatchParams bp, int cur) {
     Ctrl *c = pool.ctrl;
@@ -281,110 +400,17 @@ __global__ void __launch_bounds__(128, shade_min_blocks(KEY)) k_shade(const __gr
             const uint32_t q = pool.sorted[(size_t) key * pool.capacity + j];
             const float4 hit = pool.hit[q];
             const float4 rd  = reinterpret_cast<const float4 *>(pool.rays[cur] + q)[1];
-            float4 T = pool.T[cur][q];
+            const float4 T = pool.T[cur][q];
             const float4 wl = pool.WL[cur][q];
             const uint4 misc = pool.MISC[cur][q];
             const float4 aux = pool.AUX[cur][q];
-            uint64_t rng = (uint64_t) misc.x | ((uint64_t) misc.y << 32);
             path = misc.z;
-            const int depth = (int) (misc.w & 0xffffu);
-            const bool prev_delta = (misc.w & kFlagDelta) != 0;
-            float eta = aux.x;
-            const float prev_pdf = aux.y, stale_pdf = aux.z;
-            float4 L = f4(0.f);
-            bool add_L = false, alive = true;
-            const V3 rdir = v3(rd.x, rd.y, rd.z);
-
-            if (KEY == 0 || (KEY < 0 && key == 0)) { // miss: path.cpp:34-41 (depth 1) / :90-98,:103-108 (BSDF-sampled ray escaped)
-                if (sc.environment >= 0) {
-                    int radiance = sc.emitters[sc.environment].radiance; // constant.cpp:79-81; a miss carries no uv
-                    if (sc.has_textures) radiance = texture_resolve(sc, radiance, 0.f, 0.f);
-                    float4 le = spectrum_eval(sc, radiance, wl);
-                    if (depth == 1) { if (!bp.hide_emitters) { L = T * le; add_L = true; } }
-                    else { L = T * le * mis_weight(prev_pdf, prev_delta ? 0.f : stale_pdf); add_L = true; }
-                }
-                alive = false;
-            } else if (KEY != 0) {
-                const uint32_t geom = pool.hit_geom[q];
-                const DMeshInfo mi = sc.meshes[geom];
-                const Surface sf = make_surface(sc, mi, __float_as_uint(hit.w), hit.y, hit.z);
-                const V3 wi = to_local(sf.sh, -rdir);
-                // emitter term of the ray that arrived here: weight now, radiance after the single spectrum pass below
-                int id_le = -1;
-                float le_weight = 1.f;
-                if (mi.emitter >= 0 && wi.z > 0.f) { // area.cpp:51-54
-                    if (depth == 1) { // path.cpp:44-47
-                        if (!bp.hide_emitters) id_le = sc.emitters[mi.emitter].radiance;
-                    } else {          // path.cpp:82-88,103-108 with ds.set_query (records.cpp:7-14)
-                        float emitter_pdf = 0.f;
-                        if (!prev_delta) {
-                            float dp = fabsf(dot(rdir, sf.sh.n));
-                            emitter_pdf = mi.inv_area * ((dp != 0.f) ? (hit.x * hit.x) / dp : 0.f);
-                            if (sc.nemitters > 1) emitter_pdf *= 1.f / (float) sc.nemitters;
-                        }
-                        le_weight = mis_weight(prev_pdf, emitter_pdf);
-                        id_le = sc.emitters[mi.emitter].radiance;
-                    }
-                    if (id_le >= 0 && sc.has_textures) id_le = texture_resolve(sc, id_le, sf.uvx, sf.uvy);
-                }
-                const float4 T_in = T; // the emitter term uses the throughput before this vertex's roulette division
-                if (depth > 1 && depth >= bp.rr_depth) { // path.cpp:116-122 of the previous iteration
-                    float qq = fminf(hmax(T) * eta * eta, 0.95f);
-                    if (next1d(rng) >= qq) alive = false;
-                    else T = T / qq;
-                }
-                if (alive && bp.max_depth > 0 && depth >= bp.max_depth) alive = false; // path.cpp:48-49
-                MskBsdf bsdf = sc.bsdfs[mi.bsdf];
-                NeeSample ns;
-                ns.pdf = 0.f; ns.radiance = -1; ns.stale_pdf = 0.f;
-                bool nee = false;
-                if (alive) {
-                    if (sc.has_textures) bsdf_resolve_textures(sc, bsdf, sf.uvx, sf.uvy); // Texture::eval(si), checkerboard.cpp:25-31
-                    if (bsdf_is_smooth(TYPE >= 0 ? TYPE : bsdf.type)) { // path.cpp:56-67
-                        float sx = next1d(rng), sy = next1d(rng);
-                        ns = sample_emitter_direct(sc, sf.p, sx, sy);
-                        nee = ns.pdf != 0.f;
-                    }
-                }
-                BsdfSpectra sp;
-                float4 le, ln;
-                eval_vertex_spectra<TYPE>(sc, bsdf, alive, id_le, nee ? ns.radiance : -1, wl, sp, le, ln);
-                if (id_le >= 0) { L = T_in * le * le_weight; add_L = true; } // le_weight == 1 at depth 1
-                if (alive) {
-                    const float new_stale = ns.stale_pdf;
-                    const float tmin_spawn = (1.f + max_abs(sf.p)) * kRayEpsilon; // interaction.h:40-44, scene.cpp:91-93
-                    if (nee) {
-                        V3 wo = to_local(sf.sh, ns.d);
-                        float4 bval; float bpdf;
-                        bsdf_eval_pdf<TYPE>(sp, bsdf, wi, wo, bval, bpdf);
-                        float w = mis_weight(ns.pdf, bpdf);
-                        contrib = T * nee_value(ns, ln) * bval * w;
-                        if (!is_zero(contrib)) {
-                            emit_shadow = true;
-                            sray.o[0] = sf.p.x; sray.o[1] = sf.p.y; sray.o[2] = sf.p.z;
-                            sray.tmin = kRayEpsilon * (1.f + max_abs(sf.p));
-                            sray.d[0] = ns.d.x; sray.d[1] = ns.d.y; sray.d[2] = ns.d.z;
-                            sray.tmax = ns.dist * (1.f - kShadowEpsilon);
-                        }
-                    }
-                    float s1 = next1d(rng), s2x = next1d(rng), s2y = next1d(rng); // path.cpp:71-72, left to right
-                    BsdfSample bs = bsdf_sample<TYPE>(sp, bsdf, wi, s1, s2x, s2y);
-                    if (is_zero(bs.weight)) alive = false; // failed sample: nothing downstream can contribute
-                    else {
-                        V3 wo = to_world(sf.sh, bs.wo);
-                        T = T * bs.weight;
-                        eta *= bs.eta;
-                        emit_ray = true;
-                        nray.o[0] = sf.p.x; nray.o[1] = sf.p.y; nray.o[2] = sf.p.z; nray.tmin = tmin_spawn;
-                        nray.d[0] = wo.x; nray.d[1] = wo.y; nray.d[2] = wo.z; nray.tmax = MSK_INF;
-                        nT = T; nWL = wl;
-                        nMISC = make_uint4((uint32_t) rng, (uint32_t) (rng >> 32), path,
-                                           (uint32_t) (depth + 1) | ((bs.type & BF_Delta) ? kFlagDelta : 0u));
-                        nAUX = make_float4(eta, bs.pdf, new_stale, 0.f);
-                    }
-                }
-            }
-            if (add_L) { float4 acc = pool.L[path]; pool.L[path] = acc + L; }
+            VertexOut vo;
+            const bool miss = KEY == 0 || (KEY < 0 && key == 0);
+            shade_vertex<TYPE>(sc, bp, miss, miss ? 0xffffffffu : pool.hit_geom[q], hit, rd, T, wl, misc, aux, vo);
+            emit_ray = vo.emit_ray; emit_shadow = vo.emit_shadow;
+            nray = vo.nray; sray = vo.sray; nT = vo.nT; nWL = wl; nAUX = vo.nAUX; contrib = vo.contrib; nMISC = vo.nMISC;
+            if (vo.add_L) { float4 acc = pool.L[path]; pool.L[path] = acc + vo.L; }
         }
         // compaction: one atomic per warp and queue
         uint32_t m_ray = __ballot_sync(0xffffffffu, emit_ray), m_sh = __ballot_sync(0xffffffffu, emit_shadow);
@@ -412,6 +438,96 @@ __global__ void __launch_bounds__(128, shade_min_blocks(KEY)) k_shade(const __gr
             pool.sh_path[o]    = path;
         }
     }
+}
+
+// ---------------------------------------------------------------------------------------
+// Tail of an unbounded-depth job.  Once Russian roulette has thinned the queue, a bounce is a handful of
+// latency-bound launches over a few hundred thousand rays: on C2 the 17 bounces after depth 6 carry < 5 % of the
+// rays and took 1.28 ms of the 17.6 ms step (75 us per bounce, profiles/r01g_bounces_c2.txt).  k_tail finishes
+// those paths in ONE launch: every thread takes a surviving path and runs intersect -> shade -> shadow ray in a loop
+// until the path dies, with the same device functions (traverse, shade_vertex) and the same order of additions to
+// L[path] as the wavefront stages, so the film is bit-identical.  Divergence is irrelevant at this size; what
+// matters is that there is no queue traffic, no sort and no launch boundary between the vertices of a path.
+template <bool STATS>
+__global__ void __launch_bounds__(128) k_tail(const __grid_constant__ DScene sc, Pool pool, BatchParams bp, int cur) {
+    Ctrl *c = pool.ctrl;
+    const uint32_t n = c->n_rays[cur];
+    uint32_t n_closest = 0, n_shadow = 0, max_depth = 0, cn = 0, ct = 0, sn = 0, stt = 0;
+    // persistent lanes: a lane whose path has died takes the next surviving path (path lengths under Russian roulette
+    // are geometric, so a static assignment leaves most lanes of a warp idle behind its longest path)
+    bool have = false, more = true;
+    float4 ro, rd, T, aux, wl, L;
+    uint4 misc;
+    uint32_t path = 0;
+    const uint32_t below = (1u << lane_id()) - 1u;
+    for (;;) {
+        const uint32_t want = __ballot_sync(0xffffffffu, !have && more);
+        if (want) {
+            uint32_t base = 0;
+            if (lane_id() == (uint32_t) (__ffs(want) - 1)) base = atomicAdd(&c->cursor_isect, (uint32_t) __popc(want));
+            base = __shfl_sync(0xffffffffu, base, __ffs(want) - 1);
+            if (!have && more) {
+                const uint32_t i = base + __popc(want & below);
+                if (i < n) {
+                    const float4 *rp = reinterpret_cast<const float4 *>(pool.rays[cur] + i);
+                    ro = rp[0]; rd = rp[1];
+                    T = pool.T[cur][i]; aux = pool.AUX[cur][i]; wl = pool.WL[cur][i]; misc = pool.MISC[cur][i];
+                    path = misc.z;
+                    L = pool.L[path];
+                    have = true;
+                } else {
+                    more = false;
+                }
+            }
+        }
+        if (__ballot_sync(0xffffffffu, have) == 0u) break;
+        if (have) {
+            RayHit h;
+            uint32_t a = 0, b = 0;
+            const bool found = traverse<false, STATS>(sc.nodes, sc.tris, ro.x, ro.y, ro.z, rd.x, rd.y, rd.z, ro.w, rd.w, h, &a, &b);
+            n_closest++;
+            if (STATS) { cn += a; ct += b; }
+            max_depth = max(max_depth, misc.w & 0xffffu);
+            // the hit record exactly as IntersectIO::commit stores it
+            const float4 hit = make_float4(found ? h.t : MSK_INF, found ? h.u : 0.f, found ? h.v : 0.f, __uint_as_float(found ? h.prim : 0xffffffffu));
+            VertexOut vo;
+            shade_vertex<-1>(sc, bp, !found, found ? h.geom : 0xffffffffu, hit, rd, T, wl, misc, aux, vo);
+            if (vo.add_L) L = L + vo.L;
+            if (vo.emit_shadow) { // k_shadow: unoccluded => L += contribution
+                RayHit sh;
+                const bool occluded = traverse<true, STATS>(sc.nodes, sc.tris, vo.sray.o[0], vo.sray.o[1], vo.sray.o[2], vo.sray.d[0], vo.sray.d[1],
+                                                            vo.sray.d[2], vo.sray.tmin, vo.sray.tmax, sh, &a, &b);
+                n_shadow++;
+                if (STATS) { sn += a; stt += b; }
+                if (!occluded) L = L + vo.contrib;
+            }
+            if (vo.emit_ray) {
+                ro = make_float4(vo.nray.o[0], vo.nray.o[1], vo.nray.o[2], vo.nray.tmin);
+                rd = make_float4(vo.nray.d[0], vo.nray.d[1], vo.nray.d[2], vo.nray.tmax);
+                T = vo.nT; aux = vo.nAUX; misc = vo.nMISC;
+            } else {
+                pool.L[path] = L;
+                have = false;
+            }
+        }
+    }
+    for (int o = 16; o; o >>= 1) {
+        n_closest += __shfl_xor_sync(0xffffffffu, n_closest, o); n_shadow += __shfl_xor_sync(0xffffffffu, n_shadow, o);
+        max_depth = max(max_depth, __shfl_xor_sync(0xffffffffu, max_depth, o));
+    }
+    if (lane_id() == 0 && (n_closest | n_shadow)) {
+        atomicAdd(&c->total_closest, (unsigned long long) n_closest); atomicAdd(&c->total_shadow, (unsigned long long) n_shadow);
+        atomicAdd(&c->tail_closest, (unsigned long long) n_closest); atomicAdd(&c->tail_shadow, (unsigned long long) n_shadow);
+        atomicAdd(&c->shaded, (unsigned long long) n_closest);
+        atomicMax(&c->tail_depth, (unsigned long long) max_depth);
+    }
+    if (STATS) { add_traversal_stats(&c->nodes_closest, &c->tris_closest, cn, ct); add_traversal_stats(&c->nodes_shadow, &c->tris_shadow, sn, stt); }
+}
+
+// after k_tail: the queue it consumed is empty
+__global__ void k_end_tail(Ctrl *c, int cur) {
+    c->n_rays[cur] = 0; c->n_rays[cur ^ 1] = 0; c->n_shadow = 0; c->cursor_isect = 0; c->cursor_shadow = 0;
+    for (int i = 0; i < kNumKeys; ++i) c->type_count[i] = 0;
 }
 
 // ---------------------------------------------------------------------------------------
@@ -943,6 +1059,8 @@ struct Renderer::Impl {
     uint32_t spec_min = 1u << 18;     // MSK_SPEC_MIN: ... while the queue may hold at least this many vertices
     int shadow_static_bounces = 0;    // MSK_SHADOW_STATIC_BOUNCES: bounces whose shadow queue counts as coherent
     int debug_bounces = 0;            // MSK_DEBUG_BOUNCES: print polled queue lengths and per-launch stage times to stderr
+    uint32_t tail_threshold = 1u << 18; // MSK_TAIL_THRESHOLD: finish an unbounded job with k_tail once the queue is this short (0: never)
+    int poll_min_depth = 8;           // MSK_POLL_MIN_DEPTH: jobs with max_depth >= this (or unbounded) poll the queue length from bounce 4 on
     int async_poll = 1;               // MSK_ASYNC_POLL: poll the queue length one bounce late, without draining the stream
     std::vector<cudaEvent_t> timer_events; // MSK_RENDER_STAGE_TIMERS
     std::vector<int> timer_stage;
@@ -986,6 +1104,8 @@ int Renderer::init(int sm_count) {
     impl_->spec_min = (uint32_t) env_u("MSK_SPEC_MIN", impl_->spec_min);
     impl_->shadow_static_bounces = (int) env_u("MSK_SHADOW_STATIC_BOUNCES", impl_->shadow_static_bounces);
     impl_->async_poll = (int) env_u("MSK_ASYNC_POLL", impl_->async_poll);
+    impl_->tail_threshold = (uint32_t) env_u("MSK_TAIL_THRESHOLD", impl_->tail_threshold);
+    impl_->poll_min_depth = (int) env_u("MSK_POLL_MIN_DEPTH", impl_->poll_min_depth);
     impl_->debug_bounces = (int) env_u("MSK_DEBUG_BOUNCES", 0);
     return MSK_OK;
 }
@@ -1069,16 +1189,17 @@ int Renderer::render(cudaStream_t stream, const DScene &sc, const MskRenderDesc 
     const bool trace_paths = !aov || plan.rgba_channel >= 0; // an AOV integrator without a nested one traces primary rays only
 
     if (rd.clear_film) MSK_CUDA_CHECK(cudaMemsetAsync(d_film, 0, (size_t) npix * stride * sizeof(float), stream));
-    MSK_CUDA_CHECK(cudaMemsetAsync(&pool.ctrl->total_closest, 0, 7 * sizeof(unsigned long long), stream));
+    MSK_CUDA_CHECK(cudaMemsetAsync(&pool.ctrl->total_closest, 0, 10 * sizeof(unsigned long long), stream));
     const bool tstats = (rd.flags & MSK_RENDER_TRAVERSAL_STATS) != 0;
     MSK_CUDA_CHECK(cudaEventRecord(im.ev[0], stream));
     uint64_t launches = 0;
     uint32_t max_bounces = 0, batches = 0;
+    bool tail_used = false;
     const int pb = im.persistent_blocks;
     // MSK_RENDER_STAGE_TIMERS: bracket every launch with a pair of events (a profiling aid used by bench.py
     // for the per-kernel roofline; the extra event records perturb ms_render slightly, so it is off by default)
     const bool timers = (rd.flags & MSK_RENDER_STAGE_TIMERS) != 0;
-    enum { ST_RAYGEN, ST_INTERSECT, ST_SORT, ST_SHADE, ST_SHADOW, ST_FILM, ST_COUNT };
+    enum { ST_RAYGEN, ST_INTERSECT, ST_SORT, ST_SHADE, ST_SHADOW, ST_FILM, ST_TAIL, ST_COUNT };
     uint64_t extra_closest = 0;
     std::vector<int> &tstage = im.timer_stage;
     tstage.clear();
@@ -1118,6 +1239,9 @@ int Renderer::render(cudaStream_t stream, const DScene &sc, const MskRenderDesc 
             MSK_STAGE(ST_FILM, (k_aov_capture<<<(n + 255) / 256, 256, 0, stream>>>(sc, pool, bp, plan)));
             extra_closest += n;
         }
+        // (not with MSK_RENDER_TRAVERSAL_STATS: the per-stage node / triangle counters then describe the wavefront kernels alone)
+        const bool poll = bound >= (uint32_t) im.poll_min_depth; // unbounded jobs, and bounded ones deep enough to have a thin tail
+        const bool use_tail = im.tail_threshold > 0 && rd.integrator == MSK_INTEGRATOR_PATH && poll && !tstats;
         uint32_t n_est = n;       // upper bound of the current queue length known to the host (queues only shrink)
         bool poll_pending = false; // a poll of the previous bounce is in flight (async_poll)
         while (bounce < bound) {
@@ -1147,7 +1271,7 @@ int Renderer::render(cudaStream_t stream, const DScene &sc, const MskRenderDesc 
             // unbounded paths (Russian roulette only): poll the queue length once it is likely short.  The poll of
             // bounce b is read after bounce b+1 has been enqueued, so the stream never drains; the price is one
             // bounce over an empty queue at the very end.
-            if (bound == 0xffffffffu && bounce >= 4) {
+            if (poll && bounce >= 4 && bounce < bound) {
                 const int slot = (int) (bounce & 1u);
                 MSK_CUDA_CHECK(cudaMemcpyAsync(im.h_poll[slot], pool.ctrl, sizeof(Ctrl), cudaMemcpyDeviceToHost, stream));
                 MSK_CUDA_CHECK(cudaEventRecord(im.poll_ev[slot], stream));
@@ -1163,6 +1287,15 @@ int Renderer::render(cudaStream_t stream, const DScene &sc, const MskRenderDesc 
                     MSK_CUDA_CHECK(cudaEventSynchronize(im.poll_ev[slot]));
                     n_est = im.h_poll[slot]->n_rays[cur];
                     if (n_est == 0) break;
+                }
+                // queues only shrink: once the last polled length is below the threshold, one k_tail launch runs
+                // every surviving path of the current queue to completion instead of ~5 launches per further bounce
+                if (use_tail && n_est <= im.tail_threshold) {
+                    MSK_STAGE(ST_TAIL, (k_tail<false><<<pb, 128, 0, stream>>>(sc, pool, bp, cur)));
+                    k_end_tail<<<1, 1, 0, stream>>>(pool.ctrl, cur);
+                    launches++;
+                    tail_used = true;
+                    break;
                 }
                 if (bounce > 100000) return fail(MSK_ERR_CUDA, "path queue did not drain");
             }
@@ -1191,7 +1324,9 @@ int Renderer::render(cudaStream_t stream, const DScene &sc, const MskRenderDesc 
         stats->nodes_closest = im.h_ctrl->nodes_closest; stats->tris_closest = im.h_ctrl->tris_closest;
         stats->nodes_shadow = im.h_ctrl->nodes_shadow; stats->tris_shadow = im.h_ctrl->tris_shadow;
         stats->kernel_launches = launches;
-        stats->bounces = max_bounces; stats->batches = batches;
+        stats->bounces = tail_used ? std::max(max_bounces, (uint32_t) im.h_ctrl->tail_depth) : max_bounces;
+        stats->batches = batches;
+        stats->tail_rays_closest = im.h_ctrl->tail_closest; stats->tail_rays_shadow = im.h_ctrl->tail_shadow;
         cudaEventElapsedTime(&stats->ms_render, im.ev[0], im.ev[1]);
         if (timers) {
             float acc[ST_COUNT] = {};
@@ -1206,6 +1341,7 @@ int Renderer::render(cudaStream_t stream, const DScene &sc, const MskRenderDesc 
             stats->ms_shadow = acc[ST_SHADOW]; stats->ms_film = acc[ST_FILM]; stats->ms_sort = acc[ST_SORT];
             stats->n_intersect_launches = cnt[ST_INTERSECT]; stats->n_shade_launches = cnt[ST_SHADE];
             stats->n_shadow_launches = cnt[ST_SHADOW];
+            stats->ms_tail = acc[ST_TAIL]; stats->n_tail_launches = cnt[ST_TAIL];
         }
     }
     return MSK_OK;

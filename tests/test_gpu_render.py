@@ -294,3 +294,21 @@ def test_render_scene_without_geometry(gpu_ctx):
         assert np.isfinite(film).all() and stats.rays_shadow == 0
         np.testing.assert_allclose(film, ofilm, rtol=2e-5, atol=1e-7)
         assert (rgba[..., :3].max() > 0) == (env is not None)
+
+
+def test_tail_kernel_is_bit_identical(monkeypatch):
+    """Unbounded-depth jobs finish with k_tail (one per-path launch) once the queue is short.  It runs the same device
+    functions in the same order as the wavefront stages, so the film must not change by a single bit, and the ray
+    counts must agree."""
+    sd = scenes.bunny(96, 96, n=16)
+    rd = capi.render_desc(spp=8, max_depth=-1, rr_depth=3)
+    with capi.Context(0) as ctx, capi.Scene(ctx, sd) as sc:
+        film_tail, st_tail = sc.render(rd)
+    monkeypatch.setenv("MSK_TAIL_THRESHOLD", "0")  # read when the context is created
+    with capi.Context(0) as ctx, capi.Scene(ctx, sd) as sc:
+        film_wave, st_wave = sc.render(rd)
+    assert st_tail.tail_rays_closest > 0 and st_wave.tail_rays_closest == 0
+    np.testing.assert_array_equal(film_tail, film_wave)
+    assert (st_tail.rays_closest, st_tail.rays_shadow, st_tail.shaded_vertices) == (st_wave.rays_closest, st_wave.rays_shadow, st_wave.shaded_vertices)
+    assert st_tail.bounces == st_wave.bounces or st_wave.bounces == st_tail.bounces + 1  # the wavefront runs one bounce over an empty queue
+    assert st_tail.kernel_launches < st_wave.kernel_launches
