@@ -441,6 +441,255 @@ __global__ void __launch_bounds__(128, shade_min_blocks(KEY)) k_shade(const __gr
 }
 
 // ---------------------------------------------------------------------------------------
+// Volumetric path tracer: one iteration of VolumetricPathTracer::sample (integrators/volpath.cpp:40-165) per queue
+// entry -- free-flight sampling in the current medium (media/homogeneous.cpp:21-53), then either a medium
+// scattering event (attenuated NEE + isotropic phase sample, phase/isotropic.cpp) or the surface interaction
+// (emitter term, attenuated NEE, BSDF sample, medium transition), then Russian roulette.  The restatement decisions
+// for the stale RGB API are listed above oracle.cpp's volpath_sample and in DESIGN.md; the kernel mirrors the
+// oracle statement by statement, including the order of random draws.
+// Path state beyond the path tracer's: AUX.w carries (medium + 1) | channel << 8 | scattered << 10 | emitted << 11.
+constexpr uint32_t kVolChannelShift = 8, kVolScattered = 1u << 10, kVolEmitted = 1u << 11;
+
+__device__ __forceinline__ float spec_mean(float4 v) { return ((v.x + v.z) + (v.y + v.w)) / 4.f; } // Eigen packet reduction
+__device__ __forceinline__ float tr1(float st, float d) { return st == 0.f ? 1.f : expf(st * (-d)); }
+__device__ __forceinline__ float4 medium_tr(float4 st, float d) { // homogeneous.cpp:48,56-59
+    return make_float4(tr1(st.x, d), tr1(st.y, d), tr1(st.z, d), tr1(st.w, d));
+}
+__device__ __forceinline__ float4 medium_sigma_t(const DScene &sc, int medium, float4 wl, float4 &sigma_s) {
+    const MskMedium m = sc.media[medium];
+    const float4 sa = spectrum_eval(sc, m.sigma_a, wl);
+    sigma_s = spectrum_eval(sc, m.sigma_s, wl);
+    return sigma_s + sa; // homogeneous.cpp:17
+}
+
+// One iteration of VolumetricPathTracer::sample given the hit record of the current ray (shared by k_shade_vol and
+// the per-path tail kernel).
+__device__ __forceinline__ void shade_vertex_vol(const DScene &sc, const BatchParams &bp, bool miss, uint32_t geom, float4 hit, float4 ro,
+                                                 float4 rd, float4 T, float4 wl, uint4 misc, float4 aux, VertexOut &o) {
+    bool emit_ray = false, emit_shadow = false;
+    MskRay nray, sray;
+    float4 nT, nAUX, contrib;
+    uint4 nMISC;
+    uint64_t rng = (uint64_t) misc.x | ((uint64_t) misc.y << 32);
+    const uint32_t path = misc.z;
+    const int depth = (int) (misc.w & 0xffffu);
+    float eta = aux.x;
+    uint32_t bits = __float_as_uint(aux.w);
+    if (depth == 1) { // volpath.cpp:35-39: initial medium = sensor->medium(), emitted_radiance = true, channel draw
+        const uint32_t channel = min((uint32_t) (next1d(rng) * 4.f), 3u);
+        bits = (uint32_t) (sc.sensor_medium + 1) | (channel << kVolChannelShift) | kVolEmitted;
+    }
+    int medium = (int) (bits & 0xffu) - 1;
+    const uint32_t channel = (bits >> kVolChannelShift) & 3u;
+    bool scattered = (bits & kVolScattered) != 0, emitted = (bits & kVolEmitted) != 0;
+    float4 L = f4(0.f);
+    bool add_L = false, alive = true;
+    const V3 rorg = v3(ro.x, ro.y, ro.z), rdir = v3(rd.x, rd.y, rd.z);
+
+    // ---- free flight: medium->sample_distance(ray::spawn(ray, 0, si.t), next1d, channel), volpath.cpp:41-43
+    bool ms_flag = false;
+    float4 sigma_t = f4(0.f), sigma_s = f4(0.f), tr = f4(1.f);
+    float ms_pdf = 1.f;
+    V3 msp = rorg;
+    if (medium >= 0) {
+        const float sample = next1d(rng);
+        sigma_t = medium_sigma_t(sc, medium, wl, sigma_s);
+        const float st_c = channel == 0 ? sigma_t.x : (channel == 1 ? sigma_t.y : (channel == 2 ? sigma_t.z : sigma_t.w));
+        float dist = -logf(1.f - sample) / st_c;
+        if (dist < hit.x) { // ray.maxt - ray.mint with mint = 0, maxt = si.t
+            msp = rorg + rdir * dist;
+            if (msp.x == rorg.x && msp.y == rorg.y && msp.z == rorg.z) ms_pdf = spec_mean(medium_tr(sigma_t, dist));
+            else { ms_pdf = spec_mean(medium_tr(sigma_t, dist) * sigma_t); ms_flag = true; }
+        } else {
+            dist = hit.x;
+            ms_pdf = spec_mean(medium_tr(sigma_t, dist));
+        }
+        tr = medium_tr(sigma_t, dist);
+        if (hmax(tr) < 1e-20f) tr = f4(0.f);
+    }
+
+    if (ms_flag) { // ---- medium scattering event, volpath.cpp:44-74
+        T = T * (sigma_s * tr / ms_pdf);
+        const float sx = next1d(rng), sy = next1d(rng);
+        NeeSample ns = sample_emitter_direct(sc, msp, sx, sy);
+        if (ns.pdf != 0.f) { // scene.cpp:136-138 + isotropic phase value 1 / 4 pi
+            const float4 ln = spectrum_eval(sc, ns.radiance, wl);
+            contrib = T * (nee_value(ns, ln) * medium_tr(sigma_t, ns.dist)) * kInvFourPi;
+            if (!is_zero(contrib)) {
+                emit_shadow = true;
+                sray.o[0] = msp.x; sray.o[1] = msp.y; sray.o[2] = msp.z;
+                sray.tmin = kRayEpsilon * (1.f + max_abs(msp)); // scaled like scene.cpp:91-93 (see oracle.cpp, volpath notes)
+                sray.d[0] = ns.d.x; sray.d[1] = ns.d.y; sray.d[2] = ns.d.z;
+                sray.tmax = ns.dist * (1.f - kShadowEpsilon);
+            }
+        }
+        if (depth + 1 >= bp.max_depth && bp.max_depth > 0) alive = false;
+        else {
+            const float px = next1d(rng), py = next1d(rng);
+            const V3 wo = square_to_uniform_sphere(px, py);
+            emit_ray = true;
+            nray.o[0] = msp.x; nray.o[1] = msp.y; nray.o[2] = msp.z; nray.tmin = kRayEpsilon;
+            nray.d[0] = wo.x; nray.d[1] = wo.y; nray.d[2] = wo.z; nray.tmax = MSK_INF;
+            scattered = true;
+        }
+    } else {       // ---- surface interaction, volpath.cpp:75-155
+        if (medium >= 0) T = T * (tr / ms_pdf);
+        if (miss) { // escaped, :82-93
+            if (emitted && (!bp.hide_emitters || scattered)) {
+                float4 le = f4(0.f);
+                if (sc.environment >= 0) {
+                    int radiance = sc.emitters[sc.environment].radiance;
+                    if (sc.has_textures) radiance = texture_resolve(sc, radiance, 0.f, 0.f);
+                    le = spectrum_eval(sc, radiance, wl);
+                }
+                L = T * le;
+                if (medium >= 0) L = L * medium_tr(sigma_t, rd.w - ro.w); // eval_transmittance(ray): exp(sigma_t (mint - maxt))
+                add_L = true;
+            }
+            alive = false;
+        } else {
+            const DMeshInfo mi = sc.meshes[geom];
+            const Surface sf = make_surface(sc, mi, __float_as_uint(hit.w), hit.y, hit.z);
+            const V3 wi = to_local(sf.sh, -rdir);
+            int id_le = -1;
+            if (mi.emitter >= 0 && emitted && (!bp.hide_emitters || scattered) && wi.z > 0.f) { // :95-98, area.cpp:51-54
+                id_le = sc.emitters[mi.emitter].radiance;
+                if (sc.has_textures) id_le = texture_resolve(sc, id_le, sf.uvx, sf.uvy);
+            }
+            MskBsdf bsdf = sc.bsdfs[mi.bsdf];
+            if (sc.has_textures) bsdf_resolve_textures(sc, bsdf, sf.uvx, sf.uvy);
+            NeeSample ns;
+            ns.pdf = 0.f; ns.radiance = -1;
+            if (bsdf_is_smooth(bsdf.type)) { // :104-115: attenuated NEE, added without the MIS weight
+                const float sx = next1d(rng), sy = next1d(rng);
+                ns = sample_emitter_direct(sc, sf.p, sx, sy);
+            }
+            const bool nee = ns.pdf != 0.f;
+            BsdfSpectra sp;
+            float4 le, ln;
+            eval_vertex_spectra<-1, true>(sc, bsdf, true, id_le, nee ? ns.radiance : -1, wl, sp, le, ln);
+            if (id_le >= 0) { L = T * le; add_L = true; }
+            if (nee) {
+                const V3 wo = to_local(sf.sh, ns.d);
+                float4 bval; float bpdf;
+                bsdf_eval_pdf<-1>(sp, bsdf, wi, wo, bval, bpdf);
+                float4 ev = nee_value(ns, ln);
+                if (medium >= 0) ev = ev * medium_tr(sigma_t, ns.dist);
+                contrib = T * ev * bval;
+                if (!is_zero(contrib)) {
+                    emit_shadow = true;
+                    sray.o[0] = sf.p.x; sray.o[1] = sf.p.y; sray.o[2] = sf.p.z;
+                    sray.tmin = kRayEpsilon * (1.f + max_abs(sf.p));
+                    sray.d[0] = ns.d.x; sray.d[1] = ns.d.y; sray.d[2] = ns.d.z;
+                    sray.tmax = ns.dist * (1.f - kShadowEpsilon);
+                }
+            }
+            const float s1 = next1d(rng), s2x = next1d(rng), s2y = next1d(rng);
+            BsdfSample bs = bsdf_sample<-1>(sp, bsdf, wi, s1, s2x, s2y);
+            if (is_zero(bs.weight)) alive = false; // :122-123
+            else {
+                emitted = false;
+                bool recursive = depth + 1 < bp.max_depth || bp.max_depth < 0;
+                if ((depth < bp.max_depth || bp.max_depth < 0) && (bs.type & BF_Delta)) { emitted = true; recursive = true; } // :129-135
+                if (!recursive) alive = false;
+                else {
+                    const V3 wo = to_world(sf.sh, bs.wo);
+                    T = T * bs.weight;
+                    eta *= bs.eta;
+                    const int interior = (int) ((mi.flags >> 8) & 0xffu) - 1, exterior = (int) ((mi.flags >> 16) & 0xffu) - 1;
+                    if (interior >= 0 || exterior >= 0) medium = dot(wo, sf.n) > 0.f ? exterior : interior; // interaction.cpp:10-13
+                    emit_ray = true;
+                    nray.o[0] = sf.p.x; nray.o[1] = sf.p.y; nray.o[2] = sf.p.z; nray.tmin = (1.f + max_abs(sf.p)) * kRayEpsilon;
+                    nray.d[0] = wo.x; nray.d[1] = wo.y; nray.d[2] = wo.z; nray.tmax = MSK_INF;
+                    scattered = true;
+                }
+            }
+        }
+    }
+    if (alive && emit_ray && depth + 1 >= bp.rr_depth) { // :158-164
+        const float qq = fminf(hmax(T) * eta * eta, 0.95f);
+        if (next1d(rng) >= qq) emit_ray = false;
+        else T = T / qq;
+    }
+    if (bp.max_depth > 0 && depth + 1 > bp.max_depth) emit_ray = false; // loop condition :40
+    if (!alive) emit_ray = false;
+    if (emit_ray) {
+        bits = (uint32_t) (medium + 1) | (channel << kVolChannelShift) | (scattered ? kVolScattered : 0u) | (emitted ? kVolEmitted : 0u);
+        nT = T;
+        nMISC = make_uint4((uint32_t) rng, (uint32_t) (rng >> 32), path, (uint32_t) (depth + 1));
+        nAUX = make_float4(eta, 0.f, 0.f, __uint_as_float(bits));
+    }
+    o.emit_ray = emit_ray; o.emit_shadow = emit_shadow; o.add_L = add_L;
+    o.nray = nray; o.sray = sray; o.nT = nT; o.nAUX = nAUX; o.contrib = contrib; o.L = L; o.nMISC = nMISC;
+}
+
+#ifndef MSK_VOL_MIN_BLOCKS
+#define MSK_VOL_MIN_BLOCKS 4
+#endif
+__global__ void __launch_bounds__(128, MSK_VOL_MIN_BLOCKS) k_shade_vol(const __grid_constant__ DScene sc, Pool pool, BatchParams bp, int cur) {
+    Ctrl *c = pool.ctrl;
+    const int nxt = cur ^ 1;
+    uint32_t counts[kNumKeys], total = 0;
+#pragma unroll
+    for (int k = 0; k < kNumKeys; ++k) { counts[k] = c->type_count[k]; total += counts[k]; }
+    const uint32_t stride = gridDim.x * blockDim.x;
+    const uint32_t rounds = (total + stride - 1) / stride;
+    for (uint32_t it = 0; it < rounds; ++it) {
+        uint32_t idx = it * stride + blockIdx.x * blockDim.x + threadIdx.x;
+        bool valid = idx < total;
+        bool emit_ray = false, emit_shadow = false;
+        MskRay nray, sray;
+        float4 nT, nWL, nAUX, contrib;
+        uint4 nMISC;
+        uint32_t path = 0;
+        if (valid) {
+            uint32_t key = 0, j = idx;
+#pragma unroll
+            for (int k = 0; k < kNumKeys - 1; ++k)
+                if (key == (uint32_t) k && j >= counts[k]) { j -= counts[k]; key = k + 1; }
+            const uint32_t q = pool.sorted[(size_t) key * pool.capacity + j];
+            const float4 hit = pool.hit[q];
+            const float4 ro = reinterpret_cast<const float4 *>(pool.rays[cur] + q)[0];
+            const float4 rd = reinterpret_cast<const float4 *>(pool.rays[cur] + q)[1];
+            float4 T = pool.T[cur][q];
+            const float4 wl = pool.WL[cur][q];
+            const uint4 misc = pool.MISC[cur][q];
+            const float4 aux = pool.AUX[cur][q];
+            path = misc.z;
+            VertexOut vo;
+            shade_vertex_vol(sc, bp, key == 0, key == 0 ? 0xffffffffu : pool.hit_geom[q], hit, ro, rd, T, wl, misc, aux, vo);
+            emit_ray = vo.emit_ray; emit_shadow = vo.emit_shadow;
+            nray = vo.nray; sray = vo.sray; nT = vo.nT; nWL = wl; nAUX = vo.nAUX; contrib = vo.contrib; nMISC = vo.nMISC;
+            if (vo.add_L) { float4 acc = pool.L[path]; pool.L[path] = acc + vo.L; }
+        }
+        uint32_t m_ray = __ballot_sync(0xffffffffu, emit_ray), m_sh = __ballot_sync(0xffffffffu, emit_shadow);
+        uint32_t base_ray = 0, base_sh = 0;
+        if (lane_id() == 0) {
+            if (m_ray) base_ray = atomicAdd(&c->n_rays[nxt], (uint32_t) __popc(m_ray));
+            if (m_sh) base_sh = atomicAdd(&c->n_shadow, (uint32_t) __popc(m_sh));
+        }
+        base_ray = __shfl_sync(0xffffffffu, base_ray, 0);
+        base_sh  = __shfl_sync(0xffffffffu, base_sh, 0);
+        const uint32_t below = (1u << lane_id()) - 1u;
+        if (emit_ray) {
+            uint32_t o = base_ray + __popc(m_ray & below);
+            float4 *rp = reinterpret_cast<float4 *>(pool.rays[nxt] + o);
+            rp[0] = make_float4(nray.o[0], nray.o[1], nray.o[2], nray.tmin);
+            rp[1] = make_float4(nray.d[0], nray.d[1], nray.d[2], nray.tmax);
+            pool.T[nxt][o] = nT; pool.WL[nxt][o] = nWL; pool.MISC[nxt][o] = nMISC; pool.AUX[nxt][o] = nAUX;
+        }
+        if (emit_shadow) {
+            uint32_t o = base_sh + __popc(m_sh & below);
+            float4 *rp = reinterpret_cast<float4 *>(pool.sh_ray + o);
+            rp[0] = make_float4(sray.o[0], sray.o[1], sray.o[2], sray.tmin);
+            rp[1] = make_float4(sray.d[0], sray.d[1], sray.d[2], sray.tmax);
+            pool.sh_contrib[o] = contrib;
+            pool.sh_path[o]    = path;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
 // Tail of an unbounded-depth job.  Once Russian roulette has thinned the queue, a bounce is a handful of
 // latency-bound launches over a few hundred thousand rays: on C2 the 17 bounces after depth 6 carry < 5 % of the
 // rays and took 1.28 ms of the 17.6 ms step (75 us per bounce, profiles/r01g_bounces_c2.txt).  k_tail finishes
@@ -448,7 +697,7 @@ __global__ void __launch_bounds__(128, shade_min_blocks(KEY)) k_shade(const __gr
 // until the path dies, with the same device functions (traverse, shade_vertex) and the same order of additions to
 // L[path] as the wavefront stages, so the film is bit-identical.  Divergence is irrelevant at this size; what
 // matters is that there is no queue traffic, no sort and no launch boundary between the vertices of a path.
-template <bool STATS>
+template <bool STATS, bool VOL>
 __global__ void __launch_bounds__(128) k_tail(const __grid_constant__ DScene sc, Pool pool, BatchParams bp, int cur) {
     Ctrl *c = pool.ctrl;
     const uint32_t n = c->n_rays[cur];
@@ -491,7 +740,8 @@ __global__ void __launch_bounds__(128) k_tail(const __grid_constant__ DScene sc,
             // the hit record exactly as IntersectIO::commit stores it
             const float4 hit = make_float4(found ? h.t : MSK_INF, found ? h.u : 0.f, found ? h.v : 0.f, __uint_as_float(found ? h.prim : 0xffffffffu));
             VertexOut vo;
-            shade_vertex<-1>(sc, bp, !found, found ? h.geom : 0xffffffffu, hit, rd, T, wl, misc, aux, vo);
+            if (VOL) shade_vertex_vol(sc, bp, !found, found ? h.geom : 0xffffffffu, hit, ro, rd, T, wl, misc, aux, vo);
+            else shade_vertex<-1>(sc, bp, !found, found ? h.geom : 0xffffffffu, hit, rd, T, wl, misc, aux, vo);
             if (vo.add_L) L = L + vo.L;
             if (vo.emit_shadow) { // k_shadow: unoccluded => L += contribution
                 RayHit sh;
@@ -528,239 +778,6 @@ __global__ void __launch_bounds__(128) k_tail(const __grid_constant__ DScene sc,
 __global__ void k_end_tail(Ctrl *c, int cur) {
     c->n_rays[cur] = 0; c->n_rays[cur ^ 1] = 0; c->n_shadow = 0; c->cursor_isect = 0; c->cursor_shadow = 0;
     for (int i = 0; i < kNumKeys; ++i) c->type_count[i] = 0;
-}
-
-// ---------------------------------------------------------------------------------------
-// Volumetric path tracer: one iteration of VolumetricPathTracer::sample (integrators/volpath.cpp:40-165) per queue
-// entry -- free-flight sampling in the current medium (media/homogeneous.cpp:21-53), then either a medium
-// scattering event (attenuated NEE + isotropic phase sample, phase/isotropic.cpp) or the surface interaction
-// (emitter term, attenuated NEE, BSDF sample, medium transition), then Russian roulette.  The restatement decisions
-// for the stale RGB API are listed above oracle.cpp's volpath_sample and in DESIGN.md; the kernel mirrors the
-// oracle statement by statement, including the order of random draws.
-// Path state beyond the path tracer's: AUX.w carries (medium + 1) | channel << 8 | scattered << 10 | emitted << 11.
-constexpr uint32_t kVolChannelShift = 8, kVolScattered = 1u << 10, kVolEmitted = 1u << 11;
-
-__device__ __forceinline__ float spec_mean(float4 v) { return ((v.x + v.z) + (v.y + v.w)) / 4.f; } // Eigen packet reduction
-__device__ __forceinline__ float tr1(float st, float d) { return st == 0.f ? 1.f : expf(st * (-d)); }
-__device__ __forceinline__ float4 medium_tr(float4 st, float d) { // homogeneous.cpp:48,56-59
-    return make_float4(tr1(st.x, d), tr1(st.y, d), tr1(st.z, d), tr1(st.w, d));
-}
-__device__ __forceinline__ float4 medium_sigma_t(const DScene &sc, int medium, float4 wl, float4 &sigma_s) {
-    const MskMedium m = sc.media[medium];
-    const float4 sa = spectrum_eval(sc, m.sigma_a, wl);
-    sigma_s = spectrum_eval(sc, m.sigma_s, wl);
-    return sigma_s + sa; // homogeneous.cpp:17
-}
-
-#ifndef MSK_VOL_MIN_BLOCKS
-#define MSK_VOL_MIN_BLOCKS 4
-#endif
-__global__ void __launch_bounds__(128, MSK_VOL_MIN_BLOCKS) k_shade_vol(const __grid_constant__ DScene sc, Pool pool, BatchParams bp, int cur) {
-    Ctrl *c = pool.ctrl;
-    const int nxt = cur ^ 1;
-    uint32_t counts[kNumKeys], total = 0;
-#pragma unroll
-    for (int k = 0; k < kNumKeys; ++k) { counts[k] = c->type_count[k]; total += counts[k]; }
-    const uint32_t stride = gridDim.x * blockDim.x;
-    const uint32_t rounds = (total + stride - 1) / stride;
-    for (uint32_t it = 0; it < rounds; ++it) {
-        uint32_t idx = it * stride + blockIdx.x * blockDim.x + threadIdx.x;
-        bool valid = idx < total;
-        bool emit_ray = false, emit_shadow = false;
-        MskRay nray, sray;
-        float4 nT, nWL, nAUX, contrib;
-        uint4 nMISC;
-        uint32_t path = 0;
-        if (valid) {
-            uint32_t key = 0, j = idx;
-#pragma unroll
-            for (int k = 0; k < kNumKeys - 1; ++k)
-                if (key == (uint32_t) k && j >= counts[k]) { j -= counts[k]; key = k + 1; }
-            const uint32_t q = pool.sorted[(size_t) key * pool.capacity + j];
-            const float4 hit = pool.hit[q];
-            const float4 ro = reinterpret_cast<const float4 *>(pool.rays[cur] + q)[0];
-            const float4 rd = reinterpret_cast<const float4 *>(pool.rays[cur] + q)[1];
-            float4 T = pool.T[cur][q];
-            const float4 wl = pool.WL[cur][q];
-            const uint4 misc = pool.MISC[cur][q];
-            const float4 aux = pool.AUX[cur][q];
-            uint64_t rng = (uint64_t) misc.x | ((uint64_t) misc.y << 32);
-            path = misc.z;
-            const int depth = (int) (misc.w & 0xffffu);
-            float eta = aux.x;
-            uint32_t bits = __float_as_uint(aux.w);
-            if (depth == 1) { // volpath.cpp:35-39: initial medium = sensor->medium(), emitted_radiance = true, channel draw
-                const uint32_t channel = min((uint32_t) (next1d(rng) * 4.f), 3u);
-                bits = (uint32_t) (sc.sensor_medium + 1) | (channel << kVolChannelShift) | kVolEmitted;
-            }
-            int medium = (int) (bits & 0xffu) - 1;
-            const uint32_t channel = (bits >> kVolChannelShift) & 3u;
-            bool scattered = (bits & kVolScattered) != 0, emitted = (bits & kVolEmitted) != 0;
-            float4 L = f4(0.f);
-            bool add_L = false, alive = true;
-            const V3 rorg = v3(ro.x, ro.y, ro.z), rdir = v3(rd.x, rd.y, rd.z);
-
-            // ---- free flight: medium->sample_distance(ray::spawn(ray, 0, si.t), next1d, channel), volpath.cpp:41-43
-            bool ms_flag = false;
-            float4 sigma_t = f4(0.f), sigma_s = f4(0.f), tr = f4(1.f);
-            float ms_pdf = 1.f;
-            V3 msp = rorg;
-            if (medium >= 0) {
-                const float sample = next1d(rng);
-                sigma_t = medium_sigma_t(sc, medium, wl, sigma_s);
-                const float st_c = channel == 0 ? sigma_t.x : (channel == 1 ? sigma_t.y : (channel == 2 ? sigma_t.z : sigma_t.w));
-                float dist = -logf(1.f - sample) / st_c;
-                if (dist < hit.x) { // ray.maxt - ray.mint with mint = 0, maxt = si.t
-                    msp = rorg + rdir * dist;
-                    if (msp.x == rorg.x && msp.y == rorg.y && msp.z == rorg.z) ms_pdf = spec_mean(medium_tr(sigma_t, dist));
-                    else { ms_pdf = spec_mean(medium_tr(sigma_t, dist) * sigma_t); ms_flag = true; }
-                } else {
-                    dist = hit.x;
-                    ms_pdf = spec_mean(medium_tr(sigma_t, dist));
-                }
-                tr = medium_tr(sigma_t, dist);
-                if (hmax(tr) < 1e-20f) tr = f4(0.f);
-            }
-
-            if (ms_flag) { // ---- medium scattering event, volpath.cpp:44-74
-                T = T * (sigma_s * tr / ms_pdf);
-                const float sx = next1d(rng), sy = next1d(rng);
-                NeeSample ns = sample_emitter_direct(sc, msp, sx, sy);
-                if (ns.pdf != 0.f) { // scene.cpp:136-138 + isotropic phase value 1 / 4 pi
-                    const float4 ln = spectrum_eval(sc, ns.radiance, wl);
-                    contrib = T * (nee_value(ns, ln) * medium_tr(sigma_t, ns.dist)) * kInvFourPi;
-                    if (!is_zero(contrib)) {
-                        emit_shadow = true;
-                        sray.o[0] = msp.x; sray.o[1] = msp.y; sray.o[2] = msp.z;
-                        sray.tmin = kRayEpsilon * (1.f + max_abs(msp)); // scaled like scene.cpp:91-93 (see oracle.cpp, volpath notes)
-                        sray.d[0] = ns.d.x; sray.d[1] = ns.d.y; sray.d[2] = ns.d.z;
-                        sray.tmax = ns.dist * (1.f - kShadowEpsilon);
-                    }
-                }
-                if (depth + 1 >= bp.max_depth && bp.max_depth > 0) alive = false;
-                else {
-                    const float px = next1d(rng), py = next1d(rng);
-                    const V3 wo = square_to_uniform_sphere(px, py);
-                    emit_ray = true;
-                    nray.o[0] = msp.x; nray.o[1] = msp.y; nray.o[2] = msp.z; nray.tmin = kRayEpsilon;
-                    nray.d[0] = wo.x; nray.d[1] = wo.y; nray.d[2] = wo.z; nray.tmax = MSK_INF;
-                    scattered = true;
-                }
-            } else {       // ---- surface interaction, volpath.cpp:75-155
-                if (medium >= 0) T = T * (tr / ms_pdf);
-                if (key == 0) { // escaped, :82-93
-                    if (emitted && (!bp.hide_emitters || scattered)) {
-                        float4 le = f4(0.f);
-                        if (sc.environment >= 0) {
-                            int radiance = sc.emitters[sc.environment].radiance;
-                            if (sc.has_textures) radiance = texture_resolve(sc, radiance, 0.f, 0.f);
-                            le = spectrum_eval(sc, radiance, wl);
-                        }
-                        L = T * le;
-                        if (medium >= 0) L = L * medium_tr(sigma_t, rd.w - ro.w); // eval_transmittance(ray): exp(sigma_t (mint - maxt))
-                        add_L = true;
-                    }
-                    alive = false;
-                } else {
-                    const uint32_t geom = pool.hit_geom[q];
-                    const DMeshInfo mi = sc.meshes[geom];
-                    const Surface sf = make_surface(sc, mi, __float_as_uint(hit.w), hit.y, hit.z);
-                    const V3 wi = to_local(sf.sh, -rdir);
-                    int id_le = -1;
-                    if (mi.emitter >= 0 && emitted && (!bp.hide_emitters || scattered) && wi.z > 0.f) { // :95-98, area.cpp:51-54
-                        id_le = sc.emitters[mi.emitter].radiance;
-                        if (sc.has_textures) id_le = texture_resolve(sc, id_le, sf.uvx, sf.uvy);
-                    }
-                    MskBsdf bsdf = sc.bsdfs[mi.bsdf];
-                    if (sc.has_textures) bsdf_resolve_textures(sc, bsdf, sf.uvx, sf.uvy);
-                    NeeSample ns;
-                    ns.pdf = 0.f; ns.radiance = -1;
-                    if (bsdf_is_smooth(bsdf.type)) { // :104-115: attenuated NEE, added without the MIS weight
-                        const float sx = next1d(rng), sy = next1d(rng);
-                        ns = sample_emitter_direct(sc, sf.p, sx, sy);
-                    }
-                    const bool nee = ns.pdf != 0.f;
-                    BsdfSpectra sp;
-                    float4 le, ln;
-                    eval_vertex_spectra<-1, true>(sc, bsdf, true, id_le, nee ? ns.radiance : -1, wl, sp, le, ln);
-                    if (id_le >= 0) { L = T * le; add_L = true; }
-                    if (nee) {
-                        const V3 wo = to_local(sf.sh, ns.d);
-                        float4 bval; float bpdf;
-                        bsdf_eval_pdf<-1>(sp, bsdf, wi, wo, bval, bpdf);
-                        float4 ev = nee_value(ns, ln);
-                        if (medium >= 0) ev = ev * medium_tr(sigma_t, ns.dist);
-                        contrib = T * ev * bval;
-                        if (!is_zero(contrib)) {
-                            emit_shadow = true;
-                            sray.o[0] = sf.p.x; sray.o[1] = sf.p.y; sray.o[2] = sf.p.z;
-                            sray.tmin = kRayEpsilon * (1.f + max_abs(sf.p));
-                            sray.d[0] = ns.d.x; sray.d[1] = ns.d.y; sray.d[2] = ns.d.z;
-                            sray.tmax = ns.dist * (1.f - kShadowEpsilon);
-                        }
-                    }
-                    const float s1 = next1d(rng), s2x = next1d(rng), s2y = next1d(rng);
-                    BsdfSample bs = bsdf_sample<-1>(sp, bsdf, wi, s1, s2x, s2y);
-                    if (is_zero(bs.weight)) alive = false; // :122-123
-                    else {
-                        emitted = false;
-                        bool recursive = depth + 1 < bp.max_depth || bp.max_depth < 0;
-                        if ((depth < bp.max_depth || bp.max_depth < 0) && (bs.type & BF_Delta)) { emitted = true; recursive = true; } // :129-135
-                        if (!recursive) alive = false;
-                        else {
-                            const V3 wo = to_world(sf.sh, bs.wo);
-                            T = T * bs.weight;
-                            eta *= bs.eta;
-                            const int interior = (int) ((mi.flags >> 8) & 0xffu) - 1, exterior = (int) ((mi.flags >> 16) & 0xffu) - 1;
-                            if (interior >= 0 || exterior >= 0) medium = dot(wo, sf.n) > 0.f ? exterior : interior; // interaction.cpp:10-13
-                            emit_ray = true;
-                            nray.o[0] = sf.p.x; nray.o[1] = sf.p.y; nray.o[2] = sf.p.z; nray.tmin = (1.f + max_abs(sf.p)) * kRayEpsilon;
-                            nray.d[0] = wo.x; nray.d[1] = wo.y; nray.d[2] = wo.z; nray.tmax = MSK_INF;
-                            scattered = true;
-                        }
-                    }
-                }
-            }
-            if (alive && emit_ray && depth + 1 >= bp.rr_depth) { // :158-164
-                const float qq = fminf(hmax(T) * eta * eta, 0.95f);
-                if (next1d(rng) >= qq) emit_ray = false;
-                else T = T / qq;
-            }
-            if (bp.max_depth > 0 && depth + 1 > bp.max_depth) emit_ray = false; // loop condition :40
-            if (!alive) emit_ray = false;
-            if (emit_ray) {
-                bits = (uint32_t) (medium + 1) | (channel << kVolChannelShift) | (scattered ? kVolScattered : 0u) | (emitted ? kVolEmitted : 0u);
-                nT = T; nWL = wl;
-                nMISC = make_uint4((uint32_t) rng, (uint32_t) (rng >> 32), path, (uint32_t) (depth + 1));
-                nAUX = make_float4(eta, 0.f, 0.f, __uint_as_float(bits));
-            }
-            if (add_L) { float4 acc = pool.L[path]; pool.L[path] = acc + L; }
-        }
-        uint32_t m_ray = __ballot_sync(0xffffffffu, emit_ray), m_sh = __ballot_sync(0xffffffffu, emit_shadow);
-        uint32_t base_ray = 0, base_sh = 0;
-        if (lane_id() == 0) {
-            if (m_ray) base_ray = atomicAdd(&c->n_rays[nxt], (uint32_t) __popc(m_ray));
-            if (m_sh) base_sh = atomicAdd(&c->n_shadow, (uint32_t) __popc(m_sh));
-        }
-        base_ray = __shfl_sync(0xffffffffu, base_ray, 0);
-        base_sh  = __shfl_sync(0xffffffffu, base_sh, 0);
-        const uint32_t below = (1u << lane_id()) - 1u;
-        if (emit_ray) {
-            uint32_t o = base_ray + __popc(m_ray & below);
-            float4 *rp = reinterpret_cast<float4 *>(pool.rays[nxt] + o);
-            rp[0] = make_float4(nray.o[0], nray.o[1], nray.o[2], nray.tmin);
-            rp[1] = make_float4(nray.d[0], nray.d[1], nray.d[2], nray.tmax);
-            pool.T[nxt][o] = nT; pool.WL[nxt][o] = nWL; pool.MISC[nxt][o] = nMISC; pool.AUX[nxt][o] = nAUX;
-        }
-        if (emit_shadow) {
-            uint32_t o = base_sh + __popc(m_sh & below);
-            float4 *rp = reinterpret_cast<float4 *>(pool.sh_ray + o);
-            rp[0] = make_float4(sray.o[0], sray.o[1], sray.o[2], sray.tmin);
-            rp[1] = make_float4(sray.d[0], sray.d[1], sray.d[2], sray.tmax);
-            pool.sh_contrib[o] = contrib;
-            pool.sh_path[o]    = path;
-        }
-    }
 }
 
 // ---------------------------------------------------------------------------------------
@@ -1241,7 +1258,7 @@ int Renderer::render(cudaStream_t stream, const DScene &sc, const MskRenderDesc 
         }
         // (not with MSK_RENDER_TRAVERSAL_STATS: the per-stage node / triangle counters then describe the wavefront kernels alone)
         const bool poll = bound >= (uint32_t) im.poll_min_depth; // unbounded jobs, and bounded ones deep enough to have a thin tail
-        const bool use_tail = im.tail_threshold > 0 && rd.integrator == MSK_INTEGRATOR_PATH && poll && !tstats;
+        const bool use_tail = im.tail_threshold > 0 && poll && !tstats;
         uint32_t n_est = n;       // upper bound of the current queue length known to the host (queues only shrink)
         bool poll_pending = false; // a poll of the previous bounce is in flight (async_poll)
         while (bounce < bound) {
@@ -1291,7 +1308,8 @@ int Renderer::render(cudaStream_t stream, const DScene &sc, const MskRenderDesc 
                 // queues only shrink: once the last polled length is below the threshold, one k_tail launch runs
                 // every surviving path of the current queue to completion instead of ~5 launches per further bounce
                 if (use_tail && n_est <= im.tail_threshold) {
-                    MSK_STAGE(ST_TAIL, (k_tail<false><<<pb, 128, 0, stream>>>(sc, pool, bp, cur)));
+                    if (rd.integrator == MSK_INTEGRATOR_VOLPATH) MSK_STAGE(ST_TAIL, (k_tail<false, true><<<pb, 128, 0, stream>>>(sc, pool, bp, cur)));
+                    else MSK_STAGE(ST_TAIL, (k_tail<false, false><<<pb, 128, 0, stream>>>(sc, pool, bp, cur)));
                     k_end_tail<<<1, 1, 0, stream>>>(pool.ctrl, cur);
                     launches++;
                     tail_used = true;

@@ -296,12 +296,13 @@ def test_render_scene_without_geometry(gpu_ctx):
         assert (rgba[..., :3].max() > 0) == (env is not None)
 
 
-def test_tail_kernel_is_bit_identical(monkeypatch):
+@pytest.mark.parametrize("integrator", ["path", "volpath"])
+def test_tail_kernel_is_bit_identical(monkeypatch, integrator):
     """Unbounded-depth jobs finish with k_tail (one per-path launch) once the queue is short.  It runs the same device
     functions in the same order as the wavefront stages, so the film must not change by a single bit, and the ray
     counts must agree."""
-    sd = scenes.bunny(96, 96, n=16)
-    rd = capi.render_desc(spp=8, max_depth=-1, rr_depth=3)
+    sd = scenes.bunny(96, 96, n=16) if integrator == "path" else scenes.fog(96, 96)
+    rd = capi.render_desc(spp=8, max_depth=-1, rr_depth=3, integrator=integrator)
     with capi.Context(0) as ctx, capi.Scene(ctx, sd) as sc:
         film_tail, st_tail = sc.render(rd)
     monkeypatch.setenv("MSK_TAIL_THRESHOLD", "0")  # read when the context is created
