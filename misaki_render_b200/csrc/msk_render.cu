@@ -82,7 +82,26 @@ struct BatchParams {
     uint32_t spp;          // of the whole job (seeding)
     uint64_t base_seed;
     int32_t  max_depth, rr_depth, hide_emitters;
+    uint32_t tiled;        // path slots enumerate the pixels of a sample in 8x4 tiles (film size a multiple of 8x4)
 };
+
+// Path slot p of a sample (0 <= p < npix) -> linear pixel index.  With `tiled`, 32 consecutive slots -- one warp of
+// k_raygen, of the static traversal and of the first shade pass -- cover an 8x4 pixel tile instead of a 32x1 strip, so
+// the camera rays of a warp visit the same nodes and their hit points share material and shadow-ray direction.
+// Only the enumeration order of the paths changes: seeds depend on (pixel, sample) and the film records are written
+// per pixel, so the film is bit-identical.
+__device__ __forceinline__ uint32_t slot_to_pixel(const BatchParams &bp, uint32_t p) {
+    if (!bp.tiled) return p;
+    const uint32_t tiles_x = bp.width >> 3, l = p & 31u;
+    uint32_t t = p >> 5, tx, ty;
+    if (bp.tiled == 2u) { // the four warps of a 128-thread block cover a 16x8 block of pixels (2x2 tiles)
+        const uint32_t groups_x = tiles_x >> 1, g = t >> 2, k = t & 3u;
+        tx = (g % groups_x) * 2u + (k & 1u); ty = (g / groups_x) * 2u + (k >> 1);
+    } else {
+        tx = t % tiles_x; ty = t / tiles_x;
+    }
+    return (ty * 4u + (l >> 3)) * bp.width + tx * 8u + (l & 7u);
+}
 
 constexpr uint32_t kFlagDelta = 1u << 16;
 
@@ -109,7 +128,7 @@ __global__ void __launch_bounds__(256) k_raygen(const __grid_constant__ DScene s
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     uint32_t n = bp.npix * bp.ns;
     if (i >= n) return;
-    uint32_t pixel = i % bp.npix, s = bp.s0 + i / bp.npix;
+    uint32_t pixel = slot_to_pixel(bp, i % bp.npix), s = bp.s0 + i / bp.npix;
     uint32_t gx = pixel % bp.width, gy = pixel / bp.width;
     uint64_t rng = pcg_seed((uint64_t) pixel * bp.spp + s + bp.base_seed);
     float jx = next1d(rng), jy = next1d(rng);
@@ -816,8 +835,9 @@ __global__ void __launch_bounds__(256) k_film_records(const __grid_constant__ DS
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     uint32_t n = bp.npix * bp.ns;
     if (i >= n) return;
-    uint32_t pixel = i % bp.npix, s = bp.s0 + i / bp.npix;
+    uint32_t pixel = slot_to_pixel(bp, i % bp.npix), s = bp.s0 + i / bp.npix;
     uint32_t gx = pixel % bp.width, gy = pixel / bp.width;
+    const uint32_t r = (i / bp.npix) * bp.npix + pixel; // record index: the film gathers read records by pixel
     uint64_t rng = pcg_seed((uint64_t) pixel * bp.spp + s + bp.base_seed);
     float jx = next1d(rng), jy = next1d(rng);
     float wav = next1d(rng);
@@ -827,12 +847,12 @@ __global__ void __launch_bounds__(256) k_film_records(const __grid_constant__ DS
     float4 result = spec * weight;
     float X, Y, Z;
     spectrum_to_xyz(sc, result, wl, X, Y, Z);
-    pool.rec[i]    = make_float4(X, Y, Z, (float) gx + jx);
-    pool.rec_py[i] = (float) gy + jy;
+    pool.rec[r]    = make_float4(X, Y, Z, (float) gx + jx);
+    pool.rec_py[r] = (float) gy + jy;
     if (rgba_channel >= 0) { // aov.cpp:124-140: xyz_to_srgb(spectrum_to_xyz(spec)) of the nested integrator, before ray_weight
         float x, y, z;
         spectrum_to_xyz(sc, spec, wl, x, y, z);
-        float *a = pool.aov + (size_t) rgba_channel * pool.capacity + i;
+        float *a = pool.aov + (size_t) rgba_channel * pool.capacity + r;
         a[0]                         = 3.240479f * x + -1.537150f * y + -0.498535f * z;
         a[pool.capacity]             = -0.969256f * x + 1.875991f * y + 0.041556f * z;
         a[2 * (size_t) pool.capacity] = 0.055648f * x + -0.204043f * y + 1.057311f * z;
@@ -852,7 +872,7 @@ __global__ void __launch_bounds__(256) k_aov_capture(const __grid_constant__ DSc
     sf.p = v3(0, 0, 0); sf.n = v3(0, 0, 0); sf.sh.n = v3(0, 0, 0); sf.uvx = 0.f; sf.uvy = 0.f;
     const bool valid = geom != 0xffffffffu;
     if (valid) sf = make_surface(sc, sc.meshes[geom], __float_as_uint(hit.w), hit.y, hit.z);
-    float *a = pool.aov + i;
+    float *a = pool.aov + (i / bp.npix) * bp.npix + slot_to_pixel(bp, i % bp.npix); // by record index, like k_film_records
     const size_t cs = pool.capacity;
     uint32_t c = 0;
     for (uint32_t k = 0; k < plan.ntypes; ++k) {
@@ -1077,6 +1097,7 @@ struct Renderer::Impl {
     int shadow_static_bounces = 0;    // MSK_SHADOW_STATIC_BOUNCES: bounces whose shadow queue counts as coherent
     int debug_bounces = 0;            // MSK_DEBUG_BOUNCES: print polled queue lengths and per-launch stage times to stderr
     uint32_t tail_threshold = 1u << 18; // MSK_TAIL_THRESHOLD: finish an unbounded job with k_tail once the queue is this short (0: never)
+    int tiled_slots = 1;              // MSK_TILED_SLOTS: enumerate the pixels of a sample in 8x4 tiles (see slot_to_pixel)
     int poll_min_depth = 8;           // MSK_POLL_MIN_DEPTH: jobs with max_depth >= this (or unbounded) poll the queue length from bounce 4 on
     int async_poll = 1;               // MSK_ASYNC_POLL: poll the queue length one bounce late, without draining the stream
     std::vector<cudaEvent_t> timer_events; // MSK_RENDER_STAGE_TIMERS
@@ -1123,6 +1144,7 @@ int Renderer::init(int sm_count) {
     impl_->async_poll = (int) env_u("MSK_ASYNC_POLL", impl_->async_poll);
     impl_->tail_threshold = (uint32_t) env_u("MSK_TAIL_THRESHOLD", impl_->tail_threshold);
     impl_->poll_min_depth = (int) env_u("MSK_POLL_MIN_DEPTH", impl_->poll_min_depth);
+    impl_->tiled_slots = (int) env_u("MSK_TILED_SLOTS", impl_->tiled_slots);
     impl_->debug_bounces = (int) env_u("MSK_DEBUG_BOUNCES", 0);
     return MSK_OK;
 }
@@ -1242,6 +1264,8 @@ int Renderer::render(cudaStream_t stream, const DScene &sc, const MskRenderDesc 
         bp.npix = npix; bp.width = W; bp.s0 = s0; bp.ns = std::min(per_batch, rd.sample_end - s0);
         bp.spp = rd.spp; bp.base_seed = rd.base_seed;
         bp.max_depth = rd.max_depth; bp.rr_depth = rd.rr_depth; bp.hide_emitters = rd.hide_emitters;
+        bp.tiled = (im.tiled_slots && W % 8u == 0 && H % 4u == 0) ? 1u : 0u;
+        if (bp.tiled && im.tiled_slots >= 2 && W % 16u == 0 && H % 8u == 0) bp.tiled = 2u;
         const uint32_t n = npix * bp.ns;
         k_begin_batch<<<1, 1, 0, stream>>>(pool.ctrl, n);
         launches++;

@@ -313,3 +313,21 @@ def test_tail_kernel_is_bit_identical(monkeypatch, integrator):
     assert (st_tail.rays_closest, st_tail.rays_shadow, st_tail.shaded_vertices) == (st_wave.rays_closest, st_wave.rays_shadow, st_wave.shaded_vertices)
     assert st_tail.bounces == st_wave.bounces or st_wave.bounces == st_tail.bounces + 1  # the wavefront runs one bounce over an empty queue
     assert st_tail.kernel_launches < st_wave.kernel_launches
+
+
+def test_tiled_path_enumeration_is_bit_identical(monkeypatch):
+    """Path slots enumerate the pixels of a sample in 8x4 tiles when the film size allows (coherent warps of camera
+    rays); seeds depend on (pixel, sample) and the film records stay per pixel, so nothing in the film may change --
+    including the AOV channels, which are captured per path slot."""
+    sd = scenes.cbox(64, 48)
+    rd = capi.render_desc(spp=4, max_depth=4)
+    types = [capi.AOV_DEPTH, capi.AOV_UV, capi.AOV_INTEGRATOR_RGBA]
+    with capi.Context(0) as ctx, capi.Scene(ctx, sd) as sc:
+        film_t, _ = sc.render(rd)
+        aov_t, _ = sc.render_aov(rd, types)
+    monkeypatch.setenv("MSK_TILED_SLOTS", "0")
+    with capi.Context(0) as ctx, capi.Scene(ctx, sd) as sc:
+        film_l, _ = sc.render(rd)
+        aov_l, _ = sc.render_aov(rd, types)
+    np.testing.assert_array_equal(film_t, film_l)
+    np.testing.assert_array_equal(aov_t, aov_l)
