@@ -82,6 +82,47 @@ def test_the_references_own_scene_file_loads_unchanged():
             np.testing.assert_array_equal(a["verts"], b["verts"])
 
 
+REFERENCE_TEAPOT = Path("/root/reference/assets/teapot-full/scene.xml")
+
+
+@pytest.mark.skipif(not REFERENCE_TEAPOT.exists(), reason="the reference tree only exists in the build container")
+def test_the_references_teapot_scene_loads_unchanged(tmp_path):
+    """assets/teapot-full/scene.xml uses every row of SURVEY 8f: the `volpath` integrator, a `twosided` diffuse floor
+    with a `checkerboard` reflectance and a `to_uv` scale, smooth `dielectric` shells, `homogeneous` media named
+    interior / exterior, a `<boolean>` property and a `constant` emitter with a defaulted radiance.  Its meshes are not
+    in the reference repository, so stand-ins with the same file names are served from the search path."""
+    models = tmp_path / "models"
+    models.mkdir()
+    (models / "rectangle.obj").write_text("v -1 -1 0\nv 1 -1 0\nv 1 1 0\nv -1 1 0\nvt 0 0\nvt 1 0\nvt 1 1\nvt 0 1\nvn 0 0 1\n"
+                                          "f 1/1/1 2/2/1 3/3/1 4/4/1\n")
+    cube = ("v 0 0 0\nv 1 0 0\nv 1 1 0\nv 0 1 0\nv 0 0 1\nv 1 0 1\nv 1 1 1\nv 0 1 1\n"
+            "f 1 4 3 2\nf 5 6 7 8\nf 1 2 6 5\nf 2 3 7 6\nf 3 4 8 7\nf 4 1 5 8\n")
+    for k in range(4):
+        (models / f"Mesh00{k}.obj").write_text(cube)
+    host_api.load().mskh_add_search_path(str(tmp_path).encode())
+    with host_api.HostScene(REFERENCE_TEAPOT) as hs:
+        d, rd, meshes = hs.desc(), hs.render_desc(), hs.meshes()
+        assert (rd.integrator, rd.spp, rd.max_depth, rd.rr_depth) == (capi.INTEGRATOR_VOLPATH, 128, -1, 5)
+        assert (d.camera.width, d.camera.height, d.nmeshes, d.nemitters) == (1280, 720, 5, 1)
+        assert d.environment == 0 and d.emitters[0].type == capi.EMITTER_CONSTANT
+        floor = d.bsdfs[meshes[0]["bsdf"]]
+        assert floor.type == capi.BSDF_DIFFUSE and floor.twosided == 1
+        tex = d.spectra[floor.reflectance]
+        assert tex.kind == capi.SPEC_CHECKERBOARD
+        np.testing.assert_array_equal(tex.to_uv[:], [10, 0, 0, 0, 10, 0])
+        np.testing.assert_array_equal(np.array(d.spectra[tex.child0].c[:], np.float32), rgb2spec_model().fetch((0.725, 0.71, 0.68)))
+        np.testing.assert_array_equal(np.array(d.spectra[tex.child1].c[:], np.float32), rgb2spec_model().fetch((0.325, 0.31, 0.25)))
+        iors = [round(d.bsdfs[m["bsdf"]].int_ior, 2) for m in meshes[1:]]
+        assert [d.bsdfs[m["bsdf"]].type for m in meshes[1:]] == [capi.BSDF_DIELECTRIC] * 4 and iors == [1.5, 1.5, 1.33, 1.13]
+        assert d.nmedia == 2 and d.sensor_medium == -1
+        media = [(d.meshes[i].interior_medium, d.meshes[i].exterior_medium) for i in range(5)]
+        assert media[:3] == [(-1, -1)] * 3 and media[3][0] >= 0 and media[3][1] == -1 and media[4][0] == -1 and media[4][1] >= 0
+        sp = _spectra(d)
+        for m in (d.media[0], d.media[1]):
+            assert sp[m.sigma_s][0] == capi.SPEC_SRGB_UNBOUNDED and sp[m.sigma_s][2] == 0.0      # sigma_s = 0: absorbing only
+            assert sp[m.sigma_a][0] == capi.SPEC_SRGB_UNBOUNDED and abs(sp[m.sigma_a][2] - 2 * 0.736) < 1e-6
+
+
 def test_children_are_ordered_like_std_map_keys():
     """Unnamed children are _arg_0, _arg_1, ... and Properties::objects() walks a std::map, so the 11th and 12th
     child come before the 3rd (properties.cpp:166-176): this is the geomID order Embree saw."""
