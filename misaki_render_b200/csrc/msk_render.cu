@@ -978,8 +978,10 @@ constexpr int kFilmHaloX = kFilmTileX + 2 * kFilmMaxBorder, kFilmHaloY = kFilmTi
 __global__ void __launch_bounds__(kFilmTileX *kFilmTileY) k_film_gather_tiled(const __grid_constant__ DScene sc, Pool pool,
                                                                                BatchParams bp, float *__restrict__ film,
                                                                                uint32_t height, uint32_t stride) {
-    __shared__ float4 s_a[kFilmHaloY][kFilmHaloX]; // X, Y, Z, posx (block-relative, imageblock.cpp:86-98)
-    __shared__ float4 s_b[kFilmHaloY][kFilmHaloX]; // posy, (float) bx, (float) by, valid
+    // per halo cell: X, Y, Z, posx | posy (positions block-relative, imageblock.cpp:86-98).  20 bytes per candidate
+    // instead of the 32 of the first version (which also kept the block origin): the loop is shared-memory bound
+    __shared__ float4 s_a[kFilmHaloY][kFilmHaloX];
+    __shared__ float s_py[kFilmHaloY][kFilmHaloX];
     __shared__ float s_tab[33];
     const int W = (int) bp.width, H = (int) height;
     const int x0 = blockIdx.x * kFilmTileX, y0 = blockIdx.y * kFilmTileY;
@@ -992,6 +994,17 @@ __global__ void __launch_bounds__(kFilmTileX *kFilmTileY) k_film_gather_tiled(co
     // this thread's neighbour window in halo coordinates (clipped to the film like the reference's lo/hi clamp)
     const int hx_lo = max(x - r, 0) - (x0 - kFilmMaxBorder), hx_hi = min(x + r, W - 1) - (x0 - kFilmMaxBorder);
     const int hy_lo = max(y - r, 0) - (y0 - kFilmMaxBorder), hy_hi = min(y + r, H - 1) - (y0 - kFilmMaxBorder);
+    // this pixel's coordinate relative to the block of each neighbour column / row (m_offset - m_border_size of the
+    // 32x32 block that neighbour belongs to): small integers, exact in float, independent of the sample
+    constexpr int kWin = 2 * kFilmMaxBorder + 1;
+    const int hx_first = (int) threadIdx.x, hy_first = (int) threadIdx.y; // halo coordinate of (x - kFilmMaxBorder, y - kFilmMaxBorder)
+    float xb[kWin], yb[kWin];
+#pragma unroll
+    for (int d = 0; d < kWin; ++d) {
+        const int nx = x - kFilmMaxBorder + d, ny = y - kFilmMaxBorder + d;
+        xb[d] = (float) (x - ((nx & ~(kBlockSize - 1)) - r));
+        yb[d] = (float) (y - ((ny & ~(kBlockSize - 1)) - r));
+    }
     float aX = 0.f, aY = 0.f, aZ = 0.f, aW = 0.f;
     for (uint32_t s = 0; s < bp.ns; ++s) {
         const size_t sbase = (size_t) s * bp.npix;
@@ -1005,22 +1018,30 @@ __global__ void __launch_bounds__(kFilmTileX *kFilmTileY) k_film_gather_tiled(co
                 const float py = __ldcs(pool.rec_py + i);
                 const int bx = (nx & ~(kBlockSize - 1)) - r, by = (ny & ~(kBlockSize - 1)) - r; // m_offset - m_border_size
                 s_a[hy][hx] = make_float4(rec.x, rec.y, rec.z, rec.w - 0.5f - (float) bx);
-                s_b[hy][hx] = make_float4(py - 0.5f - (float) by, (float) bx, (float) by, 1.f);
+                s_py[hy][hx] = py - 0.5f - (float) by;
             }
         }
         __syncthreads();
         if (!inside) continue;
-        for (int hy = hy_lo; hy <= hy_hi; ++hy)
-            for (int hx = hx_lo; hx <= hx_hi; ++hx) {
-                const float4 a = s_a[hy][hx], b = s_b[hy][hx];
-                const float posx = a.w, posy = b.x;
-                const float xb = (float) x - b.y, yb = (float) y - b.z; // exact: small integers
-                if (xb < posx - radius || xb > posx + radius || yb < posy - radius || yb > posy + radius) continue;
-                const float wx = s_tab[min((int) fabsf((xb - posx) * scale), 32)];
-                const float wy = s_tab[min((int) fabsf((yb - posy) * scale), 32)];
+#pragma unroll
+        for (int dy = 0; dy < kWin; ++dy) {
+            const int hy = hy_first + dy;
+            if (hy < hy_lo || hy > hy_hi) continue;
+#pragma unroll
+            for (int dx = 0; dx < kWin; ++dx) {
+                const int hx = hx_first + dx;
+                if (hx < hx_lo || hx > hx_hi) continue;
+                const float4 a = s_a[hy][hx];
+                const float posx = a.w;
+                if (xb[dx] < posx - radius || xb[dx] > posx + radius) continue;
+                const float posy = s_py[hy][hx];
+                if (yb[dy] < posy - radius || yb[dy] > posy + radius) continue;
+                const float wx = s_tab[min((int) fabsf((xb[dx] - posx) * scale), 32)];
+                const float wy = s_tab[min((int) fabsf((yb[dy] - posy) * scale), 32)];
                 const float w = wx * wy;
                 aX += w * a.x; aY += w * a.y; aZ += w * a.z; aW += w;
             }
+        }
     }
     if (!inside) return;
     float *p = film + ((size_t) y * W + x) * stride;
