@@ -438,7 +438,21 @@ def run_ours(args, rank: int, local_rank: int, world: int):
     # (csrc/msk_peer.cu); --reduce nccl selects torch.distributed's reduce instead
     peer = None
     if world > 1 and args.reduce == "peer":
-        peer = msk_dist.PeerFilm(ctx, (sd.height, sd.width, 5), rank, world)
+        # every rank must end up on the same reduction: agree on whether the IPC set-up succeeded everywhere
+        err = None
+        try:
+            peer = msk_dist.PeerFilm(ctx, (sd.height, sd.width, 5), rank, world)
+        except Exception as e:  # noqa: BLE001 -- e.g. no peer access between two of the devices
+            err, peer = e, None
+        ok = torch.tensor([0 if peer is None else 1], dtype=torch.int32, device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if int(ok.item()) == 0:
+            if err is not None:
+                print(f"bench.py rank {rank}: peer-memory film reduction unavailable ({err}); all ranks use ncclReduce", file=sys.stderr)
+            if peer is not None:
+                peer.close()
+            peer = None
+    if peer is not None:
         film = peer.tensor(dev)
     else:
         film = torch.zeros((sd.height, sd.width, 5), dtype=torch.float32, device=dev)

@@ -331,3 +331,30 @@ def test_tiled_path_enumeration_is_bit_identical(monkeypatch):
         aov_l, _ = sc.render_aov(rd, types)
     np.testing.assert_array_equal(film_t, film_l)
     np.testing.assert_array_equal(aov_t, aov_l)
+
+
+def test_c2_full_size_properties(gpu_ctx):
+    """BASELINE configs[1] at its full size (512x512, 64 spp, unbounded depth): size-independent properties instead of a
+    full oracle render -- bit-determinism run to run, invariance under a partition of the sample range (what multi-GPU
+    sharding and batching rest on), and agreement of the image mean with the oracle's render of the first 4 samples per
+    pixel (same seeds: those samples are a subset of the job's)."""
+    sd = scenes.bunny(512, 512)
+    rd = capi.render_desc(spp=64, max_depth=-1, rr_depth=5)
+    with capi.Scene(gpu_ctx, sd) as sc:
+        a, st = sc.render(rd)
+        b, _ = sc.render(rd)
+        np.testing.assert_array_equal(a, b)
+        assert st.paths == 512 * 512 * 64 and np.isfinite(a).all()
+        part, _ = sc.render(capi.render_desc(spp=64, max_depth=-1, rr_depth=5, sample_begin=0, sample_end=24))
+        part, _ = sc.render(capi.render_desc(spp=64, max_depth=-1, rr_depth=5, sample_begin=24, sample_end=64, clear_film=False), film=part)
+        np.testing.assert_allclose(part, a, rtol=5e-5, atol=1e-5)
+        np.testing.assert_allclose(a[..., 4].mean(), 64.0, rtol=1e-3)  # filter weights: every sample deposits weight ~1
+        first4, _ = sc.render(capi.render_desc(spp=64, max_depth=-1, rr_depth=5, sample_begin=0, sample_end=4))
+        rgba4 = sc.develop(first4)
+    ofilm, _ = pyoracle.OracleScene(sd).render(capi.render_desc(spp=64, max_depth=-1, rr_depth=5, sample_begin=0, sample_end=4))
+    e = relmse(rgba4, pyoracle.develop(ofilm))
+    print(f"[C2 full size, first 4 of 64 spp] relMSE={e:.3e}")
+    assert e < EQUAL_SEED_RELMSE
+    with capi.Scene(gpu_ctx, sd) as sc:  # the 64-spp image and its first 4 samples estimate the same mean
+        rgba = sc.develop(a)
+    np.testing.assert_allclose(rgba[..., :3].mean(), rgba4[..., :3].mean(), rtol=0.03)
