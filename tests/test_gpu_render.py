@@ -348,7 +348,8 @@ def test_c2_full_size_properties(gpu_ctx):
         part, _ = sc.render(capi.render_desc(spp=64, max_depth=-1, rr_depth=5, sample_begin=0, sample_end=24))
         part, _ = sc.render(capi.render_desc(spp=64, max_depth=-1, rr_depth=5, sample_begin=24, sample_end=64, clear_film=False), film=part)
         np.testing.assert_allclose(part, a, rtol=5e-5, atol=1e-5)
-        np.testing.assert_allclose(a[..., 4].mean(), 64.0, rtol=1e-3)  # filter weights: every sample deposits weight ~1
+        # filter weights: away from the film border every sample deposits a total weight of ~1 (normalised table, rfilter.cpp:12-27)
+        np.testing.assert_allclose(a[8:-8, 8:-8, 4].mean(), 64.0, rtol=2e-2)
         first4, _ = sc.render(capi.render_desc(spp=64, max_depth=-1, rr_depth=5, sample_begin=0, sample_end=4))
         rgba4 = sc.develop(first4)
     ofilm, _ = pyoracle.OracleScene(sd).render(capi.render_desc(spp=64, max_depth=-1, rr_depth=5, sample_begin=0, sample_end=4))
