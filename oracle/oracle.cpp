@@ -5,12 +5,19 @@
 // __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs
 // may load this library; the product (misaki_render_b200) never does.
 //
-// PARITY UNPINNED: the reference ships no tests, golden vectors or fixtures and
-// cannot be compiled in this image (Eigen3, pugixml, TBB, Embree 3.12.2,
-// OpenImageIO absent), so nothing here except rgb2spec_fetch/srgb.coeff (pinned
-// against the compiled reference ext/rgb2spec, see oracle/Makefile.ref) could be
-// checked against reference output.  Every function cites the reference
-// file:line it follows; paths are relative to /root/reference.
+// PARITY: PARTLY PINNED.  The reference ships no tests, golden vectors or fixtures and
+// cannot be built as a whole in this image (Eigen3, pugixml, TBB, Embree 3.12.2,
+// OpenImageIO absent).  What IS checked against outputs of the reference itself, compiled
+// here by oracle/Makefile.ref from the sources where they lie:
+//   * rgb2spec_fetch / srgb.coeff            (ext/rgb2spec; tests/test_oracle_rgb2spec.py)
+//   * the math layer, bit for bit            (include/misaki/core/{mathutils,warp,frame,spectrum,distribution}.h,
+//     include/misaki/render/{fresnel,microfacet,srgb}.h, src/librender/spectrum.cpp against a minimal Eigen stand-in,
+//     oracle/ref_shim: PCG32 + sampler floats, the warps, coordinate_system / Frame, Fresnel, reflect / refract, GGX
+//     eval / pdf / sample / G / smith_g1, sample_wavelength, spectrum_to_xyz, xyz_to_srgb, srgb_model_eval,
+//     Distribution1D; tests/golden/ref_math.json, tests/test_oracle_ref_math.py)
+// UNPINNED (restated from the cited lines, checked by known-answer tests only): everything in src/librender/*.cpp that
+// needs the object system -- the integrators, BSDF plugins, emitters, mesh / scene code, the film -- and Embree's
+// arithmetic.  Every function cites the reference file:line it follows; paths are relative to /root/reference.
 //
 // Third-party arithmetic outside the reference tree: Embree 3.12.2 (vcpkg port
 // embree3, vcpkg/ports/embree3/vcpkg.json).  Its default triangle intersector
@@ -392,6 +399,26 @@ void build_bvh(OScene &sc) {
 // ------------------------------------------------------------------------------------------
 // Mesh: src/librender/mesh.cpp
 // ------------------------------------------------------------------------------------------
+// Distribution1D::init, distribution.h:88-96
+std::vector<float> distribution_cdf(const float *table, size_t n) {
+    std::vector<float> cdf(1, 0.f);
+    float acc = 0.f; // std::partial_sum accumulates in float
+    for (size_t i = 0; i < n; ++i) {
+        acc = (i == 0) ? table[0] : acc + table[i];
+        cdf.push_back(acc);
+    }
+    const float inv_sum = 1.f / cdf.back();
+    for (auto &c : cdf) c *= inv_sum;
+    return cdf;
+}
+// Distribution1D::sample_reuse, distribution.h:107-123
+inline std::pair<uint32_t, float> distribution_sample_reuse(const std::vector<float> &cdf, float u) {
+    auto it   = std::upper_bound(cdf.begin(), cdf.end(), u);
+    int index = std::min(std::max(int(it - cdf.begin()) - 1, 0), int(cdf.size()) - 2);
+    float pmf = cdf[index + 1] - cdf[index];
+    return { (uint32_t) index, (u - cdf[index]) / pmf };
+}
+
 void area_distr_build(OMesh &m) { // mesh.cpp:39-48 + distribution.h:84-93
     std::vector<float> table(m.ntris);
     m.surface_area = 0.f; // the reference never initialises m_surface_area (mesh.h:93); restated as 0
@@ -402,14 +429,7 @@ void area_distr_build(OMesh &m) { // mesh.cpp:39-48 + distribution.h:84-93
         m.surface_area += a;
         table[i] = a;
     }
-    m.cdf.assign(1, 0.f);
-    float acc = 0.f; // std::partial_sum accumulates in float
-    for (uint32_t i = 0; i < m.ntris; ++i) {
-        acc = (i == 0) ? table[0] : acc + table[i];
-        m.cdf.push_back(acc);
-    }
-    const float inv_sum = 1.f / m.cdf.back();
-    for (auto &c : m.cdf) c *= inv_sum;
+    m.cdf = distribution_cdf(table.data(), table.size());
 }
 
 // mesh.cpp:51-101 + interaction.cpp:24-37 + interaction.h:55-60
@@ -476,11 +496,8 @@ struct PositionSample { V3 p, n; V2 uv; float pdf; };
 
 // mesh.cpp:103-133 + distribution.h:114-123 + warp.h:11-15
 PositionSample mesh_sample_position(const OMesh &m, V2 sample) {
-    // Distribution1D::sample_reuse(sample.y)
-    auto it        = std::upper_bound(m.cdf.begin(), m.cdf.end(), sample.y);
-    int index      = std::min(std::max(int(it - m.cdf.begin()) - 1, 0), int(m.cdf.size()) - 2);
-    float pmf      = m.cdf[index + 1] - m.cdf[index];
-    sample.y       = (sample.y - m.cdf[index]) / pmf;
+    uint32_t index;
+    std::tie(index, sample.y) = distribution_sample_reuse(m.cdf, sample.y);
     const uint32_t *fi = &m.tris[(uint32_t) index * 3];
     V3 p0 = m.pos(fi[0]), p1 = m.pos(fi[1]), p2 = m.pos(fi[2]);
     V3 e0 = p1 - p0, e1 = p2 - p0;
@@ -1560,6 +1577,31 @@ void orc_ggx(int which, float au, float av, const float a[3], const float b[3], 
     if (which == 0) out[0] = d.eval(va);
     else if (which == 1) { auto [m, pdf] = d.sample(va, { b[0], b[1] }); out[0] = m.x; out[1] = m.y; out[2] = m.z; out[3] = pdf; }
     else if (which == 2) out[0] = d.smith_g1(va, vb);
+}
+// Remaining math helpers in isolation, for the golden vectors produced by the compiled reference headers
+// (tests/test_oracle_ref_math.py).  which: 0 coordinate_system(n = in[0..2]) -> s, t            (mathutils.h:196-203)
+//   1 Frame(n = in[0..2]).to_local(v = in[3..5]) | to_world(v)                                  (frame.h:16-26)
+//   2 reflect(wi = in[0..2], m = in[3..5]) | refract(wi, m, cos_theta_t = in[6], eta_ti = in[7]) (fresnel.h:16-34)
+//   3 ggx(au = in[0], av = in[1]): pdf(wi = in[2..4], m = in[5..7]), G(wi = in[2..4], wo = in[5..7], m = in[8..10])
+//   4 xyz_to_srgb(in[0..2])                                                                      (spectrum.h:138-143)
+void orc_math(int which, const float *in, float *out) {
+    auto v3 = [&](int o) { return V3(in[o], in[o + 1], in[o + 2]); };
+    auto put = [&](int o, V3 v) { out[o] = v.x; out[o + 1] = v.y; out[o + 2] = v.z; };
+    if (which == 0) { V3 s, t; coordinate_system(v3(0), s, t); put(0, s); put(3, t); }
+    else if (which == 1) { Frame f(v3(0)); put(0, f.to_local(v3(3))); put(3, f.to_world(v3(3))); }
+    else if (which == 2) { put(0, reflect(v3(0), v3(3))); put(3, refract(v3(0), v3(3), in[6], in[7])); }
+    else if (which == 3) { Microfacet d(in[0], in[1]); out[0] = d.pdf(v3(2), v3(5)); out[1] = d.G(v3(2), v3(5), v3(8)); }
+    else if (which == 4) {
+        float film[5] = { in[0], in[1], in[2], 1.f, 1.f }, rgba[4];
+        orc_develop(film, rgba, 1);
+        out[0] = rgba[0]; out[1] = rgba[1]; out[2] = rgba[2];
+    }
+}
+// Distribution1D::init + sample_reuse as mesh_sample_position uses them (distribution.h:88-123): cdf has n + 1 entries
+void orc_distribution_sample_reuse(const float *pdf, size_t n, const float *u, size_t nu, uint32_t *index, float *reused, float *cdf_out) {
+    std::vector<float> cdf = distribution_cdf(pdf, n);
+    for (size_t i = 0; i < nu; ++i) std::tie(index[i], reused[i]) = distribution_sample_reuse(cdf, u[i]);
+    if (cdf_out) std::copy(cdf.begin(), cdf.end(), cdf_out);
 }
 // BSDF in isolation: wi (local), samples -> [wo.xyz, pdf, eta, sampled_type, weight0..3]; eval/pdf for a given wo
 int orc_bsdf(OrcScene *s, int bsdf_id, const float wi[3], const float wl[4], const float smp[3], const float wo_in[3], float out_sample[10], float out_eval[4], float *out_pdf) {

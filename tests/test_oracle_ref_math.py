@@ -1,0 +1,111 @@
+"""The oracle's math layer pinned against the reference ITSELF: tests/golden/ref_math.json holds outputs of the
+reference's own headers (include/misaki/core/{mathutils,warp,frame,spectrum,distribution}.h,
+include/misaki/render/{fresnel,microfacet,srgb}.h, CIE table of src/librender/spectrum.cpp) compiled in the build
+container by oracle/Makefile.ref against a minimal Eigen stand-in and called by tools/gen_golden_ref_math.py.
+Every value is compared BIT FOR BIT (same compiler, same libm, -ffp-contract=off on both sides); the only tolerance
+is for NaN payloads.  Covered: PCG32 and the sampler's float construction, the four warps, coordinate_system / Frame,
+Fresnel (dielectric, conductor), reflect / refract, GGX eval / pdf / sample / G / smith_g1, sample_wavelength,
+spectrum_to_xyz + xyz_to_srgb, srgb_model_eval, Distribution1D::init / sample_reuse."""
+import ctypes as C
+import json
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from oracle import pyoracle as po
+
+GOLDEN = json.loads((Path(__file__).resolve().parent / "golden" / "ref_math.json").read_text())
+f32 = np.float32
+
+
+def F(bits):
+    return np.array(bits, dtype=np.uint32).view(f32)
+
+
+def same_bits(got, want_bits, what):
+    got = np.ascontiguousarray(got, dtype=f32).reshape(-1)
+    want = F(want_bits)
+    assert got.shape == want.shape, what
+    ok = (got.view(np.uint32) == want.view(np.uint32)) | (np.isnan(got) & np.isnan(want))
+    assert ok.all(), f"{what}: got {got} want {want}"
+
+
+def orc_math(which, values, nout):
+    a = np.ascontiguousarray(values, dtype=f32)
+    out = np.zeros(nout, f32)
+    po.lib().orc_math(which, a.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p))
+    return out
+
+
+def test_pcg32_and_sampler_floats():
+    for c in GOLDEN["pcg32"]:
+        assert [int(x) for x in po.pcg32_uints(c["state"], c["seq"], 16)] == c["uints"]
+        if c["seq"] == 0xda3e39cb94b95bdb:  # IndependentSampler::seed uses PCG32_DEFAULT_STREAM (independent.cpp:20-26)
+            same_bits(po.pcg32_floats(c["state"], 16), c["floats"], f"next_float32 state={c['state']}")
+
+
+def test_warps():
+    for c in GOLDEN["warp"]:
+        u, v = F(c["uv"])
+        same_bits(po.warp(c["which"], float(u), float(v)), c["out"], f"warp {c['which']} ({u}, {v})")
+
+
+def test_coordinate_system_and_frame():
+    for c in GOLDEN["frame"]:
+        st = orc_math(0, F(c["n"]), 6)
+        same_bits(st[:3], c["s"], "coordinate_system s"); same_bits(st[3:], c["t"], "coordinate_system t")
+        lw = orc_math(1, np.concatenate([F(c["n"]), F(c["v"])]), 6)
+        same_bits(lw[:3], c["local"], "Frame::to_local"); same_bits(lw[3:], c["world"], "Frame::to_world")
+
+
+def test_fresnel_dielectric_conductor_reflect_refract():
+    for c in GOLDEN["fresnel"]:
+        same_bits(po.fresnel(float(F(c["cos"])[0]), float(F(c["eta"])[0])), c["out"], "fresnel")
+    for c in GOLDEN["fresnel_conductor"]:
+        eta, k = F(c["eta"]), F(c["k"])
+        got = po.fresnel_conductor(float(F(c["cos"])[0]), np.append(eta, eta[0]), np.append(k, k[0]))  # the oracle's is 4-wide
+        same_bits(got[:3], c["out"], "fresnel_conductor")
+    for c in GOLDEN["reflect_refract"]:
+        out = orc_math(2, np.concatenate([F(c["wi"]), F(c["m"]), F(c["ct"]), F(c["ti"])]), 6)
+        same_bits(out[:3], c["reflect"], "reflect(wi, m)"); same_bits(out[3:], c["refract"], "refract(wi, m, cos_theta_t, eta_ti)")
+
+
+def test_ggx_microfacet_distribution():
+    for c in GOLDEN["ggx"]:
+        au, av = float(F(c["au"])[0]), float(F(c["av"])[0])
+        a, b, cc, want = F(c["a"]), F(c["b"]), F(c["c"]), c["out"]
+        w = c["which"]
+        if w == 0:
+            same_bits(po.ggx(0, au, av, a)[:1], want[:1], "ggx eval")
+        elif w == 1:
+            same_bits(orc_math(3, np.concatenate([[au, av], a, b, b]), 2)[:1], want[:1], "ggx pdf")
+        elif w == 2:
+            same_bits(po.ggx(1, au, av, a, b), want, "ggx sample")
+        elif w == 3:
+            same_bits(orc_math(3, np.concatenate([[au, av], a, b, cc]), 2)[1:2], want[:1], "ggx G")
+        else:
+            same_bits(po.ggx(2, au, av, a, b)[:1], want[:1], "ggx smith_g1")
+
+
+def test_spectral_sampling_and_colour():
+    for c in GOLDEN["sample_wavelength"]:
+        wl, w = po.sample_wavelength(float(F(c["u"])[0]))
+        same_bits(wl, c["wl"], "sample_wavelength wavelengths"); same_bits(w, c["weight"], "sample_wavelength weights")
+    for c in GOLDEN["spectrum_to_xyz"]:
+        xyz = po.spectrum_to_xyz(F(c["value"]), F(c["wl"]))
+        same_bits(xyz, c["xyz"], "spectrum_to_xyz")
+        same_bits(orc_math(4, xyz, 3), c["rgb"], "xyz_to_srgb")
+    for c in GOLDEN["srgb_model_eval"]:
+        same_bits(po.srgb_model_eval(F(c["c"]), F(c["wl"])), c["out"], "srgb_model_eval")
+
+
+def test_distribution1d():
+    for c in GOLDEN["distribution"]:
+        pdf, u = F(c["pdf"]), F(c["u"])
+        idx = np.empty(len(u), np.uint32); re = np.empty(len(u), f32); cdf = np.empty(len(pdf) + 1, f32)
+        po.lib().orc_distribution_sample_reuse(pdf.ctypes.data_as(C.c_void_p), C.c_size_t(len(pdf)), u.ctypes.data_as(C.c_void_p), C.c_size_t(len(u)),
+                                               idx.ctypes.data_as(C.c_void_p), re.ctypes.data_as(C.c_void_p), cdf.ctypes.data_as(C.c_void_p))
+        same_bits(cdf, c["cdf"], "Distribution1D cdf")
+        assert [int(i) for i in idx] == c["index"]
+        same_bits(re, c["reused"], "sample_reuse")

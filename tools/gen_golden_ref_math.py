@@ -1,0 +1,139 @@
+#!/usr/bin/env python3
+"""Golden vectors from the reference's OWN math headers, compiled here (oracle/Makefile.ref ->
+oracle/_ref/libmisaki_ref_math.so: include/misaki/core/{mathutils,warp,frame,spectrum,distribution}.h,
+include/misaki/render/{fresnel,microfacet,srgb}.h and src/librender/spectrum.cpp against the Eigen stand-in under
+oracle/ref_shim/).  Writes tests/golden/ref_math.json; tests/test_oracle_ref_math.py replays the inputs through the
+oracle.  Floats are stored as their uint32 bit patterns, so the comparison is exact.
+
+    make -C oracle -f Makefile.ref && python tools/gen_golden_ref_math.py
+"""
+import ctypes as C
+import json
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent.parent
+LIB = ROOT / "oracle" / "_ref" / "libmisaki_ref_math.so"
+OUT = ROOT / "tests" / "golden" / "ref_math.json"
+f32 = np.float32
+
+
+def bits(a):
+    return [int(x) for x in np.ascontiguousarray(a, dtype=f32).reshape(-1).view(np.uint32)]
+
+
+def fp(a):
+    return np.ascontiguousarray(a, dtype=f32).ctypes.data_as(C.c_void_p)
+
+
+def unit(rng, n, upper=False):
+    v = rng.normal(size=(n, 3))
+    v /= np.linalg.norm(v, axis=1, keepdims=True)
+    if upper:
+        v[:, 2] = np.abs(v[:, 2])
+    return v.astype(f32)
+
+
+def main():
+    L = C.CDLL(str(LIB))
+    rng = np.random.default_rng(20241017)
+    g = {"source": "reference headers compiled by oracle/Makefile.ref (Eigen stand-in: oracle/ref_shim); float32 values as uint32 bit patterns"}
+
+    # PCG32 (mathutils.h:89-143)
+    cases = []
+    for state, seq in [(42, 54), (0, 0xda3e39cb94b95bdb), (123456789, 0xda3e39cb94b95bdb), (2**40 + 7, 1)]:
+        u = np.empty(16, np.uint32); f = np.empty(16, f32)
+        L.ref_pcg32_uints(C.c_uint64(state), C.c_uint64(seq), u.ctypes.data_as(C.c_void_p), C.c_size_t(16))
+        L.ref_pcg32_floats(C.c_uint64(state), C.c_uint64(seq), f.ctypes.data_as(C.c_void_p), C.c_size_t(16))
+        cases.append({"state": state, "seq": seq, "uints": [int(x) for x in u], "floats": bits(f)})
+    g["pcg32"] = cases
+
+    # warps (warp.h:11-53), including the corners / axes of the concentric map
+    uv = np.concatenate([rng.random((40, 2)), [[0.5, 0.5], [0, 0], [1, 1], [0.5, 0.25], [0.25, 0.5], [0.75, 0.5], [0.5, 0.75], [1, 0]]]).astype(f32)
+    out = np.empty(3, f32)
+    g["warp"] = []
+    for which in range(4):
+        for u, v in uv:
+            L.ref_warp(which, C.c_float(u), C.c_float(v), fp(out))
+            g["warp"].append({"which": which, "uv": bits([u, v]), "out": bits(out)})
+
+    # coordinate_system / Frame (mathutils.h:196-203, frame.h:16-26)
+    g["frame"] = []
+    normals = np.concatenate([unit(rng, 20), [[0, 0, 1], [0, 0, -1], [1, 0, 0], [0, -1, 0]]]).astype(f32)
+    vs = unit(rng, len(normals))
+    for n, v in zip(normals, vs):
+        s, t, lo, wo = (np.empty(3, f32) for _ in range(4))
+        L.ref_coordinate_system(fp(n), fp(s), fp(t))
+        L.ref_frame_roundtrip(fp(n), fp(v), fp(lo), fp(wo))
+        g["frame"].append({"n": bits(n), "v": bits(v), "s": bits(s), "t": bits(t), "local": bits(lo), "world": bits(wo)})
+
+    # Fresnel (fresnel.h:37-88), reflect / refract (:16-34)
+    g["fresnel"] = []
+    o4 = np.empty(4, f32)
+    for eta in (1.5, 1.0 / 1.5, 1.33, 1.0, 2.4):
+        for c in list(rng.uniform(-1, 1, 8)) + [0.0, 1.0, -1.0, 1e-4]:
+            L.ref_fresnel(C.c_float(c), C.c_float(eta), fp(o4))
+            g["fresnel"].append({"cos": bits([c]), "eta": bits([eta]), "out": bits(o4)})
+    g["fresnel_conductor"] = []
+    o3 = np.empty(3, f32)
+    for _ in range(24):
+        c = f32(rng.uniform(0, 1)); eta = rng.uniform(0.1, 3.0, 3).astype(f32); k = rng.uniform(0.0, 6.0, 3).astype(f32)
+        L.ref_fresnel_conductor(C.c_float(c), fp(eta), fp(k), fp(o3))
+        g["fresnel_conductor"].append({"cos": bits([c]), "eta": bits(eta), "k": bits(k), "out": bits(o3)})
+    g["reflect_refract"] = []
+    for wi, m in zip(unit(rng, 16, True), unit(rng, 16, True)):
+        ct, ti = f32(rng.uniform(-1, 1)), f32(rng.uniform(0.5, 2.0))
+        r, t = np.empty(3, f32), np.empty(3, f32)
+        L.ref_reflect_refract(fp(wi), fp(m), C.c_float(ct), C.c_float(ti), fp(r), fp(t))
+        g["reflect_refract"].append({"wi": bits(wi), "m": bits(m), "ct": bits([ct]), "ti": bits([ti]), "reflect": bits(r), "refract": bits(t)})
+
+    # GGX (microfacet.h:11-43,108-175)
+    g["ggx"] = []
+    zero = np.zeros(3, f32)
+    for au, av in [(0.1, 0.1), (0.3, 0.05), (0.5, 0.5), (1e-5, 1e-5)]:
+        for a, b, c in zip(unit(rng, 10, True), unit(rng, 10, True), unit(rng, 10, True)):
+            smp = rng.random(2).astype(f32)
+            for which, (x, y, z) in enumerate([(a, zero, zero), (a, b, zero), (a, np.array([smp[0], smp[1], 0], f32), zero), (a, b, c), (a, b, zero)]):
+                L.ref_ggx(which, C.c_float(au), C.c_float(av), fp(x), fp(y), fp(z), fp(o4))
+                g["ggx"].append({"which": which, "au": bits([au]), "av": bits([av]), "a": bits(x), "b": bits(y), "c": bits(z), "out": bits(o4)})
+
+    # spectral sampling and colour (spectrum.h:83-181, srgb.h:8-19; CIE table from src/librender/spectrum.cpp)
+    g["sample_wavelength"] = []
+    for u in list(rng.random(24)) + [0.0, 0.25, 0.5, 0.999999]:
+        wl, w = np.empty(4, f32), np.empty(4, f32)
+        L.ref_sample_wavelength(C.c_float(u), fp(wl), fp(w))
+        g["sample_wavelength"].append({"u": bits([u]), "wl": bits(wl), "weight": bits(w)})
+    g["spectrum_to_xyz"] = []
+    for _ in range(24):
+        wl = rng.uniform(360, 830, 4).astype(f32); val = rng.uniform(0, 2, 4).astype(f32)
+        L.ref_spectrum_to_xyz(fp(val), fp(wl), fp(o3))
+        rgb = np.empty(3, f32)
+        L.ref_xyz_to_srgb(fp(o3.copy()), fp(rgb))
+        g["spectrum_to_xyz"].append({"value": bits(val), "wl": bits(wl), "xyz": bits(o3), "rgb": bits(rgb)})
+    g["srgb_model_eval"] = []
+    for _ in range(24):
+        c = np.array([rng.uniform(-1e-4, 1e-4), rng.uniform(-0.1, 0.1), rng.uniform(-30, 30)], f32)
+        wl = rng.uniform(360, 830, 4).astype(f32)
+        L.ref_srgb_model_eval(fp(c), fp(wl), fp(o4))
+        g["srgb_model_eval"].append({"c": bits(c), "wl": bits(wl), "out": bits(o4)})
+    for z in (np.inf, -np.inf):
+        c = np.array([0, 0, z], f32); wl = np.array([400, 500, 600, 700], f32)
+        L.ref_srgb_model_eval(fp(c), fp(wl), fp(o4))
+        g["srgb_model_eval"].append({"c": bits(c), "wl": bits(wl), "out": bits(o4)})
+
+    # Distribution1D (distribution.h:84-123) as Mesh::sample_position uses it
+    g["distribution"] = []
+    for n in (1, 2, 7, 64):
+        pdf = rng.uniform(0.01, 3.0, n).astype(f32)
+        u = np.concatenate([rng.random(12), [0.0, 0.5, 0.99999994]]).astype(f32)
+        idx = np.empty(len(u), np.uint32); re = np.empty(len(u), f32); cdf = np.empty(n + 1, f32)
+        L.ref_distribution_sample_reuse(fp(pdf), C.c_size_t(n), fp(u), C.c_size_t(len(u)), idx.ctypes.data_as(C.c_void_p), fp(re), fp(cdf))
+        g["distribution"].append({"pdf": bits(pdf), "u": bits(u), "index": [int(i) for i in idx], "reused": bits(re), "cdf": bits(cdf)})
+
+    OUT.write_text(json.dumps(g, separators=(",", ":")))
+    print(f"wrote {OUT} ({OUT.stat().st_size} bytes): " + ", ".join(f"{k}={len(v)}" for k, v in g.items() if isinstance(v, list)))
+
+
+if __name__ == "__main__":
+    main()
