@@ -3,6 +3,7 @@
 // Everything numeric still comes from the reference's own headers, included from where they lie.
 // TEST INFRASTRUCTURE (oracle/Makefile.ref); see oracle/ref_shim/Eigen/Core.
 #pragma once
+#include <cassert>
 #include <cmath>
 #include <cstdint>
 #include <cstring>
@@ -15,6 +16,7 @@ namespace std { using ::sinf; using ::cosf; } // mathutils.h:68-69 calls std::si
 #include <misaki/core/frame.h>
 #include <misaki/core/spectrum.h>
 #include <misaki/core/distribution.h>
+#include <misaki/core/properties.h> // the stand-in under oracle/ref_shim/misaki/core
 
 namespace misaki {
 using Distribution1D = math::Distribution1D<float>; // fwd.h:33-37
@@ -23,15 +25,8 @@ using Color4         = Color<float, 4>;
 using Spectrum       = SpectrumArray<float, 4>;
 using Wavelength     = SpectrumArray<float, 4>;
 
-// MicrofacetDistribution's first constructor reads a Properties object; the wrapper uses the (type, alpha_u, alpha_v)
-// constructors, so an empty property set is enough for the header to compile
-class Properties {
-public:
-    bool has_property(const std::string &) const { return false; }
-    std::string string(const std::string &) const { return std::string(); }
-    float float_(const std::string &) const { return 0.f; }
-    bool bool_(const std::string &, bool def) const { return def; }
-};
+class Shape; class Emitter; class Scene; class Medium; class BSDF; class Texture; class Sampler; // fwd.h:41-60
+struct Ray; struct RayDifferential; struct PositionSample; struct DirectionSample; struct SceneInteraction; struct BSDFSample;
 enum MskRefLogLevel { Trace, Debug, Info, Warn, Error };
 template <typename... A> inline void msk_ref_throw(A &&...) { throw 1; }
 template <typename... A> inline void msk_ref_log(A &&...) {}

@@ -5,7 +5,8 @@ container by oracle/Makefile.ref against a minimal Eigen stand-in and called by 
 Every value is compared BIT FOR BIT (same compiler, same libm, -ffp-contract=off on both sides); the only tolerance
 is for NaN payloads.  Covered: PCG32 and the sampler's float construction, the four warps, coordinate_system / Frame,
 Fresnel (dielectric, conductor), reflect / refract, GGX eval / pdf / sample / G / smith_g1, sample_wavelength,
-spectrum_to_xyz + xyz_to_srgb, srgb_model_eval, Distribution1D::init / sample_reuse."""
+spectrum_to_xyz + xyz_to_srgb, srgb_model_eval, Distribution1D::init / sample_reuse, and SmoothDiffuse::sample / eval /
+pdf from the reference's own bsdfs/diffuse.cpp (the one BSDF plugin its build compiles)."""
 import ctypes as C
 import json
 from pathlib import Path
@@ -109,3 +110,22 @@ def test_distribution1d():
         same_bits(cdf, c["cdf"], "Distribution1D cdf")
         assert [int(i) for i in idx] == c["index"]
         same_bits(re, c["reused"], "sample_reuse")
+
+
+def test_smooth_diffuse_plugin():
+    """src/librender/bsdfs/diffuse.cpp itself (compiled over stand-ins for Object / Properties / Texture)."""
+    from misaki_render_b200.scene import SceneDescription
+    scenes_by_refl = {}
+    for c in GOLDEN["bsdf_diffuse"]:
+        refl = float(F(c["reflectance"])[0])
+        if refl not in scenes_by_refl:
+            sd = SceneDescription(8, 8)
+            b = sd.bsdf_diffuse(refl)  # float -> "uniform" spectrum: the constant texture of the reference-side wrapper
+            sd.add_mesh(np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0]], f32), np.array([[0, 1, 2]], np.uint32), b)
+            scenes_by_refl[refl] = (po.OracleScene(sd), b)
+        osc, b = scenes_by_refl[refl]
+        r = osc.bsdf(b, F(c["wi"]), F(c["wl"]), F(c["smp"]), F(c["wo"]))
+        got = np.concatenate([r["wo"], [r["pdf"], r["eta"], float(r["type"])], r["weight"]]).astype(f32)
+        same_bits(got, c["sample"], "SmoothDiffuse::sample")
+        same_bits(r["eval"], c["eval"], "SmoothDiffuse::eval")
+        same_bits([r["eval_pdf"]], c["pdf"], "SmoothDiffuse::pdf")

@@ -131,6 +131,18 @@ def main():
         L.ref_distribution_sample_reuse(fp(pdf), C.c_size_t(n), fp(u), C.c_size_t(len(u)), idx.ctypes.data_as(C.c_void_p), fp(re), fp(cdf))
         g["distribution"].append({"pdf": bits(pdf), "u": bits(u), "index": [int(i) for i in idx], "reused": bits(re), "cdf": bits(cdf)})
 
+    # SmoothDiffuse::sample / eval / pdf from the reference's own src/librender/bsdfs/diffuse.cpp (constant reflectance)
+    g["bsdf_diffuse"] = []
+    osamp, oev, opdf = np.empty(10, f32), np.empty(4, f32), C.c_float()
+    wl = np.array([420, 510, 600, 690], f32)
+    for refl in (0.6, 0.05, 1.0):
+        params = np.zeros(10, f32); params[0] = refl
+        for wi, wo in zip(unit(rng, 12), unit(rng, 12)):  # both hemispheres: the one-sided BRDF returns zero below
+            smp = rng.random(3).astype(f32)
+            assert L.ref_bsdf(0, fp(params), fp(wi), fp(wl), fp(smp), fp(wo), fp(osamp), fp(oev), C.byref(opdf)) == 0
+            g["bsdf_diffuse"].append({"reflectance": bits([refl]), "wi": bits(wi), "wl": bits(wl), "smp": bits(smp), "wo": bits(wo),
+                                      "sample": bits(osamp), "eval": bits(oev), "pdf": bits([opdf.value])})
+
     OUT.write_text(json.dumps(g, separators=(",", ":")))
     print(f"wrote {OUT} ({OUT.stat().st_size} bytes): " + ", ".join(f"{k}={len(v)}" for k, v in g.items() if isinstance(v, list)))
 
