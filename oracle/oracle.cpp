@@ -15,6 +15,8 @@
 //     oracle/ref_shim: PCG32 + sampler floats, the warps, coordinate_system / Frame, Fresnel, reflect / refract, GGX
 //     eval / pdf / sample / G / smith_g1, sample_wavelength, spectrum_to_xyz, xyz_to_srgb, srgb_model_eval,
 //     Distribution1D; tests/golden/ref_math.json, tests/test_oracle_ref_math.py)
+//   * plugin sources the reference's build compiles, over stand-ins for its object system: bsdfs/diffuse.cpp, rfilter.cpp +
+//     filters/gaussian.cpp, sampler.cpp + samplers/independent.cpp, spectra/regular.cpp, spectra/uniform.cpp (same tests)
 // UNPINNED (restated from the cited lines, checked by known-answer tests only): everything in src/librender/*.cpp that
 // needs the object system -- the integrators, BSDF plugins, emitters, mesh / scene code, the film -- and Embree's
 // arithmetic.  Every function cites the reference file:line it follows; paths are relative to /root/reference.

@@ -11,16 +11,21 @@ class Properties {
 public:
     std::map<std::string, float> floats;
     std::map<std::string, bool> bools;
+    std::map<std::string, long long> ints;
+    std::map<std::string, const void *> pointers;
     std::map<std::string, std::string> strings;
     std::map<std::string, ref<Texture>> textures;
     std::vector<std::pair<std::string, ref<Object>>> children;
     ref<Texture> (*make_default)(float) = nullptr; // how a defaulted texture is built (set by the wrapper)
     std::string id() const { return std::string(); }
-    bool has_property(const std::string &n) const { return floats.count(n) || bools.count(n) || strings.count(n) || textures.count(n); }
+    bool has_property(const std::string &n) const { return floats.count(n) || bools.count(n) || strings.count(n) || textures.count(n) || ints.count(n) || pointers.count(n); }
     std::string string(const std::string &n) const { return strings.at(n); }
     std::string string(const std::string &n, const std::string &d) const { auto it = strings.find(n); return it == strings.end() ? d : it->second; }
     float float_(const std::string &n) const { return floats.at(n); }
     float float_(const std::string &n, float d) const { auto it = floats.find(n); return it == floats.end() ? d : it->second; }
+    long long int_(const std::string &n) const { return ints.at(n); }
+    long long int_(const std::string &n, long long d) const { auto it = ints.find(n); return it == ints.end() ? d : it->second; }
+    const void *pointer(const std::string &n) const { return pointers.at(n); }
     bool bool_(const std::string &n, bool d) const { auto it = bools.find(n); return it == bools.end() ? d : it->second; }
     ref<Texture> texture(const std::string &n) const { return textures.at(n); }
     ref<Texture> texture(const std::string &n, float d) const { auto it = textures.find(n); return it == textures.end() ? make_default(d) : it->second; }

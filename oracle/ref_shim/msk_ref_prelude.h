@@ -8,6 +8,7 @@
 #include <cstdint>
 #include <cstring>
 #include <limits>
+#include <memory>
 #include <string>
 #include <tuple>
 namespace std { using ::sinf; using ::cosf; } // mathutils.h:68-69 calls std::sinf / std::cosf, which libstdc++ does not declare
@@ -31,5 +32,7 @@ enum MskRefLogLevel { Trace, Debug, Info, Warn, Error };
 template <typename... A> inline void msk_ref_throw(A &&...) { throw 1; }
 template <typename... A> inline void msk_ref_log(A &&...) {}
 } // namespace misaki
+#define MSK_NOT_IMPLEMENTED(name) throw 1
+namespace fmt { template <typename... A> inline std::string format(A &&...) { return std::string(); } } // used by to_string() only
 #define Throw(...) ::misaki::msk_ref_throw(__VA_ARGS__)
 #define Log(...) ::misaki::msk_ref_log(__VA_ARGS__)

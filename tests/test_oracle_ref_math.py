@@ -129,3 +129,29 @@ def test_smooth_diffuse_plugin():
         same_bits(got, c["sample"], "SmoothDiffuse::sample")
         same_bits(r["eval"], c["eval"], "SmoothDiffuse::eval")
         same_bits([r["eval_pdf"]], c["pdf"], "SmoothDiffuse::pdf")
+
+
+def test_gaussian_filter_sampler_and_spectrum_plugins():
+    """filters/gaussian.cpp + rfilter.cpp, samplers/independent.cpp + sampler.cpp, spectra/regular.cpp, spectra/uniform.cpp."""
+    from misaki_render_b200 import capi
+    from misaki_render_b200.scene import SceneDescription
+    for c in GOLDEN["gaussian_filter"]:
+        radius, table = po.gaussian_filter(float(F(c["stddev"])[0]))
+        same_bits([radius], c["radius"], "GaussianFilter radius")
+        same_bits(table, c["table"], "ReconstructionFilter::init_discretization table")
+        assert int(np.ceil(radius - 0.5)) == c["border"]
+    for c in GOLDEN["independent_sampler"]:  # next2d() = { next1d(), next1d() }: x first
+        n = c["n1"] + 2 * c["n2"]
+        same_bits(po.pcg32_floats(c["seed"], n, c["base_seed"]), c["out"], "IndependentSampler seed / next1d / next2d")
+    for c in GOLDEN["regular_spectrum"]:
+        sd = SceneDescription(8, 8)
+        lo, hi = F(c["range"])
+        sid = sd._add_spec(capi.SPEC_REGULAR, table=F(c["values"]).copy(), lmin=float(lo), lmax=float(hi))
+        sd.add_mesh(np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0]], f32), np.array([[0, 1, 2]], np.uint32), sd.bsdf_diffuse(0.5))
+        same_bits(po.OracleScene(sd).spectrum_eval(sid, F(c["wl"])), c["out"], "RegularSpectrum::eval")
+    sd = SceneDescription(8, 8)
+    sid = sd.spectrum_uniform(float(F(GOLDEN["uniform_spectrum"][0]["value"])[0]))
+    sd.add_mesh(np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0]], f32), np.array([[0, 1, 2]], np.uint32), sd.bsdf_diffuse(0.5))
+    osc = po.OracleScene(sd)
+    for c in GOLDEN["uniform_spectrum"]:
+        same_bits(osc.spectrum_eval(sid, F(c["wl"])), c["out"], "UniformSpectrum::eval")

@@ -143,6 +143,30 @@ def main():
             g["bsdf_diffuse"].append({"reflectance": bits([refl]), "wi": bits(wi), "wl": bits(wl), "smp": bits(smp), "wo": bits(wo),
                                       "sample": bits(osamp), "eval": bits(oev), "pdf": bits([opdf.value])})
 
+    # plugin sources the reference's build compiles (oracle/ref_plugins_wrap.cpp)
+    g["gaussian_filter"] = []
+    o35 = np.empty(35, f32)
+    for stddev in (0.5, 0.25, 1.0, 0.8):
+        L.ref_gaussian_filter(C.c_float(stddev), fp(o35))
+        g["gaussian_filter"].append({"stddev": bits([stddev]), "radius": bits(o35[:1]), "border": int(o35[1]), "table": bits(o35[2:])})
+    g["independent_sampler"] = []
+    for base, seed in [(0, 0), (0, 12345), (9, 7), (1000, 2**33 + 5)]:
+        o = np.empty(6 + 2 * 5, f32)
+        L.ref_independent_sampler(C.c_uint64(base), C.c_uint64(seed), 6, 5, fp(o))
+        g["independent_sampler"].append({"base_seed": base, "seed": seed, "n1": 6, "n2": 5, "out": bits(o)})
+    g["regular_spectrum"] = []
+    mean = C.c_float()
+    for size, (lo, hi) in [(2, (400, 700)), (4, (400, 700)), (95, (360, 830)), (16, (300, 900))]:
+        vals = rng.uniform(0.0, 2.0, size).astype(f32)
+        for _ in range(6):
+            wl = rng.uniform(lo - 30, hi + 30, 4).astype(f32)  # also outside the range: the index is clamped, the weights are not
+            L.ref_regular_spectrum(C.c_float(lo), C.c_float(hi), fp(vals), C.c_size_t(size), fp(wl), fp(o4), C.byref(mean))
+            g["regular_spectrum"].append({"range": bits([lo, hi]), "values": bits(vals), "wl": bits(wl), "out": bits(o4)})
+    g["uniform_spectrum"] = []
+    for wl in ([400, 500, 600, 700], [360, 500, 600, 830], [359.9, 500, 600, 700], [400, 500, 600, 830.1]):
+        L.ref_uniform_spectrum(C.c_float(0.37), fp(np.array(wl, f32)), fp(o4))
+        g["uniform_spectrum"].append({"value": bits([0.37]), "wl": bits(wl), "out": bits(o4)})
+
     OUT.write_text(json.dumps(g, separators=(",", ":")))
     print(f"wrote {OUT} ({OUT.stat().st_size} bytes): " + ", ".join(f"{k}={len(v)}" for k, v in g.items() if isinstance(v, list)))
 
