@@ -16,10 +16,12 @@
 //     eval / pdf / sample / G / smith_g1, sample_wavelength, spectrum_to_xyz, xyz_to_srgb, srgb_model_eval,
 //     Distribution1D; tests/golden/ref_math.json, tests/test_oracle_ref_math.py)
 //   * plugin sources the reference's build compiles, over stand-ins for its object system: bsdfs/diffuse.cpp, rfilter.cpp +
-//     filters/gaussian.cpp, sampler.cpp + samplers/independent.cpp, spectra/regular.cpp, spectra/uniform.cpp (same tests)
-// UNPINNED (restated from the cited lines, checked by known-answer tests only): everything in src/librender/*.cpp that
-// needs the object system -- the integrators, BSDF plugins, emitters, mesh / scene code, the film -- and Embree's
-// arithmetic.  Every function cites the reference file:line it follows; paths are relative to /root/reference.
+//     filters/gaussian.cpp, sampler.cpp + samplers/independent.cpp, spectra/regular.cpp, spectra/uniform.cpp, and
+//     mesh.cpp + shape.cpp + records.cpp + interaction.cpp (hit reconstruction, area distribution, position / direct
+//     sampling) (same tests)
+// UNPINNED (restated from the cited lines, checked by known-answer tests only): the integrator loops, the BSDF plugins
+// other than diffuse (their sources are stale-API and compile with no Eigen), the emitters, Scene::sample_emitter_direct,
+// the camera, ImageBlock::put, the srgb / srgb_d65 spectra -- and Embree's arithmetic.  Every function cites the reference file:line it follows; paths are relative to /root/reference.
 //
 // Third-party arithmetic outside the reference tree: Embree 3.12.2 (vcpkg port
 // embree3, vcpkg/ports/embree3/vcpkg.json).  Its default triangle intersector
@@ -1598,6 +1600,42 @@ void orc_math(int which, const float *in, float *out) {
         orc_develop(film, rgba, 1);
         out[0] = rgba[0]; out[1] = rgba[1]; out[2] = rgba[2];
     }
+}
+// Hit reconstruction and mesh sampling on a single mesh given as raw arrays (layouts as oracle/ref_mesh_wrap.cpp):
+// interaction out[27] = t | p | n | uv | sh_frame.s | sh_frame.t | sh_frame.n | wi | dp_du | dp_dv
+static OMesh make_single_mesh(const float *verts, uint32_t nverts, const uint32_t *tris, uint32_t ntris, int normals, int uvs) {
+    OMesh o;
+    o.nverts = nverts; o.ntris = ntris; o.has_normals = normals != 0; o.has_uvs = uvs != 0;
+    o.verts.assign(verts, verts + (size_t) nverts * 8);
+    o.tris.assign(tris, tris + (size_t) ntris * 3);
+    area_distr_build(o);
+    return o;
+}
+void orc_mesh_interaction(const float *verts, uint32_t nverts, const uint32_t *tris, uint32_t ntris, int normals, int uvs, uint32_t prim, float u,
+                          float v, float t, const float o[3], const float d[3], float out[27]) {
+    OScene sc;
+    sc.meshes.push_back(make_single_mesh(verts, nverts, tris, ntris, normals, uvs));
+    Ray ray{ V3(o[0], o[1], o[2]), V3(d[0], d[1], d[2]), 0.f, Infinity, Spec(500.f) };
+    RawHit h; h.t = t; h.u = u; h.v = v; h.prim = prim; h.geom = 0;
+    SceneInteraction si = compute_scene_interaction(sc, ray, h);
+    float *w = out;
+    auto put3 = [&](V3 x) { *w++ = x.x; *w++ = x.y; *w++ = x.z; };
+    *w++ = si.t; put3(si.p); put3(si.n); *w++ = si.uv.x; *w++ = si.uv.y;
+    put3(si.sh_frame.s); put3(si.sh_frame.t); put3(si.sh_frame.n); put3(si.wi); put3(si.dp_du); put3(si.dp_dv);
+}
+// sampling out[22] = ps.p | ps.n | ps.uv | ps.pdf | ds.p | ds.n | ds.d | ds.dist | ds.pdf | pdf_direct(ds) | surface_area
+void orc_mesh_sampling(const float *verts, uint32_t nverts, const uint32_t *tris, uint32_t ntris, int normals, int uvs, const float sample[2],
+                       const float ref_p[3], float out[22], float *cdf_out) {
+    OMesh m = make_single_mesh(verts, nverts, tris, ntris, normals, uvs);
+    PositionSample ps = mesh_sample_position(m, { sample[0], sample[1] });
+    SceneInteraction si;
+    si.p = V3(ref_p[0], ref_p[1], ref_p[2]);
+    DirectIllumSample ds = shape_sample_direct(m, si, { sample[0], sample[1] });
+    float *w = out;
+    auto put3 = [&](V3 x) { *w++ = x.x; *w++ = x.y; *w++ = x.z; };
+    put3(ps.p); put3(ps.n); *w++ = ps.uv.x; *w++ = ps.uv.y; *w++ = ps.pdf;
+    put3(ds.p); put3(ds.n); put3(ds.d); *w++ = ds.dist; *w++ = ds.pdf; *w++ = shape_pdf_direct(m, ds); *w++ = m.surface_area;
+    if (cdf_out) std::copy(m.cdf.begin(), m.cdf.end(), cdf_out);
 }
 // Distribution1D::init + sample_reuse as mesh_sample_position uses them (distribution.h:88-123): cdf has n + 1 entries
 void orc_distribution_sample_reuse(const float *pdf, size_t n, const float *u, size_t nu, uint32_t *index, float *reused, float *cdf_out) {

@@ -32,6 +32,10 @@ void orc_warp(int which, float u, float v, float out[3]);
 void orc_fresnel(float cos_theta_i, float eta, float out[4]);
 void orc_fresnel_conductor(float cos_theta_i, const float eta[4], const float k[4], float out[4]);
 void orc_srgb_model_eval(const float c[3], const float wl[4], float out[4]);
+void orc_mesh_interaction(const float *verts, uint32_t nverts, const uint32_t *tris, uint32_t ntris, int normals, int uvs, uint32_t prim,
+                          float u, float v, float t, const float o[3], const float d[3], float out[27]);
+void orc_mesh_sampling(const float *verts, uint32_t nverts, const uint32_t *tris, uint32_t ntris, int normals, int uvs, const float sample[2],
+                       const float ref_p[3], float out[22], float *cdf_out);
 void orc_math(int which, const float *in, float *out); /* coordinate_system, Frame, reflect/refract, ggx pdf/G, xyz_to_srgb */
 void orc_distribution_sample_reuse(const float *pdf, size_t n, const float *u, size_t nu, uint32_t *index, float *reused, float *cdf_out);
 int  orc_spectrum_eval(OrcScene *s, int id, const float wl[4], float out[4]);

@@ -7,8 +7,13 @@
 #include <vector>
 namespace misaki {
 class Texture;
+struct Transform4f;
 class Properties {
 public:
+    Properties() {}
+    explicit Properties(const std::string &plugin) : plugin_name(plugin) {}
+    std::string plugin_name;
+    template <typename T> T transform(const std::string &, const T &d) const { return d; } // shapes stay in world space
     std::map<std::string, float> floats;
     std::map<std::string, bool> bools;
     std::map<std::string, long long> ints;

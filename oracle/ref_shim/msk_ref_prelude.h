@@ -18,6 +18,7 @@ namespace std { using ::sinf; using ::cosf; } // mathutils.h:68-69 calls std::si
 #include <misaki/core/spectrum.h>
 #include <misaki/core/distribution.h>
 #include <misaki/core/properties.h> // the stand-in under oracle/ref_shim/misaki/core
+#include "msk_ref_geometry.h"
 
 namespace misaki {
 using Distribution1D = math::Distribution1D<float>; // fwd.h:33-37

@@ -155,3 +155,30 @@ def test_gaussian_filter_sampler_and_spectrum_plugins():
     osc = po.OracleScene(sd)
     for c in GOLDEN["uniform_spectrum"]:
         same_bits(osc.spectrum_eval(sid, F(c["wl"])), c["out"], "UniformSpectrum::eval")
+
+
+def test_mesh_hit_reconstruction_and_sampling():
+    """src/librender/{mesh,shape,records,interaction}.cpp themselves: Mesh::compute_scene_interaction +
+    PreliminaryIntersection::compute_scene_interaction + initialize_sh_frame (position from barycentrics, geometric and
+    shading normals, uv, dp_du / dp_dv with and without texcoords, the shading frame, wi), Mesh::area_distr_build,
+    Mesh::sample_position, Shape::sample_direct / pdf_direct."""
+    L = po.lib()
+    for m in GOLDEN["mesh"]:
+        v = F(m["verts"]).reshape(-1, 8).copy(); t = np.array(m["tris"], np.uint32).reshape(-1, 3).copy()
+        nv, nt = v.shape[0], t.shape[0]
+        vp, tp = v.ctypes.data_as(C.c_void_p), t.ctypes.data_as(C.c_void_p)
+        for h in m["hits"]:
+            u, vv, tt = F(h["uvt"])
+            o, d = F(h["o"]).copy(), F(h["d"]).copy()
+            out = np.empty(27, f32)
+            L.orc_mesh_interaction(vp, nv, tp, nt, m["normals"], m["uvs"], h["prim"], C.c_float(u), C.c_float(vv), C.c_float(tt),
+                                   o.ctypes.data_as(C.c_void_p), d.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p))
+            same_bits(out, h["out"], f"compute_scene_interaction normals={m['normals']} uvs={m['uvs']} prim={h['prim']}")
+        cdf = np.empty(nt + 1, f32)
+        for s_ in m["samples"]:
+            smp, ref_p = F(s_["sample"]).copy(), F(s_["ref_p"]).copy()
+            out = np.empty(22, f32)
+            L.orc_mesh_sampling(vp, nv, tp, nt, m["normals"], m["uvs"], smp.ctypes.data_as(C.c_void_p), ref_p.ctypes.data_as(C.c_void_p),
+                                out.ctypes.data_as(C.c_void_p), cdf.ctypes.data_as(C.c_void_p))
+            same_bits(out, s_["out"], f"sample_position / sample_direct normals={m['normals']} uvs={m['uvs']}")
+        same_bits(cdf, m["cdf"], "area distribution")

@@ -167,6 +167,40 @@ def main():
         L.ref_uniform_spectrum(C.c_float(0.37), fp(np.array(wl, f32)), fp(o4))
         g["uniform_spectrum"].append({"value": bits([0.37]), "wl": bits(wl), "out": bits(o4)})
 
+    # src/librender/{mesh,shape,records,interaction}.cpp (oracle/ref_mesh_wrap.cpp): hit reconstruction and mesh sampling
+    import sys
+    sys.path.insert(0, str(ROOT))
+    from workloads import meshes as wm
+    g["mesh"] = []
+    cases = []
+    for normals, uvs in [(False, False), (True, False), (True, True), (False, True)]:
+        v, t = wm.cube_sphere(3, seed=11, octaves=2, amplitude=0.1, radius=1.0, center=(0.2, -0.1, 0.3), normals=True, uvs=True)
+        v = np.ascontiguousarray(v, f32).copy()
+        if not normals: v[:, 3:6] = 0
+        if not uvs: v[:, 6:8] = 0
+        cases.append((v, np.ascontiguousarray(t, np.uint32), normals, uvs))
+    qv = np.zeros((4, 8), f32); qv[:, :3] = [(-1, 2, -1), (1, 2, -1), (1, 2, 1), (-1, 2, 1)]
+    cases.append((qv, np.array([[0, 1, 2], [0, 2, 3]], np.uint32), False, False))  # the C2 light quad: no normals, no uvs
+    for v, t, normals, uvs in cases:
+        entry = {"verts": bits(v), "tris": [int(x) for x in t.reshape(-1)], "normals": int(normals), "uvs": int(uvs), "hits": [], "samples": []}
+        nv, nt = v.shape[0], t.shape[0]
+        tp = t.ctypes.data_as(C.c_void_p)
+        for _ in range(10):
+            prim = int(rng.integers(nt)); b = rng.random(2); b = b if b.sum() < 1 else 1 - b
+            u_, v_ = f32(b[0]), f32(b[1]); tt = f32(rng.uniform(0.5, 5.0))
+            o = rng.uniform(-3, 3, 3).astype(f32); d = unit(rng, 1)[0]
+            out = np.empty(36, f32)
+            assert L.ref_mesh_interaction(fp(v), nv, tp, nt, int(normals), int(uvs), prim, C.c_float(u_), C.c_float(v_), C.c_float(tt), fp(o), fp(d), fp(out)) == 0
+            entry["hits"].append({"prim": prim, "uvt": bits([u_, v_, tt]), "o": bits(o), "d": bits(d), "out": bits(out[:27])})
+        cdf = np.empty(nt + 1, f32)
+        for _ in range(10):
+            smp = rng.random(2).astype(f32); ref_p = rng.uniform(-3, 3, 3).astype(f32)
+            out = np.empty(22, f32)
+            assert L.ref_mesh_sampling(fp(v), nv, tp, nt, int(normals), int(uvs), fp(smp), fp(ref_p), fp(out), fp(cdf)) == 0
+            entry["samples"].append({"sample": bits(smp), "ref_p": bits(ref_p), "out": bits(out)})
+        entry["cdf"] = bits(cdf)
+        g["mesh"].append(entry)
+
     OUT.write_text(json.dumps(g, separators=(",", ":")))
     print(f"wrote {OUT} ({OUT.stat().st_size} bytes): " + ", ".join(f"{k}={len(v)}" for k, v in g.items() if isinstance(v, list)))
 
