@@ -19,9 +19,11 @@
 //     filters/gaussian.cpp, sampler.cpp + samplers/independent.cpp, spectra/regular.cpp, spectra/uniform.cpp, and
 //     mesh.cpp + shape.cpp + records.cpp + interaction.cpp (hit reconstruction, area distribution, position / direct
 //     sampling) (same tests)
-// UNPINNED (restated from the cited lines, checked by known-answer tests only): the integrator loops, the BSDF plugins
-// other than diffuse (their sources are stale-API and compile with no Eigen), the emitters, Scene::sample_emitter_direct,
-// the camera, ImageBlock::put, the srgb / srgb_d65 spectra -- and Embree's arithmetic.  Every function cites the reference file:line it follows; paths are relative to /root/reference.
+//   * PathTracer::sample itself (integrators/path.cpp) with scene.cpp's emitter sampling, emitters/area.cpp, emitter.cpp,
+//     bsdf.cpp: 400 Cornell-box paths bit for bit (Embree's calls restated around the same brute-force intersector)
+// UNPINNED (restated from the cited lines, checked by known-answer tests only): volpath.cpp and aov.cpp, the BSDF plugins
+// other than diffuse (their sources are stale-API and compile with no Eigen), the constant environment emitter, the
+// camera, ImageBlock::put, the srgb / srgb_d65 spectra -- and Embree's arithmetic.  Every function cites the reference file:line it follows; paths are relative to /root/reference.
 //
 // Third-party arithmetic outside the reference tree: Embree 3.12.2 (vcpkg port
 // embree3, vcpkg/ports/embree3/vcpkg.json).  Its default triangle intersector
@@ -848,7 +850,13 @@ inline float mis_weight(float pdf_a, float pdf_b) { // :127-131
     return pdf_a > 0.f ? pdf_a / (pdf_a + pdf_b) : 0.f;
 }
 
-struct PathParams { int max_depth, rr_depth; bool hide_emitter; int integrator = MSK_INTEGRATOR_PATH; };
+struct PathParams {
+    int max_depth, rr_depth; bool hide_emitter; int integrator = MSK_INTEGRATOR_PATH;
+    // path.cpp:71-72 draws `bsdf->sample(ctx, si, sampler->next1d(), sampler->next2d())`: the order of the two draws is
+    // unspecified in C++.  The determinism contract fixes it left to right (next1d first); GCC evaluates arguments right to
+    // left, so the golden vectors of the reference compiled here need the other order to be replayed (test-only switch).
+    bool draw_bsdf_samples_right_to_left = false;
+};
 
 Spec path_sample(const OScene &sc, Sampler &sampler, const Ray &ray_, const PathParams &pp, RayCounters &rc) {
     Ray ray = ray_;
@@ -881,8 +889,10 @@ Spec path_sample(const OScene &sc, Sampler &sampler, const Ray &ray_, const Path
             }
         }
         // draw order fixed left-to-right: next1d() then next2d() (unspecified in the reference, :72)
-        float s1 = sampler.next1d();
-        V2 s2    = sampler.next2d();
+        float s1;
+        V2 s2;
+        if (!pp.draw_bsdf_samples_right_to_left) { s1 = sampler.next1d(); s2 = sampler.next2d(); }
+        else { s2 = sampler.next2d(); s1 = sampler.next1d(); }
         auto [bs, bsdf_val] = bsdf_sample(sc, bsdf, si, s1, s2);
         scattered |= bs.sampled_type != (uint32_t) F_Null;
         // Output-equivalent shortcut for a failed sample (waives q5): with bsdf_val == 0 the
@@ -1600,6 +1610,23 @@ void orc_math(int which, const float *in, float *out) {
         orc_develop(film, rgba, 1);
         out[0] = rgba[0]; out[1] = rgba[1]; out[2] = rgba[2];
     }
+}
+// PathTracer::sample / VolumetricPathTracer::sample for ONE given camera ray with the sampler seeded as
+// IndependentSampler::seed(seed): the entry point the golden vectors of the compiled reference path tracer are replayed
+// through (tests/test_oracle_ref_math.py)
+int orc_sample_ray(OrcScene *s, const MskRenderDesc *rd, uint64_t seed, const float o[3], const float d[3], float mint, float maxt, const float wl[4],
+                   int bsdf_draws_right_to_left, float out[4]) {
+    if (!s || !rd) return fail("null argument");
+    PathParams pp{ rd->max_depth, rd->rr_depth, rd->hide_emitters != 0, (int) rd->integrator, bsdf_draws_right_to_left != 0 };
+    RayCounters rc;
+    Sampler sampler;
+    sampler.base_seed = rd->base_seed;
+    sampler.seed(seed);
+    Spec w; for (int i = 0; i < 4; ++i) w[i] = wl[i];
+    Ray ray{ V3(o[0], o[1], o[2]), V3(d[0], d[1], d[2]), mint, maxt, w };
+    Spec r = integrator_sample(s->sc, sampler, ray, pp, rc);
+    for (int i = 0; i < 4; ++i) out[i] = r[i];
+    return 0;
 }
 // Hit reconstruction and mesh sampling on a single mesh given as raw arrays (layouts as oracle/ref_mesh_wrap.cpp):
 // interaction out[27] = t | p | n | uv | sh_frame.s | sh_frame.t | sh_frame.n | wi | dp_du | dp_dv

@@ -154,6 +154,16 @@ class OracleScene:
         assert self.L.orc_trace_samples(self.h, C.byref(rd), ps.ctypes.data, out.ctypes.data, ps.shape[0]) == 0
         return out
 
+    def sample_ray(self, rd, seed, o, d, mint, maxt, wl, bsdf_draws_right_to_left=False):
+        """MonteCarloIntegrator::sample for one camera ray, sampler seeded with `seed` (orc_sample_ray).
+        bsdf_draws_right_to_left: draw next2d() before next1d() at path.cpp:71-72, as GCC orders the two arguments."""
+        o, d, wl = _f(o, 3), _f(d, 3), _f(wl, 4)
+        out = np.empty(4, np.float32)
+        assert self.L.orc_sample_ray(self.h, C.byref(rd), C.c_uint64(seed), o.ctypes.data_as(C.c_void_p), d.ctypes.data_as(C.c_void_p),
+                                     C.c_float(mint), C.c_float(maxt), wl.ctypes.data_as(C.c_void_p), int(bsdf_draws_right_to_left),
+                                     out.ctypes.data_as(C.c_void_p)) == 0
+        return out
+
     def texture_eval(self, sid, u, v, wl):
         wl = np.ascontiguousarray(wl, dtype=np.float32)
         out = np.empty(4, np.float32)

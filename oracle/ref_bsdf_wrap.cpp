@@ -7,16 +7,14 @@
 // TEST INFRASTRUCTURE: tools/gen_golden_ref_math.py calls ref_bsdf to produce golden sample / eval / pdf vectors.
 //
 // Not taken from the reference: the textures (a constant spectrum stands for every spectral parameter, so the BSDF
-// arithmetic is what is compared, not the spectra), and the three trivial base-class members that live in bsdf.cpp /
-// texture.cpp next to code needing the shape and the plugin manager.
+// arithmetic is what is compared, not the spectra), and the trivial Texture base-class members that live in texture.cpp
+// next to code needing the plugin manager.
 #include "msk_ref_prelude.h"
 #include <misaki/render/bsdf.h>
 #include <misaki/render/texture.h>
+#include "ref_wrap_common.h"
 
 namespace misaki {
-BSDF::BSDF(const Properties &props) : m_flags(+BSDFFlags::None), m_id(props.id()) {} // bsdf.cpp:8-9
-BSDF::~BSDF() {}
-std::string BSDF::id() const { return m_id; }
 Texture::Texture(const Properties &props) : m_id(props.id()) {}
 Texture::~Texture() {}
 float Texture::eval_1(const SceneInteraction &) const { throw 1; }
@@ -24,20 +22,9 @@ Spectrum Texture::eval(const SceneInteraction &) const { throw 1; }
 Color3 Texture::eval_3(const SceneInteraction &) const { throw 1; }
 float Texture::mean() const { throw 1; }
 
-class ConstTexture final : public Texture {
-public:
-    explicit ConstTexture(float v) : Texture(Properties()), m_value(v) {}
-    float eval_1(const SceneInteraction &) const override { return m_value; }
-    Spectrum eval(const SceneInteraction &) const override { return Spectrum::Constant(m_value); }
-    Color3 eval_3(const SceneInteraction &) const override { return Color3::Constant(m_value); }
-    float mean() const override { return m_value; }
-    std::string to_string() const override { return "ConstTexture"; }
-private:
-    float m_value;
-};
-static ref<Texture> make_const(float v) { return ref<Texture>(new ConstTexture(v)); }
 } // namespace misaki
 
+#include <bsdf.cpp>          // BSDF::BSDF, ~BSDF, id(), SceneInteraction::bsdf(ray)
 #include <bsdfs/diffuse.cpp>
 
 using namespace misaki;

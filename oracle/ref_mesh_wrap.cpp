@@ -7,32 +7,13 @@
 #include <misaki/render/interaction.h>
 #include <misaki/render/records.h>
 #include <misaki/render/mesh.h>
+#include "ref_wrap_common.h"
 #include <shape.cpp>
 #include <mesh.cpp>
 #include <records.cpp>
 #include <interaction.cpp>
 
 using namespace misaki;
-
-namespace {
-// Mesh's constructor and buffers are protected: the loader plugins (shapes/obj.cpp:137-177) fill them like this
-class RefMesh final : public Mesh {
-public:
-    RefMesh(const float *verts, uint32_t nverts, const uint32_t *tris, uint32_t ntris, bool normals, bool uvs) : Mesh(Properties()) {
-        m_vertex_size = 8; m_face_size = 3; // [px py pz nx ny nz u v], obj.cpp:139-142
-        m_normal_offset = normals ? 3 : 0; m_texcoord_offset = uvs ? 6 : 0;
-        m_vertex_count = nverts; m_face_count = ntris;
-        m_vertices = std::unique_ptr<float[]>(new float[(size_t) nverts * 8 + 1]);
-        m_faces = std::unique_ptr<uint32_t[]>(new uint32_t[(size_t) ntris * 3 + 1]);
-        memcpy(m_vertices.get(), verts, sizeof(float) * nverts * 8);
-        memcpy(m_faces.get(), tris, sizeof(uint32_t) * ntris * 3);
-        m_surface_area = 0.f; // never initialised by the reference (mesh.h:93); restated as 0 like the oracle
-        area_distr_build();
-    }
-    std::string to_string() const override { return "RefMesh"; }
-    const std::vector<float> &cdf() const { return m_area_distr.cdf(); }
-};
-} // namespace
 
 extern "C" {
 

@@ -33,6 +33,7 @@ public:
     const void *pointer(const std::string &n) const { return pointers.at(n); }
     bool bool_(const std::string &n, bool d) const { auto it = bools.find(n); return it == bools.end() ? d : it->second; }
     ref<Texture> texture(const std::string &n) const { return textures.at(n); }
+    ref<Texture> texture(const std::string &n, const ref<Texture> &d) const { auto it = textures.find(n); return it == textures.end() ? d : it->second; }
     ref<Texture> texture(const std::string &n, float d) const { auto it = textures.find(n); return it == textures.end() ? make_default(d) : it->second; }
     const std::vector<std::pair<std::string, ref<Object>>> &objects() const { return children; }
 };

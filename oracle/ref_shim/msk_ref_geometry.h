@@ -10,5 +10,6 @@ struct BoundingBox3f {
     BoundingBox3f(const Eigen::Vector3f &a, const Eigen::Vector3f &b) : pmin(a), pmax(b) {}
     void reset() { pmin = Eigen::Vector3f::Constant(1e30f); pmax = Eigen::Vector3f::Constant(-1e30f); }
     void expand(const Eigen::Vector3f &p) { pmin = pmin.cwiseMin(p); pmax = pmax.cwiseMax(p); }
+    void expand(const BoundingBox3f &b) { pmin = pmin.cwiseMin(b.pmin); pmax = pmax.cwiseMax(b.pmax); }
 };
 } // namespace misaki

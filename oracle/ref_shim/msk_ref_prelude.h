@@ -5,6 +5,7 @@
 #pragma once
 #include <cassert>
 #include <cmath>
+#include <cstdio>
 #include <cstdint>
 #include <cstring>
 #include <limits>
@@ -28,12 +29,16 @@ using Spectrum       = SpectrumArray<float, 4>;
 using Wavelength     = SpectrumArray<float, 4>;
 
 class Shape; class Emitter; class Scene; class Medium; class BSDF; class Texture; class Sampler; // fwd.h:41-60
+class Sensor; class Film; class ImageBlock; class Integrator; class ReconstructionFilter; class Mesh;
+class FileResolver {}; // fresolver.h: scene.cpp defines the global instance and its getter
 struct Ray; struct RayDifferential; struct PositionSample; struct DirectionSample; struct SceneInteraction; struct BSDFSample;
 enum MskRefLogLevel { Trace, Debug, Info, Warn, Error };
-template <typename... A> inline void msk_ref_throw(A &&...) { throw 1; }
+inline const char *msk_ref_first() { return "?"; }
+template <typename F, typename... A> inline const char *msk_ref_first(F &&f, A &&...) { return (const char *) f; }
+template <typename... A> [[noreturn]] inline void msk_ref_throw(A &&...a) { fprintf(stderr, "[ref] Throw: %s\n", msk_ref_first(a...)); throw 1; }
 template <typename... A> inline void msk_ref_log(A &&...) {}
 } // namespace misaki
-#define MSK_NOT_IMPLEMENTED(name) throw 1
+#define MSK_NOT_IMPLEMENTED(name) (fprintf(stderr, "[ref] not implemented: %s\n", name), throw 1)
 namespace fmt { template <typename... A> inline std::string format(A &&...) { return std::string(); } } // used by to_string() only
 #define Throw(...) ::misaki::msk_ref_throw(__VA_ARGS__)
 #define Log(...) ::misaki::msk_ref_log(__VA_ARGS__)

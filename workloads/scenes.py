@@ -78,6 +78,26 @@ def teapot(width=1024, height=1024, n=112):
     return sd
 
 
+CBOX_UNIFORM = [  # (mesh, reflectance, radiance or None): the Cornell box with wavelength-independent spectra
+    ("luminaire", 0.78, 12.0), ("floor", 0.73, None), ("ceiling", 0.73, None), ("back", 0.73, None),
+    ("greenwall", 0.25, None), ("redwall", 0.45, None), ("smallbox", 0.6, None), ("largebox", 0.5, None),
+]
+
+
+def cbox_uniform(width=64, height=64):
+    """The Cornell box geometry with `uniform` spectra everywhere: the scene on which the reference's own compiled
+    PathTracer::sample is compared with the oracle (tools/gen_golden_ref_math.py, tests/test_oracle_ref_math.py) --
+    constant spectra keep the comparison on the integrator / emitter / BSDF arithmetic."""
+    sd = SceneDescription(width, height, fov=49.3077, near_clip=10, far_clip=2800,
+                          to_world=lookat((278, 273, -800), (278, 273, -799), (0, 1, 0)))
+    for name, refl, rad in CBOX_UNIFORM:
+        tw = translate((0, -0.5, 0)) if name == "luminaire" else None
+        v, t, hn, hu = meshes.read_obj(ASSETS / "cbox" / "meshes" / f"cbox_{name}.obj", tw)
+        sd.add_mesh(v, t, sd.bsdf_diffuse(float(refl)), radiance=None if rad is None else sd.spectrum_uniform(float(rad)),
+                    has_normals=hn, has_uvs=hu)
+    return sd
+
+
 def checkers(width=96, height=96, n=12):
     """Textured scene for the "checkerboard" texture (textures/checkerboard.cpp): a ground quad with
     texcoords whose reflectance is a checkerboard of a colour and a NESTED checkerboard, a quad light WITHOUT
