@@ -22,6 +22,7 @@
 #include <samplers/independent.cpp> // class IndependentSampler (ditto, ref_plugins_wrap.cpp)
 #include <emitter.cpp>
 #include <emitters/area.cpp>
+#include <emitters/constant.cpp>
 #include <scene.cpp>
 #include <integrators/path.cpp>
 
@@ -120,9 +121,10 @@ struct RefPathScene {
 extern "C" {
 
 // Meshes as in MskSceneDesc (verts nverts x 8, tris ntris x 3), each with a diffuse reflectance (constant spectrum) and an
-// optional area-light radiance (constant spectrum, < 0: none); Scene::m_shapes order == the order given.
+// optional area-light radiance (constant spectrum, < 0: none); Scene::m_shapes order == the order given.  env_radiance >= 0:
+// a "constant" environment emitter after the shapes (emitters/constant.cpp).
 void *ref_path_scene_create(uint32_t nmeshes, const float *const *verts, const uint32_t *nverts, const uint32_t *const *tris, const uint32_t *ntris,
-                            const int *normals, const int *uvs, const float *reflectance, const float *radiance) {
+                            const int *normals, const int *uvs, const float *reflectance, const float *radiance, float env_radiance) {
     try {
         RefPathScene *s = new RefPathScene;
         Properties sp;
@@ -140,6 +142,11 @@ void *ref_path_scene_create(uint32_t nmeshes, const float *const *verts, const u
             RefMesh *m = new RefMesh(verts[i], nverts[i], tris[i], ntris[i], normals[i] != 0, uvs[i] != 0, mp);
             s->meshes.push_back(m);
             sp.children.push_back({ "_arg_" + std::to_string(i), ref<Object>(m) });
+        }
+        if (env_radiance >= 0.f) {
+            Properties ep;
+            ep.textures["radiance"] = make_const(env_radiance);
+            sp.children.push_back({ "_arg_env", ref<Object>(new ConstantBackgroundEmitter(ep)) });
         }
         s->scene = new RefScene(sp);
         s->tracer = new PathTracer(Properties());

@@ -204,28 +204,33 @@ def main():
     # PathTracer::sample itself (oracle/ref_path_wrap.cpp) on the Cornell box with uniform spectra
     from oracle import pyoracle
     from workloads import scenes
-    sd = scenes.cbox_uniform(64, 64)
-    nm = len(sd.meshes)
-    vptr = (C.c_void_p * nm)(*[m["verts"].ctypes.data for m in sd.meshes])
-    tptr = (C.c_void_p * nm)(*[m["tris"].ctypes.data for m in sd.meshes])
-    nv = (C.c_uint32 * nm)(*[m["verts"].shape[0] for m in sd.meshes]); nt = (C.c_uint32 * nm)(*[m["tris"].shape[0] for m in sd.meshes])
-    hn = (C.c_int * nm)(*[int(m["has_normals"]) for m in sd.meshes]); hu = (C.c_int * nm)(*[int(m["has_uvs"]) for m in sd.meshes])
-    refl = (C.c_float * nm)(*[r for _, r, _ in scenes.CBOX_UNIFORM]); rad = (C.c_float * nm)(*[-1.0 if e is None else e for _, _, e in scenes.CBOX_UNIFORM])
     L.ref_path_scene_create.restype = C.c_void_p
-    handle = L.ref_path_scene_create(nm, vptr, nv, tptr, nt, hn, hu, refl, rad)
-    assert handle
-    n = 400
-    smp = np.stack([rng.uniform(0, 64, n), rng.uniform(0, 64, n), rng.random(n)], axis=1).astype(f32)
-    rays = pyoracle.OracleScene(sd).camera_rays(smp)  # camera rays are INPUT here (perspective.cpp is not part of this build)
-    g["path_sample"] = []
-    for i in range(n):
-        wl, _ = pyoracle.sample_wavelength(float(smp[i, 2]))
-        out = np.empty(4, f32)
-        r = rays[i]
-        assert L.ref_path_sample(C.c_void_p(handle), C.c_uint64(1000 + i), fp(r["o"]), fp(r["d"]), C.c_float(r["tmin"]), C.c_float(r["tmax"]), fp(wl), fp(out)) == 0
-        g["path_sample"].append({"seed": 1000 + i, "o": bits(r["o"]), "d": bits(r["d"]), "t": bits([r["tmin"], r["tmax"]]), "wl": bits(wl), "out": bits(out)})
-    nz = sum(1 for c in g["path_sample"] if any(F for F in np.array(c["out"], np.uint32).view(f32)))
-    print(f"path_sample: {nz} of {n} paths returned radiance")
+
+    def path_vectors(sd, params, env, n, seed0):
+        nm = len(sd.meshes)
+        vv = [np.ascontiguousarray(m["verts"], f32) for m in sd.meshes]; tt = [np.ascontiguousarray(m["tris"], np.uint32) for m in sd.meshes]
+        vptr = (C.c_void_p * nm)(*[a.ctypes.data for a in vv]); tptr = (C.c_void_p * nm)(*[a.ctypes.data for a in tt])
+        nv = (C.c_uint32 * nm)(*[a.shape[0] for a in vv]); nt = (C.c_uint32 * nm)(*[a.shape[0] for a in tt])
+        hn = (C.c_int * nm)(*[int(m["has_normals"]) for m in sd.meshes]); hu = (C.c_int * nm)(*[int(m["has_uvs"]) for m in sd.meshes])
+        refl = (C.c_float * nm)(*[r for r, _ in params]); rad = (C.c_float * nm)(*[-1.0 if e is None else e for _, e in params])
+        handle = L.ref_path_scene_create(nm, vptr, nv, tptr, nt, hn, hu, refl, rad, C.c_float(env))
+        assert handle
+        smp = np.stack([rng.uniform(0, sd.width, n), rng.uniform(0, sd.height, n), rng.random(n)], axis=1).astype(f32)
+        rays = pyoracle.OracleScene(sd).camera_rays(smp)  # camera rays are INPUT here (perspective.cpp is not part of this build)
+        out_list = []
+        for i in range(n):
+            wl, _ = pyoracle.sample_wavelength(float(smp[i, 2]))
+            out = np.empty(4, f32)
+            r = rays[i]
+            assert L.ref_path_sample(C.c_void_p(handle), C.c_uint64(seed0 + i), fp(r["o"]), fp(r["d"]), C.c_float(r["tmin"]), C.c_float(r["tmax"]), fp(wl), fp(out)) == 0
+            out_list.append({"seed": seed0 + i, "o": bits(r["o"]), "d": bits(r["d"]), "t": bits([r["tmin"], r["tmax"]]), "wl": bits(wl), "out": bits(out)})
+        nz = sum(1 for c in out_list if np.array(c["out"], np.uint32).view(f32).any())
+        print(f"path_sample: {nz} of {n} paths returned radiance")
+        return out_list
+
+    g["path_sample"] = path_vectors(scenes.cbox_uniform(64, 64), [(r, e) for _, r, e in scenes.CBOX_UNIFORM], -1.0, 400, 1000)
+    sd2, params2 = scenes.open_uniform(64, 64)
+    g["path_sample_env"] = path_vectors(sd2, params2, scenes.OPEN_UNIFORM_ENV, 400, 5000)
 
     OUT.write_text(json.dumps(g, separators=(",", ":")))
     print(f"wrote {OUT} ({OUT.stat().st_size} bytes): " + ", ".join(f"{k}={len(v)}" for k, v in g.items() if isinstance(v, list)))

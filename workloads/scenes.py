@@ -98,6 +98,27 @@ def cbox_uniform(width=64, height=64):
     return sd
 
 
+OPEN_UNIFORM_ENV = 0.6
+
+
+def open_uniform(width=64, height=64):
+    """An open scene with uniform spectra for the second pinned path-tracer comparison: ground quad, a small blob with
+    vertex normals, a quad light and a `constant` environment (two emitters: uniform light selection, scene.cpp:76-87;
+    escaped BSDF rays: the stale-pdf environment quirk q4 / q8 of path.cpp:90-108).  Returns (scene, per-mesh
+    (reflectance, radiance or None))."""
+    sd = SceneDescription(width, height, fov=40.0, near_clip=0.1, far_clip=100.0,
+                          to_world=lookat((0.0, 2.2, -4.5), (0.0, 0.7, 0.0), (0, 1, 0)))
+    params = []
+    gv, gt = meshes.quad((-4, 0, -4), (-4, 0, 4), (4, 0, 4), (4, 0, -4))
+    sd.add_mesh(gv, gt, sd.bsdf_diffuse(0.55)); params.append((0.55, None))
+    v, t = meshes.cube_sphere(4, seed=9, octaves=2, amplitude=0.08, radius=0.8, center=(0, 0.9, 0), normals=True)
+    sd.add_mesh(v, t, sd.bsdf_diffuse(0.7), has_normals=True); params.append((0.7, None))
+    lv, lt = meshes.quad((-1, 3.5, -1), (1, 3.5, -1), (1, 3.5, 1), (-1, 3.5, 1))
+    sd.add_mesh(lv, lt, sd.bsdf_diffuse(0.5), radiance=sd.spectrum_uniform(9.0)); params.append((0.5, 9.0))
+    sd.add_constant_environment(sd.spectrum_uniform(OPEN_UNIFORM_ENV))
+    return sd, params
+
+
 def checkers(width=96, height=96, n=12):
     """Textured scene for the "checkerboard" texture (textures/checkerboard.cpp): a ground quad with
     texcoords whose reflectance is a checkerboard of a colour and a NESTED checkerboard, a quad light WITHOUT
