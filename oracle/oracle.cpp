@@ -1628,6 +1628,21 @@ int orc_sample_ray(OrcScene *s, const MskRenderDesc *rd, uint64_t seed, const fl
     for (int i = 0; i < 4; ++i) out[i] = r[i];
     return 0;
 }
+// AOVIntegrator::sample for one camera ray (same conventions as orc_sample_ray); out_aovs: the channels of `types` in order
+int orc_aov_sample_ray(OrcScene *s, const MskRenderDesc *rd, uint64_t seed, const float o[3], const float d[3], float mint, float maxt,
+                       const float wl[4], int bsdf_draws_right_to_left, const int32_t *types, uint32_t ntypes, float *out_aovs, float out[4]) {
+    if (!s || !rd || (ntypes && !types)) return fail("null argument");
+    PathParams pp{ rd->max_depth, rd->rr_depth, rd->hide_emitters != 0, (int) rd->integrator, bsdf_draws_right_to_left != 0 };
+    RayCounters rc;
+    Sampler sampler;
+    sampler.base_seed = rd->base_seed;
+    sampler.seed(seed);
+    Spec w; for (int i = 0; i < 4; ++i) w[i] = wl[i];
+    Ray ray{ V3(o[0], o[1], o[2]), V3(d[0], d[1], d[2]), mint, maxt, w };
+    Spec r = aov_sample(s->sc, sampler, ray, pp, rc, types, ntypes, out_aovs);
+    for (int i = 0; i < 4; ++i) out[i] = r[i];
+    return 0;
+}
 // Hit reconstruction and mesh sampling on a single mesh given as raw arrays (layouts as oracle/ref_mesh_wrap.cpp):
 // interaction out[27] = t | p | n | uv | sh_frame.s | sh_frame.t | sh_frame.n | wi | dp_du | dp_dv
 static OMesh make_single_mesh(const float *verts, uint32_t nverts, const uint32_t *tris, uint32_t ntris, int normals, int uvs) {

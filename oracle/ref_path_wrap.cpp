@@ -25,6 +25,7 @@
 #include <emitters/constant.cpp>
 #include <scene.cpp>
 #include <integrators/path.cpp>
+#include <integrators/aov.cpp>
 
 namespace misaki {
 
@@ -163,6 +164,25 @@ int ref_path_sample(void *handle, uint64_t seed, const float o[3], const float d
         Ray ray(Eigen::Vector3f(o[0], o[1], o[2]), Eigen::Vector3f(d[0], d[1], d[2]), mint, maxt, 0.f, Wavelength(wl[0], wl[1], wl[2], wl[3]));
         Spectrum r = s->tracer->sample(s->scene, &sampler, RayDifferential(ray), nullptr, nullptr);
         for (int i = 0; i < 4; ++i) out[i] = r.coeff(i);
+        return 0;
+    } catch (...) { return -2; }
+}
+
+// AOVIntegrator::sample (integrators/aov.cpp:87-144) with aovs = "d:depth p:position u:uv g:geo_normal s:sh_normal" and
+// the path tracer nested: out = 12 geometry channels + R, G, B, A of the nested integrator + the 4 returned radiance values
+int ref_aov_sample(void *handle, uint64_t seed, const float o[3], const float d[3], float mint, float maxt, const float wl[4], float out[20]) {
+    try {
+        RefPathScene *s = (RefPathScene *) handle;
+        Properties p;
+        p.strings["aovs"] = "d:depth p:position u:uv g:geo_normal s:sh_normal";
+        p.children.push_back({ "img", ref<Object>(s->tracer) });
+        AOVIntegrator aov(p);
+        IndependentSampler sampler;
+        sampler.seed(seed);
+        Ray ray(Eigen::Vector3f(o[0], o[1], o[2]), Eigen::Vector3f(d[0], d[1], d[2]), mint, maxt, 0.f, Wavelength(wl[0], wl[1], wl[2], wl[3]));
+        for (int i = 0; i < 20; ++i) out[i] = 0.f;
+        Spectrum r = aov.sample(s->scene, &sampler, RayDifferential(ray), nullptr, out);
+        for (int i = 0; i < 4; ++i) out[16 + i] = r.coeff(i);
         return 0;
     } catch (...) { return -2; }
 }

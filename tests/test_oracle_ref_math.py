@@ -210,3 +210,30 @@ def test_path_tracer_sample_on_the_cornell_box():
             nonzero += bool(np.any(got != 0))
         # (44 % of the Cornell-box camera rays miss the box: a square film around it); the comparison is not vacuous
         assert nonzero > floor * len(GOLDEN[key]), (key, nonzero)
+
+
+def test_aov_integrator_sample():
+    """AOVIntegrator::sample ITSELF (integrators/aov.cpp:87-144: depth, position, uv, geometric / shading normal and the
+    nested path tracer's RGBA through spectrum_to_xyz + xyz_to_srgb), compiled like the path tracer.  On a miss the
+    reference reads position / normals / uv of an uninitialised interaction; the oracle (and the GPU) write zeros there,
+    so those 11 channels are compared on hits only."""
+    from misaki_render_b200 import capi
+    from workloads import scenes
+    osc = po.OracleScene(scenes.open_uniform(64, 64)[0])
+    rd = capi.render_desc(spp=1, max_depth=-1, rr_depth=5)
+    types = np.array([capi.AOV_DEPTH, capi.AOV_POSITION, capi.AOV_UV, capi.AOV_GEO_NORMAL, capi.AOV_SH_NORMAL, capi.AOV_INTEGRATOR_RGBA], np.int32)
+    hits = 0
+    for c in GOLDEN["aov_sample"]:
+        tmin, tmax = F(c["t"])
+        o, d, wl = F(c["o"]).copy(), F(c["d"]).copy(), F(c["wl"]).copy()
+        aovs, res = np.zeros(16, f32), np.zeros(4, f32)
+        assert po.lib().orc_aov_sample_ray(osc.h, C.byref(rd), C.c_uint64(c["seed"]), o.ctypes.data_as(C.c_void_p), d.ctypes.data_as(C.c_void_p),
+                                           C.c_float(float(tmin)), C.c_float(float(tmax)), wl.ctypes.data_as(C.c_void_p), 1,
+                                           types.ctypes.data_as(C.c_void_p), len(types), aovs.ctypes.data_as(C.c_void_p), res.ctypes.data_as(C.c_void_p)) == 0
+        want = F(c["out"])
+        hit = want[0] != 0
+        hits += bool(hit)
+        sel = slice(0, 16) if hit else [0, 12, 13, 14, 15]
+        same_bits(aovs[sel], [c["out"][i] for i in (range(16) if hit else sel)], f"AOVIntegrator::sample aovs seed={c['seed']}")
+        same_bits(res, c["out"][16:], "AOVIntegrator::sample result")
+    assert hits > 0.5 * len(GOLDEN["aov_sample"])

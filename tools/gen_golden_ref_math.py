@@ -206,7 +206,7 @@ def main():
     from workloads import scenes
     L.ref_path_scene_create.restype = C.c_void_p
 
-    def path_vectors(sd, params, env, n, seed0):
+    def path_vectors(sd, params, env, n, seed0, aov=False):
         nm = len(sd.meshes)
         vv = [np.ascontiguousarray(m["verts"], f32) for m in sd.meshes]; tt = [np.ascontiguousarray(m["tris"], np.uint32) for m in sd.meshes]
         vptr = (C.c_void_p * nm)(*[a.ctypes.data for a in vv]); tptr = (C.c_void_p * nm)(*[a.ctypes.data for a in tt])
@@ -220,9 +220,10 @@ def main():
         out_list = []
         for i in range(n):
             wl, _ = pyoracle.sample_wavelength(float(smp[i, 2]))
-            out = np.empty(4, f32)
+            out = np.empty(20 if aov else 4, f32)
             r = rays[i]
-            assert L.ref_path_sample(C.c_void_p(handle), C.c_uint64(seed0 + i), fp(r["o"]), fp(r["d"]), C.c_float(r["tmin"]), C.c_float(r["tmax"]), fp(wl), fp(out)) == 0
+            fn = L.ref_aov_sample if aov else L.ref_path_sample
+            assert fn(C.c_void_p(handle), C.c_uint64(seed0 + i), fp(r["o"]), fp(r["d"]), C.c_float(r["tmin"]), C.c_float(r["tmax"]), fp(wl), fp(out)) == 0
             out_list.append({"seed": seed0 + i, "o": bits(r["o"]), "d": bits(r["d"]), "t": bits([r["tmin"], r["tmax"]]), "wl": bits(wl), "out": bits(out)})
         nz = sum(1 for c in out_list if np.array(c["out"], np.uint32).view(f32).any())
         print(f"path_sample: {nz} of {n} paths returned radiance")
@@ -231,6 +232,8 @@ def main():
     g["path_sample"] = path_vectors(scenes.cbox_uniform(64, 64), [(r, e) for _, r, e in scenes.CBOX_UNIFORM], -1.0, 400, 1000)
     sd2, params2 = scenes.open_uniform(64, 64)
     g["path_sample_env"] = path_vectors(sd2, params2, scenes.OPEN_UNIFORM_ENV, 400, 5000)
+    # AOVIntegrator::sample (integrators/aov.cpp) with the path tracer nested, same open scene
+    g["aov_sample"] = path_vectors(sd2, params2, scenes.OPEN_UNIFORM_ENV, 200, 9000, aov=True)
 
     OUT.write_text(json.dumps(g, separators=(",", ":")))
     print(f"wrote {OUT} ({OUT.stat().st_size} bytes): " + ", ".join(f"{k}={len(v)}" for k, v in g.items() if isinstance(v, list)))
