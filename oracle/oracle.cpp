@@ -20,10 +20,12 @@
 //     mesh.cpp + shape.cpp + records.cpp + interaction.cpp (hit reconstruction, area distribution, position / direct
 //     sampling) (same tests)
 //   * PathTracer::sample itself (integrators/path.cpp) with scene.cpp's emitter sampling, emitters/area.cpp, emitter.cpp,
-//     bsdf.cpp: 400 Cornell-box paths bit for bit (Embree's calls restated around the same brute-force intersector)
-// UNPINNED (restated from the cited lines, checked by known-answer tests only): volpath.cpp and aov.cpp, the BSDF plugins
-// other than diffuse (their sources are stale-API and compile with no Eigen), the constant environment emitter, the
-// camera, ImageBlock::put, the srgb / srgb_d65 spectra -- and Embree's arithmetic.  Every function cites the reference file:line it follows; paths are relative to /root/reference.
+//     emitters/constant.cpp, bsdf.cpp: 800 paths through two scenes bit for bit (Embree's calls restated around the same
+//     brute-force intersector); AOVIntegrator::sample (integrators/aov.cpp); imageblock.cpp (splat, block merge, spiral):
+//     whole films equal by SHA-256
+// UNPINNED (restated from the cited lines, checked by known-answer tests only): volpath.cpp, the BSDF plugins other than
+// diffuse (their sources are stale-API and compile with no Eigen), the camera, HDRFilm::image, the srgb / srgb_d65 plugin
+// classes (their ingredients are pinned) -- and Embree's arithmetic.  Every function cites the reference file:line it follows; paths are relative to /root/reference.
 //
 // Third-party arithmetic outside the reference tree: Embree 3.12.2 (vcpkg port
 // embree3, vcpkg/ports/embree3/vcpkg.json).  Its default triangle intersector
@@ -1626,6 +1628,32 @@ int orc_sample_ray(OrcScene *s, const MskRenderDesc *rd, uint64_t seed, const fl
     Ray ray{ V3(o[0], o[1], o[2]), V3(d[0], d[1], d[2]), mint, maxt, w };
     Spec r = integrator_sample(s->sc, sampler, ray, pp, rc);
     for (int i = 0; i < 4; ++i) out[i] = r[i];
+    return 0;
+}
+// The film accumulation in isolation, driven as SamplingIntegrator::render drives it (layouts as oracle/ref_film_wrap.cpp):
+// spiral block order, per block the filtered splat of the samples whose pixel lies in it, then the merge into the film
+int orc_film_accumulate(float stddev, int W, int H, int nch, int block_size, const float *samples, size_t n, float *film_out, int *block_order) {
+    MskCamera cam{};
+    cam.width = (uint32_t) W; cam.height = (uint32_t) H;
+    orc_gaussian_filter(stddev, &cam.filter_radius, cam.filter_table);
+    const int border = (int) std::ceil(cam.filter_radius - .5f);
+    std::fill(film_out, film_out + (size_t) W * H * nch, 0.f);
+    std::vector<BlockDesc> blocks = spiral_blocks(W, H, block_size);
+    const size_t stride = 2 + (size_t) nch;
+    for (size_t bi = 0; bi < blocks.size(); ++bi) {
+        const BlockDesc &bd = blocks[bi];
+        if (block_order) { block_order[4 * bi] = bd.ox; block_order[4 * bi + 1] = bd.oy; block_order[4 * bi + 2] = bd.sx; block_order[4 * bi + 3] = bd.sy; }
+        Block b;
+        b.ox = bd.ox; b.oy = bd.oy; b.sx = bd.sx; b.sy = bd.sy; b.border = border; b.nch = nch;
+        b.data.assign((size_t) (bd.sx + 2 * border) * (bd.sy + 2 * border) * nch, 0.f);
+        for (size_t i = 0; i < n; ++i) {
+            const float *sm = samples + i * stride;
+            int px = (int) std::floor(sm[0]), py = (int) std::floor(sm[1]);
+            if (px < bd.ox || py < bd.oy || px >= bd.ox + bd.sx || py >= bd.oy + bd.sy) continue;
+            block_put(b, cam, V2{ sm[0], sm[1] }, sm + 2);
+        }
+        film_put(film_out, W, H, b);
+    }
     return 0;
 }
 // AOVIntegrator::sample for one camera ray (same conventions as orc_sample_ray); out_aovs: the channels of `types` in order

@@ -34,6 +34,7 @@ void orc_fresnel_conductor(float cos_theta_i, const float eta[4], const float k[
 void orc_srgb_model_eval(const float c[3], const float wl[4], float out[4]);
 int  orc_sample_ray(OrcScene *s, const MskRenderDesc *rd, uint64_t seed, const float o[3], const float d[3], float mint, float maxt,
                     const float wl[4], int bsdf_draws_right_to_left, float out[4]);
+int  orc_film_accumulate(float stddev, int W, int H, int nch, int block_size, const float *samples, size_t n, float *film_out, int *block_order);
 int  orc_aov_sample_ray(OrcScene *s, const MskRenderDesc *rd, uint64_t seed, const float o[3], const float d[3], float mint, float maxt,
                         const float wl[4], int bsdf_draws_right_to_left, const int32_t *types, uint32_t ntypes, float *out_aovs, float out[4]);
 void orc_mesh_interaction(const float *verts, uint32_t nverts, const uint32_t *tris, uint32_t ntris, int normals, int uvs, uint32_t prim,

@@ -237,3 +237,24 @@ def test_aov_integrator_sample():
         same_bits(aovs[sel], [c["out"][i] for i in (range(16) if hit else sel)], f"AOVIntegrator::sample aovs seed={c['seed']}")
         same_bits(res, c["out"][16:], "AOVIntegrator::sample result")
     assert hits > 0.5 * len(GOLDEN["aov_sample"])
+
+
+def test_film_accumulation():
+    """src/librender/imageblock.cpp itself: ImageBlock::put(pos, value) (the filtered splat with its block-relative
+    position arithmetic), ImageBlock::put(block) / accumulate_2d (the merge of the padded block into the film) and
+    BlockGenerator (the spiral), driven as SamplingIntegrator::render + HDRFilm drive them, on films whose size is no
+    multiple of the block size.  The whole film must match bit for bit (SHA-256) -- this is the film the GPU gather is
+    compared with."""
+    import hashlib
+    from workloads import scenes
+    for c in GOLDEN["film"]:
+        W, H, nch = c["W"], c["H"], 5
+        smp = scenes.film_samples(W, H, c["n"], c["sample_seed"])
+        assert hashlib.sha256(smp.tobytes()).hexdigest() == c["samples_sha256"], "the seeded samples changed (numpy Generator stream?)"
+        nb = len(c["order"]) // 4
+        film = np.empty((H, W, nch), f32); order = np.empty((nb, 4), np.int32)
+        assert po.lib().orc_film_accumulate(C.c_float(float(F(c["stddev"])[0])), W, H, nch, c["block_size"], smp.ctypes.data_as(C.c_void_p),
+                                            C.c_size_t(c["n"]), film.ctypes.data_as(C.c_void_p), order.ctypes.data_as(C.c_void_p)) == 0
+        assert [int(v) for v in order.reshape(-1)] == c["order"], "BlockGenerator spiral order"
+        same_bits(np.stack([film[y, x] for y, x in c["probes"]]), c["probe_values"], "film probe pixels")
+        assert hashlib.sha256(film.tobytes()).hexdigest() == c["sha256"], f"film {W}x{H}"

@@ -235,6 +235,20 @@ def main():
     # AOVIntegrator::sample (integrators/aov.cpp) with the path tracer nested, same open scene
     g["aov_sample"] = path_vectors(sd2, params2, scenes.OPEN_UNIFORM_ENV, 200, 9000, aov=True)
 
+    # src/librender/imageblock.cpp (oracle/ref_film_wrap.cpp): filtered splat, block merge, spiral order.  The film is
+    # stored as a SHA-256 of its bytes plus a few probe pixels (a 70 x 45 x 5 film would be 60 KB of JSON).
+    import hashlib
+    g["film"] = []
+    for k, (W, H, bs, stddev, n) in enumerate([(70, 45, 32, 0.5, 3000), (33, 64, 32, 0.5, 2000), (40, 40, 16, 0.8, 2000)]):
+        nch = 5
+        smp = scenes.film_samples(W, H, n, 777 + k)
+        nb = int(np.ceil(W / bs) * np.ceil(H / bs))
+        film = np.empty((H, W, nch), f32); order = np.empty((nb, 4), np.int32)
+        assert L.ref_film_accumulate(C.c_float(stddev), W, H, nch, bs, fp(smp), C.c_size_t(n), fp(film), order.ctypes.data_as(C.c_void_p)) == 0
+        probes = [[int(y), int(x)] for y, x in zip(rng.integers(0, H, 12), rng.integers(0, W, 12))] + [[0, 0], [H - 1, W - 1], [31, 31], [32, 32 if W > 32 else W - 1]]
+        g["film"].append({"W": W, "H": H, "block_size": bs, "stddev": bits([stddev]), "sample_seed": 777 + k, "samples_sha256": hashlib.sha256(smp.tobytes()).hexdigest(), "n": n, "sha256": hashlib.sha256(film.tobytes()).hexdigest(),
+                          "order": [int(v) for v in order.reshape(-1)], "probes": probes, "probe_values": bits(np.stack([film[y, x] for y, x in probes]))})
+
     OUT.write_text(json.dumps(g, separators=(",", ":")))
     print(f"wrote {OUT} ({OUT.stat().st_size} bytes): " + ", ".join(f"{k}={len(v)}" for k, v in g.items() if isinstance(v, list)))
 

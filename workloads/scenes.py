@@ -119,6 +119,16 @@ def open_uniform(width=64, height=64):
     return sd, params
 
 
+def film_samples(W, H, n, seed, nch=5):
+    """Seeded (position, channel values) samples for the pinned film-accumulation comparison (shared by
+    tools/gen_golden_ref_math.py and tests/test_oracle_ref_math.py so the fixture only stores hashes and probe pixels).
+    The first eight positions sit on film corners, block corners (32) and pixel centres."""
+    rng = np.random.default_rng(seed)
+    smp = np.concatenate([rng.uniform(0, W, (n, 1)), rng.uniform(0, H, (n, 1)), rng.uniform(0, 2, (n, nch))], axis=1).astype(f32)
+    smp[:8, :2] = [[0, 0], [W - 1e-3, H - 1e-3], [0.5, 0.5], [31.999, 31.999], [32, 32], [W / 2, 0], [0, H / 2], [W - 0.5, 0.25]]
+    return np.ascontiguousarray(smp, dtype=f32)
+
+
 def checkers(width=96, height=96, n=12):
     """Textured scene for the "checkerboard" texture (textures/checkerboard.cpp): a ground quad with
     texcoords whose reflectance is a checkerboard of a colour and a NESTED checkerboard, a quad light WITHOUT
