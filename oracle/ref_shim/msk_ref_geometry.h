@@ -5,5 +5,10 @@
 #include <Eigen/Core>
 #include <misaki/core/bbox.h>
 namespace misaki {
-struct Transform4f { Transform4f() {} };
+struct Transform4f { // identity only: the pinned loaders and shapes are given world-space data
+    Transform4f() {}
+    Eigen::Vector3f apply_point(const Eigen::Vector3f &p) const { return p; }
+    Eigen::Vector3f apply_normal(const Eigen::Vector3f &n) const { return n; }
+    Eigen::Vector3f apply_vector(const Eigen::Vector3f &v) const { return v; }
+};
 } // namespace misaki

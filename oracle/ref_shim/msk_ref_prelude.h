@@ -8,11 +8,13 @@
 #include <cstdio>
 #include <cstdint>
 #include <cstring>
+#include <filesystem>
 #include <limits>
 #include <mutex>
 #include <memory>
 #include <string>
 #include <tuple>
+#include <unordered_map>
 namespace std { using ::sinf; using ::cosf; } // mathutils.h:68-69 calls std::sinf / std::cosf, which libstdc++ does not declare
 #include <misaki/core/platform.h>
 #include <misaki/core/mathutils.h>
@@ -31,7 +33,12 @@ using Wavelength     = SpectrumArray<float, 4>;
 
 class Shape; class Emitter; class Scene; class Medium; class BSDF; class Texture; class Sampler; // fwd.h:41-60
 class Sensor; class Film; class ImageBlock; class Integrator; class ReconstructionFilter; class Mesh;
-class FileResolver {}; // fresolver.h: scene.cpp defines the global instance and its getter
+namespace fs = std::filesystem; // fwd.h:39
+class FileResolver { // fresolver.h: no search path in the pinned build; scene.cpp defines the global instance and its getter
+public:
+    fs::path resolve(const fs::path &p) const { return p; }
+};
+FileResolver *get_file_resolver();
 struct Ray; struct RayDifferential; struct PositionSample; struct DirectionSample; struct SceneInteraction; struct BSDFSample;
 enum MskRefLogLevel { Trace, Debug, Info, Warn, Error };
 inline const char *msk_ref_first() { return "?"; }

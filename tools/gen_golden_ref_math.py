@@ -249,6 +249,30 @@ def main():
         g["film"].append({"W": W, "H": H, "block_size": bs, "stddev": bits([stddev]), "sample_seed": 777 + k, "samples_sha256": hashlib.sha256(smp.tobytes()).hexdigest(), "n": n, "sha256": hashlib.sha256(film.tobytes()).hexdigest(),
                           "order": [int(v) for v in order.reshape(-1)], "probes": probes, "probe_values": bits(np.stack([film[y, x] for y, x in probes]))})
 
+    # src/librender/shapes/obj.cpp (oracle/ref_obj_wrap.cpp): what the reference's own loader makes of OBJ files -- the
+    # Cornell-box meshes of this repository and a synthetic file with quads, shared / split vertices, normals, texcoords
+    import tempfile
+    L.ref_obj_load.restype = C.c_void_p
+    synthetic = ("v 0 0 0\nv 1 0 0\nv 1 1 0\nv 0 1 0\nv 0.5 0.5 1\nvt 0 0\nvt 1 0\nvt 1 1\nvt 0 1\nvt 0.5 0.25\nvn 0 0 1\nvn 0 1 0\nvn 1 2 3\n"
+                 "f 1/1/1 2/2/1 3/3/1 4/4/1\nf 1/1/2 2/2/2 5/5/3\nf 2/2/1 3/3/1 5/5/3\nf 3/3 4/4 5/5\nf 4//2 1//2 5//3\n")
+    g["obj"] = []
+    files = [("assets/cbox/meshes/cbox_%s.obj" % n, None) for n, _, _ in scenes.CBOX_UNIFORM] + [("synthetic.obj", synthetic)]
+    for rel, text in files:
+        for flip in (1, 0):
+            if text is None:
+                path = str(ROOT / rel)
+            else:
+                tf = tempfile.NamedTemporaryFile("w", suffix=".obj", delete=False); tf.write(text); tf.close(); path = tf.name
+            h = L.ref_obj_load(path.encode(), flip)
+            assert h, rel
+            counts = (C.c_uint32 * 4)()
+            L.ref_obj_get(C.c_void_p(h), counts, None, None)
+            v = np.zeros((counts[0], 8), f32); t = np.zeros((counts[1], 3), np.uint32)
+            L.ref_obj_get(C.c_void_p(h), counts, fp(v), t.ctypes.data_as(C.c_void_p))
+            if not counts[2]: v[:, 3:6] = 0  # absent attributes are uninitialised memory in the reference
+            if not counts[3]: v[:, 6:8] = 0
+            g["obj"].append({"file": rel, "text": text, "flip": flip, "counts": [int(c) for c in counts], "verts": bits(v), "faces": [int(x) for x in t.reshape(-1)]})
+
     OUT.write_text(json.dumps(g, separators=(",", ":")))
     print(f"wrote {OUT} ({OUT.stat().st_size} bytes): " + ", ".join(f"{k}={len(v)}" for k, v in g.items() if isinstance(v, list)))
 
