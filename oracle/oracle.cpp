@@ -22,10 +22,9 @@
 //   * PathTracer::sample itself (integrators/path.cpp) with scene.cpp's emitter sampling, emitters/area.cpp, emitter.cpp,
 //     emitters/constant.cpp, bsdf.cpp: 800 paths through two scenes bit for bit (Embree's calls restated around the same
 //     brute-force intersector); AOVIntegrator::sample (integrators/aov.cpp); imageblock.cpp (splat, block merge, spiral):
-//     whole films equal by SHA-256
+//     whole films equal by SHA-256; srgb.cpp + spectra/{srgb,srgb_d65,d65}.cpp (what an <rgb> tag becomes)
 // UNPINNED (restated from the cited lines, checked by known-answer tests only): volpath.cpp, the BSDF plugins other than
-// diffuse (their sources are stale-API and compile with no Eigen), the camera, HDRFilm::image, the srgb / srgb_d65 plugin
-// classes (their ingredients are pinned) -- and Embree's arithmetic.  Every function cites the reference file:line it follows; paths are relative to /root/reference.
+// diffuse (their sources are stale-API and compile with no Eigen), the camera, HDRFilm::image -- and Embree's arithmetic.  Every function cites the reference file:line it follows; paths are relative to /root/reference.
 //
 // Third-party arithmetic outside the reference tree: Embree 3.12.2 (vcpkg port
 // embree3, vcpkg/ports/embree3/vcpkg.json).  Its default triangle intersector

@@ -15,6 +15,9 @@
 
 using namespace misaki;
 
+// for ref_spectra_wrap.cpp: regular.cpp defines a non-inline operator<<, so it can only be compiled into one translation unit
+misaki::Object *msk_ref_make_regular(const misaki::Properties &p) { return new RegularSpectrum(p); }
+
 extern "C" {
 
 // out: radius, border_size, then the 33 table entries read back through eval_discretized (rfilter.h:13-16)

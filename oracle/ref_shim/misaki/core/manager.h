@@ -1,12 +1,20 @@
-// Stand-in for include/misaki/core/manager.h: no plugin registry; a defaulted plugin instance is a null reference
-// (Shape's default "diffuse" BSDF is never evaluated by the pinned code paths).  TEST INFRASTRUCTURE.
+// Stand-in for include/misaki/core/manager.h: a plugin table filled by the wrappers (ref_spectra_wrap.cpp registers
+// "regular" and "d65"); a plugin that is not in the table yields a null reference (Shape's default "diffuse" BSDF and
+// Scene's default "path" integrator are never used by the pinned code paths).  TEST INFRASTRUCTURE.
 #pragma once
 #include "object.h"
+#include "properties.h"
+#include <functional>
+#include <map>
+#include <string>
 namespace misaki {
-class Properties;
 class InstanceManager {
 public:
     static InstanceManager *get() { static InstanceManager m; return &m; }
-    template <typename T> ref<T> create_instance(const Properties &) { return ref<T>(); }
+    std::map<std::string, std::function<Object *(const Properties &)>> table;
+    template <typename T> ref<T> create_instance(const Properties &props) {
+        auto it = table.find(props.plugin_name);
+        return it == table.end() ? ref<T>() : ref<T>(static_cast<T *>(it->second(props)));
+    }
 };
 } // namespace misaki

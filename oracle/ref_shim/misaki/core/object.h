@@ -6,8 +6,10 @@
 #include <string>
 #include <vector>
 namespace misaki {
+template <typename T> class ref;
 class Object {
 public:
+    virtual std::vector<ref<Object>> expand() const; // object.h: plugins that stand for other plugins (spectra/d65.cpp)
     virtual ~Object() {}
     virtual std::string id() const { return std::string(); }
     virtual std::string to_string() const { return "Object"; }
@@ -25,6 +27,7 @@ public:
 private:
     T *m_ptr = nullptr; // the stand-in never frees: objects live for the duration of a generator run
 };
+inline std::vector<ref<Object>> Object::expand() const { return {}; }
 template <typename T> std::ostream &operator<<(std::ostream &os, const ref<T> &r) { return os << (r.get() ? r->to_string() : std::string("null")); }
 inline std::ostream &operator<<(std::ostream &os, const Object *o) { return os << (o ? o->to_string() : std::string("null")); }
 } // namespace misaki

@@ -1,6 +1,7 @@
 // Stand-in for include/misaki/core/properties.h: a flat property set filled by the wrapper.  TEST INFRASTRUCTURE.
 #pragma once
 #include "object.h"
+#include <array>
 #include <map>
 #include <string>
 #include <utility>
@@ -18,6 +19,11 @@ public:
     std::map<std::string, bool> bools;
     std::map<std::string, long long> ints;
     std::map<std::string, const void *> pointers;
+    std::map<std::string, std::array<float, 3>> colors;
+    void set_float(const std::string &n, float v) { floats[n] = v; }
+    void set_int(const std::string &n, long long v) { ints[n] = v; }
+    void set_pointer(const std::string &n, const void *v) { pointers[n] = v; }
+    template <typename C = struct ColorTag> auto color(const std::string &n) const; // defined once Color3 is known (msk_ref_prelude.h)
     std::map<std::string, std::string> strings;
     std::map<std::string, ref<Texture>> textures;
     std::vector<std::pair<std::string, ref<Object>>> children;

@@ -7,6 +7,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstdint>
+#include <cstdlib>
 #include <cstring>
 #include <filesystem>
 #include <limits>
@@ -34,12 +35,16 @@ using Wavelength     = SpectrumArray<float, 4>;
 class Shape; class Emitter; class Scene; class Medium; class BSDF; class Texture; class Sampler; // fwd.h:41-60
 class Sensor; class Film; class ImageBlock; class Integrator; class ReconstructionFilter; class Mesh;
 namespace fs = std::filesystem; // fwd.h:39
-class FileResolver { // fresolver.h: no search path in the pinned build; scene.cpp defines the global instance and its getter
+class FileResolver { // fresolver.h: one search directory, MSK_REF_DATA_ROOT (for data/srgb.coeff); scene.cpp defines the global instance
 public:
-    fs::path resolve(const fs::path &p) const { return p; }
+    fs::path resolve(const fs::path &p) const {
+        const char *root = getenv("MSK_REF_DATA_ROOT");
+        return (root && p.is_relative() && fs::exists(fs::path(root) / p)) ? fs::path(root) / p : p;
+    }
 };
 FileResolver *get_file_resolver();
 struct Ray; struct RayDifferential; struct PositionSample; struct DirectionSample; struct SceneInteraction; struct BSDFSample;
+template <typename C> auto Properties::color(const std::string &n) const { const auto &c = colors.at(n); return Color3(c[0], c[1], c[2]); }
 enum MskRefLogLevel { Trace, Debug, Info, Warn, Error };
 inline const char *msk_ref_first() { return "?"; }
 template <typename F, typename... A> inline const char *msk_ref_first(F &&f, A &&...) { return (const char *) f; }

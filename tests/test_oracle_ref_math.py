@@ -284,3 +284,25 @@ def test_obj_loader_of_the_host_frontend(tmp_path):
         want = F(c["verts"]).reshape(-1, 8)
         cols = list(range(3)) + (list(range(3, 6)) if hn else []) + (list(range(6, 8)) if hu else [])
         same_bits(np.ascontiguousarray(m["verts"][:, cols]), want[:, cols].reshape(-1).view(np.uint32), f"OBJ vertices {c['file']} flip={c['flip']}")
+
+
+def test_colour_to_spectrum_plugins():
+    """What an <rgb> tag becomes (xml.cpp:269-277): the reference's own srgb.cpp (srgb_model_fetch over ext/rgb2spec and
+    the table its optimiser generated), spectra/srgb.cpp, spectra/srgb_d65.cpp (scale = 2 max(rgb), D65 table x scale / 10568)
+    and spectra/d65.cpp expanded into spectra/regular.cpp, against the scene builder's spectra evaluated by the oracle --
+    the same MskSpectrum records the product's host front-end flattens to (tests/test_host_frontend.py compares those)."""
+    from misaki_render_b200.scene import SceneDescription
+    sd = SceneDescription(8, 8)
+    ids = []
+    for c in GOLDEN["colour_spectrum"]:
+        rgb, scale = F(c["rgb"]), float(F(c["scale"])[0])
+        if c["kind"] == 0:
+            ids.append(sd.spectrum_srgb(rgb))
+        elif c["kind"] == 1:
+            ids.append(sd.spectrum_srgb_d65(rgb, scale))
+        else:
+            ids.append(sd.spectrum_d65(scale))
+    sd.add_mesh(np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0]], f32), np.array([[0, 1, 2]], np.uint32), sd.bsdf_diffuse(0.5))
+    osc = po.OracleScene(sd)
+    for c, sid in zip(GOLDEN["colour_spectrum"], ids):
+        same_bits(osc.spectrum_eval(sid, F(c["wl"])), c["out"], f"colour spectrum kind={c['kind']} rgb={F(c['rgb'])}")

@@ -273,6 +273,21 @@ def main():
             if not counts[3]: v[:, 6:8] = 0
             g["obj"].append({"file": rel, "text": text, "flip": flip, "counts": [int(c) for c in counts], "verts": bits(v), "faces": [int(x) for x in t.reshape(-1)]})
 
+    # what an <rgb> tag becomes (oracle/ref_spectra_wrap.cpp): srgb.cpp + spectra/{srgb,srgb_d65,d65}.cpp with the table
+    # data/srgb.coeff generated by the reference's own optimiser (oracle/_ref/srgb.coeff == misaki_render_b200/data/srgb.coeff)
+    import os
+    os.environ["MSK_REF_DATA_ROOT"] = str(ROOT / "misaki_render_b200")
+    g["colour_spectrum"] = []
+    for kind in (0, 1, 2):
+        for _ in range(16):
+            rgb = (rng.uniform(0, 1, 3) if kind == 0 else rng.uniform(0, 40, 3)).astype(f32)
+            if _ == 0: rgb = np.array([0.5, 0.5, 0.5], f32)
+            if _ == 1 and kind == 0: rgb = np.array([0, 0, 0], f32)  # (a black <rgb> inside an emitter throws in the reference: empty distribution)
+            scale = f32(1.0 if _ % 2 == 0 else rng.uniform(0.2, 3.0))
+            wl = rng.uniform(360, 830, 4).astype(f32)
+            assert L.ref_colour_spectrum(kind, fp(rgb), C.c_float(scale), fp(wl), fp(o4)) == 0
+            g["colour_spectrum"].append({"kind": kind, "rgb": bits(rgb), "scale": bits([scale]), "wl": bits(wl), "out": bits(o4)})
+
     OUT.write_text(json.dumps(g, separators=(",", ":")))
     print(f"wrote {OUT} ({OUT.stat().st_size} bytes): " + ", ".join(f"{k}={len(v)}" for k, v in g.items() if isinstance(v, list)))
 
