@@ -175,6 +175,16 @@ public:
         if (size < 2) Throw("ContinuousDistribution: needs at least two entries!");
         if (!(m_lambda_min < m_lambda_max)) Throw("ContinuousDistribution: invalid range!");
         m_values.assign(values, values + size);
+        // SpectrumContinuousDistribution::update (regular.cpp:31-58): trapezoid masses in double; negative entries and
+        // an all-zero table are errors (so a black <rgb> inside an emitter throws, as in the reference)
+        double interval = (double(m_lambda_max) - double(m_lambda_min)) / double(size - 1);
+        bool mass = false;
+        for (size_t i = 0; i + 1 < size; ++i) {
+            double y0 = m_values[i], y1 = m_values[i + 1];
+            if (y0 < 0. || y1 < 0.) Throw("ContinuousDistribution: entries must be non-negative!");
+            mass |= 0.5 * interval * (y0 + y1) > 0.;
+        }
+        if (!mass) Throw("ContinuousDistribution: no probability mass found!");
     }
     int describe(GpuSceneBuilder &b) const override {
         MskSpectrum s = blank_spectrum(MSK_SPEC_REGULAR);

@@ -257,6 +257,17 @@ def test_volpath_media_and_phase_plugins():
         _scene(MINIMAL.format(body="").replace('<film type="hdrfilm">', '<medium type="homogeneous"/><medium type="homogeneous"/><film type="hdrfilm">'))
 
 
+def test_regular_spectrum_validation_like_the_reference():
+    """SpectrumContinuousDistribution::update (spectra/regular.cpp:31-58): negative entries and tables without mass throw --
+    hence a black <rgb> inside an emitter (srgb_d65 -> d65 x 0 -> regular) is an error, as the compiled reference shows."""
+    black = '<emitter type="area"><rgb name="radiance" value="0 0 0"/></emitter>'
+    with pytest.raises(host_api.HostError, match="no probability mass found"):
+        _scene(MINIMAL.format(body=QUAD.format(inner=black)))
+    neg = '<bsdf type="diffuse"><spectrum name="reflectance" value="400:0.1, 500:-0.2, 600:0.4"/></bsdf>'
+    with pytest.raises(host_api.HostError, match="entries must be non-negative"):
+        _scene(MINIMAL.format(body=QUAD.format(inner=neg)))
+
+
 def test_material_plugins_and_their_parameter_checks():
     rc = ('<bsdf type="roughconductor"><string name="distribution" value="ggx"/><float name="alpha" value="0.1"/>'
           '<rgb name="eta" value="0.200438, 0.924033, 1.10221"/><rgb name="k" value="3.91295, 2.45285, 2.14219"/></bsdf>')
