@@ -23,6 +23,9 @@
 //     emitters/constant.cpp, bsdf.cpp: 800 paths through two scenes bit for bit (Embree's calls restated around the same
 //     brute-force intersector); AOVIntegrator::sample (integrators/aov.cpp); imageblock.cpp (splat, block merge, spiral):
 //     whole films equal by SHA-256; srgb.cpp + spectra/{srgb,srgb_d65,d65}.cpp (what an <rgb> tag becomes)
+//   * SamplingIntegrator::render / render_block / render_sample themselves (src/librender/integrator.cpp, serial stand-in for
+//     tbb::parallel_for, camera rays as inputs): two whole films bit for bit against render() below in its test-only
+//     ORC_RENDER_REFERENCE_SEEDING mode
 // UNPINNED (restated from the cited lines, checked by known-answer tests only): volpath.cpp, the BSDF plugins other than
 // diffuse (their sources are stale-API and compile with no Eigen), the camera, HDRFilm::image -- and Embree's arithmetic.  Every function cites the reference file:line it follows; paths are relative to /root/reference.
 //
@@ -1403,6 +1406,14 @@ static int render_impl(OrcScene *s, const MskRenderDesc *rd, const int32_t *type
     const int nch = 5 + extra;
     if (rd->clear_film) std::fill(film, film + (size_t) W * H * nch, 0.f);
     PathParams pp{ rd->max_depth, rd->rr_depth, rd->hide_emitters != 0, (int) rd->integrator };
+    // Test-only: seed the sampler the way the reference does when its tile loop runs as one task -- ONE clone seeded
+    // with PCG32_DEFAULT_STATE (IndependentSampler(), independent.cpp:11-14) whose sequence runs through every block in
+    // spiral order and is never re-seeded -- and draw the BSDF samples in GCC's argument order.  This is how
+    // the film of the compiled reference's own SamplingIntegrator::render is replayed (tests/test_oracle_ref_math.py).
+    const bool ref_seeding = (rd->flags & ORC_RENDER_REFERENCE_SEEDING) != 0;
+    if (ref_seeding) { pp.draw_bsdf_samples_right_to_left = true; nthreads = 1; }
+    Sampler ref_sampler;
+    ref_sampler.seed(PCG32_DEFAULT_STATE);
     const int border = (int) std::ceil(sc.cam.filter_radius - .5f); // rfilter.cpp:22
     auto blocks = spiral_blocks(W, H, 32);                            // imageblock.h:8, integrator.cpp:48
     std::vector<Block> done(blocks.size());
@@ -1411,8 +1422,8 @@ static int render_impl(OrcScene *s, const MskRenderDesc *rd, const int32_t *type
     auto t0 = std::chrono::steady_clock::now();
     auto worker = [&]() {
         RayCounters rc;
-        Sampler sampler;
-        sampler.base_seed = rd->base_seed;
+        Sampler own_sampler;
+        own_sampler.base_seed = rd->base_seed;
         std::vector<float> aovs((size_t) nch);
         for (;;) {
             size_t bi = next.fetch_add(1);
@@ -1427,7 +1438,8 @@ static int render_impl(OrcScene *s, const MskRenderDesc *rd, const int32_t *type
                     int gx = x + bd.ox, gy = y + bd.oy;
                     uint64_t pixel = (uint64_t) gy * W + gx;
                     for (uint32_t smp = rd->sample_begin; smp < rd->sample_end; ++smp) {
-                        sampler.seed(pixel * rd->spp + smp); // determinism contract
+                        Sampler &sampler = ref_seeding ? ref_sampler : own_sampler;
+                        if (!ref_seeding) sampler.seed(pixel * rd->spp + smp); // determinism contract
                         // render_sample, integrator.cpp:103-126
                         V2 j = sampler.next2d();
                         V2 position_sample{ float(gx) + j.x, float(gy) + j.y };

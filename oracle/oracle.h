@@ -34,6 +34,9 @@ void orc_fresnel_conductor(float cos_theta_i, const float eta[4], const float k[
 void orc_srgb_model_eval(const float c[3], const float wl[4], float out[4]);
 int  orc_sample_ray(OrcScene *s, const MskRenderDesc *rd, uint64_t seed, const float o[3], const float d[3], float mint, float maxt,
                     const float wl[4], int bsdf_draws_right_to_left, float out[4]);
+/* MskRenderDesc::flags bit understood by the oracle only (test infrastructure): reproduce the reference's sampler seeding
+ * (one sampler for the whole image, spiral block order) and GCC's argument evaluation order, see oracle.cpp render_impl */
+#define ORC_RENDER_REFERENCE_SEEDING 0x80000000u
 int  orc_film_accumulate(float stddev, int W, int H, int nch, int block_size, const float *samples, size_t n, float *film_out, int *block_order);
 int  orc_aov_sample_ray(OrcScene *s, const MskRenderDesc *rd, uint64_t seed, const float o[3], const float d[3], float mint, float maxt,
                         const float wl[4], int bsdf_draws_right_to_left, const int32_t *types, uint32_t ntypes, float *out_aovs, float out[4]);

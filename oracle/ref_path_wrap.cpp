@@ -10,8 +10,7 @@
 //     brute-force Moeller-Trumbore loop -- the SAME routine the oracle uses as its intersection ground truth -- keeping
 //     everything scene.cpp does around the Embree call (hit <=> tfar != maxt, the PreliminaryIntersection hand-over).
 //     The comparison therefore isolates the integrator / emitter / BSDF / interaction code, not the intersector.
-//   * the two trivial integrator constructors of integrator.cpp (that file needs TBB), Texture::D65 (needs the plugin
-//     manager; never reached: every emitter gets an explicit radiance)
+//   * Texture::D65 (texture.cpp needs the plugin manager; never reached: every emitter gets an explicit radiance)
 #include "ref_wrap_common.h"
 #include <misaki/render/bsdf.h>
 #include <misaki/render/emitter.h>
@@ -29,18 +28,7 @@
 
 namespace misaki {
 
-SamplingIntegrator::SamplingIntegrator(const Properties &props) : Integrator(props) { // integrator.cpp:17-23
-    m_block_size    = (uint32_t) props.int_("block_size", 32);
-    m_hide_emitters = props.bool_("hide_emitters", false);
-}
-SamplingIntegrator::~SamplingIntegrator() {}
-std::vector<std::string> SamplingIntegrator::aov_names() const { return {}; }
-bool SamplingIntegrator::render(Scene *, Sensor *) { throw 1; } // the TBB tile loop is not part of this build
-MonteCarloIntegrator::MonteCarloIntegrator(const Properties &props) : SamplingIntegrator(props) { // integrator.cpp:128-137
-    m_rr_depth  = (int) props.int_("rr_depth", 5);
-    m_max_depth = (int) props.int_("max_depth", -1);
-}
-MonteCarloIntegrator::~MonteCarloIntegrator() {}
+// (SamplingIntegrator / MonteCarloIntegrator members come from integrator.cpp itself, compiled in ref_render_wrap.cpp)
 ref<Texture> Texture::D65(float) { return make_const(1.f); }
 
 // ---- Embree stand-in (see the header comment)
@@ -103,21 +91,13 @@ bool Scene::ray_test(const Ray &ray) const { // scene.cpp:255-273
     return tfar != ray.maxt;
 }
 
-class RefScene final : public Scene {
-public:
-    explicit RefScene(const Properties &props) : Scene(props) {}
-    std::string to_string() const override { return "RefScene"; }
-};
-
 } // namespace misaki
 
 using namespace misaki;
 
-struct RefPathScene {
-    std::vector<RefMesh *> meshes;
-    RefScene *scene = nullptr;
-    PathTracer *tracer = nullptr;
-};
+#include "ref_path_scene.h"
+misaki::SamplingIntegrator *msk_ref_path_tracer(RefPathScene *s) { return s->tracer; }
+misaki::Scene *msk_ref_scene(RefPathScene *s) { return s->scene; }
 
 extern "C" {
 

@@ -1,10 +1,57 @@
-// Stand-in for include/misaki/render/sensor.h (+ film.h, imageblock.h, image.h): Scene only stores its sensor; camera rays
-// are supplied by the caller of the pinned PathTracer::sample.  TEST INFRASTRUCTURE.
+// Stand-in for include/misaki/render/sensor.h + film.h (the real ones pull image.h / OpenImageIO and transform.h): the
+// members SamplingIntegrator::render and Scene use, with the same signatures.  The camera itself (perspective.cpp) is not
+// part of the pinned build: RefSensor forwards sample_ray_differential to a callback that supplies the ray (an INPUT, as
+// in the single-path comparisons); RefFilm keeps the storage block exactly as HDRFilm does (hdrfilm.cpp:28-46).
+// TEST INFRASTRUCTURE.
 #pragma once
+#include "msk_ref_prelude.h"
 #include <misaki/core/object.h>
+#include <misaki/core/ray.h>
+#include <misaki/render/imageblock.h>
 #include <misaki/render/sampler.h>
+#include <string>
+#include <vector>
 namespace misaki {
-class Film : public Object {};
-class ImageBlock : public Object {};
-class Sensor : public Object { public: const Medium *medium() const { return nullptr; } };
+class Film : public Object {
+public:
+    Film(const Eigen::Vector2i &size, const ReconstructionFilter *filter) : m_size(size), m_filter(filter) {}
+    const Eigen::Vector2i &size() const { return m_size; }
+    const ReconstructionFilter *filter() const { return m_filter; }
+    void prepare(const std::vector<std::string> &channels) { // hdrfilm.cpp:28-39
+        m_storage = new ImageBlock(m_size, channels.size());
+        m_storage->set_offset(Eigen::Vector2i(0, 0));
+        m_storage->clear();
+    }
+    void put(const ImageBlock *block) { m_storage->put(block); } // hdrfilm.cpp:43-46
+    const ImageBlock *storage() const { return m_storage; }
+private:
+    Eigen::Vector2i m_size;
+    const ReconstructionFilter *m_filter;
+    ImageBlock *m_storage = nullptr;
+};
+class Sensor : public Object {
+public:
+    // out: o[3] d[3] mint maxt | wavelengths[4] | ray_weight[4]
+    typedef void (*RayCallback)(float wavelength_sample, float px, float py, float *out16);
+    Sensor(Film *film, Sampler *sampler, RayCallback cb) : m_film(film), m_sampler(sampler), m_cb(cb) {}
+    Film *film() { return m_film; }
+    const Film *film() const { return m_film; }
+    Sampler *sampler() { return m_sampler; }
+    const Sampler *sampler() const { return m_sampler; }
+    const Medium *medium() const { return nullptr; }
+    std::pair<RayDifferential, Spectrum> sample_ray_differential(const float wavelength_sample, const Eigen::Vector2f &sample2,
+                                                                 const Eigen::Vector2f & /*aperture sample: consumed, unused*/) const {
+        float r[16];
+        m_cb(wavelength_sample, sample2.x(), sample2.y(), r);
+        Ray ray(Eigen::Vector3f(r[0], r[1], r[2]), Eigen::Vector3f(r[3], r[4], r[5]), r[6], r[7], 0.f, Wavelength(r[8], r[9], r[10], r[11]));
+        RayDifferential rd(ray);
+        rd.wavelengths = ray.wavelengths;
+        rd.o_x = rd.o_y = ray.o; rd.d_x = rd.d_y = ray.d; // no compiled BSDF consumes differentials (bsdf.cpp:18)
+        return { rd, Spectrum(r[12], r[13], r[14], r[15]) };
+    }
+private:
+    Film *m_film;
+    Sampler *m_sampler;
+    RayCallback m_cb;
+};
 } // namespace misaki

@@ -306,3 +306,25 @@ def test_colour_to_spectrum_plugins():
     osc = po.OracleScene(sd)
     for c, sid in zip(GOLDEN["colour_spectrum"], ids):
         same_bits(osc.spectrum_eval(sid, F(c["wl"])), c["out"], f"colour spectrum kind={c['kind']} rgb={F(c['rgb'])}")
+
+
+def test_sampling_integrator_render_whole_films():
+    """SamplingIntegrator::render / render_block / render_sample THEMSELVES (src/librender/integrator.cpp): the tile loop
+    over the spiral, the order of random draws per camera sample (position 2, wavelength 1, aperture 2), the path tracer,
+    spectrum_to_xyz, the XYZAW channels, the filtered splat and the merge into the film -- the reference's own code end to
+    end, with a serial stand-in for tbb::parallel_for and the camera ray of each sample supplied as an input.  The reference
+    never seeds its sampler per pixel (one clone per TBB task), so the oracle replays the film in its test-only
+    reference-seeding mode (ORC_RENDER_REFERENCE_SEEDING); every other line is the code the GPU is compared with.
+    The whole film must match bit for bit."""
+    import hashlib
+    from misaki_render_b200 import capi
+    from workloads import scenes
+    for c in GOLDEN["render"]:
+        W, H = c["W"], c["H"]
+        sd = scenes.cbox_uniform(W, H) if c["scene"] == "cbox" else scenes.open_uniform(W, H)[0]
+        rd = capi.render_desc(spp=c["spp"], max_depth=-1, rr_depth=5)
+        rd.flags |= 0x80000000  # ORC_RENDER_REFERENCE_SEEDING (oracle.h)
+        film, _ = po.OracleScene(sd).render(rd, nthreads=1)
+        same_bits(np.stack([film[y, x] for y, x in c["probes"]]), c["probe_values"], f"render {c['scene']} probe pixels")
+        assert hashlib.sha256(np.ascontiguousarray(film, f32).tobytes()).hexdigest() == c["sha256"], f"film {c['scene']} {W}x{H}"
+        assert film[..., :3].max() > 0

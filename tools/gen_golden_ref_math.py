@@ -206,6 +206,17 @@ def main():
     from workloads import scenes
     L.ref_path_scene_create.restype = C.c_void_p
 
+    def ref_scene(sd, params, env):
+        nm = len(sd.meshes)
+        vv = [np.ascontiguousarray(m["verts"], f32) for m in sd.meshes]; tt = [np.ascontiguousarray(m["tris"], np.uint32) for m in sd.meshes]
+        vptr = (C.c_void_p * nm)(*[a.ctypes.data for a in vv]); tptr = (C.c_void_p * nm)(*[a.ctypes.data for a in tt])
+        nv = (C.c_uint32 * nm)(*[a.shape[0] for a in vv]); nt = (C.c_uint32 * nm)(*[a.shape[0] for a in tt])
+        hn = (C.c_int * nm)(*[int(m["has_normals"]) for m in sd.meshes]); hu = (C.c_int * nm)(*[int(m["has_uvs"]) for m in sd.meshes])
+        refl = (C.c_float * nm)(*[r for r, _ in params]); rad = (C.c_float * nm)(*[-1.0 if e is None else e for _, e in params])
+        handle = L.ref_path_scene_create(nm, vptr, nv, tptr, nt, hn, hu, refl, rad, C.c_float(env))
+        assert handle
+        return handle
+
     def path_vectors(sd, params, env, n, seed0, aov=False):
         nm = len(sd.meshes)
         vv = [np.ascontiguousarray(m["verts"], f32) for m in sd.meshes]; tt = [np.ascontiguousarray(m["tris"], np.uint32) for m in sd.meshes]
@@ -287,6 +298,30 @@ def main():
             wl = rng.uniform(360, 830, 4).astype(f32)
             assert L.ref_colour_spectrum(kind, fp(rgb), C.c_float(scale), fp(wl), fp(o4)) == 0
             g["colour_spectrum"].append({"kind": kind, "rgb": bits(rgb), "scale": bits([scale]), "wl": bits(wl), "out": bits(o4)})
+
+    # SamplingIntegrator::render itself (oracle/ref_render_wrap.cpp): whole films of the reference's own tile loop
+    g["render"] = []
+    CB = C.CFUNCTYPE(None, C.c_float, C.c_float, C.c_float, C.POINTER(C.c_float))
+    for (W, H, spp, which) in [(48, 40, 2, "cbox"), (40, 33, 2, "open")]:
+        if which == "cbox":
+            sd, params, env = scenes.cbox_uniform(W, H), [(r, e) for _, r, e in scenes.CBOX_UNIFORM], -1.0
+        else:
+            (sd, params), env = scenes.open_uniform(W, H), scenes.OPEN_UNIFORM_ENV
+        osc = pyoracle.OracleScene(sd)
+
+        def camera(ws, px, py, out, osc=osc):  # the camera ray of a sample is an input (perspective.cpp is not in the pinned build)
+            r = osc.camera_rays(np.array([[px, py, ws]], f32))[0]
+            wl, w = pyoracle.sample_wavelength(float(ws))
+            vals = list(r["o"]) + list(r["d"]) + [r["tmin"], r["tmax"]] + list(wl) + list(w)
+            for i, v in enumerate(vals):
+                out[i] = float(v)
+
+        film = np.empty((H, W, 5), f32)
+        assert L.ref_render(C.c_void_p(ref_scene(sd, params, env)), W, H, spp, C.c_float(0.5), CB(camera), fp(film)) == 0
+        probes = [[int(y), int(x)] for y, x in zip(rng.integers(0, H, 10), rng.integers(0, W, 10))] + [[0, 0], [H - 1, W - 1], [31, 31], [32, 32]]
+        g["render"].append({"scene": which, "W": W, "H": H, "spp": spp, "sha256": hashlib.sha256(film.tobytes()).hexdigest(), "probes": probes,
+                            "probe_values": bits(np.stack([film[y, x] for y, x in probes])), "mean": bits(film.mean(axis=(0, 1)))})
+        print(f"render {which} {W}x{H}x{spp}: mean XYZAW = {film.mean(axis=(0, 1))}")
 
     OUT.write_text(json.dumps(g, separators=(",", ":")))
     print(f"wrote {OUT} ({OUT.stat().st_size} bytes): " + ", ".join(f"{k}={len(v)}" for k, v in g.items() if isinstance(v, list)))
