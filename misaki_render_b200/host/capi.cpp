@@ -100,6 +100,12 @@ int mskh_render(MskhScene *h, const char *output_filename, MskStats *stats) {
 int mskh_develop(const float *film_xyzaw, size_t npixels, float *rgba) {
     return guarded([&] { develop_xyzaw(film_xyzaw, npixels, rgba); });
 }
+int mskh_develop_channels(const float *film, size_t npixels, size_t nchannels, float *out) {
+    return guarded([&] {
+        if (nchannels < 5) Throw("develop: expected at least the X, Y, Z, A, W channels");
+        develop_channels(film, npixels, nchannels, out);
+    });
+}
 int mskh_write_exr(const char *filename, const float *rgba, uint32_t width, uint32_t height) {
     return guarded([&] { write_exr_rgba(filename, rgba, width, height); });
 }

@@ -23,6 +23,8 @@ int  mskh_render(MskhScene *scene, const char *output_filename, MskStats *stats)
 int  mskh_registered_plugins(char *buffer, size_t size);
 /* HDRFilm::image (XYZAW -> RGBA) and the image writers behind Film::develop */
 int  mskh_develop(const float *film_xyzaw, size_t npixels, float *rgba);
+/* the same with AOV channels after W (hdrfilm.cpp:84-87): film npixels x nchannels -> out npixels x (nchannels - 1) */
+int  mskh_develop_channels(const float *film, size_t npixels, size_t nchannels, float *out);
 int  mskh_write_exr(const char *filename, const float *rgba, uint32_t width, uint32_t height);
 int  mskh_write_pfm(const char *filename, const float *rgba, uint32_t width, uint32_t height);
 /* srgb_model_fetch (rgb2spec) as the spectrum plugins use it */

@@ -43,6 +43,7 @@ def load() -> C.CDLL:
         L.mskh_render.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(capi.MskStats)]
         L.mskh_registered_plugins.argtypes = [C.c_char_p, C.c_size_t]
         L.mskh_develop.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p]
+        L.mskh_develop_channels.argtypes = [C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p]
         L.mskh_write_exr.argtypes = [C.c_char_p, C.c_void_p, C.c_uint32, C.c_uint32]
         L.mskh_write_pfm.argtypes = [C.c_char_p, C.c_void_p, C.c_uint32, C.c_uint32]
         L.mskh_srgb_model_fetch.argtypes = [C.c_void_p, C.c_void_p]
@@ -126,6 +127,14 @@ def develop(film: np.ndarray) -> np.ndarray:
     rgba = np.empty(film.shape[:2] + (4,), dtype=np.float32)
     _check(load().mskh_develop(film.ctypes.data, film.shape[0] * film.shape[1], rgba.ctypes.data))
     return rgba
+
+
+def develop_channels(film: np.ndarray) -> np.ndarray:
+    """HDRFilm::image of a film with AOV channels after X, Y, Z, A, W: RGBA, then every further channel / W."""
+    film = np.ascontiguousarray(film, dtype=np.float32)
+    out = np.empty(film.shape[:2] + (film.shape[2] - 1,), dtype=np.float32)
+    _check(load().mskh_develop_channels(film.ctypes.data, film.shape[0] * film.shape[1], film.shape[2], out.ctypes.data))
+    return out
 
 
 def write_exr(path, rgba: np.ndarray):

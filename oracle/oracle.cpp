@@ -26,8 +26,10 @@
 //   * SamplingIntegrator::render / render_block / render_sample themselves (src/librender/integrator.cpp, serial stand-in for
 //     tbb::parallel_for, camera rays as inputs): two whole films bit for bit against render() below in its test-only
 //     ORC_RENDER_REFERENCE_SEEDING mode
+//   * Film / HDRFilm (film.cpp, films/hdrfilm.cpp): prepare / put inside that render loop, and HDRFilm::image (the develop
+//     step) bit for bit against orc_develop and the product's host develop
 // UNPINNED (restated from the cited lines, checked by known-answer tests only): volpath.cpp, the BSDF plugins other than
-// diffuse (their sources are stale-API and compile with no Eigen), the camera, HDRFilm::image -- and Embree's arithmetic.  Every function cites the reference file:line it follows; paths are relative to /root/reference.
+// diffuse (their sources are stale-API and compile with no Eigen), the camera -- and Embree's arithmetic.  Every function cites the reference file:line it follows; paths are relative to /root/reference.
 //
 // Third-party arithmetic outside the reference tree: Embree 3.12.2 (vcpkg port
 // embree3, vcpkg/ports/embree3/vcpkg.json).  Its default triangle intersector

@@ -1,7 +1,7 @@
 // C entry point over the reference's OWN SamplingIntegrator::render / render_block / render_sample
 // (src/librender/integrator.cpp, with utils.cpp), #included from where it lies: the tile loop over BlockGenerator's
 // spiral, the order of random draws per camera sample (position 2, wavelength 1, aperture 2), spectrum_to_xyz, the
-// XYZAW channels, ImageBlock::put and Film::put -- driving the reference's own PathTracer / Scene of ref_path_wrap.cpp.
+// XYZAW channels, ImageBlock::put and HDRFilm::put (films/hdrfilm.cpp) -- driving the reference's own PathTracer / Scene of ref_path_wrap.cpp.
 // tbb::parallel_for is a serial stand-in (ONE task: the sampler is cloned once, integrator.cpp:57, and never re-seeded --
 // SURVEY F6); the camera ray of a sample is supplied by a callback (perspective.cpp is not part of the pinned build).
 // TEST INFRASTRUCTURE, see ref_math_wrap.cpp.
@@ -15,6 +15,8 @@
 using namespace misaki;
 misaki::SamplingIntegrator *msk_ref_path_tracer(RefPathScene *s);
 misaki::Scene *msk_ref_scene(RefPathScene *s);
+misaki::Film *msk_ref_make_hdrfilm(int W, int H, const misaki::ReconstructionFilter *filter); // ref_hdrfilm_wrap.cpp
+const float *msk_ref_hdrfilm_storage(misaki::Film *film);
 
 // film_out: H x W x 5 (X, Y, Z, A, W).  block_size: SamplingIntegrator "block_size" (default 32) is fixed when the tracer is
 // constructed, so the scene's tracer is used as is.
@@ -24,13 +26,13 @@ extern "C" int ref_render(void *handle, int W, int H, int spp, float stddev, Sen
         Properties fp;
         fp.floats["stddev"] = stddev;
         GaussianFilter *filter = new GaussianFilter(fp);
-        Film *film = new Film(Eigen::Vector2i(W, H), filter);
+        Film *film = msk_ref_make_hdrfilm(W, H, filter); // the reference's own HDRFilm: prepare / put under its mutex
         Properties sp;
         sp.ints["sample_count"] = spp;
         IndependentSampler *sampler = new IndependentSampler(sp);
         Sensor *sensor = new Sensor(film, sampler, cb);
         if (!msk_ref_path_tracer(s)->render(msk_ref_scene(s), sensor)) return -1;
-        memcpy(film_out, film->storage()->data().data(), sizeof(float) * (size_t) W * H * 5);
+        memcpy(film_out, msk_ref_hdrfilm_storage(film), sizeof(float) * (size_t) W * H * 5);
         return 0;
     } catch (...) { return -2; }
 }

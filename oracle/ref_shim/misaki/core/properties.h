@@ -34,8 +34,8 @@ public:
     std::string string(const std::string &n, const std::string &d) const { auto it = strings.find(n); return it == strings.end() ? d : it->second; }
     float float_(const std::string &n) const { return floats.at(n); }
     float float_(const std::string &n, float d) const { auto it = floats.find(n); return it == floats.end() ? d : it->second; }
-    long long int_(const std::string &n) const { return ints.at(n); }
-    long long int_(const std::string &n, long long d) const { auto it = ints.find(n); return it == ints.end() ? d : it->second; }
+    int int_(const std::string &n) const { return (int) ints.at(n); } // properties.h:74 (int)
+    int int_(const std::string &n, int d) const { auto it = ints.find(n); return it == ints.end() ? d : (int) it->second; }
     const void *pointer(const std::string &n) const { return pointers.at(n); }
     bool bool_(const std::string &n, bool d) const { auto it = bools.find(n); return it == bools.end() ? d : it->second; }
     ref<Texture> texture(const std::string &n) const { return textures.at(n); }

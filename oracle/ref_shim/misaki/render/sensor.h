@@ -1,34 +1,18 @@
-// Stand-in for include/misaki/render/sensor.h + film.h (the real ones pull image.h / OpenImageIO and transform.h): the
-// members SamplingIntegrator::render and Scene use, with the same signatures.  The camera itself (perspective.cpp) is not
-// part of the pinned build: RefSensor forwards sample_ray_differential to a callback that supplies the ray (an INPUT, as
-// in the single-path comparisons); RefFilm keeps the storage block exactly as HDRFilm does (hdrfilm.cpp:28-46).
+// Stand-in for include/misaki/render/sensor.h (the real one pulls transform.h): the members SamplingIntegrator::render and
+// Scene use, with the same signatures.  The camera itself (perspective.cpp) is not part of the pinned build: Sensor forwards
+// sample_ray_differential to a callback that supplies the ray (an INPUT, as in the single-path comparisons).  The film IS the
+// reference's own (film.h / film.cpp / films/hdrfilm.cpp, ref_hdrfilm_wrap.cpp).
 // TEST INFRASTRUCTURE.
 #pragma once
 #include "msk_ref_prelude.h"
 #include <misaki/core/object.h>
 #include <misaki/core/ray.h>
+#include <misaki/render/film.h>
 #include <misaki/render/imageblock.h>
 #include <misaki/render/sampler.h>
 #include <string>
 #include <vector>
 namespace misaki {
-class Film : public Object {
-public:
-    Film(const Eigen::Vector2i &size, const ReconstructionFilter *filter) : m_size(size), m_filter(filter) {}
-    const Eigen::Vector2i &size() const { return m_size; }
-    const ReconstructionFilter *filter() const { return m_filter; }
-    void prepare(const std::vector<std::string> &channels) { // hdrfilm.cpp:28-39
-        m_storage = new ImageBlock(m_size, channels.size());
-        m_storage->set_offset(Eigen::Vector2i(0, 0));
-        m_storage->clear();
-    }
-    void put(const ImageBlock *block) { m_storage->put(block); } // hdrfilm.cpp:43-46
-    const ImageBlock *storage() const { return m_storage; }
-private:
-    Eigen::Vector2i m_size;
-    const ReconstructionFilter *m_filter;
-    ImageBlock *m_storage = nullptr;
-};
 class Sensor : public Object {
 public:
     // out: o[3] d[3] mint maxt | wavelengths[4] | ray_weight[4]

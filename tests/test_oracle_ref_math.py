@@ -24,6 +24,10 @@ def F(bits):
     return np.array(bits, dtype=np.uint32).view(f32)
 
 
+def bits_of(a):
+    return np.ascontiguousarray(a, dtype=f32).reshape(-1).view(np.uint32)
+
+
 def same_bits(got, want_bits, what):
     got = np.ascontiguousarray(got, dtype=f32).reshape(-1)
     want = F(want_bits)
@@ -328,3 +332,18 @@ def test_sampling_integrator_render_whole_films():
         same_bits(np.stack([film[y, x] for y, x in c["probes"]]), c["probe_values"], f"render {c['scene']} probe pixels")
         assert hashlib.sha256(np.ascontiguousarray(film, f32).tobytes()).hexdigest() == c["sha256"], f"film {c['scene']} {W}x{H}"
         assert film[..., :3].max() > 0
+
+
+def test_hdrfilm_image_develop():
+    """HDRFilm::image (src/librender/films/hdrfilm.cpp:48-90, compiled with film.cpp over the reference's own ImageBlock
+    storage; only the OpenImageIO-backed Image is a buffer stand-in): XYZ -> linear sRGB, / W with the W == 0 guard,
+    alpha = A / W, AOV channels / W.  Checked bit for bit against the oracle's develop AND the product's host develop
+    (misaki_render_b200/host/imageio.cpp, what GpuPathIntegrator's film runs before the EXR writer)."""
+    from misaki_render_b200 import host_api
+    for c in GOLDEN["hdrfilm_image"]:
+        W, H, nch = c["W"], c["H"], c["nch"]
+        film = np.array(c["film"], np.uint32).view(f32).reshape(H, W, nch)
+        want = np.array(c["image"], np.uint32).view(f32).reshape(H, W, nch - 1)
+        same_bits(host_api.develop_channels(film), bits_of(want), f"host develop_channels {W}x{H}x{nch}")
+        same_bits(host_api.develop(film[..., :5]), bits_of(want[..., :4]), f"host develop {W}x{H}")
+        same_bits(po.develop(film[..., :5]), bits_of(want[..., :4]), f"oracle develop {W}x{H}")

@@ -323,6 +323,21 @@ def main():
                             "probe_values": bits(np.stack([film[y, x] for y, x in probes])), "mean": bits(film.mean(axis=(0, 1)))})
         print(f"render {which} {W}x{H}x{spp}: mean XYZAW = {film.mean(axis=(0, 1))}")
 
+    # HDRFilm::image (films/hdrfilm.cpp:48-90 over film.cpp and the reference's own ImageBlock storage): the develop step
+    g["hdrfilm_image"] = []
+    for (W, H, nch) in [(16, 12, 5), (9, 7, 8)]:
+        film = np.empty((H, W, nch), f32)
+        film[..., :3] = rng.random((H, W, 3)) * rng.choice([0.01, 1.0, 60.0, 4000.0], (H, W, 1))
+        film[..., 4] = rng.random((H, W)) * 4 + 0.25
+        film[..., 3] = film[..., 4] * (rng.random((H, W)) > 0.2)
+        film[..., 5:] = rng.normal(size=(H, W, nch - 5)) * 100
+        film[0, 0] = 0.0  # a pixel no sample reached: weight 0 -> 0, not NaN (hdrfilm.cpp:73-74)
+        film[1, 2, 4] = 0.0  # radiance without weight
+        out = np.empty((H, W, nch - 1), f32)
+        assert L.ref_hdrfilm_image(fp(film), W, H, nch, fp(out)) == 0
+        assert np.isfinite(out).all()
+        g["hdrfilm_image"].append({"W": W, "H": H, "nch": nch, "film": bits(film), "image": bits(out)})
+
     OUT.write_text(json.dumps(g, separators=(",", ":")))
     print(f"wrote {OUT} ({OUT.stat().st_size} bytes): " + ", ".join(f"{k}={len(v)}" for k, v in g.items() if isinstance(v, list)))
 
