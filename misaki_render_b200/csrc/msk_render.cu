@@ -270,7 +270,10 @@ __global__ void __launch_bounds__(kSortThreads) k_sort(const __grid_constant__ D
 #ifndef MSK_SHADE_DIFFUSE_BLOCKS
 #define MSK_SHADE_DIFFUSE_BLOCKS 4
 #endif
-constexpr int shade_min_blocks(int key) { return key < 0 ? MSK_SHADE_MIN_BLOCKS : (key == 0 ? 8 : (key == 1 ? MSK_SHADE_DIFFUSE_BLOCKS : 4)); }
+#ifndef MSK_SHADE_GLOSSY_BLOCKS
+#define MSK_SHADE_GLOSSY_BLOCKS 4
+#endif
+constexpr int shade_min_blocks(int key) { return key < 0 ? MSK_SHADE_MIN_BLOCKS : (key == 0 ? 8 : (key == 1 ? MSK_SHADE_DIFFUSE_BLOCKS : MSK_SHADE_GLOSSY_BLOCKS)); }
 // One path vertex of PathTracer::sample given the hit record of the ray that arrived (shared by the wavefront stage
 // k_shade and the per-path tail kernel k_tail).  TYPE >= 0: BSDF type known at compile time.
 struct VertexOut {
