@@ -24,7 +24,8 @@
 //     brute-force intersector); AOVIntegrator::sample (integrators/aov.cpp); imageblock.cpp (splat, block merge, spiral):
 //     whole films equal by SHA-256; srgb.cpp + spectra/{srgb,srgb_d65,d65}.cpp (what an <rgb> tag becomes)
 //   * SamplingIntegrator::render / render_block / render_sample themselves (src/librender/integrator.cpp, serial stand-in for
-//     tbb::parallel_for, camera rays as inputs): two whole films bit for bit against render() below in its test-only
+//     tbb::parallel_for, camera rays as inputs): three whole films -- one of them config C1's Cornell box with the reference's
+//     own <rgb> textures -- bit for bit against render() below in its test-only
 //     ORC_RENDER_REFERENCE_SEEDING mode
 //   * Film / HDRFilm (film.cpp, films/hdrfilm.cpp): prepare / put inside that render loop, and HDRFilm::image (the develop
 //     step) bit for bit against orc_develop and the product's host develop

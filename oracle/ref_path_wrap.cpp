@@ -96,6 +96,8 @@ bool Scene::ray_test(const Ray &ray) const { // scene.cpp:255-273
 using namespace misaki;
 
 #include "ref_path_scene.h"
+#include <functional>
+misaki::Texture *msk_ref_make_rgb_texture(const float rgb[3], bool within_emitter); // ref_spectra_wrap.cpp
 misaki::SamplingIntegrator *msk_ref_path_tracer(RefPathScene *s) { return s->tracer; }
 misaki::Scene *msk_ref_scene(RefPathScene *s) { return s->scene; }
 
@@ -104,20 +106,21 @@ extern "C" {
 // Meshes as in MskSceneDesc (verts nverts x 8, tris ntris x 3), each with a diffuse reflectance (constant spectrum) and an
 // optional area-light radiance (constant spectrum, < 0: none); Scene::m_shapes order == the order given.  env_radiance >= 0:
 // a "constant" environment emitter after the shapes (emitters/constant.cpp).
-void *ref_path_scene_create(uint32_t nmeshes, const float *const *verts, const uint32_t *nverts, const uint32_t *const *tris, const uint32_t *ntris,
-                            const int *normals, const int *uvs, const float *reflectance, const float *radiance, float env_radiance) {
+static void *create_scene(uint32_t nmeshes, const float *const *verts, const uint32_t *nverts, const uint32_t *const *tris, const uint32_t *ntris,
+                          const int *normals, const int *uvs, const std::function<ref<Texture>(uint32_t)> &reflectance,
+                          const std::function<ref<Texture>(uint32_t)> &radiance /* null reference: no area light */, float env_radiance) {
     try {
         RefPathScene *s = new RefPathScene;
         Properties sp;
         for (uint32_t i = 0; i < nmeshes; ++i) {
             Properties bp;
             bp.make_default = make_const;
-            bp.textures["reflectance"] = make_const(reflectance[i]);
+            bp.textures["reflectance"] = reflectance(i);
             Properties mp;
             mp.children.push_back({ "_arg_0", ref<Object>(new SmoothDiffuse(bp)) });
-            if (radiance[i] >= 0.f) {
+            if (ref<Texture> rad = radiance(i)) {
                 Properties ep;
-                ep.textures["radiance"] = make_const(radiance[i]);
+                ep.textures["radiance"] = rad;
                 mp.children.push_back({ "_arg_1", ref<Object>(new AreaLight(ep)) });
             }
             RefMesh *m = new RefMesh(verts[i], nverts[i], tris[i], ntris[i], normals[i] != 0, uvs[i] != 0, mp);
@@ -133,6 +136,20 @@ void *ref_path_scene_create(uint32_t nmeshes, const float *const *verts, const u
         s->tracer = new PathTracer(Properties());
         return s;
     } catch (...) { return nullptr; }
+}
+void *ref_path_scene_create(uint32_t nmeshes, const float *const *verts, const uint32_t *nverts, const uint32_t *const *tris, const uint32_t *ntris,
+                            const int *normals, const int *uvs, const float *reflectance, const float *radiance, float env_radiance) {
+    return create_scene(nmeshes, verts, nverts, tris, ntris, normals, uvs, [&](uint32_t i) { return make_const(reflectance[i]); },
+                        [&](uint32_t i) { return radiance[i] >= 0.f ? make_const(radiance[i]) : ref<Texture>(); }, env_radiance);
+}
+// The same with the textures an <rgb> tag becomes (xml.cpp:269-277): reflectance_rgb / radiance_rgb hold 3 floats per mesh,
+// a negative radiance_rgb[3 i] means no area light -- the scenes of the reference's own XML files (assets/cbox/scene.xml).
+void *ref_path_scene_create_rgb(uint32_t nmeshes, const float *const *verts, const uint32_t *nverts, const uint32_t *const *tris, const uint32_t *ntris,
+                                const int *normals, const int *uvs, const float *reflectance_rgb, const float *radiance_rgb) {
+    return create_scene(nmeshes, verts, nverts, tris, ntris, normals, uvs,
+                        [&](uint32_t i) { return ref<Texture>(msk_ref_make_rgb_texture(reflectance_rgb + 3 * i, false)); },
+                        [&](uint32_t i) { return radiance_rgb[3 * i] >= 0.f ? ref<Texture>(msk_ref_make_rgb_texture(radiance_rgb + 3 * i, true)) : ref<Texture>(); },
+                        -1.f);
 }
 // PathTracer::sample for one camera ray with the sampler seeded as IndependentSampler::seed(seed) (base_seed 0);
 // max_depth -1 / rr_depth 5 / hide_emitter false are hard-wired in the reference (path.cpp:135-136)

@@ -14,12 +14,25 @@
 using namespace misaki;
 misaki::Object *msk_ref_make_regular(const misaki::Properties &p); // spectra/regular.cpp lives in ref_plugins_wrap.cpp
 
+static void register_expansions() {
+    InstanceManager *mgr = InstanceManager::get();
+    mgr->table["regular"] = [](const Properties &p) -> Object * { return msk_ref_make_regular(p); };
+    mgr->table["d65"] = [](const Properties &p) -> Object * { return new D65Spectrum(p); };
+}
+// What create_texture_from_rgb (xml.cpp:269-277) builds for an <rgb> tag: "srgb", or "srgb_d65" inside an <emitter>, with the
+// colour as the only property.  Used by ref_path_wrap.cpp to put the reference's own colour textures into its scenes.
+misaki::Texture *msk_ref_make_rgb_texture(const float rgb[3], bool within_emitter) {
+    register_expansions();
+    Properties p(within_emitter ? "srgb_d65" : "srgb");
+    p.colors["color"] = { rgb[0], rgb[1], rgb[2] };
+    if (within_emitter) return new SRGBEmitterSpectrum(p);
+    return new SRGBReflectanceSpectrum(p);
+}
+
 // kind: 0 "srgb" (reflectance <rgb>), 1 "srgb_d65" (<rgb> inside an emitter, with "scale"), 2 "d65" (scale) expanded
 extern "C" int ref_colour_spectrum(int kind, const float rgb[3], float scale, const float wl[4], float out[4]) {
     try {
-        InstanceManager *mgr = InstanceManager::get();
-        mgr->table["regular"] = [](const Properties &p) -> Object * { return msk_ref_make_regular(p); };
-        mgr->table["d65"] = [](const Properties &p) -> Object * { return new D65Spectrum(p); };
+        register_expansions();
         Properties p;
         p.colors["color"] = { rgb[0], rgb[1], rgb[2] };
         p.floats["scale"] = scale;

@@ -325,7 +325,8 @@ def test_sampling_integrator_render_whole_films():
     from workloads import scenes
     for c in GOLDEN["render"]:
         W, H = c["W"], c["H"]
-        sd = scenes.cbox_uniform(W, H) if c["scene"] == "cbox" else scenes.open_uniform(W, H)[0]
+        sd = {"cbox": lambda: scenes.cbox_uniform(W, H), "open": lambda: scenes.open_uniform(W, H)[0],
+              "cbox_rgb": lambda: scenes.cbox(W, H)}[c["scene"]]()  # cbox_rgb: BASELINE config C1's scene itself
         rd = capi.render_desc(spp=c["spp"], max_depth=-1, rr_depth=5)
         rd.flags |= 0x80000000  # ORC_RENDER_REFERENCE_SEEDING (oracle.h)
         film, _ = po.OracleScene(sd).render(rd, nthreads=1)

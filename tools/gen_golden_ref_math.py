@@ -217,6 +217,18 @@ def main():
         assert handle
         return handle
 
+    def ref_scene_rgb(sd, refl_rgb, rad_rgb):
+        nm = len(sd.meshes)
+        vv = [np.ascontiguousarray(m["verts"], f32) for m in sd.meshes]; tt = [np.ascontiguousarray(m["tris"], np.uint32) for m in sd.meshes]
+        vptr = (C.c_void_p * nm)(*[a.ctypes.data for a in vv]); tptr = (C.c_void_p * nm)(*[a.ctypes.data for a in tt])
+        nv = (C.c_uint32 * nm)(*[a.shape[0] for a in vv]); nt = (C.c_uint32 * nm)(*[a.shape[0] for a in tt])
+        hn = (C.c_int * nm)(*[int(m["has_normals"]) for m in sd.meshes]); hu = (C.c_int * nm)(*[int(m["has_uvs"]) for m in sd.meshes])
+        refl = np.ascontiguousarray(refl_rgb, f32); rad = np.ascontiguousarray(rad_rgb, f32)
+        L.ref_path_scene_create_rgb.restype = C.c_void_p
+        handle = L.ref_path_scene_create_rgb(nm, vptr, nv, tptr, nt, hn, hu, fp(refl), fp(rad))
+        assert handle
+        return handle
+
     def path_vectors(sd, params, env, n, seed0, aov=False):
         nm = len(sd.meshes)
         vv = [np.ascontiguousarray(m["verts"], f32) for m in sd.meshes]; tt = [np.ascontiguousarray(m["tris"], np.uint32) for m in sd.meshes]
@@ -302,9 +314,11 @@ def main():
     # SamplingIntegrator::render itself (oracle/ref_render_wrap.cpp): whole films of the reference's own tile loop
     g["render"] = []
     CB = C.CFUNCTYPE(None, C.c_float, C.c_float, C.c_float, C.POINTER(C.c_float))
-    for (W, H, spp, which) in [(48, 40, 2, "cbox"), (40, 33, 2, "open")]:
+    for (W, H, spp, which) in [(48, 40, 2, "cbox"), (40, 33, 2, "open"), (44, 36, 3, "cbox_rgb")]:
         if which == "cbox":
             sd, params, env = scenes.cbox_uniform(W, H), [(r, e) for _, r, e in scenes.CBOX_UNIFORM], -1.0
+        elif which == "cbox_rgb":  # config C1 itself: the <rgb> reflectances and the (40, 40, 40) luminaire of assets/cbox/scene.xml
+            sd = scenes.cbox(W, H)
         else:
             (sd, params), env = scenes.open_uniform(W, H), scenes.OPEN_UNIFORM_ENV
         osc = pyoracle.OracleScene(sd)
@@ -317,7 +331,11 @@ def main():
                 out[i] = float(v)
 
         film = np.empty((H, W, 5), f32)
-        assert L.ref_render(C.c_void_p(ref_scene(sd, params, env)), W, H, spp, C.c_float(0.5), CB(camera), fp(film)) == 0
+        if which == "cbox_rgb":
+            handle = ref_scene_rgb(sd, [r for _, r in scenes.CBOX_SHAPES], [(40, 40, 40) if n == "luminaire" else (-1, -1, -1) for n, _ in scenes.CBOX_SHAPES])
+        else:
+            handle = ref_scene(sd, params, env)
+        assert L.ref_render(C.c_void_p(handle), W, H, spp, C.c_float(0.5), CB(camera), fp(film)) == 0
         probes = [[int(y), int(x)] for y, x in zip(rng.integers(0, H, 10), rng.integers(0, W, 10))] + [[0, 0], [H - 1, W - 1], [31, 31], [32, 32]]
         g["render"].append({"scene": which, "W": W, "H": H, "spp": spp, "sha256": hashlib.sha256(film.tobytes()).hexdigest(), "probes": probes,
                             "probe_values": bits(np.stack([film[y, x] for y, x in probes])), "mean": bits(film.mean(axis=(0, 1)))})
