@@ -18,7 +18,8 @@ Keys beyond the base contract:
   e2e        paths/s through msk_gpu_render with a HOST film buffer (D2H copy inside the timed region)
   roofline   the dominant kernel's algorithmic bytes / its CUDA-event time vs the measured HBM copy peak
   cpu_baseline  oracle (CPU restatement of the reference, all host threads) on a bounded sample of the job
-  --impl reference   times that CPU restatement alone (the reference itself cannot be built here: DESIGN.md)
+  --impl reference   times that CPU restatement alone (the reference as a whole cannot be built here: DESIGN.md);
+                     --ref-kind reference --workload c1 times the reference's own compiled render loop from oracle/_ref
 """
 from __future__ import annotations
 
@@ -159,6 +160,8 @@ def run_reference(args, rank: int):
     from misaki_render_b200 import capi
     from oracle import pyoracle
     sd, rdk, wname = workload(args.workload, 1)
+    if args.ref_kind == "reference":
+        return run_reference_code(args, sd, rdk, wname)
     osc = pyoracle.OracleScene(sd)
     spp = rdk["spp"]
     osc.render(capi.render_desc(sample_begin=0, sample_end=1, **rdk))  # builds the oracle's BVH lazily
@@ -188,6 +191,43 @@ def run_reference(args, rank: int):
     }
     print(json.dumps(line), flush=True)
 
+
+
+def run_reference_code(args, sd, rdk, wname):
+    """--ref-kind reference (C1 only): the reference's OWN compiled render loop from oracle/_ref (pyoracle.ReferenceLoop:
+    integrator.cpp, path.cpp, scene.cpp, mesh / interaction, imageblock.cpp, hdrfilm.cpp, its colour textures) on the
+    Cornell box of assets/cbox/scene.xml -- the one BASELINE config whose plugins the reference's build compiles.  Embree
+    (brute force over the 36 triangles here), TBB (std::threads over the same tasks) and Eigen (oracle/ref_shim, scalar) are
+    stand-ins, so this is the reference's CODE, not its performance with its real dependencies."""
+    from oracle import pyoracle
+    from workloads import scenes
+    if args.workload != "c1":
+        raise SystemExit("--ref-kind reference: only C1's plugins (diffuse, area, srgb) are compiled by the reference's build")
+    if not pyoracle.REF_CODE_LIB.exists():
+        raise SystemExit(f"{pyoracle.REF_CODE_LIB} is missing (python -c 'import __graft_entry__ as g; g.build()' where /root/reference exists)")
+    loop = pyoracle.ReferenceLoop(sd, [r for _, r in scenes.CBOX_SHAPES],
+                                  [(40, 40, 40) if n == "luminaire" else (-1, -1, -1) for n, _ in scenes.CBOX_SHAPES])
+    threads, spp = os.cpu_count() or 1, rdk["spp"]
+    _, dt1 = loop.render(1, threads)
+    total_steps = args.steps + args.warmup
+    s = int(max(1, min(spp, (args.ref_budget / total_steps) / max(dt1, 1e-6))))
+    for _ in range(args.warmup):
+        loop.render(s, threads)
+    secs = sum(loop.render(s, threads)[1] for _ in range(args.steps))
+    paths = sd.width * sd.height * s * args.steps
+    value = paths / secs
+    sample = f"{s} of {spp} samples per pixel of every pixel ({sd.width}x{sd.height}); unbounded depth, roulette from 5 (hard-wired, path.cpp:135-136)"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": secs / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": {"workload": wname, "sample_per_step": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "reference", "sample": sample, "cpu": cpu_model(),
+                         "note": "the reference's own integrator / path tracer / scene / film code compiled from /root/reference "
+                                 "(oracle/Makefile.ref); stand-ins: brute-force intersector for Embree, std::thread for TBB, "
+                                 "scalar oracle/ref_shim for Eigen"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
 
 
 # --------------------------------------------------------------------------------------------- C5 intersection sweep
@@ -633,6 +673,8 @@ def main():
     ap.add_argument("--spp", type=int, default=0, help="override samples per pixel per GPU (development only)")
     ap.add_argument("--cpu-budget", type=float, default=15.0, help="seconds of CPU work for cpu_baseline")
     ap.add_argument("--ref-budget", type=float, default=150.0, help="seconds for the whole --impl reference run")
+    ap.add_argument("--ref-kind", default="port", choices=["port", "reference"],
+                    help="--impl reference: the oracle port (every workload) or, for C1, the reference's own compiled code from oracle/_ref")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--reduce", default="peer", choices=["peer", "nccl"], help="N > 1: film reduction by the library's NVLink peer kernel or by NCCL")
     args = ap.parse_args()

@@ -1354,6 +1354,23 @@ int orc_camera_rays(OrcScene *s, const float *samples /* n x 3: px, py, waveleng
     return 0;
 }
 
+// The camera as a plain C callback for oracle/ref_render_wrap.cpp (whose Sensor stand-in asks a callback for the ray of
+// each sample; perspective.cpp is not part of the pinned build): orc_ref_camera_bind fixes the camera, the function returned
+// by orc_ref_camera_callback then fills out16 = o[3] d[3] mint maxt | wavelengths[4] | ray weight[4].  Read-only after bind.
+static MskCamera g_callback_camera;
+static void ref_camera_callback(float wavelength_sample, float px, float py, float *out16) {
+    auto [ray, w] = camera_sample_ray(g_callback_camera, wavelength_sample, { px, py });
+    const float v[16] = { ray.o.x, ray.o.y, ray.o.z, ray.d.x, ray.d.y, ray.d.z, ray.mint, ray.maxt,
+                          ray.wavelengths[0], ray.wavelengths[1], ray.wavelengths[2], ray.wavelengths[3], w[0], w[1], w[2], w[3] };
+    memcpy(out16, v, sizeof(v));
+}
+int orc_ref_camera_bind(OrcScene *s) {
+    if (!s) return fail("null scene");
+    g_callback_camera = s->sc.cam;
+    return 0;
+}
+void *orc_ref_camera_callback(void) { return (void *) &ref_camera_callback; }
+
 // AOVIntegrator::sample, integrators/aov.cpp:87-144.  `types` lists the AOVs in channel order; an
 // MSK_AOV_INTEGRATOR_RGBA entry is the nested PathTracer (aov.cpp:124-140).  Deviations (oracle.h): fields of a
 // missed ray read 0 (uninitialised in the reference, scene.cpp:247-251), and without a nested integrator the

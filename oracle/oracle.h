@@ -19,6 +19,9 @@ int  orc_intersect(OrcScene *s, const MskRay *rays, MskHit *hits, size_t n, int 
 int  orc_occluded(OrcScene *s, const MskRay *rays, uint8_t *occ, size_t n);
 int  orc_intersect_margin(OrcScene *s, const MskRay *rays, float *second_t, float *min_bary, size_t n);
 int  orc_camera_rays(OrcScene *s, const float *samples, MskRay *rays, size_t n);
+/* the same camera as a C callback (ws, px, py, out16) for oracle/ref_render_wrap.cpp's Sensor stand-in */
+int  orc_ref_camera_bind(OrcScene *s);
+void *orc_ref_camera_callback(void);
 int  orc_render(OrcScene *s, const MskRenderDesc *rd, float *film, int nthreads, OrcStats *stats);
 int  orc_aov_channels(const int32_t *types, uint32_t ntypes);
 int  orc_render_aov(OrcScene *s, const MskRenderDesc *rd, const int32_t *types, uint32_t ntypes, float *film, int nthreads, OrcStats *stats);

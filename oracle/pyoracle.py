@@ -295,3 +295,66 @@ class RefRgb2Spec:
     def eval_precise(self, coeff, lam):
         coeff = _f(coeff, 3).copy()
         return self.L.rgb2spec_eval_precise(coeff.ctypes.data, lam)
+
+
+REF_CODE_LIB = HERE / "_ref" / "libmisaki_ref_math.so"
+
+
+class ReferenceLoop:
+    """The reference's OWN compiled render loop (oracle/ref_render_wrap.cpp: integrator.cpp, integrators/path.cpp,
+    scene.cpp's emitter sampling, mesh / interaction, imageblock.cpp, films/hdrfilm.cpp, its srgb / srgb_d65 textures)
+    on a scene of diffuse meshes with <rgb> reflectances and area lights -- what assets/cbox/scene.xml describes.
+    Stand-ins: Embree's two calls are a brute-force Moeller-Trumbore loop, tbb::parallel_for is `threads` std::threads
+    over the same tasks, Eigen is oracle/ref_shim, the camera ray of a sample comes from the oracle's camera.  Used by
+    tools/gen_golden_ref_math.py and by bench.py --impl reference --ref-kind reference."""
+
+    def __init__(self, sd, reflectance_rgb, radiance_rgb):
+        import os
+        os.environ.setdefault("MSK_REF_DATA_ROOT", str(HERE.parent / "misaki_render_b200"))  # data/srgb.coeff (srgb.cpp:14-18)
+        self.L = C.CDLL(str(REF_CODE_LIB))
+        self.sd = sd
+        nm = len(sd.meshes)
+        self._keep = [[np.ascontiguousarray(m["verts"], np.float32) for m in sd.meshes],
+                      [np.ascontiguousarray(m["tris"], np.uint32) for m in sd.meshes]]
+        vptr = (C.c_void_p * nm)(*[a.ctypes.data for a in self._keep[0]])
+        tptr = (C.c_void_p * nm)(*[a.ctypes.data for a in self._keep[1]])
+        nv = (C.c_uint32 * nm)(*[a.shape[0] for a in self._keep[0]])
+        nt = (C.c_uint32 * nm)(*[a.shape[0] for a in self._keep[1]])
+        hn = (C.c_int * nm)(*[int(m["has_normals"]) for m in sd.meshes])
+        hu = (C.c_int * nm)(*[int(m["has_uvs"]) for m in sd.meshes])
+        refl, rad = _f(reflectance_rgb, nm * 3).copy(), _f(radiance_rgb, nm * 3).copy()
+        self.L.ref_path_scene_create_rgb.restype = C.c_void_p
+        self.h = self.L.ref_path_scene_create_rgb(nm, vptr, nv, tptr, nt, hn, hu, C.c_void_p(refl.ctypes.data), C.c_void_p(rad.ctypes.data))
+        if not self.h:
+            raise RuntimeError("ref_path_scene_create_rgb failed")
+        self.osc = OracleScene(sd)
+        L = lib()
+        L.orc_ref_camera_bind.argtypes = [C.c_void_p]
+        L.orc_ref_camera_callback.restype = C.c_void_p
+        if L.orc_ref_camera_bind(self.osc.h) != 0:
+            raise RuntimeError("orc_ref_camera_bind failed")
+        self.cb = C.c_void_p(L.orc_ref_camera_callback())
+        self.L.ref_render.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_void_p, C.c_void_p]
+
+    def render(self, spp: int, threads: int = 1, stddev: float = 0.5):
+        """Returns (film H x W x 5, seconds).  threads == 1 is the deterministic single-task mode of the golden vectors."""
+        import os
+        import sys
+        import time
+        film = np.empty((self.sd.height, self.sd.width, 5), np.float32)
+        os.environ["MSK_REF_TBB_THREADS"] = str(int(threads))
+        sys.stdout.flush()
+        saved, devnull = os.dup(1), os.open(os.devnull, os.O_WRONLY)  # the reference prints a progress bar per tile (utils.h:15-39)
+        os.dup2(devnull, 1)
+        try:
+            t = time.perf_counter()
+            rc = self.L.ref_render(self.h, self.sd.width, self.sd.height, int(spp), float(stddev), self.cb, film.ctypes.data)
+            dt = time.perf_counter() - t
+        finally:
+            os.dup2(saved, 1)
+            os.close(saved)
+            os.close(devnull)
+            os.environ["MSK_REF_TBB_THREADS"] = "1"
+        if rc != 0:
+            raise RuntimeError(f"ref_render failed ({rc})")
+        return film, dt

@@ -348,3 +348,22 @@ def test_hdrfilm_image_develop():
         same_bits(host_api.develop_channels(film), bits_of(want), f"host develop_channels {W}x{H}x{nch}")
         same_bits(host_api.develop(film[..., :5]), bits_of(want[..., :4]), f"host develop {W}x{H}")
         same_bits(po.develop(film[..., :5]), bits_of(want[..., :4]), f"oracle develop {W}x{H}")
+
+
+@pytest.mark.skipif(not po.REF_CODE_LIB.exists(), reason="oracle/_ref is built only where /root/reference exists")
+def test_reference_loop_helper_reproduces_its_golden_film_and_runs_threaded():
+    """pyoracle.ReferenceLoop (the compiled reference loop behind `bench.py --impl reference --ref-kind reference`): in
+    its single-task mode it reproduces the committed golden film of config C1's scene; with several threads (the timing
+    mode: every task clones the sampler again, integrator.cpp:57) the film is a valid render of the same scene."""
+    import hashlib
+    from workloads import scenes
+    c = next(c for c in GOLDEN["render"] if c["scene"] == "cbox_rgb")
+    sd = scenes.cbox(c["W"], c["H"])
+    loop = po.ReferenceLoop(sd, [r for _, r in scenes.CBOX_SHAPES],
+                            [(40, 40, 40) if n == "luminaire" else (-1, -1, -1) for n, _ in scenes.CBOX_SHAPES])
+    film, _ = loop.render(c["spp"], threads=1)
+    assert hashlib.sha256(film.tobytes()).hexdigest() == c["sha256"]
+    par, _ = loop.render(c["spp"], threads=4)
+    assert np.isfinite(par).all()
+    np.testing.assert_allclose(par[..., 4].sum(), film[..., 4].sum(), rtol=1e-2)            # as many samples, other positions
+    assert abs(par[..., 1].sum() / film[..., 1].sum() - 1) < 0.25                            # same scene, other random numbers
