@@ -367,3 +367,22 @@ def test_reference_loop_helper_reproduces_its_golden_film_and_runs_threaded():
     assert np.isfinite(par).all()
     np.testing.assert_allclose(par[..., 4].sum(), film[..., 4].sum(), rtol=1e-2)            # as many samples, other positions
     assert abs(par[..., 1].sum() / film[..., 1].sum() - 1) < 0.25                            # same scene, other random numbers
+
+
+def test_oracle_converges_to_the_reference_codes_image():
+    """SURVEY 8(d)(ii) against the reference's OWN code: tests/golden/ref_cbox48_converged.npz is BASELINE config C1's
+    Cornell box rendered by the compiled reference loop at 4096 spp (tools/gen_golden_ref_converged.py).  The oracle, with
+    its own per-(pixel, sample) seeds, must approach that image at the Monte-Carlo rate -- relMSE ~ 1 / spp, at 256 spp
+    within 10 % of what the reference's own 256-spp render shows against it -- which a biased integrator cannot do."""
+    from misaki_render_b200 import capi
+    from tests.util import relmse
+    from workloads import scenes
+    g = np.load(Path(__file__).parent / "golden" / "ref_cbox48_converged.npz")
+    osc = po.OracleScene(scenes.cbox(48, 48))
+    e = {}
+    for spp in (64, 256, 1024):
+        film, _ = osc.render(capi.render_desc(spp=spp, max_depth=-1, rr_depth=5))
+        e[spp] = relmse(po.develop(film), g["image"])
+    assert abs(e[256] / float(g["ref_relmse_256"]) - 1) < 0.10, e
+    assert e[1024] < 1.25 * float(g["ref_relmse_1024"]), e
+    assert 3.0 < e[64] / e[256] < 5.0 and 3.0 < e[256] / e[1024] < 5.0, e  # ~ 1 / spp down to the fixture's own noise floor
