@@ -185,3 +185,11 @@ int ref_aov_sample(void *handle, uint64_t seed, const float o[3], const float d[
 }
 
 } // extern "C"
+
+// The AOV integrator of ref_aov_sample as an object, for the whole-film comparison of ref_render_wrap.cpp
+misaki::SamplingIntegrator *msk_ref_make_aov(RefPathScene *s) {
+    misaki::Properties p;
+    p.strings["aovs"] = "d:depth p:position u:uv g:geo_normal s:sh_normal";
+    p.children.push_back({ "img", misaki::ref<misaki::Object>(s->tracer) });
+    return new misaki::AOVIntegrator(p);
+}

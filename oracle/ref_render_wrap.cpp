@@ -18,11 +18,11 @@ misaki::Scene *msk_ref_scene(RefPathScene *s);
 misaki::Film *msk_ref_make_hdrfilm(int W, int H, const misaki::ReconstructionFilter *filter); // ref_hdrfilm_wrap.cpp
 const float *msk_ref_hdrfilm_storage(misaki::Film *film);
 
-// film_out: H x W x 5 (X, Y, Z, A, W).  block_size: SamplingIntegrator "block_size" (default 32) is fixed when the tracer is
-// constructed, so the scene's tracer is used as is.
-extern "C" int ref_render(void *handle, int W, int H, int spp, float stddev, Sensor::RayCallback cb, float *film_out) {
+misaki::SamplingIntegrator *msk_ref_make_aov(RefPathScene *s); // ref_path_wrap.cpp
+
+static int render_with(SamplingIntegrator *integrator, RefPathScene *s, int W, int H, int spp, float stddev, Sensor::RayCallback cb, int nch,
+                       float *film_out) {
     try {
-        RefPathScene *s = (RefPathScene *) handle;
         Properties fp;
         fp.floats["stddev"] = stddev;
         GaussianFilter *filter = new GaussianFilter(fp);
@@ -31,8 +31,22 @@ extern "C" int ref_render(void *handle, int W, int H, int spp, float stddev, Sen
         sp.ints["sample_count"] = spp;
         IndependentSampler *sampler = new IndependentSampler(sp);
         Sensor *sensor = new Sensor(film, sampler, cb);
-        if (!msk_ref_path_tracer(s)->render(msk_ref_scene(s), sensor)) return -1;
-        memcpy(film_out, msk_ref_hdrfilm_storage(film), sizeof(float) * (size_t) W * H * 5);
+        if (!integrator->render(msk_ref_scene(s), sensor)) return -1;
+        memcpy(film_out, msk_ref_hdrfilm_storage(film), sizeof(float) * (size_t) W * H * nch);
         return 0;
+    } catch (...) { return -2; }
+}
+// film_out: H x W x 5 (X, Y, Z, A, W).  block_size: SamplingIntegrator "block_size" (default 32) is fixed when the tracer is
+// constructed, so the scene's tracer is used as is.
+extern "C" int ref_render(void *handle, int W, int H, int spp, float stddev, Sensor::RayCallback cb, float *film_out) {
+    RefPathScene *s = (RefPathScene *) handle;
+    return render_with(msk_ref_path_tracer(s), s, W, H, spp, stddev, cb, 5, film_out);
+}
+// The same loop driving AOVIntegrator (integrators/aov.cpp: depth, position, uv, geometric / shading normal, nested path
+// tracer RGBA): film_out is H x W x 21 -- X, Y, Z, A, W and the 16 AOV channels in aov_names() order (integrator.cpp:36-41).
+extern "C" int ref_render_aov(void *handle, int W, int H, int spp, float stddev, Sensor::RayCallback cb, float *film_out) {
+    RefPathScene *s = (RefPathScene *) handle;
+    try {
+        return render_with(msk_ref_make_aov(s), s, W, H, spp, stddev, cb, 21, film_out);
     } catch (...) { return -2; }
 }

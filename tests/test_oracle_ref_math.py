@@ -386,3 +386,20 @@ def test_oracle_converges_to_the_reference_codes_image():
     assert abs(e[256] / float(g["ref_relmse_256"]) - 1) < 0.10, e
     assert e[1024] < 1.25 * float(g["ref_relmse_1024"]), e
     assert 3.0 < e[64] / e[256] < 5.0 and 3.0 < e[256] / e[1024] < 5.0, e  # ~ 1 / spp down to the fixture's own noise floor
+
+
+def test_aov_integrator_whole_film():
+    """The reference's render loop driving AOVIntegrator (integrator.cpp:36-41 channel list from aov_names(), render_sample's
+    aovs + 5, HDRFilm with 21 channels): a whole film of the Cornell box -- XYZAW plus depth, position, uv, geometric /
+    shading normal and the nested path tracer's RGBA -- bit for bit against the oracle's AOV render in reference-seeding mode."""
+    import hashlib
+    from misaki_render_b200 import capi
+    from workloads import scenes
+    c = GOLDEN["render_aov"]
+    rd = capi.render_desc(spp=c["spp"], max_depth=-1, rr_depth=5)
+    rd.flags |= 0x80000000  # ORC_RENDER_REFERENCE_SEEDING (oracle.h)
+    types = [capi.AOV_DEPTH, capi.AOV_POSITION, capi.AOV_UV, capi.AOV_GEO_NORMAL, capi.AOV_SH_NORMAL, capi.AOV_INTEGRATOR_RGBA]
+    film, _ = po.OracleScene(scenes.cbox_uniform(c["W"], c["H"])).render_aov(rd, types, nthreads=1)
+    assert film.shape == (c["H"], c["W"], 21)
+    same_bits(np.stack([film[y, x] for y, x in c["probes"]]), c["probe_values"], "AOV film probe pixels")
+    assert hashlib.sha256(np.ascontiguousarray(film, f32).tobytes()).hexdigest() == c["sha256"]

@@ -340,6 +340,12 @@ def main():
         g["render"].append({"scene": which, "W": W, "H": H, "spp": spp, "sha256": hashlib.sha256(film.tobytes()).hexdigest(), "probes": probes,
                             "probe_values": bits(np.stack([film[y, x] for y, x in probes])), "mean": bits(film.mean(axis=(0, 1)))})
         print(f"render {which} {W}x{H}x{spp}: mean XYZAW = {film.mean(axis=(0, 1))}")
+        if which == "cbox":  # the same loop with AOVIntegrator (every camera ray of this scene hits: no uninitialised reads)
+            afilm = np.empty((H, W, 21), f32)
+            assert L.ref_render_aov(C.c_void_p(handle), W, H, spp, C.c_float(0.5), CB(camera), fp(afilm)) == 0
+            assert np.isfinite(afilm).all()
+            g["render_aov"] = {"scene": which, "W": W, "H": H, "spp": spp, "sha256": hashlib.sha256(afilm.tobytes()).hexdigest(), "probes": probes,
+                               "probe_values": bits(np.stack([afilm[y, x] for y, x in probes]))}
 
     # HDRFilm::image (films/hdrfilm.cpp:48-90 over film.cpp and the reference's own ImageBlock storage): the develop step
     g["hdrfilm_image"] = []
