@@ -40,7 +40,7 @@
 extern "C" {
 #endif
 
-#define MSK_ABI_VERSION 4
+#define MSK_ABI_VERSION 5
 
 typedef enum {
     MSK_OK            = 0,
@@ -233,6 +233,9 @@ typedef struct MskScene MskScene;
 int         msk_gpu_abi_version(void);
 const char *msk_gpu_last_error(void);
 
+/* number of CUDA devices visible to the process (0 without a driver); the host plugin's `devices` property and
+ * MSK_DEVICES are resolved against it */
+int  msk_gpu_device_count(void);
 int  msk_gpu_init(int device, MskCtx **out);
 void msk_gpu_shutdown(MskCtx *ctx);
 /* the CUDA stream all work of this ctx is enqueued on (a cudaStream_t) */
@@ -282,9 +285,20 @@ int    msk_gpu_film_share_create(MskCtx *ctx, size_t nfloats, MskFilmShare **out
 float *msk_gpu_film_share_ptr(MskFilmShare *share); /* device pointer of the local film (render into it with *_dev) */
 int    msk_gpu_film_share_export(MskFilmShare *share, MskIpcMemHandle *out);
 int    msk_gpu_film_share_open(MskFilmShare *share, const MskIpcMemHandle *peers, uint32_t npeers);
+/* one process driving several GPUs: the root maps its peers' shares (same process, one MskCtx per device) with
+ * cudaDeviceEnablePeerAccess instead of IPC handles; peers in device order, as for msk_gpu_film_share_open */
+int    msk_gpu_film_share_attach(MskFilmShare *share, MskFilmShare *const *peers, uint32_t npeers);
 int    msk_gpu_reduce_film(MskFilmShare *share, int is_root, uint32_t epoch);
 int    msk_gpu_film_share_check(MskFilmShare *share);
 void   msk_gpu_film_share_destroy(MskFilmShare *share);
+
+/* ---- one call, several GPUs of one process: what SamplingIntegrator::render does with every core of the machine
+ * (integrator.cpp:54-75) done with every listed GPU.  scenes[i] was created from the SAME description on its own
+ * context (one MskCtx per device); GPU i renders the i-th balanced sub-range of rd's [sample_begin, sample_end) of
+ * every pixel on its own host thread, scenes[0]'s GPU sums the films in list order with the peer-memory kernel above
+ * and the result is copied to film_host (XYZAW, as msk_gpu_render).  Identical to the one-GPU film up to float
+ * summation order (per-(pixel, sample) seeding).  stats: counters summed, ms_render = the slowest GPU. */
+int    msk_gpu_render_multi(MskScene *const *scenes, uint32_t nscenes, const MskRenderDesc *rd, float *film_host, MskStats *stats);
 
 #ifdef __cplusplus
 }

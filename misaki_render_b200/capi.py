@@ -25,6 +25,7 @@ EXPORTED_SYMBOLS = [
     "msk_gpu_aov_channels", "msk_gpu_render_aov", "msk_gpu_render_aov_dev",
     "msk_gpu_film_share_create", "msk_gpu_film_share_ptr", "msk_gpu_film_share_export", "msk_gpu_film_share_open",
     "msk_gpu_reduce_film", "msk_gpu_film_share_check", "msk_gpu_film_share_destroy",
+    "msk_gpu_device_count", "msk_gpu_film_share_attach", "msk_gpu_render_multi",
 ]
 
 # enums
@@ -33,7 +34,7 @@ BSDF_DIFFUSE, BSDF_CONDUCTOR, BSDF_ROUGHCONDUCTOR, BSDF_ROUGHDIELECTRIC, BSDF_DI
 EMITTER_AREA, EMITTER_CONSTANT = range(2)
 RENDER_STAGE_TIMERS = 1
 RENDER_TRAVERSAL_STATS = 2
-ABI_VERSION = 4
+ABI_VERSION = 5
 INTEGRATOR_PATH, INTEGRATOR_VOLPATH = range(2)
 AOV_DEPTH, AOV_POSITION, AOV_UV, AOV_GEO_NORMAL, AOV_SH_NORMAL, AOV_INTEGRATOR_RGBA = range(6)
 AOV_NAMES = {"depth": AOV_DEPTH, "position": AOV_POSITION, "uv": AOV_UV, "geo_normal": AOV_GEO_NORMAL, "sh_normal": AOV_SH_NORMAL,
@@ -168,6 +169,9 @@ def load(path: os.PathLike | None = None) -> C.CDLL:
     lib.msk_gpu_film_share_check.argtypes = [C.c_void_p]
     lib.msk_gpu_film_share_destroy.argtypes = [C.c_void_p]
     lib.msk_gpu_film_share_destroy.restype = None
+    lib.msk_gpu_device_count.argtypes = []
+    lib.msk_gpu_film_share_attach.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.c_uint32]
+    lib.msk_gpu_render_multi.argtypes = [C.POINTER(C.c_void_p), C.c_uint32, C.POINTER(MskRenderDesc), C.c_void_p, C.POINTER(MskStats)]
     if path is None:
         _lib = lib
     return lib
@@ -306,6 +310,24 @@ class Scene:
         rgba = np.empty((self.height, self.width, 4), dtype=np.float32)
         check(self.lib, self.lib.msk_gpu_develop(self.handle, film.ctypes.data, rgba.ctypes.data))
         return rgba
+
+
+def device_count() -> int:
+    return int(load().msk_gpu_device_count())
+
+
+def render_multi(scenes, rd: MskRenderDesc, film: np.ndarray | None = None):
+    """msk_gpu_render_multi: `scenes` are capi.Scene objects of the same description, one per context / GPU; GPU i
+    renders the i-th sub-range of rd's samples, the first scene's GPU sums the films over peer memory.  Host film out
+    (H x W x 5 float32).  Returns (film, stats)."""
+    s0 = scenes[0]
+    if film is None:
+        film = np.zeros((s0.height, s0.width, 5), dtype=np.float32)
+    assert film.dtype == np.float32 and film.flags.c_contiguous and film.shape == (s0.height, s0.width, 5)
+    arr = (C.c_void_p * len(scenes))(*[s.handle for s in scenes])
+    stats = MskStats()
+    check(s0.lib, s0.lib.msk_gpu_render_multi(arr, len(scenes), C.byref(rd), film.ctypes.data, C.byref(stats)))
+    return film, stats
 
 
 class FilmShare:

@@ -5,6 +5,7 @@
 #include "msk_render.h"
 #include "spectral_tables.h"
 
+#include <atomic>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -13,6 +14,7 @@
 #include <limits>
 #include <new>
 #include <string>
+#include <thread>
 #include <vector>
 
 namespace msk {
@@ -92,6 +94,12 @@ extern "C" {
 
 int msk_gpu_abi_version(void) { return MSK_ABI_VERSION; }
 const char *msk_gpu_last_error(void) { return g_error.c_str(); }
+
+int msk_gpu_device_count(void) {
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return count;
+}
 
 int msk_gpu_init(int device, MskCtx **out) {
     if (!out) return fail(MSK_ERR_ARG, "msk_gpu_init: null output");
@@ -343,6 +351,7 @@ int msk_gpu_scene_create(MskCtx *ctx, const MskSceneDesc *d, MskScene **out) {
     if (2 * s->bvh.depth + 2 > (uint32_t) 64) // node groups + postponed triangle groups, msk_traverse.cuh kStackSize
         return bail(fail(MSK_ERR_UNSUPPORTED, "BVH depth %u exceeds the traversal stack", s->bvh.depth));
     s->d.nodes = s->bvh.nodes; s->d.tris = s->bvh.tris;
+    s->d.k47 = 0x47000000u;
     cudaError_t es = cudaStreamSynchronize(ctx->stream);
     if (es != cudaSuccess) return bail(cuda_fail(es, "cudaStreamSynchronize", __FILE__, __LINE__));
     *out = s;
@@ -360,7 +369,7 @@ int msk_gpu_accel_info(MskScene *s, MskAccelInfo *out) {
     if (!s || !out) return fail(MSK_ERR_ARG, "null argument");
     *out = MskAccelInfo{};
     out->ntris = s->bvh.ntris; out->nnodes = s->bvh.nnodes;
-    out->node_bytes = s->bvh.nnodes * 80ull; out->tri_bytes = s->bvh.ntris * 48ull;
+    out->node_bytes = s->bvh.nnodes * 80ull; out->tri_bytes = s->bvh.tri_slots * 48ull;
     out->ms_build = s->bvh.ms_build; out->sah_cost = s->bvh.sah_cost; out->max_depth = s->bvh.depth;
     return MSK_OK;
 }
@@ -461,6 +470,77 @@ int msk_gpu_render(MskScene *s, const MskRenderDesc *rd, float *film_host, MskSt
     if (e == cudaSuccess && !rc) e = cudaStreamSynchronize(st);
     if (e != cudaSuccess) return cuda_fail(e, "msk_gpu_render", __FILE__, __LINE__);
     return rc;
+}
+
+// Several GPUs of one process (include/misaki_b200.h).  One host thread per GPU: CUDA calls of different devices do not
+// serialise behind each other, and the polls of unbounded-depth jobs (Renderer::render) block only their own thread.
+int msk_gpu_render_multi(MskScene *const *scenes, uint32_t nscenes, const MskRenderDesc *rd, float *film_host, MskStats *stats) {
+    if (!scenes || !nscenes || !rd || !film_host) return fail(MSK_ERR_ARG, "null argument");
+    if (nscenes > 16) return fail(MSK_ERR_UNSUPPORTED, "at most 16 GPUs per render");
+    for (uint32_t i = 0; i < nscenes; ++i) {
+        if (!scenes[i]) return fail(MSK_ERR_ARG, "scene %u is null", i);
+        if (scenes[i]->d.cam.width != scenes[0]->d.cam.width || scenes[i]->d.cam.height != scenes[0]->d.cam.height || scenes[i]->ntris != scenes[0]->ntris)
+            return fail(MSK_ERR_ARG, "scene %u differs from scene 0: every GPU needs the same description", i);
+        for (uint32_t j = 0; j < i; ++j)
+            if (scenes[j]->ctx == scenes[i]->ctx) return fail(MSK_ERR_ARG, "scenes %u and %u share a context: one MskCtx per entry", j, i);
+    }
+    if (nscenes == 1) return msk_gpu_render(scenes[0], rd, film_host, stats);
+    if (rd->sample_end < rd->sample_begin || rd->sample_end > rd->spp) return fail(MSK_ERR_ARG, "bad sample range");
+    if (!rd->clear_film) return fail(MSK_ERR_UNSUPPORTED, "msk_gpu_render_multi accumulates into a cleared film only");
+    const size_t nfloats = (size_t) scenes[0]->d.cam.width * scenes[0]->d.cam.height * 5;
+    const size_t padded = (nfloats + 3) & ~(size_t) 3; // the reduction adds float4s; the tail past the film stays zero
+    std::vector<MskFilmShare *> shares(nscenes, nullptr);
+    std::vector<int> rcs(nscenes, MSK_OK);
+    std::vector<std::string> errs(nscenes);
+    std::vector<MskStats> st(nscenes);
+    auto destroy_all = [&]() { for (auto *s : shares) msk_gpu_film_share_destroy(s); };
+    for (uint32_t i = 0; i < nscenes; ++i) {
+        int rc = msk_gpu_film_share_create(scenes[i]->ctx, padded, &shares[i]);
+        if (rc) { destroy_all(); return rc; }
+    }
+    {
+        int rc = msk_gpu_film_share_attach(shares[0], shares.data() + 1, nscenes - 1);
+        if (rc) { destroy_all(); return rc; }
+    }
+    static std::atomic<uint32_t> g_epoch{ 0 };
+    uint32_t epoch = ++g_epoch;
+    if (!epoch) epoch = ++g_epoch;
+    const uint32_t total = rd->sample_end - rd->sample_begin, base = total / nscenes, rem = total % nscenes;
+    auto worker = [&](uint32_t i) {
+        MskRenderDesc r = *rd;
+        r.sample_begin = rd->sample_begin + i * base + std::min(i, rem);
+        r.sample_end = r.sample_begin + base + (i < rem ? 1u : 0u);
+        r.clear_film = 1;
+        int rc = msk_gpu_render_dev(scenes[i], &r, msk_gpu_film_share_ptr(shares[i]), &st[i]);
+        if (!rc) rc = msk_gpu_reduce_film(shares[i], i == 0, epoch);
+        if (!rc) rc = msk_gpu_film_share_check(shares[i]); // drains this GPU's stream
+        if (!rc && i == 0) {
+            DeviceGuard guard(scenes[0]->ctx->device);
+            cudaError_t e = cudaMemcpyAsync(film_host, msk_gpu_film_share_ptr(shares[0]), nfloats * sizeof(float), cudaMemcpyDeviceToHost, scenes[0]->ctx->stream);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(scenes[0]->ctx->stream);
+            if (e != cudaSuccess) rc = cuda_fail(e, "msk_gpu_render_multi (film copy)", __FILE__, __LINE__);
+        }
+        rcs[i] = rc;
+        if (rc) errs[i] = g_error; // the error string is thread-local
+    };
+    std::vector<std::thread> threads;
+    for (uint32_t i = 1; i < nscenes; ++i) threads.emplace_back(worker, i);
+    worker(0);
+    for (auto &t : threads) t.join();
+    destroy_all();
+    for (uint32_t i = 0; i < nscenes; ++i)
+        if (rcs[i]) return fail(rcs[i], "GPU %d: %s", scenes[i]->ctx->device, errs[i].c_str());
+    if (stats) {
+        *stats = st[0];
+        for (uint32_t i = 1; i < nscenes; ++i) {
+            stats->paths += st[i].paths; stats->rays_closest += st[i].rays_closest; stats->rays_shadow += st[i].rays_shadow;
+            stats->shaded_vertices += st[i].shaded_vertices; stats->kernel_launches += st[i].kernel_launches;
+            stats->batches += st[i].batches; stats->bounces = std::max(stats->bounces, st[i].bounces);
+            stats->tail_rays_closest += st[i].tail_rays_closest; stats->tail_rays_shadow += st[i].tail_rays_shadow;
+            stats->ms_render = std::max(stats->ms_render, st[i].ms_render);
+        }
+    }
+    return MSK_OK;
 }
 
 // AOVIntegrator (integrators/aov.cpp): channel count of a description, or a negative status

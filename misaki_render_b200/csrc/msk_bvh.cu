@@ -13,7 +13,8 @@
 //        LBVH (default)  k_karras (Karras 2012) + k_refit
 //   6. k_collapse    level-synchronous top-down collapse of the binary tree into 8-wide nodes
 //                    with 8-bit quantised child boxes (80 B per node, five 128-bit loads),
-//                    children placed in octant-ordered slots (Ylitie, Karras, Laine 2017)
+//                    inner children placed in octant-ordered slots (Ylitie, Karras, Laine 2017), leaves in the
+//                    tightest run of free slots, their triangles at static slots 3j + k (msk_device.cuh)
 #include "msk_device.cuh"
 #include "msk_bvh.h"
 
@@ -45,14 +46,15 @@ __host__ __device__ __forceinline__ float ord2f(uint32_t u) {
 struct BuildState {
     uint32_t cmin[3], cmax[3];   // centroid bounds (ordered uints)
     uint32_t node_count;         // wide nodes allocated
-    uint32_t tri_count;          // triangles emitted into leaf order
+    uint32_t tri_count;          // triangle SLOTS allocated (padded per-node blocks, msk_device.cuh)
+    uint32_t tri_emitted;        // triangles written
     uint32_t queue_count;        // items produced for the next level
     uint32_t overflow;
 };
 
 __global__ void k_init_state(BuildState *st) {
     for (int a = 0; a < 3; ++a) { st->cmin[a] = 0xffffffffu; st->cmax[a] = 0u; }
-    st->node_count = 1; st->tri_count = 0; st->queue_count = 0; st->overflow = 0;
+    st->node_count = 1; st->tri_count = 0; st->tri_emitted = 0; st->queue_count = 0; st->overflow = 0;
 }
 
 // one launch per mesh: gathers vertices of its triangles into build order
@@ -288,8 +290,8 @@ struct WorkItem { uint32_t bvh2, wide; };
 // One thread builds one wide node from the binary subtree rooted at item.bvh2.
 __global__ void k_collapse(const WorkItem *__restrict__ in, uint32_t nin, WorkItem *__restrict__ out, uint32_t out_cap,
                            Bvh2 t, int n, const uint32_t *__restrict__ sorted, const float4 *__restrict__ gathered,
-                           float4 *__restrict__ nodes, uint32_t node_cap, float4 *__restrict__ tris, BuildState *st,
-                           int root_is_leaf) {
+                           float4 *__restrict__ nodes, uint32_t node_cap, float4 *__restrict__ tris, uint32_t tri_cap,
+                           BuildState *st, int root_is_leaf) {
     uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
     if (w >= nin) return;
     WorkItem item = in[w];
@@ -317,11 +319,18 @@ __global__ void k_collapse(const WorkItem *__restrict__ in, uint32_t nin, WorkIt
     }
     float4 plo = t.lo[item.bvh2], phi = t.hi[item.bvh2];
     float pc[3] = { 0.5f * (plo.x + phi.x), 0.5f * (plo.y + phi.y), 0.5f * (plo.z + phi.z) };
-    // octant-ordered slot assignment: slot s prefers the child furthest along d_s = (s&4 ? + : -, s&2 ? + : -, s&1 ? + : -)
+    // Inner children: octant-ordered slot assignment -- slot s prefers the child furthest along
+    // d_s = (s&4 ? + : -, s&2 ? + : -, s&1 ? + : -), so that visiting slots in the order s ^ octinv is front to back.
+    // Leaves are all tested before the ray descends, so their slots carry no order: they take the tightest run of
+    // the slots the inner children left free (their triangle block is padded over that run).
     float cost[8][8];
     float4 clo[8], chi[8];
+    uint32_t cnts[8];
+    uint32_t inner_cand = 0, nleaf = 0;
     for (int c = 0; c < nc; ++c) {
         clo[c] = t.lo[cand[c]]; chi[c] = t.hi[cand[c]];
+        cnts[c] = node_count(t, n, cand[c]);
+        if (cnts[c] > (uint32_t) kMaxLeafTris) inner_cand |= 1u << c; else nleaf++;
         float dx = 0.5f * (clo[c].x + chi[c].x) - pc[0], dy = 0.5f * (clo[c].y + chi[c].y) - pc[1],
               dz = 0.5f * (clo[c].z + chi[c].z) - pc[2];
         for (int s = 0; s < 8; ++s)
@@ -329,47 +338,55 @@ __global__ void k_collapse(const WorkItem *__restrict__ in, uint32_t nin, WorkIt
     }
     int slot_child[8];
     for (int s = 0; s < 8; ++s) slot_child[s] = -1;
-    uint32_t child_done = 0, slot_done = 0;
+    uint32_t child_done = 0, slot_done = 0, imask = 0, ninner = 0;
     for (int k = 0; k < nc; ++k) {
         float best = -FLT_MAX; int bc = -1, bs = -1;
         for (int c = 0; c < nc; ++c) {
-            if (child_done & (1u << c)) continue;
+            if ((child_done & (1u << c)) || !(inner_cand & (1u << c))) continue;
             for (int s = 0; s < 8; ++s) {
                 if (slot_done & (1u << s)) continue;
                 if (cost[c][s] > best) { best = cost[c][s]; bc = c; bs = s; }
             }
         }
+        if (bc < 0) break;
         slot_child[bs] = bc; child_done |= 1u << bc; slot_done |= 1u << bs;
+        imask |= 1u << bs; ninner++;
     }
-    // classify, count
-    uint32_t imask = 0, ninner = 0, ntri = 0;
-    for (int s = 0; s < 8; ++s) {
-        int c = slot_child[s];
-        if (c < 0) continue;
-        uint32_t cnt = node_count(t, n, cand[c]);
-        if (cnt > (uint32_t) kMaxLeafTris) { imask |= 1u << s; ninner++; } else ntri += cnt;
+    uint32_t span = 0, smin = 0;
+    if (nleaf) {
+        int freeslots[8], nf = 0;
+        for (int s = 0; s < 8; ++s) if (!(slot_done & (1u << s))) freeslots[nf++] = s;
+        int bi = 0, bspan = 99;
+        for (int i = 0; i + (int) nleaf <= nf; ++i) {
+            const int sp_ = freeslots[i + nleaf - 1] - freeslots[i] + 1;
+            if (sp_ < bspan) { bspan = sp_; bi = i; }
+        }
+        int k = bi;
+        for (int c = 0; c < nc; ++c)
+            if (!(inner_cand & (1u << c))) slot_child[freeslots[k++]] = c;
+        smin = (uint32_t) freeslots[bi];
+        span = 3u * (uint32_t) bspan;
     }
     uint32_t child_base = ninner ? atomicAdd(&st->node_count, ninner) : 0u;
-    uint32_t tri_base   = ntri ? atomicAdd(&st->tri_count, ntri) : 0u;
+    uint32_t tri_alloc  = span ? atomicAdd(&st->tri_count, span) : 0u;
     uint32_t qbase      = ninner ? atomicAdd(&st->queue_count, ninner) : 0u;
-    if (child_base + ninner > node_cap || qbase + ninner > out_cap) { st->overflow = 1; return; }
+    if (child_base + ninner > node_cap || qbase + ninner > out_cap || (uint64_t) tri_alloc + span > (uint64_t) tri_cap) { st->overflow = 1; return; }
+    const uint32_t tri_base = tri_alloc - 3u * smin; // slot 3j + k of this node lives at tri_base + 3j + k (mod 2^32)
 
     uint32_t ex = quant_exp(phi.x - plo.x), ey = quant_exp(phi.y - plo.y), ez = quant_exp(phi.z - plo.z);
     float sx = __uint_as_float(ex << 23), sy = __uint_as_float(ey << 23), sz = __uint_as_float(ez << 23);
-    uint32_t meta[2] = { 0, 0 }, q[6][2] = {};
-    uint32_t inner_rank = 0, tri_off = 0;
+    uint32_t q[6][2] = {};
+    uint32_t inner_rank = 0, trimask = 0, emitted = 0;
     for (int s = 0; s < 8; ++s) {
         int c = slot_child[s];
         if (c < 0) continue;
         uint32_t node = cand[c];
-        uint32_t cnt  = node_count(t, n, node);
-        uint32_t m;
+        uint32_t cnt  = cnts[c];
         if (imask & (1u << s)) {
-            m = (1u << 5) | (24u + s);
             out[qbase + inner_rank] = WorkItem{ node, child_base + inner_rank };
             inner_rank++;
         } else {
-            m = (((1u << cnt) - 1u) << 5) | tri_off;
+            trimask |= ((1u << cnt) - 1u) << (3 * s);
             // the <= kMaxLeafTris triangles of the subtree, left to right
             uint32_t todo[kMaxLeafTris + 1];
             int sp = 0;
@@ -379,16 +396,15 @@ __global__ void k_collapse(const WorkItem *__restrict__ in, uint32_t nin, WorkIt
                 const uint32_t u = todo[--sp];
                 if (u >= (uint32_t) (n - 1)) {
                     const uint32_t tri = sorted[u - (uint32_t) (n - 1)];
-                    const size_t dst = 3 * (size_t) (tri_base + tri_off + k);
+                    const size_t dst = 3 * (size_t) (uint32_t) (tri_base + 3u * (uint32_t) s + k);
                     tris[dst + 0] = gathered[3 * (size_t) tri + 0];
                     tris[dst + 1] = gathered[3 * (size_t) tri + 1];
                     tris[dst + 2] = gathered[3 * (size_t) tri + 2];
                     ++k;
                 } else { todo[sp++] = t.right[u]; todo[sp++] = t.left[u]; }
             }
-            tri_off += cnt;
+            emitted += cnt;
         }
-        meta[s >> 2] |= m << (8 * (s & 3));
         // conservative 8-bit quantisation against the grid origin plo with cell size 2^e
         float lo3[3] = { clo[c].x, clo[c].y, clo[c].z }, hi3[3] = { chi[c].x, chi[c].y, chi[c].z };
         float p3[3] = { plo.x, plo.y, plo.z }, s3[3] = { sx, sy, sz };
@@ -402,9 +418,10 @@ __global__ void k_collapse(const WorkItem *__restrict__ in, uint32_t nin, WorkIt
             q[3 + a][s >> 2] |= (uint32_t) qh << (8 * (s & 3));
         }
     }
+    if (emitted) atomicAdd(&st->tri_emitted, emitted);
     float4 *dst = nodes + (size_t) item.wide * kNodeFloat4s;
     dst[0] = make_float4(plo.x, plo.y, plo.z, __uint_as_float(ex | (ey << 8) | (ez << 16) | (imask << 24)));
-    dst[1] = make_float4(__uint_as_float(child_base), __uint_as_float(tri_base), __uint_as_float(meta[0]), __uint_as_float(meta[1]));
+    dst[1] = make_float4(__uint_as_float(child_base), __uint_as_float(tri_base), __uint_as_float((imask << 24) | trimask), 0.f);
     dst[2] = make_float4(__uint_as_float(q[0][0]), __uint_as_float(q[0][1]), __uint_as_float(q[1][0]), __uint_as_float(q[1][1]));
     dst[3] = make_float4(__uint_as_float(q[2][0]), __uint_as_float(q[2][1]), __uint_as_float(q[3][0]), __uint_as_float(q[3][1]));
     dst[4] = make_float4(__uint_as_float(q[4][0]), __uint_as_float(q[4][1]), __uint_as_float(q[5][0]), __uint_as_float(q[5][1]));
@@ -430,8 +447,8 @@ template <typename T> cudaError_t dalloc(T **p, size_t n) { return cudaMalloc((v
 
 } // namespace
 
-int bvh_build(cudaStream_t stream, const float4 *d_verts, const uint32_t *d_indices, const std::vector<DMeshInfo> &meshes,
-              BvhResult *out, int builder) {
+static int bvh_build_impl(cudaStream_t stream, const float4 *d_verts, const uint32_t *d_indices, const std::vector<DMeshInfo> &meshes,
+                          BvhResult *out, int builder, size_t tri_cap_override) {
     *out = BvhResult{};
     out->builder = builder;
     size_t n = 0;
@@ -443,11 +460,17 @@ int bvh_build(cudaStream_t stream, const float4 *d_verts, const uint32_t *d_indi
     MSK_CUDA_CHECK(cudaEventRecord(e0, stream));
 
     size_t node_cap = n ? (size_t) (0.66 * (double) n) + 16 : 1;
+    // Triangle slots are padded per node (msk_device.cuh): at most 24 per node with leaves; measured ~2.5-3 per
+    // triangle on the BASELINE meshes.  Build into a generous block, shrink to fit afterwards; the rare overflow
+    // (reported by the collapse) is retried with the worst-case bound.
+    size_t tri_cap = std::min<size_t>(6 * n + 1024, 24 * node_cap);
+    if (tri_cap_override) tri_cap = tri_cap_override;
+    if (tri_cap > 0xfffffff0ull) return fail(MSK_ERR_UNSUPPORTED, "too many triangles (%zu) for the padded leaf layout", n);
     MSK_CUDA_CHECK(dalloc(&out->nodes, node_cap * kNodeFloat4s));
-    MSK_CUDA_CHECK(dalloc(&out->tris, n * kTriFloat4s));
+    MSK_CUDA_CHECK(dalloc(&out->tris, tri_cap * kTriFloat4s));
     if (n == 0) {
         k_empty_root<<<1, 32, 0, stream>>>(out->nodes);
-        out->nnodes = 1; out->ntris = 0; out->depth = 1;
+        out->nnodes = 1; out->ntris = 0; out->tri_slots = 0; out->depth = 1;
         MSK_CUDA_CHECK(cudaEventRecord(e1, stream));
         MSK_CUDA_CHECK(cudaEventSynchronize(e1));
         cudaEventElapsedTime(&out->ms_build, e0, e1);
@@ -549,18 +572,30 @@ int bvh_build(cudaStream_t stream, const float4 *d_verts, const uint32_t *d_indi
     BuildState hst{};
     while (nin) {
         k_collapse<<<(nin + 127) / 128, 128, 0, stream>>>(qa, nin, qb, (uint32_t) qcap, t, (int) n, sorted, gathered, out->nodes,
-                                                        (uint32_t) node_cap, out->tris, st, n == 1 ? 1 : 0);
+                                                        (uint32_t) node_cap, out->tris, (uint32_t) tri_cap, st, n == 1 ? 1 : 0);
         BVH_CHECK(cudaMemcpyAsync(&hst, st, sizeof(hst), cudaMemcpyDeviceToHost, stream));
         BVH_CHECK(cudaStreamSynchronize(stream));
-        if (hst.overflow) { cleanup(); cudaFree(out->nodes); cudaFree(out->tris); *out = BvhResult{};
-            return fail(MSK_ERR_OOM, "BVH node pool overflow (n=%zu)", n); }
+        if (hst.overflow) {
+            cleanup(); cudaFree(out->nodes); cudaFree(out->tris); *out = BvhResult{};
+            if (tri_cap < 24 * node_cap && hst.node_count <= node_cap) // the padded triangle block was too small: worst-case bound
+                return bvh_build_impl(stream, d_verts, d_indices, meshes, out, builder, 24 * node_cap);
+            return fail(MSK_ERR_OOM, "BVH node pool overflow (n=%zu)", n);
+        }
         nin = hst.queue_count;
         BVH_CHECK(cudaMemsetAsync(&st->queue_count, 0, sizeof(uint32_t), stream));
         std::swap(qa, qb);
         depth++;
     }
-    if (hst.tri_count != n) { cleanup(); cudaFree(out->nodes); cudaFree(out->tris); *out = BvhResult{};
-        return fail(MSK_ERR_CUDA, "BVH collapse emitted %u of %zu triangles", hst.tri_count, n); }
+    if (hst.tri_emitted != n) { cleanup(); cudaFree(out->nodes); cudaFree(out->tris); *out = BvhResult{};
+        return fail(MSK_ERR_CUDA, "BVH collapse emitted %u of %zu triangles", hst.tri_emitted, n); }
+    if ((tri_cap - hst.tri_count) * sizeof(float4) * kTriFloat4s > (64u << 20)) { // shrink to fit
+        float4 *fit = nullptr;
+        BVH_CHECK(dalloc(&fit, (size_t) hst.tri_count * kTriFloat4s));
+        BVH_CHECK(cudaMemcpyAsync(fit, out->tris, (size_t) hst.tri_count * kTriFloat4s * sizeof(float4), cudaMemcpyDeviceToDevice, stream));
+        BVH_CHECK(cudaStreamSynchronize(stream));
+        cudaFree(out->tris);
+        out->tris = fit;
+    }
     float hsah = 0.f;
     float4 rlo, rhi;
     BVH_CHECK(cudaMemcpyAsync(&hsah, sah, sizeof(float), cudaMemcpyDeviceToHost, stream));
@@ -569,7 +604,7 @@ int bvh_build(cudaStream_t stream, const float4 *d_verts, const uint32_t *d_indi
     BVH_CHECK(cudaEventRecord(e1, stream));
     BVH_CHECK(cudaEventSynchronize(e1));
     cudaEventElapsedTime(&out->ms_build, e0, e1);
-    out->nnodes = hst.node_count; out->ntris = n; out->depth = depth;
+    out->nnodes = hst.node_count; out->ntris = n; out->tri_slots = hst.tri_count; out->depth = depth;
     float ra = (rhi.x - rlo.x) * (rhi.y - rlo.y) + (rhi.y - rlo.y) * (rhi.z - rlo.z) + (rhi.z - rlo.z) * (rhi.x - rlo.x);
     out->sah_cost = ra > 0.f ? hsah / ra : 0.f;
     out->lo[0] = rlo.x; out->lo[1] = rlo.y; out->lo[2] = rlo.z;
@@ -577,6 +612,11 @@ int bvh_build(cudaStream_t stream, const float4 *d_verts, const uint32_t *d_indi
     cleanup();
 #undef BVH_CHECK
     return MSK_OK;
+}
+
+int bvh_build(cudaStream_t stream, const float4 *d_verts, const uint32_t *d_indices, const std::vector<DMeshInfo> &meshes,
+              BvhResult *out, int builder) {
+    return bvh_build_impl(stream, d_verts, d_indices, meshes, out, builder, 0);
 }
 
 void bvh_free(BvhResult *r) {

@@ -7,8 +7,8 @@ namespace msk {
 
 struct BvhResult {
     float4  *nodes = nullptr;  // nnodes x 5 float4 (80-byte wide nodes), device
-    float4  *tris  = nullptr;  // ntris  x 3 float4 in leaf order, device
-    uint64_t nnodes = 0, ntris = 0;
+    float4  *tris  = nullptr;  // tri_slots x 3 float4: the padded per-node triangle blocks (msk_device.cuh), device
+    uint64_t nnodes = 0, ntris = 0, tri_slots = 0;
     uint32_t depth = 0;        // levels of the wide tree
     int      builder = 0;      // MSK_BVH_PLOC / MSK_BVH_LBVH
     uint32_t build_rounds = 0; // PLOC: clustering rounds

@@ -16,14 +16,18 @@ namespace msk {
 int cuda_fail(cudaError_t err, const char *expr, const char *file, int line);
 int fail(int code, const char *fmt, ...);
 
-// ---- wide BVH node: 80 bytes = five 16-byte loads (Ylitie, Karras, Laine 2017 layout) ----
+// ---- wide BVH node: 80 bytes = five 16-byte loads (quantised boxes as in Ylitie, Karras, Laine 2017) ----
 //  n0: p.x p.y p.z | ex ey ez imask          origin of the quantisation grid, exponents, internal-child mask
-//  n1: child_base | tri_base | meta[0..3] | meta[4..7]
+//  n1: child_base | tri_base | valid | -
 //  n2: qlo_x[0..7]            | qlo_y[0..7]
 //  n3: qlo_z[0..7]            | qhi_x[0..7]
 //  n4: qhi_y[0..7]            | qhi_z[0..7]
-// meta[i]: 0 = empty; internal child: 0b001sssss with sssss = 24 + slot; leaf: top 3 bits = triangle
-// count in unary (1, 3 or 7), low 5 bits = offset of its first triangle from tri_base (< 24).
+// Child slot j (0..7) is either empty, an inner node -- bit j of imask; its node is child_base + the number of inner
+// slots below j -- or a leaf of 1..kMaxLeafTris triangles stored at triangle slots tri_base + 3j + k.  `valid` =
+// imask << 24 | bit 3j + k for every triangle present, so a traversal step ORs the STATIC word
+// 1 << (24 + j) | 7 << 3j for every child box the ray enters and masks with `valid` once.  Triangle storage is
+// therefore padded: a node owns the slot range [3 jmin, 3 jmax + 3) of its leaf slots (tri_base is biased by
+// -3 jmin, modulo 2^32); the builder packs the leaves of a node into the tightest run of free slots.
 constexpr int kNodeFloat4s = 5;
 constexpr int kTriFloat4s  = 3; // v0.xyz, prim | v1.xyz, geom | v2.xyz, -
 constexpr int kMaxLeafTris = 3;
@@ -77,6 +81,7 @@ struct DScene {
     uint32_t bsdf_type_mask; // bit t: some mesh uses a BSDF of MskBsdfType t
     int32_t  sensor_medium;  // medium the camera sits in, or -1 (sensor.cpp:12-18)
     uint32_t has_textures;   // some spectrum is uv-dependent (MSK_SPEC_CHECKERBOARD): resolve ids per surface point
+    uint32_t k47;            // 0x47000000: the byte -> float bias of the node decode, opaque to ptxas (msk_traverse.cuh: qfloat)
     DCamera  cam;
 };
 

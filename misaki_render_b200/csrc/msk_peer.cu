@@ -15,7 +15,13 @@
 //
 // Flags are polled with volatile (L1-bypassing) loads and published after __threadfence_system(); film data is read
 // with ld.global.cg.  Every spin has a wall-clock bound (MSK_PEER_TIMEOUT_S, default 30 s) after which the kernel gives up and
-// raises an error word that the host reports, so a crashed peer cannot hang the GPU.
+// raises an error word that the host reports, so a crashed peer cannot hang the GPU.  The time-out decision is
+// GRID-WIDE: every block records the outcome of its spin, the blocks meet at a counter, and either all of them add the
+// peers' films or none does; after a time-out the peers are NOT released (their own wait then times out and reports
+// too) and the film is left as the root rendered it.  msk_gpu_film_share_check reports and clears the error.
+//
+// One process driving several GPUs (the host plugin's `devices` property, msk_gpu_render_multi) uses the same kernels
+// on pointers made visible with cudaDeviceEnablePeerAccess instead of IPC handles (msk_gpu_film_share_attach).
 #include "msk_device.cuh"
 
 #include <algorithm>
@@ -43,6 +49,7 @@ struct PeerCtrl {
     uint32_t consumed;  // written by the root: epoch it has finished reading
     uint32_t error;     // a spin timed out
     uint32_t done_blocks; // root only: blocks of k_film_reduce that have finished
+    uint32_t arrived;     // root only: blocks of k_film_reduce whose spin has ended (grid-wide time-out decision)
 };
 
 __device__ __forceinline__ unsigned long long globaltimer_ns() {
@@ -81,7 +88,13 @@ __global__ void __launch_bounds__(256) k_film_reduce(float4 *film, PeerCtrl *sel
     if (threadIdx.x == 0) {
         int good = 1;
         for (uint32_t p = 0; p < peers.n; ++p) good &= spin_until(&peers.ctrl[p]->ready, epoch, timeout_ns) ? 1 : 0;
-        ok = good;
+        if (!good) atomicExch(&self->error, 1u);
+        __threadfence();
+        // every block of the grid is resident (<= 4 blocks of 256 threads per SM), so this counter is a grid barrier:
+        // once all spins have ended, all blocks read the same error word
+        atomicAdd(&self->arrived, 1u);
+        if (!spin_until(&self->arrived, gridDim.x, timeout_ns)) atomicExch(&self->error, 1u);
+        ok = *reinterpret_cast<volatile uint32_t *>(&self->error) == 0u;
         __threadfence_system(); // acquire: order the film loads below after the flag loads
     }
     __syncthreads();
@@ -94,15 +107,14 @@ __global__ void __launch_bounds__(256) k_film_reduce(float4 *film, PeerCtrl *sel
             }
             film[i] = acc;
         }
-    } else if (threadIdx.x == 0) {
-        self->error = 1;
     }
     __syncthreads();
     if (threadIdx.x == 0) {
         __threadfence_system();
-        if (atomicAdd(&self->done_blocks, 1u) == gridDim.x - 1) { // last block: release the peers' films
-            self->done_blocks = 0;
-            for (uint32_t p = 0; p < peers.n; ++p) *reinterpret_cast<volatile uint32_t *>(&peers.ctrl[p]->consumed) = epoch;
+        if (atomicAdd(&self->done_blocks, 1u) == gridDim.x - 1) { // last block: release the peers' films (not after a time-out)
+            self->done_blocks = 0; self->arrived = 0;
+            if (ok)
+                for (uint32_t p = 0; p < peers.n; ++p) *reinterpret_cast<volatile uint32_t *>(&peers.ctrl[p]->consumed) = epoch;
         }
     }
 }
@@ -116,6 +128,7 @@ struct MskFilmShare {
     size_t nfloats = 0;
     unsigned char *base = nullptr; // [PeerCtrl | pad to 256 B][film]
     std::vector<void *> peer_bases;
+    bool peers_are_ipc = true;     // false: in-process peers (msk_gpu_film_share_attach), nothing to close
     uint32_t *h_error = nullptr;
     unsigned long long timeout_ns = 0;
 };
@@ -165,8 +178,9 @@ int msk_gpu_film_share_open(MskFilmShare *s, const MskIpcMemHandle *peers, uint3
     int prev = -1;
     cudaGetDevice(&prev);
     cudaSetDevice(s->device);
-    for (void *p : s->peer_bases) cudaIpcCloseMemHandle(p);
+    if (s->peers_are_ipc) for (void *p : s->peer_bases) cudaIpcCloseMemHandle(p);
     s->peer_bases.clear();
+    s->peers_are_ipc = true;
     int rc = MSK_OK;
     for (uint32_t i = 0; i < npeers && rc == MSK_OK; ++i) {
         cudaIpcMemHandle_t h;
@@ -176,6 +190,37 @@ int msk_gpu_film_share_open(MskFilmShare *s, const MskIpcMemHandle *peers, uint3
         if (e != cudaSuccess) rc = cuda_fail(e, "cudaIpcOpenMemHandle (peer film)", __FILE__, __LINE__);
         else s->peer_bases.push_back(p);
     }
+    if (prev >= 0 && prev != s->device) cudaSetDevice(prev);
+    return rc;
+}
+
+// In-process variant of msk_gpu_film_share_open: the peers' shares live in this process (one MskCtx per device), so the root
+// maps their memory with cudaDeviceEnablePeerAccess instead of IPC handles.  A peer on the root's own device (two contexts on
+// one GPU: the single-GPU test of the multi-device path) needs no mapping.
+int msk_gpu_film_share_attach(MskFilmShare *s, MskFilmShare *const *peers, uint32_t npeers) {
+    if (!s || (npeers && !peers)) return fail(MSK_ERR_ARG, "null argument");
+    if (npeers > 15) return fail(MSK_ERR_UNSUPPORTED, "at most 16 GPUs per reduction");
+    int prev = -1;
+    cudaGetDevice(&prev);
+    cudaSetDevice(s->device);
+    if (s->peers_are_ipc) for (void *p : s->peer_bases) cudaIpcCloseMemHandle(p);
+    s->peer_bases.clear();
+    s->peers_are_ipc = false;
+    int rc = MSK_OK;
+    for (uint32_t i = 0; i < npeers && rc == MSK_OK; ++i) {
+        MskFilmShare *p = peers[i];
+        if (!p || p->nfloats != s->nfloats) { rc = fail(MSK_ERR_ARG, "peer film %u: null or of another size", i); break; }
+        if (p->device != s->device) {
+            int can = 0;
+            cudaError_t e = cudaDeviceCanAccessPeer(&can, s->device, p->device);
+            if (e != cudaSuccess || !can) { rc = fail(MSK_ERR_UNSUPPORTED, "device %d cannot access the memory of device %d (no NVLink / PCIe peer path)", s->device, p->device); break; }
+            e = cudaDeviceEnablePeerAccess(p->device, 0);
+            if (e == cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); e = cudaSuccess; }
+            if (e != cudaSuccess) { rc = cuda_fail(e, "cudaDeviceEnablePeerAccess", __FILE__, __LINE__); break; }
+        }
+        s->peer_bases.push_back(p->base);
+    }
+    if (rc != MSK_OK) s->peer_bases.clear();
     if (prev >= 0 && prev != s->device) cudaSetDevice(prev);
     return rc;
 }
@@ -216,7 +261,11 @@ int msk_gpu_film_share_check(MskFilmShare *s) {
     PeerCtrl *self = reinterpret_cast<PeerCtrl *>(s->base);
     MSK_CUDA_CHECK(cudaMemcpyAsync(s->h_error, &self->error, sizeof(uint32_t), cudaMemcpyDeviceToHost, s->stream));
     MSK_CUDA_CHECK(cudaStreamSynchronize(s->stream));
-    if (*s->h_error) return fail(MSK_ERR_CUDA, "film reduction timed out waiting for a peer GPU");
+    if (*s->h_error) { // report once, then clear so that the share is usable again (the counters of the aborted launch too)
+        MSK_CUDA_CHECK(cudaMemsetAsync(&self->error, 0, 3 * sizeof(uint32_t), s->stream));
+        MSK_CUDA_CHECK(cudaStreamSynchronize(s->stream));
+        return fail(MSK_ERR_CUDA, "film reduction timed out waiting for a peer GPU; the film holds this GPU's samples only");
+    }
     return MSK_OK;
 }
 
@@ -226,7 +275,7 @@ void msk_gpu_film_share_destroy(MskFilmShare *s) {
     cudaGetDevice(&prev);
     cudaSetDevice(s->device);
     cudaStreamSynchronize(s->stream);
-    for (void *p : s->peer_bases) cudaIpcCloseMemHandle(p);
+    if (s->peers_are_ipc) for (void *p : s->peer_bases) cudaIpcCloseMemHandle(p);
     cudaFree(s->base);
     if (s->h_error) cudaFreeHost(s->h_error);
     if (prev >= 0 && prev != s->device) cudaSetDevice(prev);

@@ -195,9 +195,11 @@ struct IntersectIO {
 
 template <bool STATS>
 __global__ void __launch_bounds__(128, MSK_TRAV_MIN_BLOCKS) k_intersect(const __grid_constant__ DScene sc, Pool pool, int cur, int coherent) {
+    MSK_TRAV_SHARED;
+    const Accel ac{ sc.nodes, sc.tris, sc.k47, perm_lut_init(msk_s_perm) };
     Ctrl *c = pool.ctrl;
     IntersectIO<STATS> io{ pool, pool.rays[cur], &sc };
-    trace_queue<false, STATS>(sc.nodes, sc.tris, c->n_rays[cur], &c->cursor_isect, io, coherent != 0);
+    trace_queue<false, STATS>(ac, msk_s_stack, c->n_rays[cur], &c->cursor_isect, io, coherent != 0);
     if (STATS) add_traversal_stats(&c->nodes_closest, &c->tris_closest, io.cn_total, io.ct_total);
 }
 
@@ -720,7 +722,11 @@ __global__ void __launch_bounds__(128, MSK_VOL_MIN_BLOCKS) k_shade_vol(const __g
 // L[path] as the wavefront stages, so the film is bit-identical.  Divergence is irrelevant at this size; what
 // matters is that there is no queue traffic, no sort and no launch boundary between the vertices of a path.
 template <bool STATS, bool VOL>
-__global__ void __launch_bounds__(128) k_tail(const __grid_constant__ DScene sc, Pool pool, BatchParams bp, int cur) {
+__global__ void __launch_bounds__(kTravThreads) k_tail(const __grid_constant__ DScene sc, Pool pool, BatchParams bp, int cur) {
+    MSK_TRAV_SHARED;
+    const Accel ac{ sc.nodes, sc.tris, sc.k47, perm_lut_init(msk_s_perm) };
+    MSK_TRAV_LOCAL_STACK;
+    TravStack stack(msk_local_stack, msk_s_stack);
     Ctrl *c = pool.ctrl;
     const uint32_t n = c->n_rays[cur];
     uint32_t n_closest = 0, n_shadow = 0, max_depth = 0, cn = 0, ct = 0, sn = 0, stt = 0;
@@ -755,7 +761,7 @@ __global__ void __launch_bounds__(128) k_tail(const __grid_constant__ DScene sc,
         if (have) {
             RayHit h;
             uint32_t a = 0, b = 0;
-            const bool found = traverse<false, STATS>(sc.nodes, sc.tris, ro.x, ro.y, ro.z, rd.x, rd.y, rd.z, ro.w, rd.w, h, &a, &b);
+            const bool found = traverse<false, STATS>(ac, stack, ro.x, ro.y, ro.z, rd.x, rd.y, rd.z, ro.w, rd.w, h, &a, &b);
             n_closest++;
             if (STATS) { cn += a; ct += b; }
             max_depth = max(max_depth, misc.w & 0xffffu);
@@ -767,7 +773,7 @@ __global__ void __launch_bounds__(128) k_tail(const __grid_constant__ DScene sc,
             if (vo.add_L) L = L + vo.L;
             if (vo.emit_shadow) { // k_shadow: unoccluded => L += contribution
                 RayHit sh;
-                const bool occluded = traverse<true, STATS>(sc.nodes, sc.tris, vo.sray.o[0], vo.sray.o[1], vo.sray.o[2], vo.sray.d[0], vo.sray.d[1],
+                const bool occluded = traverse<true, STATS>(ac, stack, vo.sray.o[0], vo.sray.o[1], vo.sray.o[2], vo.sray.d[0], vo.sray.d[1],
                                                             vo.sray.d[2], vo.sray.tmin, vo.sray.tmax, sh, &a, &b);
                 n_shadow++;
                 if (STATS) { sn += a; stt += b; }
@@ -826,9 +832,11 @@ struct ShadowIO {
 
 template <bool STATS>
 __global__ void __launch_bounds__(128, MSK_TRAV_MIN_BLOCKS) k_shadow(const __grid_constant__ DScene sc, Pool pool, int coherent) {
+    MSK_TRAV_SHARED;
+    const Accel ac{ sc.nodes, sc.tris, sc.k47, perm_lut_init(msk_s_perm) };
     Ctrl *c = pool.ctrl;
     ShadowIO<STATS> io{ pool };
-    trace_queue<true, STATS>(sc.nodes, sc.tris, c->n_shadow, &c->cursor_shadow, io, coherent != 0);
+    trace_queue<true, STATS>(ac, msk_s_stack, c->n_shadow, &c->cursor_shadow, io, coherent != 0);
     if (STATS) add_traversal_stats(&c->nodes_shadow, &c->tris_shadow, io.cn_total, io.ct_total);
 }
 
@@ -1079,8 +1087,10 @@ template <bool STATS>
 __global__ void __launch_bounds__(128, MSK_TRAV_MIN_BLOCKS) k_query_closest(const __grid_constant__ DScene sc, const MskRay *__restrict__ rays,
                                                        MskHit *__restrict__ hits, uint32_t n, uint32_t *cursor,
                                                        uint32_t *nnodes, uint32_t *ntris) {
+    MSK_TRAV_SHARED;
+    const Accel ac{ sc.nodes, sc.tris, sc.k47, perm_lut_init(msk_s_perm) };
     QueryClosestIO<STATS> io{ rays, hits, nnodes, ntris };
-    trace_queue<false, STATS>(sc.nodes, sc.tris, n, cursor, io, false);
+    trace_queue<false, STATS>(ac, msk_s_stack, n, cursor, io, false);
 }
 
 struct QueryAnyIO {
@@ -1097,8 +1107,10 @@ struct QueryAnyIO {
 
 __global__ void __launch_bounds__(128, MSK_TRAV_MIN_BLOCKS) k_query_any(const __grid_constant__ DScene sc, const MskRay *__restrict__ rays,
                                                    uint8_t *__restrict__ occ, uint32_t n, uint32_t *cursor) {
+    MSK_TRAV_SHARED;
+    const Accel ac{ sc.nodes, sc.tris, sc.k47, perm_lut_init(msk_s_perm) };
     QueryAnyIO io{ rays, occ };
-    trace_queue<true, false>(sc.nodes, sc.tris, n, cursor, io, false);
+    trace_queue<true, false>(ac, msk_s_stack, n, cursor, io, false);
 }
 
 template <typename T> cudaError_t dalloc(T **p, size_t n) { return cudaMalloc((void **) p, std::max<size_t>(n, 1) * sizeof(T)); }

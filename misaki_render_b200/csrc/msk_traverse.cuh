@@ -15,8 +15,20 @@ namespace msk {
 
 constexpr int kStackSize = 64; // node groups + postponed triangle groups: at most 2 per level of the wide tree
 
-#ifndef MSK_FETCH_THRESHOLD
-#define MSK_FETCH_THRESHOLD 20
+// Lockstep driver: idle lanes are refilled once at least this many lanes of the warp are idle (or none is busy).
+// begin() -- reciprocal direction, octant, the nine coefficients of the watertight shear -- is ~100 instructions; run
+// for two or three lanes at a time it cost a quarter of the warp's issue slots (round-1 profile: 17.6 of 32 lanes
+// active per instruction).
+#ifndef MSK_REFILL_MIN
+#define MSK_REFILL_MIN 8
+#endif
+// Entries of the traversal stack kept in shared memory (per lane; the rest spills to local memory).  0: all local.
+#ifndef MSK_SMEM_STACK
+#define MSK_SMEM_STACK 8
+#endif
+// Octant permutation of the inner-child hit byte: 1 = table in shared memory (one LDS), 0 = three delta swaps on the ALU.
+#ifndef MSK_PERM_LUT
+#define MSK_PERM_LUT 1
 #endif
 #ifndef MSK_STATIC_MIN_GROUP
 #define MSK_STATIC_MIN_GROUP 4 /* 32 disables the adaptive group size of short static queues */
@@ -108,15 +120,72 @@ __device__ __forceinline__ float nz(float d) { // keep reciprocal directions fin
     return fabsf(d) < 1e-18f ? copysignf(1e-18f, d) : d;
 }
 
-__device__ __forceinline__ uint32_t extract_byte(uint32_t x, int i) { return (x >> (8 * i)) & 0xffu; }
+// What a traversal kernel needs of the scene.
+struct Accel {
+    const float4 *nodes, *tris;
+    uint32_t k47; // 0x47000000, read from a kernel parameter so that ptxas cannot fold it (see qfloat)
+    uint32_t lut; // shared-memory address of the octant permutation table (perm_lut_init)
+};
 
-// Byte j of q as the float 32768 + b, built with ONE byte-permute on the ALU pipe: the byte lands in bits
+// Byte J of q as the float 32768 + b, built with ONE byte-permute on the ALU pipe: the byte lands in bits
 // 8..15 of 0x47000000 (= 2^15, whose ulp is 2^-8... i.e. mantissa bit 8 has weight 1).  An int->float
 // convert (I2F) would go through the quarter-rate XU pipe, which ncu showed 87 % busy in the first version of
 // this kernel (profiles/r01a_ncu_k_intersect.txt); 48 of them per node visit made XU the bound.
-template <int J> __device__ __forceinline__ float qfloat(uint32_t q) {
-    return __uint_as_float(__byte_perm(q, 0x47000000u, 0x7504u | (J << 4)));
+// PRMT takes ONE immediate.  With both the selector and 0x47000000 known, ptxas put the constant into the
+// immediate and re-materialised the selector from a uniform register before every PRMT (48 IMAD.U32 per node
+// visit, a fifth of the node test's issue slots in the round-1 SASS); with k47 an opaque kernel parameter the
+// selector is the immediate and k47 stays in one register.
+template <int J> __device__ __forceinline__ float qfloat(uint32_t q, uint32_t k47) {
+    uint32_t r;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(q), "r"(k47), "n"(0x7504 | (J << 4)));
+    return __uint_as_float(r);
 }
+
+// Octant permutation table: perm[o][h] moves bit s of the byte h to bit s ^ o.  The inner-child hit bits of a
+// node are produced in slot order (static bit positions, see node_step) and must be visited in the order
+// slot ^ octinv descending; one LDS replaces a dozen ALU instructions per node visit on the pipe that bounds
+// the kernel.
+constexpr int kPermLutBytes = 8 * 256;
+__device__ __forceinline__ uint32_t perm_byte(uint32_t h, uint32_t o) {
+    if (o & 1u) h = ((h & 0x55u) << 1) | ((h >> 1) & 0x55u);
+    if (o & 2u) h = ((h & 0x33u) << 2) | ((h >> 2) & 0x33u);
+    if (o & 4u) h = ((h & 0x0fu) << 4) | (h >> 4);
+    return h;
+}
+__device__ __forceinline__ uint32_t perm_lut_init(uint8_t *lut) { // call from every thread of the block
+    for (uint32_t i = threadIdx.x; i < (uint32_t) kPermLutBytes; i += blockDim.x) lut[i] = (uint8_t) perm_byte(i & 0xffu, i >> 8);
+    __syncthreads();
+    return (uint32_t) __cvta_generic_to_shared(lut);
+}
+
+// Traversal stack: the first MSK_SMEM_STACK entries of every lane live in shared memory (entry k of the block's
+// lanes is contiguous: conflict-free 64-bit accesses), deeper entries in local memory.  The round-1 kernels kept
+// all 64 entries (512 B per thread) in local memory, i.e. in the same L1 the node fetches go through.
+constexpr int kSmemStack = MSK_SMEM_STACK;
+constexpr int kTravThreads = 128; // block size of every kernel that traverses
+constexpr int kLocalStack = kStackSize - kSmemStack;
+struct TravStack {
+    uint2 *local;  // this lane's local-memory entries (kLocalStack of them)
+    uint32_t smem; // shared address of this lane's entry 0
+    __device__ __forceinline__ TravStack(uint2 *local_entries, uint2 *shared_entries)
+        : local(local_entries), smem(kSmemStack ? (uint32_t) __cvta_generic_to_shared(shared_entries + threadIdx.x) : 0u) {}
+    __device__ __forceinline__ void store(int i, uint2 v) {
+        if (kSmemStack && i < kSmemStack)
+            asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(smem + (uint32_t) i * (kTravThreads * 8u)), "r"(v.x), "r"(v.y) : "memory");
+        else local[i - kSmemStack] = v;
+    }
+    __device__ __forceinline__ uint2 load(int i) const {
+        uint2 v;
+        if (kSmemStack && i < kSmemStack)
+            asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(smem + (uint32_t) i * (kTravThreads * 8u)) : "memory");
+        else v = local[i - kSmemStack];
+        return v;
+    }
+};
+#define MSK_TRAV_LOCAL_STACK uint2 msk_local_stack[msk::kLocalStack > 0 ? msk::kLocalStack : 1]
+#define MSK_TRAV_SHARED                                                        \
+    __shared__ uint8_t msk_s_perm[msk::kPermLutBytes];                           \
+    __shared__ uint2 msk_s_stack[msk::kSmemStack ? msk::kSmemStack * msk::kTravThreads : 1]
 
 // Per-lane traversal state.  A lane owns one ray at a time; the warp refills idle lanes from the queue
 // (dynamic fetch, Aila & Laine 2009) instead of waiting for its slowest ray.
@@ -136,8 +205,7 @@ struct Traversal {
         ox = ro.x; oy = ro.y; oz = ro.z; tmin = ro.w;
         tmax = rd.w; tfar0 = rd.w;
         // MUFU.RCP (1 ulp) instead of three IEEE divisions: the slab test already carries float rounding of the
-        // same size, and begin() runs with few lanes active (3.7 of 32 in the first profile), so every
-        // instruction here costs a whole issue slot
+        // same size, and begin() runs with few lanes active, so every instruction here costs a whole issue slot
         idx = rcp_approx(nz(rd.x)); idy = rcp_approx(nz(rd.y)); idz = rcp_approx(nz(rd.z));
         // signs of the clamped direction (-0 counts as negative)
         const uint32_t oct = (idx < 0.f ? 4u : 0u) | (idy < 0.f ? 2u : 0u) | (idz < 0.f ? 1u : 0u);
@@ -155,24 +223,29 @@ struct Traversal {
     __device__ __forceinline__ bool is_hit() const { return found && hit.t != tfar0; }
 };
 
-constexpr int kFetchThreshold = MSK_FETCH_THRESHOLD; // while-while mode: leave the loop to refill when fewer lanes are busy
-constexpr int kTriThreshold   = MSK_TRI_THRESHOLD;   // run a triangle phase once this many lanes have triangles pending
+constexpr int kTriThreshold = MSK_TRI_THRESHOLD; // run a triangle phase once this many lanes have triangles pending
+constexpr int kRefillMin    = MSK_REFILL_MIN;
 
 // Visit the next pending inner node of s.ngroup: pushes what remains of the group, tests the node's 8
 // quantised child boxes, leaves the children hit in s.ngroup and the triangles hit in s.tgroup.
+//
+// Hit bits have STATIC positions (node layout in msk_device.cuh): the child in slot j raises bit 24 + j and bits
+// 3j..3j+2 with one predicated OR of an immediate, and one AND with the node's `valid` word keeps the inner bit of
+// inner children and the bits of the triangles a leaf child really holds.  (Round 1 decoded a bit position and a
+// triangle count per child from meta bytes: five ALU instructions per child on the pipe that bounds this kernel.)
+// The inner byte is then permuted into traversal order slot ^ octinv.
 template <bool STATS>
-__device__ __forceinline__ void node_step(const float4 *__restrict__ nodes, Traversal &s, uint2 *stack) {
+__device__ __forceinline__ void node_step(const Accel &ac, Traversal &s, TravStack &stack) {
     const bool negx = s.idx < 0.f, negy = s.idy < 0.f, negz = s.idz < 0.f;
-    const uint32_t octinv4 = s.octinv * 0x01010101u;
     const uint32_t hits  = s.ngroup.y;
     const uint32_t imask = s.ngroup.y & 0xffu;
     const uint32_t bit   = 31u - __clz(hits);
     s.ngroup.y &= ~(1u << bit);
-    if (s.ngroup.y > 0x00ffffffu) stack[s.sp++] = s.ngroup;
+    if (s.ngroup.y > 0x00ffffffu) stack.store(s.sp++, s.ngroup);
     const uint32_t slot = (bit - 24u) ^ s.octinv;
     const uint32_t rel  = __popc(imask & ~(0xffffffffu << slot));
     const uint32_t node = s.ngroup.x + rel;
-    const float4 *np = nodes + (size_t) node * kNodeFloat4s;
+    const float4 *np = ac.nodes + (size_t) node * kNodeFloat4s;
     const float4 n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3), n4 = __ldg(np + 4);
     if (STATS) s.cnt_nodes++;
     const uint32_t e = __float_as_uint(n0.w);
@@ -185,16 +258,12 @@ __device__ __forceinline__ void node_step(const float4 *__restrict__ nodes, Trav
                 aoz = fmaf(-32768.f, adz, (n0.z - s.oz) * s.idz);
     const float ex = fabsf(adx) * 0.00390625f, ey = fabsf(ady) * 0.00390625f, ez = fabsf(adz) * 0.00390625f;
     const float nox = aox - ex, fox = aox + ex, noy = aoy - ey, foy = aoy + ey, noz = aoz - ez, foz = aoz + ez;
+    const uint32_t k47 = ac.k47;
     s.ngroup.x = __float_as_uint(n1.x);
     s.tgroup.x = __float_as_uint(n1.y);
     uint32_t hitmask = 0;
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
-        const uint32_t meta4 = __float_as_uint(h ? n1.w : n1.z);
-        const uint32_t is_inner4   = (meta4 & (meta4 << 1)) & 0x10101010u;
-        const uint32_t inner_mask4 = (is_inner4 >> 4) * 0xffu;
-        const uint32_t bit_index4  = (meta4 ^ (octinv4 & inner_mask4)) & 0x1f1f1f1fu;
-        const uint32_t child_bits4 = (meta4 >> 5) & 0x07070707u;
         const uint32_t qlox = __float_as_uint(h ? n2.y : n2.x), qloy = __float_as_uint(h ? n2.w : n2.z),
                        qloz = __float_as_uint(h ? n3.y : n3.x), qhix = __float_as_uint(h ? n3.w : n3.z),
                        qhiy = __float_as_uint(h ? n4.y : n4.x), qhiz = __float_as_uint(h ? n4.w : n4.z);
@@ -204,26 +273,33 @@ __device__ __forceinline__ void node_step(const float4 *__restrict__ nodes, Trav
         const uint32_t nzq = negz ? qhiz : qloz, fz = negz ? qloz : qhiz;
 #define MSK_CHILD(J)                                                                                              \
     {                                                                                                             \
-        const float t0x = fmaf(qfloat<J>(nx), adx, nox), t1x = fmaf(qfloat<J>(fx), adx, fox);                     \
-        const float t0y = fmaf(qfloat<J>(ny), ady, noy), t1y = fmaf(qfloat<J>(fy), ady, foy);                     \
-        const float t0z = fmaf(qfloat<J>(nzq), adz, noz), t1z = fmaf(qfloat<J>(fz), adz, foz);                    \
+        const float t0x = fmaf(qfloat<J>(nx, k47), adx, nox), t1x = fmaf(qfloat<J>(fx, k47), adx, fox);           \
+        const float t0y = fmaf(qfloat<J>(ny, k47), ady, noy), t1y = fmaf(qfloat<J>(fy, k47), ady, foy);           \
+        const float t0z = fmaf(qfloat<J>(nzq, k47), adz, noz), t1z = fmaf(qfloat<J>(fz, k47), adz, foz);          \
         const float tn = fmaxf(fmaxf(t0x, t0y), fmaxf(t0z, s.tmin));                                              \
         const float tf = fminf(fminf(t1x, t1y), fminf(t1z, s.tmax));                                              \
-        if (tn <= tf) hitmask |= extract_byte(child_bits4, J) << extract_byte(bit_index4, J);                     \
+        if (tn <= tf) hitmask |= (1u << (24 + 4 * h + J)) | (7u << (3 * (4 * h + J)));                            \
     }
         MSK_CHILD(0) MSK_CHILD(1) MSK_CHILD(2) MSK_CHILD(3)
 #undef MSK_CHILD
     }
-    s.ngroup.y = (hitmask & 0xff000000u) | (e >> 24);
+    hitmask &= __float_as_uint(n1.z); // valid: imask << 24 | bit 3j + k for triangle k of the leaf in slot j
+    uint32_t inner;
+#if MSK_PERM_LUT
+    asm("ld.shared.u8 %0, [%1];" : "=r"(inner) : "r"(ac.lut + (s.octinv << 8) + (hitmask >> 24)));
+#else
+    inner = perm_byte(hitmask >> 24, s.octinv);
+#endif
+    s.ngroup.y = (inner << 24) | (e >> 24);
     s.tgroup.y = hitmask & 0x00ffffffu;
 }
 
 // Test the highest pending triangle of s.tgroup.  Returns true when it is hit (tmax shrinks).
 template <bool STATS>
-__device__ __forceinline__ bool tri_step(const float4 *__restrict__ tris, Traversal &s) {
+__device__ __forceinline__ bool tri_step(const Accel &ac, Traversal &s) {
     const uint32_t k = 31u - __clz(s.tgroup.y);
     s.tgroup.y &= ~(1u << k);
-    const float4 *tp = tris + (size_t) (s.tgroup.x + k) * kTriFloat4s;
+    const float4 *tp = ac.tris + (size_t) (s.tgroup.x + k) * kTriFloat4s; // slot 3j + k of the node's triangle block (mod 2^32)
     const float4 v0 = __ldg(tp), v1 = __ldg(tp + 1), v2 = __ldg(tp + 2);
     if (STATS) s.cnt_tris++;
     float t, u, v;
@@ -237,27 +313,31 @@ __device__ __forceinline__ bool tri_step(const float4 *__restrict__ tris, Traver
     return false;
 }
 
-// One ray to completion, classic while-while order (used where rays are not queued).
+// One ray to completion, classic while-while order.
 template <bool ANY, bool STATS>
-__device__ __forceinline__ bool traverse(const float4 *__restrict__ nodes, const float4 *__restrict__ tris, float ox, float oy,
-                                         float oz, float dx, float dy, float dz, float tmin, float tmax, RayHit &hit,
-                                         uint32_t *nnodes = nullptr, uint32_t *ntris = nullptr) {
-    uint2 stack[kStackSize];
-    Traversal s;
-    s.begin(make_float4(ox, oy, oz, tmin), make_float4(dx, dy, dz, tmax));
+__device__ __forceinline__ void traverse_one(const Accel &ac, Traversal &s, TravStack &stack) {
     for (;;) {
-        if (s.ngroup.y > 0x00ffffffu) node_step<STATS>(nodes, s, stack);
+        if (s.ngroup.y > 0x00ffffffu) node_step<STATS>(ac, s, stack);
         else { s.tgroup = s.ngroup; s.ngroup = make_uint2(0u, 0u); }
         bool stop = false;
         while (s.tgroup.y) {
-            if (tri_step<STATS>(tris, s) && ANY) { stop = true; break; }
+            if (tri_step<STATS>(ac, s) && ANY) { stop = true; break; }
         }
         if (stop) break;
         if (s.ngroup.y <= 0x00ffffffu) {
             if (s.sp == 0) break;
-            s.ngroup = stack[--s.sp];
+            s.ngroup = stack.load(--s.sp);
         }
     }
+}
+
+// (used where rays are not queued: the per-path tail kernel)
+template <bool ANY, bool STATS>
+__device__ __forceinline__ bool traverse(const Accel &ac, TravStack &stack, float ox, float oy, float oz, float dx, float dy, float dz,
+                                         float tmin, float tmax, RayHit &hit, uint32_t *nnodes = nullptr, uint32_t *ntris = nullptr) {
+    Traversal s;
+    s.begin(make_float4(ox, oy, oz, tmin), make_float4(dx, dy, dz, tmax));
+    traverse_one<ANY, STATS>(ac, s, stack);
     if (s.is_hit()) hit = s.hit;
     if (STATS) { *nnodes = s.cnt_nodes; *ntris = s.cnt_tris; }
     return s.is_hit();
@@ -271,8 +351,9 @@ __device__ __forceinline__ bool traverse(const float4 *__restrict__ nodes, const
 // The warp advances in LOCKSTEP phases, each entered by a vote, so that the two expensive code blocks run
 // with as many lanes as possible (ncu on the first while-while version: 8 of 32 lanes active in the node
 // test, 3 of 32 in the triangle test -- profiles/r01a_ncu_k_intersect.txt):
-//   refill    idle lanes take the next ray (indices come from a per-warp chunk reserved with one atomic; the
-//             ray itself was prefetched into registers while the previous ray was in flight)
+//   refill    once kRefillMin lanes are idle they commit their results and take the next rays (indices come from a
+//             per-warp chunk reserved with one atomic; the ray itself was prefetched into registers while the
+//             previous ray was in flight)
 //   node      every lane with a pending inner node visits one (8 child boxes)
 //   triangle  runs only when >= kTriThreshold lanes hold pending triangles or a lane has nothing else to do;
 //             every lane with pending triangles tests one.  Triangles found meanwhile wait on the stack.
@@ -285,8 +366,7 @@ constexpr uint32_t kChunk = 128; // ray indices reserved per atomic
 
 // Static assignment: the warp takes 32 consecutive rays and every lane runs its ray to completion.
 template <bool ANY, bool STATS, typename IO>
-__device__ __forceinline__ void trace_queue_static(const float4 *__restrict__ nodes, const float4 *__restrict__ tris, uint32_t n,
-                                                   uint32_t *cursor, IO &io, uint2 *stack) {
+__device__ __forceinline__ void trace_queue_static(const Accel &ac, uint32_t n, uint32_t *cursor, IO &io, TravStack &stack) {
     Traversal s;
     const uint32_t lane = threadIdx.x & 31u;
     // A queue shorter than one ray per lane of the grid is latency-bound: the launch lasts as long as its slowest
@@ -312,19 +392,7 @@ __device__ __forceinline__ void trace_queue_static(const float4 *__restrict__ no
             float4 ro, rd;
             io.load(q, ro, rd);
             s.begin(ro, rd);
-            for (;;) {
-                if (s.ngroup.y > 0x00ffffffu) node_step<STATS>(nodes, s, stack);
-                else { s.tgroup = s.ngroup; s.ngroup = make_uint2(0u, 0u); }
-                bool stop = false;
-                while (s.tgroup.y) {
-                    if (tri_step<STATS>(tris, s) && ANY) { stop = true; break; }
-                }
-                if (stop) break;
-                if (s.ngroup.y <= 0x00ffffffu) {
-                    if (s.sp == 0) break;
-                    s.ngroup = stack[--s.sp];
-                }
-            }
+            traverse_one<ANY, STATS>(ac, s, stack);
         }
         __syncwarp();
         io.commit(valid, q, s);
@@ -332,8 +400,7 @@ __device__ __forceinline__ void trace_queue_static(const float4 *__restrict__ no
 }
 
 template <bool ANY, bool STATS, typename IO>
-__device__ __forceinline__ void trace_queue(const float4 *__restrict__ nodes, const float4 *__restrict__ tris, uint32_t n,
-                                            uint32_t *cursor, IO &io, bool coherent) {
+__device__ __forceinline__ void trace_queue(const Accel &ac, uint2 *shared_stack, uint32_t n, uint32_t *cursor, IO &io, bool coherent) {
     // Coherent queues (camera rays: neighbouring lanes follow the same nodes, so a static warp of 32 runs
     // converged and its node fetches coalesce) and queues too small to fill the machine (latency-bound: more,
     // shorter warps win) use the static assignment; incoherent bulk queues use the lockstep phases.
@@ -344,9 +411,10 @@ __device__ __forceinline__ void trace_queue(const float4 *__restrict__ nodes, co
 #else
     const bool use_static = coherent || n < gridDim.x * (blockDim.x / 32u) * 64u;
 #endif
-    uint2 stack[kStackSize];
+    MSK_TRAV_LOCAL_STACK;
+    TravStack stack(msk_local_stack, shared_stack);
     if (use_static) {
-        trace_queue_static<ANY, STATS>(nodes, tris, n, cursor, io, stack);
+        trace_queue_static<ANY, STATS>(ac, n, cursor, io, stack);
         return;
     }
     Traversal s;
@@ -364,7 +432,6 @@ __device__ __forceinline__ void trace_queue(const float4 *__restrict__ nodes, co
     auto take = [&](uint32_t want) -> uint32_t {
         uint32_t need = (uint32_t) __popc(want);
         if (chunk_end - chunk_next < need && more) { // reserve a new chunk (the rest of the old one is handed out first)
-            // simplification: hand out what is left, then continue from the new chunk
             uint32_t base = 0;
             if (lane == 0) base = atomicAdd(cursor, kChunk);
             base = __shfl_sync(0xffffffffu, base, 0);
@@ -395,7 +462,7 @@ __device__ __forceinline__ void trace_queue(const float4 *__restrict__ nodes, co
     for (;;) {
         // ---- refill
         const uint32_t idle = __ballot_sync(0xffffffffu, !busy);
-        if (idle) {
+        if (__popc(idle) >= kRefillMin) {
             io.commit(have, q, s);
             have = false;
             const bool start = !busy && nq != 0xffffffffu;
@@ -409,8 +476,8 @@ __device__ __forceinline__ void trace_queue(const float4 *__restrict__ nodes, co
         }
         // ---- node phase
         if (busy && s.ngroup.y > 0x00ffffffu) {
-            if (s.tgroup.y) stack[s.sp++] = s.tgroup; // postponed triangles wait on the stack
-            node_step<STATS>(nodes, s, stack);
+            if (s.tgroup.y) stack.store(s.sp++, s.tgroup); // postponed triangles wait on the stack
+            node_step<STATS>(ac, s, stack);
         }
         // ---- triangle phase
         const bool has_t = busy && s.tgroup.y != 0u;
@@ -418,13 +485,13 @@ __device__ __forceinline__ void trace_queue(const float4 *__restrict__ nodes, co
         if (mt) {
             const bool starved = has_t && s.ngroup.y <= 0x00ffffffu;
             if (__popc(mt) >= kTriThreshold || __any_sync(0xffffffffu, starved)) {
-                if (has_t && tri_step<STATS>(tris, s) && ANY) { busy = false; have = true; }
+                if (has_t && tri_step<STATS>(ac, s) && ANY) { busy = false; have = true; }
             }
         }
         // ---- pop
         if (busy && s.ngroup.y <= 0x00ffffffu) {
             if (s.sp > 0) {
-                const uint2 g = stack[s.sp - 1];
+                const uint2 g = stack.load(s.sp - 1);
                 if (g.y > 0x00ffffffu) { s.ngroup = g; --s.sp; }
                 else if (s.tgroup.y == 0u) { s.tgroup = g; --s.sp; }
             } else if (s.tgroup.y == 0u) { busy = false; have = true; }

@@ -59,6 +59,7 @@ def render_sharded(scene: capi.Scene, rd: capi.MskRenderDesc, film_dev, rank: in
         stats = scene.render_dev(shard_desc(rd, rank, world), film_dev.data_ptr())
         if peer is not None:  # film_dev is peer.tensor(): the library's NVLink peer-memory reduction
             peer.reduce()
+            peer.check()  # drains the stream; raises if a device-side wait timed out (the film would be this rank's only)
         else:
             reduce_film(film_dev, 0, group)
         if host_out is not None and rank == 0:
