@@ -40,7 +40,7 @@ import numpy as np  # noqa: E402
 METRIC, UNIT = "paths/s", "paths/s"
 # algorithmic bytes per unit of work
 BYTES_RAY_IN, BYTES_HIT_OUT, BYTES_OCC_OUT = 32, 20, 4
-BYTES_NODE, BYTES_TRI = 80, 48  # this build's wide node / pre-gathered triangle (DESIGN.md "Data layout")
+BYTES_NODE, BYTES_TRI = 80, 36  # 80 B wide node, 36 B of packed vertices per triangle (this build stores a triangle in 48 B, DESIGN.md "Data layout")
 BYTES_SHADE_VERTEX = 400
 BYTES_RAYGEN_SAMPLE = 112
 
@@ -230,6 +230,127 @@ def run_reference_code(args, sd, rdk, wname):
     print(json.dumps(line), flush=True)
 
 
+# --------------------------------------------------------------------------------------------- rooflines
+SM_ISSUE_SLOTS_PER_CLK = 4  # warp schedulers per SM, one warp instruction per clock each
+
+
+def source_sha() -> str:
+    """Hash of the CUDA sources: ties the ncu-measured instruction / DRAM counters under profiles/ to the build they describe."""
+    import hashlib
+    h = hashlib.sha256()
+    for f in sorted((ROOT / "misaki_render_b200" / "csrc").iterdir()):
+        if f.suffix in (".cu", ".cuh", ".h"):
+            h.update(f.name.encode()); h.update(f.read_bytes())
+    return h.hexdigest()[:16]
+
+
+def load_counters(wl: str):
+    """profiles/ncu_counters.json (tools/ncu_counters.py, one `ncu --metrics` pass per workload over exactly one step):
+    per kernel the warp / thread instructions executed, the DRAM bytes and the launches of that step.  Used only if it
+    was taken on THIS source tree (source_sha); otherwise the issue / DRAM rooflines are reported as unavailable rather
+    than from a stale capture."""
+    f = ROOT / "profiles" / "ncu_counters.json"
+    try:
+        d = json.loads(f.read_text())
+    except (OSError, ValueError):
+        return None, "profiles/ncu_counters.json missing"
+    if d.get("source_sha") != source_sha():
+        return None, f"profiles/ncu_counters.json was captured on another source tree ({d.get('source_sha')} != {source_sha()})"
+    return d.get("workloads", {}).get(wl), None
+
+
+def peaks():
+    f = ROOT / "MEASURED_PEAKS.json"
+    if f.exists():
+        d = json.loads(f.read_text())
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)", float(d.get("sm_max_mhz", 1965.0))
+    return 6650.0, "fallback (B200_PROFILING.md)", 1965.0
+
+
+def kernel_roofline(kernel: str, ms: float, launches: int, alg_bytes: float, counters, counters_note, sm_count: int = 148):
+    """Both bounds of SURVEY 8(d) for one kernel (all its launches of a step, `ms` = their summed CUDA-event time measured
+    live): HBM -- algorithmic bytes / time, and DRAM bytes (ncu) / time, vs the measured copy peak; SM issue -- warp
+    instructions (ncu) / time vs SMs x 4 schedulers x max clock.  `bound` = the larger fraction."""
+    hbm_peak, peak_src, sm_mhz = peaks()
+    issue_peak = sm_count * SM_ISSUE_SLOTS_PER_CLK * sm_mhz * 1e6 / 1e9  # G warp-instructions / s
+    alg = alg_bytes / (ms * 1e-3) / 1e9 if ms > 0 else 0.0
+    out = {"kernel": kernel, "launches_per_step": int(launches), "avg_launch_ms": ms / max(launches, 1),
+           "hbm": {"algorithmic_gbs": alg, "algorithmic_frac": alg / hbm_peak, "algorithmic_bytes_per_launch": alg_bytes / max(launches, 1),
+                   "dram_gbs": None, "dram_frac": None, "peak": hbm_peak, "peak_source": peak_src},
+           "issue": {"gwarp_inst_per_s": None, "frac": None, "threads_per_inst": None, "thread_inst_per_ray": None,
+                     "peak": issue_peak, "peak_source": f"{sm_count} SMs x 4 schedulers x {sm_mhz:.0f} MHz"}}
+    c = (counters or {}).get(kernel)
+    if c:
+        inst, tinst, dram = float(c["inst_executed"]), float(c["thread_inst_executed"]), float(c["dram_bytes"])
+        out["issue"].update(gwarp_inst_per_s=inst / (ms * 1e-3) / 1e9, frac=inst / (ms * 1e-3) / 1e9 / issue_peak,
+                            threads_per_inst=tinst / max(inst, 1.0), warp_inst_per_step=inst, ncu_launches=int(c["launches"]))
+        out["hbm"].update(dram_gbs=dram / (ms * 1e-3) / 1e9, dram_frac=dram / (ms * 1e-3) / 1e9 / hbm_peak, dram_bytes_per_launch=dram / max(launches, 1))
+        out["counters"] = "profiles/ncu_counters.json (same source tree; counts are per step and seed-deterministic, time is live)"
+    else:
+        out["counters"] = counters_note or "no ncu counters for this kernel"
+    fi, fh = out["issue"]["frac"], out["hbm"]["dram_frac"]
+    if fi is not None and fi >= (fh or 0.0):
+        out.update(bound="issue", achieved=out["issue"]["gwarp_inst_per_s"], peak=issue_peak, unit="Gwarp-inst/s", frac=fi)
+    elif fh is not None:
+        out.update(bound="hbm", achieved=out["hbm"]["dram_gbs"], peak=hbm_peak, unit="GB/s", frac=fh)
+    else:  # no counters: the algorithmic-traffic rate is all that can be stated
+        out.update(bound="hbm", achieved=alg, peak=hbm_peak, unit="GB/s", frac=alg / hbm_peak)
+    out["traffic"] = out["hbm"].get("dram_bytes_per_launch")
+    return out
+
+
+# --------------------------------------------------------------------------------------------- harness
+class Harness:
+    """Device, library context and stream of this rank + the collectives bench.py needs around the timed regions."""
+
+    def __init__(self, rank: int, local_rank: int, world: int):
+        import torch
+        import torch.distributed as dist
+        from misaki_render_b200 import capi
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py: no CUDA device -- this backend has no CPU fallback (use --impl reference for the CPU arm)")
+        self.torch, self.dist, self.capi = torch, dist, capi
+        self.rank, self.local_rank, self.world = rank, local_rank, world
+        torch.cuda.set_device(local_rank)
+        self.dev = torch.device("cuda", local_rank)
+        if world > 1:
+            dist.init_process_group("nccl", device_id=self.dev)
+        t0 = time.perf_counter()
+        self.ctx = capi.Context(local_rank)
+        self.init_ms = (time.perf_counter() - t0) * 1e3
+        self.ext = torch.cuda.ExternalStream(self.ctx.stream, device=self.dev)
+        self.flush = torch.empty(256 << 20, dtype=torch.uint8, device=self.dev)  # > 126 MB L2
+        self.sm_count = torch.cuda.get_device_properties(self.dev).multi_processor_count
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def allmax(self, x: float) -> float:
+        if self.world == 1:
+            return x
+        t = self.torch.tensor([x], dtype=self.torch.float64, device=self.dev)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def allsum(self, x: float) -> float:
+        if self.world == 1:
+            return x
+        t = self.torch.tensor([x], dtype=self.torch.float64, device=self.dev)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)
+        return float(t.item())
+
+    def close(self):
+        self.flush = None
+        self.barrier()
+        if self.world > 1:
+            self.dist.destroy_process_group()
+        self.torch.cuda.synchronize()
+        self.torch.cuda.empty_cache()
+        self.ctx.close()
+
+
 # --------------------------------------------------------------------------------------------- C5 intersection sweep
 def c5_inputs(res: int, rank: int):
     """BASELINE configs[4]: the 9 998 244-triangle displaced sphere and its two ray sets."""
@@ -286,28 +407,19 @@ def run_c5_reference(args, rank: int):
 C5_NAME = "C5 10M-triangle displaced sphere (9998244 tris, one geomID): 4096^2 primary + incoherent cosine-hemisphere secondary rays, closest hit + any hit"
 
 
-def run_c5(args, rank: int, local_rank: int, world: int):
+def c5_case(h: Harness, args, steps: int, warmup: int, want_e2e: bool, want_cpu: bool):
     """Intersection sweep: one STEP = closest-hit and any-hit queries over both ray sets (4 launches).  Rays and
     results are resident in HBM for `value`; `e2e` goes through msk_gpu_intersect / msk_gpu_occluded with pinned
     host buffers.  N > 1: every rank traces the full ray sets against its own BVH replica (weak scaling, no
     collective -- the queries are independent)."""
-    import torch
-    import torch.distributed as dist
-    from misaki_render_b200 import capi
+    torch, capi = h.torch, h.capi
     from workloads import scenes
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device -- this backend has no CPU fallback")
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+    dev, ext, rank, world = h.dev, h.ext, h.rank, h.world
     sd, prim = c5_inputs(args.c5_res, rank)
-    ctx = capi.Context(local_rank)
     t0 = time.time()
-    scene = capi.Scene(ctx, sd)
+    scene = capi.Scene(h.ctx, sd)
     t_scene = time.time() - t0
     info = scene.accel_info()
-    ext = torch.cuda.ExternalStream(ctx.stream, device=dev)
 
     def to_dev(a):
         return torch.from_numpy(a.view(np.uint8).reshape(-1)).to(dev)
@@ -325,7 +437,7 @@ def run_c5(args, rank: int, local_rank: int, world: int):
     n_sec = len(sec)
     d_sec = to_dev(sec)
     sets = [("primary", d_prim, n_prim), ("secondary", d_sec, n_sec)]
-    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(5)] for _ in range(args.steps)]
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(5)] for _ in range(steps)]
 
     def step(ev):
         with torch.cuda.stream(ext):
@@ -337,27 +449,18 @@ def run_c5(args, rank: int, local_rank: int, world: int):
                 scene.occluded_dev(d_r.data_ptr(), d_occ.data_ptr(), n); k += 1
             if ev: ev[k].record(ext)
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    for _ in range(args.warmup):
+    for _ in range(warmup):
         step(None)
-    sampler = ClockSampler(physical_gpu_index(local_rank)) if rank == 0 else None
-    barrier()
+    sampler = ClockSampler(physical_gpu_index(h.local_rank)) if rank == 0 else None
+    h.barrier()
     tm0 = time.time()
-    for i in range(args.steps):
+    for i in range(steps):
         step(evs[i])
-    barrier()
+    h.barrier()
     tm1 = time.time()
-    ms_total = sum(e[0].elapsed_time(e[4]) for e in evs)
-    if world > 1:
-        t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_total = float(t.item())
+    ms_total = h.allmax(sum(e[0].elapsed_time(e[4]) for e in evs))
     clocks = sampler.stop(tm0, tm1) if sampler else None
-    ms_step = ms_total / args.steps
+    ms_step = ms_total / steps
     rays_step = 2 * (n_prim + n_sec) * world
     value = rays_step / (ms_step * 1e-3) / 1e6
     names = ["primary_closest", "primary_any", "secondary_closest", "secondary_any"]
@@ -365,29 +468,31 @@ def run_c5(args, rank: int, local_rank: int, world: int):
     launch_ms = {nm: float(np.mean([e[i].elapsed_time(e[i + 1]) for e in evs])) for i, nm in enumerate(names)}
     launch_mrays = {nm: counts[i] / (launch_ms[nm] * 1e-3) / 1e6 for i, nm in enumerate(names)}
 
-    # ---- end to end through the host-buffer entry points (H2D of the rays, D2H of the results inside)
-    pin_r = torch.from_numpy(sec.view(np.uint8).reshape(-1)).pin_memory()
-    pin_h = torch.empty(n_sec * 20, dtype=torch.uint8).pin_memory()
-    pin_o = torch.empty(n_sec, dtype=torch.uint8).pin_memory()
-    r_np, h_np, o_np = pin_r.numpy().view(capi.RAY_DTYPE), pin_h.numpy().view(capi.HIT_DTYPE), pin_o.numpy()
-    lib = capi.load()
+    e2e = None
+    if want_e2e:  # end to end through the host-buffer entry points (H2D of the rays, D2H of the results inside)
+        pin_r = torch.from_numpy(sec.view(np.uint8).reshape(-1)).pin_memory()
+        pin_h = torch.empty(n_sec * 20, dtype=torch.uint8).pin_memory()
+        pin_o = torch.empty(n_sec, dtype=torch.uint8).pin_memory()
+        r_np, h_np, o_np = pin_r.numpy().view(capi.RAY_DTYPE), pin_h.numpy().view(capi.HIT_DTYPE), pin_o.numpy()
+        lib = capi.load()
 
-    def e2e_step():
-        capi.check(lib, lib.msk_gpu_intersect(scene.handle, r_np.ctypes.data, h_np.ctypes.data, n_sec))
-        capi.check(lib, lib.msk_gpu_occluded(scene.handle, r_np.ctypes.data, o_np.ctypes.data, n_sec))
+        def e2e_step():
+            capi.check(lib, lib.msk_gpu_intersect(scene.handle, r_np.ctypes.data, h_np.ctypes.data, n_sec))
+            capi.check(lib, lib.msk_gpu_occluded(scene.handle, r_np.ctypes.data, o_np.ctypes.data, n_sec))
 
-    e2e_step()
-    barrier()
-    w0 = time.perf_counter()
-    e2e_n = max(1, min(args.steps, 5))
-    for _ in range(e2e_n):
         e2e_step()
-    barrier()
-    e2e_s = time.perf_counter() - w0
-    e2e = {"value": 2 * n_sec * world * e2e_n / e2e_s / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": 2 * n_sec * 32, "d2h_bytes_per_step": n_sec * 21,
-           "ms_per_step": e2e_s / e2e_n * 1e3, "timer": "host wall clock",
-           "note": f"secondary set only: msk_gpu_intersect + msk_gpu_occluded with pinned host rays/results; one-off scene upload + BVH build = {t_scene * 1e3:.0f} ms "
-                   f"(BVH build {info.ms_build:.1f} ms on device)"}
+        h.barrier()
+        w0 = time.perf_counter()
+        e2e_n = max(1, min(steps, 5))
+        for _ in range(e2e_n):
+            e2e_step()
+        h.barrier()
+        e2e_s = time.perf_counter() - w0
+        e2e = {"value": 2 * n_sec * world * e2e_n / e2e_s / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": 2 * n_sec * 32, "d2h_bytes_per_step": n_sec * 21,
+               "ms_per_step": e2e_s / e2e_n * 1e3, "timer": "host wall clock",
+               "note": f"secondary set only: msk_gpu_intersect + msk_gpu_occluded with pinned host rays/results; one-off scene upload + BVH build = {t_scene * 1e3:.0f} ms "
+                       f"(BVH build {info.ms_build:.1f} ms on device)"}
+        pin_r = pin_h = pin_o = r_np = h_np = o_np = None
 
     roofline = cpu = None
     if rank == 0:
@@ -401,79 +506,59 @@ def run_c5(args, rank: int, local_rank: int, world: int):
         which = top.split("_")[0]
         n_top = n_prim if which == "primary" else n_sec
         bytes_ray = BYTES_RAY_IN + BYTES_HIT_OUT + per[which]["nodes"] * BYTES_NODE + per[which]["tris"] * BYTES_TRI
-        peaks_file = ROOT / "MEASURED_PEAKS.json"
-        if peaks_file.exists():
-            peak, peak_src = float(json.loads(peaks_file.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
-        else:
-            peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
-        achieved = n_top * bytes_ray / (launch_ms[top] * 1e-3) / 1e9
-        traffic = None
-        tf = ROOT / "profiles" / "roofline_traffic.json"
-        if tf.exists():
-            try:
-                traffic = json.loads(tf.read_text()).get("c5", {}).get(top)
-            except (ValueError, OSError):
-                traffic = None
-        roofline = {"bound": "hbm", "kernel": f"k_query_closest ({which} rays)", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                    "traffic": traffic, "peak_source": peak_src, "launches_per_step": 1, "avg_launch_ms": launch_ms[top],
-                    "algorithmic_bytes_per_launch": n_top * bytes_ray, "per_ray": per,
-                    "bytes_model": "SURVEY 8(d): 32 B ray + 20 B hit + visited wide nodes x 80 B + tested triangles x 48 B per closest-hit ray "
-                                   "(counted on a strided 1 Mi-ray sample); BVH + triangles = "
-                                   f"{(info.node_bytes + info.tri_bytes) / 1e6:.0f} MB > 126 MB L2",
-                    "launch_ms": launch_ms, "launch_mrays_per_s": launch_mrays}
-        if world == 1 and not args.no_cpu:
+        counters, note = load_counters("c5")
+        roofline = kernel_roofline(f"k_query_closest[{which}]", launch_ms[top], 1, n_top * bytes_ray, counters, note, h.sm_count)
+        roofline.update(per_ray=per, launch_ms=launch_ms, launch_mrays_per_s=launch_mrays,
+                        bytes_model=f"SURVEY 8(d): 32 B ray + 20 B hit + visited wide nodes x {BYTES_NODE} B + tested triangles x {BYTES_TRI} B per closest-hit ray "
+                                    f"(counted on a strided 1 Mi-ray sample); BVH + padded triangle slots = {(info.node_bytes + info.tri_bytes) / 1e6:.0f} MB > 126 MB L2")
+        if roofline["issue"]["frac"] is not None:
+            roofline["issue"]["thread_inst_per_ray"] = roofline["issue"]["threads_per_inst"] * roofline["issue"]["warp_inst_per_step"] / n_top
+        if world == 1 and want_cpu:
             v, inf = c5_oracle_sample(sd, {"primary": prim, "secondary": sec}, args.cpu_budget)
             cpu = {"value": v, "unit": "Mrays/s", "cores": inf["threads"], "kind": "port", "cpu": cpu_model(), "detail": inf["detail"],
                    "sample": f"strided sample of {inf['rays'] // 4} rays of each set, closest + any hit ({inf['seconds']:.1f} s)",
                    "note": "oracle SAH BVH2 + Moeller-Trumbore over all host threads; NOT Embree"}
-        line = {"metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
-                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": {"workload": C5_NAME, "rays_primary": n_prim, "rays_secondary": n_sec, "tris": int(info.ntris), "wide_nodes": int(info.nnodes),
-                           "bvh_bytes": int(info.node_bytes + info.tri_bytes), "bvh_build_ms": info.ms_build, "sah_cost": info.sah_cost,
-                           "l2": "ray sets (0.5 GB each) and the BVH (0.6 GB) exceed the 126 MB L2; no flush needed",
-                           "partition": "replicated BVH, every rank traces the full ray sets (independent queries, no collective)"},
-                "e2e": e2e, "gpu_launches": 4 * args.steps, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "wall_s_timed_region": tm1 - tm0}
-        print(json.dumps(line), flush=True)
+    out = {"metric": "Mrays/s", "value": value, "unit": "Mrays/s", "ms_per_step": ms_step, "steps": steps, "warmup": warmup, "scaling": "weak",
+           "config": {"workload": C5_NAME, "rays_primary": n_prim, "rays_secondary": n_sec, "tris": int(info.ntris), "wide_nodes": int(info.nnodes),
+                      "bvh_bytes": int(info.node_bytes + info.tri_bytes), "bvh_build_ms": info.ms_build, "sah_cost": info.sah_cost,
+                      "l2": "ray sets (0.5 GB each) and the BVH exceed the 126 MB L2; no flush needed",
+                      "partition": "replicated BVH, every rank traces the full ray sets (independent queries, no collective)"},
+           "e2e": e2e, "gpu_launches": 4 * steps, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "wall_s_timed_region": tm1 - tm0}
     # release every torch tensor that was used on the library's stream BEFORE that stream is destroyed: the caching
     # allocator records an event on each stream a block was used on when the block is freed
-    d_prim = d_sec = d_hits = d_occ = sets = pin_r = pin_h = pin_o = r_np = h_np = o_np = None
-    barrier()
-    if world > 1:
-        dist.destroy_process_group()
-    torch.cuda.synchronize()
+    d_prim = d_sec = d_hits = d_occ = sets = None
+    h.barrier()
     scene.close()
-    ctx.close()
+    return out
 
 
-# --------------------------------------------------------------------------------------------- our arm
-def run_ours(args, rank: int, local_rank: int, world: int):
-    import torch
-    import torch.distributed as dist
-    from misaki_render_b200 import capi, distributed as msk_dist
-
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device -- this backend has no CPU fallback (use --impl reference for the CPU arm)")
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-
-    sd, rdk, wname = workload(args.workload, world)
-    if args.spp:
-        rdk["spp"] = args.spp
-    spp_rank = rdk["spp"]
-    job = dict(rdk, spp=spp_rank * world)  # weak scaling: the job grows with N, each rank renders spp_rank samples
+# --------------------------------------------------------------------------------------------- render workloads
+def render_case(h: Harness, args, wl: str, steps: int, warmup: int, scaling: str, want_e2e: bool, want_roofline: bool, want_cpu: bool,
+                want_cold: bool = False, spp_override: int = 0):
+    """One render workload on this harness.  scaling "weak": every rank renders the workload's spp of an N x spp job;
+    "strong": the workload's own job (fixed spp) is split into N sample ranges.  Either way the film reduction into rank 0
+    is inside the timed region.  Returns the result dict (meaningful on rank 0)."""
+    torch, capi, dist = h.torch, h.capi, h.dist
+    from misaki_render_b200 import distributed as msk_dist
+    rank, world, dev, ext = h.rank, h.world, h.dev, h.ext
+    sd, rdk, wname = workload(wl, world)
+    if spp_override:
+        rdk["spp"] = spp_override
+    if scaling == "strong":
+        job = dict(rdk)
+        spp_rank = rdk["spp"] / world
+    else:
+        spp_rank = rdk["spp"]
+        job = dict(rdk, spp=rdk["spp"] * world)
     rd_job = capi.render_desc(**job)
     rd_rank = msk_dist.shard_desc(rd_job, rank, world)
     npix = sd.width * sd.height
-    paths_per_step = npix * spp_rank * world
+    paths_per_step = npix * job["spp"]
 
-    ctx = capi.Context(local_rank)
-    t0 = time.time()
-    scene = capi.Scene(ctx, sd)
-    t_scene = time.time() - t0
+    t0 = time.perf_counter()
+    scene = capi.Scene(h.ctx, sd)
+    t_scene = time.perf_counter() - t0
     info = scene.accel_info()
-    ext = torch.cuda.ExternalStream(ctx.stream, device=dev)
     # N > 1: the film lives in CUDA-IPC-exportable memory and is reduced by the library's own peer-memory kernel
     # (csrc/msk_peer.cu); --reduce nccl selects torch.distributed's reduce instead
     peer = None
@@ -481,7 +566,7 @@ def run_ours(args, rank: int, local_rank: int, world: int):
         # every rank must end up on the same reduction: agree on whether the IPC set-up succeeded everywhere
         err = None
         try:
-            peer = msk_dist.PeerFilm(ctx, (sd.height, sd.width, 5), rank, world)
+            peer = msk_dist.PeerFilm(h.ctx, (sd.height, sd.width, 5), rank, world)
         except Exception as e:  # noqa: BLE001 -- e.g. no peer access between two of the devices
             err, peer = e, None
         ok = torch.tensor([0 if peer is None else 1], dtype=torch.int32, device=dev)
@@ -492,16 +577,12 @@ def run_ours(args, rank: int, local_rank: int, world: int):
             if peer is not None:
                 peer.close()
             peer = None
-    if peer is not None:
-        film = peer.tensor(dev)
-    else:
-        film = torch.zeros((sd.height, sd.width, 5), dtype=torch.float32, device=dev)
+    film = peer.tensor(dev) if peer is not None else torch.zeros((sd.height, sd.width, 5), dtype=torch.float32, device=dev)
     film_host = torch.zeros((sd.height, sd.width, 5), dtype=torch.float32).pin_memory()
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
 
     def step(collect):
         with torch.cuda.stream(ext):
-            flush.zero_()  # evict the scene/BVH and queue tails from L2 between steps
+            h.flush.zero_()  # evict the scene/BVH and queue tails from L2 between steps
             st = scene.render_dev(rd_rank, film.data_ptr())
             if peer is not None:
                 peer.reduce()
@@ -510,73 +591,79 @@ def run_ours(args, rank: int, local_rank: int, world: int):
         if collect is not None:
             collect.append(st)
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    for _ in range(max(args.warmup, 0)):
+    for _ in range(max(warmup, 0)):
         step(None)
-    sampler = ClockSampler(physical_gpu_index(local_rank)) if rank == 0 else None
-    barrier()
+    sampler = ClockSampler(physical_gpu_index(h.local_rank)) if rank == 0 else None
+    h.barrier()
     stats = []
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     tm0 = time.time()
     ev0.record(ext)
-    for _ in range(args.steps):
+    for _ in range(steps):
         step(stats)
     ev1.record(ext)
-    barrier()
+    h.barrier()
     tm1 = time.time()
-    ms_total = ev0.elapsed_time(ev1)
-    if world > 1:
-        t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_total = float(t.item())
+    ms_total = h.allmax(ev0.elapsed_time(ev1))
     clocks = sampler.stop(tm0, tm1) if sampler else None
-    ms_step = ms_total / args.steps
+    ms_step = ms_total / steps
     value = paths_per_step / (ms_step * 1e-3)
-    rays_rank = sum(s.rays_closest + s.rays_shadow for s in stats) / args.steps
-    rays_t = torch.tensor([rays_rank], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(rays_t, op=dist.ReduceOp.SUM)
-    mrays = float(rays_t.item()) / (ms_step * 1e-3) / 1e6
+    mrays = h.allsum(sum(s.rays_closest + s.rays_shadow for s in stats) / steps) / (ms_step * 1e-3) / 1e6
     launches = int(sum(s.kernel_launches for s in stats))
 
     # ---- end to end: the public host-buffer entry point, D2H of the film inside the timed region
-    e2e_steps = args.steps
-    fh = film_host.numpy()
-
-    def e2e_step():
-        if world == 1:
-            scene.render(rd_rank, film=fh)  # msk_gpu_render: host film in/out
-        else:
-            msk_dist.render_sharded(scene, rd_job, film, rank, world, host_out=film_host, peer=peer)
-
-    for _ in range(min(args.warmup, 2)):
-        e2e_step()
-    barrier()
-    w0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        e2e_step()
-    barrier()
-    e2e_s = time.perf_counter() - w0
-    if world > 1:
-        t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_s = float(t.item())
+    e2e = None
     film_bytes = npix * 5 * 4
-    e2e = {"value": paths_per_step * e2e_steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(capi.C.sizeof(capi.MskRenderDesc)),
-           "d2h_bytes_per_step": film_bytes, "ms_per_step": e2e_s / e2e_steps * 1e3, "timer": "host wall clock around the call",
-           "note": "scene + BVH stay resident across steps (as Embree's scene does across Integrator::render calls); "
-                   f"one-off scene upload + BVH build = {t_scene * 1e3:.1f} ms (BVH build {info.ms_build:.2f} ms)"}
+    if want_e2e:
+        fh = film_host.numpy()
+
+        def e2e_step():
+            if world == 1:
+                scene.render(rd_rank, film=fh)  # msk_gpu_render: host film in/out
+            else:
+                msk_dist.render_sharded(scene, rd_job, film, rank, world, host_out=film_host, peer=peer)
+
+        for _ in range(min(warmup, 2)):
+            e2e_step()
+        h.barrier()
+        w0 = time.perf_counter()
+        for _ in range(steps):
+            e2e_step()
+        h.barrier()
+        e2e_s = h.allmax(time.perf_counter() - w0)
+        e2e = {"value": paths_per_step * steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(capi.C.sizeof(capi.MskRenderDesc)),
+               "d2h_bytes_per_step": film_bytes, "ms_per_step": e2e_s / steps * 1e3, "timer": "host wall clock around the call",
+               "note": "scene + BVH stay resident across steps (as Embree's scene does across Integrator::render calls); see e2e_cold for "
+                       "scene upload + BVH build + render + destroy"}
+        fh = None
+
+    # ---- cold: what one msk_gpu_scene_create + msk_gpu_render + msk_gpu_scene_destroy costs (the host plugin's render())
+    cold = None
+    if want_cold and world == 1:
+        fh = film_host.numpy()
+        times = []
+        for _ in range(3):
+            c0 = time.perf_counter()
+            sc2 = capi.Scene(h.ctx, sd)
+            c1 = time.perf_counter()
+            sc2.render(rd_rank, film=fh)
+            c2 = time.perf_counter()
+            sc2.close()
+            c3 = time.perf_counter()
+            times.append((c3 - c0, c1 - c0, c2 - c1, c3 - c2))
+        best = min(times)
+        cold = {"value": paths_per_step / best[0], "unit": UNIT, "ms_total": best[0] * 1e3, "ms_scene_create": best[1] * 1e3, "ms_render": best[2] * 1e3,
+                "ms_scene_destroy": best[3] * 1e3, "ms_first_scene_create_of_process": t_scene * 1e3, "ms_context_init": h.init_ms,
+                "h2d_bytes": int(sum(m["verts"].nbytes + m["tris"].nbytes for m in sd.meshes)), "d2h_bytes": film_bytes,
+                "note": "best of 3; msk_gpu_init (context + kernel warm-up, once per process) is listed separately"}
+        fh = None
 
     # ---- per-kernel roofline: one extra step with stage timers, one with the instrumented traversal
     roofline = None
-    if rank == 0:
+    if want_roofline and rank == 0:
         rd_t = msk_dist.shard_desc(rd_job, rank, world); rd_t.flags = capi.RENDER_STAGE_TIMERS
         with torch.cuda.stream(ext):
-            flush.zero_()
+            h.flush.zero_()
             st_t = scene.render_dev(rd_t, film.data_ptr())
         rd_s = msk_dist.shard_desc(rd_job, rank, world); rd_s.flags = capi.RENDER_TRAVERSAL_STATS
         st_s = scene.render_dev(rd_s, film.data_ptr())
@@ -592,74 +679,118 @@ def run_ours(args, rank: int, local_rank: int, world: int):
             "k_shadow": (st_t.ms_shadow, st_t.n_shadow_launches,
                          wf_s * (st_s.rays_shadow * (BYTES_RAY_IN + BYTES_OCC_OUT) + st_s.nodes_shadow * BYTES_NODE + st_s.tris_shadow * BYTES_TRI)),
         }
-        peaks_file = ROOT / "MEASURED_PEAKS.json"
-        if peaks_file.exists():
-            peak, peak_src = float(json.loads(peaks_file.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
-        else:
-            peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
-        top = max(stages, key=lambda k: stages[k][0])
-        ms, nl, nbytes = stages[top]
-        achieved = nbytes / (ms * 1e-3) / 1e9 if ms > 0 else 0.0
-        traffic = None
-        tf = ROOT / "profiles" / "roofline_traffic.json"
-        if tf.exists():
-            try:
-                traffic = json.loads(tf.read_text()).get(args.workload, {}).get(top)
-            except (ValueError, OSError):
-                traffic = None
-        stage_ms = {"raygen": st_t.ms_raygen, "intersect": st_t.ms_intersect, "sort": st_t.ms_sort, "shade": st_t.ms_shade, "shadow": st_t.ms_shadow,
-                    "film": st_t.ms_film, "tail": st_t.ms_tail, "step_with_timers": st_t.ms_render}
-        roofline = {
-            "bound": "hbm", "kernel": top, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-            "traffic": traffic, "peak_source": peak_src,
-            "launches_per_step": int(nl), "avg_launch_ms": ms / max(nl, 1), "algorithmic_bytes_per_launch": nbytes / max(nl, 1),
-            "bytes_model": "SURVEY 8(d): per closest-hit ray 32 B in + 20 B out + visited wide nodes x 80 B + tested triangles x 48 B "
-                           "(counted by the instrumented kernel on the same rays); any-hit 32 + 4; shaded vertex 400 B. "
-                           "Node/triangle bytes are served mostly from L2 for this L2-resident scene, so this is an "
-                           "algorithmic-traffic figure, not DRAM traffic (see `traffic`).",
-            "per_ray": {"nodes_closest": nodes_c, "tris_closest": tris_c, "nodes_shadow": nodes_s, "tris_shadow": tris_s},
-            "stage_ms": stage_ms,
-            "tail": {"rays_closest": int(st_t.tail_rays_closest), "rays_shadow": int(st_t.tail_rays_shadow), "launches": int(st_t.n_tail_launches),
-                     "note": "k_tail: one launch runs every path still alive once the queue is short (MSK_TAIL_THRESHOLD rays) to completion"},
-            "stage_gbs": {k: (v[2] / (v[0] * 1e-3) / 1e9 if v[0] > 0 else 0.0) for k, v in stages.items()},
-        }
+        counters, note = load_counters(wl) if (scaling == "weak" and world == 1 and not spp_override) else (None, "counters are per step of the N = 1 job")
+        per_kernel = {k: kernel_roofline(k, v[0], v[1], v[2], counters, note, h.sm_count) for k, v in stages.items() if v[0] > 0}
+        top = max(per_kernel, key=lambda k: stages[k][0])
+        roofline = dict(per_kernel[top])
+        if roofline["issue"]["frac"] is not None:
+            n_rays = {"k_intersect": wf_c * st_s.rays_closest, "k_shadow": wf_s * st_s.rays_shadow, "k_shade": wf_c * st_s.shaded_vertices}[top]
+            roofline["issue"]["thread_inst_per_ray"] = roofline["issue"]["threads_per_inst"] * roofline["issue"]["warp_inst_per_step"] / max(n_rays, 1)
+        roofline.update(
+            bytes_model=f"SURVEY 8(d): per closest-hit ray 32 B in + 20 B out + visited wide nodes x {BYTES_NODE} B + tested triangles x {BYTES_TRI} B "
+                        "(counted by the instrumented kernel on the same rays; this build stores a triangle in 48 B); any-hit 32 + 4; "
+                        "shaded vertex 400 B.  The scene is L2-resident, so node / triangle bytes are L1/L2 traffic: `hbm.algorithmic_*` is an "
+                        "algorithmic-traffic rate, `hbm.dram_*` the DRAM side measured by ncu, and the kernel is bound by SM issue.",
+            per_ray={"nodes_closest": nodes_c, "tris_closest": tris_c, "nodes_shadow": nodes_s, "tris_shadow": tris_s},
+            stage_ms={"raygen": st_t.ms_raygen, "intersect": st_t.ms_intersect, "sort": st_t.ms_sort, "shade": st_t.ms_shade, "shadow": st_t.ms_shadow,
+                      "film": st_t.ms_film, "tail": st_t.ms_tail, "step_with_timers": st_t.ms_render},
+            tail={"rays_closest": int(st_t.tail_rays_closest), "rays_shadow": int(st_t.tail_rays_shadow), "launches": int(st_t.n_tail_launches),
+                  "note": "k_tail: one launch runs every path still alive once the queue is short (MSK_TAIL_THRESHOLD rays) to completion"},
+            kernels={k: {"bound": v["bound"], "frac": v["frac"], "ms": stages[k][0], "issue_frac": v["issue"]["frac"], "threads_per_inst": v["issue"]["threads_per_inst"],
+                         "dram_frac": v["hbm"]["dram_frac"], "algorithmic_gbs": v["hbm"]["algorithmic_gbs"]} for k, v in per_kernel.items()})
 
     # ---- CPU baseline (rank 0, N = 1 only): oracle on a bounded sample
     cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu:
+    if rank == 0 and world == 1 and want_cpu:
         v, mr, inf = oracle_sample(sd, rdk, args.cpu_budget)
         cpu = {"value": v, "unit": UNIT, "cores": inf["threads"], "kind": "port", "mrays_per_s": mr, "cpu": cpu_model(),
                "sample": f"first {inf['samples']} of {rdk['spp']} samples per pixel, all {npix} pixels, same seeds "
                          f"({inf['paths']} paths, {inf['seconds']:.1f} s)",
-               "note": "oracle/ CPU restatement (own SAH BVH + Moeller-Trumbore, std::thread tiles); not TBB+Embree"}
+               "note": "oracle/ CPU restatement (own SAH BVH + Moeller-Trumbore, std::thread tiles; built -O2 without FMA contraction, it is the parity "
+                       "checker); not TBB+Embree.  The rough-conductor / dielectric glue and the camera of this restatement are unpinned (DESIGN.md)"}
 
-    if rank == 0:
-        line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-            "data": "synthetic",
-            "config": {"workload": wname, "spp_per_gpu": spp_rank, "job_spp": spp_rank * world, "partition": "sample ranges + 1 film reduce/step",
-                       "film_reduce": "none (1 GPU)" if world == 1 else ("msk_gpu_reduce_film: one kernel pulling peer films over NVLink (CUDA IPC)" if peer is not None else "ncclReduce"),
-                       "l2": "256 MiB memset between steps (inside the timed region); path queues (~1.6 GB/batch) exceed the 126 MB L2",
-                       "tris": int(info.ntris), "wide_nodes": int(info.nnodes), "bvh_build_ms": info.ms_build},
-            "mrays_per_s": mrays, "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
-            "wall_s_timed_region": tm1 - tm0,
-        }
-        print(json.dumps(line), flush=True)
+    out = {"metric": METRIC, "value": value, "unit": UNIT, "ms_per_step": ms_step, "steps": steps, "warmup": warmup, "scaling": scaling,
+           "config": {"workload": wname, "spp_per_gpu": spp_rank, "job_spp": job["spp"], "partition": "sample ranges + 1 film reduce/step",
+                      "film_reduce": "none (1 GPU)" if world == 1 else ("msk_gpu_reduce_film: one kernel pulling peer films over NVLink (CUDA IPC)" if peer is not None else "ncclReduce"),
+                      "l2": "256 MiB memset between steps (inside the timed region); the path queues of a batch exceed the 126 MB L2",
+                      "tris": int(info.ntris), "wide_nodes": int(info.nnodes), "bvh_build_ms": info.ms_build},
+           "mrays_per_s": mrays, "e2e": e2e, "e2e_cold": cold, "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+           "wall_s_timed_region": tm1 - tm0}
     # release every torch tensor that was used on the library's stream (NCCL's record_stream included) BEFORE that
     # stream is destroyed: the caching allocator records an event on each such stream when the block is freed
     if peer is not None:
         peer.check()
-    film = film_host = flush = fh = None
-    barrier()
+    film = film_host = None
+    h.barrier()
     if peer is not None:
         peer.close()
-    if world > 1:
-        dist.destroy_process_group()
-    torch.cuda.synchronize()
-    torch.cuda.empty_cache()
     scene.close()
-    ctx.close()
+    return out
+
+
+def slim(case, keys=("metric", "value", "unit", "ms_per_step", "steps", "scaling", "mrays_per_s", "gpu_launches", "config", "roofline", "e2e")):
+    return {k: case[k] for k in keys if k in case and case[k] is not None}
+
+
+def run_ours(args, rank: int, local_rank: int, world: int):
+    h = Harness(rank, local_rank, world)
+    one = args.workload == "c5"
+    if one:
+        main_case = c5_case(h, args, args.steps, args.warmup, True, not args.no_cpu)
+    else:
+        main_case = render_case(h, args, args.workload, args.steps, args.warmup, args.scaling, True, True, not args.no_cpu, want_cold=True, spp_override=args.spp)
+    sub = strong = None
+    if args.sub:
+        # The other BASELINE configurations, driver-timed inside the default run (short: they are not the headline).  C3 and C5
+        # only at N = 1 (C5's host-side mesh + ray generation takes ~1 min per rank).
+        sub = {}
+        sub["c1"] = slim(render_case(h, args, "c1", 20, 5, "weak", False, True, False))
+        if world == 1:
+            sub["c3"] = slim(render_case(h, args, "c3", 2, 1, "weak", False, True, False))
+            sub["c5"] = slim(c5_case(h, args, 3, 2, False, False))
+        # BASELINE configs[3] as written: the fixed 1920x1080x4096-spp Cornell-box job split into N sample ranges, film
+        # reduce inside the timed region -- STRONG scaling.  And C1 (16 spp split N ways): where launch latency shows.
+        strong = {"c4": slim(render_case(h, args, "c4", 1 if world < 4 else 2, 0, "strong", False, False, False)),
+                  "c1": slim(render_case(h, args, "c1", 20, 5, "strong", False, False, False))}
+    if rank == 0:
+        line = {"metric": main_case["metric"], "value": main_case["value"], "unit": main_case["unit"], "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": main_case["ms_per_step"], "higher_is_better": True, "scaling": main_case["scaling"],
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic"}
+        line.update({k: v for k, v in main_case.items() if k not in line})
+        if sub:
+            line["sub"] = sub
+        if strong:
+            line["strong_scaling"] = strong
+        print(json.dumps(line), flush=True)
+    h.close()
+
+
+def run_one_step(args):
+    """--one-step: exactly one render step (or one C5 sweep) and nothing else, for `ncu --metrics` passes (tools/ncu_counters.py)."""
+    os.environ.setdefault("MSK_WARMUP", "0")
+    from misaki_render_b200 import capi
+    import torch
+    with capi.Context(0) as ctx:
+        if args.workload == "c5":
+            from workloads import scenes
+            sd, prim = c5_inputs(args.c5_res, 0)
+            with capi.Scene(ctx, sd) as scene:
+                hits = scene.intersect(prim)
+                m = sd.meshes[0]
+                sec = scenes.secondary_rays((m["verts"], m["tris"]), prim, hits, seed=0)
+                d_sec = torch.from_numpy(sec.view(np.uint8).reshape(-1)).cuda()
+                d_hits = torch.empty(len(sec) * 20, dtype=torch.uint8, device="cuda")
+                d_occ = torch.empty(len(sec), dtype=torch.uint8, device="cuda")
+                torch.cuda.synchronize()
+                print("ONE_STEP_BEGIN", flush=True)
+                scene.intersect_dev(d_sec.data_ptr(), d_hits.data_ptr(), len(sec))
+                scene.occluded_dev(d_sec.data_ptr(), d_occ.data_ptr(), len(sec))
+                torch.cuda.synchronize()
+                d_sec = d_hits = d_occ = None
+        else:
+            sd, rdk, _ = workload(args.workload, 1)
+            with capi.Scene(ctx, sd) as scene:
+                scene.render(capi.render_desc(**rdk))
 
 
 def main():
@@ -668,7 +799,9 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="c2", choices=["c1", "c2", "c3", "c4", "c5", "vol"])
+    ap.add_argument("--workload", default=None, choices=["c1", "c2", "c3", "c4", "c5", "vol"])
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="N > 1: weak = every GPU renders the workload's spp of an N x spp job; strong = the workload's own job split N ways")
     ap.add_argument("--c5-res", type=int, default=4096, help="C5: primary rays are a res x res pinhole grid")
     ap.add_argument("--spp", type=int, default=0, help="override samples per pixel per GPU (development only)")
     ap.add_argument("--cpu-budget", type=float, default=15.0, help="seconds of CPU work for cpu_baseline")
@@ -676,22 +809,30 @@ def main():
     ap.add_argument("--ref-kind", default="port", choices=["port", "reference"],
                     help="--impl reference: the oracle port (every workload) or, for C1, the reference's own compiled code from oracle/_ref")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-sub", action="store_true", help="skip the sub-results (C1 / C3 / C5 and the strong-scaling C4 / C1 jobs) of the default run")
+    ap.add_argument("--one-step", action="store_true", help="run exactly one step of the workload and exit (for ncu passes)")
     ap.add_argument("--reduce", default="peer", choices=["peer", "nccl"], help="N > 1: film reduction by the library's NVLink peer kernel or by NCCL")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
     args.steps = max(args.steps, 1)
+    # the sub-results ride along with the default invocation only (no explicit workload): `python bench.py [--gpus N --steps K --warmup W]`
+    args.sub = args.workload is None and not args.no_sub and not args.spp and args.scaling == "weak" and args.impl == "ours"
+    if args.workload is None:
+        args.workload = "c2"
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if args.impl == "reference":
         (run_c5_reference if args.workload == "c5" else run_reference)(args, rank)
         return
+    if args.one_step:
+        return run_one_step(args)
     if world == 1 and args.gpus > 1:
         # bare `python bench.py --gpus N`: re-launch under torchrun, one rank per GPU
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
                "--master-addr", "127.0.0.1", "--master-port", os.environ.get("MASTER_PORT", "29531"), str(Path(__file__).resolve())] + sys.argv[1:]
         raise SystemExit(subprocess.call(cmd))
-    (run_c5 if args.workload == "c5" else run_ours)(args, rank, local_rank, world)
+    run_ours(args, rank, local_rank, world)
 
 
 if __name__ == "__main__":

@@ -6,6 +6,7 @@
 #include "spectral_tables.h"
 
 #include <atomic>
+#include <chrono>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -90,6 +91,8 @@ int check_spectrum(const MskSceneDesc *d, int id, const char *what) {
 
 } // namespace
 
+static void warm_up(MskCtx *ctx);
+
 extern "C" {
 
 int msk_gpu_abi_version(void) { return MSK_ABI_VERSION; }
@@ -124,6 +127,11 @@ int msk_gpu_init(int device, MskCtx **out) {
     if (e2 != cudaSuccess) { delete ctx; return cuda_fail(e2, "cudaStreamCreate", __FILE__, __LINE__); }
     int rc = ctx->renderer.init(ctx->sm_count);
     if (rc) { cudaStreamDestroy(ctx->stream); delete ctx; return rc; }
+    // CUDA loads a kernel's code at its first launch.  Spread over the ~40 kernels of a first scene + render that was
+    // 140 ms inside the first BVH build and ~0.5 s of the first msk_gpu_scene_create + msk_gpu_render (round-1 bench).
+    // Pay it here, once per context, by pushing a two-triangle scene through build + render + queries (MSK_WARMUP=0 skips).
+    const char *wu = getenv("MSK_WARMUP");
+    if (!(wu && *wu && !atoi(wu))) warm_up(ctx);
     *out = ctx;
     return MSK_OK;
 }
@@ -144,10 +152,17 @@ int msk_gpu_scene_create(MskCtx *ctx, const MskSceneDesc *d, MskScene **out) {
     if (!ctx || !d || !out) return fail(MSK_ERR_ARG, "msk_gpu_scene_create: null argument");
     *out = nullptr;
     DeviceGuard guard(ctx->device);
+    // MSK_DEBUG_SETUP=1: host wall-clock breakdown of this call on stderr (validation | upload | BVH build | total)
+    const bool debug_setup = getenv("MSK_DEBUG_SETUP") && atoi(getenv("MSK_DEBUG_SETUP"));
+    const auto t_begin = std::chrono::steady_clock::now();
+    auto since = [&](std::chrono::steady_clock::time_point t0) { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count(); };
     // ---- validation (malformed descriptions must fail loudly, not read out of bounds on the device)
     if (d->camera.width == 0 || d->camera.height == 0) return fail(MSK_ERR_ARG, "film size must be positive");
     if (!(d->camera.filter_radius > 0.f) || d->camera.filter_radius > 4.f)
         return fail(MSK_ERR_UNSUPPORTED, "filter radius %g outside (0, 4]", d->camera.filter_radius);
+    if ((d->nmeshes && !d->meshes) || (d->nbsdfs && !d->bsdfs) || (d->nspectra && !d->spectra) || (d->nemitters && !d->emitters) ||
+        (d->ntable_floats && !d->spectrum_tables))
+        return fail(MSK_ERR_ARG, "scene description: null array with a non-zero count");
     for (uint32_t i = 0; i < d->nspectra; ++i) {
         const MskSpectrum &s = d->spectra[i];
         if (s.kind < 0 || s.kind > MSK_SPEC_CHECKERBOARD) return fail(MSK_ERR_ARG, "spectrum %u: unknown kind %d", i, s.kind);
@@ -164,6 +179,9 @@ int msk_gpu_scene_create(MskCtx *ctx, const MskSceneDesc *d, MskScene **out) {
         if (b.type < 0 || b.type >= MSK_BSDF_TYPE_COUNT) return fail(MSK_ERR_ARG, "bsdf %u: unknown type %d", i, b.type);
         int rc = check_spectrum(d, b.reflectance, "bsdf reflectance");
         if (rc) return rc;
+        // ids a BSDF type does not use must still be -1 or valid: the texture pass resolves every id >= 0 (bsdf_resolve_textures)
+        for (int32_t id : { b.transmittance, b.eta, b.k })
+            if (id < -1 || id >= (int32_t) d->nspectra) return fail(MSK_ERR_ARG, "bsdf %u: spectrum id %d out of range (unused ids must be -1)", i, id);
         if (b.type == MSK_BSDF_CONDUCTOR || b.type == MSK_BSDF_ROUGHCONDUCTOR) {
             if ((rc = check_spectrum(d, b.eta, "conductor eta")) || (rc = check_spectrum(d, b.k, "conductor k"))) return rc;
         }
@@ -217,6 +235,8 @@ int msk_gpu_scene_create(MskCtx *ctx, const MskSceneDesc *d, MskScene **out) {
         const MskMesh &m = d->meshes[i];
         if (m.bsdf < 0 || (uint32_t) m.bsdf >= d->nbsdfs) return bail(fail(MSK_ERR_ARG, "mesh %u: bsdf id out of range", i));
         if (m.emitter >= (int32_t) d->nemitters) return bail(fail(MSK_ERR_ARG, "mesh %u: emitter id out of range", i));
+        if (m.emitter >= 0 && (d->emitters[m.emitter].type != MSK_EMITTER_AREA || d->emitters[m.emitter].shape != (int32_t) i))
+            return bail(fail(MSK_ERR_ARG, "mesh %u: emitter %d is not an area emitter of this mesh", i, m.emitter));
         if ((m.nverts && !m.verts) || (m.ntris && !m.tris)) return bail(fail(MSK_ERR_ARG, "mesh %u: null buffer", i));
         infos[i].vert_offset = (uint32_t) nverts; infos[i].tri_offset = (uint32_t) ntris; infos[i].ntris = m.ntris;
         infos[i].bsdf = m.bsdf; infos[i].emitter = m.emitter;
@@ -263,6 +283,7 @@ int msk_gpu_scene_create(MskCtx *ctx, const MskSceneDesc *d, MskScene **out) {
             infos[i].inv_area = 1.f / area_sum;
         }
     }
+    const double ms_validate = since(t_begin);
     // one contiguous upload per array
     float4 *d_verts = nullptr;
     uint32_t *d_indices = nullptr;
@@ -341,6 +362,7 @@ int msk_gpu_scene_create(MskCtx *ctx, const MskSceneDesc *d, MskScene **out) {
     // uniformly tessellated BASELINE meshes (C5 primary rays: 15.3 vs 18.5 wide nodes per ray; fuller 8-wide nodes
     // after the collapse: 1.47 M vs 1.62 M), although PLOC lowers the binary SAH cost (66.7 -> 62.4).  A PLOC tree too
     // deep for the traversal stack (degenerate input) falls back to the balanced LBVH.
+    const double ms_upload = since(t_begin) - ms_validate;
     const char *bsel = getenv("MSK_BVH_BUILDER");
     int builder = (bsel && !strcmp(bsel, "ploc")) ? MSK_BVH_PLOC : MSK_BVH_LBVH;
     if ((rc = bvh_build(ctx->stream, d_verts, d_indices, infos, &s->bvh, builder))) return bail(rc);
@@ -354,6 +376,9 @@ int msk_gpu_scene_create(MskCtx *ctx, const MskSceneDesc *d, MskScene **out) {
     s->d.k47 = 0x47000000u;
     cudaError_t es = cudaStreamSynchronize(ctx->stream);
     if (es != cudaSuccess) return bail(cuda_fail(es, "cudaStreamSynchronize", __FILE__, __LINE__));
+    if (debug_setup)
+        fprintf(stderr, "[msk] scene_create: %zu tris | validate + CDFs %.2f ms | malloc + upload %.2f ms | BVH %.2f ms host (%.2f ms device) | total %.2f ms\n",
+                ntris, ms_validate, ms_upload, since(t_begin) - ms_validate - ms_upload, s->bvh.ms_build, since(t_begin));
     *out = s;
     return MSK_OK;
 }
@@ -506,11 +531,21 @@ int msk_gpu_render_multi(MskScene *const *scenes, uint32_t nscenes, const MskRen
     uint32_t epoch = ++g_epoch;
     if (!epoch) epoch = ++g_epoch;
     const uint32_t total = rd->sample_end - rd->sample_begin, base = total / nscenes, rem = total % nscenes;
-    auto worker = [&](uint32_t i) {
+    auto shard = [&](uint32_t i) {
         MskRenderDesc r = *rd;
         r.sample_begin = rd->sample_begin + i * base + std::min(i, rem);
         r.sample_end = r.sample_begin + base + (i < rem ? 1u : 0u);
         r.clear_film = 1;
+        return r;
+    };
+    for (uint32_t i = 0; i < nscenes; ++i) { // every allocation happens before any GPU starts (see Renderer::reserve)
+        DeviceGuard guard(scenes[i]->ctx->device);
+        const MskRenderDesc r = shard(i);
+        int rc = scenes[i]->ctx->renderer.reserve(scenes[i]->d, r);
+        if (rc) { destroy_all(); return rc; }
+    }
+    auto worker = [&](uint32_t i) {
+        const MskRenderDesc r = shard(i);
         int rc = msk_gpu_render_dev(scenes[i], &r, msk_gpu_film_share_ptr(shares[i]), &st[i]);
         if (!rc) rc = msk_gpu_reduce_film(shares[i], i == 0, epoch);
         if (!rc) rc = msk_gpu_film_share_check(shares[i]); // drains this GPU's stream
@@ -580,6 +615,54 @@ int msk_gpu_render_aov(MskScene *s, const MskRenderDesc *rd, const MskAovDesc *a
     if (e != cudaSuccess) return cuda_fail(e, "msk_gpu_render_aov", __FILE__, __LINE__);
     return rc;
 }
+
+} // extern "C"
+
+// A floor quad under a quad light, diffuse, 8 x 4 pixels: touches the BVH builder, every wavefront stage (two bounces, one
+// of them through the specialised shade kernels), the tail kernel, the film gather and the batch queries.  Failures are
+// ignored: the real call that follows reports them.
+static void warm_up(MskCtx *ctx) {
+    static const float verts[2][4 * 8] = {
+        { -1, 0, -1, 0, 1, 0, 0, 0,   1, 0, -1, 0, 1, 0, 1, 0,   1, 0, 1, 0, 1, 0, 1, 1,   -1, 0, 1, 0, 1, 0, 0, 1 },
+        { -0.5f, 2, -0.5f, 0, -1, 0, 0, 0,   0.5f, 2, -0.5f, 0, -1, 0, 1, 0,   0.5f, 2, 0.5f, 0, -1, 0, 1, 1,   -0.5f, 2, 0.5f, 0, -1, 0, 0, 1 } };
+    static const uint32_t tris_up[6] = { 0, 2, 1, 0, 3, 2 }, tris_down[6] = { 0, 1, 2, 0, 2, 3 };
+    MskSpectrum spec[2]{};
+    spec[0].kind = MSK_SPEC_UNIFORM; spec[0].value = 0.5f; spec[0].child0 = spec[0].child1 = -1;
+    spec[1] = spec[0]; spec[1].value = 5.f;
+    MskBsdf bsdf{};
+    bsdf.type = MSK_BSDF_DIFFUSE; bsdf.reflectance = 0; bsdf.transmittance = bsdf.eta = bsdf.k = -1;
+    MskEmitter em{};
+    em.type = MSK_EMITTER_AREA; em.radiance = 1; em.shape = 1;
+    MskMesh meshes[2]{};
+    meshes[0].verts = verts[0]; meshes[0].nverts = 4; meshes[0].tris = tris_up; meshes[0].ntris = 2; meshes[0].bsdf = 0; meshes[0].emitter = -1;
+    meshes[0].interior_medium = meshes[0].exterior_medium = -1;
+    meshes[1] = meshes[0]; meshes[1].verts = verts[1]; meshes[1].tris = tris_down; meshes[1].emitter = 0;
+    MskSceneDesc d{};
+    d.meshes = meshes; d.nmeshes = 2; d.bsdfs = &bsdf; d.nbsdfs = 1; d.emitters = &em; d.nemitters = 1; d.spectra = spec; d.nspectra = 2;
+    d.environment = -1; d.sensor_medium = -1;
+    MskCamera &c = d.camera;
+    c.width = 8; c.height = 4; c.near_clip = 0.01f; c.far_clip = 100.f; c.filter_radius = 2.f;
+    for (int i = 0; i < 33; ++i) c.filter_table[i] = i < 32 ? 1.f - i / 32.f : 0.f;
+    // sample_to_camera: pixel (x, y) -> a point on the plane z = 1 in front of a camera at (0, 1, -3) looking along +z
+    const float s2c[16] = { 0.25f, 0, 0, -1,   0, -0.25f, 0, 0.5f,   0, 0, 0, 1,   0, 0, 0, 1 };
+    const float c2w[16] = { 1, 0, 0, 0,   0, 1, 0, 1,   0, 0, 1, -3,   0, 0, 0, 1 };
+    memcpy(c.sample_to_camera, s2c, sizeof(s2c)); memcpy(c.to_world, c2w, sizeof(c2w));
+    MskScene *sc = nullptr;
+    if (msk_gpu_scene_create(ctx, &d, &sc) != MSK_OK) return;
+    float film[8 * 4 * 5];
+    for (int32_t depth : { 3, -1 }) { // bounded: wavefront only; unbounded: polls the queue and finishes with k_tail
+        MskRenderDesc rd{};
+        rd.spp = 2; rd.sample_end = 2; rd.max_depth = depth; rd.rr_depth = 2; rd.clear_film = 1;
+        msk_gpu_render(sc, &rd, film, nullptr);
+    }
+    MskRay ray{ { 0, 1, 0 }, 1e-3f, { 0, -1, 0 }, 10.f };
+    MskHit hit; uint8_t occ;
+    msk_gpu_intersect(sc, &ray, &hit, 1);
+    msk_gpu_occluded(sc, &ray, &occ, 1);
+    msk_gpu_scene_destroy(sc);
+}
+
+extern "C" {
 
 // HDRFilm::image, hdrfilm.cpp:48-90 (host side; runs once per image)
 int msk_gpu_develop(MskScene *s, const float *film, float *rgba) {

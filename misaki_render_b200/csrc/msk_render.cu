@@ -1223,6 +1223,21 @@ int Renderer::aov_plan(const MskAovDesc &aov, uint32_t *nch) {
     return MSK_OK;
 }
 
+// Allocates the path pool a render of `rd` will use, so that the render itself makes no allocation.  cudaMalloc
+// synchronises the whole device; msk_gpu_render_multi calls this for every context before any of them starts, because one
+// context's reduction kernel may already be spinning on a flag that another context OF THE SAME DEVICE publishes only after
+// its render (two contexts on one GPU: the one-GPU test of the multi-device path).
+int Renderer::reserve(const DScene &sc, const MskRenderDesc &rd) {
+    const uint64_t npix64 = (uint64_t) sc.cam.width * sc.cam.height;
+    if (!npix64 || npix64 > (1ull << 27)) return fail(MSK_ERR_UNSUPPORTED, "film size %ux%u unsupported", sc.cam.width, sc.cam.height);
+    if (rd.sample_end < rd.sample_begin || rd.sample_end > rd.spp) return fail(MSK_ERR_ARG, "bad sample range");
+    const uint32_t npix = (uint32_t) npix64;
+    const uint32_t target = rd.paths_per_batch ? rd.paths_per_batch : impl_->batch_paths;
+    uint32_t per_batch = std::max(1u, target / npix);
+    per_batch = std::min(per_batch, std::max(rd.sample_end - rd.sample_begin, 1u));
+    return ensure_pool(npix * per_batch);
+}
+
 int Renderer::render(cudaStream_t stream, const DScene &sc, const MskRenderDesc &rd, float *d_film, MskStats *stats, const MskAovDesc *aov) {
     const uint32_t W = sc.cam.width, H = sc.cam.height;
     const uint64_t npix64 = (uint64_t) W * H;

@@ -14,6 +14,7 @@ public:
     // stride is 5 + nch and the AOV channels follow XYZAW
     int render(cudaStream_t stream, const DScene &sc, const MskRenderDesc &rd, float *d_film, MskStats *stats,
                const MskAovDesc *aov = nullptr);
+    int reserve(const DScene &sc, const MskRenderDesc &rd);    // allocate the path pool of such a render now
     static int aov_plan(const MskAovDesc &aov, uint32_t *nch); // validates, counts channels
     int intersect(cudaStream_t stream, const DScene &sc, const MskRay *d_rays, MskHit *d_hits, size_t n);
     int intersect_stats(cudaStream_t stream, const DScene &sc, const MskRay *d_rays, size_t n, uint32_t *d_nodes, uint32_t *d_tris);

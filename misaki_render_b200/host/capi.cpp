@@ -49,7 +49,7 @@ int mskh_load_file_params(const char *filename, const char *const *names, const 
         for (size_t i = 0; i < nparams; ++i) params.emplace_back(names[i], values[i]);
         std::string path = filename;
         size_t slash = path.find_last_of('/');
-        get_file_resolver()->prepend(slash == std::string::npos ? "." : path.substr(0, slash)); // main.cpp:68
+        ScopedSearchPath scene_dir(slash == std::string::npos ? "." : path.substr(0, slash)); // main.cpp:68, for this load only
         std::unique_ptr<MskhScene> h(new MskhScene);
         h->root = xml::load_file(get_file_resolver()->resolve(path), params);
         finish_load(h.get());
@@ -62,7 +62,8 @@ int mskh_load_file(const char *filename, MskhScene **out) { return mskh_load_fil
 int mskh_load_string(const char *xml_text, const char *base_dir, MskhScene **out) {
     *out = nullptr;
     return guarded([&] {
-        if (base_dir && *base_dir) get_file_resolver()->prepend(base_dir);
+        std::unique_ptr<ScopedSearchPath> scene_dir;
+        if (base_dir && *base_dir) scene_dir.reset(new ScopedSearchPath(base_dir));
         std::unique_ptr<MskhScene> h(new MskhScene);
         h->root = xml::load_string(xml_text);
         finish_load(h.get());

@@ -219,11 +219,20 @@ class FileResolver {
 public:
     void append(const std::string &dir) { m_paths.push_back(dir); }
     void prepend(const std::string &dir) { m_paths.insert(m_paths.begin(), dir); }
+    void pop_front() { if (!m_paths.empty()) m_paths.erase(m_paths.begin()); }
     std::string resolve(const std::string &path) const; // first existing <dir>/<path>, else path itself
 private:
     std::vector<std::string> m_paths;
 };
 FileResolver *get_file_resolver();
+// The directory of the scene being loaded, searched first FOR THE DURATION OF THAT LOAD (main.cpp:68 prepends it for the
+// life of the process, which is one load there; a library that loads many scenes must not let scene B find scene A's files)
+struct ScopedSearchPath {
+    explicit ScopedSearchPath(const std::string &dir) { get_file_resolver()->prepend(dir); }
+    ~ScopedSearchPath() { get_file_resolver()->pop_front(); }
+    ScopedSearchPath(const ScopedSearchPath &) = delete;
+    ScopedSearchPath &operator=(const ScopedSearchPath &) = delete;
+};
 
 namespace xml {
 using ParameterList = std::vector<std::pair<std::string, std::string>>;

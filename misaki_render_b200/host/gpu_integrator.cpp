@@ -12,7 +12,9 @@
 #include "render.h"
 
 #include <cstdlib>
+#include <map>
 #include <mutex>
+#include <thread>
 
 namespace misaki {
 
@@ -44,54 +46,108 @@ protected:
 MSK_IMPLEMENT_CLASS(MonteCarloIntegrator, SamplingIntegrator)
 
 namespace {
-struct DeviceContext { // one MskCtx per process and device, created on first use
+// One MskCtx per (device, ordinal) and process, created on first use.  The ordinal distinguishes repeated entries of a
+// device list ("0,0": two contexts on one GPU, which is how the multi-device path is tested on a one-GPU box).
+struct DevicePool {
     std::mutex mutex;
-    MskCtx *ctx = nullptr;
-    int device = -1;
-    ~DeviceContext() { if (ctx) msk_gpu_shutdown(ctx); }
+    std::map<std::pair<int, int>, MskCtx *> ctxs;
+    MskCtx *get(int device, int ordinal) {
+        auto key = std::make_pair(device, ordinal);
+        auto it = ctxs.find(key);
+        if (it != ctxs.end()) return it->second;
+        MskCtx *ctx = nullptr;
+        if (msk_gpu_init(device, &ctx) != MSK_OK) Throw("%s", msk_gpu_last_error());
+        ctxs[key] = ctx;
+        return ctx;
+    }
+    ~DevicePool() { for (auto &kv : ctxs) msk_gpu_shutdown(kv.second); }
 };
-DeviceContext g_dev;
+DevicePool g_pool;
+
+// The GPUs a render uses.  The reference uses every core of the machine from one Integrator::render call
+// (integrator.cpp:54-75, main.cpp:60-61); here: the `devices` property of the integrator (a count; 0 = all visible GPUs),
+// else the environment variable MSK_DEVICES (a count, "all", or a comma-separated list of device ids), else one GPU --
+// `device` / MSK_DEVICE / 0, which is also the first GPU of a count.
+std::vector<int> resolve_devices(int device_prop, int devices_prop) {
+    const int first = device_prop >= 0 ? device_prop : (getenv("MSK_DEVICE") ? atoi(getenv("MSK_DEVICE")) : 0);
+    int count = 1;
+    if (devices_prop >= 0) count = devices_prop;
+    else if (const char *env = getenv("MSK_DEVICES")) {
+        std::string v(env);
+        if (v.find(',') != std::string::npos) {
+            std::vector<int> list;
+            for (const std::string &tok : string::tokenize(v, ",")) list.push_back(atoi(tok.c_str()));
+            if (list.empty()) Throw("MSK_DEVICES: empty device list");
+            return list;
+        }
+        count = v == "all" ? 0 : atoi(v.c_str());
+    }
+    const int visible = msk_gpu_device_count();
+    if (count <= 0) count = visible - first;
+    if (count < 1 || first + count > visible) Throw("%d GPU(s) starting at device %d requested, %d visible", count, first, visible);
+    std::vector<int> list;
+    for (int i = 0; i < count; ++i) list.push_back(first + i);
+    return list;
+}
 } // namespace
 
-// Shared by the "path" and "aov" plugins: flatten the scene, run msk_gpu_render[_aov], hand the film-sized
-// border-less block to Film::put.  `aov_types` empty and `aov == false`: the plain path tracer.
-static void gpu_render(Scene *scene, Sensor *sensor, const MskRenderDesc &rd, int device_prop, bool aov,
+// Shared by the "path" and "aov" plugins: flatten the scene, run msk_gpu_render[_aov / _multi], hand the film-sized
+// border-less block to Film::put.  `aov_types` empty and `aov == false`: the plain path tracer.  With several devices
+// every GPU gets its own copy of the scene + BVH and a sample sub-range (msk_gpu_render_multi); the AOV integrator
+// (one bounce) stays on the first.
+static void gpu_render(Scene *scene, Sensor *sensor, const MskRenderDesc &rd, int device_prop, int devices_prop, bool aov,
                        const std::vector<int32_t> &aov_types, const std::vector<std::string> &aov_names, MskStats &stats) {
     Film *film = sensor->film();
     std::vector<std::string> channels = aov_names; // integrator.cpp:36-41: X,Y,Z,A,W first
     for (size_t i = 0; i < 5; ++i) channels.insert(channels.begin() + i, std::string(1, "XYZAW"[i]));
     film->prepare(channels);
     GpuSceneBuilder builder(scene);
-    int device = device_prop >= 0 ? device_prop : (getenv("MSK_DEVICE") ? atoi(getenv("MSK_DEVICE")) : 0);
-    std::lock_guard<std::mutex> lock(g_dev.mutex);
-    if (g_dev.ctx && g_dev.device != device) { msk_gpu_shutdown(g_dev.ctx); g_dev.ctx = nullptr; }
-    if (!g_dev.ctx) {
-        if (msk_gpu_init(device, &g_dev.ctx) != MSK_OK) Throw("%s", msk_gpu_last_error());
-        g_dev.device = device;
+    std::vector<int> devices = resolve_devices(device_prop, devices_prop);
+    if (aov) devices.resize(1);
+    std::lock_guard<std::mutex> lock(g_pool.mutex);
+    const size_t nd = devices.size();
+    std::vector<MskCtx *> ctxs(nd, nullptr);
+    std::map<int, int> seen;
+    for (size_t i = 0; i < nd; ++i) ctxs[i] = g_pool.get(devices[i], seen[devices[i]]++);
+    // scene upload + BVH build, one host thread per GPU
+    std::vector<MskScene *> gpu_scenes(nd, nullptr);
+    std::vector<std::string> errors(nd);
+    auto create = [&](size_t i) {
+        if (msk_gpu_scene_create(ctxs[i], &builder.desc(), &gpu_scenes[i]) != MSK_OK) errors[i] = msk_gpu_last_error();
+    };
+    {
+        std::vector<std::thread> threads;
+        for (size_t i = 1; i < nd; ++i) threads.emplace_back(create, i);
+        create(0);
+        for (auto &t : threads) t.join();
     }
-    MskScene *gpu_scene = nullptr;
-    if (msk_gpu_scene_create(g_dev.ctx, &builder.desc(), &gpu_scene) != MSK_OK) Throw("%s", msk_gpu_last_error());
+    auto destroy_scenes = [&]() { for (MskScene *s : gpu_scenes) msk_gpu_scene_destroy(s); };
+    for (size_t i = 0; i < nd; ++i)
+        if (!errors[i].empty()) { destroy_scenes(); Throw("%s", errors[i].c_str()); }
     MskAccelInfo info{};
-    msk_gpu_accel_info(gpu_scene, &info);
-    Log(Info, "GPU scene: %llu triangles, %llu wide nodes, BVH built in %.2f ms", (unsigned long long) info.ntris,
-        (unsigned long long) info.nnodes, info.ms_build);
+    msk_gpu_accel_info(gpu_scenes[0], &info);
+    Log(Info, "GPU scene: %llu triangles, %llu wide nodes, BVH built in %.2f ms (%zu GPU%s)", (unsigned long long) info.ntris,
+        (unsigned long long) info.nnodes, info.ms_build, nd, nd == 1 ? "" : "s, samples partitioned");
     Log(Info, "Start rendering...");
     ref<ImageBlock> block = new ImageBlock(film->width(), film->height(), (uint32_t) channels.size());
     int rc;
     if (aov) {
         MskAovDesc ad{ aov_types.data(), (uint32_t) aov_types.size(), 0 };
         int nch = msk_gpu_aov_channels(&ad);
-        if (nch < 0 || (size_t) nch + 5 != channels.size()) { msk_gpu_scene_destroy(gpu_scene); Throw("%s", nch < 0 ? msk_gpu_last_error() : "AOV channel names do not match the AOV types"); }
-        rc = msk_gpu_render_aov(gpu_scene, &rd, &ad, block->data().data(), &stats);
+        if (nch < 0 || (size_t) nch + 5 != channels.size()) { destroy_scenes(); Throw("%s", nch < 0 ? msk_gpu_last_error() : "AOV channel names do not match the AOV types"); }
+        rc = msk_gpu_render_aov(gpu_scenes[0], &rd, &ad, block->data().data(), &stats);
+    } else if (nd > 1) {
+        rc = msk_gpu_render_multi(gpu_scenes.data(), (uint32_t) nd, &rd, block->data().data(), &stats);
     } else {
-        rc = msk_gpu_render(gpu_scene, &rd, block->data().data(), &stats);
+        rc = msk_gpu_render(gpu_scenes[0], &rd, block->data().data(), &stats);
     }
-    msk_gpu_scene_destroy(gpu_scene);
-    if (rc != MSK_OK) Throw("%s", msk_gpu_last_error());
+    std::string err = rc != MSK_OK ? msk_gpu_last_error() : "";
+    destroy_scenes();
+    if (rc != MSK_OK) Throw("%s", err.c_str());
     film->put(block.get()); // integrator.cpp:69 / hdrfilm.cpp:43-46
     double rays = (double) stats.rays_closest + (double) stats.rays_shadow;
-    Log(Info, "Rendering finished. (took %.2f ms on the device: %.1f Mpaths/s, %.1f Mrays/s, %llu kernel launches)", stats.ms_render,
-        stats.paths / (stats.ms_render * 1e3), rays / (stats.ms_render * 1e3), (unsigned long long) stats.kernel_launches);
+    Log(Info, "Rendering finished. (took %.2f ms on the device%s: %.1f Mpaths/s, %.1f Mrays/s, %llu kernel launches)", stats.ms_render,
+        nd == 1 ? "" : "s", stats.paths / (stats.ms_render * 1e3), rays / (stats.ms_render * 1e3), (unsigned long long) stats.kernel_launches);
 }
 
 class GpuPathIntegrator : public MonteCarloIntegrator {
@@ -101,6 +157,7 @@ public:
         // XML values are silently ignored there (path.cpp:135-136).  They are honoured here: the
         // BASELINE configurations specify depths 5 and 16.
         m_device = (int) props.int_("device", -1);
+        m_devices = (int) props.int_("devices", -1); // number of GPUs (0 = all visible); default: MSK_DEVICES, else 1
         m_sample_begin = props.int_("sample_begin", 0);
         m_sample_end = props.int_("sample_end", -1);
     }
@@ -119,7 +176,7 @@ public:
     bool render(Scene *scene, Sensor *sensor) override {
         MskRenderDesc rd;
         render_desc(sensor, rd);
-        gpu_render(scene, sensor, rd, m_device, false, {}, {}, m_stats);
+        gpu_render(scene, sensor, rd, m_device, m_devices, false, {}, {}, m_stats);
         return true;
     }
     const MskStats &stats() const { return m_stats; }
@@ -128,7 +185,7 @@ public:
 protected:
     uint32_t m_integrator = MSK_INTEGRATOR_PATH;
 private:
-    int m_device;
+    int m_device, m_devices;
     int64_t m_sample_begin, m_sample_end;
     MskStats m_stats{};
 };
@@ -184,7 +241,7 @@ public:
             rd.max_depth = m_max_depth; rd.rr_depth = m_rr_depth; rd.hide_emitters = m_hide_emitters;
             rd.base_seed = sensor->sampler()->base_seed(); rd.clear_film = 1;
         }
-        gpu_render(scene, sensor, rd, m_device >= 0 ? m_device : (m_nested ? m_nested->device() : -1), true, m_types, m_names, m_stats);
+        gpu_render(scene, sensor, rd, m_device >= 0 ? m_device : (m_nested ? m_nested->device() : -1), 1, true, m_types, m_names, m_stats);
         return true;
     }
     const MskStats &stats() const { return m_stats; }

@@ -41,7 +41,7 @@ int main(int argc, char **argv) {
         film->set_destination_file(output.empty() ? scene_path : output);
         if (!scene->integrator()) Throw("No integrator specified for scene");
         if (scene->integrator()->render(scene, sensor)) film->develop();
-        else Log(Warn, "Rendering failed, result not saved.");
+        else { Log(Warn, "Rendering failed, result not saved."); return 3; } // (main.cpp:38-43 only warns; scripts need the status)
     } catch (const std::exception &e) {
         fprintf(stderr, "%s\n", e.what());
         return 1;

@@ -300,6 +300,68 @@ class RefRgb2Spec:
 REF_CODE_LIB = HERE / "_ref" / "libmisaki_ref_math.so"
 
 
+class ReferenceCamera:
+    """The reference's OWN compiled camera (oracle/ref_camera_wrap.cpp: include/misaki/core/transform.h, sensor.cpp,
+    sensors/perspective.cpp over the Eigen stand-in).  Used by tools/gen_golden_ref_camera.py and, as the ray callback of
+    ReferenceLoop, by tools/gen_golden_ref_converged.py."""
+
+    def __init__(self, width, height, fov, near_clip, far_clip, to_world=None):
+        self.L = C.CDLL(str(REF_CODE_LIB))
+        self.L.ref_camera_create.restype = C.c_void_p
+        self.L.ref_camera_create.argtypes = [C.c_int, C.c_int, C.c_float, C.c_float, C.c_float, C.c_void_p]
+        self.L.ref_camera_destroy.argtypes = [C.c_void_p]
+        self.L.ref_camera_sample_rays.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
+        self.L.ref_camera_callback.restype = C.c_void_p
+        self.L.ref_camera_callback.argtypes = [C.c_void_p]
+        tw = None if to_world is None else _f(np.asarray(to_world, np.float32).reshape(-1), 16).copy()
+        self.h = self.L.ref_camera_create(int(width), int(height), float(fov), float(near_clip), float(far_clip), None if tw is None else tw.ctypes.data)
+        if not self.h:
+            raise RuntimeError("ref_camera_create failed")
+
+    @classmethod
+    def of(cls, sd):
+        return cls(sd.width, sd.height, sd.fov, sd.near_clip, sd.far_clip, sd.to_world)
+
+    def sample_rays(self, samples):
+        """samples: n x 3 (wavelength sample, px, py).  Returns n x 16: o[3] d[3] mint maxt | wavelengths[4] | weight[4]."""
+        s = _f(samples).reshape(-1, 3)
+        out = np.empty((s.shape[0], 16), np.float32)
+        if self.L.ref_camera_sample_rays(self.h, s.ctypes.data, s.shape[0], out.ctypes.data) != 0:
+            raise RuntimeError("ref_camera_sample_rays failed")
+        return out
+
+    def callback(self):
+        return C.c_void_p(self.L.ref_camera_callback(self.h))
+
+    def matrices(self, width, height, fov, near_clip, far_clip):
+        self.L.ref_camera_matrices.argtypes = [C.c_int, C.c_int, C.c_float, C.c_float, C.c_float, C.c_void_p, C.c_void_p]
+        a, b = np.empty(16, np.float32), np.empty(16, np.float32)
+        assert self.L.ref_camera_matrices(int(width), int(height), float(fov), float(near_clip), float(far_clip), a.ctypes.data, b.ctypes.data) == 0
+        return a.reshape(4, 4), b.reshape(4, 4)
+
+    def close(self):
+        if self.h:
+            self.L.ref_camera_destroy(self.h)
+            self.h = None
+
+
+def ref_lookat(origin, target, up):
+    L = C.CDLL(str(REF_CODE_LIB))
+    L.ref_transform_lookat.argtypes = [C.c_void_p] * 4
+    o, t, u, out = _f(origin, 3).copy(), _f(target, 3).copy(), _f(up, 3).copy(), np.empty(16, np.float32)
+    L.ref_transform_lookat(o.ctypes.data, t.ctypes.data, u.ctypes.data, out.ctypes.data)
+    return out.reshape(4, 4)
+
+
+def ref_transform(kind, v, angle=0.0):
+    """kind: 'translate' | 'scale' | 'rotate' (axis v, angle as Transform4f::rotate receives it).  Returns (matrix, carried inverse)."""
+    L = C.CDLL(str(REF_CODE_LIB))
+    L.ref_transform_make.argtypes = [C.c_int, C.c_void_p, C.c_float, C.c_void_p, C.c_void_p]
+    vv, a, b = _f(v, 3).copy(), np.empty(16, np.float32), np.empty(16, np.float32)
+    L.ref_transform_make({"translate": 0, "scale": 1, "rotate": 2}[kind], vv.ctypes.data, float(angle), a.ctypes.data, b.ctypes.data)
+    return a.reshape(4, 4), b.reshape(4, 4)
+
+
 class ReferenceLoop:
     """The reference's OWN compiled render loop (oracle/ref_render_wrap.cpp: integrator.cpp, integrators/path.cpp,
     scene.cpp's emitter sampling, mesh / interaction, imageblock.cpp, films/hdrfilm.cpp, its srgb / srgb_d65 textures)
@@ -308,7 +370,9 @@ class ReferenceLoop:
     over the same tasks, Eigen is oracle/ref_shim, the camera ray of a sample comes from the oracle's camera.  Used by
     tools/gen_golden_ref_math.py and by bench.py --impl reference --ref-kind reference."""
 
-    def __init__(self, sd, reflectance_rgb, radiance_rgb):
+    def __init__(self, sd, reflectance_rgb, radiance_rgb, camera="oracle"):
+        """camera: "oracle" -- the oracle's restatement supplies the ray of each sample; "reference" -- the reference's own
+        PerspectiveCamera does (ReferenceCamera)."""
         import os
         os.environ.setdefault("MSK_REF_DATA_ROOT", str(HERE.parent / "misaki_render_b200"))  # data/srgb.coeff (srgb.cpp:14-18)
         self.L = C.CDLL(str(REF_CODE_LIB))
@@ -334,6 +398,10 @@ class ReferenceLoop:
         if L.orc_ref_camera_bind(self.osc.h) != 0:
             raise RuntimeError("orc_ref_camera_bind failed")
         self.cb = C.c_void_p(L.orc_ref_camera_callback())
+        self.ref_camera = None
+        if camera == "reference":
+            self.ref_camera = ReferenceCamera.of(sd)
+            self.cb = self.ref_camera.callback()
         self.L.ref_render.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_void_p, C.c_void_p]
 
     def render(self, spp: int, threads: int = 1, stddev: float = 0.5):

@@ -9,12 +9,17 @@
 namespace misaki {
 class Texture;
 struct Transform4f;
+template <typename T> T msk_ref_make_transform(const float *row_major_4x4); // msk_ref_geometry.h, once transform.h is known
 class Properties {
 public:
     Properties() {}
     explicit Properties(const std::string &plugin) : plugin_name(plugin) {}
     std::string plugin_name;
-    template <typename T> T transform(const std::string &, const T &d) const { return d; } // shapes stay in world space
+    std::map<std::string, std::array<float, 16>> matrices; // row-major 4x4
+    template <typename T> T transform(const std::string &n, const T &d) const { // shapes stay in world space: no entry, the default
+        auto it = matrices.find(n);
+        return it == matrices.end() ? d : msk_ref_make_transform<T>(it->second.data());
+    }
     std::map<std::string, float> floats;
     std::map<std::string, bool> bools;
     std::map<std::string, long long> ints;

@@ -4,6 +4,11 @@
 // reference's own (film.h / film.cpp / films/hdrfilm.cpp, ref_hdrfilm_wrap.cpp).
 // TEST INFRASTRUCTURE.
 #pragma once
+#if defined(MSK_REF_REAL_SENSOR)
+// ref_camera_wrap.cpp: the reference's own include/misaki/render/sensor.h (gen copy, oracle/Makefile.ref), with the class
+// renamed by that translation unit so that it does not collide with the stand-in the render-loop wrappers use
+#include <misaki/render/sensor_real.h>
+#else
 #include "msk_ref_prelude.h"
 #include <misaki/core/object.h>
 #include <misaki/core/ray.h>
@@ -39,3 +44,4 @@ private:
     RayCallback m_cb;
 };
 } // namespace misaki
+#endif

@@ -491,3 +491,23 @@ def test_the_bunny_scene_fails_as_it_does_in_the_reference(tmp_path):
     (tmp_path / "scene.xml").write_text((REFERENCE_ROOT / "assets/bunny/scene.xml").read_text())
     with pytest.raises(host_api.HostError, match='"debug"'):
         host_api.HostScene(tmp_path / "scene.xml").__enter__()
+
+
+def test_scene_directory_is_searched_for_that_load_only(tmp_path):
+    """mskh_load_* put the scene's directory in front of the FileResolver for the duration of the load (the reference's
+    main.cpp:68 does it once per process).  A relative mesh missing from scene B's directory must not resolve to the
+    same-named file of a scene A loaded earlier."""
+    a, b = tmp_path / "a", tmp_path / "b"
+    a.mkdir(); b.mkdir()
+    (a / "quad.obj").write_text("v 0 0 0\nv 1 0 0\nv 1 1 0\nv 0 1 0\nf 1 2 3 4\n")
+    body = MINIMAL.format(body='<shape type="obj"><string name="filename" value="quad.obj"/></shape>')
+    (a / "scene.xml").write_text(body)
+    (b / "scene.xml").write_text(body)
+    with host_api.HostScene(a / "scene.xml") as sa:
+        assert len(sa.meshes()) == 1
+    with pytest.raises(host_api.HostError):
+        host_api.HostScene(b / "scene.xml")
+    with host_api.HostScene(xml=body, base_dir=str(a)) as sa2:  # load_string with a base directory: same scoping
+        assert len(sa2.meshes()) == 1
+    with pytest.raises(host_api.HostError):
+        host_api.HostScene(xml=body, base_dir=str(b))
