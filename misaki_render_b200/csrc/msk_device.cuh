@@ -30,7 +30,10 @@ int fail(int code, const char *fmt, ...);
 // -3 jmin, modulo 2^32); the builder packs the leaves of a node into the tightest run of free slots.
 constexpr int kNodeFloat4s = 5;
 constexpr int kTriFloat4s  = 3; // v0.xyz, prim | v1.xyz, geom | v2.xyz, -
-constexpr int kMaxLeafTris = 3;
+#ifndef MSK_MAX_LEAF_TRIS
+#define MSK_MAX_LEAF_TRIS 3 /* 1..3: three static triangle bits per child slot */
+#endif
+constexpr int kMaxLeafTris = MSK_MAX_LEAF_TRIS;
 
 struct DMeshInfo {
     uint32_t vert_offset; // first vertex in DScene::verts (units of vertices)

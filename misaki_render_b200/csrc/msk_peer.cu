@@ -152,6 +152,11 @@ int msk_gpu_film_share_create(MskCtx *ctx, size_t nfloats, MskFilmShare **out) {
     int prev = -1;
     cudaGetDevice(&prev);
     cudaSetDevice(s->device);
+    // CUDA loads a kernel's code at its first launch, and that load may synchronise the whole context.  A root whose
+    // k_film_reduce is already spinning would then wait for a peer OF THE SAME CONTEXT (two MskCtx on one GPU) whose first
+    // k_film_publish can never be loaded: force the three kernels in now.
+    cudaFuncAttributes fa;
+    cudaFuncGetAttributes(&fa, k_film_reduce); cudaFuncGetAttributes(&fa, k_film_publish); cudaFuncGetAttributes(&fa, k_film_wait_consumed);
     cudaError_t e = cudaMalloc((void **) &s->base, kCtrlBytes + nfloats * sizeof(float)); // plain cudaMalloc: exportable
     if (e == cudaSuccess) e = cudaMemset(s->base, 0, kCtrlBytes + nfloats * sizeof(float));
     if (e == cudaSuccess) e = cudaMallocHost((void **) &s->h_error, sizeof(uint32_t));

@@ -83,6 +83,12 @@ struct Frame { V3 s, t, n; };
 __device__ __forceinline__ V3 to_local(const Frame &f, V3 v) { return v3(dot(v, f.s), dot(v, f.t), dot(v, f.n)); }
 __device__ __forceinline__ V3 to_world(const Frame &f, V3 v) { return f.s * v.x + f.t * v.y + f.n * v.z; }
 
+// sin / cos of an angle that is known to lie within a few multiples of pi (every call site below): CUDA's sincosf carries a
+// Payne-Hanek slow path for huge arguments -- never taken here, but ~150 instructions of every shade kernel's code
+// (profiles/r01g_ncu_k_shade.txt: stall_no_instruction).  sincospif reduces its argument exactly and has no slow path; the
+// division by pi costs one rounding of the angle (<= 1 ulp), the same size as the rounding of the angle itself.
+__device__ __forceinline__ void sincos_of(float phi, float *sn, float *cs) { sincospif(phi * kInvPi, sn, cs); }
+
 __device__ __forceinline__ V3 square_to_cosine_hemisphere(float sx, float sy) { // warp.h:17-43
     float x = 2.f * sx - 1.f, y = 2.f * sy - 1.f;
     float phi, r;
@@ -90,14 +96,14 @@ __device__ __forceinline__ V3 square_to_cosine_hemisphere(float sx, float sy) { 
     else if (x * x > y * y) { r = x; phi = (kPi / 4.f) * (y / x); }
     else { r = y; phi = (kPi / 2.f) - (x / y) * (kPi / 4.f); }
     float sn, cs;
-    sincosf(phi, &sn, &cs);
+    sincos_of(phi, &sn, &cs);
     float px = r * cs, py = r * sn;
     return v3(px, py, safe_sqrt(1.f - (px * px + py * py)));
 }
 __device__ __forceinline__ V3 square_to_uniform_sphere(float sx, float sy) { // warp.h:46-53
     float z = -2.f * sy + 1.f, r = safe_sqrt(-z * z + 1.f);
     float sn, cs;
-    sincosf(2.f * kPi * sx, &sn, &cs);
+    sincospif(2.f * sx, &sn, &cs); // sin / cos (2 pi sx)
     return v3(r * cs, r * sn, z);
 }
 
@@ -254,9 +260,18 @@ __device__ __forceinline__ float ggx_eval(const Ggx &g, V3 m) { // microfacet.h:
 }
 __device__ __forceinline__ float ggx_pdf(const Ggx &g, V3 m) { return ggx_eval(g, m) * m.z; } // microfacet.h:127-129
 __device__ __forceinline__ V3 ggx_sample(const Ggx &g, float sx, float sy, float &pdf) {   // microfacet.h:20-40
-    float phi_m = atanf(g.au / g.av * tanf(kPi + 2 * kPi * sy)) + kPi * floorf(2 * sy + 0.5f);
     float sin_phi, cos_phi;
-    sincosf(phi_m, &sin_phi, &cos_phi);
+    if (g.au == g.av) {
+        // isotropic: phi_m = atan(tan(pi + 2 pi sy)) + pi floor(2 sy + 1/2) is 2 pi sy up to a multiple of 2 pi, so its sine and
+        // cosine are those of 2 pi sy -- no tan / atan round trip (~150 instructions per vertex of the C2 / C3 materials)
+        sincospif(2.f * sy, &sin_phi, &cos_phi);
+    } else {
+        // tan(pi + 2 pi sy) = tan(2 pi sy) = sinpi(2 sy) / cospi(2 sy): exact argument reduction, no Payne-Hanek path
+        float st, ct;
+        sincospif(2.f * sy, &st, &ct);
+        float phi_m = atanf(g.au / g.av * (st / ct)) + kPi * floorf(2 * sy + 0.5f);
+        sincos_of(phi_m, &sin_phi, &cos_phi);
+    }
     float c = cos_phi / g.au, s = sin_phi / g.av;
     float alpha_sqr = 1.f / (c * c + s * s);
     float tan2 = alpha_sqr * sx / (1.f - sx);

