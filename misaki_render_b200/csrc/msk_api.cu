@@ -374,6 +374,12 @@ int msk_gpu_scene_create(MskCtx *ctx, const MskSceneDesc *d, MskScene **out) {
         return bail(fail(MSK_ERR_UNSUPPORTED, "BVH depth %u exceeds the traversal stack", s->bvh.depth));
     s->d.nodes = s->bvh.nodes; s->d.tris = s->bvh.tris;
     s->d.k47 = 0x47000000u;
+    s->d.nnodes = (uint32_t) s->bvh.nnodes;
+    for (int a = 0; a < 3; ++a) {
+        const float ext = s->bvh.hi[a] - s->bvh.lo[a];
+        s->d.bb_lo[a] = s->bvh.lo[a];
+        s->d.bb_scale[a] = ext > 0.f ? 0.999f / ext : 0.f;
+    }
     cudaError_t es = cudaStreamSynchronize(ctx->stream);
     if (es != cudaSuccess) return bail(cuda_fail(es, "cudaStreamSynchronize", __FILE__, __LINE__));
     if (debug_setup)

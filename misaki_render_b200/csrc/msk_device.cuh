@@ -84,6 +84,8 @@ struct DScene {
     uint32_t bsdf_type_mask; // bit t: some mesh uses a BSDF of MskBsdfType t
     int32_t  sensor_medium;  // medium the camera sits in, or -1 (sensor.cpp:12-18)
     uint32_t has_textures;   // some spectrum is uv-dependent (MSK_SPEC_CHECKERBOARD): resolve ids per surface point
+    uint32_t nnodes;         // wide BVH nodes
+    float    bb_lo[3], bb_scale[3]; // scene bounds: (p - bb_lo) * bb_scale in [0, 1) -- ray reordering keys (msk_render.cu: k_ray_keys)
     uint32_t k47;            // 0x47000000: the byte -> float bias of the node decode, opaque to ptxas (msk_traverse.cuh: qfloat)
     DCamera  cam;
 };

@@ -23,6 +23,8 @@
 #include "msk_shading.cuh"
 #include "msk_traverse.cuh"
 
+#include <cub/cub.cuh>
+
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
@@ -67,6 +69,8 @@ struct Pool {
     uint32_t *sorted;               // kNumKeys segments of `capacity` queue indices
     float   *aov;                   // AOV integrator: channel-major per-sample values, aov[c * capacity + i]
     Ctrl    *ctrl;
+    // MSK_RAY_SORT (experiment): queue indices of the current ray queue ordered by (origin Morton cell, direction octant)
+    uint32_t *rs_keys[2], *rs_vals[2];
 };
 
 // AOVIntegrator (aov.cpp:22-29): the requested outputs in channel order
@@ -165,12 +169,15 @@ struct IntersectIO {
     const Pool &pool;
     const MskRay *rays;
     const DScene *scp = nullptr;
+    const uint32_t *perm = nullptr; // MSK_RAY_SORT: position in the traversal order -> queue index
     uint32_t cn_total = 0, ct_total = 0;
     __device__ __forceinline__ void load(uint32_t q, float4 &ro, float4 &rd) const {
+        if (perm) q = __ldg(perm + q);
         const float4 *rp = reinterpret_cast<const float4 *>(rays + q);
         ro = __ldcs(rp); rd = __ldcs(rp + 1);
     }
     __device__ __forceinline__ void commit(bool have, uint32_t q, const Traversal &s) {
+        if (perm && have) q = __ldg(perm + q);
 #if MSK_SORT_IN_COMMIT
         const uint32_t done = __ballot_sync(0xffffffffu, have);
 #endif
@@ -194,13 +201,35 @@ struct IntersectIO {
 };
 
 template <bool STATS>
-__global__ void __launch_bounds__(128, MSK_TRAV_MIN_BLOCKS) k_intersect(const __grid_constant__ DScene sc, Pool pool, int cur, int coherent) {
+__global__ void __launch_bounds__(128, MSK_TRAV_MIN_BLOCKS) k_intersect(const __grid_constant__ DScene sc, Pool pool, int cur, int coherent, const uint32_t *perm) {
     MSK_TRAV_SHARED;
     const Accel ac{ sc.nodes, sc.tris, sc.k47, perm_lut_init(msk_s_perm) };
     Ctrl *c = pool.ctrl;
-    IntersectIO<STATS> io{ pool, pool.rays[cur], &sc };
+    IntersectIO<STATS> io{ pool, pool.rays[cur], &sc, perm };
     trace_queue<false, STATS>(ac, msk_s_stack, c->n_rays[cur], &c->cursor_isect, io, coherent != 0);
     if (STATS) add_traversal_stats(&c->nodes_closest, &c->tris_closest, io.cn_total, io.ct_total);
+}
+
+// MSK_RAY_SORT (experiment, off by default): key of every ray of the current queue = 8-bit-per-axis Morton cell of its
+// origin, then the octant of its direction; entries past the queue length sort to the end.
+__device__ __forceinline__ uint32_t spread8(uint32_t v) { // 8 bits -> every third bit
+    v = (v | (v << 8)) & 0x00f00fu; v = (v | (v << 4)) & 0x0c30c3u; v = (v | (v << 2)) & 0x249249u;
+    return v;
+}
+__global__ void __launch_bounds__(256) k_ray_keys(const __grid_constant__ DScene sc, Pool pool, int cur, uint32_t n_max, uint32_t *keys, uint32_t *vals) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_max) return;
+    uint32_t key = 0xffffffffu;
+    if (i < pool.ctrl->n_rays[cur]) {
+        const float4 *rp = reinterpret_cast<const float4 *>(pool.rays[cur] + i);
+        const float4 o = rp[0], d = rp[1];
+        const uint32_t qx = (uint32_t) fminf(fmaxf((o.x - sc.bb_lo[0]) * sc.bb_scale[0], 0.f) * 256.f, 255.f);
+        const uint32_t qy = (uint32_t) fminf(fmaxf((o.y - sc.bb_lo[1]) * sc.bb_scale[1], 0.f) * 256.f, 255.f);
+        const uint32_t qz = (uint32_t) fminf(fmaxf((o.z - sc.bb_lo[2]) * sc.bb_scale[2], 0.f) * 256.f, 255.f);
+        const uint32_t oct = (d.x < 0.f ? 4u : 0u) | (d.y < 0.f ? 2u : 0u) | (d.z < 0.f ? 1u : 0u);
+        key = (((spread8(qx) << 2) | (spread8(qy) << 1) | spread8(qz)) << 3) | oct;
+    }
+    keys[i] = key; vals[i] = i;
 }
 
 // ---------------------------------------------------------------------------------------
@@ -406,8 +435,13 @@ __global__ void __launch_bounds__(128, shade_min_blocks(KEY)) k_shade(const __gr
     }
     const uint32_t stride = gridDim.x * blockDim.x;
     const uint32_t rounds = (total + stride - 1) / stride;
+    // (Tried: reading this thread's next queue index one iteration ahead and pulling that vertex's state lines into L2 with
+    // prefetch.global.L2 while the current vertex is shaded -- the stage runs at 25 % occupancy with DRAM at 46 % of peak,
+    // profiles/r02d_ncu_k_shade.txt.  C2 shade 2.31 -> 2.41 ms: the extra index load and seven prefetches per vertex cost
+    // more issue slots and registers than the L2 hits save.)
+    const uint32_t first = blockIdx.x * blockDim.x + threadIdx.x;
     for (uint32_t it = 0; it < rounds; ++it) {
-        uint32_t idx = it * stride + blockIdx.x * blockDim.x + threadIdx.x;
+        uint32_t idx = it * stride + first;
         bool valid = idx < total;
         bool emit_ray = false, emit_shadow = false;
         MskRay nray, sray;
@@ -1136,6 +1170,13 @@ struct Renderer::Impl {
     int tiled_slots = 1;              // MSK_TILED_SLOTS: enumerate the pixels of a sample in 8x4 tiles (see slot_to_pixel)
     int poll_min_depth = 8;           // MSK_POLL_MIN_DEPTH: jobs with max_depth >= this (or unbounded) poll the queue length from bounce 4 on
     int async_poll = 1;               // MSK_ASYNC_POLL: poll the queue length one bounce late, without draining the stream
+    uint32_t static_nodes = 64;       // MSK_STATIC_NODES: scenes with at most this many wide nodes always use the static traversal (every ray does the same few steps: nothing to re-balance)
+    int use_graph = 1;                // MSK_GRAPH: bounded-depth jobs (a fixed launch sequence) replay a cached CUDA graph
+    cudaGraphExec_t graph_exec = nullptr;
+    std::vector<unsigned char> graph_key; // everything the captured launches depend on
+    uint64_t graph_launches = 0, graph_extra_closest = 0; uint32_t graph_bounces = 0, graph_batches = 0;
+    int ray_sort = 0;                 // MSK_RAY_SORT (experiment): 1 = reorder the closest-hit queue of bounces >= 1 by (origin cell, octant)
+    void *rs_tmp = nullptr; size_t rs_tmp_bytes = 0;
     std::vector<cudaEvent_t> timer_events; // MSK_RENDER_STAGE_TIMERS
     std::vector<int> timer_stage;
     int persistent_blocks = 0, sm_count = 0;
@@ -1146,10 +1187,13 @@ Renderer::Renderer() : impl_(new Impl) {}
 Renderer::~Renderer() { release(); delete impl_; }
 
 void Renderer::release() {
+    if (impl_->graph_exec) { cudaGraphExecDestroy(impl_->graph_exec); impl_->graph_exec = nullptr; impl_->graph_key.clear(); }
     Pool &p = impl_->pool;
     for (int i = 0; i < 2; ++i) { cudaFree(p.rays[i]); cudaFree(p.T[i]); cudaFree(p.WL[i]); cudaFree(p.AUX[i]); cudaFree(p.MISC[i]); }
     cudaFree(p.hit); cudaFree(p.hit_geom); cudaFree(p.L); cudaFree(p.sh_ray); cudaFree(p.sh_contrib); cudaFree(p.sh_path);
     cudaFree(p.sorted); cudaFree(p.rec); cudaFree(p.rec_py); cudaFree(p.ctrl); cudaFree(p.aov);
+    for (int i = 0; i < 2; ++i) { cudaFree(p.rs_keys[i]); cudaFree(p.rs_vals[i]); }
+    cudaFree(impl_->rs_tmp); impl_->rs_tmp = nullptr; impl_->rs_tmp_bytes = 0;
     p = Pool{};
     impl_->capacity = 0; impl_->aov_floats = 0;
     cudaFree(impl_->query_cursor); impl_->query_cursor = nullptr;
@@ -1181,16 +1225,22 @@ int Renderer::init(int sm_count) {
     impl_->tail_threshold = (uint32_t) env_u("MSK_TAIL_THRESHOLD", impl_->tail_threshold);
     impl_->poll_min_depth = (int) env_u("MSK_POLL_MIN_DEPTH", impl_->poll_min_depth);
     impl_->tiled_slots = (int) env_u("MSK_TILED_SLOTS", impl_->tiled_slots);
+    impl_->ray_sort = (int) env_u("MSK_RAY_SORT", impl_->ray_sort);
+    impl_->use_graph = (int) env_u("MSK_GRAPH", impl_->use_graph);
+    impl_->static_nodes = (uint32_t) env_u("MSK_STATIC_NODES", impl_->static_nodes);
     impl_->debug_bounces = (int) env_u("MSK_DEBUG_BOUNCES", 0);
     return MSK_OK;
 }
 
 int Renderer::ensure_pool(uint32_t capacity) {
     if (capacity <= impl_->capacity) return MSK_OK;
+    if (impl_->graph_exec) { cudaGraphExecDestroy(impl_->graph_exec); impl_->graph_exec = nullptr; impl_->graph_key.clear(); } // captured the old pool
     Pool &p = impl_->pool;
     for (int i = 0; i < 2; ++i) { cudaFree(p.rays[i]); cudaFree(p.T[i]); cudaFree(p.WL[i]); cudaFree(p.AUX[i]); cudaFree(p.MISC[i]); }
     cudaFree(p.hit); cudaFree(p.hit_geom); cudaFree(p.L); cudaFree(p.sh_ray); cudaFree(p.sh_contrib); cudaFree(p.sh_path);
     cudaFree(p.sorted); cudaFree(p.rec); cudaFree(p.rec_py); cudaFree(p.ctrl); cudaFree(p.aov);
+    for (int i = 0; i < 2; ++i) { cudaFree(p.rs_keys[i]); cudaFree(p.rs_vals[i]); }
+    cudaFree(impl_->rs_tmp); impl_->rs_tmp = nullptr; impl_->rs_tmp_bytes = 0;
     p = Pool{};
     impl_->capacity = 0; impl_->aov_floats = 0;
     size_t n = capacity;
@@ -1203,6 +1253,11 @@ int Renderer::ensure_pool(uint32_t capacity) {
     MSK_CUDA_CHECK(dalloc(&p.sorted, n * kNumKeys)); MSK_CUDA_CHECK(dalloc(&p.rec, n)); MSK_CUDA_CHECK(dalloc(&p.rec_py, n));
     MSK_CUDA_CHECK(dalloc(&p.ctrl, 1));
     MSK_CUDA_CHECK(cudaMemset(p.ctrl, 0, sizeof(Ctrl)));
+    if (impl_->ray_sort) {
+        for (int i = 0; i < 2; ++i) { MSK_CUDA_CHECK(dalloc(&p.rs_keys[i], n)); MSK_CUDA_CHECK(dalloc(&p.rs_vals[i], n)); }
+        MSK_CUDA_CHECK(cub::DeviceRadixSort::SortPairs(nullptr, impl_->rs_tmp_bytes, p.rs_keys[0], p.rs_keys[1], p.rs_vals[0], p.rs_vals[1], (int) n, 0, 27));
+        MSK_CUDA_CHECK(cudaMalloc(&impl_->rs_tmp, std::max<size_t>(impl_->rs_tmp_bytes, 16)));
+    }
     p.capacity = capacity;
     impl_->capacity = capacity;
     return MSK_OK;
@@ -1278,10 +1333,7 @@ int Renderer::render(cudaStream_t stream, const DScene &sc, const MskRenderDesc 
     const uint32_t stride = 5 + plan.nch;
     const bool trace_paths = !aov || plan.rgba_channel >= 0; // an AOV integrator without a nested one traces primary rays only
 
-    if (rd.clear_film) MSK_CUDA_CHECK(cudaMemsetAsync(d_film, 0, (size_t) npix * stride * sizeof(float), stream));
-    MSK_CUDA_CHECK(cudaMemsetAsync(&pool.ctrl->total_closest, 0, 10 * sizeof(unsigned long long), stream));
     const bool tstats = (rd.flags & MSK_RENDER_TRAVERSAL_STATS) != 0;
-    MSK_CUDA_CHECK(cudaEventRecord(im.ev[0], stream));
     uint64_t launches = 0;
     uint32_t max_bounces = 0, batches = 0;
     bool tail_used = false;
@@ -1310,6 +1362,10 @@ int Renderer::render(cudaStream_t stream, const DScene &sc, const MskRenderDesc 
         return MSK_OK;
     };
 #define MSK_STAGE(st, launch) do { int rc__ = stage_begin(st); if (rc__) return rc__; launch; launches++; rc__ = stage_end(); if (rc__) return rc__; } while (0)
+    // every launch of the job, in stream order (replayed from a CUDA graph when the sequence is fixed, see below)
+    auto enqueue = [&]() -> int {
+    if (rd.clear_film) MSK_CUDA_CHECK(cudaMemsetAsync(d_film, 0, (size_t) npix * stride * sizeof(float), stream));
+    MSK_CUDA_CHECK(cudaMemsetAsync(&pool.ctrl->total_closest, 0, 10 * sizeof(unsigned long long), stream));
     for (uint32_t s0 = rd.sample_begin; s0 < rd.sample_end; s0 += per_batch) {
         BatchParams bp;
         bp.npix = npix; bp.width = W; bp.s0 = s0; bp.ns = std::min(per_batch, rd.sample_end - s0);
@@ -1327,7 +1383,7 @@ int Renderer::render(cudaStream_t stream, const DScene &sc, const MskRenderDesc 
         // needs its shade pass (emission), so a bounded job runs exactly max_depth iterations
         const uint32_t bound = !trace_paths ? 0u : (rd.max_depth > 0 ? (uint32_t) rd.max_depth : (rd.max_depth == 0 ? 0u : 0xffffffffu));
         if (aov && bound == 0) { // the AOV integrator's own ray_intersect (aov.cpp:90) when no path bounce runs
-            MSK_STAGE(ST_INTERSECT, (k_intersect<false><<<pb, 128, 0, stream>>>(sc, pool, 0, 1)));
+            MSK_STAGE(ST_INTERSECT, (k_intersect<false><<<pb, 128, 0, stream>>>(sc, pool, 0, 1, nullptr)));
             MSK_STAGE(ST_FILM, (k_aov_capture<<<(n + 255) / 256, 256, 0, stream>>>(sc, pool, bp, plan)));
             extra_closest += n;
         }
@@ -1337,8 +1393,18 @@ int Renderer::render(cudaStream_t stream, const DScene &sc, const MskRenderDesc 
         uint32_t n_est = n;       // upper bound of the current queue length known to the host (queues only shrink)
         bool poll_pending = false; // a poll of the previous bounce is in flight (async_poll)
         while (bounce < bound) {
-            if (tstats) MSK_STAGE(ST_INTERSECT, (k_intersect<true><<<pb, 128, 0, stream>>>(sc, pool, cur, bounce == 0)));
-            else MSK_STAGE(ST_INTERSECT, (k_intersect<false><<<pb, 128, 0, stream>>>(sc, pool, cur, bounce == 0)));
+            const uint32_t *perm = nullptr;
+            if (im.ray_sort && bounce >= 1 && n_est >= (1u << 18)) { // the reordering pass is timed with the material sort
+                MSK_STAGE(ST_SORT, (k_ray_keys<<<(n_est + 255) / 256, 256, 0, stream>>>(sc, pool, cur, n_est, pool.rs_keys[0], pool.rs_vals[0])));
+                size_t tmp_bytes = im.rs_tmp_bytes;
+                if (stage_begin(ST_SORT)) return MSK_ERR_CUDA;
+                MSK_CUDA_CHECK(cub::DeviceRadixSort::SortPairs(im.rs_tmp, tmp_bytes, pool.rs_keys[0], pool.rs_keys[1], pool.rs_vals[0], pool.rs_vals[1], (int) n_est, 0, 27, stream));
+                if (stage_end()) return MSK_ERR_CUDA;
+                perm = pool.rs_vals[1];
+            }
+            const int tiny_scene = sc.nnodes <= im.static_nodes;
+            if (tstats) MSK_STAGE(ST_INTERSECT, (k_intersect<true><<<pb, 128, 0, stream>>>(sc, pool, cur, bounce == 0 || tiny_scene, perm)));
+            else MSK_STAGE(ST_INTERSECT, (k_intersect<false><<<pb, 128, 0, stream>>>(sc, pool, cur, bounce == 0 || tiny_scene, perm)));
             // the AOV integrator shares the primary hit with the nested path tracer (the reference intersects twice)
             if (aov && bounce == 0) MSK_STAGE(ST_FILM, (k_aov_capture<<<(n + 255) / 256, 256, 0, stream>>>(sc, pool, bp, plan)));
             if (!MSK_SORT_IN_COMMIT) MSK_STAGE(ST_SORT, (k_sort<<<im.sm_count * 4, kSortThreads, 0, stream>>>(sc, pool, cur)));
@@ -1353,7 +1419,7 @@ int Renderer::render(cudaStream_t stream, const DScene &sc, const MskRenderDesc 
             } else {
                 MSK_STAGE(ST_SHADE, (k_shade<-1><<<pb, 128, 0, stream>>>(sc, pool, bp, cur)));
             }
-            const int sh_coherent = (int) bounce < im.shadow_static_bounces;
+            const int sh_coherent = (int) bounce < im.shadow_static_bounces || tiny_scene;
             if (tstats) MSK_STAGE(ST_SHADOW, (k_shadow<true><<<pb, 128, 0, stream>>>(sc, pool, sh_coherent)));
             else MSK_STAGE(ST_SHADOW, (k_shadow<false><<<pb, 128, 0, stream>>>(sc, pool, sh_coherent)));
             k_end_bounce<<<1, 1, 0, stream>>>(pool.ctrl, cur);
@@ -1403,7 +1469,45 @@ int Renderer::render(cudaStream_t stream, const DScene &sc, const MskRenderDesc 
         if (plan.nch) MSK_STAGE(ST_FILM, (k_film_gather_aov<<<fg, fb, 0, stream>>>(sc, pool, bp, d_film, H, stride, plan.nch)));
         batches++;
     }
+    return MSK_OK;
+    };
 #undef MSK_STAGE
+    // A bounded-depth job below the polling depth is a FIXED sequence of launches (queue lengths live on the device): C1 is
+    // 34 launches of 5-90 us each, and the host-side launch cost and the gaps between them were ~7 % of its 1 ms step.  The
+    // sequence is captured once into a CUDA graph and replayed while nothing it depends on changes (scene pointers and
+    // parameters, the render description, the film pointer, the pool); anything else runs launch by launch.
+    const uint32_t bound_all = !trace_paths ? 0u : (rd.max_depth > 0 ? (uint32_t) rd.max_depth : (rd.max_depth == 0 ? 0u : 0xffffffffu));
+    const uint64_t nbatches = nsamples ? ((uint64_t) nsamples + per_batch - 1) / per_batch : 0;
+    const bool graphable = im.use_graph && !timers && !tstats && !im.debug_bounces && bound_all < (uint32_t) im.poll_min_depth && nbatches * (6ull * bound_all + 8) <= 1024;
+    if (graphable) {
+        std::vector<unsigned char> key(sizeof(DScene) + sizeof(MskRenderDesc) + sizeof(float *) + sizeof(AovPlan) + sizeof(int));
+        unsigned char *k = key.data();
+        memcpy(k, &sc, sizeof(DScene)); k += sizeof(DScene);
+        memcpy(k, &rd, sizeof(MskRenderDesc)); k += sizeof(MskRenderDesc);
+        memcpy(k, &d_film, sizeof(float *)); k += sizeof(float *);
+        memcpy(k, &plan, sizeof(AovPlan)); k += sizeof(AovPlan);
+        const int has_aov = aov != nullptr;
+        memcpy(k, &has_aov, sizeof(int));
+        if (!im.graph_exec || key != im.graph_key) {
+            if (im.graph_exec) { cudaGraphExecDestroy(im.graph_exec); im.graph_exec = nullptr; im.graph_key.clear(); }
+            cudaGraph_t graph = nullptr;
+            MSK_CUDA_CHECK(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
+            rc = enqueue();
+            cudaError_t ce = cudaStreamEndCapture(stream, &graph); // always end the capture, also after a failed enqueue
+            if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+            if (ce != cudaSuccess) return cuda_fail(ce, "cudaStreamEndCapture", __FILE__, __LINE__);
+            ce = cudaGraphInstantiate(&im.graph_exec, graph, 0);
+            cudaGraphDestroy(graph);
+            if (ce != cudaSuccess) { im.graph_exec = nullptr; return cuda_fail(ce, "cudaGraphInstantiate", __FILE__, __LINE__); }
+            im.graph_key = key; im.graph_launches = launches; im.graph_bounces = max_bounces; im.graph_batches = batches; im.graph_extra_closest = extra_closest;
+        }
+        launches = im.graph_launches; max_bounces = im.graph_bounces; batches = im.graph_batches; extra_closest = im.graph_extra_closest;
+        MSK_CUDA_CHECK(cudaEventRecord(im.ev[0], stream));
+        MSK_CUDA_CHECK(cudaGraphLaunch(im.graph_exec, stream));
+    } else {
+        MSK_CUDA_CHECK(cudaEventRecord(im.ev[0], stream));
+        if ((rc = enqueue())) return rc;
+    }
     MSK_CUDA_CHECK(cudaEventRecord(im.ev[1], stream));
     MSK_CUDA_CHECK(cudaGetLastError());
     if (stats) {

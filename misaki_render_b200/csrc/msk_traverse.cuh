@@ -30,6 +30,16 @@ constexpr int kStackSize = 64; // node groups + postponed triangle groups: at mo
 #ifndef MSK_PERM_LUT
 #define MSK_PERM_LUT 1
 #endif
+// Lockstep driver: a lane left with nothing but triangles to test ("starved") forces a triangle phase only after it has
+// waited this many iterations; meanwhile other lanes' triangles accumulate and the phase runs with more lanes.
+#ifndef MSK_TRI_PATIENCE
+#define MSK_TRI_PATIENCE 0
+#endif
+// Lockstep driver: node phases per iteration (the triangle phase, the pop and the refill vote are then paid once per
+// MSK_NODE_STEPS node visits; lanes out of node work pop a pending node group in between).
+#ifndef MSK_NODE_STEPS
+#define MSK_NODE_STEPS 1
+#endif
 #ifndef MSK_STATIC_MIN_GROUP
 #define MSK_STATIC_MIN_GROUP 4 /* 32 disables the adaptive group size of short static queues */
 #endif
@@ -422,6 +432,7 @@ __device__ __forceinline__ void trace_queue(const Accel &ac, uint2 *shared_stack
     const uint32_t lane = threadIdx.x & 31u, below = (1u << lane) - 1u;
     bool busy = false, have = false;
     uint32_t q = 0;
+    int waited = 0; // iterations this lane has been starved (MSK_TRI_PATIENCE)
     // prefetched next ray of this lane
     float4 nro = make_float4(0, 0, 0, 0), nrd = make_float4(0, 0, 0, 0);
     uint32_t nq = 0xffffffffu;             // 0xffffffff: none
@@ -475,18 +486,27 @@ __device__ __forceinline__ void trace_queue(const Accel &ac, uint2 *shared_stack
             if (__ballot_sync(0xffffffffu, busy) == 0u) break;
         }
         // ---- node phase
-        if (busy && s.ngroup.y > 0x00ffffffu) {
-            if (s.tgroup.y) stack.store(s.sp++, s.tgroup); // postponed triangles wait on the stack
-            node_step<STATS>(ac, s, stack);
+#pragma unroll
+        for (int rep = 0; rep < MSK_NODE_STEPS; ++rep) {
+            if (rep > 0 && busy && s.ngroup.y <= 0x00ffffffu && s.tgroup.y == 0u && s.sp > 0) { // next node group, if that is what is on top
+                const uint2 g = stack.load(s.sp - 1);
+                if (g.y > 0x00ffffffu) s.ngroup = g; else s.tgroup = g;
+                --s.sp;
+            }
+            if (busy && s.ngroup.y > 0x00ffffffu) {
+                if (s.tgroup.y) stack.store(s.sp++, s.tgroup); // postponed triangles wait on the stack
+                node_step<STATS>(ac, s, stack);
+            }
         }
         // ---- triangle phase
         const bool has_t = busy && s.tgroup.y != 0u;
         const uint32_t mt = __ballot_sync(0xffffffffu, has_t);
         if (mt) {
             const bool starved = has_t && s.ngroup.y <= 0x00ffffffu;
-            if (__popc(mt) >= kTriThreshold || __any_sync(0xffffffffu, starved)) {
+            if (__popc(mt) >= kTriThreshold || __any_sync(0xffffffffu, starved && waited >= MSK_TRI_PATIENCE)) {
                 if (has_t && tri_step<STATS>(ac, s) && ANY) { busy = false; have = true; }
-            }
+                waited = 0;
+            } else if (starved) ++waited;
         }
         // ---- pop
         if (busy && s.ngroup.y <= 0x00ffffffu) {

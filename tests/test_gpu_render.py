@@ -315,6 +315,35 @@ def test_tail_kernel_is_bit_identical(monkeypatch, integrator):
     assert st_tail.kernel_launches < st_wave.kernel_launches
 
 
+def test_graph_replay_and_tiny_scene_scheduling_are_bit_identical(monkeypatch):
+    """Bounded-depth jobs replay a cached CUDA graph of their fixed launch sequence, and scenes of a few wide nodes always
+    use the static traversal: scheduling only -- the film, the AOV film and the counters must not change by a bit, a second
+    call (the replay proper) included, and a changed render description must re-capture."""
+    sd = scenes.cbox(64, 48)
+    rd, rd2 = capi.render_desc(spp=4, max_depth=5), capi.render_desc(spp=6, max_depth=3, sample_begin=1, sample_end=5)
+    types = [capi.AOV_DEPTH, capi.AOV_INTEGRATOR_RGBA]
+    with capi.Context(0) as ctx, capi.Scene(ctx, sd) as sc:
+        film_a, st_a = sc.render(rd)
+        film_b, st_b = sc.render(rd)      # replay of the cached graph
+        film_c, st_c = sc.render(rd2)     # another sequence: re-capture
+        film_d, _ = sc.render(rd)
+        aov_a, ast_a = sc.render_aov(rd, types)
+    np.testing.assert_array_equal(film_a, film_b)
+    np.testing.assert_array_equal(film_a, film_d)
+    assert (st_a.rays_closest, st_a.rays_shadow, st_a.kernel_launches, st_a.bounces) == (st_b.rays_closest, st_b.rays_shadow, st_b.kernel_launches, st_b.bounces)
+    monkeypatch.setenv("MSK_GRAPH", "0")  # read when the context is created
+    monkeypatch.setenv("MSK_STATIC_NODES", "0")
+    with capi.Context(0) as ctx, capi.Scene(ctx, sd) as sc:
+        film_p, st_p = sc.render(rd)
+        film_q, st_q = sc.render(rd2)
+        aov_p, ast_p = sc.render_aov(rd, types)
+    np.testing.assert_array_equal(film_a, film_p)
+    np.testing.assert_array_equal(film_c, film_q)
+    np.testing.assert_array_equal(aov_a, aov_p)
+    assert (st_a.rays_closest, st_a.rays_shadow, st_a.kernel_launches) == (st_p.rays_closest, st_p.rays_shadow, st_p.kernel_launches)
+    assert (st_c.paths, st_c.rays_closest) == (st_q.paths, st_q.rays_closest) and ast_a.rays_closest == ast_p.rays_closest
+
+
 def test_tiled_path_enumeration_is_bit_identical(monkeypatch):
     """Path slots enumerate the pixels of a sample in 8x4 tiles when the film size allows (coherent warps of camera
     rays); seeds depend on (pixel, sample) and the film records stay per pixel, so nothing in the film may change --

@@ -23,8 +23,10 @@ METRICS = "smsp__inst_executed.sum,smsp__thread_inst_executed.sum,dram__bytes_re
 
 
 def run(wls):
+    from bench import source_sha
     out = ROOT / "gpurun_out"
     out.mkdir(exist_ok=True)
+    (out / "ncu_counters_sha.txt").write_text(source_sha())  # the tree the passes below run on
     for wl in wls:
         cmd = ["ncu", "--metrics", METRICS, "--clock-control", "none", "--csv", "--log-file", str(out / f"ncu_counters_{wl}.csv"),
                sys.executable, str(ROOT / "bench.py"), "--workload", wl, "--one-step"]
@@ -39,8 +41,8 @@ def to_num(x, unit):
 
 
 def collect(wls):
-    from bench import source_sha
-    result = {"source_sha": source_sha(), "metrics": METRICS, "how": "tools/ncu_counters.py (one step per workload under ncu --metrics, --clock-control none)",
+    sha = (ROOT / "gpurun_out" / "ncu_counters_sha.txt").read_text().strip()
+    result = {"source_sha": sha, "metrics": METRICS, "how": "tools/ncu_counters.py (one step per workload under ncu --metrics, --clock-control none)",
               "workloads": {}}
     for wl in wls:
         f = ROOT / "gpurun_out" / f"ncu_counters_{wl}.csv"
