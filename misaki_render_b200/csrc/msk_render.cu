@@ -86,25 +86,43 @@ struct BatchParams {
     uint32_t spp;          // of the whole job (seeding)
     uint64_t base_seed;
     int32_t  max_depth, rr_depth, hide_emitters;
-    uint32_t tiled;        // path slots enumerate the pixels of a sample in 8x4 tiles (film size a multiple of 8x4)
+    uint32_t tiled;        // path slots enumerate the film in 8x4 tiles (film size a multiple of 8x4), see slot_decode
+    uint32_t sw_log2;      // tiled: a warp holds 2^sw_log2 consecutive samples of 32 >> sw_log2 pixels (divides ns)
 };
 
-// Path slot p of a sample (0 <= p < npix) -> linear pixel index.  With `tiled`, 32 consecutive slots -- one warp of
-// k_raygen, of the static traversal and of the first shade pass -- cover an 8x4 pixel tile instead of a 32x1 strip, so
-// the camera rays of a warp visit the same nodes and their hit points share material and shadow-ray direction.
-// Only the enumeration order of the paths changes: seeds depend on (pixel, sample) and the film records are written
-// per pixel, so the film is bit-identical.
-__device__ __forceinline__ uint32_t slot_to_pixel(const BatchParams &bp, uint32_t p) {
-    if (!bp.tiled) return p;
-    const uint32_t tiles_x = bp.width >> 3, l = p & 31u;
-    uint32_t t = p >> 5, tx, ty;
+// Path slot i of a batch (0 <= i < npix * ns) -> (linear pixel index, sample offset within the batch).
+//
+// Untiled: sample-major, pixels linear.  With `tiled` (film a multiple of 8x4) the slots of an 8x4 pixel tile are
+// contiguous and a warp -- of k_raygen, of the static traversal of bounce 0, of the first shade and shadow passes --
+// covers 2^sw_log2 consecutive SAMPLES of a compact sub-tile of 32 >> sw_log2 pixels (8x4, 4x4, 4x2, 2x2, 2x1, 1x1:
+// the low bits of the pixel's Morton code inside the tile).  With 32 samples of ONE pixel per warp the camera rays of
+// a warp differ by sub-pixel jitter only: they visit the same nodes and leaves (a static warp of 8x4 pixels of one
+// sample ran at 17.9 of 32 lanes per instruction on C2, profiles/r02d), hit the same material and send their shadow
+// rays from the same spot.  Only the enumeration order of the paths changes: seeds depend on (pixel, sample) and the
+// film records are written per (sample, pixel), so the film is bit-identical.
+__device__ __forceinline__ void slot_decode(const BatchParams &bp, uint32_t i, uint32_t &pixel, uint32_t &s_off) {
+    if (!bp.tiled) { pixel = i % bp.npix; s_off = i / bp.npix; return; }
+    const uint32_t tiles_x = bp.width >> 3, l = i & 31u, w = i >> 5;
+    if (bp.sw_log2 > 5u) { // MSK_SAMPLES_PER_WARP=0 (A/B): the round-1 order, sample-major, one 8x4 tile of one sample per warp
+        const uint32_t p = i % bp.npix, t = p >> 5;
+        s_off = i / bp.npix;
+        pixel = ((t / tiles_x) * 4u + (l >> 3)) * bp.width + (t % tiles_x) * 8u + (l & 7u);
+        return;
+    }
+    const uint32_t sw = bp.sw_log2, pw = 5u - sw;          // log2 of samples / pixels per warp
+    const uint32_t k = w & ((1u << sw) - 1u), tg = w >> sw; // sub-tile of the 8x4 tile | tile * groups + sample group
+    const uint32_t groups = bp.ns >> sw, g = tg % groups;
+    uint32_t t = tg / groups, tx, ty;
     if (bp.tiled == 2u) { // the four warps of a 128-thread block cover a 16x8 block of pixels (2x2 tiles)
-        const uint32_t groups_x = tiles_x >> 1, g = t >> 2, k = t & 3u;
-        tx = (g % groups_x) * 2u + (k & 1u); ty = (g / groups_x) * 2u + (k >> 1);
+        const uint32_t groups_x = tiles_x >> 1, q = t >> 2, c = t & 3u;
+        tx = (q % groups_x) * 2u + (c & 1u); ty = (q / groups_x) * 2u + (c >> 1);
     } else {
         tx = t % tiles_x; ty = t / tiles_x;
     }
-    return (ty * 4u + (l >> 3)) * bp.width + tx * 8u + (l & 7u);
+    const uint32_t m = (k << pw) | (l & ((1u << pw) - 1u)); // Morton code in the tile: x0 y0 x1 y1 x2 from bit 0
+    const uint32_t x = (m & 1u) | ((m >> 1) & 2u) | ((m >> 2) & 4u), y = ((m >> 1) & 1u) | ((m >> 2) & 2u);
+    s_off = (g << sw) + (l >> pw);
+    pixel = (ty * 4u + y) * bp.width + tx * 8u + x;
 }
 
 constexpr uint32_t kFlagDelta = 1u << 16;
@@ -132,7 +150,9 @@ __global__ void __launch_bounds__(256) k_raygen(const __grid_constant__ DScene s
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     uint32_t n = bp.npix * bp.ns;
     if (i >= n) return;
-    uint32_t pixel = slot_to_pixel(bp, i % bp.npix), s = bp.s0 + i / bp.npix;
+    uint32_t pixel, s_off;
+    slot_decode(bp, i, pixel, s_off);
+    const uint32_t s = bp.s0 + s_off;
     uint32_t gx = pixel % bp.width, gy = pixel / bp.width;
     uint64_t rng = pcg_seed((uint64_t) pixel * bp.spp + s + bp.base_seed);
     float jx = next1d(rng), jy = next1d(rng);
@@ -877,31 +897,63 @@ __global__ void __launch_bounds__(128, MSK_TRAV_MIN_BLOCKS) k_shadow(const __gri
 // ---------------------------------------------------------------------------------------
 // Film.  render_sample tail (integrator.cpp:115-125): xyz = spectrum_to_xyz(result * ray_weight).
 __global__ void __launch_bounds__(256) k_film_records(const __grid_constant__ DScene sc, Pool pool, BatchParams bp, int rgba_channel) {
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    uint32_t n = bp.npix * bp.ns;
-    if (i >= n) return;
-    uint32_t pixel = slot_to_pixel(bp, i % bp.npix), s = bp.s0 + i / bp.npix;
-    uint32_t gx = pixel % bp.width, gy = pixel / bp.width;
-    const uint32_t r = (i / bp.npix) * bp.npix + pixel; // record index: the film gathers read records by pixel
-    uint64_t rng = pcg_seed((uint64_t) pixel * bp.spp + s + bp.base_seed);
-    float jx = next1d(rng), jy = next1d(rng);
-    float wav = next1d(rng);
-    float4 wl, weight;
-    sample_wavelength(wav, wl, weight);
-    const float4 spec = pool.L[i];
-    float4 result = spec * weight;
-    float X, Y, Z;
-    spectrum_to_xyz(sc, result, wl, X, Y, Z);
-    pool.rec[r]    = make_float4(X, Y, Z, (float) gx + jx);
-    pool.rec_py[r] = (float) gy + jy;
-    if (rgba_channel >= 0) { // aov.cpp:124-140: xyz_to_srgb(spectrum_to_xyz(spec)) of the nested integrator, before ray_weight
-        float x, y, z;
-        spectrum_to_xyz(sc, spec, wl, x, y, z);
-        float *a = pool.aov + (size_t) rgba_channel * pool.capacity + r;
-        a[0]                         = 3.240479f * x + -1.537150f * y + -0.498535f * z;
-        a[pool.capacity]             = -0.969256f * x + 1.875991f * y + 0.041556f * z;
-        a[2 * (size_t) pool.capacity] = 0.055648f * x + -0.204043f * y + 1.057311f * z;
-        a[3 * (size_t) pool.capacity] = 1.f;
+    // Records are stored by (sample, pixel) for the gather; with several samples of a pixel in one warp (slot_decode)
+    // the 32 lanes of a warp would write 32 different sample planes (measured: film 1.04 -> 1.23 ms on C2, 14.5 -> 21.5
+    // on C3).  The 256 records of a block -- a compact pixel block times a run of samples -- are therefore exchanged
+    // through shared memory so that consecutive threads write the pixels of a row of one sample plane.
+    __shared__ float4 s_rec[256];
+    __shared__ float s_py[256];
+    __shared__ uint32_t s_r[256];
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t n = bp.npix * bp.ns;
+    const bool exchange = bp.tiled && bp.sw_log2 >= 1u && bp.sw_log2 <= 5u;
+    float4 rec = make_float4(0.f, 0.f, 0.f, 0.f);
+    float py = 0.f;
+    uint32_t r = 0xffffffffu;
+    if (i < n) {
+        uint32_t pixel, s_off;
+        slot_decode(bp, i, pixel, s_off);
+        const uint32_t s = bp.s0 + s_off;
+        uint32_t gx = pixel % bp.width, gy = pixel / bp.width;
+        r = s_off * bp.npix + pixel; // record index: the film gathers read records by (sample, pixel)
+        uint64_t rng = pcg_seed((uint64_t) pixel * bp.spp + s + bp.base_seed);
+        float jx = next1d(rng), jy = next1d(rng);
+        float wav = next1d(rng);
+        float4 wl, weight;
+        sample_wavelength(wav, wl, weight);
+        const float4 spec = pool.L[i];
+        float4 result = spec * weight;
+        float X, Y, Z;
+        spectrum_to_xyz(sc, result, wl, X, Y, Z);
+        rec = make_float4(X, Y, Z, (float) gx + jx);
+        py = (float) gy + jy;
+        if (rgba_channel >= 0) { // aov.cpp:124-140: xyz_to_srgb(spectrum_to_xyz(spec)) of the nested integrator, before ray_weight
+            float x, y, z;
+            spectrum_to_xyz(sc, spec, wl, x, y, z);
+            float *a = pool.aov + (size_t) rgba_channel * pool.capacity + r;
+            a[0]                         = 3.240479f * x + -1.537150f * y + -0.498535f * z;
+            a[pool.capacity]             = -0.969256f * x + 1.875991f * y + 0.041556f * z;
+            a[2 * (size_t) pool.capacity] = 0.055648f * x + -0.204043f * y + 1.057311f * z;
+            a[3 * (size_t) pool.capacity] = 1.f;
+        }
+    }
+    if (exchange) {
+        s_rec[threadIdx.x] = rec; s_py[threadIdx.x] = py; s_r[threadIdx.x] = r;
+        __syncthreads();
+        // output thread j -> the thread that computed the j-th record in (group, sample, row-major pixel) order.  The 8
+        // warps of the block hold, per group, `pb` pixels (an aligned Morton block: 8x4, 4x4 or 4x2) times `sw` samples.
+        const uint32_t sw = bp.sw_log2, pw = 5u - sw, pb_log2 = min(5u, 3u + pw), bw_log2 = pb_log2 == 5u ? 3u : 2u;
+        const uint32_t j = threadIdx.x, per_group = 1u << (pb_log2 + sw);
+        const uint32_t grp = j / per_group, q = j % per_group, s_local = q >> pb_log2, pm = q & ((1u << pb_log2) - 1u);
+        const uint32_t x = pm & ((1u << bw_log2) - 1u), y = pm >> bw_log2;
+        const uint32_t m = (x & 1u) | ((y & 1u) << 1) | ((x & 2u) << 1) | ((y & 2u) << 2) | ((x & 4u) << 2);
+        const uint32_t wg_log2 = pb_log2 - pw; // warps per group
+        const uint32_t src = (((grp << wg_log2) + (m >> pw)) << 5) | (s_local << pw) | (m & ((1u << pw) - 1u));
+        rec = s_rec[src]; py = s_py[src]; r = s_r[src];
+    }
+    if (r != 0xffffffffu) {
+        pool.rec[r]    = rec;
+        pool.rec_py[r] = py;
     }
 }
 
@@ -917,7 +969,9 @@ __global__ void __launch_bounds__(256) k_aov_capture(const __grid_constant__ DSc
     sf.p = v3(0, 0, 0); sf.n = v3(0, 0, 0); sf.sh.n = v3(0, 0, 0); sf.uvx = 0.f; sf.uvy = 0.f;
     const bool valid = geom != 0xffffffffu;
     if (valid) sf = make_surface(sc, sc.meshes[geom], __float_as_uint(hit.w), hit.y, hit.z);
-    float *a = pool.aov + (i / bp.npix) * bp.npix + slot_to_pixel(bp, i % bp.npix); // by record index, like k_film_records
+    uint32_t pixel, s_off;
+    slot_decode(bp, i, pixel, s_off);
+    float *a = pool.aov + s_off * bp.npix + pixel; // by record index, like k_film_records
     const size_t cs = pool.capacity;
     uint32_t c = 0;
     for (uint32_t k = 0; k < plan.ntypes; ++k) {
@@ -1152,22 +1206,36 @@ template <typename T> cudaError_t dalloc(T **p, size_t n) { return cudaMalloc((v
 } // namespace
 
 // =========================================================================================
-struct Renderer::Impl {
+// One in-flight batch: its own path pool, stream and poll buffers (see Renderer::render).
+constexpr int kMaxLanes = 4;
+struct Lane {
     Pool pool{};
+    cudaStream_t stream = nullptr;            // lane 0 runs on the caller's stream; the others own one
+    Ctrl *h_poll[2] = { nullptr, nullptr };   // pinned: queue-length polls of unbounded-depth jobs, double-buffered
+    Ctrl *h_ctrl = nullptr;                   // pinned: the lane's counters at the end of a job
+    cudaEvent_t poll_ev[2]{};
+    cudaEvent_t film_done = nullptr;          // the lane's last film kernel of a batch
+    size_t aov_floats = 0;                    // allocated size of pool.aov
+};
+
+struct Renderer::Impl {
+    Lane lanes[kMaxLanes];
+    int npools = 0;        // lanes whose pool is allocated (all with `capacity` paths)
     uint32_t capacity = 0;
     uint32_t *query_cursor = nullptr;
-    Ctrl *h_ctrl = nullptr; // pinned
-    Ctrl *h_poll[2] = { nullptr, nullptr }; // pinned: queue-length polls of unbounded-depth jobs, double-buffered
-    cudaEvent_t poll_ev[2]{};
     cudaEvent_t ev[8]{};
+    cudaEvent_t fork_ev = nullptr;
     // Tuning knobs (environment, read once in init(); defaults are the measured best on C2, tools/ab_knobs.sh)
     uint32_t batch_paths = 32u << 20; // MSK_BATCH_PATHS: paths per wavefront batch (C2: 8 Mi -> 16 Mi = 804 -> 919 Mpaths/s, the per-batch tail of short bounces is paid once)
+    int inflight = 2;                 // MSK_INFLIGHT: batches in flight, each on its own stream and pool (1: one batch after the other)
+    uint32_t split_min = 4u << 20;    // MSK_SPLIT_MIN_PATHS: a job of fewer batches than lanes is split further while a batch keeps this many paths
     int spec_shade = 1;               // MSK_SPEC_SHADE: one k_shade launch per material key present in the scene
     uint32_t spec_min = 1u << 18;     // MSK_SPEC_MIN: ... while the queue may hold at least this many vertices
     int shadow_static_bounces = 0;    // MSK_SHADOW_STATIC_BOUNCES: bounces whose shadow queue counts as coherent
     int debug_bounces = 0;            // MSK_DEBUG_BOUNCES: print polled queue lengths and per-launch stage times to stderr
     uint32_t tail_threshold = 1u << 18; // MSK_TAIL_THRESHOLD: finish an unbounded job with k_tail once the queue is this short (0: never)
-    int tiled_slots = 1;              // MSK_TILED_SLOTS: enumerate the pixels of a sample in 8x4 tiles (see slot_to_pixel)
+    int tiled_slots = 1;              // MSK_TILED_SLOTS: enumerate the film in 8x4 tiles (see slot_decode)
+    int samples_per_warp = 32;        // MSK_SAMPLES_PER_WARP: upper bound of the samples of one pixel group a warp holds (0: sample-major order)
     int poll_min_depth = 8;           // MSK_POLL_MIN_DEPTH: jobs with max_depth >= this (or unbounded) poll the queue length from bounce 4 on
     int async_poll = 1;               // MSK_ASYNC_POLL: poll the queue length one bounce late, without draining the stream
     uint32_t static_nodes = 64;       // MSK_STATIC_NODES: scenes with at most this many wide nodes always use the static traversal (every ray does the same few steps: nothing to re-balance)
@@ -1180,27 +1248,78 @@ struct Renderer::Impl {
     std::vector<cudaEvent_t> timer_events; // MSK_RENDER_STAGE_TIMERS
     std::vector<int> timer_stage;
     int persistent_blocks = 0, sm_count = 0;
-    size_t aov_floats = 0; // allocated size of pool.aov
+
+    void free_pools() {
+        for (int l = 0; l < kMaxLanes; ++l) {
+            Pool &p = lanes[l].pool;
+            for (int i = 0; i < 2; ++i) { cudaFree(p.rays[i]); cudaFree(p.T[i]); cudaFree(p.WL[i]); cudaFree(p.AUX[i]); cudaFree(p.MISC[i]); }
+            cudaFree(p.hit); cudaFree(p.hit_geom); cudaFree(p.L); cudaFree(p.sh_ray); cudaFree(p.sh_contrib); cudaFree(p.sh_path);
+            cudaFree(p.sorted); cudaFree(p.rec); cudaFree(p.rec_py); cudaFree(p.ctrl); cudaFree(p.aov);
+            for (int i = 0; i < 2; ++i) { cudaFree(p.rs_keys[i]); cudaFree(p.rs_vals[i]); }
+            p = Pool{};
+            lanes[l].aov_floats = 0;
+        }
+        cudaFree(rs_tmp); rs_tmp = nullptr; rs_tmp_bytes = 0;
+        npools = 0; capacity = 0;
+    }
+    void drop_graph() {
+        if (graph_exec) { cudaGraphExecDestroy(graph_exec); graph_exec = nullptr; graph_key.clear(); }
+    }
+    // samples per pixel and batch, lanes in flight for a job of `nsamples` samples per pixel over `npix` pixels
+    void plan(uint32_t npix, uint32_t nsamples, uint32_t paths_per_batch, bool single_lane, uint32_t *per_batch, int *nlanes) const {
+        const uint32_t target = paths_per_batch ? paths_per_batch : batch_paths;
+        uint32_t pb = std::max(1u, target / npix);
+        int nl = single_lane ? 1 : std::min(std::max(inflight, 1), kMaxLanes);
+        nsamples = std::max(nsamples, 1u);
+        if (nl > 1 && !paths_per_batch) { // fewer batches than lanes: split while a batch stays large enough to fill the machine
+            const uint32_t want = (nsamples + (uint32_t) nl - 1u) / (uint32_t) nl;
+            const uint32_t floor_ = std::max(1u, split_min / npix);
+            if (want < pb) pb = std::max(want, std::min(floor_, pb));
+        }
+        // a warp holds up to 32 samples of a pixel (slot_decode): keep the batch a multiple of 32, else a power of two
+        if (pb >= 32u) pb &= ~31u;
+        else { uint32_t q = 1; while (q * 2u <= pb) q *= 2u; pb = q; }
+        pb = std::min(pb, nsamples);
+        const uint32_t nbatches = (nsamples + pb - 1u) / pb;
+        *per_batch = pb;
+        *nlanes = (int) std::min<uint32_t>((uint32_t) nl, nbatches);
+    }
+    // What a job runs as (shared by reserve() and render(), which must agree on the pools).  A bounded-depth job below the
+    // polling depth is a FIXED sequence of launches (queue lengths live on the device): C1 is 34 launches of 5-90 us
+    // each, and the host-side launch cost and the gaps between them were ~7 % of its 1 ms step.  The sequence is captured
+    // once into a CUDA graph and replayed while nothing it depends on changes (scene pointers and parameters, the render
+    // description, the film pointer, the pool); anything else runs launch by launch.
+    // One lane: profiling modes (stage timers and traversal counters describe one batch at a time), the AOV integrator
+    // (one bounce), graph replay, the ray-sort experiment (one scratch buffer).
+    void job_plan(uint32_t npix, const MskRenderDesc &rd, bool has_aov, uint32_t bound, uint32_t *per_batch, int *nlanes, bool *graphable) const {
+        const uint32_t nsamples = rd.sample_end - rd.sample_begin;
+        const bool timers = (rd.flags & MSK_RENDER_STAGE_TIMERS) != 0, tstats = (rd.flags & MSK_RENDER_TRAVERSAL_STATS) != 0;
+        plan(npix, nsamples, rd.paths_per_batch, true, per_batch, nlanes);
+        const uint64_t nbatches1 = nsamples ? ((uint64_t) nsamples + *per_batch - 1) / *per_batch : 0;
+        *graphable = use_graph && !timers && !tstats && !debug_bounces && bound < (uint32_t) poll_min_depth && nbatches1 * (6ull * bound + 8) <= 1024;
+        const bool single = timers || tstats || debug_bounces || ray_sort || has_aov || *graphable || bound == 0;
+        if (!single) plan(npix, nsamples, rd.paths_per_batch, false, per_batch, nlanes);
+    }
 };
 
 Renderer::Renderer() : impl_(new Impl) {}
 Renderer::~Renderer() { release(); delete impl_; }
 
 void Renderer::release() {
-    if (impl_->graph_exec) { cudaGraphExecDestroy(impl_->graph_exec); impl_->graph_exec = nullptr; impl_->graph_key.clear(); }
-    Pool &p = impl_->pool;
-    for (int i = 0; i < 2; ++i) { cudaFree(p.rays[i]); cudaFree(p.T[i]); cudaFree(p.WL[i]); cudaFree(p.AUX[i]); cudaFree(p.MISC[i]); }
-    cudaFree(p.hit); cudaFree(p.hit_geom); cudaFree(p.L); cudaFree(p.sh_ray); cudaFree(p.sh_contrib); cudaFree(p.sh_path);
-    cudaFree(p.sorted); cudaFree(p.rec); cudaFree(p.rec_py); cudaFree(p.ctrl); cudaFree(p.aov);
-    for (int i = 0; i < 2; ++i) { cudaFree(p.rs_keys[i]); cudaFree(p.rs_vals[i]); }
-    cudaFree(impl_->rs_tmp); impl_->rs_tmp = nullptr; impl_->rs_tmp_bytes = 0;
-    p = Pool{};
-    impl_->capacity = 0; impl_->aov_floats = 0;
+    impl_->drop_graph();
+    impl_->free_pools();
     cudaFree(impl_->query_cursor); impl_->query_cursor = nullptr;
-    if (impl_->h_ctrl) { cudaFreeHost(impl_->h_ctrl); impl_->h_ctrl = nullptr; }
-    for (auto &h : impl_->h_poll) if (h) { cudaFreeHost(h); h = nullptr; }
-    for (auto &e : impl_->poll_ev) if (e) { cudaEventDestroy(e); e = nullptr; }
+    for (int l = 0; l < kMaxLanes; ++l) {
+        Lane &ln = impl_->lanes[l];
+        if (l > 0 && ln.stream) { cudaStreamDestroy(ln.stream); }
+        ln.stream = nullptr;
+        if (ln.h_ctrl) { cudaFreeHost(ln.h_ctrl); ln.h_ctrl = nullptr; }
+        for (auto &h : ln.h_poll) if (h) { cudaFreeHost(h); h = nullptr; }
+        for (auto &e : ln.poll_ev) if (e) { cudaEventDestroy(e); e = nullptr; }
+        if (ln.film_done) { cudaEventDestroy(ln.film_done); ln.film_done = nullptr; }
+    }
     for (auto &e : impl_->ev) if (e) { cudaEventDestroy(e); e = nullptr; }
+    if (impl_->fork_ev) { cudaEventDestroy(impl_->fork_ev); impl_->fork_ev = nullptr; }
     for (auto &e : impl_->timer_events) cudaEventDestroy(e);
     impl_->timer_events.clear();
 }
@@ -1209,15 +1328,23 @@ int Renderer::init(int sm_count) {
     impl_->sm_count = sm_count;
     impl_->persistent_blocks = sm_count * 8; // 128-thread CTAs, 8 resident per SM
     MSK_CUDA_CHECK(dalloc(&impl_->query_cursor, 1));
-    MSK_CUDA_CHECK(cudaMallocHost((void **) &impl_->h_ctrl, sizeof(Ctrl)));
-    for (auto &h : impl_->h_poll) MSK_CUDA_CHECK(cudaMallocHost((void **) &h, sizeof(Ctrl)));
-    for (auto &e : impl_->poll_ev) MSK_CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    for (int l = 0; l < kMaxLanes; ++l) {
+        Lane &ln = impl_->lanes[l];
+        if (l > 0) MSK_CUDA_CHECK(cudaStreamCreateWithFlags(&ln.stream, cudaStreamNonBlocking));
+        MSK_CUDA_CHECK(cudaMallocHost((void **) &ln.h_ctrl, sizeof(Ctrl)));
+        for (auto &h : ln.h_poll) MSK_CUDA_CHECK(cudaMallocHost((void **) &h, sizeof(Ctrl)));
+        for (auto &e : ln.poll_ev) MSK_CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        MSK_CUDA_CHECK(cudaEventCreateWithFlags(&ln.film_done, cudaEventDisableTiming));
+    }
     for (auto &e : impl_->ev) MSK_CUDA_CHECK(cudaEventCreate(&e));
+    MSK_CUDA_CHECK(cudaEventCreateWithFlags(&impl_->fork_ev, cudaEventDisableTiming));
     auto env_u = [](const char *name, long long dflt) -> long long {
         const char *v = getenv(name);
         return (v && *v) ? atoll(v) : dflt;
     };
     impl_->batch_paths = (uint32_t) std::max<long long>(1, env_u("MSK_BATCH_PATHS", impl_->batch_paths));
+    impl_->inflight = (int) env_u("MSK_INFLIGHT", impl_->inflight);
+    impl_->split_min = (uint32_t) std::max<long long>(1, env_u("MSK_SPLIT_MIN_PATHS", impl_->split_min));
     impl_->spec_shade = (int) env_u("MSK_SPEC_SHADE", impl_->spec_shade);
     impl_->spec_min = (uint32_t) env_u("MSK_SPEC_MIN", impl_->spec_min);
     impl_->shadow_static_bounces = (int) env_u("MSK_SHADOW_STATIC_BOUNCES", impl_->shadow_static_bounces);
@@ -1225,6 +1352,7 @@ int Renderer::init(int sm_count) {
     impl_->tail_threshold = (uint32_t) env_u("MSK_TAIL_THRESHOLD", impl_->tail_threshold);
     impl_->poll_min_depth = (int) env_u("MSK_POLL_MIN_DEPTH", impl_->poll_min_depth);
     impl_->tiled_slots = (int) env_u("MSK_TILED_SLOTS", impl_->tiled_slots);
+    impl_->samples_per_warp = (int) env_u("MSK_SAMPLES_PER_WARP", impl_->samples_per_warp);
     impl_->ray_sort = (int) env_u("MSK_RAY_SORT", impl_->ray_sort);
     impl_->use_graph = (int) env_u("MSK_GRAPH", impl_->use_graph);
     impl_->static_nodes = (uint32_t) env_u("MSK_STATIC_NODES", impl_->static_nodes);
@@ -1232,34 +1360,37 @@ int Renderer::init(int sm_count) {
     return MSK_OK;
 }
 
-int Renderer::ensure_pool(uint32_t capacity) {
-    if (capacity <= impl_->capacity) return MSK_OK;
-    if (impl_->graph_exec) { cudaGraphExecDestroy(impl_->graph_exec); impl_->graph_exec = nullptr; impl_->graph_key.clear(); } // captured the old pool
-    Pool &p = impl_->pool;
-    for (int i = 0; i < 2; ++i) { cudaFree(p.rays[i]); cudaFree(p.T[i]); cudaFree(p.WL[i]); cudaFree(p.AUX[i]); cudaFree(p.MISC[i]); }
-    cudaFree(p.hit); cudaFree(p.hit_geom); cudaFree(p.L); cudaFree(p.sh_ray); cudaFree(p.sh_contrib); cudaFree(p.sh_path);
-    cudaFree(p.sorted); cudaFree(p.rec); cudaFree(p.rec_py); cudaFree(p.ctrl); cudaFree(p.aov);
-    for (int i = 0; i < 2; ++i) { cudaFree(p.rs_keys[i]); cudaFree(p.rs_vals[i]); }
-    cudaFree(impl_->rs_tmp); impl_->rs_tmp = nullptr; impl_->rs_tmp_bytes = 0;
-    p = Pool{};
-    impl_->capacity = 0; impl_->aov_floats = 0;
-    size_t n = capacity;
-    for (int i = 0; i < 2; ++i) {
-        MSK_CUDA_CHECK(dalloc(&p.rays[i], n)); MSK_CUDA_CHECK(dalloc(&p.T[i], n)); MSK_CUDA_CHECK(dalloc(&p.WL[i], n));
-        MSK_CUDA_CHECK(dalloc(&p.AUX[i], n)); MSK_CUDA_CHECK(dalloc(&p.MISC[i], n));
+// `count` pools of `capacity` paths each (pools only grow; a larger capacity re-allocates them all)
+int Renderer::ensure_pool(uint32_t capacity, int count) {
+    Impl &im = *impl_;
+    count = std::max(count, 1);
+    if (capacity <= im.capacity && count <= im.npools) return MSK_OK;
+    im.drop_graph(); // captured the old pool
+    if (capacity > im.capacity) { count = std::max(count, im.npools); im.free_pools(); }
+    else capacity = im.capacity;
+    const size_t n = capacity;
+    for (int l = im.npools; l < count; ++l) {
+        Pool &p = im.lanes[l].pool;
+        for (int i = 0; i < 2; ++i) {
+            MSK_CUDA_CHECK(dalloc(&p.rays[i], n)); MSK_CUDA_CHECK(dalloc(&p.T[i], n)); MSK_CUDA_CHECK(dalloc(&p.WL[i], n));
+            MSK_CUDA_CHECK(dalloc(&p.AUX[i], n)); MSK_CUDA_CHECK(dalloc(&p.MISC[i], n));
+        }
+        MSK_CUDA_CHECK(dalloc(&p.hit, n)); MSK_CUDA_CHECK(dalloc(&p.hit_geom, n)); MSK_CUDA_CHECK(dalloc(&p.L, n));
+        MSK_CUDA_CHECK(dalloc(&p.sh_ray, n)); MSK_CUDA_CHECK(dalloc(&p.sh_contrib, n)); MSK_CUDA_CHECK(dalloc(&p.sh_path, n));
+        MSK_CUDA_CHECK(dalloc(&p.sorted, n * kNumKeys)); MSK_CUDA_CHECK(dalloc(&p.rec, n)); MSK_CUDA_CHECK(dalloc(&p.rec_py, n));
+        MSK_CUDA_CHECK(dalloc(&p.ctrl, 1));
+        MSK_CUDA_CHECK(cudaMemset(p.ctrl, 0, sizeof(Ctrl)));
+        if (im.ray_sort) {
+            for (int i = 0; i < 2; ++i) { MSK_CUDA_CHECK(dalloc(&p.rs_keys[i], n)); MSK_CUDA_CHECK(dalloc(&p.rs_vals[i], n)); }
+            if (!im.rs_tmp) {
+                MSK_CUDA_CHECK(cub::DeviceRadixSort::SortPairs(nullptr, im.rs_tmp_bytes, p.rs_keys[0], p.rs_keys[1], p.rs_vals[0], p.rs_vals[1], (int) n, 0, 27));
+                MSK_CUDA_CHECK(cudaMalloc(&im.rs_tmp, std::max<size_t>(im.rs_tmp_bytes, 16)));
+            }
+        }
+        p.capacity = capacity;
+        im.npools = l + 1;
     }
-    MSK_CUDA_CHECK(dalloc(&p.hit, n)); MSK_CUDA_CHECK(dalloc(&p.hit_geom, n)); MSK_CUDA_CHECK(dalloc(&p.L, n));
-    MSK_CUDA_CHECK(dalloc(&p.sh_ray, n)); MSK_CUDA_CHECK(dalloc(&p.sh_contrib, n)); MSK_CUDA_CHECK(dalloc(&p.sh_path, n));
-    MSK_CUDA_CHECK(dalloc(&p.sorted, n * kNumKeys)); MSK_CUDA_CHECK(dalloc(&p.rec, n)); MSK_CUDA_CHECK(dalloc(&p.rec_py, n));
-    MSK_CUDA_CHECK(dalloc(&p.ctrl, 1));
-    MSK_CUDA_CHECK(cudaMemset(p.ctrl, 0, sizeof(Ctrl)));
-    if (impl_->ray_sort) {
-        for (int i = 0; i < 2; ++i) { MSK_CUDA_CHECK(dalloc(&p.rs_keys[i], n)); MSK_CUDA_CHECK(dalloc(&p.rs_vals[i], n)); }
-        MSK_CUDA_CHECK(cub::DeviceRadixSort::SortPairs(nullptr, impl_->rs_tmp_bytes, p.rs_keys[0], p.rs_keys[1], p.rs_vals[0], p.rs_vals[1], (int) n, 0, 27));
-        MSK_CUDA_CHECK(cudaMalloc(&impl_->rs_tmp, std::max<size_t>(impl_->rs_tmp_bytes, 16)));
-    }
-    p.capacity = capacity;
-    impl_->capacity = capacity;
+    im.capacity = capacity;
     return MSK_OK;
 }
 
@@ -1278,7 +1409,7 @@ int Renderer::aov_plan(const MskAovDesc &aov, uint32_t *nch) {
     return MSK_OK;
 }
 
-// Allocates the path pool a render of `rd` will use, so that the render itself makes no allocation.  cudaMalloc
+// Allocates the path pools a render of `rd` will use, so that the render itself makes no allocation.  cudaMalloc
 // synchronises the whole device; msk_gpu_render_multi calls this for every context before any of them starts, because one
 // context's reduction kernel may already be spinning on a flag that another context OF THE SAME DEVICE publishes only after
 // its render (two contexts on one GPU: the one-GPU test of the multi-device path).
@@ -1287,13 +1418,21 @@ int Renderer::reserve(const DScene &sc, const MskRenderDesc &rd) {
     if (!npix64 || npix64 > (1ull << 27)) return fail(MSK_ERR_UNSUPPORTED, "film size %ux%u unsupported", sc.cam.width, sc.cam.height);
     if (rd.sample_end < rd.sample_begin || rd.sample_end > rd.spp) return fail(MSK_ERR_ARG, "bad sample range");
     const uint32_t npix = (uint32_t) npix64;
-    const uint32_t target = rd.paths_per_batch ? rd.paths_per_batch : impl_->batch_paths;
-    uint32_t per_batch = std::max(1u, target / npix);
-    per_batch = std::min(per_batch, std::max(rd.sample_end - rd.sample_begin, 1u));
-    return ensure_pool(npix * per_batch);
+    const uint32_t bound = rd.max_depth > 0 ? (uint32_t) rd.max_depth : (rd.max_depth == 0 ? 0u : 0xffffffffu);
+    uint32_t per_batch; int nlanes; bool graphable;
+    impl_->job_plan(npix, rd, false, bound, &per_batch, &nlanes, &graphable);
+    return ensure_pool(npix * per_batch, nlanes);
 }
 
-int Renderer::render(cudaStream_t stream, const DScene &sc, const MskRenderDesc &rd, float *d_film, MskStats *stats, const MskAovDesc *aov) {
+// The batch loop.  A batch is all pixels x a run of consecutive samples; its bounces are a chain of dependent launches
+// whose queues thin out geometrically, so the late bounces of a batch cannot fill the machine (C3: bounces 8-16 run over
+// < 0.5 M rays each, 5 launches per bounce; the fog workload has ~60 such bounces per batch).  Up to MSK_INFLIGHT batches
+// are therefore IN FLIGHT at once, each on its own stream with its own path pool: the thin tail of one batch runs under
+// the fat bounces of the next, which is what a regenerating path pool buys without mixing path depths in one
+// queue -- the sorted, depth-uniform wavefront and the per-batch film gather stay as they are.  The film stays
+// bit-deterministic: the film kernels of batch b wait (event) for those of batch b - 1, so every pixel accumulates its
+// batches in order.
+int Renderer::render(cudaStream_t stream0, const DScene &sc, const MskRenderDesc &rd, float *d_film, MskStats *stats, const MskAovDesc *aov) {
     const uint32_t W = sc.cam.width, H = sc.cam.height;
     const uint64_t npix64 = (uint64_t) W * H;
     if (!W || !H || npix64 > (1ull << 27)) return fail(MSK_ERR_UNSUPPORTED, "film size %ux%u unsupported", W, H);
@@ -1301,19 +1440,17 @@ int Renderer::render(cudaStream_t stream, const DScene &sc, const MskRenderDesc 
     if (rd.integrator > MSK_INTEGRATOR_VOLPATH) return fail(MSK_ERR_ARG, "unknown integrator %u", rd.integrator);
     if (rd.rr_depth <= 0) return fail(MSK_ERR_ARG, "\"rr_depth\" must be set to a value greater than zero!");
     if (rd.max_depth < 0 && rd.max_depth != -1) return fail(MSK_ERR_ARG, "\"max_depth\" must be set to -1 (infinite) or a value >= 0");
-    const uint32_t npix = (uint32_t) npix64;
-    const uint32_t im_batch_paths = impl_->batch_paths;
-    uint32_t target = rd.paths_per_batch ? rd.paths_per_batch : im_batch_paths;
-    uint32_t per_batch = std::max(1u, target / npix);
-    const uint32_t nsamples = rd.sample_end - rd.sample_begin;
-    per_batch = std::min(per_batch, std::max(nsamples, 1u));
-    int rc = ensure_pool(npix * per_batch);
-    if (rc) return rc;
-    Pool &pool = impl_->pool;
     Impl &im = *impl_;
+    const uint32_t npix = (uint32_t) npix64;
+    const uint32_t nsamples = rd.sample_end - rd.sample_begin;
+    const bool tstats = (rd.flags & MSK_RENDER_TRAVERSAL_STATS) != 0;
+    // MSK_RENDER_STAGE_TIMERS: bracket every launch with a pair of events (a profiling aid used by bench.py
+    // for the per-kernel roofline; the extra event records perturb ms_render slightly, so it is off by default)
+    const bool timers = (rd.flags & MSK_RENDER_STAGE_TIMERS) != 0;
     // AOV integrator: film stride 5 + nch; per-sample AOV values live beside the path pool
     AovPlan plan{};
     plan.rgba_channel = -1;
+    int rc;
     if (aov) {
         if ((rc = aov_plan(*aov, &plan.nch))) return rc;
         plan.ntypes = aov->ntypes;
@@ -1323,162 +1460,238 @@ int Renderer::render(cudaStream_t stream, const DScene &sc, const MskRenderDesc 
             if (aov->types[i] == MSK_AOV_INTEGRATOR_RGBA) plan.rgba_channel = (int32_t) c;
             c += per[aov->types[i]];
         }
-        const size_t need = (size_t) impl_->capacity * std::max(plan.nch, 1u);
-        if (im.aov_floats < need) {
-            cudaFree(pool.aov); pool.aov = nullptr; im.aov_floats = 0;
-            MSK_CUDA_CHECK(dalloc(&pool.aov, need));
-            im.aov_floats = need;
-        }
     }
     const uint32_t stride = 5 + plan.nch;
     const bool trace_paths = !aov || plan.rgba_channel >= 0; // an AOV integrator without a nested one traces primary rays only
+    // a path reaches vertex `depth` only while depth <= max_depth, and the vertex at max_depth still
+    // needs its shade pass (emission), so a bounded job runs exactly max_depth iterations
+    const uint32_t bound = !trace_paths ? 0u : (rd.max_depth > 0 ? (uint32_t) rd.max_depth : (rd.max_depth == 0 ? 0u : 0xffffffffu));
+    uint32_t per_batch; int nlanes; bool graphable;
+    im.job_plan(npix, rd, aov != nullptr, bound, &per_batch, &nlanes, &graphable);
+    if ((rc = ensure_pool(npix * per_batch, nlanes))) return rc;
+    if (aov) {
+        Lane &l0 = im.lanes[0];
+        const size_t need = (size_t) im.capacity * std::max(plan.nch, 1u);
+        if (l0.aov_floats < need) {
+            cudaFree(l0.pool.aov); l0.pool.aov = nullptr; l0.aov_floats = 0;
+            MSK_CUDA_CHECK(dalloc(&l0.pool.aov, need));
+            l0.aov_floats = need;
+        }
+    }
+    im.lanes[0].stream = stream0;
 
-    const bool tstats = (rd.flags & MSK_RENDER_TRAVERSAL_STATS) != 0;
     uint64_t launches = 0;
     uint32_t max_bounces = 0, batches = 0;
     bool tail_used = false;
     const int pb = im.persistent_blocks;
-    // MSK_RENDER_STAGE_TIMERS: bracket every launch with a pair of events (a profiling aid used by bench.py
-    // for the per-kernel roofline; the extra event records perturb ms_render slightly, so it is off by default)
-    const bool timers = (rd.flags & MSK_RENDER_STAGE_TIMERS) != 0;
     enum { ST_RAYGEN, ST_INTERSECT, ST_SORT, ST_SHADE, ST_SHADOW, ST_FILM, ST_TAIL, ST_COUNT };
     uint64_t extra_closest = 0;
     std::vector<int> &tstage = im.timer_stage;
     tstage.clear();
     size_t tev = 0;
-    auto stage_begin = [&](int st) -> int {
+    auto stage_begin = [&](int st) -> int { // (timers imply one lane: the caller's stream)
         if (!timers) return MSK_OK;
         if (tev + 2 > im.timer_events.size()) {
             for (int k = 0; k < 2; ++k) { cudaEvent_t e; MSK_CUDA_CHECK(cudaEventCreate(&e)); im.timer_events.push_back(e); }
         }
         tstage.push_back(st);
-        MSK_CUDA_CHECK(cudaEventRecord(im.timer_events[tev], stream));
+        MSK_CUDA_CHECK(cudaEventRecord(im.timer_events[tev], stream0));
         return MSK_OK;
     };
     auto stage_end = [&]() -> int {
         if (!timers) return MSK_OK;
-        MSK_CUDA_CHECK(cudaEventRecord(im.timer_events[tev + 1], stream));
+        MSK_CUDA_CHECK(cudaEventRecord(im.timer_events[tev + 1], stream0));
         tev += 2;
         return MSK_OK;
     };
 #define MSK_STAGE(st, launch) do { int rc__ = stage_begin(st); if (rc__) return rc__; launch; launches++; rc__ = stage_end(); if (rc__) return rc__; } while (0)
-    // every launch of the job, in stream order (replayed from a CUDA graph when the sequence is fixed, see below)
-    auto enqueue = [&]() -> int {
-    if (rd.clear_film) MSK_CUDA_CHECK(cudaMemsetAsync(d_film, 0, (size_t) npix * stride * sizeof(float), stream));
-    MSK_CUDA_CHECK(cudaMemsetAsync(&pool.ctrl->total_closest, 0, 10 * sizeof(unsigned long long), stream));
-    for (uint32_t s0 = rd.sample_begin; s0 < rd.sample_end; s0 += per_batch) {
-        BatchParams bp;
+
+    // state of the batch a lane is working on
+    struct Run {
+        bool active = false, done = false;
+        uint64_t index = 0;      // batch number within the job
+        BatchParams bp{};
+        uint32_t n = 0, bounce = 0, n_est = 0;
+        int cur = 0;
+        bool poll = false, use_tail = false, poll_pending = false;
+    };
+    Run runs[kMaxLanes];
+
+    // raygen of a new batch
+    auto start = [&](int li, uint64_t index, uint32_t s0) -> int {
+        Lane &ln = im.lanes[li];
+        Pool &pool = ln.pool;
+        cudaStream_t stream = ln.stream;
+        Run &r = runs[li];
+        r = Run{};
+        r.active = true; r.index = index;
+        BatchParams &bp = r.bp;
         bp.npix = npix; bp.width = W; bp.s0 = s0; bp.ns = std::min(per_batch, rd.sample_end - s0);
         bp.spp = rd.spp; bp.base_seed = rd.base_seed;
         bp.max_depth = rd.max_depth; bp.rr_depth = rd.rr_depth; bp.hide_emitters = rd.hide_emitters;
         bp.tiled = (im.tiled_slots && W % 8u == 0 && H % 4u == 0) ? 1u : 0u;
         if (bp.tiled && im.tiled_slots >= 2 && W % 16u == 0 && H % 8u == 0) bp.tiled = 2u;
+        bp.sw_log2 = 0;
+        if (im.samples_per_warp <= 0) bp.sw_log2 = 0xffffffffu;
+        else while (bp.sw_log2 < 5u && (2u << bp.sw_log2) <= (uint32_t) im.samples_per_warp && bp.ns % (2u << bp.sw_log2) == 0u) bp.sw_log2++;
         const uint32_t n = npix * bp.ns;
+        r.n = n; r.n_est = n; // n_est: upper bound of the current queue length known to the host (queues only shrink)
         k_begin_batch<<<1, 1, 0, stream>>>(pool.ctrl, n);
         launches++;
         MSK_STAGE(ST_RAYGEN, (k_raygen<<<(n + 255) / 256, 256, 0, stream>>>(sc, pool, bp)));
-        int cur = 0;
-        uint32_t bounce = 0;
-        // a path reaches vertex `depth` only while depth <= max_depth, and the vertex at max_depth still
-        // needs its shade pass (emission), so a bounded job runs exactly max_depth iterations
-        const uint32_t bound = !trace_paths ? 0u : (rd.max_depth > 0 ? (uint32_t) rd.max_depth : (rd.max_depth == 0 ? 0u : 0xffffffffu));
         if (aov && bound == 0) { // the AOV integrator's own ray_intersect (aov.cpp:90) when no path bounce runs
             MSK_STAGE(ST_INTERSECT, (k_intersect<false><<<pb, 128, 0, stream>>>(sc, pool, 0, 1, nullptr)));
             MSK_STAGE(ST_FILM, (k_aov_capture<<<(n + 255) / 256, 256, 0, stream>>>(sc, pool, bp, plan)));
             extra_closest += n;
         }
         // (not with MSK_RENDER_TRAVERSAL_STATS: the per-stage node / triangle counters then describe the wavefront kernels alone)
-        const bool poll = bound >= (uint32_t) im.poll_min_depth; // unbounded jobs, and bounded ones deep enough to have a thin tail
-        const bool use_tail = im.tail_threshold > 0 && poll && !tstats;
-        uint32_t n_est = n;       // upper bound of the current queue length known to the host (queues only shrink)
-        bool poll_pending = false; // a poll of the previous bounce is in flight (async_poll)
-        while (bounce < bound) {
-            const uint32_t *perm = nullptr;
-            if (im.ray_sort && bounce >= 1 && n_est >= (1u << 18)) { // the reordering pass is timed with the material sort
-                MSK_STAGE(ST_SORT, (k_ray_keys<<<(n_est + 255) / 256, 256, 0, stream>>>(sc, pool, cur, n_est, pool.rs_keys[0], pool.rs_vals[0])));
-                size_t tmp_bytes = im.rs_tmp_bytes;
-                if (stage_begin(ST_SORT)) return MSK_ERR_CUDA;
-                MSK_CUDA_CHECK(cub::DeviceRadixSort::SortPairs(im.rs_tmp, tmp_bytes, pool.rs_keys[0], pool.rs_keys[1], pool.rs_vals[0], pool.rs_vals[1], (int) n_est, 0, 27, stream));
-                if (stage_end()) return MSK_ERR_CUDA;
-                perm = pool.rs_vals[1];
-            }
-            const int tiny_scene = sc.nnodes <= im.static_nodes;
-            if (tstats) MSK_STAGE(ST_INTERSECT, (k_intersect<true><<<pb, 128, 0, stream>>>(sc, pool, cur, bounce == 0 || tiny_scene, perm)));
-            else MSK_STAGE(ST_INTERSECT, (k_intersect<false><<<pb, 128, 0, stream>>>(sc, pool, cur, bounce == 0 || tiny_scene, perm)));
-            // the AOV integrator shares the primary hit with the nested path tracer (the reference intersects twice)
-            if (aov && bounce == 0) MSK_STAGE(ST_FILM, (k_aov_capture<<<(n + 255) / 256, 256, 0, stream>>>(sc, pool, bp, plan)));
-            if (!MSK_SORT_IN_COMMIT) MSK_STAGE(ST_SORT, (k_sort<<<im.sm_count * 4, kSortThreads, 0, stream>>>(sc, pool, cur)));
-            if (rd.integrator == MSK_INTEGRATOR_VOLPATH) {
-                MSK_STAGE(ST_SHADE, (k_shade_vol<<<pb, 128, 0, stream>>>(sc, pool, bp, cur)));
-            } else if (im.spec_shade && n_est >= im.spec_min) {
-                const uint32_t keys = 1u | (sc.bsdf_type_mask << 1);
-#define MSK_SHADE_KEY(K) if (keys & (1u << K)) MSK_STAGE(ST_SHADE, (k_shade<K><<<pb, 128, 0, stream>>>(sc, pool, bp, cur)))
-                MSK_SHADE_KEY(0); MSK_SHADE_KEY(1); MSK_SHADE_KEY(2); MSK_SHADE_KEY(3); MSK_SHADE_KEY(4); MSK_SHADE_KEY(5);
-#undef MSK_SHADE_KEY
-                static_assert(kNumKeys == 6, "one specialised k_shade launch per key");
-            } else {
-                MSK_STAGE(ST_SHADE, (k_shade<-1><<<pb, 128, 0, stream>>>(sc, pool, bp, cur)));
-            }
-            const int sh_coherent = (int) bounce < im.shadow_static_bounces || tiny_scene;
-            if (tstats) MSK_STAGE(ST_SHADOW, (k_shadow<true><<<pb, 128, 0, stream>>>(sc, pool, sh_coherent)));
-            else MSK_STAGE(ST_SHADOW, (k_shadow<false><<<pb, 128, 0, stream>>>(sc, pool, sh_coherent)));
-            k_end_bounce<<<1, 1, 0, stream>>>(pool.ctrl, cur);
-            launches++;
-            cur ^= 1;
-            bounce++;
-            // unbounded paths (Russian roulette only): poll the queue length once it is likely short.  The poll of
-            // bounce b is read after bounce b+1 has been enqueued, so the stream never drains; the price is one
-            // bounce over an empty queue at the very end.
-            if (poll && bounce >= 4 && bounce < bound) {
-                const int slot = (int) (bounce & 1u);
-                MSK_CUDA_CHECK(cudaMemcpyAsync(im.h_poll[slot], pool.ctrl, sizeof(Ctrl), cudaMemcpyDeviceToHost, stream));
-                MSK_CUDA_CHECK(cudaEventRecord(im.poll_ev[slot], stream));
-                if (im.async_poll) {
-                    if (poll_pending) {
-                        MSK_CUDA_CHECK(cudaEventSynchronize(im.poll_ev[slot ^ 1]));
-                        n_est = im.h_poll[slot ^ 1]->n_rays[cur ^ 1]; // queue the bounce just enqueued ran over
-                        if (im.debug_bounces) fprintf(stderr, "[msk] bounce %u ran over %u rays\n", bounce - 1, n_est);
-                        if (n_est == 0) break;
-                    }
-                    poll_pending = true;
-                } else {
-                    MSK_CUDA_CHECK(cudaEventSynchronize(im.poll_ev[slot]));
-                    n_est = im.h_poll[slot]->n_rays[cur];
-                    if (n_est == 0) break;
-                }
-                // queues only shrink: once the last polled length is below the threshold, one k_tail launch runs
-                // every surviving path of the current queue to completion instead of ~5 launches per further bounce
-                if (use_tail && n_est <= im.tail_threshold) {
-                    if (rd.integrator == MSK_INTEGRATOR_VOLPATH) MSK_STAGE(ST_TAIL, (k_tail<false, true><<<pb, 128, 0, stream>>>(sc, pool, bp, cur)));
-                    else MSK_STAGE(ST_TAIL, (k_tail<false, false><<<pb, 128, 0, stream>>>(sc, pool, bp, cur)));
-                    k_end_tail<<<1, 1, 0, stream>>>(pool.ctrl, cur);
-                    launches++;
-                    tail_used = true;
-                    break;
-                }
-                if (bounce > 100000) return fail(MSK_ERR_CUDA, "path queue did not drain");
-            }
+        r.poll = bound >= (uint32_t) im.poll_min_depth; // unbounded jobs, and bounded ones deep enough to have a thin tail
+        r.use_tail = im.tail_threshold > 0 && r.poll && !tstats;
+        r.done = bound == 0;
+        return MSK_OK;
+    };
+
+    // one bounce of a lane's batch (or the switch to the tail kernel); sets done once the batch needs no further bounce
+    auto step = [&](int li) -> int {
+        Lane &ln = im.lanes[li];
+        Pool &pool = ln.pool;
+        cudaStream_t stream = ln.stream;
+        Run &r = runs[li];
+        const BatchParams &bp = r.bp;
+        const uint32_t n = r.n;
+        const int cur = r.cur;
+        const uint32_t bounce = r.bounce;
+        const uint32_t *perm = nullptr;
+        if (im.ray_sort && bounce >= 1 && r.n_est >= (1u << 18)) { // the reordering pass is timed with the material sort
+            MSK_STAGE(ST_SORT, (k_ray_keys<<<(r.n_est + 255) / 256, 256, 0, stream>>>(sc, pool, cur, r.n_est, pool.rs_keys[0], pool.rs_vals[0])));
+            size_t tmp_bytes = im.rs_tmp_bytes;
+            if (stage_begin(ST_SORT)) return MSK_ERR_CUDA;
+            MSK_CUDA_CHECK(cub::DeviceRadixSort::SortPairs(im.rs_tmp, tmp_bytes, pool.rs_keys[0], pool.rs_keys[1], pool.rs_vals[0], pool.rs_vals[1], (int) r.n_est, 0, 27, stream));
+            if (stage_end()) return MSK_ERR_CUDA;
+            perm = pool.rs_vals[1];
         }
-        max_bounces = std::max(max_bounces, bounce);
+        const int tiny_scene = sc.nnodes <= im.static_nodes;
+        if (tstats) MSK_STAGE(ST_INTERSECT, (k_intersect<true><<<pb, 128, 0, stream>>>(sc, pool, cur, bounce == 0 || tiny_scene, perm)));
+        else MSK_STAGE(ST_INTERSECT, (k_intersect<false><<<pb, 128, 0, stream>>>(sc, pool, cur, bounce == 0 || tiny_scene, perm)));
+        // the AOV integrator shares the primary hit with the nested path tracer (the reference intersects twice)
+        if (aov && bounce == 0) MSK_STAGE(ST_FILM, (k_aov_capture<<<(n + 255) / 256, 256, 0, stream>>>(sc, pool, bp, plan)));
+        if (!MSK_SORT_IN_COMMIT) MSK_STAGE(ST_SORT, (k_sort<<<im.sm_count * 4, kSortThreads, 0, stream>>>(sc, pool, cur)));
+        if (rd.integrator == MSK_INTEGRATOR_VOLPATH) {
+            MSK_STAGE(ST_SHADE, (k_shade_vol<<<pb, 128, 0, stream>>>(sc, pool, bp, cur)));
+        } else if (im.spec_shade && r.n_est >= im.spec_min) {
+            const uint32_t keys = 1u | (sc.bsdf_type_mask << 1);
+#define MSK_SHADE_KEY(K) if (keys & (1u << K)) MSK_STAGE(ST_SHADE, (k_shade<K><<<pb, 128, 0, stream>>>(sc, pool, bp, cur)))
+            MSK_SHADE_KEY(0); MSK_SHADE_KEY(1); MSK_SHADE_KEY(2); MSK_SHADE_KEY(3); MSK_SHADE_KEY(4); MSK_SHADE_KEY(5);
+#undef MSK_SHADE_KEY
+            static_assert(kNumKeys == 6, "one specialised k_shade launch per key");
+        } else {
+            MSK_STAGE(ST_SHADE, (k_shade<-1><<<pb, 128, 0, stream>>>(sc, pool, bp, cur)));
+        }
+        const int sh_coherent = (int) bounce < im.shadow_static_bounces || tiny_scene;
+        if (tstats) MSK_STAGE(ST_SHADOW, (k_shadow<true><<<pb, 128, 0, stream>>>(sc, pool, sh_coherent)));
+        else MSK_STAGE(ST_SHADOW, (k_shadow<false><<<pb, 128, 0, stream>>>(sc, pool, sh_coherent)));
+        k_end_bounce<<<1, 1, 0, stream>>>(pool.ctrl, cur);
+        launches++;
+        r.cur ^= 1;
+        r.bounce++;
+        if (r.bounce >= bound) { r.done = true; return MSK_OK; }
+        // unbounded paths (Russian roulette only): poll the queue length once it is likely short.  The poll of
+        // bounce b is read after bounce b+1 has been enqueued, so the stream never drains; the price is one
+        // bounce over an empty queue at the very end.
+        if (r.poll && r.bounce >= 4) {
+            const int slot = (int) (r.bounce & 1u);
+            MSK_CUDA_CHECK(cudaMemcpyAsync(ln.h_poll[slot], pool.ctrl, sizeof(Ctrl), cudaMemcpyDeviceToHost, stream));
+            MSK_CUDA_CHECK(cudaEventRecord(ln.poll_ev[slot], stream));
+            if (im.async_poll) {
+                if (r.poll_pending) {
+                    MSK_CUDA_CHECK(cudaEventSynchronize(ln.poll_ev[slot ^ 1]));
+                    r.n_est = ln.h_poll[slot ^ 1]->n_rays[r.cur ^ 1]; // queue the bounce just enqueued ran over
+                    if (im.debug_bounces) fprintf(stderr, "[msk] bounce %u ran over %u rays\n", r.bounce - 1, r.n_est);
+                    if (r.n_est == 0) { r.done = true; return MSK_OK; }
+                }
+                r.poll_pending = true;
+            } else {
+                MSK_CUDA_CHECK(cudaEventSynchronize(ln.poll_ev[slot]));
+                r.n_est = ln.h_poll[slot]->n_rays[r.cur];
+                if (r.n_est == 0) { r.done = true; return MSK_OK; }
+            }
+            // queues only shrink: once the last polled length is below the threshold, one k_tail launch runs
+            // every surviving path of the current queue to completion instead of ~5 launches per further bounce
+            if (r.use_tail && r.n_est <= im.tail_threshold) {
+                if (rd.integrator == MSK_INTEGRATOR_VOLPATH) MSK_STAGE(ST_TAIL, (k_tail<false, true><<<pb, 128, 0, stream>>>(sc, pool, bp, r.cur)));
+                else MSK_STAGE(ST_TAIL, (k_tail<false, false><<<pb, 128, 0, stream>>>(sc, pool, bp, r.cur)));
+                k_end_tail<<<1, 1, 0, stream>>>(pool.ctrl, r.cur);
+                launches++;
+                tail_used = true;
+                r.done = true;
+                return MSK_OK;
+            }
+            if (r.bounce > 100000) return fail(MSK_ERR_CUDA, "path queue did not drain");
+        }
+        return MSK_OK;
+    };
+
+    // film accumulation of a finished batch, after the previous batch's (prev_lane < 0: the first batch of the job)
+    auto finish = [&](int li, int prev_lane) -> int {
+        Lane &ln = im.lanes[li];
+        Pool &pool = ln.pool;
+        cudaStream_t stream = ln.stream;
+        Run &r = runs[li];
+        const BatchParams &bp = r.bp;
+        const uint32_t n = r.n;
+        max_bounces = std::max(max_bounces, r.bounce);
         MSK_STAGE(ST_FILM, (k_film_records<<<(n + 255) / 256, 256, 0, stream>>>(sc, pool, bp, plan.rgba_channel)));
+        if (prev_lane >= 0 && prev_lane != li) MSK_CUDA_CHECK(cudaStreamWaitEvent(stream, im.lanes[prev_lane].film_done, 0));
         dim3 fg((W + kFilmTileX - 1) / kFilmTileX, (H + kFilmTileY - 1) / kFilmTileY), fb(kFilmTileX, kFilmTileY);
         if ((int) std::ceil(sc.cam.filter_radius - 0.5f) <= kFilmMaxBorder)
             MSK_STAGE(ST_FILM, (k_film_gather_tiled<<<fg, fb, 0, stream>>>(sc, pool, bp, d_film, H, stride)));
         else
             MSK_STAGE(ST_FILM, (k_film_gather<<<fg, fb, 0, stream>>>(sc, pool, bp, d_film, H, stride)));
         if (plan.nch) MSK_STAGE(ST_FILM, (k_film_gather_aov<<<fg, fb, 0, stream>>>(sc, pool, bp, d_film, H, stride, plan.nch)));
+        if (nlanes > 1) MSK_CUDA_CHECK(cudaEventRecord(ln.film_done, stream));
         batches++;
-    }
-    return MSK_OK;
+        r.active = false;
+        return MSK_OK;
+    };
+
+    // every launch of the job (replayed from a CUDA graph when the sequence is fixed, see above)
+    auto enqueue = [&]() -> int {
+        if (rd.clear_film) MSK_CUDA_CHECK(cudaMemsetAsync(d_film, 0, (size_t) npix * stride * sizeof(float), stream0));
+        if (nlanes > 1) { // the other lanes start after whatever precedes this job on the caller's stream
+            MSK_CUDA_CHECK(cudaEventRecord(im.fork_ev, stream0));
+            for (int l = 1; l < nlanes; ++l) MSK_CUDA_CHECK(cudaStreamWaitEvent(im.lanes[l].stream, im.fork_ev, 0));
+        }
+        for (int l = 0; l < nlanes; ++l)
+            MSK_CUDA_CHECK(cudaMemsetAsync(&im.lanes[l].pool.ctrl->total_closest, 0, 10 * sizeof(unsigned long long), im.lanes[l].stream));
+        uint32_t next_s0 = rd.sample_begin;
+        uint64_t next_index = 0, next_finish = 0;
+        int last_finished_lane = -1;
+        for (;;) {
+            bool any = false;
+            for (int l = 0; l < nlanes; ++l) {
+                Run &r = runs[l];
+                if (!r.active && next_s0 < rd.sample_end) {
+                    if ((rc = start(l, next_index++, next_s0))) return rc;
+                    next_s0 += per_batch;
+                }
+                if (!r.active) continue;
+                any = true;
+                if (!r.done && (rc = step(l))) return rc;
+                if (r.done && r.index == next_finish) { // the film accumulates its batches in order
+                    if ((rc = finish(l, last_finished_lane))) return rc;
+                    last_finished_lane = l;
+                    next_finish++;
+                }
+            }
+            if (!any) break;
+        }
+        for (int l = 1; l < nlanes; ++l) { // join: everything of the job precedes what follows on the caller's stream
+            MSK_CUDA_CHECK(cudaEventRecord(im.lanes[l].film_done, im.lanes[l].stream));
+            MSK_CUDA_CHECK(cudaStreamWaitEvent(stream0, im.lanes[l].film_done, 0));
+        }
+        return MSK_OK;
     };
 #undef MSK_STAGE
-    // A bounded-depth job below the polling depth is a FIXED sequence of launches (queue lengths live on the device): C1 is
-    // 34 launches of 5-90 us each, and the host-side launch cost and the gaps between them were ~7 % of its 1 ms step.  The
-    // sequence is captured once into a CUDA graph and replayed while nothing it depends on changes (scene pointers and
-    // parameters, the render description, the film pointer, the pool); anything else runs launch by launch.
-    const uint32_t bound_all = !trace_paths ? 0u : (rd.max_depth > 0 ? (uint32_t) rd.max_depth : (rd.max_depth == 0 ? 0u : 0xffffffffu));
-    const uint64_t nbatches = nsamples ? ((uint64_t) nsamples + per_batch - 1) / per_batch : 0;
-    const bool graphable = im.use_graph && !timers && !tstats && !im.debug_bounces && bound_all < (uint32_t) im.poll_min_depth && nbatches * (6ull * bound_all + 8) <= 1024;
     if (graphable) {
         std::vector<unsigned char> key(sizeof(DScene) + sizeof(MskRenderDesc) + sizeof(float *) + sizeof(AovPlan) + sizeof(int));
         unsigned char *k = key.data();
@@ -1489,11 +1702,11 @@ int Renderer::render(cudaStream_t stream, const DScene &sc, const MskRenderDesc 
         const int has_aov = aov != nullptr;
         memcpy(k, &has_aov, sizeof(int));
         if (!im.graph_exec || key != im.graph_key) {
-            if (im.graph_exec) { cudaGraphExecDestroy(im.graph_exec); im.graph_exec = nullptr; im.graph_key.clear(); }
+            im.drop_graph();
             cudaGraph_t graph = nullptr;
-            MSK_CUDA_CHECK(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
+            MSK_CUDA_CHECK(cudaStreamBeginCapture(stream0, cudaStreamCaptureModeThreadLocal));
             rc = enqueue();
-            cudaError_t ce = cudaStreamEndCapture(stream, &graph); // always end the capture, also after a failed enqueue
+            cudaError_t ce = cudaStreamEndCapture(stream0, &graph); // always end the capture, also after a failed enqueue
             if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
             if (ce != cudaSuccess) return cuda_fail(ce, "cudaStreamEndCapture", __FILE__, __LINE__);
             ce = cudaGraphInstantiate(&im.graph_exec, graph, 0);
@@ -1502,28 +1715,35 @@ int Renderer::render(cudaStream_t stream, const DScene &sc, const MskRenderDesc 
             im.graph_key = key; im.graph_launches = launches; im.graph_bounces = max_bounces; im.graph_batches = batches; im.graph_extra_closest = extra_closest;
         }
         launches = im.graph_launches; max_bounces = im.graph_bounces; batches = im.graph_batches; extra_closest = im.graph_extra_closest;
-        MSK_CUDA_CHECK(cudaEventRecord(im.ev[0], stream));
-        MSK_CUDA_CHECK(cudaGraphLaunch(im.graph_exec, stream));
+        MSK_CUDA_CHECK(cudaEventRecord(im.ev[0], stream0));
+        MSK_CUDA_CHECK(cudaGraphLaunch(im.graph_exec, stream0));
     } else {
-        MSK_CUDA_CHECK(cudaEventRecord(im.ev[0], stream));
+        MSK_CUDA_CHECK(cudaEventRecord(im.ev[0], stream0));
         if ((rc = enqueue())) return rc;
     }
-    MSK_CUDA_CHECK(cudaEventRecord(im.ev[1], stream));
+    MSK_CUDA_CHECK(cudaEventRecord(im.ev[1], stream0));
     MSK_CUDA_CHECK(cudaGetLastError());
     if (stats) {
-        MSK_CUDA_CHECK(cudaMemcpyAsync(im.h_ctrl, pool.ctrl, sizeof(Ctrl), cudaMemcpyDeviceToHost, stream));
-        MSK_CUDA_CHECK(cudaStreamSynchronize(stream));
+        for (int l = 0; l < nlanes; ++l) // (after the join: every lane's counters are final in stream0's order)
+            MSK_CUDA_CHECK(cudaMemcpyAsync(im.lanes[l].h_ctrl, im.lanes[l].pool.ctrl, sizeof(Ctrl), cudaMemcpyDeviceToHost, stream0));
+        MSK_CUDA_CHECK(cudaStreamSynchronize(stream0));
         *stats = MskStats{};
         stats->paths = (uint64_t) npix * nsamples;
-        stats->rays_closest = im.h_ctrl->total_closest + extra_closest;
-        stats->rays_shadow = im.h_ctrl->total_shadow;
-        stats->shaded_vertices = im.h_ctrl->shaded;
-        stats->nodes_closest = im.h_ctrl->nodes_closest; stats->tris_closest = im.h_ctrl->tris_closest;
-        stats->nodes_shadow = im.h_ctrl->nodes_shadow; stats->tris_shadow = im.h_ctrl->tris_shadow;
+        stats->rays_closest = extra_closest;
+        uint64_t tail_depth = 0;
+        for (int l = 0; l < nlanes; ++l) {
+            const Ctrl &hc = *im.lanes[l].h_ctrl;
+            stats->rays_closest += hc.total_closest;
+            stats->rays_shadow += hc.total_shadow;
+            stats->shaded_vertices += hc.shaded;
+            stats->nodes_closest += hc.nodes_closest; stats->tris_closest += hc.tris_closest;
+            stats->nodes_shadow += hc.nodes_shadow; stats->tris_shadow += hc.tris_shadow;
+            stats->tail_rays_closest += hc.tail_closest; stats->tail_rays_shadow += hc.tail_shadow;
+            tail_depth = std::max<uint64_t>(tail_depth, hc.tail_depth);
+        }
         stats->kernel_launches = launches;
-        stats->bounces = tail_used ? std::max(max_bounces, (uint32_t) im.h_ctrl->tail_depth) : max_bounces;
+        stats->bounces = tail_used ? std::max(max_bounces, (uint32_t) tail_depth) : max_bounces;
         stats->batches = batches;
-        stats->tail_rays_closest = im.h_ctrl->tail_closest; stats->tail_rays_shadow = im.h_ctrl->tail_shadow;
         cudaEventElapsedTime(&stats->ms_render, im.ev[0], im.ev[1]);
         if (timers) {
             float acc[ST_COUNT] = {};

@@ -21,7 +21,7 @@ public:
     int occluded(cudaStream_t stream, const DScene &sc, const MskRay *d_rays, uint8_t *d_occ, size_t n);
 
 private:
-    int ensure_pool(uint32_t capacity);
+    int ensure_pool(uint32_t capacity, int count);
     struct Impl;
     Impl *impl_;
 };

@@ -134,7 +134,7 @@ __device__ __forceinline__ float nz(float d) { // keep reciprocal directions fin
 struct Accel {
     const float4 *nodes, *tris;
     uint32_t k47; // 0x47000000, read from a kernel parameter so that ptxas cannot fold it (see qfloat)
-    uint32_t lut; // shared-memory address of the octant permutation table (perm_lut_init)
+    const uint8_t *lut; // the octant permutation table in shared memory (perm_lut_init)
 };
 
 // Byte J of q as the float 32768 + b, built with ONE byte-permute on the ALU pipe: the byte lands in bits
@@ -162,10 +162,10 @@ __device__ __forceinline__ uint32_t perm_byte(uint32_t h, uint32_t o) {
     if (o & 4u) h = ((h & 0x0fu) << 4) | (h >> 4);
     return h;
 }
-__device__ __forceinline__ uint32_t perm_lut_init(uint8_t *lut) { // call from every thread of the block
+__device__ __forceinline__ const uint8_t *perm_lut_init(uint8_t *lut) { // call from every thread of the block
     for (uint32_t i = threadIdx.x; i < (uint32_t) kPermLutBytes; i += blockDim.x) lut[i] = (uint8_t) perm_byte(i & 0xffu, i >> 8);
     __syncthreads();
-    return (uint32_t) __cvta_generic_to_shared(lut);
+    return lut;
 }
 
 // Traversal stack: the first MSK_SMEM_STACK entries of every lane live in shared memory (entry k of the block's
@@ -174,22 +174,22 @@ __device__ __forceinline__ uint32_t perm_lut_init(uint8_t *lut) { // call from e
 constexpr int kSmemStack = MSK_SMEM_STACK;
 constexpr int kTravThreads = 128; // block size of every kernel that traverses
 constexpr int kLocalStack = kStackSize - kSmemStack;
+// (Plain C++ accesses to the __shared__ arrays: the first version took their addresses with __cvta_generic_to_shared for
+// inline ld/st.shared, and ptxas re-materialised that address -- S2UR SR_CgaCtaId, UMOV, UIADD3, ULEA, LEA -- at every
+// use instead of holding a register: 13 warp instructions per iteration of the lockstep loop, 2.7 % of the kernel,
+// profiles/r02d_ncu_k_intersect.txt.)
 struct TravStack {
     uint2 *local;  // this lane's local-memory entries (kLocalStack of them)
-    uint32_t smem; // shared address of this lane's entry 0
+    uint2 *shared; // this lane's entry 0 in shared memory
     __device__ __forceinline__ TravStack(uint2 *local_entries, uint2 *shared_entries)
-        : local(local_entries), smem(kSmemStack ? (uint32_t) __cvta_generic_to_shared(shared_entries + threadIdx.x) : 0u) {}
+        : local(local_entries), shared(shared_entries + threadIdx.x) {}
     __device__ __forceinline__ void store(int i, uint2 v) {
-        if (kSmemStack && i < kSmemStack)
-            asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(smem + (uint32_t) i * (kTravThreads * 8u)), "r"(v.x), "r"(v.y) : "memory");
+        if (kSmemStack && i < kSmemStack) shared[i * kTravThreads] = v;
         else local[i - kSmemStack] = v;
     }
     __device__ __forceinline__ uint2 load(int i) const {
-        uint2 v;
-        if (kSmemStack && i < kSmemStack)
-            asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(smem + (uint32_t) i * (kTravThreads * 8u)) : "memory");
-        else v = local[i - kSmemStack];
-        return v;
+        if (kSmemStack && i < kSmemStack) return shared[i * kTravThreads];
+        return local[i - kSmemStack];
     }
 };
 #define MSK_TRAV_LOCAL_STACK uint2 msk_local_stack[msk::kLocalStack > 0 ? msk::kLocalStack : 1]
@@ -296,7 +296,7 @@ __device__ __forceinline__ void node_step(const Accel &ac, Traversal &s, TravSta
     hitmask &= __float_as_uint(n1.z); // valid: imask << 24 | bit 3j + k for triangle k of the leaf in slot j
     uint32_t inner;
 #if MSK_PERM_LUT
-    asm("ld.shared.u8 %0, [%1];" : "=r"(inner) : "r"(ac.lut + (s.octinv << 8) + (hitmask >> 24)));
+    inner = ac.lut[(s.octinv << 8) + (hitmask >> 24)];
 #else
     inner = perm_byte(hitmask >> 24, s.octinv);
 #endif

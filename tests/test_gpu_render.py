@@ -362,6 +362,48 @@ def test_tiled_path_enumeration_is_bit_identical(monkeypatch):
     np.testing.assert_array_equal(aov_t, aov_l)
 
 
+@pytest.mark.parametrize("spp", [4, 12, 32])
+def test_samples_per_warp_enumeration_is_bit_identical(monkeypatch, spp):
+    """A warp holds up to 32 consecutive samples of a compact pixel group (slot_decode): 1x1 pixel x 32 samples down to
+    8x4 pixels x 1 sample, by what divides the batch's sample count (12 spp -> 4 samples of 4x2 pixels).  Every setting,
+    and the sample-major round-1 order (0), must give the same film and AOV bits."""
+    sd = scenes.cbox(64, 48)
+    rd = capi.render_desc(spp=spp, max_depth=4)
+    types = [capi.AOV_DEPTH, capi.AOV_UV, capi.AOV_INTEGRATOR_RGBA]
+    films = []
+    for spw in ["0", "1", "2", "8", "32"]:
+        monkeypatch.setenv("MSK_SAMPLES_PER_WARP", spw)
+        with capi.Context(0) as ctx, capi.Scene(ctx, sd) as sc:
+            films.append((sc.render(rd)[0], sc.render_aov(rd, types)[0]))
+    assert films[0][0].any()
+    for f, a in films[1:]:
+        np.testing.assert_array_equal(f, films[0][0])
+        np.testing.assert_array_equal(a, films[0][1])
+
+
+@pytest.mark.parametrize("integrator,max_depth", [("path", -1), ("path", 3), ("volpath", -1)])
+def test_batches_in_flight_are_bit_identical(monkeypatch, integrator, max_depth):
+    """Up to four batches are in flight at once, each on its own stream and path pool (Renderer::render); the film
+    kernels of consecutive batches are chained by events, so for a fixed batch partition the film and the ray counters
+    must not depend on how many lanes run it -- polled unbounded jobs (tail kernel included), bounded ones, volpath."""
+    sd = scenes.fog(64, 48, n=8) if integrator == "volpath" else scenes.cbox(64, 48)
+    rd = capi.render_desc(spp=20, max_depth=max_depth, rr_depth=3, integrator=integrator, paths_per_batch=64 * 48 * 4)
+    out = []
+    for lanes in ["1", "2", "3", "4"]:
+        monkeypatch.setenv("MSK_INFLIGHT", lanes)
+        monkeypatch.setenv("MSK_GRAPH", "0")
+        with capi.Context(0) as ctx, capi.Scene(ctx, sd) as sc:
+            film, st = sc.render(rd)
+            film2, _ = sc.render(rd)
+            np.testing.assert_array_equal(film, film2)
+            out.append((film, st))
+    assert out[0][1].batches == 5 and out[0][0].any()
+    for film, st in out[1:]:
+        np.testing.assert_array_equal(film, out[0][0])
+        assert (st.rays_closest, st.rays_shadow, st.shaded_vertices, st.batches) == \
+            (out[0][1].rays_closest, out[0][1].rays_shadow, out[0][1].shaded_vertices, out[0][1].batches)
+
+
 def test_c2_full_size_properties(gpu_ctx):
     """BASELINE configs[1] at its full size (512x512, 64 spp, unbounded depth): size-independent properties instead of a
     full oracle render -- bit-determinism run to run, invariance under a partition of the sample range (what multi-GPU
