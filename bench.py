@@ -19,6 +19,8 @@ Keys beyond the base contract:
   roofline   the dominant kernel's algorithmic bytes / its CUDA-event time vs the measured HBM copy peak
   cpu_baseline  oracle (CPU restatement of the reference, all host threads) on a bounded sample of the job
   --impl reference   times that CPU restatement alone (the reference as a whole cannot be built here: DESIGN.md);
+                     --ref-kind fast (default) is the restatement compiled for speed on this host (-O3 -march=native, FMA),
+                     --ref-kind port the parity checker's own build (-O2, no FMA),
                      --ref-kind reference --workload c1 times the reference's own compiled render loop from oracle/_ref
 """
 from __future__ import annotations
@@ -124,6 +126,20 @@ class ClockSampler:
                 "power_w_max": max(pw) if pw else None, "reasons": reasons, "samples": len(rows)}
 
 
+def cpu_arm_build(args) -> str:
+    """Select the build of the CPU restatement the CPU legs time (before its first use in this process) and describe it.
+    --ref-kind fast (default): oracle/Makefile `fast` -- the same source compiled for speed on this host; port: the
+    parity checker's own conservative build."""
+    from oracle import pyoracle
+    if getattr(args, "ref_kind", "fast") == "fast" and pyoracle.flavour() != "fast":
+        try:
+            pyoracle.select_fast()
+        except AssertionError:
+            pass
+    return {"fast": "speed build of the restatement (oracle/Makefile `fast`: -O3 -march=native -funroll-loops, FMA contraction on), compiled on this host",
+            "checker": "the parity checker's own build (-O2 -march=x86-64-v3, no FMA contraction)"}[pyoracle.flavour()]
+
+
 def oracle_sample(sd, rd_kwargs, budget_s: float, nthreads: int = 0):
     """Time the CPU oracle on a bounded sample: the first `s` of the job's samples per pixel, s chosen from a
     1-sample calibration so the run takes about `budget_s` seconds.  Returns (paths/s, Mrays/s, info)."""
@@ -162,6 +178,7 @@ def run_reference(args, rank: int):
     sd, rdk, wname = workload(args.workload, 1)
     if args.ref_kind == "reference":
         return run_reference_code(args, sd, rdk, wname)
+    build = cpu_arm_build(args)
     osc = pyoracle.OracleScene(sd)
     spp = rdk["spp"]
     osc.render(capi.render_desc(sample_begin=0, sample_end=1, **rdk))  # builds the oracle's BVH lazily
@@ -184,7 +201,7 @@ def run_reference(args, rank: int):
         "config": {"workload": wname, "sample_per_step": sample},
         "mrays_per_s": rays / secs / 1e6,
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": int(st.threads), "kind": "port", "sample": sample,
-                         "cpu": cpu_model(),
+                         "cpu": cpu_model(), "build": build,
                          "note": "CPU restatement of misaki's path (own SAH BVH + Moeller-Trumbore, std::thread over "
                                  "32x32 tiles); NOT TBB+Embree, which cannot be built in this image"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -386,6 +403,7 @@ def run_c5_reference(args, rank: int):
         return
     sd, prim = c5_inputs(args.c5_res, 0)
     from oracle import pyoracle
+    build = cpu_arm_build(args)
     osc = pyoracle.OracleScene(sd)
     ph = osc.intersect(np.ascontiguousarray(prim[:: max(1, len(prim) // 400000)]))
     from workloads import scenes
@@ -398,7 +416,7 @@ def run_c5_reference(args, rank: int):
     line = {"impl": "reference", "metric": "Mrays/s", "value": v, "unit": "Mrays/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": inf["seconds"] * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": C5_NAME, "sample_per_step": sample}, "detail": inf["detail"],
-            "cpu_baseline": {"value": v, "unit": "Mrays/s", "cores": inf["threads"], "kind": "port", "sample": sample, "cpu": cpu_model(),
+            "cpu_baseline": {"value": v, "unit": "Mrays/s", "cores": inf["threads"], "kind": "port", "sample": sample, "cpu": cpu_model(), "build": build,
                              "note": "oracle SAH BVH2 + Moeller-Trumbore, std::thread; NOT Embree"},
             "e2e": {"value": v, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
@@ -514,6 +532,7 @@ def c5_case(h: Harness, args, steps: int, warmup: int, want_e2e: bool, want_cpu:
         if roofline["issue"]["frac"] is not None:
             roofline["issue"]["thread_inst_per_ray"] = roofline["issue"]["threads_per_inst"] * roofline["issue"]["warp_inst_per_step"] / n_top
         if world == 1 and want_cpu:
+            cpu_arm_build(args)
             v, inf = c5_oracle_sample(sd, {"primary": prim, "secondary": sec}, args.cpu_budget)
             cpu = {"value": v, "unit": "Mrays/s", "cores": inf["threads"], "kind": "port", "cpu": cpu_model(), "detail": inf["detail"],
                    "sample": f"strided sample of {inf['rays'] // 4} rays of each set, closest + any hit ({inf['seconds']:.1f} s)",
@@ -702,12 +721,13 @@ def render_case(h: Harness, args, wl: str, steps: int, warmup: int, scaling: str
     # ---- CPU baseline (rank 0, N = 1 only): oracle on a bounded sample
     cpu = None
     if rank == 0 and world == 1 and want_cpu:
+        build = cpu_arm_build(args)
         v, mr, inf = oracle_sample(sd, rdk, args.cpu_budget)
-        cpu = {"value": v, "unit": UNIT, "cores": inf["threads"], "kind": "port", "mrays_per_s": mr, "cpu": cpu_model(),
+        cpu = {"value": v, "unit": UNIT, "cores": inf["threads"], "kind": "port", "mrays_per_s": mr, "cpu": cpu_model(), "build": build,
                "sample": f"first {inf['samples']} of {rdk['spp']} samples per pixel, all {npix} pixels, same seeds "
                          f"({inf['paths']} paths, {inf['seconds']:.1f} s)",
-               "note": "oracle/ CPU restatement (own SAH BVH + Moeller-Trumbore, std::thread tiles; built -O2 without FMA contraction, it is the parity "
-                       "checker); not TBB+Embree.  The rough-conductor / dielectric glue and the camera of this restatement are unpinned (DESIGN.md)"}
+               "note": "oracle/ CPU restatement (own SAH BVH + Moeller-Trumbore, std::thread tiles); not TBB+Embree.  The rough-conductor / "
+                       "dielectric sample/eval/pdf glue of this restatement is unpinned (the reference's plugins do not compile, DESIGN.md); its components are"}
 
     out = {"metric": METRIC, "value": value, "unit": UNIT, "ms_per_step": ms_step, "steps": steps, "warmup": warmup, "scaling": scaling,
            "config": {"workload": wname, "spp_per_gpu": spp_rank, "job_spp": job["spp"], "partition": "sample ranges + 1 film reduce/step",
@@ -806,8 +826,9 @@ def main():
     ap.add_argument("--spp", type=int, default=0, help="override samples per pixel per GPU (development only)")
     ap.add_argument("--cpu-budget", type=float, default=15.0, help="seconds of CPU work for cpu_baseline")
     ap.add_argument("--ref-budget", type=float, default=150.0, help="seconds for the whole --impl reference run")
-    ap.add_argument("--ref-kind", default="port", choices=["port", "reference"],
-                    help="--impl reference: the oracle port (every workload) or, for C1, the reference's own compiled code from oracle/_ref")
+    ap.add_argument("--ref-kind", default="fast", choices=["fast", "port", "reference"],
+                    help="build of the CPU arm (--impl reference and cpu_baseline): fast = the oracle restatement compiled for speed on this host (default), "
+                         "port = the parity checker's own build, reference = (C1 only) the reference's own compiled code from oracle/_ref")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-sub", action="store_true", help="skip the sub-results (C1 / C3 / C5 and the strong-scaling C4 / C1 jobs) of the default run")
     ap.add_argument("--one-step", action="store_true", help="run exactly one step of the workload and exit (for ncu passes)")

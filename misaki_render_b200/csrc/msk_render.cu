@@ -146,7 +146,10 @@ __global__ void k_end_bounce(Ctrl *c, int cur) {
 
 // ---------------------------------------------------------------------------------------
 // render_sample: integrator.cpp:103-126 (first half), perspective.cpp:22-41
-__global__ void __launch_bounds__(256) k_raygen(const __grid_constant__ DScene sc, Pool pool, BatchParams bp) {
+// write_state == 0: the first shade pass knows a camera path's throughput (1) and (eta, pdfs) = (1, 0, 0) without reading
+// them (k_shade's `first`), so they are not written either: 32 of the 112 bytes per camera sample, and 32 of the ~280 a
+// first-bounce vertex moves.
+__global__ void __launch_bounds__(256) k_raygen(const __grid_constant__ DScene sc, Pool pool, BatchParams bp, int write_state) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     uint32_t n = bp.npix * bp.ns;
     if (i >= n) return;
@@ -166,10 +169,12 @@ __global__ void __launch_bounds__(256) k_raygen(const __grid_constant__ DScene s
     float4 *rp = reinterpret_cast<float4 *>(pool.rays[0] + i);
     rp[0] = make_float4(o.x, o.y, o.z, mint);
     rp[1] = make_float4(d.x, d.y, d.z, maxt);
-    pool.T[0][i]    = f4(1.f);
     pool.WL[0][i]   = wl;
     pool.MISC[0][i] = make_uint4((uint32_t) rng, (uint32_t) (rng >> 32), i, 1u);
-    pool.AUX[0][i]  = make_float4(1.f, 0.f, 0.f, 0.f);
+    if (write_state) {
+        pool.T[0][i]   = f4(1.f);
+        pool.AUX[0][i] = make_float4(1.f, 0.f, 0.f, 0.f);
+    }
     pool.L[i]       = f4(0.f);
 }
 
@@ -443,7 +448,7 @@ __device__ __forceinline__ void shade_vertex(const DScene &sc, const BatchParams
 }
 
 template <int KEY>
-__global__ void __launch_bounds__(128, shade_min_blocks(KEY)) k_shade(const __grid_constant__ DScene sc, Pool pool, BatchParams bp, int cur) {
+__global__ void __launch_bounds__(128, shade_min_blocks(KEY)) k_shade(const __grid_constant__ DScene sc, Pool pool, BatchParams bp, int cur, int first) {
     Ctrl *c = pool.ctrl;
     const int nxt = cur ^ 1;
     constexpr int TYPE = KEY > 0 ? KEY - 1 : -1;
@@ -459,9 +464,9 @@ __global__ void __launch_bounds__(128, shade_min_blocks(KEY)) k_shade(const __gr
     // prefetch.global.L2 while the current vertex is shaded -- the stage runs at 25 % occupancy with DRAM at 46 % of peak,
     // profiles/r02d_ncu_k_shade.txt.  C2 shade 2.31 -> 2.41 ms: the extra index load and seven prefetches per vertex cost
     // more issue slots and registers than the L2 hits save.)
-    const uint32_t first = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t tid0 = blockIdx.x * blockDim.x + threadIdx.x;
     for (uint32_t it = 0; it < rounds; ++it) {
-        uint32_t idx = it * stride + first;
+        uint32_t idx = it * stride + tid0;
         bool valid = idx < total;
         bool emit_ray = false, emit_shadow = false;
         MskRay nray, sray;
@@ -478,10 +483,11 @@ __global__ void __launch_bounds__(128, shade_min_blocks(KEY)) k_shade(const __gr
             const uint32_t q = pool.sorted[(size_t) key * pool.capacity + j];
             const float4 hit = pool.hit[q];
             const float4 rd  = reinterpret_cast<const float4 *>(pool.rays[cur] + q)[1];
-            const float4 T = pool.T[cur][q];
+            // (first: the vertices of camera rays -- k_raygen did not write their constant throughput and eta / pdf record)
+            const float4 T = first ? f4(1.f) : pool.T[cur][q];
             const float4 wl = pool.WL[cur][q];
             const uint4 misc = pool.MISC[cur][q];
-            const float4 aux = pool.AUX[cur][q];
+            const float4 aux = first ? make_float4(1.f, 0.f, 0.f, 0.f) : pool.AUX[cur][q];
             path = misc.z;
             VertexOut vo;
             const bool miss = KEY == 0 || (KEY < 0 && key == 0);
@@ -1239,6 +1245,7 @@ struct Renderer::Impl {
     int poll_min_depth = 8;           // MSK_POLL_MIN_DEPTH: jobs with max_depth >= this (or unbounded) poll the queue length from bounce 4 on
     int async_poll = 1;               // MSK_ASYNC_POLL: poll the queue length one bounce late, without draining the stream
     uint32_t static_nodes = 64;       // MSK_STATIC_NODES: scenes with at most this many wide nodes always use the static traversal (every ray does the same few steps: nothing to re-balance)
+    int first_elide = 1;              // MSK_FIRST_ELIDE: camera paths' constant initial state is neither written by k_raygen nor read by the first k_shade
     int use_graph = 1;                // MSK_GRAPH: bounded-depth jobs (a fixed launch sequence) replay a cached CUDA graph
     cudaGraphExec_t graph_exec = nullptr;
     std::vector<unsigned char> graph_key; // everything the captured launches depend on
@@ -1355,6 +1362,7 @@ int Renderer::init(int sm_count) {
     impl_->samples_per_warp = (int) env_u("MSK_SAMPLES_PER_WARP", impl_->samples_per_warp);
     impl_->ray_sort = (int) env_u("MSK_RAY_SORT", impl_->ray_sort);
     impl_->use_graph = (int) env_u("MSK_GRAPH", impl_->use_graph);
+    impl_->first_elide = (int) env_u("MSK_FIRST_ELIDE", impl_->first_elide);
     impl_->static_nodes = (uint32_t) env_u("MSK_STATIC_NODES", impl_->static_nodes);
     impl_->debug_bounces = (int) env_u("MSK_DEBUG_BOUNCES", 0);
     return MSK_OK;
@@ -1506,6 +1514,9 @@ int Renderer::render(cudaStream_t stream0, const DScene &sc, const MskRenderDesc
     };
 #define MSK_STAGE(st, launch) do { int rc__ = stage_begin(st); if (rc__) return rc__; launch; launches++; rc__ = stage_end(); if (rc__) return rc__; } while (0)
 
+    // the path tracer's first shade pass takes the camera paths' initial state as known (k_raygen, k_shade); the volumetric
+    // kernel reads it
+    const bool first_elide = im.first_elide && rd.integrator != MSK_INTEGRATOR_VOLPATH;
     // state of the batch a lane is working on
     struct Run {
         bool active = false, done = false;
@@ -1538,7 +1549,7 @@ int Renderer::render(cudaStream_t stream0, const DScene &sc, const MskRenderDesc
         r.n = n; r.n_est = n; // n_est: upper bound of the current queue length known to the host (queues only shrink)
         k_begin_batch<<<1, 1, 0, stream>>>(pool.ctrl, n);
         launches++;
-        MSK_STAGE(ST_RAYGEN, (k_raygen<<<(n + 255) / 256, 256, 0, stream>>>(sc, pool, bp)));
+        MSK_STAGE(ST_RAYGEN, (k_raygen<<<(n + 255) / 256, 256, 0, stream>>>(sc, pool, bp, first_elide ? 0 : 1)));
         if (aov && bound == 0) { // the AOV integrator's own ray_intersect (aov.cpp:90) when no path bounce runs
             MSK_STAGE(ST_INTERSECT, (k_intersect<false><<<pb, 128, 0, stream>>>(sc, pool, 0, 1, nullptr)));
             MSK_STAGE(ST_FILM, (k_aov_capture<<<(n + 255) / 256, 256, 0, stream>>>(sc, pool, bp, plan)));
@@ -1571,6 +1582,7 @@ int Renderer::render(cudaStream_t stream0, const DScene &sc, const MskRenderDesc
             perm = pool.rs_vals[1];
         }
         const int tiny_scene = sc.nnodes <= im.static_nodes;
+        const int first = first_elide && bounce == 0;
         if (tstats) MSK_STAGE(ST_INTERSECT, (k_intersect<true><<<pb, 128, 0, stream>>>(sc, pool, cur, bounce == 0 || tiny_scene, perm)));
         else MSK_STAGE(ST_INTERSECT, (k_intersect<false><<<pb, 128, 0, stream>>>(sc, pool, cur, bounce == 0 || tiny_scene, perm)));
         // the AOV integrator shares the primary hit with the nested path tracer (the reference intersects twice)
@@ -1580,12 +1592,12 @@ int Renderer::render(cudaStream_t stream0, const DScene &sc, const MskRenderDesc
             MSK_STAGE(ST_SHADE, (k_shade_vol<<<pb, 128, 0, stream>>>(sc, pool, bp, cur)));
         } else if (im.spec_shade && r.n_est >= im.spec_min) {
             const uint32_t keys = 1u | (sc.bsdf_type_mask << 1);
-#define MSK_SHADE_KEY(K) if (keys & (1u << K)) MSK_STAGE(ST_SHADE, (k_shade<K><<<pb, 128, 0, stream>>>(sc, pool, bp, cur)))
+#define MSK_SHADE_KEY(K) if (keys & (1u << K)) MSK_STAGE(ST_SHADE, (k_shade<K><<<pb, 128, 0, stream>>>(sc, pool, bp, cur, first)))
             MSK_SHADE_KEY(0); MSK_SHADE_KEY(1); MSK_SHADE_KEY(2); MSK_SHADE_KEY(3); MSK_SHADE_KEY(4); MSK_SHADE_KEY(5);
 #undef MSK_SHADE_KEY
             static_assert(kNumKeys == 6, "one specialised k_shade launch per key");
         } else {
-            MSK_STAGE(ST_SHADE, (k_shade<-1><<<pb, 128, 0, stream>>>(sc, pool, bp, cur)));
+            MSK_STAGE(ST_SHADE, (k_shade<-1><<<pb, 128, 0, stream>>>(sc, pool, bp, cur, first)));
         }
         const int sh_coherent = (int) bounce < im.shadow_static_bounces || tiny_scene;
         if (tstats) MSK_STAGE(ST_SHADOW, (k_shadow<true><<<pb, 128, 0, stream>>>(sc, pool, sh_coherent)));

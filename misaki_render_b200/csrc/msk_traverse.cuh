@@ -40,6 +40,10 @@ constexpr int kStackSize = 64; // node groups + postponed triangle groups: at mo
 #ifndef MSK_NODE_STEPS
 #define MSK_NODE_STEPS 1
 #endif
+// Lockstep driver: triangles a lane may test per triangle phase.
+#ifndef MSK_TRI_REPS
+#define MSK_TRI_REPS 1
+#endif
 #ifndef MSK_STATIC_MIN_GROUP
 #define MSK_STATIC_MIN_GROUP 4 /* 32 disables the adaptive group size of short static queues */
 #endif
@@ -134,7 +138,7 @@ __device__ __forceinline__ float nz(float d) { // keep reciprocal directions fin
 struct Accel {
     const float4 *nodes, *tris;
     uint32_t k47; // 0x47000000, read from a kernel parameter so that ptxas cannot fold it (see qfloat)
-    const uint8_t *lut; // the octant permutation table in shared memory (perm_lut_init)
+    uint32_t lut; // shared-memory address of the octant permutation table (perm_lut_init), opaque
 };
 
 // Byte J of q as the float 32768 + b, built with ONE byte-permute on the ALU pipe: the byte lands in bits
@@ -156,16 +160,23 @@ template <int J> __device__ __forceinline__ float qfloat(uint32_t q, uint32_t k4
 // slot ^ octinv descending; one LDS replaces a dozen ALU instructions per node visit on the pipe that bounds
 // the kernel.
 constexpr int kPermLutBytes = 8 * 256;
+// A shared-memory address is cheap to re-derive in ptxas's cost model (S2UR SR_CgaCtaId, UMOV, UIADD3, ULEA, LEA), so it
+// re-materialised the table and stack addresses at every use instead of holding two registers: 13 warp instructions per
+// iteration of the lockstep loop, 2.7 % of the kernel (profiles/r02d_ncu_k_intersect.txt).  Passing the value through
+// a self-shuffle (once per kernel) makes it a value ptxas cannot re-derive.
+__device__ __forceinline__ uint32_t opaque(uint32_t v) {
+    return __shfl_sync(0xffffffffu, v, threadIdx.x & 31u);
+}
 __device__ __forceinline__ uint32_t perm_byte(uint32_t h, uint32_t o) {
     if (o & 1u) h = ((h & 0x55u) << 1) | ((h >> 1) & 0x55u);
     if (o & 2u) h = ((h & 0x33u) << 2) | ((h >> 2) & 0x33u);
     if (o & 4u) h = ((h & 0x0fu) << 4) | (h >> 4);
     return h;
 }
-__device__ __forceinline__ const uint8_t *perm_lut_init(uint8_t *lut) { // call from every thread of the block
+__device__ __forceinline__ uint32_t perm_lut_init(uint8_t *lut) { // call from every thread of the block
     for (uint32_t i = threadIdx.x; i < (uint32_t) kPermLutBytes; i += blockDim.x) lut[i] = (uint8_t) perm_byte(i & 0xffu, i >> 8);
     __syncthreads();
-    return lut;
+    return opaque((uint32_t) __cvta_generic_to_shared(lut));
 }
 
 // Traversal stack: the first MSK_SMEM_STACK entries of every lane live in shared memory (entry k of the block's
@@ -174,22 +185,22 @@ __device__ __forceinline__ const uint8_t *perm_lut_init(uint8_t *lut) { // call 
 constexpr int kSmemStack = MSK_SMEM_STACK;
 constexpr int kTravThreads = 128; // block size of every kernel that traverses
 constexpr int kLocalStack = kStackSize - kSmemStack;
-// (Plain C++ accesses to the __shared__ arrays: the first version took their addresses with __cvta_generic_to_shared for
-// inline ld/st.shared, and ptxas re-materialised that address -- S2UR SR_CgaCtaId, UMOV, UIADD3, ULEA, LEA -- at every
-// use instead of holding a register: 13 warp instructions per iteration of the lockstep loop, 2.7 % of the kernel,
-// profiles/r02d_ncu_k_intersect.txt.)
 struct TravStack {
     uint2 *local;  // this lane's local-memory entries (kLocalStack of them)
-    uint2 *shared; // this lane's entry 0 in shared memory
+    uint32_t smem; // shared address of this lane's entry 0 (opaque: held in a register, see above)
     __device__ __forceinline__ TravStack(uint2 *local_entries, uint2 *shared_entries)
-        : local(local_entries), shared(shared_entries + threadIdx.x) {}
+        : local(local_entries), smem(kSmemStack ? opaque((uint32_t) __cvta_generic_to_shared(shared_entries + threadIdx.x)) : 0u) {}
     __device__ __forceinline__ void store(int i, uint2 v) {
-        if (kSmemStack && i < kSmemStack) shared[i * kTravThreads] = v;
+        if (kSmemStack && i < kSmemStack)
+            asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(smem + (uint32_t) i * (kTravThreads * 8u)), "r"(v.x), "r"(v.y) : "memory");
         else local[i - kSmemStack] = v;
     }
     __device__ __forceinline__ uint2 load(int i) const {
-        if (kSmemStack && i < kSmemStack) return shared[i * kTravThreads];
-        return local[i - kSmemStack];
+        uint2 v;
+        if (kSmemStack && i < kSmemStack)
+            asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(smem + (uint32_t) i * (kTravThreads * 8u)) : "memory");
+        else v = local[i - kSmemStack];
+        return v;
     }
 };
 #define MSK_TRAV_LOCAL_STACK uint2 msk_local_stack[msk::kLocalStack > 0 ? msk::kLocalStack : 1]
@@ -296,7 +307,7 @@ __device__ __forceinline__ void node_step(const Accel &ac, Traversal &s, TravSta
     hitmask &= __float_as_uint(n1.z); // valid: imask << 24 | bit 3j + k for triangle k of the leaf in slot j
     uint32_t inner;
 #if MSK_PERM_LUT
-    inner = ac.lut[(s.octinv << 8) + (hitmask >> 24)];
+    asm("ld.shared.u8 %0, [%1];" : "=r"(inner) : "r"(ac.lut + (s.octinv << 8) + (hitmask >> 24)));
 #else
     inner = perm_byte(hitmask >> 24, s.octinv);
 #endif
@@ -505,6 +516,14 @@ __device__ __forceinline__ void trace_queue(const Accel &ac, uint2 *shared_stack
             const bool starved = has_t && s.ngroup.y <= 0x00ffffffu;
             if (__popc(mt) >= kTriThreshold || __any_sync(0xffffffffu, starved && waited >= MSK_TRI_PATIENCE)) {
                 if (has_t && tri_step<STATS>(ac, s) && ANY) { busy = false; have = true; }
+                // A leaf hit usually leaves two or three triangles pending, and a lane with nothing but triangles
+                // left sits out the node phases in between: up to MSK_TRI_REPS triangles per lane and phase.
+#pragma unroll 1
+                for (int rep = 1; rep < MSK_TRI_REPS; ++rep) {
+                    const bool again = busy && s.tgroup.y != 0u;
+                    if (!__any_sync(0xffffffffu, again)) break;
+                    if (again && tri_step<STATS>(ac, s) && ANY) { busy = false; have = true; }
+                }
                 waited = 0;
             } else if (starved) ++waited;
         }

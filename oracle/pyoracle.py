@@ -25,14 +25,37 @@ def build():
 
 
 _lib = None
+_flavour = "checker"
+
+
+def select_fast() -> bool:
+    """bench.py's CPU arm only: use the speed build of the same restatement (oracle/Makefile `fast`: -O3 -march=native,
+    FMA on), compiled here and now because -march=native binds it to this host.  Must be called before the first use
+    of the library in the process; returns False (and keeps the checker build) when the build fails."""
+    global _flavour
+    assert _lib is None, "select_fast() must precede the first use of the oracle"
+    fast = HERE / "_build" / "liboracle_fast.so"
+    try:
+        if fast.exists():
+            fast.unlink()  # a copy built on another host may use instructions this one lacks
+        subprocess.run(["make", "-C", str(HERE), "fast"], check=True, capture_output=True, timeout=300)
+    except (subprocess.SubprocessError, OSError):
+        return False
+    _flavour = "fast"
+    return True
+
+
+def flavour() -> str:
+    return _flavour
 
 
 def lib() -> C.CDLL:
     global _lib
     if _lib is None:
-        if not LIB.exists():
+        path = HERE / "_build" / "liboracle_fast.so" if _flavour == "fast" else LIB
+        if not path.exists():
             build()
-        L = C.CDLL(str(LIB))
+        L = C.CDLL(str(path))
         L.orc_last_error.restype = C.c_char_p
         L.orc_scene_create.argtypes = [C.POINTER(capi.MskSceneDesc), C.POINTER(C.c_void_p)]
         L.orc_scene_destroy.argtypes = [C.c_void_p]
