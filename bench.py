@@ -610,6 +610,7 @@ def render_case(h: Harness, args, wl: str, steps: int, warmup: int, scaling: str
         if collect is not None:
             collect.append(st)
 
+    scene.reserve(rd_rank)  # path pools allocated outside the timed region also when a case runs without warm-up steps
     for _ in range(max(warmup, 0)):
         step(None)
     sampler = ClockSampler(physical_gpu_index(h.local_rank)) if rank == 0 else None

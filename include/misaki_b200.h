@@ -257,6 +257,10 @@ int  msk_gpu_intersect_stats(MskScene *scene, const MskRay *rays, size_t n,
 
 /* film layout: height x width x 5 float32, channels X,Y,Z,A,W (integrator.cpp:39-40) */
 int  msk_gpu_render(MskScene *scene, const MskRenderDesc *rd, float *film_host, MskStats *stats);
+/* Allocates now the path pools a render of `rd` on this scene will use (one per batch in flight), so that the render
+ * itself allocates nothing; optional -- msk_gpu_render* allocate on first use and keep the pools.  The reference has no
+ * counterpart (its per-thread state is the sampler clone and the ImageBlock of integrator.cpp:57-61). */
+int  msk_gpu_render_reserve(MskScene *scene, const MskRenderDesc *rd);
 int  msk_gpu_render_dev(MskScene *scene, const MskRenderDesc *rd, float *d_film, MskStats *stats);
 /* AOV integrator: film layout height x width x (5 + msk_gpu_aov_channels(aov)) float32 = X,Y,Z,A,W followed by
  * the AOV channels, every channel splatted with the reconstruction filter like XYZAW (integrator.cpp:103-126).

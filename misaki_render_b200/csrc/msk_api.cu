@@ -475,6 +475,12 @@ int msk_gpu_intersect_stats(MskScene *s, const MskRay *rays, size_t n, uint32_t 
     return rc;
 }
 
+int msk_gpu_render_reserve(MskScene *s, const MskRenderDesc *rd) {
+    if (!s || !rd) return fail(MSK_ERR_ARG, "null argument");
+    DeviceGuard guard(s->ctx->device);
+    return s->ctx->renderer.reserve(s->d, *rd);
+}
+
 int msk_gpu_render_dev(MskScene *s, const MskRenderDesc *rd, float *d_film, MskStats *stats) {
     if (!s || !rd || !d_film) return fail(MSK_ERR_ARG, "null argument");
     DeviceGuard guard(s->ctx->device);
