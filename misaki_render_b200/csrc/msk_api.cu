@@ -382,6 +382,7 @@ int msk_gpu_scene_create(MskCtx *ctx, const MskSceneDesc *d, MskScene **out) {
     }
     cudaError_t es = cudaStreamSynchronize(ctx->stream);
     if (es != cudaSuccess) return bail(cuda_fail(es, "cudaStreamSynchronize", __FILE__, __LINE__));
+    if (debug_setup) bvh_print_shape(ctx->stream, s->bvh);
     if (debug_setup)
         fprintf(stderr, "[msk] scene_create: %zu tris | validate + CDFs %.2f ms | malloc + upload %.2f ms | BVH %.2f ms host (%.2f ms device) | total %.2f ms\n",
                 ntris, ms_validate, ms_upload, since(t_begin) - ms_validate - ms_upload, s->bvh.ms_build, since(t_begin));

@@ -20,6 +20,9 @@
 
 #include <cub/cub.cuh>
 #include <cfloat>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <vector>
 
 namespace msk {
@@ -285,13 +288,96 @@ __device__ __forceinline__ uint32_t quant_exp(float extent) {
     return min(max(e, 1u), 254u);
 }
 
+// ---- SAH-optimal collapse (Ylitie, Karras, Laine 2017, section 4.1) --------------------------------------------
+// Which binary nodes become the (at most 8) children of a wide node is decided by dynamic programming over the binary
+// tree instead of greedily opening the largest child.  C(n, i) = the cheapest way to represent the subtree of binary
+// node n by at most i roots in its parent's child list, a root being either a LEAF SLOT (<= kMaxLeafTris triangles
+// behind one child box: cost area(n) * triangles * c_prim -- the triangles are tested whenever the box is entered) or a
+// wide INNER node (cost area(n) * c_node + the cheapest distribution of its 8 slots over n's two children):
+//     D(n, j)  = min over 0 < k < j of C(left, k) + C(right, j - k)                      j = 2..8
+//     C(n, 1)  = min(C_leaf(n), area(n) * c_node + D(n, 8))
+//     C(n, i)  = min(D(n, i), C(n, i - 1))                                               i = 2..7
+// (areas are half areas; only ratios matter).  Bottom-up pass k_plan stores C(n, 1..7) and the arg-mins, the top-down
+// collapse reads them back (expand below).  The greedy rule -- open the largest-area candidate while slots remain -- on
+// a uniformly tessellated mesh hands every slot a subtree of equal size, powers of two: 29 % of C2's wide nodes had
+// exactly 4 children (46 % under PLOC, whose 3x lower binary-tree SAH the collapse then wasted;
+// gpurun_out/r02p_bvh_shape.txt).
+struct Plan {
+    float   *cost;  // 7 per internal binary node: C(n, 1..7)
+    uint8_t *split; // 8 per internal binary node: [0] = 1 when C(n, 1) is a leaf slot; [j - 1], j = 2..7 = roots handed to the
+                    // left child in D(n, j), or 0 when j - 1 roots are as cheap; [7] = the left share of D(n, 8)
+};
+
+__global__ void k_set_parents(Bvh2 t, int n) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n - 1) return;
+    t.parent[t.left[i]] = (uint32_t) i; t.parent[t.right[i]] = (uint32_t) i;
+    if (i == 0) t.parent[0] = 0xffffffffu;
+}
+
+__device__ __forceinline__ void plan_costs(const Bvh2 &t, int n, const Plan &pl, uint32_t node, float c_prim, float (&c)[7]) {
+    if (node >= (uint32_t) (n - 1)) { // a single triangle: one leaf slot, however many roots are allowed
+        const float a = half_area(__ldcg(&t.lo[node]), __ldcg(&t.hi[node])) * c_prim;
+#pragma unroll
+        for (int i = 0; i < 7; ++i) c[i] = a;
+    } else {
+#pragma unroll
+        for (int i = 0; i < 7; ++i) c[i] = __ldcg(pl.cost + 7 * (size_t) node + i);
+    }
+}
+
+__global__ void k_plan(Bvh2 t, int n, Plan pl, float c_node, float c_prim) {
+    int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n || n == 1) return;
+    uint32_t p = t.parent[n - 1 + j];
+    while (p != 0xffffffffu) {
+        __threadfence();
+        if (atomicAdd(&t.flags[p], 1u) == 0) return; // first arrival: the sibling will finish this node
+        float cl[7], cr[7];
+        plan_costs(t, n, pl, t.left[p], c_prim, cl);
+        plan_costs(t, n, pl, t.right[p], c_prim, cr);
+        const float area = half_area(t.lo[p], t.hi[p]);
+        float d[9];
+        uint8_t kk[9];
+#pragma unroll
+        for (int jj = 2; jj <= 8; ++jj) {
+            float best = FLT_MAX;
+            uint8_t bk = 1;
+#pragma unroll
+            for (int k = 1; k < jj; ++k) {
+                const float v = cl[k - 1] + cr[jj - k - 1]; // (k and jj - k are both <= 7)
+                if (v < best) { best = v; bk = (uint8_t) k; }
+            }
+            d[jj] = best; kk[jj] = bk;
+        }
+        const uint32_t cnt = t.count[p];
+        const float c_leaf = cnt <= (uint32_t) kMaxLeafTris ? area * (float) cnt * c_prim : FLT_MAX;
+        const float c_inner = area * c_node + d[8];
+        float c[8];
+        uint8_t sp[8];
+        c[1] = fminf(c_leaf, c_inner);
+        sp[0] = c_leaf <= c_inner ? 1 : 0;
+#pragma unroll
+        for (int i = 2; i <= 7; ++i) {
+            if (d[i] < c[i - 1]) { c[i] = d[i]; sp[i - 1] = kk[i]; }
+            else { c[i] = c[i - 1]; sp[i - 1] = 0; }
+        }
+        sp[7] = kk[8];
+#pragma unroll
+        for (int i = 0; i < 7; ++i) pl.cost[7 * (size_t) p + i] = c[i + 1];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) pl.split[8 * (size_t) p + i] = sp[i];
+        p = t.parent[p];
+    }
+}
+
 struct WorkItem { uint32_t bvh2, wide; };
 
 // One thread builds one wide node from the binary subtree rooted at item.bvh2.
 __global__ void k_collapse(const WorkItem *__restrict__ in, uint32_t nin, WorkItem *__restrict__ out, uint32_t out_cap,
                            Bvh2 t, int n, const uint32_t *__restrict__ sorted, const float4 *__restrict__ gathered,
                            float4 *__restrict__ nodes, uint32_t node_cap, float4 *__restrict__ tris, uint32_t tri_cap,
-                           BuildState *st, int root_is_leaf) {
+                           BuildState *st, int root_is_leaf, Plan pl) {
     uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
     if (w >= nin) return;
     WorkItem item = in[w];
@@ -299,6 +385,26 @@ __global__ void k_collapse(const WorkItem *__restrict__ in, uint32_t nin, WorkIt
     int nc = 0;
     if (root_is_leaf) {
         cand[nc++] = item.bvh2; // n == 1: the single triangle
+    } else if (pl.split) {
+        // the 8 slots of this node distributed as k_plan found cheapest: (node, roots) pairs, left before right
+        uint32_t snode[8];
+        uint8_t sroots[8];
+        int sp = 0;
+        const uint32_t r = item.bvh2;
+        const uint8_t k8 = pl.split[8 * (size_t) r + 7];
+        snode[sp] = t.right[r]; sroots[sp++] = (uint8_t) (8 - k8);
+        snode[sp] = t.left[r];  sroots[sp++] = k8;
+        while (sp) {
+            const uint32_t u = snode[--sp];
+            const uint8_t j = sroots[sp];
+            if (u >= (uint32_t) (n - 1) || j == 1) { cand[nc++] = u; continue; }
+            const uint8_t k = pl.split[8 * (size_t) u + (j - 1)];
+            if (k == 0) { snode[sp] = u; sroots[sp++] = (uint8_t) (j - 1); } // one root fewer is as cheap
+            else {
+                snode[sp] = t.right[u]; sroots[sp++] = (uint8_t) (j - k);
+                snode[sp] = t.left[u];  sroots[sp++] = k;
+            }
+        }
     } else {
         cand[nc++] = t.left[item.bvh2];
         cand[nc++] = t.right[item.bvh2];
@@ -330,7 +436,8 @@ __global__ void k_collapse(const WorkItem *__restrict__ in, uint32_t nin, WorkIt
     for (int c = 0; c < nc; ++c) {
         clo[c] = t.lo[cand[c]]; chi[c] = t.hi[cand[c]];
         cnts[c] = node_count(t, n, cand[c]);
-        if (cnts[c] > (uint32_t) kMaxLeafTris) inner_cand |= 1u << c; else nleaf++;
+        const bool inner = pl.split ? (cand[c] < (uint32_t) (n - 1) && pl.split[8 * (size_t) cand[c]] == 0) : cnts[c] > (uint32_t) kMaxLeafTris;
+        if (inner) inner_cand |= 1u << c; else nleaf++;
         float dx = 0.5f * (clo[c].x + chi[c].x) - pc[0], dy = 0.5f * (clo[c].y + chi[c].y) - pc[1],
               dz = 0.5f * (clo[c].z + chi[c].z) - pc[2];
         for (int s = 0; s < 8; ++s)
@@ -443,9 +550,43 @@ __global__ void k_sah(const Bvh2 t, int n, float *out) {
     if ((threadIdx.x & 31) == 0 && v != 0.f) atomicAdd(out, v);
 }
 
+// MSK_DEBUG_SETUP: shape of the wide tree -- histogram of inner / leaf children per node and of triangles per leaf
+// out[0..8] nodes with k inner children | out[9..17] nodes with k leaf children | out[18..26] nodes with k children in total |
+// out[27..30] leaves with 0..3 triangles
+__global__ void k_shape(const float4 *__restrict__ nodes, uint32_t nnodes, unsigned long long *out) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nnodes) return;
+    const uint32_t valid = __float_as_uint(nodes[(size_t) i * kNodeFloat4s + 1].z);
+    const uint32_t ninner = __popc(valid >> 24);
+    uint32_t nleaf = 0;
+    for (int j = 0; j < 8; ++j) {
+        const uint32_t t = __popc((valid >> (3 * j)) & 7u);
+        if (t) { nleaf++; atomicAdd(out + 27 + t, 1ull); }
+    }
+    atomicAdd(out + ninner, 1ull); atomicAdd(out + 9 + nleaf, 1ull); atomicAdd(out + 18 + ninner + nleaf, 1ull);
+}
+
 template <typename T> cudaError_t dalloc(T **p, size_t n) { return cudaMalloc((void **) p, std::max<size_t>(n, 1) * sizeof(T)); }
 
 } // namespace
+
+void bvh_print_shape(cudaStream_t stream, const BvhResult &r) {
+    unsigned long long *d = nullptr, h[31] = {};
+    if (cudaMalloc(&d, sizeof(h)) != cudaSuccess) return;
+    cudaMemsetAsync(d, 0, sizeof(h), stream);
+    k_shape<<<blocks_for(r.nnodes), kThreads, 0, stream>>>(r.nodes, (uint32_t) r.nnodes, d);
+    cudaMemcpyAsync(h, d, sizeof(h), cudaMemcpyDeviceToHost, stream);
+    cudaStreamSynchronize(stream);
+    cudaFree(d);
+    fprintf(stderr, "[msk] wide BVH: %llu nodes, depth %u, sah %.2f | nodes by inner children 0..8:", (unsigned long long) r.nnodes, r.depth, r.sah_cost);
+    for (int k = 0; k <= 8; ++k) fprintf(stderr, " %llu", h[k]);
+    fprintf(stderr, " | by leaf children 0..8:");
+    for (int k = 0; k <= 8; ++k) fprintf(stderr, " %llu", h[9 + k]);
+    fprintf(stderr, " | by children 0..8:");
+    double tot = 0, cnt = 0;
+    for (int k = 0; k <= 8; ++k) { fprintf(stderr, " %llu", h[18 + k]); tot += (double) k * h[18 + k]; cnt += (double) h[18 + k]; }
+    fprintf(stderr, " (mean %.2f) | leaves with 1..3 triangles: %llu %llu %llu\n", cnt ? tot / cnt : 0.0, h[28], h[29], h[30]);
+}
 
 static int bvh_build_impl(cudaStream_t stream, const float4 *d_verts, const uint32_t *d_indices, const std::vector<DMeshInfo> &meshes,
                           BvhResult *out, int builder, size_t tri_cap_override) {
@@ -487,6 +628,7 @@ static int bvh_build_impl(cudaStream_t stream, const float4 *d_verts, const uint
     Bvh2 t{};
     WorkItem *qa = nullptr, *qb = nullptr;
     float *sah = nullptr;
+    Plan pl{ nullptr, nullptr };
     uint32_t *p_cid[2] = { nullptr, nullptr }, *p_nn = nullptr, *p_flags = nullptr, *p_pos = nullptr, *p_counters = nullptr;
     float4 *p_lo[2] = { nullptr, nullptr }, *p_hi[2] = { nullptr, nullptr };
     void *p_tmp = nullptr;
@@ -495,6 +637,7 @@ static int bvh_build_impl(cudaStream_t stream, const float4 *d_verts, const uint
         cudaFree(gathered); cudaFree(keys); cudaFree(keys_sorted); cudaFree(vals); cudaFree(sorted); cudaFree(st);
         cudaFree(cub_tmp); cudaFree(t.left); cudaFree(t.right); cudaFree(t.parent); cudaFree(t.count);
         cudaFree(t.lo); cudaFree(t.hi); cudaFree(t.flags); cudaFree(qa); cudaFree(qb); cudaFree(sah);
+        cudaFree(pl.cost); cudaFree(pl.split);
         for (int k = 0; k < 2; ++k) { cudaFree(p_cid[k]); cudaFree(p_lo[k]); cudaFree(p_hi[k]); }
         cudaFree(p_nn); cudaFree(p_flags); cudaFree(p_pos); cudaFree(p_tmp); cudaFree(p_counters);
         cudaEventDestroy(e0); cudaEventDestroy(e1);
@@ -554,6 +697,9 @@ static int bvh_build_impl(cudaStream_t stream, const float4 *d_verts, const uint
             c = c2; cur ^= 1; rounds++;
         }
         out->build_rounds = rounds;
+        BVH_CHECK(dalloc(&t.flags, nint));
+        BVH_CHECK(dalloc(&t.parent, 2 * n));
+        if (n > 1) k_set_parents<<<blocks_for(n - 1), kThreads, 0, stream>>>(t, (int) n);
     } else {
         BVH_CHECK(dalloc(&t.flags, nint));
         BVH_CHECK(dalloc(&t.parent, 2 * n));
@@ -563,6 +709,29 @@ static int bvh_build_impl(cudaStream_t stream, const float4 *d_verts, const uint
     }
     if (n > 1) k_sah<<<blocks_for(n - 1), kThreads, 0, stream>>>(t, (int) n, sah);
 
+    // SAH-optimal collapse plan (MSK_BVH_COLLAPSE=greedy: the round-1 rule, open the largest child while slots remain)
+    {
+        const char *csel = getenv("MSK_BVH_COLLAPSE");
+        const bool sah_collapse = !(csel && csel[0] == 'g');
+        const char *cn = getenv("MSK_BVH_CNODE"), *cp = getenv("MSK_BVH_CPRIM");
+        // a node step and a triangle test cost the lockstep traversal about the same number of issue slots per lane
+        // (212 warp instructions at 23 lanes against 91 at 9.7: DESIGN.md section 3)
+        const float c_node = cn && *cn ? (float) atof(cn) : 1.0f, c_prim = cp && *cp ? (float) atof(cp) : 1.0f;
+        if (sah_collapse && n > 1) {
+            BVH_CHECK(dalloc(&pl.cost, 7 * nint));
+            BVH_CHECK(dalloc(&pl.split, 8 * nint));
+            BVH_CHECK(cudaMemsetAsync(t.flags, 0, nint * sizeof(uint32_t), stream));
+            const bool dbg = getenv("MSK_DEBUG_SETUP") && atoi(getenv("MSK_DEBUG_SETUP"));
+            if (dbg) cudaStreamSynchronize(stream);
+            const auto t0 = std::chrono::steady_clock::now();
+            k_plan<<<blocks_for(n), kThreads, 0, stream>>>(t, (int) n, pl, c_node, c_prim);
+            if (dbg) {
+                cudaStreamSynchronize(stream);
+                fprintf(stderr, "[msk] k_plan: %.2f ms\n", std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
+            }
+        }
+    }
+
     // level-synchronous collapse
     size_t qcap = node_cap;
     BVH_CHECK(dalloc(&qa, qcap)); BVH_CHECK(dalloc(&qb, qcap));
@@ -570,9 +739,11 @@ static int bvh_build_impl(cudaStream_t stream, const float4 *d_verts, const uint
     BVH_CHECK(cudaMemcpyAsync(qa, &root, sizeof(root), cudaMemcpyHostToDevice, stream));
     uint32_t nin = 1, depth = 0;
     BuildState hst{};
+    const bool dbg_collapse = getenv("MSK_DEBUG_SETUP") && atoi(getenv("MSK_DEBUG_SETUP"));
     while (nin) {
+        const auto tc0 = std::chrono::steady_clock::now();
         k_collapse<<<(nin + 127) / 128, 128, 0, stream>>>(qa, nin, qb, (uint32_t) qcap, t, (int) n, sorted, gathered, out->nodes,
-                                                        (uint32_t) node_cap, out->tris, (uint32_t) tri_cap, st, n == 1 ? 1 : 0);
+                                                        (uint32_t) node_cap, out->tris, (uint32_t) tri_cap, st, n == 1 ? 1 : 0, pl);
         BVH_CHECK(cudaMemcpyAsync(&hst, st, sizeof(hst), cudaMemcpyDeviceToHost, stream));
         BVH_CHECK(cudaStreamSynchronize(stream));
         if (hst.overflow) {
@@ -581,6 +752,7 @@ static int bvh_build_impl(cudaStream_t stream, const float4 *d_verts, const uint
                 return bvh_build_impl(stream, d_verts, d_indices, meshes, out, builder, 24 * node_cap);
             return fail(MSK_ERR_OOM, "BVH node pool overflow (n=%zu)", n);
         }
+        if (dbg_collapse) fprintf(stderr, "[msk] collapse level %u: %u nodes, %.2f ms\n", depth, nin, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tc0).count());
         nin = hst.queue_count;
         BVH_CHECK(cudaMemsetAsync(&st->queue_count, 0, sizeof(uint32_t), stream));
         std::swap(qa, qb);

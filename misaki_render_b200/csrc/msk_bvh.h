@@ -22,5 +22,6 @@ enum { MSK_BVH_PLOC = 0, MSK_BVH_LBVH = 1 };
 int  bvh_build(cudaStream_t stream, const float4 *d_verts, const uint32_t *d_indices, const std::vector<DMeshInfo> &meshes,
                BvhResult *out, int builder = MSK_BVH_LBVH);
 void bvh_free(BvhResult *r);
+void bvh_print_shape(cudaStream_t stream, const BvhResult &r); // MSK_DEBUG_SETUP: child / leaf histograms of the wide tree on stderr
 
 } // namespace msk

@@ -71,6 +71,30 @@ def test_edge_cases(gpu_ctx):
         assert np.allclose(h["t"], ref["t"], rtol=1e-5)
 
 
+@pytest.mark.parametrize("builder", ["lbvh", "ploc"])
+def test_sah_optimal_collapse_same_hits_fewer_nodes(gpu_ctx, monkeypatch, builder):
+    """The wide tree is collapsed from the binary one by dynamic programming over the SAH cost (k_plan, msk_bvh.cu) instead
+    of greedily opening the largest child (MSK_BVH_COLLAPSE=greedy): fewer, fuller nodes over the same triangles -- same
+    closest hits, same occlusion, under both binary builders."""
+    sd = scenes.bunny(64, 64)
+    osc = pyoracle.OracleScene(sd)
+    rays = np.concatenate([_camera_rays(sd, osc, 3000, 17), random_rays(3000, (-2, 0.05, -2), (2, 2.5, 2), seed=18)])
+    monkeypatch.setenv("MSK_BVH_BUILDER", builder)
+    with capi.Scene(gpu_ctx, sd) as sc:
+        sah, sah_occ, si = sc.intersect(rays), sc.occluded(rays), sc.accel_info()
+    monkeypatch.setenv("MSK_BVH_COLLAPSE", "greedy")
+    with capi.Scene(gpu_ctx, sd) as sc:
+        gr, gr_occ, gi = sc.intersect(rays), sc.occluded(rays), sc.accel_info()
+    assert si.ntris == gi.ntris and si.nnodes < gi.nnodes
+    ref = osc.intersect(rays, brute_force=True)
+    t2, mb = osc.margin(rays)
+    assert compare_hits(sah, ref, t2, mb, rays)["mismatches"] == 0
+    assert compare_hits(gr, ref, t2, mb, rays)["mismatches"] == 0
+    nondeg = mb > 1e-6
+    assert (sah["prim"] == gr["prim"])[nondeg].all()
+    assert (sah_occ == gr_occ)[nondeg | ~np.isfinite(ref["t"])].all()
+
+
 def test_ploc_builder_same_hits(gpu_ctx, monkeypatch):
     """MSK_BVH_BUILDER=ploc (SAH-driven clustering instead of the Morton-prefix tree): another tree over the same
     triangles must report the same closest hits and the same occlusion."""
