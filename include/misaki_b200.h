@@ -19,7 +19,7 @@
  *   msk_gpu_render[_dev]     SamplingIntegrator::render  integrator.cpp:31-126
  *                            PathTracer::sample          integrators/path.cpp:23-131
  *                            ImageBlock::put/Film::put   imageblock.cpp:36-114, hdrfilm.cpp:43-46
- *   msk_gpu_develop          HDRFilm::image              hdrfilm.cpp:48-90
+ *   msk_gpu_develop[_dev]    HDRFilm::image              hdrfilm.cpp:48-90
  *   msk_gpu_render_aov[_dev] AOVIntegrator::sample       integrators/aov.cpp:87-144 (+ the nested "path" child)
  *
  * Conventions: plain C, POD structs, no exceptions across the boundary.  Every
@@ -272,6 +272,9 @@ int  msk_gpu_render_aov(MskScene *scene, const MskRenderDesc *rd, const MskAovDe
 int  msk_gpu_render_aov_dev(MskScene *scene, const MskRenderDesc *rd, const MskAovDesc *aov, float *d_film, MskStats *stats);
 /* XYZAW film -> RGBA (linear sRGB / W, A / W), both host, n = width*height pixels */
 int  msk_gpu_develop(MskScene *scene, const float *film_host, float *rgba_host);
+/* the same on device buffers (XYZAW film as written by msk_gpu_render_dev; rgba: 4 floats per pixel, 16-byte aligned);
+ * asynchronous on msk_gpu_stream(ctx); bit-identical to msk_gpu_develop */
+int  msk_gpu_develop_dev(MskScene *scene, const float *d_film, float *d_rgba);
 
 /* ---- multi-GPU film reduction over NVLink peer memory (replaces Film::put under the mutex,
  * films/hdrfilm.cpp:43-46, across GPUs).  One process per GPU.  Every rank creates a share (a cudaMalloc'ed film with

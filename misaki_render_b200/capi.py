@@ -21,7 +21,7 @@ EXPORTED_SYMBOLS = [
     "msk_gpu_abi_version", "msk_gpu_last_error", "msk_gpu_init", "msk_gpu_shutdown", "msk_gpu_stream",
     "msk_gpu_scene_create", "msk_gpu_scene_destroy", "msk_gpu_accel_info", "msk_gpu_intersect",
     "msk_gpu_occluded", "msk_gpu_intersect_dev", "msk_gpu_occluded_dev", "msk_gpu_intersect_stats",
-    "msk_gpu_render", "msk_gpu_render_dev", "msk_gpu_render_reserve", "msk_gpu_develop",
+    "msk_gpu_render", "msk_gpu_render_dev", "msk_gpu_render_reserve", "msk_gpu_develop", "msk_gpu_develop_dev",
     "msk_gpu_aov_channels", "msk_gpu_render_aov", "msk_gpu_render_aov_dev",
     "msk_gpu_film_share_create", "msk_gpu_film_share_ptr", "msk_gpu_film_share_export", "msk_gpu_film_share_open",
     "msk_gpu_reduce_film", "msk_gpu_film_share_check", "msk_gpu_film_share_destroy",
@@ -157,6 +157,7 @@ def load(path: os.PathLike | None = None) -> C.CDLL:
     lib.msk_gpu_render.argtypes = [C.c_void_p, C.POINTER(MskRenderDesc), C.c_void_p, C.POINTER(MskStats)]
     lib.msk_gpu_render_dev.argtypes = [C.c_void_p, C.POINTER(MskRenderDesc), C.c_void_p, C.POINTER(MskStats)]
     lib.msk_gpu_render_reserve.argtypes = [C.c_void_p, C.POINTER(MskRenderDesc)]
+    lib.msk_gpu_develop_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     lib.msk_gpu_develop.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     lib.msk_gpu_aov_channels.argtypes = [C.POINTER(MskAovDesc)]
     lib.msk_gpu_render_aov.argtypes = [C.c_void_p, C.POINTER(MskRenderDesc), C.POINTER(MskAovDesc), C.c_void_p, C.POINTER(MskStats)]
@@ -290,6 +291,10 @@ class Scene:
     def reserve(self, rd: MskRenderDesc):
         """Allocate the path pools a render of `rd` will use now (msk_gpu_render_reserve)."""
         check(self.lib, self.lib.msk_gpu_render_reserve(self.handle, C.byref(rd)))
+
+    def develop_dev(self, d_film: int, d_rgba: int):
+        """HDRFilm::image on device buffers (msk_gpu_develop_dev), asynchronous on the context's stream."""
+        check(self.lib, self.lib.msk_gpu_develop_dev(self.handle, d_film, d_rgba))
 
     def render_dev(self, rd: MskRenderDesc, d_film: int, want_stats: bool = True):
         stats = MskStats()

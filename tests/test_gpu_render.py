@@ -404,6 +404,27 @@ def test_batches_in_flight_are_bit_identical(monkeypatch, integrator, max_depth)
             (out[0][1].rays_closest, out[0][1].rays_shadow, out[0][1].shaded_vertices, out[0][1].batches)
 
 
+def test_develop_on_the_device_is_bit_identical(gpu_ctx):
+    """msk_gpu_develop_dev (k_develop: HDRFilm::image on a device film) against msk_gpu_develop (host loop) and the oracle's
+    develop, which is pinned bit for bit to the reference's compiled hdrfilm.cpp -- zero-weight pixels included."""
+    import torch
+    sd = scenes.cbox(64, 48)
+    with capi.Scene(gpu_ctx, sd) as sc:
+        film, _ = sc.render(capi.render_desc(spp=4, max_depth=3))
+        film[5, 7, :] = 0.0   # a pixel no sample reached: W == 0 develops to 0, not NaN (hdrfilm.cpp:63-66)
+        film[9, 3, 4] = 0.0
+        host = sc.develop(film)
+        stream = torch.cuda.ExternalStream(gpu_ctx.stream)
+        with torch.cuda.stream(stream):
+            d_film = torch.from_numpy(film).cuda()
+            d_rgba = torch.empty((sd.height, sd.width, 4), dtype=torch.float32, device="cuda")
+            sc.develop_dev(d_film.data_ptr(), d_rgba.data_ptr())
+            dev = d_rgba.cpu().numpy()
+    np.testing.assert_array_equal(dev, host)
+    np.testing.assert_array_equal(dev, pyoracle.develop(film))
+    assert np.isfinite(dev).all() and not dev[5, 7].any()
+
+
 def test_c2_full_size_properties(gpu_ctx):
     """BASELINE configs[1] at its full size (512x512, 64 spp, unbounded depth): size-independent properties instead of a
     full oracle render -- bit-determinism run to run, invariance under a partition of the sample range (what multi-GPU
