@@ -1238,6 +1238,7 @@ struct Renderer::Impl {
     int spec_shade = 1;               // MSK_SPEC_SHADE: one k_shade launch per material key present in the scene
     uint32_t spec_min = 1u << 18;     // MSK_SPEC_MIN: ... while the queue may hold at least this many vertices
     int shadow_static_bounces = 0;    // MSK_SHADOW_STATIC_BOUNCES: bounces whose shadow queue counts as coherent
+    int static_bounces = 1;           // MSK_STATIC_BOUNCES: bounces whose closest-hit queue counts as coherent (camera rays)
     int debug_bounces = 0;            // MSK_DEBUG_BOUNCES: print polled queue lengths and per-launch stage times to stderr
     uint32_t tail_threshold = 1u << 18; // MSK_TAIL_THRESHOLD: finish an unbounded job with k_tail once the queue is this short (0: never)
     int tiled_slots = 1;              // MSK_TILED_SLOTS: enumerate the film in 8x4 tiles (see slot_decode)
@@ -1355,6 +1356,7 @@ int Renderer::init(int sm_count) {
     impl_->spec_shade = (int) env_u("MSK_SPEC_SHADE", impl_->spec_shade);
     impl_->spec_min = (uint32_t) env_u("MSK_SPEC_MIN", impl_->spec_min);
     impl_->shadow_static_bounces = (int) env_u("MSK_SHADOW_STATIC_BOUNCES", impl_->shadow_static_bounces);
+    impl_->static_bounces = (int) env_u("MSK_STATIC_BOUNCES", impl_->static_bounces);
     impl_->async_poll = (int) env_u("MSK_ASYNC_POLL", impl_->async_poll);
     impl_->tail_threshold = (uint32_t) env_u("MSK_TAIL_THRESHOLD", impl_->tail_threshold);
     impl_->poll_min_depth = (int) env_u("MSK_POLL_MIN_DEPTH", impl_->poll_min_depth);
@@ -1583,8 +1585,8 @@ int Renderer::render(cudaStream_t stream0, const DScene &sc, const MskRenderDesc
         }
         const int tiny_scene = sc.nnodes <= im.static_nodes;
         const int first = first_elide && bounce == 0;
-        if (tstats) MSK_STAGE(ST_INTERSECT, (k_intersect<true><<<pb, 128, 0, stream>>>(sc, pool, cur, bounce == 0 || tiny_scene, perm)));
-        else MSK_STAGE(ST_INTERSECT, (k_intersect<false><<<pb, 128, 0, stream>>>(sc, pool, cur, bounce == 0 || tiny_scene, perm)));
+        if (tstats) MSK_STAGE(ST_INTERSECT, (k_intersect<true><<<pb, 128, 0, stream>>>(sc, pool, cur, (int) bounce < im.static_bounces || tiny_scene, perm)));
+        else MSK_STAGE(ST_INTERSECT, (k_intersect<false><<<pb, 128, 0, stream>>>(sc, pool, cur, (int) bounce < im.static_bounces || tiny_scene, perm)));
         // the AOV integrator shares the primary hit with the nested path tracer (the reference intersects twice)
         if (aov && bounce == 0) MSK_STAGE(ST_FILM, (k_aov_capture<<<(n + 255) / 256, 256, 0, stream>>>(sc, pool, bp, plan)));
         if (!MSK_SORT_IN_COMMIT) MSK_STAGE(ST_SORT, (k_sort<<<im.sm_count * 4, kSortThreads, 0, stream>>>(sc, pool, cur)));
