@@ -190,13 +190,6 @@ struct OScene {
     float env_radius = 0.f; // constant.cpp:21-28
     std::vector<BVHNode> nodes;
     std::vector<TriRef> refs;
-#ifdef ORC_FAST
-    // speed build only (oracle/Makefile `fast`, bench.py's CPU arm): the same tree re-laid out for an ordered walk
-    struct FNode { float lo[2][3], hi[2][3]; uint32_t child[2], count[2]; }; // both child boxes in the parent; count > 0: leaf [child, child + count)
-    struct FTri { V3 v0, v1, v2; uint32_t geom, prim; };                      // pre-gathered vertices in leaf order
-    std::vector<FNode> fnodes;
-    std::vector<FTri> ftris;
-#endif
 };
 
 struct Ray { V3 o, d; float mint, maxt; Spec wavelengths; };
@@ -313,102 +306,6 @@ RawHit intersect_bvh(const OScene &sc, const Ray &ray, bool any_hit) {
     }
     return best;
 }
-
-#ifdef ORC_FAST
-// The speed build's walk over the same tree and the same triangles with the same arithmetic (tri_intersect, the widened
-// slab test, the (geom, prim) tie rule), so it returns the records of intersect_bvh bit for bit; what changes is the work:
-// both child boxes are tested in the parent, the nearer child is entered first (the checker walks unordered), and a leaf's
-// vertices are contiguous instead of three index hops away.
-inline bool slab_fast(const float lo[3], const float hi[3], const float o[3], const float inv[3], float tmin, float tmax, float &tnear) {
-    float t0 = tmin, t1 = tmax;
-    for (int a = 0; a < 3; ++a) {
-        float ta = (lo[a] - o[a]) * inv[a], tb = (hi[a] - o[a]) * inv[a];
-        if (ta > tb) std::swap(ta, tb);
-        t0 = std::max(t0, ta * (1.f - 4e-7f) - 1e-30f);
-        t1 = std::min(t1, tb * (1.f + 4e-7f) + 1e-30f);
-    }
-    tnear = t0;
-    return t0 <= t1;
-}
-
-inline bool leaf_fast(const OScene &sc, uint32_t first, uint32_t count, const Ray &ray, bool any_hit, RawHit &best) {
-    for (uint32_t i = 0; i < count; ++i) {
-        const OScene::FTri &tr = sc.ftris[first + i];
-        float t, u, v;
-        if (tri_intersect(tr.v0, tr.v1, tr.v2, ray.o, ray.d, ray.mint, ray.maxt, t, u, v)) {
-            bool better = t < best.t || (t == best.t && (tr.geom < best.geom || (tr.geom == best.geom && tr.prim < best.prim)));
-            if (better) { best.t = t; best.u = u; best.v = v; best.prim = tr.prim; best.geom = tr.geom; }
-            if (any_hit) return true;
-        }
-    }
-    return false;
-}
-
-RawHit intersect_fast(const OScene &sc, const Ray &ray, bool any_hit) {
-    RawHit best;
-    if (sc.nodes.empty()) return best;
-    if (sc.fnodes.empty()) { // a single leaf
-        leaf_fast(sc, 0, (uint32_t) sc.ftris.size(), ray, any_hit, best);
-        return best;
-    }
-    const float inv[3] = { 1.f / ray.d.x, 1.f / ray.d.y, 1.f / ray.d.z };
-    const float o[3] = { ray.o.x, ray.o.y, ray.o.z };
-    struct Entry { uint32_t node; float tnear; };
-    Entry stack[128];
-    int sp = 0;
-    stack[sp++] = { 0u, ray.mint };
-    while (sp) {
-        const Entry e = stack[--sp];
-        if (e.tnear > std::min(ray.maxt, best.t)) continue; // entered behind the closest hit found meanwhile
-        const OScene::FNode &n = sc.fnodes[e.node];
-        const float tmax = std::min(ray.maxt, best.t);
-        float tn[2];
-        bool hit[2];
-        for (int c = 0; c < 2; ++c) hit[c] = slab_fast(n.lo[c], n.hi[c], o, inv, ray.mint, tmax, tn[c]);
-        const int first = (hit[0] && hit[1] && tn[1] < tn[0]) ? 1 : 0;
-        // the farther child waits on the stack, the nearer is handled now (leaves at once, inner nodes pushed last)
-        for (int k = 1; k >= 0; --k) {
-            const int c = k == 1 ? 1 - first : first;
-            if (!hit[c] || n.count[c]) continue;
-            stack[sp++] = { n.child[c], tn[c] };
-        }
-        for (int k = 0; k < 2; ++k) {
-            const int c = k == 0 ? first : 1 - first;
-            if (!hit[c] || !n.count[c]) continue;
-            if (tn[c] > std::min(ray.maxt, best.t)) continue;
-            if (leaf_fast(sc, n.child[c], n.count[c], ray, any_hit, best)) return best;
-        }
-    }
-    return best;
-}
-
-void build_fast_layout(OScene &sc) {
-    sc.fnodes.clear(); sc.ftris.clear();
-    sc.ftris.reserve(sc.refs.size());
-    for (const TriRef &r : sc.refs) {
-        const OMesh &m = sc.meshes[r.geom];
-        const uint32_t *f = &m.tris[r.prim * 3];
-        sc.ftris.push_back({ m.pos(f[0]), m.pos(f[1]), m.pos(f[2]), r.geom, r.prim });
-    }
-    if (sc.nodes.empty() || sc.nodes[0].count) return; // no tree, or the root is a leaf
-    std::vector<uint32_t> remap(sc.nodes.size(), 0xffffffffu);
-    for (size_t i = 0; i < sc.nodes.size(); ++i)
-        if (!sc.nodes[i].count) { remap[i] = (uint32_t) sc.fnodes.size(); sc.fnodes.push_back({}); }
-    for (size_t i = 0; i < sc.nodes.size(); ++i) {
-        const BVHNode &b = sc.nodes[i];
-        if (b.count) continue;
-        OScene::FNode &fn = sc.fnodes[remap[i]];
-        const uint32_t ch[2] = { b.left, b.right };
-        for (int c = 0; c < 2; ++c) {
-            const BVHNode &cn = sc.nodes[ch[c]];
-            for (int a = 0; a < 3; ++a) { fn.lo[c][a] = cn.lo[a]; fn.hi[c][a] = cn.hi[a]; }
-            fn.count[c] = cn.count;
-            fn.child[c] = cn.count ? cn.first : remap[ch[c]];
-        }
-    }
-}
-#define intersect_bvh intersect_fast
-#endif
 
 // binned SAH BVH2 build (oracle-private)
 void build_bvh(OScene &sc) {
@@ -1399,9 +1296,6 @@ int orc_scene_create(const MskSceneDesc *d, OrcScene **out) {
         sc.env_radius = std::max(RayEpsilon, radius * (1.f + RayEpsilon));
     }
     build_bvh(sc);
-#ifdef ORC_FAST
-    build_fast_layout(sc);
-#endif
     *out = S.release();
     return 0;
 }
