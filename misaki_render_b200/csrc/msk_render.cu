@@ -1083,10 +1083,17 @@ constexpr int kFilmHaloX = kFilmTileX + 2 * kFilmMaxBorder, kFilmHaloY = kFilmTi
 __global__ void __launch_bounds__(kFilmTileX *kFilmTileY) k_film_gather_tiled(const __grid_constant__ DScene sc, Pool pool,
                                                                                BatchParams bp, float *__restrict__ film,
                                                                                uint32_t height, uint32_t stride) {
-    // per halo cell: X, Y, Z, posx | posy (positions block-relative, imageblock.cpp:86-98).  20 bytes per candidate
-    // instead of the 32 of the first version (which also kept the block origin): the loop is shared-memory bound
-    __shared__ float4 s_a[kFilmHaloY][kFilmHaloX];
-    __shared__ float s_py[kFilmHaloY][kFilmHaloX];
+    // Per halo cell (one sample of one pixel): X, Y, Z and the cell's filter weights towards the five pixel columns and the
+    // five pixel rows it can reach, computed ONCE by the thread that stages the cell -- the reference's own arithmetic per
+    // (sample, target pixel): block-relative positions (imageblock.cpp:86-98), the lo / hi range test, the 33-entry table --
+    // with 0 outside the range (adding 0 * value is what skipping the pixel is).  The first version evaluated both weights
+    // in the consumer, per (pixel, candidate): 25 candidates x (two range tests, two table look-ups) per pixel and sample,
+    // 870 thread instructions, the kernel 67 % issue-bound (profiles/ncu_counters.json: 588 M warp instructions per C2
+    // step); staging computes 10 weights per cell instead of 50 per pixel, the consumer is 3 shared loads and 5 FMAs per
+    // candidate.  Same neighbour order, same products and sums: bit-identical film.
+    constexpr int kWin = 2 * kFilmMaxBorder + 1;
+    __shared__ float4 s_xyz[kFilmHaloY][kFilmHaloX];
+    __shared__ float s_wx[kWin][kFilmHaloY][kFilmHaloX], s_wy[kWin][kFilmHaloY][kFilmHaloX];
     __shared__ float s_tab[33];
     const int W = (int) bp.width, H = (int) height;
     const int x0 = blockIdx.x * kFilmTileX, y0 = blockIdx.y * kFilmTileY;
@@ -1099,17 +1106,7 @@ __global__ void __launch_bounds__(kFilmTileX *kFilmTileY) k_film_gather_tiled(co
     // this thread's neighbour window in halo coordinates (clipped to the film like the reference's lo/hi clamp)
     const int hx_lo = max(x - r, 0) - (x0 - kFilmMaxBorder), hx_hi = min(x + r, W - 1) - (x0 - kFilmMaxBorder);
     const int hy_lo = max(y - r, 0) - (y0 - kFilmMaxBorder), hy_hi = min(y + r, H - 1) - (y0 - kFilmMaxBorder);
-    // this pixel's coordinate relative to the block of each neighbour column / row (m_offset - m_border_size of the
-    // 32x32 block that neighbour belongs to): small integers, exact in float, independent of the sample
-    constexpr int kWin = 2 * kFilmMaxBorder + 1;
     const int hx_first = (int) threadIdx.x, hy_first = (int) threadIdx.y; // halo coordinate of (x - kFilmMaxBorder, y - kFilmMaxBorder)
-    float xb[kWin], yb[kWin];
-#pragma unroll
-    for (int d = 0; d < kWin; ++d) {
-        const int nx = x - kFilmMaxBorder + d, ny = y - kFilmMaxBorder + d;
-        xb[d] = (float) (x - ((nx & ~(kBlockSize - 1)) - r));
-        yb[d] = (float) (y - ((ny & ~(kBlockSize - 1)) - r));
-    }
     float aX = 0.f, aY = 0.f, aZ = 0.f, aW = 0.f;
     for (uint32_t s = 0; s < bp.ns; ++s) {
         const size_t sbase = (size_t) s * bp.npix;
@@ -1122,8 +1119,16 @@ __global__ void __launch_bounds__(kFilmTileX *kFilmTileY) k_film_gather_tiled(co
                 const float4 rec = __ldcs(pool.rec + i);
                 const float py = __ldcs(pool.rec_py + i);
                 const int bx = (nx & ~(kBlockSize - 1)) - r, by = (ny & ~(kBlockSize - 1)) - r; // m_offset - m_border_size
-                s_a[hy][hx] = make_float4(rec.x, rec.y, rec.z, rec.w - 0.5f - (float) bx);
-                s_py[hy][hx] = py - 0.5f - (float) by;
+                const float posx = rec.w - 0.5f - (float) bx, posy = py - 0.5f - (float) by;
+                s_xyz[hy][hx] = make_float4(rec.x, rec.y, rec.z, 0.f);
+#pragma unroll
+                for (int d = 0; d < kWin; ++d) { // target pixel (nx - border + d, .) / (., ny - border + d), relative to THIS sample's block
+                    const float xb = (float) (nx - kFilmMaxBorder + d - bx), yb = (float) (ny - kFilmMaxBorder + d - by);
+                    // lo = ceil(pos - radius) <= x <= floor(pos + radius) = hi
+                    const bool outx = xb < posx - radius || xb > posx + radius, outy = yb < posy - radius || yb > posy + radius;
+                    s_wx[d][hy][hx] = outx ? 0.f : s_tab[min((int) fabsf((xb - posx) * scale), 32)];
+                    s_wy[d][hy][hx] = outy ? 0.f : s_tab[min((int) fabsf((yb - posy) * scale), 32)];
+                }
             }
         }
         __syncthreads();
@@ -1136,14 +1141,9 @@ __global__ void __launch_bounds__(kFilmTileX *kFilmTileY) k_film_gather_tiled(co
             for (int dx = 0; dx < kWin; ++dx) {
                 const int hx = hx_first + dx;
                 if (hx < hx_lo || hx > hx_hi) continue;
-                const float4 a = s_a[hy][hx];
-                const float posx = a.w;
-                if (xb[dx] < posx - radius || xb[dx] > posx + radius) continue;
-                const float posy = s_py[hy][hx];
-                if (yb[dy] < posy - radius || yb[dy] > posy + radius) continue;
-                const float wx = s_tab[min((int) fabsf((xb[dx] - posx) * scale), 32)];
-                const float wy = s_tab[min((int) fabsf((yb[dy] - posy) * scale), 32)];
-                const float w = wx * wy;
+                // this pixel is target kWin - 1 - dx of the cell dx columns into its window (x = nx - border + (kWin - 1 - dx))
+                const float w = s_wx[kWin - 1 - dx][hy][hx] * s_wy[kWin - 1 - dy][hy][hx];
+                const float4 a = s_xyz[hy][hx];
                 aX += w * a.x; aY += w * a.y; aZ += w * a.z; aW += w;
             }
         }
