@@ -44,6 +44,11 @@ constexpr int kStackSize = 64; // node groups + postponed triangle groups: at mo
 #ifndef MSK_TRI_REPS
 #define MSK_TRI_REPS 1
 #endif
+// Any-hit queries visit children in slot order instead of front to back (see node_step): C2 any-hit stage 2.48 -> 2.41 ms,
+// C3 77.4 -> 72.0 ms, same occlusion results and bit-identical films (profiles/r02x_ab_any_unordered.txt).
+#ifndef MSK_ANY_UNORDERED
+#define MSK_ANY_UNORDERED 1
+#endif
 #ifndef MSK_STATIC_MIN_GROUP
 #define MSK_STATIC_MIN_GROUP 4 /* 32 disables the adaptive group size of short static queues */
 #endif
@@ -255,7 +260,9 @@ constexpr int kRefillMin    = MSK_REFILL_MIN;
 // inner children and the bits of the triangles a leaf child really holds.  (Round 1 decoded a bit position and a
 // triangle count per child from meta bytes: five ALU instructions per child on the pipe that bounds this kernel.)
 // The inner byte is then permuted into traversal order slot ^ octinv.
-template <bool STATS>
+// ORDERED = false (any-hit queries under MSK_ANY_UNORDERED): children are visited in slot order -- no octant permutation of
+// the hit byte, no slot ^ octinv; an occlusion query does not care which occluder it finds.
+template <bool STATS, bool ORDERED = true>
 __device__ __forceinline__ void node_step(const Accel &ac, Traversal &s, TravStack &stack) {
     const bool negx = s.idx < 0.f, negy = s.idy < 0.f, negz = s.idz < 0.f;
     const uint32_t hits  = s.ngroup.y;
@@ -263,7 +270,7 @@ __device__ __forceinline__ void node_step(const Accel &ac, Traversal &s, TravSta
     const uint32_t bit   = 31u - __clz(hits);
     s.ngroup.y &= ~(1u << bit);
     if (s.ngroup.y > 0x00ffffffu) stack.store(s.sp++, s.ngroup);
-    const uint32_t slot = (bit - 24u) ^ s.octinv;
+    const uint32_t slot = ORDERED ? (bit - 24u) ^ s.octinv : bit - 24u;
     const uint32_t rel  = __popc(imask & ~(0xffffffffu << slot));
     const uint32_t node = s.ngroup.x + rel;
     const float4 *np = ac.nodes + (size_t) node * kNodeFloat4s;
@@ -306,6 +313,8 @@ __device__ __forceinline__ void node_step(const Accel &ac, Traversal &s, TravSta
     }
     hitmask &= __float_as_uint(n1.z); // valid: imask << 24 | bit 3j + k for triangle k of the leaf in slot j
     uint32_t inner;
+    if (!ORDERED) inner = hitmask >> 24;
+    else
 #if MSK_PERM_LUT
     asm("ld.shared.u8 %0, [%1];" : "=r"(inner) : "r"(ac.lut + (s.octinv << 8) + (hitmask >> 24)));
 #else
@@ -338,7 +347,7 @@ __device__ __forceinline__ bool tri_step(const Accel &ac, Traversal &s) {
 template <bool ANY, bool STATS>
 __device__ __forceinline__ void traverse_one(const Accel &ac, Traversal &s, TravStack &stack) {
     for (;;) {
-        if (s.ngroup.y > 0x00ffffffu) node_step<STATS>(ac, s, stack);
+        if (s.ngroup.y > 0x00ffffffu) node_step<STATS, !(ANY && MSK_ANY_UNORDERED)>(ac, s, stack);
         else { s.tgroup = s.ngroup; s.ngroup = make_uint2(0u, 0u); }
         bool stop = false;
         while (s.tgroup.y) {
@@ -506,7 +515,7 @@ __device__ __forceinline__ void trace_queue(const Accel &ac, uint2 *shared_stack
             }
             if (busy && s.ngroup.y > 0x00ffffffu) {
                 if (s.tgroup.y) stack.store(s.sp++, s.tgroup); // postponed triangles wait on the stack
-                node_step<STATS>(ac, s, stack);
+                node_step<STATS, !(ANY && MSK_ANY_UNORDERED)>(ac, s, stack);
             }
         }
         // ---- triangle phase
