@@ -251,6 +251,10 @@ struct Traversal {
 
 constexpr int kTriThreshold = MSK_TRI_THRESHOLD; // run a triangle phase once this many lanes have triangles pending
 constexpr int kRefillMin    = MSK_REFILL_MIN;
+#ifndef MSK_REFILL_MIN_ANY
+#define MSK_REFILL_MIN_ANY MSK_REFILL_MIN /* any-hit queries end early and refill more often: their own threshold */
+#endif
+constexpr int kRefillMinAny = MSK_REFILL_MIN_ANY;
 
 // Visit the next pending inner node of s.ngroup: pushes what remains of the group, tests the node's 8
 // quantised child boxes, leaves the children hit in s.ngroup and the triangles hit in s.tgroup.
@@ -493,7 +497,7 @@ __device__ __forceinline__ void trace_queue(const Accel &ac, uint2 *shared_stack
     for (;;) {
         // ---- refill
         const uint32_t idle = __ballot_sync(0xffffffffu, !busy);
-        if (__popc(idle) >= kRefillMin) {
+        if (__popc(idle) >= (ANY ? kRefillMinAny : kRefillMin)) {
             io.commit(have, q, s);
             have = false;
             const bool start = !busy && nq != 0xffffffffu;
