@@ -231,7 +231,7 @@ __global__ void __launch_bounds__(128, MSK_TRAV_MIN_BLOCKS) k_intersect(const __
     const Accel ac{ sc.nodes, sc.tris, sc.k47, perm_lut_init(msk_s_perm) };
     Ctrl *c = pool.ctrl;
     IntersectIO<STATS> io{ pool, pool.rays[cur], &sc, perm };
-    trace_queue<false, STATS>(ac, msk_s_stack, c->n_rays[cur], &c->cursor_isect, io, coherent != 0);
+    trace_queue<false, STATS>(ac, MSK_TRAV_SMEM, c->n_rays[cur], &c->cursor_isect, io, coherent != 0);
     if (STATS) add_traversal_stats(&c->nodes_closest, &c->tris_closest, io.cn_total, io.ct_total);
 }
 
@@ -896,7 +896,7 @@ __global__ void __launch_bounds__(128, MSK_TRAV_MIN_BLOCKS) k_shadow(const __gri
     const Accel ac{ sc.nodes, sc.tris, sc.k47, perm_lut_init(msk_s_perm) };
     Ctrl *c = pool.ctrl;
     ShadowIO<STATS> io{ pool };
-    trace_queue<true, STATS>(ac, msk_s_stack, c->n_shadow, &c->cursor_shadow, io, coherent != 0);
+    trace_queue<true, STATS>(ac, MSK_TRAV_SMEM, c->n_shadow, &c->cursor_shadow, io, coherent != 0);
     if (STATS) add_traversal_stats(&c->nodes_shadow, &c->tris_shadow, io.cn_total, io.ct_total);
 }
 
@@ -1184,7 +1184,7 @@ __global__ void __launch_bounds__(128, MSK_TRAV_MIN_BLOCKS) k_query_closest(cons
     MSK_TRAV_SHARED;
     const Accel ac{ sc.nodes, sc.tris, sc.k47, perm_lut_init(msk_s_perm) };
     QueryClosestIO<STATS> io{ rays, hits, nnodes, ntris };
-    trace_queue<false, STATS>(ac, msk_s_stack, n, cursor, io, false);
+    trace_queue<false, STATS>(ac, MSK_TRAV_SMEM, n, cursor, io, false);
 }
 
 struct QueryAnyIO {
@@ -1204,7 +1204,7 @@ __global__ void __launch_bounds__(128, MSK_TRAV_MIN_BLOCKS) k_query_any(const __
     MSK_TRAV_SHARED;
     const Accel ac{ sc.nodes, sc.tris, sc.k47, perm_lut_init(msk_s_perm) };
     QueryAnyIO io{ rays, occ };
-    trace_queue<true, false>(ac, msk_s_stack, n, cursor, io, false);
+    trace_queue<true, false>(ac, MSK_TRAV_SMEM, n, cursor, io, false);
 }
 
 template <typename T> cudaError_t dalloc(T **p, size_t n) { return cudaMalloc((void **) p, std::max<size_t>(n, 1) * sizeof(T)); }

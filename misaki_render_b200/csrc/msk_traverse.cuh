@@ -18,9 +18,10 @@ constexpr int kStackSize = 64; // node groups + postponed triangle groups: at mo
 // Lockstep driver: idle lanes are refilled once at least this many lanes of the warp are idle (or none is busy).
 // begin() -- reciprocal direction, octant, the nine coefficients of the watertight shear -- is ~100 instructions; run
 // for two or three lanes at a time it cost a quarter of the warp's issue slots (round-1 profile: 17.6 of 32 lanes
-// active per instruction).
+// active per instruction).  With the shared-memory pool of prepared rays (MSK_RAY_POOL) a refill is five 128-bit
+// shared loads and the threshold that measures best drops from 8 to 4-6 (profiles/r03b_ab_raypool_refill.txt).
 #ifndef MSK_REFILL_MIN
-#define MSK_REFILL_MIN 8
+#define MSK_REFILL_MIN 4
 #endif
 // Entries of the traversal stack kept in shared memory (per lane; the rest spills to local memory).  0: all local.
 #ifndef MSK_SMEM_STACK
@@ -56,10 +57,44 @@ constexpr int kStackSize = 64; // node groups + postponed triangle groups: at mo
 #define MSK_TRI_THRESHOLD 12
 #endif
 
+// Packed FP32 (sm_100: fma / add / mul .f32x2 on a 64-bit register pair, one issue slot for two lanes' worth of IEEE
+// operations): the two plane parameters of a child box per axis (near, far) and the two sheared coordinates of a
+// triangle vertex (x, y) are computed pairwise.  Every element is the same round-to-nearest operation on the same
+// operands as the scalar code, so hits and films are bit-identical; the node test drops from 48 FFMA to 24 FFMA2
+// (243 -> 226 SASS instructions per node visit).  MEASURED SLOWER and therefore off: the 64-bit register pairs cost
+// 8-50 B of spills under the 80-register cap of the traversal kernels and the FMA pipe was never the bound (ALU pipe:
+// PRMT / FMNMX / FSETP); C2 closest hit 5.04 -> 5.07 ms, C3 145.0 -> 147.7 ms (profiles/r03a_ab_f32x2_raypool.txt).
+#ifndef MSK_F32X2
+#define MSK_F32X2 0
+#endif
+
 struct RayHit {
     float t, u, v;
     uint32_t prim, geom;
 };
+
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pack2(float lo, float hi) {
+    f32x2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpack2(f32x2 v, float &lo, float &hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+    f32x2 r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
+    f32x2 r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) {
+    f32x2 r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
 
 // Per-ray constants of the watertight test.  Woop et al. permute the axes so that the dominant direction
 // component becomes z and shear the translated vertices: Ax = A[kx] - sx A[kz], Ay = A[ky] - sy A[kz],
@@ -104,9 +139,19 @@ __device__ __forceinline__ bool woop_intersect(const WoopRay &w, float ox, float
     const float ax = v0.x - ox, ay = v0.y - oy, az = v0.z - oz;
     const float bx = v1.x - ox, by = v1.y - oy, bz = v1.z - oz;
     const float cx = v2.x - ox, cy = v2.y - oy, cz = v2.z - oz;
+#if MSK_F32X2
+    float Ax, Ay, Bx, By, Cx, Cy;
+    {
+        const f32x2 mx = pack2(w.mxx, w.myx), my = pack2(w.mxy, w.myy), mz = pack2(w.mxz, w.myz); // register pairs, no moves
+        unpack2(fma2(mx, pack2(ax, ax), fma2(my, pack2(ay, ay), mul2(mz, pack2(az, az)))), Ax, Ay);
+        unpack2(fma2(mx, pack2(bx, bx), fma2(my, pack2(by, by), mul2(mz, pack2(bz, bz)))), Bx, By);
+        unpack2(fma2(mx, pack2(cx, cx), fma2(my, pack2(cy, cy), mul2(mz, pack2(cz, cz)))), Cx, Cy);
+    }
+#else
     const float Ax = fmaf(w.mxx, ax, fmaf(w.mxy, ay, w.mxz * az)), Ay = fmaf(w.myx, ax, fmaf(w.myy, ay, w.myz * az));
     const float Bx = fmaf(w.mxx, bx, fmaf(w.mxy, by, w.mxz * bz)), By = fmaf(w.myx, bx, fmaf(w.myy, by, w.myz * bz));
     const float Cx = fmaf(w.mxx, cx, fmaf(w.mxy, cy, w.mxz * cz)), Cy = fmaf(w.myx, cx, fmaf(w.myy, cy, w.myz * cz));
+#endif
     // edge functions: explicit round-to-nearest mul/sub (never contracted to FMA) so that a shared edge gives
     // exact negatives in the two triangles
     float U = __fsub_rn(__fmul_rn(Cx, By), __fmul_rn(Cy, Bx));
@@ -208,10 +253,24 @@ struct TravStack {
         return v;
     }
 };
+// Lockstep driver: rays are prepared (begin(): reciprocal direction, octant, watertight shear -- ~100 instructions) by ALL
+// 32 lanes of a warp at once, 32 rays at a time, into a per-warp pool in shared memory; an idle lane then takes a prepared
+// ray with five 128-bit shared loads.  0: every lane prefetches its own next ray and runs begin() when it refills (with
+// the 8-12 lanes that are idle at that moment).  The raw rays of the NEXT fill sit in registers (their loads are in
+// flight while the pool is consumed).  Which lane traces which ray changes nothing in a ray's result: films are
+// bit-identical (profiles/r03a_film_hash_bit_identity.txt).  C2 1494 -> 1538 Mpaths/s (closest hit 5.05 -> 4.85 ms, any
+// hit 2.37 -> 2.23), C3 922 -> 938, C5 sweep 17.54 -> 16.52 ms (incoherent closest hit 2.94 -> 3.10 Grays/s), fog
+// workload 360 -> 370 (profiles/r03b_ab_raypool_refill.txt).  10 KB of shared memory per CTA.
+#ifndef MSK_RAY_POOL
+#define MSK_RAY_POOL 1
+#endif
+constexpr int kPoolSlotFloat4s = 5; // 80 B per prepared ray: 128-bit accesses at this stride are bank-conflict-free
 #define MSK_TRAV_LOCAL_STACK uint2 msk_local_stack[msk::kLocalStack > 0 ? msk::kLocalStack : 1]
 #define MSK_TRAV_SHARED                                                        \
     __shared__ uint8_t msk_s_perm[msk::kPermLutBytes];                           \
-    __shared__ uint2 msk_s_stack[msk::kSmemStack ? msk::kSmemStack * msk::kTravThreads : 1]
+    __shared__ uint2 msk_s_stack[msk::kSmemStack ? msk::kSmemStack * msk::kTravThreads : 1]; \
+    __shared__ float4 msk_s_pool[MSK_RAY_POOL ? msk::kPoolSlotFloat4s * msk::kTravThreads : 1]
+#define MSK_TRAV_SMEM msk_s_stack, msk_s_pool
 
 // Per-lane traversal state.  A lane owns one ray at a time; the warp refills idle lanes from the queue
 // (dynamic fetch, Aila & Laine 2009) instead of waiting for its slowest ray.
@@ -237,12 +296,33 @@ struct Traversal {
         const uint32_t oct = (idx < 0.f ? 4u : 0u) | (idy < 0.f ? 2u : 0u) | (idz < 0.f ? 1u : 0u);
         octinv = 7u - oct;
         wr = woop_setup(rd.x, rd.y, rd.z);
+        reset();
+    }
+    __device__ __forceinline__ void reset() {
         ngroup = make_uint2(0u, 0x80000000u); // root: "child slot 7 of a virtual parent at base 0"
         tgroup = make_uint2(0u, 0u);
         sp = 0;
         found = false;
         hit.t = __int_as_float(0x7f800000); hit.u = 0.f; hit.v = 0.f; hit.prim = 0xffffffffu; hit.geom = 0xffffffffu;
         cnt_nodes = 0; cnt_tris = 0;
+    }
+    // the per-ray constants that begin() derives, as one 80-byte record (the lockstep driver's shared-memory ray pool)
+    __device__ __forceinline__ void save(float4 *slot, uint32_t q) const {
+        slot[0] = make_float4(ox, oy, oz, tmin);
+        slot[1] = make_float4(idx, idy, idz, tfar0);
+        slot[2] = make_float4(wr.mxx, wr.mxy, wr.mxz, wr.myx);
+        slot[3] = make_float4(wr.myy, wr.myz, wr.mzx, wr.mzy);
+        slot[4] = make_float4(wr.mzz, __uint_as_float(q), __uint_as_float(octinv), 0.f);
+    }
+    __device__ __forceinline__ uint32_t restore(const float4 *slot) {
+        const float4 a = slot[0], b = slot[1], c = slot[2], d = slot[3], e = slot[4];
+        ox = a.x; oy = a.y; oz = a.z; tmin = a.w;
+        idx = b.x; idy = b.y; idz = b.z; tmax = b.w; tfar0 = b.w;
+        wr.mxx = c.x; wr.mxy = c.y; wr.mxz = c.z; wr.myx = c.w;
+        wr.myy = d.x; wr.myz = d.y; wr.mzx = d.z; wr.mzy = d.w;
+        wr.mzz = e.x; octinv = __float_as_uint(e.z);
+        reset();
+        return __float_as_uint(e.y);
     }
     // Scene::ray_intersect / ray_test report a hit iff Embree moved tfar (scene.cpp:234,272): a hit at
     // exactly t == maxt reads as a miss
@@ -289,7 +369,12 @@ __device__ __forceinline__ void node_step(const Accel &ac, Traversal &s, TravSta
     const float aox = fmaf(-32768.f, adx, (n0.x - s.ox) * s.idx), aoy = fmaf(-32768.f, ady, (n0.y - s.oy) * s.idy),
                 aoz = fmaf(-32768.f, adz, (n0.z - s.oz) * s.idz);
     const float ex = fabsf(adx) * 0.00390625f, ey = fabsf(ady) * 0.00390625f, ez = fabsf(adz) * 0.00390625f;
+#if MSK_F32X2
+    const f32x2 nfx = add2(pack2(aox, aox), pack2(-ex, ex)), nfy = add2(pack2(aoy, aoy), pack2(-ey, ey)), nfz = add2(pack2(aoz, aoz), pack2(-ez, ez));
+    const f32x2 adx2 = pack2(adx, adx), ady2 = pack2(ady, ady), adz2 = pack2(adz, adz);
+#else
     const float nox = aox - ex, fox = aox + ex, noy = aoy - ey, foy = aoy + ey, noz = aoz - ez, foz = aoz + ez;
+#endif
     const uint32_t k47 = ac.k47;
     s.ngroup.x = __float_as_uint(n1.x);
     s.tgroup.x = __float_as_uint(n1.y);
@@ -303,17 +388,28 @@ __device__ __forceinline__ void node_step(const Accel &ac, Traversal &s, TravSta
         const uint32_t nx = negx ? qhix : qlox, fx = negx ? qlox : qhix;
         const uint32_t ny = negy ? qhiy : qloy, fy = negy ? qloy : qhiy;
         const uint32_t nzq = negz ? qhiz : qloz, fz = negz ? qloz : qhiz;
-#define MSK_CHILD(J)                                                                                              \
-    {                                                                                                             \
+#if MSK_F32X2
+#define MSK_CHILD_PLANES(J)                                                                                       \
+        float t0x, t1x, t0y, t1y, t0z, t1z;                                                                       \
+        unpack2(fma2(pack2(qfloat<J>(nx, k47), qfloat<J>(fx, k47)), adx2, nfx), t0x, t1x);                        \
+        unpack2(fma2(pack2(qfloat<J>(ny, k47), qfloat<J>(fy, k47)), ady2, nfy), t0y, t1y);                        \
+        unpack2(fma2(pack2(qfloat<J>(nzq, k47), qfloat<J>(fz, k47)), adz2, nfz), t0z, t1z);
+#else
+#define MSK_CHILD_PLANES(J)                                                                                       \
         const float t0x = fmaf(qfloat<J>(nx, k47), adx, nox), t1x = fmaf(qfloat<J>(fx, k47), adx, fox);           \
         const float t0y = fmaf(qfloat<J>(ny, k47), ady, noy), t1y = fmaf(qfloat<J>(fy, k47), ady, foy);           \
-        const float t0z = fmaf(qfloat<J>(nzq, k47), adz, noz), t1z = fmaf(qfloat<J>(fz, k47), adz, foz);          \
+        const float t0z = fmaf(qfloat<J>(nzq, k47), adz, noz), t1z = fmaf(qfloat<J>(fz, k47), adz, foz);
+#endif
+#define MSK_CHILD(J)                                                                                              \
+    {                                                                                                             \
+        MSK_CHILD_PLANES(J)                                                                                       \
         const float tn = fmaxf(fmaxf(t0x, t0y), fmaxf(t0z, s.tmin));                                              \
         const float tf = fminf(fminf(t1x, t1y), fminf(t1z, s.tmax));                                              \
         if (tn <= tf) hitmask |= (1u << (24 + 4 * h + J)) | (7u << (3 * (4 * h + J)));                            \
     }
         MSK_CHILD(0) MSK_CHILD(1) MSK_CHILD(2) MSK_CHILD(3)
 #undef MSK_CHILD
+#undef MSK_CHILD_PLANES
     }
     hitmask &= __float_as_uint(n1.z); // valid: imask << 24 | bit 3j + k for triangle k of the leaf in slot j
     uint32_t inner;
@@ -434,7 +530,7 @@ __device__ __forceinline__ void trace_queue_static(const Accel &ac, uint32_t n, 
 }
 
 template <bool ANY, bool STATS, typename IO>
-__device__ __forceinline__ void trace_queue(const Accel &ac, uint2 *shared_stack, uint32_t n, uint32_t *cursor, IO &io, bool coherent) {
+__device__ __forceinline__ void trace_queue(const Accel &ac, uint2 *shared_stack, float4 *shared_pool, uint32_t n, uint32_t *cursor, IO &io, bool coherent) {
     // Coherent queues (camera rays: neighbouring lanes follow the same nodes, so a static warp of 32 runs
     // converged and its node fetches coalesce) and queues too small to fill the machine (latency-bound: more,
     // shorter warps win) use the static assignment; incoherent bulk queues use the lockstep phases.
@@ -460,6 +556,56 @@ __device__ __forceinline__ void trace_queue(const Accel &ac, uint2 *shared_stack
     // prefetched next ray of this lane
     float4 nro = make_float4(0, 0, 0, 0), nrd = make_float4(0, 0, 0, 0);
     uint32_t nq = 0xffffffffu;             // 0xffffffff: none
+#if MSK_RAY_POOL
+    // The warp's pool of prepared rays [pool_head, pool_count) in shared memory, and in registers (nq, nro, nrd) the 32 raw
+    // rays the next fill will prepare -- their loads are in flight while the pool is being consumed.
+    float4 *const pool_w = shared_pool + (threadIdx.x & ~31u) * kPoolSlotFloat4s;
+    uint32_t pool_head = 0, pool_count = 0; // warp-uniform
+    bool more = true;                       // warp-uniform: the global queue may still hold rays
+    auto fetch_raw = [&]() {                // all lanes
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(cursor, 32u);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (base >= n) { more = false; nq = 0xffffffffu; return; }
+        nq = n - base > lane ? base + lane : 0xffffffffu;
+        if (nq != 0xffffffffu) io.load(nq, nro, nrd);
+    };
+    auto fill = [&]() { // all lanes, pool empty: prepare the raw rays (a prefix of the lanes holds one), fetch the next 32
+        pool_head = 0;
+        pool_count = (uint32_t) __popc(__ballot_sync(0xffffffffu, nq != 0xffffffffu));
+        __syncwarp(); // every lane has finished reading its slot of the previous fill
+        if (nq != 0xffffffffu) {
+            Traversal p;
+            p.begin(nro, nrd);
+            p.save(pool_w + lane * kPoolSlotFloat4s, nq);
+        }
+        __syncwarp();
+        if (more) fetch_raw(); else nq = 0xffffffffu;
+    };
+    fetch_raw();
+    for (;;) {
+        // ---- refill
+        const uint32_t idle = __ballot_sync(0xffffffffu, !busy);
+        if (__popc(idle) >= (ANY ? kRefillMinAny : kRefillMin)) {
+            io.commit(have, q, s);
+            have = false;
+            uint32_t want = idle;
+            for (;;) {
+                if (pool_head == pool_count) {
+                    if (__ballot_sync(0xffffffffu, nq != 0xffffffffu) == 0u) break; // queue exhausted
+                    fill();
+                }
+                const uint32_t avail = pool_count - pool_head;
+                const uint32_t rank = (uint32_t) __popc(want & below);
+                const bool take = ((want >> lane) & 1u) && rank < avail;
+                if (take) { q = s.restore(pool_w + (pool_head + rank) * kPoolSlotFloat4s); busy = true; }
+                pool_head += min((uint32_t) __popc(want), avail);
+                want &= ~__ballot_sync(0xffffffffu, take);
+                if (!want) break;
+            }
+            if (__ballot_sync(0xffffffffu, busy) == 0u) break;
+        }
+#else
     uint32_t chunk_next = 0, chunk_end = 0; // warp-uniform
     bool more = true;                       // warp-uniform: the global queue may still hold rays
 
@@ -509,6 +655,7 @@ __device__ __forceinline__ void trace_queue(const Accel &ac, uint2 *shared_stack
             }
             if (__ballot_sync(0xffffffffu, busy) == 0u) break;
         }
+#endif
         // ---- node phase
 #pragma unroll
         for (int rep = 0; rep < MSK_NODE_STEPS; ++rep) {

@@ -13,7 +13,7 @@ for cfg in "$@"; do
   lib=$PWD/misaki_render_b200/lib/libmisaki_b200.so
   [ -n "${variant:-}" ] && lib=$PWD/build/variants/$variant/libmisaki_b200.so
   printf '%-28s' "$name"
-  env $envs MSK_B200_LIB=$lib python bench.py --workload $wl --steps ${STEPS:-8} --warmup 3 --no-cpu 2> gpurun_out/ab_$name.err | tee gpurun_out/ab_$name.json | python -c "
+  env $envs MSK_B200_LIB=$lib timeout ${BENCH_TIMEOUT:-240} python bench.py --workload $wl --steps ${STEPS:-8} --warmup 3 --no-cpu 2> gpurun_out/ab_$name.err | tee gpurun_out/ab_$name.json | python -c "
 import json,sys
 d=json.loads(sys.stdin.read()); r=d['roofline']
 print('M/s %.1f  ms/step %.2f  launches %d  stages %s' % (d['value']/1e6, d['ms_per_step'], d.get('gpu_launches',0), {k: round(v,2) for k,v in r.get('stage_ms', r.get('launch_ms')).items()}))" || tail -3 gpurun_out/ab_$name.err
