@@ -310,8 +310,11 @@ def kernel_roofline(kernel: str, ms: float, launches: int, alg_bytes: float, cou
         out.update(bound="issue", achieved=out["issue"]["gwarp_inst_per_s"], peak=issue_peak, unit="Gwarp-inst/s", frac=fi)
     elif fh is not None:
         out.update(bound="hbm", achieved=out["hbm"]["dram_gbs"], peak=hbm_peak, unit="GB/s", frac=fh)
-    else:  # no counters: the algorithmic-traffic rate is all that can be stated
-        out.update(bound="hbm", achieved=alg, peak=hbm_peak, unit="GB/s", frac=alg / hbm_peak)
+    else:  # no counters of THIS source tree: every traversal / shade kernel measured so far is issue-bound at 3-40 % DRAM
+        # utilisation (profiles/*ncu*), so the algorithmic-traffic rate above must not be presented as an HBM fraction
+        out.update(bound="issue", achieved=None, peak=issue_peak, unit="Gwarp-inst/s", frac=None,
+                   note="no ncu counters for this source tree (tools/ncu_counters.py): issue / DRAM fractions not stated; "
+                        "hbm.algorithmic_* is the SURVEY 8(d) traffic model, served mostly by L1/L2")
     out["traffic"] = out["hbm"].get("dram_bytes_per_launch")
     return out
 
