@@ -63,7 +63,6 @@ struct Pool {
     float4  *L;                     // accumulated radiance per path of the batch
     MskRay  *sh_ray;
     float4  *sh_contrib;
-    uint32_t *sh_path;
     float4  *rec;                   // X, Y, Z, pos.x
     float   *rec_py;
     uint32_t *sorted;               // kNumKeys segments of `capacity` queue indices
@@ -201,6 +200,7 @@ struct IntersectIO {
         const float4 *rp = reinterpret_cast<const float4 *>(rays + q);
         ro = __ldcs(rp); rd = __ldcs(rp + 1);
     }
+    __device__ __forceinline__ uint32_t tag(float4 &) const { return 0u; }
     __device__ __forceinline__ void commit(bool have, uint32_t q, const Traversal &s) {
         if (perm && have) q = __ldg(perm + q);
 #if MSK_SORT_IN_COMMIT
@@ -421,7 +421,7 @@ __device__ __forceinline__ void shade_vertex(const DScene &sc, const BatchParams
                 if (!is_zero(contrib)) {
                     emit_shadow = true;
                     sray.o[0] = sf.p.x; sray.o[1] = sf.p.y; sray.o[2] = sf.p.z;
-                    sray.tmin = kRayEpsilon * (1.f + max_abs(sf.p));
+                    sray.tmin = shadow_tmin(sf.p.x, sf.p.y, sf.p.z);
                     sray.d[0] = ns.d.x; sray.d[1] = ns.d.y; sray.d[2] = ns.d.z;
                     sray.tmax = ns.dist * (1.f - kShadowEpsilon);
                 }
@@ -516,10 +516,9 @@ __global__ void __launch_bounds__(128, shade_min_blocks(KEY)) k_shade(const __gr
         if (emit_shadow) {
             uint32_t o = base_sh + __popc(m_sh & below);
             float4 *rp = reinterpret_cast<float4 *>(pool.sh_ray + o);
-            rp[0] = make_float4(sray.o[0], sray.o[1], sray.o[2], sray.tmin);
+            rp[0] = make_float4(sray.o[0], sray.o[1], sray.o[2], __uint_as_float(path)); // tmin = shadow_tmin(o): ShadowIO::tag
             rp[1] = make_float4(sray.d[0], sray.d[1], sray.d[2], sray.tmax);
             pool.sh_contrib[o] = contrib;
-            pool.sh_path[o]    = path;
         }
     }
 }
@@ -602,7 +601,7 @@ __device__ __forceinline__ void shade_vertex_vol(const DScene &sc, const BatchPa
             if (!is_zero(contrib)) {
                 emit_shadow = true;
                 sray.o[0] = msp.x; sray.o[1] = msp.y; sray.o[2] = msp.z;
-                sray.tmin = kRayEpsilon * (1.f + max_abs(msp)); // scaled like scene.cpp:91-93 (see oracle.cpp, volpath notes)
+                sray.tmin = shadow_tmin(msp.x, msp.y, msp.z); // scaled like scene.cpp:91-93 (see oracle.cpp, volpath notes)
                 sray.d[0] = ns.d.x; sray.d[1] = ns.d.y; sray.d[2] = ns.d.z;
                 sray.tmax = ns.dist * (1.f - kShadowEpsilon);
             }
@@ -663,7 +662,7 @@ __device__ __forceinline__ void shade_vertex_vol(const DScene &sc, const BatchPa
                 if (!is_zero(contrib)) {
                     emit_shadow = true;
                     sray.o[0] = sf.p.x; sray.o[1] = sf.p.y; sray.o[2] = sf.p.z;
-                    sray.tmin = kRayEpsilon * (1.f + max_abs(sf.p));
+                    sray.tmin = shadow_tmin(sf.p.x, sf.p.y, sf.p.z);
                     sray.d[0] = ns.d.x; sray.d[1] = ns.d.y; sray.d[2] = ns.d.z;
                     sray.tmax = ns.dist * (1.f - kShadowEpsilon);
                 }
@@ -765,10 +764,9 @@ __global__ void __launch_bounds__(128, MSK_VOL_MIN_BLOCKS) k_shade_vol(const __g
         if (emit_shadow) {
             uint32_t o = base_sh + __popc(m_sh & below);
             float4 *rp = reinterpret_cast<float4 *>(pool.sh_ray + o);
-            rp[0] = make_float4(sray.o[0], sray.o[1], sray.o[2], sray.tmin);
+            rp[0] = make_float4(sray.o[0], sray.o[1], sray.o[2], __uint_as_float(path)); // tmin = shadow_tmin(o): ShadowIO::tag
             rp[1] = make_float4(sray.d[0], sray.d[1], sray.d[2], sray.tmax);
             pool.sh_contrib[o] = contrib;
-            pool.sh_path[o]    = path;
         }
     }
 }
@@ -879,13 +877,20 @@ struct ShadowIO {
         const float4 *rp = reinterpret_cast<const float4 *>(pool.sh_ray + q);
         ro = __ldcs(rp); rd = __ldcs(rp + 1);
     }
+    // The queue record carries the path index where the ray's tmin would be: every producer sets tmin to the spawn offset
+    // of its origin (shadow_tmin), which is recomputed here, so commit() has the address of L[path] without a dependent
+    // load (ncu: the sh_path -> L[path] chain was 11 % of the stall samples of the bounce-0 launch, profiles/r03d_ncu_k_shadow_b0.txt).
+    __device__ __forceinline__ uint32_t tag(float4 &ro) const {
+        const uint32_t path = __float_as_uint(ro.w);
+        ro.w = shadow_tmin(ro.x, ro.y, ro.z);
+        return path;
+    }
     __device__ __forceinline__ void commit(bool have, uint32_t q, const Traversal &s) {
         if (!have) return;
         if (STATS) { cn_total += s.cnt_nodes; ct_total += s.cnt_tris; }
         if (!s.is_hit()) { // unoccluded (scene.cpp:272): one shadow ray per path and bounce, so no atomics
-            const uint32_t path = pool.sh_path[q];
-            const float4 acc = pool.L[path];
-            pool.L[path] = acc + __ldcs(pool.sh_contrib + q);
+            const float4 acc = pool.L[s.tag];
+            pool.L[s.tag] = acc + __ldcs(pool.sh_contrib + q);
         }
     }
 };
@@ -1164,6 +1169,7 @@ struct QueryClosestIO {
         const float4 *rp = reinterpret_cast<const float4 *>(rays + q);
         ro = __ldcs(rp); rd = __ldcs(rp + 1);
     }
+    __device__ __forceinline__ uint32_t tag(float4 &) const { return 0u; }
     __device__ __forceinline__ void commit(bool have, uint32_t q, const Traversal &s) {
         if (!have) return;
         if (STATS) { nnodes[q] = s.cnt_nodes; ntris[q] = s.cnt_tris; }
@@ -1194,6 +1200,7 @@ struct QueryAnyIO {
         const float4 *rp = reinterpret_cast<const float4 *>(rays + q);
         ro = __ldcs(rp); rd = __ldcs(rp + 1);
     }
+    __device__ __forceinline__ uint32_t tag(float4 &) const { return 0u; }
     __device__ __forceinline__ void commit(bool have, uint32_t q, const Traversal &s) {
         if (have) occ[q] = s.is_hit() ? 1 : 0;
     }
@@ -1261,7 +1268,7 @@ struct Renderer::Impl {
         for (int l = 0; l < kMaxLanes; ++l) {
             Pool &p = lanes[l].pool;
             for (int i = 0; i < 2; ++i) { cudaFree(p.rays[i]); cudaFree(p.T[i]); cudaFree(p.WL[i]); cudaFree(p.AUX[i]); cudaFree(p.MISC[i]); }
-            cudaFree(p.hit); cudaFree(p.hit_geom); cudaFree(p.L); cudaFree(p.sh_ray); cudaFree(p.sh_contrib); cudaFree(p.sh_path);
+            cudaFree(p.hit); cudaFree(p.hit_geom); cudaFree(p.L); cudaFree(p.sh_ray); cudaFree(p.sh_contrib);
             cudaFree(p.sorted); cudaFree(p.rec); cudaFree(p.rec_py); cudaFree(p.ctrl); cudaFree(p.aov);
             for (int i = 0; i < 2; ++i) { cudaFree(p.rs_keys[i]); cudaFree(p.rs_vals[i]); }
             p = Pool{};
@@ -1386,7 +1393,7 @@ int Renderer::ensure_pool(uint32_t capacity, int count) {
             MSK_CUDA_CHECK(dalloc(&p.AUX[i], n)); MSK_CUDA_CHECK(dalloc(&p.MISC[i], n));
         }
         MSK_CUDA_CHECK(dalloc(&p.hit, n)); MSK_CUDA_CHECK(dalloc(&p.hit_geom, n)); MSK_CUDA_CHECK(dalloc(&p.L, n));
-        MSK_CUDA_CHECK(dalloc(&p.sh_ray, n)); MSK_CUDA_CHECK(dalloc(&p.sh_contrib, n)); MSK_CUDA_CHECK(dalloc(&p.sh_path, n));
+        MSK_CUDA_CHECK(dalloc(&p.sh_ray, n)); MSK_CUDA_CHECK(dalloc(&p.sh_contrib, n));
         MSK_CUDA_CHECK(dalloc(&p.sorted, n * kNumKeys)); MSK_CUDA_CHECK(dalloc(&p.rec, n)); MSK_CUDA_CHECK(dalloc(&p.rec_py, n));
         MSK_CUDA_CHECK(dalloc(&p.ctrl, 1));
         MSK_CUDA_CHECK(cudaMemset(p.ctrl, 0, sizeof(Ctrl)));

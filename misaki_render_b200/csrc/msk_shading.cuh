@@ -44,6 +44,9 @@ __device__ __forceinline__ bool is_zero(float4 a) { return a.x == 0.f && a.y == 
 constexpr float kPi = 3.14159265358979323846f, kInvPi = 0.31830988618379067154f, kInvFourPi = 0.07957747154594766788f;
 constexpr float kEpsilon = 5.9604644775390625e-08f;          // mathutils.h:16-17 (epsilon/2)
 constexpr float kRayEpsilon = kEpsilon * 1500, kShadowEpsilon = kRayEpsilon * 10; // mathutils.h:19-20
+// tmin of a visibility ray spawned at o (interaction.h:40-44 scaled as scene.cpp:91-93).  A function of the origin alone: the
+// shadow queue stores the path index in the ray record's tmin field and k_shadow recomputes this value (ShadowIO::tag).
+__device__ __forceinline__ float shadow_tmin(float ox, float oy, float oz) { return kRayEpsilon * (1.f + max_abs(v3(ox, oy, oz))); }
 #define MSK_INF __int_as_float(0x7f800000)
 
 __device__ __forceinline__ float sqr(float a) { return a * a; }

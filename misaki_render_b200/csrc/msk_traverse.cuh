@@ -285,6 +285,7 @@ struct Traversal {
     RayHit hit;
     bool found;
     uint32_t cnt_nodes, cnt_tris;
+    uint32_t tag; // a word the IO adaptor attaches to the ray when it is loaded (IO::tag) and reads back in commit()
 
     __device__ __forceinline__ void begin(float4 ro, float4 rd) {
         ox = ro.x; oy = ro.y; oz = ro.z; tmin = ro.w;
@@ -312,7 +313,7 @@ struct Traversal {
         slot[1] = make_float4(idx, idy, idz, tfar0);
         slot[2] = make_float4(wr.mxx, wr.mxy, wr.mxz, wr.myx);
         slot[3] = make_float4(wr.myy, wr.myz, wr.mzx, wr.mzy);
-        slot[4] = make_float4(wr.mzz, __uint_as_float(q), __uint_as_float(octinv), 0.f);
+        slot[4] = make_float4(wr.mzz, __uint_as_float(q), __uint_as_float(octinv), __uint_as_float(tag));
     }
     __device__ __forceinline__ uint32_t restore(const float4 *slot) {
         const float4 a = slot[0], b = slot[1], c = slot[2], d = slot[3], e = slot[4];
@@ -320,7 +321,7 @@ struct Traversal {
         idx = b.x; idy = b.y; idz = b.z; tmax = b.w; tfar0 = b.w;
         wr.mxx = c.x; wr.mxy = c.y; wr.mxz = c.z; wr.myx = c.w;
         wr.myy = d.x; wr.myz = d.y; wr.mzx = d.z; wr.mzy = d.w;
-        wr.mzz = e.x; octinv = __float_as_uint(e.z);
+        wr.mzz = e.x; octinv = __float_as_uint(e.z); tag = __float_as_uint(e.w);
         reset();
         return __float_as_uint(e.y);
     }
@@ -475,6 +476,8 @@ __device__ __forceinline__ bool traverse(const Accel &ac, TravStack &stack, floa
 
 // Persistent-warp driver: every lane pulls rays from the queue [0, n) until it is empty.
 //   io.load(q, ro, rd)                 fetch ray q
+//   io.tag(ro)                         called once per loaded ray before it is set up: may unpack a word the producer stored in
+//                                      the ray record (and restore the field it borrowed); the word is Traversal::tag in commit()
 //   io.commit(have, q, s)              called by ALL 32 lanes converged; lanes with `have` deliver the result
 //                                      of their finished ray q (s.is_hit(), s.hit, s.cnt_*)
 //
@@ -521,6 +524,7 @@ __device__ __forceinline__ void trace_queue_static(const Accel &ac, uint32_t n, 
         if (valid) {
             float4 ro, rd;
             io.load(q, ro, rd);
+            s.tag = io.tag(ro);
             s.begin(ro, rd);
             traverse_one<ANY, STATS>(ac, s, stack);
         }
@@ -576,6 +580,7 @@ __device__ __forceinline__ void trace_queue(const Accel &ac, uint2 *shared_stack
         __syncwarp(); // every lane has finished reading its slot of the previous fill
         if (nq != 0xffffffffu) {
             Traversal p;
+            p.tag = io.tag(nro);
             p.begin(nro, nrd);
             p.save(pool_w + lane * kPoolSlotFloat4s, nq);
         }
@@ -647,7 +652,7 @@ __device__ __forceinline__ void trace_queue(const Accel &ac, uint2 *shared_stack
             io.commit(have, q, s);
             have = false;
             const bool start = !busy && nq != 0xffffffffu;
-            if (start) { q = nq; s.begin(nro, nrd); busy = true; nq = 0xffffffffu; }
+            if (start) { q = nq; s.tag = io.tag(nro); s.begin(nro, nrd); busy = true; nq = 0xffffffffu; }
             const uint32_t want = __ballot_sync(0xffffffffu, start);
             if (want && (more || chunk_next < chunk_end)) {
                 const uint32_t idx = take(want);
@@ -656,45 +661,56 @@ __device__ __forceinline__ void trace_queue(const Accel &ac, uint2 *shared_stack
             if (__ballot_sync(0xffffffffu, busy) == 0u) break;
         }
 #endif
-        // ---- node phase
+        auto node_phase = [&]() {
 #pragma unroll
-        for (int rep = 0; rep < MSK_NODE_STEPS; ++rep) {
-            if (rep > 0 && busy && s.ngroup.y <= 0x00ffffffu && s.tgroup.y == 0u && s.sp > 0) { // next node group, if that is what is on top
-                const uint2 g = stack.load(s.sp - 1);
-                if (g.y > 0x00ffffffu) s.ngroup = g; else s.tgroup = g;
-                --s.sp;
-            }
-            if (busy && s.ngroup.y > 0x00ffffffu) {
-                if (s.tgroup.y) stack.store(s.sp++, s.tgroup); // postponed triangles wait on the stack
-                node_step<STATS, !(ANY && MSK_ANY_UNORDERED)>(ac, s, stack);
-            }
-        }
-        // ---- triangle phase
-        const bool has_t = busy && s.tgroup.y != 0u;
-        const uint32_t mt = __ballot_sync(0xffffffffu, has_t);
-        if (mt) {
-            const bool starved = has_t && s.ngroup.y <= 0x00ffffffu;
-            if (__popc(mt) >= kTriThreshold || __any_sync(0xffffffffu, starved && waited >= MSK_TRI_PATIENCE)) {
-                if (has_t && tri_step<STATS>(ac, s) && ANY) { busy = false; have = true; }
-                // A leaf hit usually leaves two or three triangles pending, and a lane with nothing but triangles
-                // left sits out the node phases in between: up to MSK_TRI_REPS triangles per lane and phase.
-#pragma unroll 1
-                for (int rep = 1; rep < MSK_TRI_REPS; ++rep) {
-                    const bool again = busy && s.tgroup.y != 0u;
-                    if (!__any_sync(0xffffffffu, again)) break;
-                    if (again && tri_step<STATS>(ac, s) && ANY) { busy = false; have = true; }
+            for (int rep = 0; rep < MSK_NODE_STEPS; ++rep) {
+                if (rep > 0 && busy && s.ngroup.y <= 0x00ffffffu && s.tgroup.y == 0u && s.sp > 0) { // next node group, if that is what is on top
+                    const uint2 g = stack.load(s.sp - 1);
+                    if (g.y > 0x00ffffffu) s.ngroup = g; else s.tgroup = g;
+                    --s.sp;
                 }
-                waited = 0;
-            } else if (starved) ++waited;
-        }
-        // ---- pop
-        if (busy && s.ngroup.y <= 0x00ffffffu) {
-            if (s.sp > 0) {
-                const uint2 g = stack.load(s.sp - 1);
-                if (g.y > 0x00ffffffu) { s.ngroup = g; --s.sp; }
-                else if (s.tgroup.y == 0u) { s.tgroup = g; --s.sp; }
-            } else if (s.tgroup.y == 0u) { busy = false; have = true; }
-        }
+                if (busy && s.ngroup.y > 0x00ffffffu) {
+                    if (s.tgroup.y) stack.store(s.sp++, s.tgroup); // postponed triangles wait on the stack
+                    node_step<STATS, !(ANY && MSK_ANY_UNORDERED)>(ac, s, stack);
+                }
+            }
+        };
+        auto tri_phase = [&]() {
+            const bool has_t = busy && s.tgroup.y != 0u;
+            const uint32_t mt = __ballot_sync(0xffffffffu, has_t);
+            if (mt) {
+                const bool starved = has_t && s.ngroup.y <= 0x00ffffffu;
+                if (__popc(mt) >= kTriThreshold || __any_sync(0xffffffffu, starved && waited >= MSK_TRI_PATIENCE)) {
+                    if (has_t && tri_step<STATS>(ac, s) && ANY) { busy = false; have = true; }
+                    // A leaf hit usually leaves two or three triangles pending, and a lane with nothing but triangles
+                    // left sits out the node phases in between: up to MSK_TRI_REPS triangles per lane and phase.
+#pragma unroll 1
+                    for (int rep = 1; rep < MSK_TRI_REPS; ++rep) {
+                        const bool again = busy && s.tgroup.y != 0u;
+                        if (!__any_sync(0xffffffffu, again)) break;
+                        if (again && tri_step<STATS>(ac, s) && ANY) { busy = false; have = true; }
+                    }
+                    waited = 0;
+                } else if (starved) ++waited;
+            }
+        };
+        auto pop_phase = [&]() {
+            if (busy && s.ngroup.y <= 0x00ffffffu) {
+                if (s.sp > 0) {
+                    const uint2 g = stack.load(s.sp - 1);
+                    if (g.y > 0x00ffffffu) { s.ngroup = g; --s.sp; }
+                    else if (s.tgroup.y == 0u) { s.tgroup = g; --s.sp; }
+                } else if (s.tgroup.y == 0u) { busy = false; have = true; }
+            }
+        };
+        // (Tried: triangle -> pop -> node, i.e. the refill vote and the loop head between a node step and the test of the
+        // triangles it found, as lead time for an L1 prefetch of the next triangle -- the wait for the triangle record is the
+        // largest single stall of the kernel, 8 % of the samples.  Per lane the sequence of steps is the same, but a lane that
+        // finishes in the pop phase then sits out a node phase before it is refilled: C2 1558 -> 1500 Mpaths/s, with the
+        // prefetch 1465, C3 948 -> 913 / 900 (profiles/r03e_ab_shadow_tag_rotated_loop.txt).)
+        node_phase();
+        tri_phase();
+        pop_phase();
     }
 }
 
