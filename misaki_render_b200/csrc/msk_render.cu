@@ -225,13 +225,13 @@ struct IntersectIO {
     }
 };
 
-template <bool STATS>
+template <bool STATS, bool PACKETS = false>
 __global__ void __launch_bounds__(128, MSK_TRAV_MIN_BLOCKS) k_intersect(const __grid_constant__ DScene sc, Pool pool, int cur, int coherent, const uint32_t *perm) {
     MSK_TRAV_SHARED;
     const Accel ac{ sc.nodes, sc.tris, sc.k47, perm_lut_init(msk_s_perm) };
     Ctrl *c = pool.ctrl;
     IntersectIO<STATS> io{ pool, pool.rays[cur], &sc, perm };
-    trace_queue<false, STATS>(ac, MSK_TRAV_SMEM, c->n_rays[cur], &c->cursor_isect, io, coherent != 0);
+    trace_queue<false, STATS, PACKETS>(ac, MSK_TRAV_SMEM, c->n_rays[cur], &c->cursor_isect, io, coherent);
     if (STATS) add_traversal_stats(&c->nodes_closest, &c->tris_closest, io.cn_total, io.ct_total);
 }
 
@@ -901,7 +901,7 @@ __global__ void __launch_bounds__(128, MSK_TRAV_MIN_BLOCKS) k_shadow(const __gri
     const Accel ac{ sc.nodes, sc.tris, sc.k47, perm_lut_init(msk_s_perm) };
     Ctrl *c = pool.ctrl;
     ShadowIO<STATS> io{ pool };
-    trace_queue<true, STATS>(ac, MSK_TRAV_SMEM, c->n_shadow, &c->cursor_shadow, io, coherent != 0);
+    trace_queue<true, STATS>(ac, MSK_TRAV_SMEM, c->n_shadow, &c->cursor_shadow, io, coherent);
     if (STATS) add_traversal_stats(&c->nodes_shadow, &c->tris_shadow, io.cn_total, io.ct_total);
 }
 
@@ -1190,7 +1190,7 @@ __global__ void __launch_bounds__(128, MSK_TRAV_MIN_BLOCKS) k_query_closest(cons
     MSK_TRAV_SHARED;
     const Accel ac{ sc.nodes, sc.tris, sc.k47, perm_lut_init(msk_s_perm) };
     QueryClosestIO<STATS> io{ rays, hits, nnodes, ntris };
-    trace_queue<false, STATS>(ac, MSK_TRAV_SMEM, n, cursor, io, false);
+    trace_queue<false, STATS>(ac, MSK_TRAV_SMEM, n, cursor, io, 0);
 }
 
 struct QueryAnyIO {
@@ -1211,7 +1211,7 @@ __global__ void __launch_bounds__(128, MSK_TRAV_MIN_BLOCKS) k_query_any(const __
     MSK_TRAV_SHARED;
     const Accel ac{ sc.nodes, sc.tris, sc.k47, perm_lut_init(msk_s_perm) };
     QueryAnyIO io{ rays, occ };
-    trace_queue<true, false>(ac, MSK_TRAV_SMEM, n, cursor, io, false);
+    trace_queue<true, false>(ac, MSK_TRAV_SMEM, n, cursor, io, 0);
 }
 
 template <typename T> cudaError_t dalloc(T **p, size_t n) { return cudaMalloc((void **) p, std::max<size_t>(n, 1) * sizeof(T)); }
@@ -1246,6 +1246,9 @@ struct Renderer::Impl {
     uint32_t spec_min = 1u << 18;     // MSK_SPEC_MIN: ... while the queue may hold at least this many vertices
     int shadow_static_bounces = 0;    // MSK_SHADOW_STATIC_BOUNCES: bounces whose shadow queue counts as coherent
     int static_bounces = 1;           // MSK_STATIC_BOUNCES: bounces whose closest-hit queue counts as coherent (camera rays)
+    int packet_camera = 1;            // MSK_PACKET_CAMERA: the warps of the camera-ray queue (samples of one pixel group) are traversed as packets
+                                      // (C2 1549 -> 1570 Mpaths/s, C3 946 -> 955, bit-identical films; not for tiny scenes: C4 1802 -> 1797.  Bounce-0
+                                      // shadow rays as packets -- shafts from a pixel's footprint to the light -- were 3x slower, profiles/r03g_ab_packets.txt)
     int debug_bounces = 0;            // MSK_DEBUG_BOUNCES: print polled queue lengths and per-launch stage times to stderr
     uint32_t tail_threshold = 1u << 18; // MSK_TAIL_THRESHOLD: finish an unbounded job with k_tail once the queue is this short (0: never)
     int tiled_slots = 1;              // MSK_TILED_SLOTS: enumerate the film in 8x4 tiles (see slot_decode)
@@ -1364,6 +1367,7 @@ int Renderer::init(int sm_count) {
     impl_->spec_min = (uint32_t) env_u("MSK_SPEC_MIN", impl_->spec_min);
     impl_->shadow_static_bounces = (int) env_u("MSK_SHADOW_STATIC_BOUNCES", impl_->shadow_static_bounces);
     impl_->static_bounces = (int) env_u("MSK_STATIC_BOUNCES", impl_->static_bounces);
+    impl_->packet_camera = (int) env_u("MSK_PACKET_CAMERA", impl_->packet_camera);
     impl_->async_poll = (int) env_u("MSK_ASYNC_POLL", impl_->async_poll);
     impl_->tail_threshold = (uint32_t) env_u("MSK_TAIL_THRESHOLD", impl_->tail_threshold);
     impl_->poll_min_depth = (int) env_u("MSK_POLL_MIN_DEPTH", impl_->poll_min_depth);
@@ -1374,6 +1378,9 @@ int Renderer::init(int sm_count) {
     impl_->first_elide = (int) env_u("MSK_FIRST_ELIDE", impl_->first_elide);
     impl_->static_nodes = (uint32_t) env_u("MSK_STATIC_NODES", impl_->static_nodes);
     impl_->debug_bounces = (int) env_u("MSK_DEBUG_BOUNCES", 0);
+    // the packet kernel is not reached by the warm-up render of msk_gpu_init (a tiny scene): load it now, not in the first render
+    cudaFuncAttributes fa;
+    MSK_CUDA_CHECK(cudaFuncGetAttributes(&fa, k_intersect<false, true>));
     return MSK_OK;
 }
 
@@ -1591,9 +1598,13 @@ int Renderer::render(cudaStream_t stream0, const DScene &sc, const MskRenderDesc
             perm = pool.rs_vals[1];
         }
         const int tiny_scene = sc.nnodes <= im.static_nodes;
+        // 0: lockstep driver, 1: static warps of 32 consecutive rays, 2: static warps traversed as packets (camera rays)
+        const int isect_coherent = bounce == 0 && im.static_bounces > 0 && im.packet_camera && !tiny_scene && !perm ? 2 : ((int) bounce < im.static_bounces || tiny_scene);
         const int first = first_elide && bounce == 0;
-        if (tstats) MSK_STAGE(ST_INTERSECT, (k_intersect<true><<<pb, 128, 0, stream>>>(sc, pool, cur, (int) bounce < im.static_bounces || tiny_scene, perm)));
-        else MSK_STAGE(ST_INTERSECT, (k_intersect<false><<<pb, 128, 0, stream>>>(sc, pool, cur, (int) bounce < im.static_bounces || tiny_scene, perm)));
+        if (isect_coherent == 2 && tstats) MSK_STAGE(ST_INTERSECT, (k_intersect<true, true><<<pb, 128, 0, stream>>>(sc, pool, cur, isect_coherent, perm)));
+        else if (isect_coherent == 2) MSK_STAGE(ST_INTERSECT, (k_intersect<false, true><<<pb, 128, 0, stream>>>(sc, pool, cur, isect_coherent, perm)));
+        else if (tstats) MSK_STAGE(ST_INTERSECT, (k_intersect<true><<<pb, 128, 0, stream>>>(sc, pool, cur, isect_coherent, perm)));
+        else MSK_STAGE(ST_INTERSECT, (k_intersect<false><<<pb, 128, 0, stream>>>(sc, pool, cur, isect_coherent, perm)));
         // the AOV integrator shares the primary hit with the nested path tracer (the reference intersects twice)
         if (aov && bounce == 0) MSK_STAGE(ST_FILM, (k_aov_capture<<<(n + 255) / 256, 256, 0, stream>>>(sc, pool, bp, plan)));
         if (!MSK_SORT_IN_COMMIT) MSK_STAGE(ST_SORT, (k_sort<<<im.sm_count * 4, kSortThreads, 0, stream>>>(sc, pool, cur)));

@@ -462,6 +462,154 @@ __device__ __forceinline__ void traverse_one(const Accel &ac, Traversal &s, Trav
     }
 }
 
+// ---- Packet traversal of a coherent warp (camera rays: 32 samples of one pixel share the origin and almost the direction).
+// The warp walks the tree ONCE: node groups, triangle groups and the stack are warp-uniform (every lane keeps the same copy
+// in its own Traversal / stack slots), child j of a node is tested against the bounds of the whole packet by lane j & 7 --
+// interval arithmetic over the origins [olo, ohi] and reciprocal directions [rlo, rhi] of the 32 rays -- and every lane
+// tests every triangle of the leaves the packet enters with its own ray.  The per-ray node test (220 warp instructions per
+// visit, each lane finding what its neighbours find) becomes ~100, and nothing diverges.
+// Exactness: a child is entered whenever ANY ray of the packet could enter it (bounds are outward-rounded and padded), children
+// are visited in the same octant order as by a single ray (all rays of a packet share the octant, otherwise the caller falls
+// back to per-ray traversal), and a ray accepts exactly the triangle hits it would accept alone (tnear < t <= its own tfar),
+// in the same order: hits and films are bit-identical to per-ray traversal.
+struct PacketBounds {
+    // per axis: reciprocal directions [rlo, rhi] (one sign), the origin bound that minimises the entry parameter of the
+    // near plane (on) and the one that maximises the exit parameter of the far plane (of), sn = -1 / +1 for positive /
+    // negative directions (sign of the padding of the near side), opad = 1e-6 max |origin|, sg = -+ 1/64 cell
+    float rlo[3], rhi[3], on[3], of[3], sn[3], opad[3], sg[3];
+    float tmin, tmax;
+};
+__device__ __forceinline__ float warp_min(float v) {
+#pragma unroll
+    for (int m = 16; m > 0; m >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, m));
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int m = 16; m > 0; m >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, m));
+    return v;
+}
+__device__ __forceinline__ void packet_axis(PacketBounds &pb, int a, bool valid, float o, float r) {
+    const float inf = __int_as_float(0x7f800000);
+    const float olo = warp_min(valid ? o : inf), ohi = warp_max(valid ? o : -inf);
+    pb.rlo[a] = warp_min(valid ? r : inf); pb.rhi[a] = warp_max(valid ? r : -inf);
+    const bool neg = pb.rhi[a] < 0.f; // all rays of the packet share the sign (checked by the caller through the octant)
+    pb.on[a] = neg ? olo : ohi; pb.of[a] = neg ? ohi : olo;
+    pb.sn[a] = neg ? 1.f : -1.f;
+    pb.sg[a] = neg ? 0.015625f : -0.015625f;
+    pb.opad[a] = 1e-6f * fmaxf(fabsf(olo), fabsf(ohi));
+}
+// One axis of the packet-vs-child test.  near4 / far4: the two words holding the 8 quantised near / far planes of the node
+// (chosen by the packet's direction sign), j: this lane's child.  Returns a lower bound of the parameter at which any ray of
+// the packet can pass the child's near plane and an upper bound of the parameter at which any ray can still be inside
+// its far plane; planes are moved 1/64 cell outwards (the per-ray test pads by 1/256 cell and rounds within 1/512) and
+// plane - origin is padded by 8 ulp of the coordinates involved.
+__device__ __forceinline__ void packet_child_axis(const PacketBounds &pb, int a, uint32_t near_lo4, uint32_t near_hi4, uint32_t far_lo4,
+                                                  uint32_t far_hi4, uint32_t j, float p, float c, float &tn, float &tf) {
+    const float qn = (float) (__byte_perm(near_lo4, near_hi4, j) & 0xffu), qf = (float) (__byte_perm(far_lo4, far_hi4, j) & 0xffu);
+    const float pn = fmaf(qn, c, fmaf(c, pb.sg[a], p)), pf = fmaf(qf, c, fmaf(c, -pb.sg[a], p));
+    const float pad = fmaf(c, 256e-6f, fmaf(fabsf(p), 1e-6f, pb.opad[a]));
+    const float an = fmaf(pb.sn[a], pad, pn - pb.on[a]), af = fmaf(-pb.sn[a], pad, pf - pb.of[a]);
+    tn = fminf(an * pb.rlo[a], an * pb.rhi[a]);
+    tf = fmaxf(af * pb.rlo[a], af * pb.rhi[a]);
+}
+
+template <bool STATS, bool ORDERED>
+__device__ __forceinline__ void node_step_packet(const Accel &ac, Traversal &s, TravStack &stack, const PacketBounds &pb) {
+    const uint32_t hits  = s.ngroup.y;
+    const uint32_t imask = s.ngroup.y & 0xffu;
+    const uint32_t bit   = 31u - __clz(hits);
+    s.ngroup.y &= ~(1u << bit);
+    if (s.ngroup.y > 0x00ffffffu) stack.store(s.sp++, s.ngroup);
+    const uint32_t slot = ORDERED ? (bit - 24u) ^ s.octinv : bit - 24u;
+    const uint32_t rel  = __popc(imask & ~(0xffffffffu << slot));
+    const uint32_t node = s.ngroup.x + rel;
+    const float4 *np = ac.nodes + (size_t) node * kNodeFloat4s;
+    const float4 n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3), n4 = __ldg(np + 4);
+    if (STATS) s.cnt_nodes++;
+    const uint32_t e = __float_as_uint(n0.w);
+    const float cx = __uint_as_float((e & 0xffu) << 23), cy = __uint_as_float(((e >> 8) & 0xffu) << 23), cz = __uint_as_float(((e >> 16) & 0xffu) << 23);
+    const uint32_t j = threadIdx.x & 7u; // this lane's child slot (lanes 8..31 repeat the work of lanes 0..7)
+    const bool negx = !(s.octinv & 4u), negy = !(s.octinv & 2u), negz = !(s.octinv & 1u);
+    const uint32_t lox0 = __float_as_uint(n2.x), lox1 = __float_as_uint(n2.y), loy0 = __float_as_uint(n2.z), loy1 = __float_as_uint(n2.w),
+                   loz0 = __float_as_uint(n3.x), loz1 = __float_as_uint(n3.y), hix0 = __float_as_uint(n3.z), hix1 = __float_as_uint(n3.w),
+                   hiy0 = __float_as_uint(n4.x), hiy1 = __float_as_uint(n4.y), hiz0 = __float_as_uint(n4.z), hiz1 = __float_as_uint(n4.w);
+    float tnx, tfx, tny, tfy, tnz, tfz;
+    packet_child_axis(pb, 0, negx ? hix0 : lox0, negx ? hix1 : lox1, negx ? lox0 : hix0, negx ? lox1 : hix1, j, n0.x, cx, tnx, tfx);
+    packet_child_axis(pb, 1, negy ? hiy0 : loy0, negy ? hiy1 : loy1, negy ? loy0 : hiy0, negy ? loy1 : hiy1, j, n0.y, cy, tny, tfy);
+    packet_child_axis(pb, 2, negz ? hiz0 : loz0, negz ? hiz1 : loz1, negz ? loz0 : hiz0, negz ? loz1 : hiz1, j, n0.z, cz, tnz, tfz);
+    // some ray may enter the box only if the earliest possible entry is not after the latest possible exit (both moved
+    // outwards by 4e-6 relative for the rounding of the products; x * (1 +- e) keeps an infinity an infinity)
+    float tn = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, pb.tmin));
+    float tf = fminf(fminf(tfx, tfy), fminf(tfz, pb.tmax));
+    tn = fminf(tn * 0.999996f, tn * 1.000004f);
+    tf = fmaxf(tf * 0.999996f, tf * 1.000004f);
+    const uint32_t w = tn <= tf ? (1u << (24u + j)) | (7u << (3u * j)) : 0u;
+    uint32_t hitmask = __reduce_or_sync(0xffffffffu, w);
+    s.ngroup.x = __float_as_uint(n1.x);
+    s.tgroup.x = __float_as_uint(n1.y);
+    hitmask &= __float_as_uint(n1.z);
+    uint32_t inner;
+    if (!ORDERED) inner = hitmask >> 24;
+    else
+#if MSK_PERM_LUT
+    asm("ld.shared.u8 %0, [%1];" : "=r"(inner) : "r"(ac.lut + (s.octinv << 8) + (hitmask >> 24)));
+#else
+    inner = perm_byte(hitmask >> 24, s.octinv);
+#endif
+    s.ngroup.y = (inner << 24) | (e >> 24);
+    s.tgroup.y = hitmask & 0x00ffffffu;
+}
+
+// All 32 lanes call this converged; `valid` lanes hold a ray that begin() has set up.  Returns false -- having done nothing --
+// when the rays do not share one direction octant (the caller then traverses them one by one).
+template <bool ANY, bool STATS>
+__device__ __forceinline__ bool traverse_packet(const Accel &ac, Traversal &s, TravStack &stack, bool valid) {
+    const uint32_t vm = __ballot_sync(0xffffffffu, valid);
+    if (vm == 0u) return true;
+    const uint32_t oct0 = __shfl_sync(0xffffffffu, s.octinv, __ffs(vm) - 1);
+    if (__any_sync(0xffffffffu, valid && s.octinv != oct0)) return false;
+    const float inf = __int_as_float(0x7f800000);
+    PacketBounds pb;
+    packet_axis(pb, 0, valid, s.ox, s.idx);
+    packet_axis(pb, 1, valid, s.oy, s.idy);
+    packet_axis(pb, 2, valid, s.oz, s.idz);
+    pb.tmin = warp_min(valid ? s.tmin : inf);
+    pb.tmax = warp_max(valid ? s.tmax : -inf);
+    if (!valid) { s.octinv = oct0; s.reset(); } // warp-uniform control state in every lane
+    bool active = valid; // this lane still looks for a hit
+    for (;;) {
+        if (s.ngroup.y > 0x00ffffffu) node_step_packet<STATS, !(ANY && MSK_ANY_UNORDERED)>(ac, s, stack, pb);
+        else { s.tgroup = s.ngroup; s.ngroup = make_uint2(0u, 0u); }
+        bool hit_any = false;
+        while (s.tgroup.y) { // warp-uniform
+            const uint32_t k = 31u - __clz(s.tgroup.y);
+            s.tgroup.y &= ~(1u << k);
+            const float4 *tp = ac.tris + (size_t) (s.tgroup.x + k) * kTriFloat4s;
+            const float4 v0 = __ldg(tp), v1 = __ldg(tp + 1), v2 = __ldg(tp + 2);
+            float t, u, v;
+            if (active) {
+                if (STATS) s.cnt_tris++;
+                if (woop_intersect(s.wr, s.ox, s.oy, s.oz, v0, v1, v2, s.tmin, s.tmax, t, u, v)) {
+                    s.tmax = t;
+                    s.hit.t = t; s.hit.u = u; s.hit.v = v;
+                    s.hit.prim = __float_as_uint(v0.w); s.hit.geom = __float_as_uint(v1.w);
+                    s.found = true;
+                    hit_any = true;
+                    if (ANY) active = false;
+                }
+            }
+        }
+        if (ANY) { if (__ballot_sync(0xffffffffu, active) == 0u) break; }
+        else if (__any_sync(0xffffffffu, hit_any)) pb.tmax = warp_max(valid ? s.tmax : -inf); // closest hits only shrink the packet
+        if (s.ngroup.y <= 0x00ffffffu) {
+            if (s.sp == 0) break;
+            s.ngroup = stack.load(--s.sp);
+        }
+    }
+    return true;
+}
+
 // (used where rays are not queued: the per-path tail kernel)
 template <bool ANY, bool STATS>
 __device__ __forceinline__ bool traverse(const Accel &ac, TravStack &stack, float ox, float oy, float oz, float dx, float dy, float dz,
@@ -498,7 +646,7 @@ constexpr uint32_t kChunk = 128; // ray indices reserved per atomic
 #endif
 
 // Static assignment: the warp takes 32 consecutive rays and every lane runs its ray to completion.
-template <bool ANY, bool STATS, typename IO>
+template <bool ANY, bool STATS, bool PACKETS = false, typename IO>
 __device__ __forceinline__ void trace_queue_static(const Accel &ac, uint32_t n, uint32_t *cursor, IO &io, TravStack &stack) {
     Traversal s;
     const uint32_t lane = threadIdx.x & 31u;
@@ -526,15 +674,26 @@ __device__ __forceinline__ void trace_queue_static(const Accel &ac, uint32_t n, 
             io.load(q, ro, rd);
             s.tag = io.tag(ro);
             s.begin(ro, rd);
-            traverse_one<ANY, STATS>(ac, s, stack);
+        }
+        __syncwarp();
+        if (!PACKETS || !traverse_packet<ANY, STATS>(ac, s, stack, valid)) {
+            if (valid) traverse_one<ANY, STATS>(ac, s, stack);
         }
         __syncwarp();
         io.commit(valid, q, s);
     }
 }
 
-template <bool ANY, bool STATS, typename IO>
-__device__ __forceinline__ void trace_queue(const Accel &ac, uint2 *shared_stack, float4 *shared_pool, uint32_t n, uint32_t *cursor, IO &io, bool coherent) {
+// PACKETS: the kernel is compiled for packet traversal only (every warp of the queue is a packet: camera rays); its own
+// kernel, so that the register allocation of the lockstep loop is not disturbed by the packet code (and vice versa).
+template <bool ANY, bool STATS, bool PACKETS = false, typename IO>
+__device__ __forceinline__ void trace_queue(const Accel &ac, uint2 *shared_stack, float4 *shared_pool, uint32_t n, uint32_t *cursor, IO &io, int coherent) {
+    if (PACKETS) {
+        MSK_TRAV_LOCAL_STACK;
+        TravStack stack(msk_local_stack, shared_stack);
+        trace_queue_static<ANY, STATS, true>(ac, n, cursor, io, stack);
+        return;
+    }
     // Coherent queues (camera rays: neighbouring lanes follow the same nodes, so a static warp of 32 runs
     // converged and its node fetches coalesce) and queues too small to fill the machine (latency-bound: more,
     // shorter warps win) use the static assignment; incoherent bulk queues use the lockstep phases.
@@ -543,7 +702,7 @@ __device__ __forceinline__ void trace_queue(const Accel &ac, uint2 *shared_stack
 #elif MSK_TRAVERSAL_MODE == 1
     const bool use_static = false;
 #else
-    const bool use_static = coherent || n < gridDim.x * (blockDim.x / 32u) * 64u;
+    const bool use_static = coherent != 0 || n < gridDim.x * (blockDim.x / 32u) * 64u;
 #endif
     MSK_TRAV_LOCAL_STACK;
     TravStack stack(msk_local_stack, shared_stack);

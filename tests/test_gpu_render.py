@@ -381,6 +381,28 @@ def test_samples_per_warp_enumeration_is_bit_identical(monkeypatch, spp):
         np.testing.assert_array_equal(a, films[0][1])
 
 
+@pytest.mark.parametrize("spp", [5, 32])
+def test_camera_ray_packets_are_bit_identical(monkeypatch, spp):
+    """The camera-ray queue of a scene that is not tiny is traversed warp by warp as a packet (msk_traverse.cuh:
+    traverse_packet: one walk of the tree per warp, children tested against the bounds of the 32 rays, every lane tests the
+    triangles with its own ray); a ray accepts the same hits in the same order as alone, so film, AOVs and ray counters must
+    equal those of per-ray traversal -- 32 samples of one pixel per warp, and 5 samples (warps of 8x4 pixels)."""
+    sd = scenes.bunny(96, 64, n=20)
+    rd = capi.render_desc(spp=spp, max_depth=-1, rr_depth=4)
+    types = [capi.AOV_DEPTH, capi.AOV_UV, capi.AOV_INTEGRATOR_RGBA]
+    out = []
+    for packets in ["0", "1"]:
+        monkeypatch.setenv("MSK_PACKET_CAMERA", packets)
+        monkeypatch.setenv("MSK_STATIC_NODES", "0")  # no scene counts as tiny: the packet kernel runs whatever the mesh size
+        with capi.Context(0) as ctx, capi.Scene(ctx, sd) as sc:
+            film, st = sc.render(rd)
+            out.append((film, sc.render_aov(rd, types)[0], int(st.rays_closest), int(st.rays_shadow)))
+    assert out[0][0].any()
+    np.testing.assert_array_equal(out[1][0], out[0][0])
+    np.testing.assert_array_equal(out[1][1], out[0][1])
+    assert out[1][2:] == out[0][2:]
+
+
 @pytest.mark.parametrize("integrator,max_depth", [("path", -1), ("path", 3), ("volpath", -1)])
 def test_batches_in_flight_are_bit_identical(monkeypatch, integrator, max_depth):
     """Up to four batches are in flight at once, each on its own stream and path pool (Renderer::render); the film
